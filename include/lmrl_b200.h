@@ -1,0 +1,167 @@
+/* lmrl_b200.h — C ABI of the B200 batched-rollout engine for LMRL-Gym.
+ *
+ * The reference has no FFI on this path: the boundary is a pair of Python ABCs in LLM_RL/environment.py
+ * (BatchedTextEnv.reset/step :56-69, BatchedTextPolicy.act :120-123) driven by interact_environment (:154-207) and
+ * text_env_eval (:211-267).  Each entry point below names the reference interface it replaces; INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers + sizes, int status (0 = ok, negative = error; text via lmrl_last_error()).
+ *   - functions ending in _host take HOST pointers, do their own H2D/D2H copies on the engine stream and return
+ *     after the results are in the caller's buffers.  Functions ending in _dev take DEVICE pointers, enqueue on the
+ *     engine stream and return without synchronising.
+ *   - one engine = one GPU (one process per GPU; rollouts shard over engines with no collective).
+ *   - no exceptions / longjmp cross the ABI; the library never falls back to a CPU path.
+ */
+#ifndef LMRL_B200_H
+#define LMRL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmrl_engine lmrl_engine;
+
+#define LMRL_ENV_NONE   0
+#define LMRL_ENV_WORDLE 1
+#define LMRL_ENV_MAZE   2
+
+/* maze observation renderers (llm_rl_scripts/maze/env/env.py:15-81) */
+#define LMRL_MAZE_DESCRIBE_GOAL_WALLS      0  /* describe_observation               */
+#define LMRL_MAZE_DESCRIBE_GOAL_POS_WALLS  1  /* describe_observation_give_position */
+#define LMRL_MAZE_DESCRIBE_WALLS           2  /* describe_observation_only_walls    */
+
+typedef struct lmrl_config {
+    int32_t device;            /* CUDA ordinal */
+    int32_t max_envs;          /* B: concurrent environments on this GPU */
+    int32_t max_input_length;  /* BlockingStrategy max_length (LEFT pad / LEFT truncate), eval_bc_gpt2.py:100-104 */
+    int32_t max_new_tokens;    /* GenerationConfig.max_new_tokens, eval_bc_gpt2.py:90-95 */
+    int32_t max_turns;         /* upper bound on env steps per episode (6 Wordle, max_steps+1 Maze) */
+    int32_t reserved[3];
+} lmrl_config;
+
+typedef struct lmrl_gpt2_dims {
+    int32_t n_layer, n_head, d_model, d_ff, n_vocab /* rows of wte actually sampled from (unpadded) */, n_pos;
+    float ln_eps;
+    int32_t reserved;
+} lmrl_gpt2_dims;
+
+/* fp32 host weights in HF GPT-2 layout (Conv1D: [in, out]); converted to bf16 device layout at load */
+typedef struct lmrl_gpt2_weights {
+    const float* wte;            /* [n_vocab_rows, d]   (n_vocab_rows >= n_vocab; extra rows = padding ids) */
+    int32_t n_vocab_rows;
+    int32_t reserved;
+    const float* wpe;            /* [n_pos, d] */
+    const float* const* ln1_g;   /* [L] -> [d] */
+    const float* const* ln1_b;
+    const float* const* attn_w;  /* [L] -> [d, 3d]  c_attn.weight */
+    const float* const* attn_b;  /* [L] -> [3d] */
+    const float* const* proj_w;  /* [L] -> [d, d]   attn c_proj.weight */
+    const float* const* proj_b;
+    const float* const* ln2_g;
+    const float* const* ln2_b;
+    const float* const* fc_w;    /* [L] -> [d, d_ff] */
+    const float* const* fc_b;
+    const float* const* fc2_w;   /* [L] -> [d_ff, d] */
+    const float* const* fc2_b;
+    const float* lnf_g;
+    const float* lnf_b;
+} lmrl_gpt2_weights;
+
+typedef struct lmrl_sampling {
+    float temperature;     /* GenerationConfig.temperature (None -> 1.0) */
+    int32_t do_sample;     /* 0 = greedy argmax */
+    uint64_t seed;         /* base of the counter-based sampling RNG, keyed by (seed, episode seed, turn, token) */
+} lmrl_sampling;
+
+const char* lmrl_last_error(void);
+int lmrl_abi_version(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+int lmrl_create(const lmrl_config* cfg, lmrl_engine** out);
+int lmrl_destroy(lmrl_engine* e);
+int lmrl_sync(lmrl_engine* e);
+int64_t lmrl_device_bytes(lmrl_engine* e);          /* HBM held by this engine */
+void* lmrl_stream(lmrl_engine* e);                  /* cudaStream_t the engine launches on */
+
+/* ---- tables --------------------------------------------------------------------------------------------------- */
+/* replaces tokenizer.batch_decode / tokenizer.encode of value_rl_base/base_interface.py:112,126 for the closed set of
+ * env strings: id -> bytes for every id, plus single-token ids of 'c' / ' c' for ASCII c and of each single byte */
+int lmrl_load_tokenizer(lmrl_engine* e, const uint8_t* token_bytes, const int32_t* offsets, int32_t n_tokens,
+                        const int32_t* byte_tok /*[256]*/, const int32_t* tok_first /*[128]*/,
+                        const int32_t* tok_space /*[128]*/, int32_t space_id, int32_t newline_id,
+                        const int32_t* header_tokens, int32_t n_header);
+
+/* replaces Vocabulary.from_file + WordleEnvironment.__init__ (wordle/env/game.py:164-170, env.py:40-44) */
+int lmrl_load_wordle(lmrl_engine* e, const uint32_t* packed_words, int32_t n_words, int32_t require_words_in_vocab,
+                     float bad_word_reward);
+
+/* replaces setup_maze_env / MazeEnv.__init__ (maze/env/maze_utils.py:9-52, env.py:134-159).
+ * rewards = {at goal, unknown action, otherwise} (env.py:109-131).  obs_tokens/obs_len: token ids of the observation
+ * text for every cell y*W+x (only needed by the fused rollout; may be NULL for the text path). */
+int lmrl_load_maze(lmrl_engine* e, const uint8_t* grid, int32_t H, int32_t W, int32_t goal_y, int32_t goal_x,
+                   int32_t max_steps, int32_t last_k, const float* rewards3,
+                   const int32_t* obs_tokens, const int32_t* obs_len, int32_t obs_pitch);
+
+/* replaces load_params / GPT2PPOPolicy.set_params (ppo/gpt2/interface.py:548-549) */
+int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w);
+
+/* ---- environments, text path (BatchedTextEnv.reset / .step, environment.py:56-69) ------------------------------- */
+/* seeds: one uint64 per env (abs(seed) of random.Random(seed), wordle/env/env.py:53) */
+int lmrl_wordle_reset_host(lmrl_engine* e, const uint64_t* seeds, int32_t n);
+/* action text as UTF-8 bytes, row i at action_bytes + i*pitch; skip[i] != 0 leaves env i untouched (done rows).
+ * outputs per env: reward, done, valid (legal guess => the reference reward is a Python int), feedback codes
+ * (0 g, 1 y, 2 b, 255 none), size of the filtered vocabulary after the step */
+int lmrl_wordle_step_host(lmrl_engine* e, const uint8_t* action_bytes, const int32_t* action_len, int32_t pitch,
+                          const uint8_t* skip, int32_t n, float* reward, uint8_t* done, uint8_t* valid,
+                          uint8_t* feedback5, int32_t* n_filtered);
+/* opt_pos / opt_goal: [n][2] (y,x) or -1,-1 when the option is absent (maze/env/env.py:190-200); may be NULL */
+int lmrl_maze_reset_host(lmrl_engine* e, const uint64_t* seeds, const int32_t* opt_pos, const int32_t* opt_goal,
+                         int32_t n, int32_t* pos_out /*[n][2]*/, int32_t* goal_out /*[n][2]*/);
+int lmrl_maze_step_host(lmrl_engine* e, const uint8_t* action_bytes, const int32_t* action_len, int32_t pitch,
+                        const uint8_t* skip, int32_t n, float* reward, uint8_t* done, uint8_t* known,
+                        int32_t* outcome /*0 running, 1 Success, 2 Failure*/, int32_t* pos_out /*[n][2]*/);
+/* test hooks: raw env state */
+int lmrl_wordle_peek_host(lmrl_engine* e, int32_t n, uint32_t* know10, uint32_t* target, int32_t* n_actions);
+
+/* ---- policy, token path (BatchedTextPolicy.act -> generate_from_str, ppo/gpt2/interface.py:507-546) ------------ */
+/* prompts: LEFT-truncated to max_input_length by the callee; row i = tokens + i*pitch, n_tok[i] ids (0 = inactive row).
+ * out_tokens [n][max_new_tokens], out_len[n] (generation stops after the newline/EOS id or at max_new_tokens).
+ * episode_keys: one uint64 per row feeding the counter-based sampler (NULL = row index). */
+int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
+                       const uint64_t* episode_keys, int32_t turn, const lmrl_sampling* s,
+                       int32_t* out_tokens, int32_t* out_len);
+/* parity hook: teacher-forced forward of one ragged batch, fp32 logits of the LAST position of every row */
+int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
+                     float* logits /*[n][n_vocab]*/);
+
+/* ---- fused rollout (interact_environment's while-loop, environment.py:176-206, with no host round trip) -------- */
+typedef struct lmrl_rollout_out {      /* all HOST pointers for _host, DEVICE pointers for _dev; any may be NULL */
+    float* ep_return;       /* [n]  sum of rewards (fp32 accumulation in step order)            :238 */
+    int32_t* ep_length;     /* [n]  number of transitions                                        :240 */
+    uint8_t* ep_done;       /* [n]  done flag of the last transition                             :239 */
+    float* step_reward;     /* [n][max_turns] */
+    uint8_t* step_valid;    /* [n][max_turns] */
+    uint8_t* step_feedback; /* [n][max_turns][5]  (Wordle) */
+    int32_t* step_aux;      /* [n][max_turns]  Wordle: filtered size; Maze: cell index after the step */
+    int32_t* act_tokens;    /* [n][max_turns][max_new_tokens]  sampled ids per turn */
+    int32_t* act_len;       /* [n][max_turns] */
+} lmrl_rollout_out;
+
+int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, const int32_t* opt_pos, int32_t n,
+                      const lmrl_sampling* s, lmrl_rollout_out* out);
+int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, const int32_t* opt_pos_dev, int32_t n,
+                     const lmrl_sampling* s, lmrl_rollout_out* out_dev);
+/* scripted-action variant (env kernels only; actions come from the device RandomMixturePolicy equivalent,
+ * wordle/env/scripted_policies.py:114-126): used by the env microbenchmark */
+int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, int32_t n, float prob_smart,
+                                     uint64_t policy_seed, lmrl_rollout_out* out_dev);
+
+/* counters for bench.py: kernels launched by this engine since the last reset, and last GEMM timing hooks */
+int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMRL_B200_H */

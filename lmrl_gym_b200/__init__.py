@@ -1,0 +1,29 @@
+"""lmrl_gym_b200 — B200-native batched rollout engine behind LMRL-Gym's TextEnv / TextPolicy / text_env_eval surface.
+
+Host-side mirror of the reference interface (``environment``), device tables (``vocab``, ``tokenizer``) and the
+ctypes binding of the CUDA library.  Importing the package never touches the GPU; constructing an ``Engine``,
+env or policy loads ``csrc/liblmrl_b200.so`` and raises ``LmrlError`` if it is missing — there is no CPU fallback.
+"""
+from .environment import (  # noqa: F401
+    Text, TextHistory, TextTrajectory, TextTrajectoryChain, TextEnv, BatchedTextEnv, TextPolicy, BatchedTextPolicy,
+    TextEnvToBatchedTextEnv, BatchedTextEnvToTextEnv, TextPolicyToBatchedTextPolicy, BatchedTextPolicyToTextPolicy,
+    InteractionTransition, interact_environment, text_env_eval, text_history_to_str, summarize_episodes,
+)
+from .tokenizer import ByteTokenizer  # noqa: F401
+from ._lib import LmrlError  # noqa: F401
+
+
+def __getattr__(name):
+    if name == "Engine":
+        from .engine import Engine
+        return Engine
+    if name == "B200WordleEnv":
+        from .wordle import B200WordleEnv
+        return B200WordleEnv
+    if name == "B200MazeEnv":
+        from .maze import B200MazeEnv
+        return B200MazeEnv
+    if name in ("B200GPT2Policy", "GPT2Config", "init_gpt2_params"):
+        from . import gpt2
+        return getattr(gpt2, name)
+    raise AttributeError(name)

@@ -1,0 +1,108 @@
+"""ctypes binding of csrc/liblmrl_b200.so (the C ABI declared in include/lmrl_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, ``LmrlError`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "liblmrl_b200.so")
+
+
+class LmrlError(RuntimeError):
+    pass
+
+
+class lmrl_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_envs", C.c_int32), ("max_input_length", C.c_int32),
+                ("max_new_tokens", C.c_int32), ("max_turns", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class lmrl_gpt2_dims(C.Structure):
+    _fields_ = [("n_layer", C.c_int32), ("n_head", C.c_int32), ("d_model", C.c_int32), ("d_ff", C.c_int32),
+                ("n_vocab", C.c_int32), ("n_pos", C.c_int32), ("ln_eps", C.c_float), ("reserved", C.c_int32)]
+
+
+_PF = C.POINTER(C.c_float)
+_PPF = C.POINTER(_PF)
+
+
+class lmrl_gpt2_weights(C.Structure):
+    _fields_ = [("wte", _PF), ("n_vocab_rows", C.c_int32), ("reserved", C.c_int32), ("wpe", _PF),
+                ("ln1_g", _PPF), ("ln1_b", _PPF), ("attn_w", _PPF), ("attn_b", _PPF), ("proj_w", _PPF), ("proj_b", _PPF),
+                ("ln2_g", _PPF), ("ln2_b", _PPF), ("fc_w", _PPF), ("fc_b", _PPF), ("fc2_w", _PPF), ("fc2_b", _PPF),
+                ("lnf_g", _PF), ("lnf_b", _PF)]
+
+
+class lmrl_sampling(C.Structure):
+    _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64)]
+
+
+class lmrl_rollout_out(C.Structure):
+    _fields_ = [("ep_return", C.c_void_p), ("ep_length", C.c_void_p), ("ep_done", C.c_void_p),
+                ("step_reward", C.c_void_p), ("step_valid", C.c_void_p), ("step_feedback", C.c_void_p),
+                ("step_aux", C.c_void_p), ("act_tokens", C.c_void_p), ("act_len", C.c_void_p)]
+
+
+# every symbol include/lmrl_b200.h declares: name -> (restype, argtypes)
+_V = C.c_void_p
+_I = C.c_int32
+SYMBOLS = {
+    "lmrl_last_error": (C.c_char_p, []),
+    "lmrl_abi_version": (C.c_int, []),
+    "lmrl_create": (C.c_int, [C.POINTER(lmrl_config), C.POINTER(_V)]),
+    "lmrl_destroy": (C.c_int, [_V]),
+    "lmrl_sync": (C.c_int, [_V]),
+    "lmrl_device_bytes": (C.c_int64, [_V]),
+    "lmrl_stream": (_V, [_V]),
+    "lmrl_load_tokenizer": (C.c_int, [_V, _V, _V, _I, _V, _V, _V, _I, _I, _V, _I]),
+    "lmrl_load_wordle": (C.c_int, [_V, _V, _I, _I, C.c_float]),
+    "lmrl_load_maze": (C.c_int, [_V, _V, _I, _I, _I, _I, _I, _I, _V, _V, _V, _I]),
+    "lmrl_load_gpt2": (C.c_int, [_V, C.POINTER(lmrl_gpt2_dims), C.POINTER(lmrl_gpt2_weights)]),
+    "lmrl_wordle_reset_host": (C.c_int, [_V, _V, _I]),
+    "lmrl_wordle_step_host": (C.c_int, [_V, _V, _V, _I, _V, _I, _V, _V, _V, _V, _V]),
+    "lmrl_maze_reset_host": (C.c_int, [_V, _V, _V, _V, _I, _V, _V]),
+    "lmrl_maze_step_host": (C.c_int, [_V, _V, _V, _I, _V, _I, _V, _V, _V, _V, _V]),
+    "lmrl_wordle_peek_host": (C.c_int, [_V, _I, _V, _V, _V]),
+    "lmrl_generate_host": (C.c_int, [_V, _V, _V, _I, _I, _V, _I, C.POINTER(lmrl_sampling), _V, _V]),
+    "lmrl_logits_host": (C.c_int, [_V, _V, _V, _I, _I, _V]),
+    "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
+    "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
+    "lmrl_wordle_scripted_rollout_dev": (C.c_int, [_V, _V, _I, C.c_float, C.c_uint64, C.POINTER(lmrl_rollout_out)]),
+    "lmrl_launch_count": (C.c_int64, [_V, _I]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LmrlError(f"{LIB_PATH} is missing: build it with `python -m lmrl_gym_b200.build` "
+                        "(nvcc, sm_100a). There is no CPU fallback for the rollout engine.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = load().lmrl_last_error()
+        raise LmrlError(msg.decode("utf-8", "replace") if msg else f"lmrl call failed with status {status}")
+
+
+def ptr(a) -> int:
+    """numpy array -> void* (None -> NULL)."""
+    if a is None:
+        return None
+    return a.ctypes.data

@@ -1,0 +1,94 @@
+// engine.h — the opaque engine behind include/lmrl_b200.h: device allocations, tables, env state, stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/lmrl_b200.h"
+#include "env_kernels.cuh"
+
+namespace lmrl {
+
+extern thread_local std::string g_last_error;
+
+inline int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return -1;
+}
+
+#define LMRL_CUDA(x)                                                                                   \
+    do {                                                                                               \
+        cudaError_t err__ = (x);                                                                       \
+        if (err__ != cudaSuccess)                                                                      \
+            return ::lmrl::fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+#define LMRL_CHECK(cond, ...)                      \
+    do {                                           \
+        if (!(cond)) return ::lmrl::fail(__VA_ARGS__); \
+    } while (0)
+
+struct Gpt2Dev;   // gpt2_engine.cuh
+
+}  // namespace lmrl
+
+struct lmrl_engine {
+    lmrl_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    int64_t bytes = 0;
+    int64_t launches = 0;
+
+    // tables
+    bool has_tok = false, has_wordle = false, has_maze = false, has_gpt2 = false;
+    lmrl::TokenizerDev tok{};
+    int32_t* d_byte_tok = nullptr; int32_t* d_tok_first = nullptr; int32_t* d_tok_space = nullptr;
+    std::vector<int32_t> header_tokens;
+    int32_t* d_header = nullptr;
+    int max_token_bytes = 0;
+    lmrl::WordleDev wordle{};
+    lmrl::MazeDev maze{};
+    int32_t* d_maze_obs_tokens = nullptr; int32_t* d_maze_obs_len = nullptr; int maze_obs_pitch = 0;
+
+    // step I/O staging (device)
+    uint8_t* d_act_bytes = nullptr; int32_t* d_act_len = nullptr; int act_pitch = 0;
+    uint8_t* d_skip = nullptr;
+    uint64_t* d_seeds = nullptr;
+    int32_t* d_opt_pos = nullptr; int32_t* d_opt_goal = nullptr;
+    lmrl::StepOut step{};
+    int32_t* d_action_id = nullptr;
+
+    lmrl::Gpt2Dev* gpt2 = nullptr;
+
+    template <typename T>
+    int alloc(T** p, size_t count) {
+        void* q = nullptr;
+        const size_t nbytes = (count ? count : 1) * sizeof(T);
+        cudaError_t err = cudaMalloc(&q, nbytes);
+        if (err != cudaSuccess) return lmrl::fail("cudaMalloc(%zu bytes) failed: %s", nbytes, cudaGetErrorString(err));
+        cudaMemsetAsync(q, 0, nbytes, stream);
+        allocs.push_back(q);
+        bytes += (int64_t)nbytes;
+        *p = reinterpret_cast<T*>(q);
+        return 0;
+    }
+    template <typename T>
+    int upload(T** p, const T* host, size_t count) {
+        if (alloc(p, count)) return -1;
+        if (count) {
+            cudaError_t err = cudaMemcpyAsync(*p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream);
+            if (err != cudaSuccess) return lmrl::fail("H2D copy failed: %s", cudaGetErrorString(err));
+            cudaStreamSynchronize(stream);   // host buffer may be transient
+        }
+        return 0;
+    }
+};

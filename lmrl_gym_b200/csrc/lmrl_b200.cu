@@ -1,0 +1,11 @@
+// lmrl_b200.cu — single translation unit of liblmrl_b200.so (sm_100a).
+//   engine.h          opaque engine, allocation bookkeeping
+//   env_core.h        per-env integer logic (host+device)
+//   env_kernels.cuh   Wordle / Maze kernels
+//   lmrl_api.inl      C ABI: lifecycle, tables, text-path envs
+//   gpt2_engine.inl   C ABI: GPT-2 decoder, sampler, fused rollout
+#include <stdarg.h>
+#include <algorithm>
+#include "engine.h"
+#include "gpt2_engine.inl"
+#include "lmrl_api.inl"

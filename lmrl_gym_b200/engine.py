@@ -1,0 +1,67 @@
+"""Engine: one GPU's worth of device-resident rollout state behind the C ABI (include/lmrl_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import LmrlError, check, ptr
+from .tokenizer import ByteTokenizer
+
+ENV_WORDLE, ENV_MAZE = 1, 2
+
+
+class Engine:
+    """Owns an ``lmrl_engine`` handle.  Envs and policies bound to the same Engine can be fused by
+    ``text_env_eval`` / ``interact_environment`` (lmrl_gym_b200/environment.py)."""
+
+    def __init__(self, max_envs: int, device: int = 0, max_input_length: int = 256, max_new_tokens: int = 6,
+                 max_turns: int = 6, tokenizer: Optional[ByteTokenizer] = None):
+        self.lib = _lib.load()
+        self.cfg = _lib.lmrl_config(device=device, max_envs=max_envs, max_input_length=max_input_length,
+                                    max_new_tokens=max_new_tokens, max_turns=max_turns)
+        self.handle = C.c_void_p()
+        check(self.lib.lmrl_create(C.byref(self.cfg), C.byref(self.handle)))
+        self.max_envs = max_envs
+        self.device = device
+        self.max_input_length = max_input_length
+        self.max_new_tokens = max_new_tokens
+        self.max_turns = max_turns
+        self.tokenizer: Optional[ByteTokenizer] = None
+        self.env_kind = 0
+        if tokenizer is not None:
+            self.load_tokenizer(tokenizer)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.lmrl_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables ----
+    def load_tokenizer(self, tok: ByteTokenizer, header: str = "Wordle:\n"):
+        t = tok.device_tables()
+        self._tok_tables = t
+        hdr = np.asarray(tok.encode(header), dtype=np.int32)
+        check(self.lib.lmrl_load_tokenizer(self.handle, ptr(t["token_bytes"]), ptr(t["offsets"]), len(tok),
+                                           ptr(t["byte_tok"]), ptr(t["tok_first"]), ptr(t["tok_space"]),
+                                           tok.encode("a b")[1] if False else int(t["byte_tok"][0x20]), tok.newline_id(),
+                                           ptr(hdr), len(hdr)))
+        self.tokenizer = tok
+
+    def sync(self):
+        check(self.lib.lmrl_sync(self.handle))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.lmrl_device_bytes(self.handle))
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.lmrl_launch_count(self.handle, 1 if reset else 0))

@@ -1,0 +1,133 @@
+"""The per-env device logic (csrc/env_core.h), compiled for the host, against Python itself and the goldens."""
+import ctypes as C
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from lmrl_gym_b200 import build
+from lmrl_gym_b200.tokenizer import ByteTokenizer
+from lmrl_gym_b200.vocab import load_packed, unpack_word
+from lmrl_gym_b200.maze import maze_grid, GOALS, REWARDS
+
+
+@pytest.fixture(scope="module")
+def hc():
+    return C.CDLL(build.build_host())
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def test_mt_matches_cpython(hc):
+    for seed in [0, 1, 2**32 - 1, 2**32, 2**64 - 1, 987654321987654321]:
+        out = np.zeros(1400, np.uint32)
+        hc.hc_mt_u32_stream(C.c_uint64(seed), 1400, _p(out))
+        r = random.Random(seed)
+        assert out.tolist() == [r.getrandbits(32) for _ in range(1400)]
+        ns = np.asarray([1, 2, 3, 24, 25, 2315, 12972, 1, 7, 2**31 + 5], np.uint32)
+        got = np.zeros(len(ns), np.uint32)
+        hc.hc_mt_randbelow_stream(C.c_uint64(seed), _p(ns), len(ns), _p(got))
+        r = random.Random(seed)
+        assert got.tolist() == [r.choice(range(int(n))) for n in ns]
+
+
+def test_utf8_replace_matches_python(hc):
+    rng = random.Random(5)
+    interesting = [0x00, 0x20, 0x41, 0x7F, 0x80, 0xBF, 0xC0, 0xC1, 0xC2, 0xDF, 0xE0, 0xE1, 0xEC, 0xED, 0xEE, 0xEF, 0xF0, 0xF1,
+                   0xF3, 0xF4, 0xF5, 0xFF, 0x90, 0x8F, 0xA0, 0x9F]
+    for trial in range(4000):
+        n = rng.randrange(0, 12)
+        b = bytes(rng.choice(interesting) if rng.random() < 0.8 else rng.randrange(256) for _ in range(n))
+        want = [ord(c) for c in b.decode("utf-8", errors="replace")]
+        buf = np.frombuffer(b, np.uint8).copy() if n else np.zeros(1, np.uint8)
+        out = np.zeros(64, np.uint32)
+        m = hc.hc_utf8_decode(_p(buf), n, _p(out), 64)
+        assert out[:m].tolist() == want, b
+
+
+def test_normalise_matches_python(hc):
+    rng = random.Random(6)
+    alphabet = list("abc xyz\n\t\r\x0b\x0c\x1c\x1d\x1e\x1f\x85\xa0    ​    　﻿Zé")
+    for trial in range(3000):
+        s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 14)))
+        want = [ord(c) for c in s.strip().replace(" ", "")]
+        b = s.encode("utf-8")
+        buf = np.frombuffer(b, np.uint8).copy() if b else np.zeros(1, np.uint8)
+        out = np.zeros(64, np.uint32)
+        m = hc.hc_normalise(_p(buf), len(b), _p(out), 64)
+        assert out[:m].tolist() == want, repr(s)
+
+
+def test_render_line_matches_tokenizer(hc):
+    tok = ByteTokenizer.synthetic()
+    t = tok.device_tables()
+    rng = random.Random(7)
+    alphabet = list("abcdefghijklmnopqrstuvwxyzABC019-_'!? \t\n\x1dé �")
+    space_id, nl = int(t["byte_tok"][0x20]), tok.newline_id()
+    for trial in range(2000):
+        s = "".join(rng.choice(alphabet) for _ in range(rng.randrange(0, 10)))
+        norm = s.strip().replace(" ", "")
+        line = " ".join(norm) + "\n"
+        want = tok.encode(line)
+        b = s.encode("utf-8")
+        buf = np.frombuffer(b, np.uint8).copy() if b else np.zeros(1, np.uint8)
+        out = np.zeros(128, np.int32)
+        m = hc.hc_render_action_line(_p(buf), len(b), _p(t["tok_first"]), _p(t["tok_space"]), _p(t["byte_tok"]), space_id, nl,
+                                     _p(out), 128)
+        assert out[:m].tolist() == want, repr(s)
+        assert tok.decode(want) == line
+
+
+def test_wordle_core_matches_reference_goldens(hc, golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "wordle_cases.json")))
+    sym = {"g": 0, "y": 1, "b": 2}
+    for case in cases:
+        words = load_packed(case["vocab_file"])
+        acts = [a.encode("utf-8") for a in case["actions"]]
+        blob = b"".join(acts)
+        buf = np.frombuffer(blob, np.uint8).copy() if blob else np.zeros(1, np.uint8)
+        lens = np.asarray([len(a) for a in acts], np.int32)
+        n = len(acts)
+        reward = np.zeros(n, np.float32); done = np.zeros(n, np.uint8); valid = np.zeros(n, np.uint8)
+        fb = np.zeros((n, 5), np.uint8); nf = np.zeros(n, np.int32); tg = np.zeros(n, np.uint32)
+        hc.hc_wordle_episode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6
+        steps = hc.hc_wordle_episode(_p(words), len(words), int(case["require_words_in_vocab"]), case["bad_word_reward"],
+                                     abs(case["seed"]), _p(buf), _p(lens), n, _p(reward), _p(done), _p(valid), _p(fb), _p(nf), _p(tg))
+        assert steps == len(case["steps"])
+        for k, st in enumerate(case["steps"]):
+            assert float(reward[k]) == float(st["reward"])
+            assert bool(done[k]) == st["done"]
+            assert int(nf[k]) == st["n_filtered"]
+            last = st["obs"][-1][0]
+            want_fb = [sym[c] for c in last.strip().split(" ")] if last != "\n" else []
+            assert [int(c) for c in fb[k] if c < 3] == want_fb
+            assert bool(valid[k]) == (last != "\n")
+
+
+def test_maze_core_matches_reference_goldens(hc, golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "maze_cases.json")))
+    hc.hc_maze_episode.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                                 C.c_int] + [C.c_void_p] * 5
+    for case in cases:
+        grid = maze_grid(case["maze_name"])
+        H, W = grid.shape
+        gy, gx = GOALS[case["maze_name"]]
+        rw = np.asarray(REWARDS[case["reward_function"] or "standard_reward"], np.float32)
+        acts = [a.encode() for a in case["actions"]]
+        blob = b"".join(acts)
+        buf = np.frombuffer(blob, np.uint8).copy() if blob else np.zeros(1, np.uint8)
+        lens = np.asarray([len(a) for a in acts], np.int32)
+        n = len(acts)
+        start = np.zeros(2, np.int32); reward = np.zeros(n, np.float32); done = np.zeros(n, np.uint8)
+        outcome = np.zeros(n, np.int32); pos = np.zeros((n, 2), np.int32)
+        oy, ox = (case["options"]["init_position"] if case["options"] else (-1, -1))
+        steps = hc.hc_maze_episode(_p(np.ascontiguousarray(grid)), H, W, gy, gx, case["max_steps"], _p(rw), abs(case["seed"]), oy, ox,
+                                   _p(buf), _p(lens), n, _p(start), _p(reward), _p(done), _p(outcome), _p(pos))
+        assert steps == len(case["steps"])
+        for k, st in enumerate(case["steps"]):
+            assert float(reward[k]) == st["reward"] and bool(done[k]) == st["done"]
+            assert pos[k].tolist() == st["position"]

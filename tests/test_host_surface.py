@@ -1,0 +1,127 @@
+"""Host logic: tokenizer, vocab tables, the generic rollout loop and summary, and the C-ABI export list."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+
+from lmrl_gym_b200 import _lib, build
+from lmrl_gym_b200.environment import (BatchedTextEnv, BatchedTextPolicy, Text, TextEnv, TextPolicy, interact_environment,
+                                       text_env_eval)
+from lmrl_gym_b200.tokenizer import ByteTokenizer, gpt2_byte_order
+from lmrl_gym_b200.vocab import load_packed, load_vocab_words, pack_words
+from oracle.mt19937 import seed_stream
+from oracle.wordle import ReformatWordleOracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_vocab_tables():
+    assert len(load_packed("wordle_official.txt")) == 2315
+    assert len(load_packed("wordle_official_200")) == 236
+    words = load_vocab_words("tweet_words.txt")
+    assert len(words) == 40 and all(len(w) == 5 and w.islower() for w in words)
+    assert (pack_words(words) == load_packed("tweet_words")).all()
+
+
+def test_synthetic_tokenizer_shape_and_roundtrip():
+    tok = ByteTokenizer.synthetic()
+    assert len(tok) == 50258 and tok.newline_id() == 198 and tok.encode(" ")[0] == 220
+    order = gpt2_byte_order()
+    assert order[0] == ord("!") and order[198] == 10 and order[220] == 32 and sorted(order) == list(range(256))
+    for s in ["Wordle:\n", "c r a n e\n", "g y b b b\n", "\n", "move left\n",
+              "The goal is at position 8, 6. Your current position is at position 1 0, 3. There are walls to your left, below you.\n",
+              "ééé   x", "Wordle:\n\n\nc r a n e\n"]:
+        ids = tok.encode(s)
+        assert tok.decode(ids) == s
+    assert tok.encode("c r a n e\n") == [tok.encode("c")[0]] + [tok.encode("x " + c)[1] for c in "rane"] + [198]
+    assert len(tok.encode("Wordle:\n")) == 3
+    # per-item and joined tokenisation agree on env text (the deviation documented in DESIGN.md cannot trigger)
+    parts = ["Wordle:\n", "\n", "\n", "s l a t e\n", "b b y g b\n"]
+    assert sum((tok.encode(p) for p in parts), []) == tok.encode("".join(parts))
+
+
+def test_bpe_merge_path():
+    # a toy merges table exercises the real-BPE branch used for genuine GPT-2 files
+    base = [bytes([b]) for b in gpt2_byte_order()]
+    toks = base + [b"ab", b"abc", b" a"]
+    tok = ByteTokenizer(toks + [b"", b""], merges=[(b"a", b"b"), (b"ab", b"c"), (b" ", b"a")], special_ids=(len(toks), len(toks) + 1))
+    assert tok.encode("abc") == [257]
+    assert tok.encode("abab") == [256, 256]
+    assert tok.decode(tok.encode("xabc ab")) == "xabc ab"
+
+
+class _OracleEnv(TextEnv):
+    def __init__(self, words):
+        self.o = ReformatWordleOracle(words)
+
+    def reset(self, seed=None, options=None):
+        return tuple(Text(t, a) for t, a in self.o.reset(seed))
+
+    def step(self, h):
+        hist, r, d = self.o.step(tuple((t.text, t.is_action) for t in h))
+        return tuple(Text(t, a) for t, a in hist), r, d
+
+
+def test_generic_loop_reproduces_reference_eval(golden_dir):
+    gold = json.load(open(os.path.join(golden_dir, "eval_loop.json")))
+    words = gold["words"]
+
+    class Cyclic(BatchedTextPolicy):
+        def __init__(self):
+            self.calls = []
+
+        def act(self, text_history, done=None):
+            self.calls.append((len(text_history), list(done)))
+            out = []
+            for h, d in zip(text_history, done):
+                if d:
+                    out.append(None)
+                    continue
+                k = (len(h) * 7 + sum(len(t.text) for t in h)) % len(words)
+                out.append(h + (Text(" ".join(words[k]) + "\n", True),))
+            return out
+
+    pol = Cyclic()
+    inter, summary = text_env_eval(_OracleEnv(load_vocab_words("wordle_official.txt")), pol, n_rollouts=gold["n_rollouts"],
+                                   seed_generator=seed_stream(gold["seed"]), bsize=gold["bsize"], verbose=False)
+    assert all(n == gold["bsize"] for n, _ in pol.calls)           # last batch is padded with done rows
+    assert pol.calls[-1][1][-2:] == [True, True]
+    for ep, g in zip(inter, gold["episodes"]):
+        assert float(sum(t.reward for t in ep)) == g["ret"] and len(ep) == g["length"] and ep[-1].done == g["done"]
+        assert [[t.text, t.is_action] for t in ep[-1].post_transition_history] == g["final"]
+    for k in ("reward", "done", "length"):
+        for s in ("mean", "std", "min", "max"):
+            assert float(summary[k][s]) == gold["summary"][k][s]
+    assert summary["reward"]["mean"].dtype == np.float32
+
+
+def test_finished_rows_contribute_one_transition():
+    class Env(BatchedTextEnv):
+        def reset(self, seed=None, options=None):
+            self.t = 0
+            return [(Text("o", False),), (Text("o", False),)]
+
+        def step(self, text_history, done=None):
+            self.t += 1
+            return [None if d else (h + (Text("x", False),), 1.0, self.t >= need)
+                    for h, d, need in zip(text_history, done, (1, 3))]
+
+    class Pol(BatchedTextPolicy):
+        def act(self, text_history, done=None):
+            return [None if d else h + (Text("a", True),) for h, d in zip(text_history, done)]
+
+    inter = interact_environment(Env(), Pol(), bsize=2)
+    assert [len(ep) for ep in inter] == [1, 3]
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lmrl_b200.h")).read()
+    declared = set(re.findall(r"\b(lmrl_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = C.CDLL(build.build_cuda())       # loads without a GPU; no compute call is made here
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.lmrl_abi_version.restype = C.c_int
+    assert lib.lmrl_abi_version() == 1
