@@ -1,2 +1,429 @@
-// placeholder until the decoder lands
-void lmrl_gpt2_free(lmrl_engine*) {}
+// gpt2_engine.inl — GPT-2 KV-cache decoder, fused LM-head sampler and the fused rollout loop (C ABI part 2).
+//
+// Reference path being replaced: GPT2PPOPolicy.act -> generate_from_str -> pjit _generate ->
+// HF FlaxGenerationMixin._sample (prefill + lax.while_loop of single-token forwards) around the env's Python step.
+// Here one host thread enqueues, per turn: [row build -> embed -> L x (LN, QKV GEMM + KV append, attention,
+// proj GEMM + residual, LN, FC GEMM + GeLU, FC2 GEMM + residual) -> final LN of the sampled rows -> LM-head GEMM
+// with fused Gumbel arg-max] x max_new_tokens, then the env step kernel.  Row counts and done masks stay on the
+// device; nothing is copied to the host until the rollout is over.
+#include "gpt2_kernels.cuh"
+
+namespace lmrl {
+
+struct LayerDev {
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    __nv_bfloat16 *w_qkv, *w_proj, *w_fc, *w_fc2;      // [N][K] bf16
+    float *b_qkv, *b_proj, *b_fc, *b_fc2;
+};
+
+struct Gpt2Dev {
+    lmrl_gpt2_dims dims{};
+    int v_pad = 0;            // LM-head rows padded to a multiple of 128
+    int t_cap = 0;            // KV positions per env
+    int m_cap = 0;            // row capacity of the activation buffers
+    int stream_cap = 0;
+    __nv_bfloat16 *wte = nullptr, *wpe = nullptr;
+    float *lnf_g = nullptr, *lnf_b = nullptr;
+    std::vector<LayerDev> layers;
+    __nv_bfloat16* kv = nullptr;      // [L][2][B][H][t_cap][64]
+    size_t kv_layer_stride = 0;       // elements between layers (covers K and V)
+    // activations
+    float* x = nullptr;
+    __nv_bfloat16 *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *xl = nullptr;
+    RowsDev rows{};
+    GenDev gen{};
+    StreamDev stream{};
+    uint64_t* row_key = nullptr;
+    unsigned long long* best = nullptr;
+    uint64_t* episode_key = nullptr;  // [B]
+    float* logits = nullptr;          // parity hook buffer, allocated on first use
+    size_t logits_rows = 0;
+    // rollout logs (device)
+    float* ep_return = nullptr; int32_t* ep_length = nullptr; uint8_t* ep_done = nullptr;
+    float* step_reward = nullptr; uint8_t* step_valid = nullptr; uint8_t* step_fb = nullptr; int32_t* step_aux = nullptr;
+    int32_t* act_tokens = nullptr; int32_t* act_len = nullptr;
+    int sm_count = 148;
+    std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
+};
+
+__global__ void transpose_to_bf16_kernel(const float* __restrict__ src, int K, int N, __nv_bfloat16* __restrict__ dst) {
+    // src [K][N] fp32 (HF Conv1D layout) -> dst [N][K] bf16
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (k0 + i < K && n0 + threadIdx.x < N) tile[i][threadIdx.x] = src[(size_t)(k0 + i) * N + n0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (n0 + i < N && k0 + threadIdx.x < K) dst[(size_t)(n0 + i) * K + k0 + threadIdx.x] = __float2bfloat16(tile[threadIdx.x][i]);
+}
+
+__global__ void convert_to_bf16_kernel(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
+}
+
+__global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, int n_header, StreamDev st, Gpt2Dev* /*unused*/,
+                                   const uint64_t* __restrict__ seeds, uint64_t* __restrict__ episode_key, float* ep_return,
+                                   int32_t* ep_length, uint8_t* ep_done) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (int i = 0; i < n_header; ++i) st.tokens[(size_t)e * st.cap + i] = header[i];
+    st.len[e] = n_header;
+    st.kv_len[e] = 0;
+    episode_key[e] = seeds[e];
+    ep_return[e] = 0.f; ep_length[e] = 0; ep_done[e] = 0;
+}
+
+// after the env step: append this turn's results to the per-episode logs
+__global__ void log_turn_kernel(int n, int max_turns, GenDev gen, const int32_t* __restrict__ n_actions, StepOut step,
+                                float* ep_return, int32_t* ep_length, uint8_t* ep_done, float* step_reward, uint8_t* step_valid,
+                                uint8_t* step_fb, int32_t* step_aux, int32_t* act_tokens, int32_t* act_len) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int glen = gen.len[e];
+    if (glen <= 0) return;                      // env did not act this turn (already done)
+    const int t = n_actions[e] - 1;
+    if (t < 0 || t >= max_turns) return;
+    const size_t o = (size_t)e * max_turns + t;
+    step_reward[o] = step.reward[e];
+    step_valid[o] = step.valid[e];
+    step_aux[o] = step.aux[e];
+    for (int i = 0; i < 5; ++i) step_fb[o * 5 + i] = step.fb[e * 5 + i];
+    for (int k = 0; k < gen.max_new; ++k) act_tokens[o * gen.max_new + k] = k < glen ? gen.tok[e * gen.max_new + k] : -1;
+    act_len[o] = glen;
+    ep_return[e] += step.reward[e];
+    ep_length[e] = t + 1;
+    ep_done[e] = step.done[e];
+}
+
+template <int EPI>
+static int launch_gemm(lmrl_engine* e, const GemmArgs& g) {
+    static bool configured = false;
+    if (!configured) {
+        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_mma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        configured = true;
+    }
+    gemm_bf16_mma_kernel<EPI><<<e->gpt2->sm_count * 2, GEMM_THREADS, GEMM_SMEM_BYTES, e->stream>>>(g);
+    e->launches++;
+    return 0;
+}
+
+// One forward pass over the current ragged batch + sampling of one token per contributing env.
+// mode 0 = prefill of un-cached stream tokens, mode 1 = single-token decode.
+static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t* done, const int32_t* turn_of_env, int turn_const,
+                              const lmrl_sampling& s, float* logits_out) {
+    Gpt2Dev& G = *e->gpt2;
+    const lmrl_gpt2_dims& D = G.dims;
+    cudaStream_t st = e->stream;
+    const int ew_blocks = G.sm_count * 8;
+    build_rows_kernel<<<1, 1024, 0, st>>>(mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
+    e->launches++;
+    if (mode == 0) {
+        fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
+        e->launches++;
+    }
+    embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x);
+    e->launches++;
+    const size_t att_smem = (size_t)G.t_cap * (ATT_KPITCH * 2 + 64 * 2 + 4 * (ATT_THREADS / 32));
+    for (int l = 0; l < D.n_layer; ++l) {
+        const LayerDev& L = G.layers[l];
+        layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn);
+        e->launches++;
+        GemmArgs a{};
+        a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
+        a.out = G.q; a.kcache = G.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
+        a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+        if (launch_gemm<EPI_QKV>(e, a)) return -1;
+        attention_kernel<<<dim3(D.n_head, n_env), ATT_THREADS, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                 0.125f, G.att);
+        e->launches++;
+        GemmArgs p{};
+        p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
+        if (launch_gemm<EPI_RESID>(e, p)) return -1;
+        layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn);
+        e->launches++;
+        GemmArgs f{};
+        f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
+        if (launch_gemm<EPI_GELU>(e, f)) return -1;
+        GemmArgs f2{};
+        f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
+        if (launch_gemm<EPI_RESID>(e, f2)) return -1;
+    }
+    layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, G.lnf_g, G.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last, G.xl);
+    e->launches++;
+    prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best);
+    e->launches++;
+    GemmArgs h{};
+    h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
+    h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
+    h.n_vocab = D.n_vocab; h.logits_out = logits_out;
+    if (launch_gemm<EPI_SAMPLE>(e, h)) return -1;
+    finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best);
+    e->launches++;
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int gpt2_alloc_state(lmrl_engine* e) {
+    Gpt2Dev& G = *e->gpt2;
+    const lmrl_gpt2_dims& D = G.dims;
+    const int B = e->cfg.max_envs;
+    const int max_in = e->cfg.max_input_length, max_new = e->cfg.max_new_tokens, T = e->cfg.max_turns;
+    G.t_cap = (max_in + max_new + 7) / 8 * 8;
+    G.stream_cap = max_in + MAX_LINE_TOKENS;
+    G.m_cap = ((size_t)B * max_in + 127) / 128 * 128;
+    G.kv_layer_stride = (size_t)2 * B * D.d_model * G.t_cap;
+    if (e->alloc(&G.kv, G.kv_layer_stride * D.n_layer)) return -1;
+    if (e->alloc(&G.x, (size_t)G.m_cap * D.d_model) || e->alloc(&G.xn, (size_t)G.m_cap * D.d_model) ||
+        e->alloc(&G.q, (size_t)G.m_cap * D.d_model) || e->alloc(&G.att, (size_t)G.m_cap * D.d_model) ||
+        e->alloc(&G.h, (size_t)G.m_cap * D.d_ff) || e->alloc(&G.xl, (size_t)((B + 127) / 128 * 128) * D.d_model))
+        return -1;
+    if (e->alloc(&G.rows.M, 1) || e->alloc(&G.rows.n_slots, 1) || e->alloc(&G.rows.row_env, G.m_cap) || e->alloc(&G.rows.row_pos, G.m_cap) ||
+        e->alloc(&G.rows.row_tok, G.m_cap) || e->alloc(&G.rows.slot_env, B) || e->alloc(&G.rows.slot_row0, B) ||
+        e->alloc(&G.rows.slot_nrow, B) || e->alloc(&G.rows.slot_last, B))
+        return -1;
+    if (e->alloc(&G.gen.tok, (size_t)B * max_new) || e->alloc(&G.gen.len, B) || e->alloc(&G.gen.active, B) || e->alloc(&G.gen.cur, B)) return -1;
+    G.gen.max_new = max_new;
+    G.gen.eos_id = e->tok.t.newline_id;
+    if (e->alloc(&G.stream.tokens, (size_t)B * G.stream_cap) || e->alloc(&G.stream.len, B) || e->alloc(&G.stream.kv_len, B)) return -1;
+    G.stream.cap = G.stream_cap; G.stream.max_input = max_in;
+    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.episode_key, B)) return -1;
+    if (e->alloc(&G.ep_return, B) || e->alloc(&G.ep_length, B) || e->alloc(&G.ep_done, B) || e->alloc(&G.step_reward, (size_t)B * T) ||
+        e->alloc(&G.step_valid, (size_t)B * T) || e->alloc(&G.step_fb, (size_t)B * T * 5) || e->alloc(&G.step_aux, (size_t)B * T) ||
+        e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
+        return -1;
+    const size_t att_smem = (size_t)G.t_cap * (ATT_KPITCH * 2 + 64 * 2 + 4 * (ATT_THREADS / 32));
+    LMRL_CHECK(att_smem <= 227 * 1024, "max_input_length + max_new_tokens = %d positions do not fit the attention kernel's shared memory", G.t_cap);
+    LMRL_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    return 0;
+}
+
+}  // namespace lmrl
+
+using namespace lmrl;
+
+void lmrl_gpt2_free(lmrl_engine* e) {
+    if (!e || !e->gpt2) return;
+    for (void* p : e->gpt2->owned) cudaFree(p);
+    delete e->gpt2;
+    e->gpt2 = nullptr;
+}
+
+extern "C" {
+
+int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) {
+    LMRL_CHECK(e && dims && w, "lmrl_load_gpt2: null argument");
+    LMRL_CHECK(e->has_tok, "lmrl_load_gpt2: load the tokenizer tables first (EOS id, header)");
+    LMRL_CHECK(dims->d_model % 128 == 0 && dims->d_model <= 1024 && dims->d_model == dims->n_head * 64 && dims->d_ff % 128 == 0,
+               "lmrl_load_gpt2: unsupported shape d_model=%d n_head=%d d_ff=%d (need head_dim 64, d_model<=1024, multiples of 128)",
+               dims->d_model, dims->n_head, dims->d_ff);
+    LMRL_CHECK(w->n_vocab_rows >= dims->n_vocab, "lmrl_load_gpt2: wte has fewer rows than n_vocab");
+    LMRL_CHECK(e->cfg.max_input_length + e->cfg.max_new_tokens <= dims->n_pos, "lmrl_load_gpt2: max_input_length + max_new_tokens exceeds n_pos");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    const bool fresh = e->gpt2 == nullptr;
+    if (fresh) {
+        e->gpt2 = new Gpt2Dev();
+        e->gpt2->dims = *dims;
+        cudaDeviceProp prop;
+        LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
+        e->gpt2->sm_count = prop.multiProcessorCount;
+    } else {
+        LMRL_CHECK(memcmp(&e->gpt2->dims, dims, sizeof *dims) == 0, "lmrl_load_gpt2: set_params with a different architecture");
+    }
+    Gpt2Dev& G = *e->gpt2;
+    const int d = dims->d_model, ff = dims->d_ff, L = dims->n_layer;
+    G.v_pad = (dims->n_vocab + 127) / 128 * 128;
+    // staging buffer for fp32 uploads
+    const size_t stage_elems = std::max((size_t)w->n_vocab_rows * d, (size_t)d * std::max(ff, 3 * d));
+    float* stage = nullptr;
+    LMRL_CUDA(cudaMalloc(&stage, stage_elems * sizeof(float)));
+    auto up = [&](const float* host, size_t n) -> int {
+        LMRL_CUDA(cudaMemcpyAsync(stage, host, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        return 0;
+    };
+    auto vec = [&](float** dst, const float* host, size_t n) -> int {
+        if (fresh && e->alloc(dst, n)) return -1;
+        LMRL_CUDA(cudaMemcpyAsync(*dst, host, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        return 0;
+    };
+    auto mat_t = [&](__nv_bfloat16** dst, const float* host, int K, int N) -> int {   // [K][N] fp32 -> [N][K] bf16
+        if (fresh && e->alloc(dst, (size_t)K * N)) return -1;
+        if (up(host, (size_t)K * N)) return -1;
+        transpose_to_bf16_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, K, N, *dst);
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+        return 0;
+    };
+    int rc = 0;
+    if (fresh) { rc |= e->alloc(&G.wte, (size_t)G.v_pad * d); rc |= e->alloc(&G.wpe, (size_t)dims->n_pos * d); G.layers.resize(L); }
+    if (!rc) {
+        const int rows = std::min(w->n_vocab_rows, G.v_pad);
+        rc |= up(w->wte, (size_t)rows * d);
+        convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(stage, (size_t)rows * d, G.wte);
+        cudaStreamSynchronize(e->stream);
+        rc |= up(w->wpe, (size_t)dims->n_pos * d);
+        convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(stage, (size_t)dims->n_pos * d, G.wpe);
+        cudaStreamSynchronize(e->stream);
+        rc |= vec(&G.lnf_g, w->lnf_g, d); rc |= vec(&G.lnf_b, w->lnf_b, d);
+    }
+    for (int l = 0; l < L && !rc; ++l) {
+        LayerDev& Ld = G.layers[l];
+        rc |= vec(&Ld.ln1_g, w->ln1_g[l], d); rc |= vec(&Ld.ln1_b, w->ln1_b[l], d);
+        rc |= vec(&Ld.ln2_g, w->ln2_g[l], d); rc |= vec(&Ld.ln2_b, w->ln2_b[l], d);
+        rc |= mat_t(&Ld.w_qkv, w->attn_w[l], d, 3 * d); rc |= vec(&Ld.b_qkv, w->attn_b[l], 3 * d);
+        rc |= mat_t(&Ld.w_proj, w->proj_w[l], d, d); rc |= vec(&Ld.b_proj, w->proj_b[l], d);
+        rc |= mat_t(&Ld.w_fc, w->fc_w[l], d, ff); rc |= vec(&Ld.b_fc, w->fc_b[l], ff);
+        rc |= mat_t(&Ld.w_fc2, w->fc2_w[l], ff, d); rc |= vec(&Ld.b_fc2, w->fc2_b[l], d);
+    }
+    cudaStreamSynchronize(e->stream);
+    cudaFree(stage);
+    if (rc) return -1;
+    if (fresh && gpt2_alloc_state(e)) return -1;
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    LMRL_CUDA(cudaGetLastError());
+    e->has_gpt2 = true;
+    return 0;
+}
+
+static int load_prompts(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n) {
+    Gpt2Dev& G = *e->gpt2;
+    LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "batch of %d rows exceeds engine capacity %d", n, e->cfg.max_envs);
+    const int max_in = e->cfg.max_input_length;
+    // LEFT truncation on the host side of the copy: keep the last max_input tokens of every row
+    std::vector<int32_t> lens(n), packed((size_t)n * max_in, 0);
+    for (int i = 0; i < n; ++i) {
+        const int len = std::min(n_tok[i], max_in), skip = n_tok[i] - len;
+        LMRL_CHECK(n_tok[i] <= pitch && n_tok[i] >= 0, "row %d: n_tok %d exceeds pitch %d", i, n_tok[i], pitch);
+        lens[i] = len;
+        memcpy(packed.data() + (size_t)i * max_in, tokens + (size_t)i * pitch + skip, sizeof(int32_t) * len);
+    }
+    LMRL_CUDA(cudaMemcpy2DAsync(G.stream.tokens, sizeof(int32_t) * G.stream.cap, packed.data(), sizeof(int32_t) * max_in,
+                                sizeof(int32_t) * max_in, n, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(G.stream.len, lens.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemsetAsync(G.stream.kv_len, 0, sizeof(int32_t) * n, e->stream));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));   // host staging vectors die at return
+    return 0;
+}
+
+int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
+                       const uint64_t* episode_keys, int32_t turn, const lmrl_sampling* s, int32_t* out_tokens, int32_t* out_len) {
+    LMRL_CHECK(e && e->has_gpt2, "lmrl_generate: no GPT-2 parameters loaded");
+    LMRL_CHECK(tokens && n_tok && s && out_tokens && out_len, "lmrl_generate: null argument");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    if (load_prompts(e, tokens, n_tok, pitch, n)) return -1;
+    if (episode_keys) LMRL_CUDA(cudaMemcpyAsync(G.episode_key, episode_keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
+    else {
+        std::vector<uint64_t> idx(n);
+        for (int i = 0; i < n; ++i) idx[i] = (uint64_t)i;
+        LMRL_CUDA(cudaMemcpyAsync(G.episode_key, idx.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
+    e->launches++;
+    for (int k = 0; k < e->cfg.max_new_tokens; ++k)
+        if (forward_and_sample(e, k == 0 ? 0 : 1, n, nullptr, nullptr, turn, *s, nullptr)) return -1;
+    LMRL_CUDA(cudaMemcpyAsync(out_tokens, G.gen.tok, sizeof(int32_t) * (size_t)n * e->cfg.max_new_tokens, cudaMemcpyDeviceToHost, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(out_len, G.gen.len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, float* logits) {
+    LMRL_CHECK(e && e->has_gpt2, "lmrl_logits: no GPT-2 parameters loaded");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    if (load_prompts(e, tokens, n_tok, pitch, n)) return -1;
+    const size_t need = (size_t)e->cfg.max_envs * G.dims.n_vocab;
+    if (G.logits_rows < need) {
+        LMRL_CUDA(cudaMalloc(&G.logits, need * sizeof(float)));
+        G.owned.push_back(G.logits);
+        G.logits_rows = need;
+    }
+    clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
+    lmrl_sampling s{1.0f, 0, 0};
+    if (forward_and_sample(e, 0, n, nullptr, nullptr, 0, s, G.logits)) return -1;
+    // rows come back in slot order == env order for envs with tokens; scatter on the host
+    std::vector<int32_t> slot_env(n);
+    int n_slots = 0;
+    LMRL_CUDA(cudaMemcpyAsync(&n_slots, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(slot_env.data(), G.rows.slot_env, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    for (int j = 0; j < n_slots; ++j)
+        LMRL_CUDA(cudaMemcpyAsync(logits + (size_t)slot_env[j] * G.dims.n_vocab, G.logits + (size_t)j * G.dims.n_vocab,
+                                  sizeof(float) * G.dims.n_vocab, cudaMemcpyDeviceToHost, e->stream));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, int32_t n, const lmrl_sampling& s) {
+    Gpt2Dev& G = *e->gpt2;
+    LMRL_CHECK(env_kind == LMRL_ENV_WORDLE, "fused rollout: only the Wordle env is fused in this build (env_kind=%d)", env_kind);
+    LMRL_CHECK(e->has_wordle, "fused rollout: no Wordle vocabulary loaded");
+    LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "fused rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
+    LMRL_CHECK(e->cfg.max_new_tokens * e->max_token_bytes <= MAX_ACTION_CP, "fused rollout: max_new_tokens * longest token exceeds %d bytes", MAX_ACTION_CP);
+    const int T = e->cfg.max_turns;
+    cudaStream_t st = e->stream;
+    const int blocks = (n + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK;
+    wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n);
+    init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, nullptr, seeds_dev, G.episode_key,
+                                                        G.ep_return, G.ep_length, G.ep_done);
+    e->launches += 2;
+    ActionSrc src{};
+    src.tokens = G.gen.tok; src.ntokens = G.gen.len; src.tpitch = G.gen.max_new;
+    for (int turn = 0; turn < T; ++turn) {
+        clear_gen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, G.gen);
+        e->launches++;
+        for (int k = 0; k < e->cfg.max_new_tokens; ++k)
+            if (forward_and_sample(e, k == 0 ? 0 : 1, n, e->wordle.done, e->wordle.n_actions, 0, s, nullptr)) return -1;
+        wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(e->wordle, e->tok, src, nullptr,
+                                                                                                                  e->step, G.stream, n);
+        log_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, G.gen, e->wordle.n_actions, e->step, G.ep_return, G.ep_length, G.ep_done,
+                                                         G.step_reward, G.step_valid, G.step_fb, G.step_aux, G.act_tokens, G.act_len);
+        e->launches += 2;
+    }
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int rollout_export(lmrl_engine* e, int32_t n, lmrl_rollout_out* out, cudaMemcpyKind kind) {
+    Gpt2Dev& G = *e->gpt2;
+    const size_t T = e->cfg.max_turns, K = e->cfg.max_new_tokens;
+    if (!out) return 0;
+    if (out->ep_return) LMRL_CUDA(cudaMemcpyAsync(out->ep_return, G.ep_return, sizeof(float) * n, kind, e->stream));
+    if (out->ep_length) LMRL_CUDA(cudaMemcpyAsync(out->ep_length, G.ep_length, sizeof(int32_t) * n, kind, e->stream));
+    if (out->ep_done) LMRL_CUDA(cudaMemcpyAsync(out->ep_done, G.ep_done, n, kind, e->stream));
+    if (out->step_reward) LMRL_CUDA(cudaMemcpyAsync(out->step_reward, G.step_reward, sizeof(float) * n * T, kind, e->stream));
+    if (out->step_valid) LMRL_CUDA(cudaMemcpyAsync(out->step_valid, G.step_valid, n * T, kind, e->stream));
+    if (out->step_feedback) LMRL_CUDA(cudaMemcpyAsync(out->step_feedback, G.step_fb, n * T * 5, kind, e->stream));
+    if (out->step_aux) LMRL_CUDA(cudaMemcpyAsync(out->step_aux, G.step_aux, sizeof(int32_t) * n * T, kind, e->stream));
+    if (out->act_tokens) LMRL_CUDA(cudaMemcpyAsync(out->act_tokens, G.act_tokens, sizeof(int32_t) * n * T * K, kind, e->stream));
+    if (out->act_len) LMRL_CUDA(cudaMemcpyAsync(out->act_len, G.act_len, sizeof(int32_t) * n * T, kind, e->stream));
+    return 0;
+}
+
+int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, const int32_t* /*opt_pos*/, int32_t n,
+                      const lmrl_sampling* s, lmrl_rollout_out* out) {
+    LMRL_CHECK(e && e->has_gpt2, "lmrl_rollout: no GPT-2 parameters loaded");
+    LMRL_CHECK(seeds && s, "lmrl_rollout: null argument");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "lmrl_rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
+    LMRL_CUDA(cudaMemcpyAsync(e->d_seeds, seeds, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
+    if (rollout_enqueue(e, env_kind, e->d_seeds, n, *s)) return -1;
+    if (rollout_export(e, n, out, cudaMemcpyDeviceToHost)) return -1;
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, const int32_t* /*opt_pos_dev*/, int32_t n,
+                     const lmrl_sampling* s, lmrl_rollout_out* out_dev) {
+    LMRL_CHECK(e && e->has_gpt2, "lmrl_rollout: no GPT-2 parameters loaded");
+    LMRL_CHECK(seeds_dev && s, "lmrl_rollout: null argument");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    if (rollout_enqueue(e, env_kind, seeds_dev, n, *s)) return -1;
+    return rollout_export(e, n, out_dev, cudaMemcpyDeviceToDevice);
+}
+
+int lmrl_wordle_scripted_rollout_dev(lmrl_engine*, const uint64_t*, int32_t, float, uint64_t, lmrl_rollout_out*) {
+    return lmrl::fail("lmrl_wordle_scripted_rollout_dev: not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,297 @@
+// gpt2_kernels.cuh — the non-GEMM kernels of the GPT-2 KV-cache decoder over a RAGGED batch of rows.
+//
+// A "row" is one (environment, position) pair that needs a forward pass this launch: during prefill an env
+// contributes its not-yet-cached stream tokens, during decode one row per generating env.  Row counts live in
+// device memory (RowsDev::M) so a whole rollout is enqueued without host round trips.
+//
+// Replaces, per SURVEY.md §2.2: K1 (wte[ids]+wpe[pos], ln_1), K3 (causal attention with left-pad position ids,
+// value_rl_base/gpt2/generation.py:152-171 — here positions are simply the index in the env's own stream),
+// the LayerNorms of K5/K7, and the HF sampler bookkeeping (EOS / max_new_tokens).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gemm_mma.cuh"
+
+namespace lmrl {
+
+struct RowsDev {
+    int* M;            // [1] live rows this pass
+    int* n_slots;      // [1] envs contributing rows this pass
+    int* row_env;      // [Mcap]
+    int* row_pos;      // [Mcap]
+    int* row_tok;      // [Mcap]
+    int* slot_env;     // [B]   compact list of contributing envs
+    int* slot_row0;    // [B]   first row of the slot
+    int* slot_nrow;    // [B]
+    int* slot_last;    // [B]   row index of the slot's last row (the one that is sampled from)
+};
+
+struct GenDev {
+    int* tok;          // [B][max_new] sampled ids this turn
+    int* len;          // [B]
+    uint8_t* active;   // [B] still generating this turn
+    int* cur;          // [B] tokens whose KV is (about to be) valid == position of the next fed token
+    int max_new;
+    int eos_id;
+};
+
+// ---- row builder: exclusive scan over envs (single CTA; B <= 16384) ---------------------------------------------
+// mode 0 (prefill): env e contributes stream tokens [kv_len[e], len[e]) if it is not done
+// mode 1 (decode) : env e contributes its last sampled token at position cur[e] if it is still generating
+__global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ done, const int32_t* __restrict__ stream_tok,
+                                  const int32_t* __restrict__ stream_len, const int32_t* __restrict__ kv_len, int stream_cap,
+                                  GenDev gen, RowsDev rows) {
+    __shared__ int warp_sums[2][32];
+    __shared__ int carry[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    if (tid == 0) { carry[0] = 0; carry[1] = 0; }
+    __syncthreads();
+    for (int base = 0; base < B; base += blockDim.x) {
+        const int e = base + tid;
+        int n = 0;
+        if (e < B) {
+            if (mode == 0) n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0);
+            else n = gen.active[e] ? 1 : 0;
+        }
+        const int has = n > 0;
+        int xs = n, xh = has;      // inclusive warp scans of rows and of slots
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xFFFFFFFFu, xs, o), b = __shfl_up_sync(0xFFFFFFFFu, xh, o);
+            if (lane >= o) { xs += a; xh += b; }
+        }
+        if (lane == 31) { warp_sums[0][warp] = xs; warp_sums[1][warp] = xh; }
+        __syncthreads();
+        if (warp == 0) {
+            int a = lane < nwarp ? warp_sums[0][lane] : 0, b = lane < nwarp ? warp_sums[1][lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ua = __shfl_up_sync(0xFFFFFFFFu, a, o), ub = __shfl_up_sync(0xFFFFFFFFu, b, o);
+                if (lane >= o) { a += ua; b += ub; }
+            }
+            warp_sums[0][lane] = a; warp_sums[1][lane] = b;     // inclusive over warps
+        }
+        __syncthreads();
+        const int row0 = carry[0] + (warp ? warp_sums[0][warp - 1] : 0) + xs - n;
+        const int slot = carry[1] + (warp ? warp_sums[1][warp - 1] : 0) + xh - has;
+        if (has) {
+            rows.slot_env[slot] = e; rows.slot_row0[slot] = row0; rows.slot_nrow[slot] = n; rows.slot_last[slot] = row0 + n - 1;
+            if (mode == 1) {
+                const int p = gen.cur[e];
+                rows.row_env[row0] = e; rows.row_pos[row0] = p; rows.row_tok[row0] = gen.tok[e * gen.max_new + gen.len[e] - 1];
+                gen.cur[e] = p + 1;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { carry[0] += warp_sums[0][nwarp - 1]; carry[1] += warp_sums[1][nwarp - 1]; }
+        __syncthreads();
+    }
+    if (tid == 0) { *rows.M = carry[0]; *rows.n_slots = carry[1]; }
+}
+
+// prefill: expand each slot into its rows (one warp per slot); also resets the per-turn generation state
+__global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok, const int32_t* __restrict__ stream_len,
+                                         int32_t* __restrict__ kv_len, int stream_cap, GenDev gen, RowsDev rows) {
+    const int lane = threadIdx.x & 31;
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= *rows.n_slots) return;
+    const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot], p0 = kv_len[e];
+    for (int i = lane; i < n; i += 32) {
+        rows.row_env[r0 + i] = e; rows.row_pos[r0 + i] = p0 + i; rows.row_tok[r0 + i] = stream_tok[(size_t)e * stream_cap + p0 + i];
+    }
+    if (lane == 0) { gen.cur[e] = p0 + n; gen.len[e] = 0; gen.active[e] = 1; kv_len[e] = p0 + n; }
+}
+
+__global__ void clear_gen_kernel(int B, GenDev gen) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < B) { gen.active[e] = 0; gen.len[e] = 0; }
+}
+
+// ---- K1: x = wte[tok] + wpe[pos] (fp32 residual stream) ------------------------------------------------------------
+__global__ void embed_kernel(const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe, int d, RowsDev rows,
+                             float* __restrict__ x) {
+    const int M = *rows.M;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps) {
+        const __nv_bfloat16* a = wte + (size_t)rows.row_tok[r] * d;
+        const __nv_bfloat16* b = wpe + (size_t)rows.row_pos[r] * d;
+        for (int c = lane * 8; c < d; c += 256) {
+            const uint4 ua = *reinterpret_cast<const uint4*>(a + c), ub = *reinterpret_cast<const uint4*>(b + c);
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ua);
+            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+            float o[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 fa = __bfloat1622float2(pa[q]), fb = __bfloat1622float2(pb[q]);
+                o[2 * q] = fa.x + fb.x; o[2 * q + 1] = fa.y + fb.y;
+            }
+            float4* dst = reinterpret_cast<float4*>(x + (size_t)r * d + c);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
+// ---- LayerNorm: fp32 row -> bf16 row; one warp per row, d <= 1024, d % 128 == 0 ------------------------------------
+// gather != nullptr: output row j takes input row gather[j] (final LN of the sampled rows only), count from n_dev
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 int d, float eps, const int* __restrict__ n_dev, const int* __restrict__ gather,
+                                 __nv_bfloat16* __restrict__ out) {
+    const int n = *n_dev;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int nv = d >> 7;                 // float4 per lane
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+        const int r = gather ? gather[j] : j;
+        const float4* src = reinterpret_cast<const float4*>(x + (size_t)r * d);
+        float4 v[8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nv) { v[i] = src[lane + 32 * i]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        const float mean = s / d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nv) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+                q += a * a + b * b + c * c + e * e;
+            }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+        const float rstd = rsqrtf(q / d + eps);
+        __nv_bfloat16* dst = out + (size_t)j * d;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < nv) {
+                const int c = (lane + 32 * i) * 4;
+                const float4 g4 = *reinterpret_cast<const float4*>(gamma + c), b4 = *reinterpret_cast<const float4*>(beta + c);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g4.x + b4.x, (v[i].y - mean) * rstd * g4.y + b4.y);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g4.z + b4.z, (v[i].w - mean) * rstd * g4.w + b4.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(dst + c) = pk;
+            }
+    }
+}
+
+// ---- K3: causal attention over the slab KV cache, one CTA per (slot, head) ------------------------------------------
+// K/V of the (env, head) are staged once in shared memory (cp.async, K rows padded to 144 B so that a lane-per-key
+// 16-byte read pattern is bank-conflict free) and reused by every row of the slot; each warp owns rows w, w+4, ...
+// Scores: lane = key.  Softmax: warp shuffles.  P·V: lane = pair of head dims.
+constexpr int ATT_THREADS = 128;
+constexpr int ATT_KPITCH = 72;   // bf16 elements per staged K row (64 + 8 pad)
+
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
+                                                                int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
+    const int slot = blockIdx.y, head = blockIdx.x;
+    if (slot >= *rows.n_slots) return;
+    extern __shared__ __align__(16) unsigned char att_smem[];
+    const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
+    const int ctx = rows.row_pos[r0 + n - 1] + 1;        // keys visible to the slot's last row
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
+    __nv_bfloat16* sV = sK + (size_t)t_cap * ATT_KPITCH;
+    float* sP = reinterpret_cast<float*>(sV + (size_t)t_cap * 64);     // [4 warps][t_cap]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __nv_bfloat16* gK = kcache + ((size_t)e * n_head + head) * t_cap * 64;
+    const __nv_bfloat16* gV = vcache + ((size_t)e * n_head + head) * t_cap * 64;
+    for (int c = tid; c < ctx * 8; c += ATT_THREADS) {
+        const int j = c >> 3, ch = c & 7;
+        cp_async16(smem_u32(sK + j * ATT_KPITCH + ch * 8), gK + j * 64 + ch * 8);
+        cp_async16(smem_u32(sV + j * 64 + ch * 8), gV + j * 64 + ch * 8);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    float* myP = sP + warp * t_cap;
+    for (int i = warp; i < n; i += ATT_THREADS / 32) {
+        const int r = r0 + i, p = rows.row_pos[r];
+        // q row (64 dims) in registers as 32 packed pairs, pre-scaled
+        uint32_t qreg[32];
+        const uint4* qsrc = reinterpret_cast<const uint4*>(q + (size_t)r * d_model + head * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 u = __ldg(qsrc + c);
+            qreg[4 * c] = u.x; qreg[4 * c + 1] = u.y; qreg[4 * c + 2] = u.z; qreg[4 * c + 3] = u.w;
+        }
+        float mx = -INFINITY;
+        const int nkeys = p + 1;
+        for (int j = lane; j < nkeys; j += 32) {
+            const uint4* kr = reinterpret_cast<const uint4*>(sK + j * ATT_KPITCH);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 u = kr[c];
+                const uint32_t kk[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qreg[4 * c + t]));
+                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk[t]));
+                    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s);
+                }
+            }
+            s *= scale;
+            myP[j] = s;
+            mx = fmaxf(mx, s);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < nkeys; j += 32) {
+            const float w = __expf(myP[j] - mx);
+            myP[j] = w;
+            sum += w;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        __syncwarp();
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < nkeys; ++j) {
+            const float w = myP[j];
+            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + j * 64 + lane * 2));
+            o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1);
+        }
+        const float inv = 1.0f / sum;
+        *reinterpret_cast<__nv_bfloat162*>(out + (size_t)r * d_model + head * 64 + lane * 2) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+        __syncwarp();
+    }
+}
+
+// ---- sampler bookkeeping ------------------------------------------------------------------------------------------------
+// per-row sampling key: fmix of (base seed, episode key, turn, token index) — independent of batch layout / GPU count
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void prepare_sample_kernel(RowsDev rows, GenDev gen, const uint64_t* __restrict__ episode_key, const int32_t* __restrict__ turn_of_env,
+                                      int turn_const, uint64_t base_seed, uint64_t* __restrict__ row_key, unsigned long long* __restrict__ best) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *rows.n_slots) return;
+    const int e = rows.slot_env[j];
+    const uint64_t ek = episode_key ? episode_key[e] : (uint64_t)e;
+    const uint64_t turn = turn_of_env ? (uint64_t)turn_of_env[e] : (uint64_t)turn_const;
+    row_key[j] = splitmix64(splitmix64(base_seed ^ splitmix64(ek)) + (turn << 32) + (uint64_t)gen.len[e]);
+    best[j] = 0ull;
+}
+
+__global__ void finalize_sample_kernel(RowsDev rows, GenDev gen, const unsigned long long* __restrict__ best) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *rows.n_slots) return;
+    const int e = rows.slot_env[j];
+    const int tok = (int)(0xFFFFFFFFu - (uint32_t)(best[j] & 0xFFFFFFFFull));
+    const int k = gen.len[e];
+    gen.tok[e * gen.max_new + k] = tok;
+    gen.len[e] = k + 1;
+    if (tok == gen.eos_id || k + 1 >= gen.max_new) gen.active[e] = 0;
+}
+
+}  // namespace lmrl

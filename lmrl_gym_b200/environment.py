@@ -191,7 +191,7 @@ def _fused_pair(env, policy):
     """(engine) if env and policy are device objects bound to the same engine, else None."""
     eng_e = getattr(env, "_lmrl_engine", None)
     eng_p = getattr(policy, "_lmrl_engine", None)
-    if eng_e is not None and eng_e is eng_p and getattr(env, "_lmrl_fusable", False):
+    if eng_e is not None and eng_e is eng_p and getattr(env, "_lmrl_fusable", False) and getattr(policy, "fusable", False):
         return eng_e
     return None
 

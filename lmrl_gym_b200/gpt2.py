@@ -1,0 +1,190 @@
+"""GPT-2 sampling policy on the device engine, behind the reference's BatchedTextPolicy interface.
+
+Drop-in for ``GPT2PPOPolicy`` (LLM_RL/algorithms/ppo/gpt2/interface.py:480-549): ``act(text_history, done)`` joins
+each history into a prompt (environment.py:18), LEFT-truncates it to ``max_input_length`` tokens, samples up to
+``max_new_tokens`` ids (stop at the newline/EOS id, as ``GenerationConfig(eos_token_id=tokenizer.encode('\\n')[0])``
+of wordle/ppo/train_ppo_gpt2.py:223), decodes the completion and appends it as an action ``Text``;
+``set_params(params)`` swaps the weights (interface.py:548-549).  When the env passed to ``text_env_eval`` is a device
+env on the same ``Engine`` the whole loop is fused on the GPU instead (lmrl_gym_b200/rollout.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+from .engine import Engine
+from .environment import BatchedTextPolicy, Text, TextHistory, text_history_to_str
+
+
+@dataclass
+class GPT2Config:
+    n_layer: int = 12
+    n_head: int = 12
+    d_model: int = 768
+    d_ff: int = 3072
+    n_vocab: int = 50257          # ids the sampler may emit (the reference masks padded ids to -inf, interface.py:330)
+    n_vocab_rows: int = 50258     # rows of wte (50257 + <|pad|>)
+    n_pos: int = 1024
+    ln_eps: float = 1e-5
+
+    @classmethod
+    def small(cls):
+        return cls()
+
+    @classmethod
+    def medium(cls):
+        return cls(n_layer=24, n_head=16, d_model=1024, d_ff=4096)
+
+    @property
+    def matmul_params(self) -> int:
+        d, f = self.d_model, self.d_ff
+        return self.n_layer * (3 * d * d + d * d + 2 * d * f) + d * self.n_vocab
+
+
+def init_gpt2_params(cfg: GPT2Config, seed: int = 0) -> Dict:
+    """Seeded random init with HF GPT-2's scheme (normal(0, 0.02); c_proj scaled by 1/sqrt(2L); LN = 1/0)."""
+    rng = np.random.default_rng(seed)
+    d, f, L = cfg.d_model, cfg.d_ff, cfg.n_layer
+
+    def nrm(shape, std=0.02):
+        return (rng.standard_normal(shape, dtype=np.float32) * np.float32(std))
+
+    proj_std = 0.02 / np.sqrt(2.0 * L)
+    layers = []
+    for _ in range(L):
+        layers.append(dict(
+            ln1_g=np.ones(d, np.float32), ln1_b=np.zeros(d, np.float32),
+            attn_w=nrm((d, 3 * d)), attn_b=np.zeros(3 * d, np.float32),
+            proj_w=nrm((d, d), proj_std), proj_b=np.zeros(d, np.float32),
+            ln2_g=np.ones(d, np.float32), ln2_b=np.zeros(d, np.float32),
+            fc_w=nrm((d, f)), fc_b=np.zeros(f, np.float32),
+            fc2_w=nrm((f, d), proj_std), fc2_b=np.zeros(d, np.float32)))
+    return dict(wte=nrm((cfg.n_vocab_rows, d)), wpe=nrm((cfg.n_pos, d)), lnf_g=np.ones(d, np.float32),
+                lnf_b=np.zeros(d, np.float32), layers=layers)
+
+
+def params_from_hf_state_dict(sd, cfg: GPT2Config) -> Dict:
+    """``transformers.GPT2LMHeadModel().state_dict()`` (torch) -> the dict layout above."""
+    g = lambda k: np.ascontiguousarray(sd[k].detach().cpu().float().numpy())  # noqa: E731
+    layers = []
+    for l in range(cfg.n_layer):
+        p = f"transformer.h.{l}."
+        layers.append(dict(
+            ln1_g=g(p + "ln_1.weight"), ln1_b=g(p + "ln_1.bias"), attn_w=g(p + "attn.c_attn.weight"), attn_b=g(p + "attn.c_attn.bias"),
+            proj_w=g(p + "attn.c_proj.weight"), proj_b=g(p + "attn.c_proj.bias"), ln2_g=g(p + "ln_2.weight"), ln2_b=g(p + "ln_2.bias"),
+            fc_w=g(p + "mlp.c_fc.weight"), fc_b=g(p + "mlp.c_fc.bias"), fc2_w=g(p + "mlp.c_proj.weight"), fc2_b=g(p + "mlp.c_proj.bias")))
+    return dict(wte=g("transformer.wte.weight"), wpe=g("transformer.wpe.weight"), lnf_g=g("transformer.ln_f.weight"),
+                lnf_b=g("transformer.ln_f.bias"), layers=layers)
+
+
+_LAYER_KEYS = ["ln1_g", "ln1_b", "attn_w", "attn_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc_w", "fc_b", "fc2_w", "fc2_b"]
+
+
+def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict):
+    L = cfg.n_layer
+    assert len(params["layers"]) == L
+    keep = []  # keep contiguous fp32 copies alive during the call
+
+    def arr(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a)
+        return a.ctypes.data_as(_lib._PF)
+
+    w = _lib.lmrl_gpt2_weights()
+    w.wte = arr(params["wte"])
+    w.n_vocab_rows = int(params["wte"].shape[0])
+    w.wpe = arr(params["wpe"])
+    w.lnf_g = arr(params["lnf_g"])
+    w.lnf_b = arr(params["lnf_b"])
+    for key in _LAYER_KEYS:
+        ptrs = (_lib._PF * L)(*[arr(layer[key]) for layer in params["layers"]])
+        keep.append(ptrs)
+        setattr(w, key, C.cast(ptrs, _lib._PPF))
+    dims = _lib.lmrl_gpt2_dims(n_layer=cfg.n_layer, n_head=cfg.n_head, d_model=cfg.d_model, d_ff=cfg.d_ff, n_vocab=cfg.n_vocab,
+                               n_pos=cfg.n_pos, ln_eps=cfg.ln_eps)
+    check(engine.lib.lmrl_load_gpt2(engine.handle, C.byref(dims), C.byref(w)))
+
+
+def default_out_str_process(s: str) -> str:
+    # the lambda every reference Wordle/Maze driver passes (e.g. wordle/bc/eval_bc_gpt2.py:105)
+    return s.removesuffix("\n") + "\n"
+
+
+class B200GPT2Policy(BatchedTextPolicy):
+    def __init__(self, engine: Engine, params: Dict, config: Optional[GPT2Config] = None, do_sample: bool = True,
+                 temperature: Optional[float] = None, seed: int = 0, in_str_process: Optional[Callable[[str], str]] = None,
+                 out_str_process: Optional[Callable[[str], str]] = None):
+        if engine.tokenizer is None:
+            raise _lib.LmrlError("Engine needs a tokenizer before a policy can be bound to it")
+        self._lmrl_engine = engine
+        self.config = config or GPT2Config.small()
+        self.do_sample = bool(do_sample)
+        self.temperature = 1.0 if temperature is None else float(temperature)
+        self.seed = int(seed)
+        self.in_str_process = in_str_process
+        self.out_str_process = out_str_process
+        self._calls = 0
+        _upload_params(engine, self.config, params)
+
+    @property
+    def fusable(self) -> bool:
+        return self.in_str_process is None and self.out_str_process is None
+
+    def sampling(self) -> "_lib.lmrl_sampling":
+        return _lib.lmrl_sampling(temperature=self.temperature, do_sample=int(self.do_sample), seed=self.seed & ((1 << 64) - 1))
+
+    def set_params(self, params: Dict) -> None:
+        _upload_params(self._lmrl_engine, self.config, params)
+
+    def generate_tokens(self, prompts: List[List[int]], episode_keys=None, turn: int = 0):
+        e = self._lmrl_engine
+        n = len(prompts)
+        pitch = max(8, max((len(p) for p in prompts), default=8))
+        toks = np.zeros((n, pitch), np.int32)
+        lens = np.zeros(n, np.int32)
+        for i, p in enumerate(prompts):
+            toks[i, :len(p)] = p
+            lens[i] = len(p)
+        out = np.zeros((n, e.max_new_tokens), np.int32)
+        out_len = np.zeros(n, np.int32)
+        keys = None if episode_keys is None else np.asarray(episode_keys, dtype=np.uint64)
+        s = self.sampling()
+        check(e.lib.lmrl_generate_host(e.handle, ptr(toks), ptr(lens), pitch, n, ptr(keys), int(turn), C.byref(s), ptr(out), ptr(out_len)))
+        return [out[i, :out_len[i]].tolist() for i in range(n)]
+
+    def logits(self, prompts: List[List[int]]) -> np.ndarray:
+        """Parity hook: fp32 logits of the last position of every prompt."""
+        e = self._lmrl_engine
+        n = len(prompts)
+        pitch = max(8, max(len(p) for p in prompts))
+        toks = np.zeros((n, pitch), np.int32)
+        lens = np.zeros(n, np.int32)
+        for i, p in enumerate(prompts):
+            toks[i, :len(p)] = p
+            lens[i] = len(p)
+        out = np.zeros((n, self.config.n_vocab), np.float32)
+        check(e.lib.lmrl_logits_host(e.handle, ptr(toks), ptr(lens), pitch, n, ptr(out)))
+        return out
+
+    def act(self, text_history: List[Optional[TextHistory]], done: Optional[List[bool]] = None) -> List[Optional[TextHistory]]:
+        if done is None:
+            done = [False] * len(text_history)
+        tok = self._lmrl_engine.tokenizer
+        in_f = self.in_str_process or (lambda x: x)
+        out_f = self.out_str_process or default_out_str_process
+        live = [i for i, d in enumerate(done) if not d]
+        out: List[Optional[TextHistory]] = [None] * len(text_history)
+        cap = self._lmrl_engine.max_envs
+        for lo in range(0, len(live), cap):
+            idx = live[lo:lo + cap]
+            prompts = [tok.encode(in_f(text_history_to_str(text_history[i]))) for i in idx]
+            gens = self.generate_tokens(prompts, episode_keys=[self._calls * (1 << 20) + i for i in idx], turn=0)
+            for i, g in zip(idx, gens):
+                out[i] = tuple(text_history[i]) + (Text(out_f(tok.decode(g)), True),)
+        self._calls += 1
+        return out

@@ -1,0 +1,140 @@
+"""GPT-2 decoder + sampler — fp32 torch-CPU restatement (oracle; test infrastructure only).  PARITY UNPINNED.
+
+The reference's policy arithmetic lives in third-party code that is neither under /root/reference nor installable
+here: Sea-Snell/JaxSEQ (git HEAD, unpinned: setup_jaxseq.sh:1-3) driving transformers==4.26.1 FlaxGPT2LMHeadModel /
+FlaxGenerationMixin on jax==0.4.7 (requirements.txt:1-20).  Call sites in the reference:
+LLM_RL/algorithms/ppo/gpt2/interface.py:527-535 and value_rl_base/gpt2/interface.py:98-105.  What is restated here
+is the published GPT-2 architecture as HF implements it (GPT2Config defaults: pre-LN blocks, fused c_attn, 64-wide
+heads, gelu_new, LN eps 1e-5, learned positions, tied LM head) and the semantics of HF sampling the reference uses
+(do_sample, temperature, EOS = '\\n', max_new_tokens; top-k/top-p None: wordle/bc/eval_bc_gpt2.py:42-44, 90-95).
+``forward_last_logits`` is itself checked against ``transformers.GPT2LMHeadModel`` (torch) with identical weights in
+tests/test_oracle_gpt2.py.
+
+Sampling: ``jax.random.categorical`` cannot be matched bit-for-bit, so the engine defines its own counter-based
+Gumbel-max sampler; ``row_key`` / ``gumbel_noise`` restate that definition (csrc/gemm_mma.cuh::noise_bits,
+csrc/gpt2_kernels.cuh::prepare_sample_kernel) so that tests can check the chosen token is the arg-max of
+(oracle logits / T + noise) up to the logit tolerance.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+M64 = (1 << 64) - 1
+
+
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def _t(a, emulate):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return t.to(torch.bfloat16).to(torch.float32) if emulate else t
+
+
+def _r(t: torch.Tensor, emulate: bool) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32) if emulate else t
+
+
+def gelu_new(x: torch.Tensor) -> torch.Tensor:
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+def layer_norm(x, g, b, eps):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * g + b
+
+
+def forward_hidden(params: Dict, tokens: Sequence[int], n_head: int, eps: float = 1e-5, weights_bf16: bool = True,
+                   emulate_bf16: bool = False) -> torch.Tensor:
+    """Full causal forward of one sequence; returns the final-LN hidden states [T, d].
+
+    weights_bf16: matrices/embeddings rounded to bf16 first (what the engine stores), biases/LN params stay fp32.
+    emulate_bf16: additionally round activations where the engine does (LN outputs, q/k/v, attention output,
+                  GeLU output)."""
+    W = lambda a: _t(a, weights_bf16)  # noqa: E731
+    F = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))  # noqa: E731
+    T = len(tokens)
+    ids = torch.as_tensor(list(tokens), dtype=torch.long)
+    x = W(params["wte"])[ids] + W(params["wpe"])[:T]
+    d = x.shape[1]
+    hd = d // n_head
+    mask = torch.tril(torch.ones(T, T, dtype=torch.bool))
+    for L in params["layers"]:
+        xn = _r(layer_norm(x, F(L["ln1_g"]), F(L["ln1_b"]), eps), emulate_bf16)
+        qkv = _r(xn @ W(L["attn_w"]) + F(L["attn_b"]), emulate_bf16)
+        q, k, v = qkv.split(d, dim=1)
+        q = q.view(T, n_head, hd).transpose(0, 1)
+        k = k.view(T, n_head, hd).transpose(0, 1)
+        v = v.view(T, n_head, hd).transpose(0, 1)
+        s = (q @ k.transpose(1, 2)) / math.sqrt(hd)
+        s = s.masked_fill(~mask, float("-inf"))
+        a = _r((torch.softmax(s, dim=-1) @ v).transpose(0, 1).reshape(T, d), emulate_bf16)
+        x = x + a @ W(L["proj_w"]) + F(L["proj_b"])
+        xn = _r(layer_norm(x, F(L["ln2_g"]), F(L["ln2_b"]), eps), emulate_bf16)
+        h = _r(gelu_new(xn @ W(L["fc_w"]) + F(L["fc_b"])), emulate_bf16)
+        x = x + h @ W(L["fc2_w"]) + F(L["fc2_b"])
+    return _r(layer_norm(x, F(params["lnf_g"]), F(params["lnf_b"]), eps), emulate_bf16)
+
+
+def forward_last_logits(params: Dict, tokens: Sequence[int], n_head: int, n_vocab: int, **kw) -> np.ndarray:
+    h = forward_hidden(params, tokens, n_head, **kw)
+    wte = _t(params["wte"], kw.get("weights_bf16", True))[:n_vocab]
+    return (h[-1] @ wte.T).numpy()
+
+
+# ---- the engine's sampler, restated -------------------------------------------------------------------------------
+
+def splitmix64(z: int) -> int:
+    z = (z + 0x9E3779B97F4A7C15) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    return z ^ (z >> 31)
+
+
+def row_key(base_seed: int, episode_key: int, turn: int, k: int) -> int:
+    return splitmix64((splitmix64(base_seed ^ splitmix64(episode_key)) + (turn << 32) + k) & M64)
+
+
+def _fmix32(h: np.ndarray) -> np.ndarray:
+    h = h.astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    h = (h.astype(np.uint64) * np.uint64(0x85EBCA6B)).astype(np.uint32)
+    h ^= h >> np.uint32(13)
+    h = (h.astype(np.uint64) * np.uint64(0xC2B2AE35)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return h
+
+
+def gumbel_noise(key: int, n_vocab: int) -> np.ndarray:
+    col = np.arange(n_vocab, dtype=np.uint32)
+    h = _fmix32(col ^ np.uint32(key & 0xFFFFFFFF))
+    h = _fmix32(h ^ np.uint32(key >> 32))
+    u = ((h >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
+    return -np.log(-np.log(u))
+
+
+def sample_scores(logits: np.ndarray, key: int, temperature: float = 1.0, do_sample: bool = True) -> np.ndarray:
+    s = logits.astype(np.float64) / (temperature if temperature and temperature > 0 else 1.0)
+    if do_sample:
+        s = s + gumbel_noise(key, len(logits))
+    return s
+
+
+def generate(params: Dict, prompt: Sequence[int], n_head: int, n_vocab: int, eos_id: int, max_new_tokens: int,
+             base_seed: int, episode_key: int, turn: int, temperature: float = 1.0, do_sample: bool = True,
+             max_input_length: Optional[int] = None, **kw) -> List[int]:
+    """HF-style sampling loop for ONE sequence (prompt LEFT-truncated to max_input_length)."""
+    toks = list(prompt)[-max_input_length:] if max_input_length else list(prompt)
+    out: List[int] = []
+    for k in range(max_new_tokens):
+        logits = forward_last_logits(params, toks + out, n_head, n_vocab, **kw)
+        t = int(np.argmax(sample_scores(logits, row_key(base_seed, episode_key, turn, k), temperature, do_sample)))
+        out.append(t)
+        if t == eos_id:
+            break
+    return out

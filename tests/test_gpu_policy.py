@@ -1,0 +1,206 @@
+"""GPU parity: GPT-2 decoder / sampler / fused rollout (through the C ABI) vs the torch-fp32 oracle and the oracle env.
+
+Tolerances (floating point, stated per north_star): the engine keeps weights and inter-kernel activations in bf16 with
+fp32 accumulation, so last-position logits are compared
+  * against the oracle that rounds at the same points (``emulate_bf16=True``):   max |diff| <= 2e-2
+  * against the plain fp32 oracle on bf16-rounded weights:                        max |diff| <= 6e-2, mean |diff| <= 1e-2
+(logit std is ~0.5 for the random-init models used here).  Sampled tokens must be the arg-max of the oracle's
+(logits/T + Gumbel noise) up to twice the logit tolerance.  Env state, rewards and returns are bit-exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params  # noqa: E402
+from lmrl_gym_b200.tokenizer import ByteTokenizer  # noqa: E402
+from lmrl_gym_b200.vocab import load_vocab_words  # noqa: E402
+
+TOL_EMU, TOL_F32, TOL_F32_MEAN = 2e-2, 6e-2, 1e-2
+
+
+@pytest.fixture(scope="module")
+def tok():
+    return ByteTokenizer.synthetic()
+
+
+def _small_cfg():
+    return GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+
+
+def _steer_to_letters(params, tok, alpha=12.0, newline_bonus=-1.6):
+    """Make the LM head context-free and concentrated on letter tokens + newline (see test docstring below)."""
+    letters = [tok.encode(c)[0] for c in "abcdefghijklmnopqrstuvwxyz"] + [tok.encode("x " + c)[1] for c in "abcdefghijklmnopqrstuvwxyz"]
+    from oracle.gpt2 import bf16_round
+    w = bf16_round(params["wte"]).astype(np.float64)
+    b = np.zeros(w.shape[1])
+    for v in letters:
+        b += alpha * w[v] / (w[v] @ w[v])
+    nl = tok.newline_id()
+    b += (alpha + newline_bonus + np.log(len(letters) / 5.0)) * w[nl] / (w[nl] @ w[nl])
+    params["lnf_g"] = np.zeros_like(params["lnf_g"])
+    params["lnf_b"] = b.astype(np.float32)
+    return params
+
+
+def test_logits_match_oracle_small_and_ragged(tok):
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    cfg = _small_cfg()
+    params = init_gpt2_params(cfg, seed=3)
+    rng = np.random.default_rng(0)
+    for l in params["layers"]:       # non-trivial biases / LN params
+        for k in ("attn_b", "proj_b", "fc_b", "fc2_b", "ln1_b", "ln2_b"):
+            l[k] = (0.1 * rng.standard_normal(l[k].shape)).astype(np.float32)
+        l["ln1_g"] = (1 + 0.1 * rng.standard_normal(l["ln1_g"].shape)).astype(np.float32)
+    eng = Engine(max_envs=160, max_input_length=64, max_new_tokens=4, tokenizer=tok)
+    pol = B200GPT2Policy(eng, params, cfg)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, 64, size=150)]
+    prompts[0] = prompts[0][:1]
+    prompts[1] = rng.integers(0, cfg.n_vocab, size=64).tolist()
+    got = pol.logits(prompts)
+    worst_emu = worst_f32 = 0.0
+    for i in range(0, 150, 5):
+        emu = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+        f32 = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab)
+        worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+        worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+        assert np.abs(got[i] - f32).mean() <= TOL_F32_MEAN
+    print(f"small model: max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
+    assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
+    # LEFT truncation: a prompt longer than max_input_length is cut to its last 64 tokens
+    long_p = rng.integers(0, cfg.n_vocab, size=100).tolist()
+    a = pol.logits([long_p])[0]
+    b = og.forward_last_logits(params, long_p[-64:], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+    assert np.abs(a - b).max() <= TOL_EMU
+    eng.close()
+
+
+def test_logits_match_oracle_gpt2_small_shape(tok):
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    cfg = GPT2Config.small()
+    params = init_gpt2_params(cfg, seed=0)
+    eng = Engine(max_envs=32, max_input_length=48, max_new_tokens=2, tokenizer=tok)
+    pol = B200GPT2Policy(eng, params, cfg)
+    rng = np.random.default_rng(1)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(3, 48, size=24)]
+    prompts[0] = tok.encode("Wordle:\nc r a n e\nb y b b g\n")
+    got = pol.logits(prompts)
+    worst_emu = worst_f32 = 0.0
+    for i in range(0, 24, 4):
+        emu = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+        f32 = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab)
+        worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+        worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+    print(f"gpt2-small: max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
+    assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
+    eng.close()
+
+
+def test_generate_matches_oracle_sampler(tok):
+    """Prefill + KV-cache decode + fused Gumbel arg-max: every sampled id is the oracle's arg-max (teacher-forced on the
+    device's own prefix) up to tolerance; greedy decoding likewise; EOS stops a row."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    cfg = _small_cfg()
+    params = init_gpt2_params(cfg, seed=5)
+    eng = Engine(max_envs=64, max_input_length=32, max_new_tokens=5, tokenizer=tok)
+    rng = np.random.default_rng(2)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, 32, size=48)]
+    keys = [int(k) for k in rng.integers(0, 2**63, size=48)]
+    for do_sample, temperature in [(True, 1.0), (True, 0.7), (False, 1.0)]:
+        pol = B200GPT2Policy(eng, params, cfg, do_sample=do_sample, temperature=temperature, seed=99)
+        gens = pol.generate_tokens(prompts, episode_keys=keys, turn=3)
+        for i in range(0, 48, 4):
+            assert 1 <= len(gens[i]) <= 5
+            for k, t in enumerate(gens[i]):
+                logits = og.forward_last_logits(params, prompts[i] + gens[i][:k], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+                s = og.sample_scores(logits, og.row_key(99, keys[i], 3, k), temperature, do_sample)
+                assert s[t] >= s.max() - 2 * TOL_EMU / temperature, (i, k)
+            assert tok.newline_id() not in gens[i][:-1]
+    # steered model: newline is likely, rows must stop right after it
+    sp = _steer_to_letters(init_gpt2_params(cfg, seed=5), tok)
+    pol = B200GPT2Policy(eng, sp, cfg, seed=1)
+    gens = pol.generate_tokens(prompts, episode_keys=keys, turn=0)
+    assert any(len(g) < 5 for g in gens) and all(tok.newline_id() not in g[:-1] for g in gens)
+    eng.close()
+
+
+def test_fused_rollout_matches_oracle_env_and_sampler(tok):
+    """The fused loop end to end.  The LM head is steered to letters/newline so that ~7% of actions are legal 5-letter
+    guesses (require_words_in_vocab=False makes them transition the game), the rest are malformed: both env branches,
+    the MT19937 target draw, re-rendering and KV roll-back are exercised.  Every transition is replayed through the
+    CPU oracle env; sampled ids are checked against the oracle sampler on the canonical prompt."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from lmrl_gym_b200.environment import text_env_eval
+    from oracle import gpt2 as og
+    from oracle.mt19937 import seed_stream
+    from oracle.wordle import ReformatWordleOracle
+    cfg = _small_cfg()
+    params = _steer_to_letters(init_gpt2_params(cfg, seed=7), tok)
+    B = 256
+    eng = Engine(max_envs=B, max_input_length=96, max_new_tokens=6, max_turns=6, tokenizer=tok)
+    env = B200WordleEnv(eng, "wordle_official.txt", require_words_in_vocab=False, bad_word_reward=-1.0)
+    pol = B200GPT2Policy(eng, params, cfg, seed=11)
+    inter, summary = text_env_eval(env, pol, n_rollouts=B + 40, seed_generator=seed_stream(0), bsize=B, verbose=False)
+    assert len(inter) == B + 40
+    words = load_vocab_words("wordle_official.txt")
+    seeds = seed_stream(0)
+    n_legal = n_steps = 0
+    rets, lens, dones = [], [], []
+    for i, ep in enumerate(inter):
+        seed = next(seeds)
+        o = ReformatWordleOracle(words, require_words_in_vocab=False, bad_word_reward=-1.0)
+        h = o.reset(seed)
+        assert 1 <= len(ep) <= 6
+        for t, tr in enumerate(ep):
+            assert [[x.text, x.is_action] for x in tr.pre_action_history] == [[a, b] for a, b in h]
+            action = tr.post_action_history[-1].text
+            h, r, d = o.step(h + ((action, True),))
+            assert [[x.text, x.is_action] for x in tr.post_transition_history] == [[a, b] for a, b in h]
+            assert tr.reward == r and type(tr.reward) is type(r) and tr.done == d
+            n_legal += h[-1][0] != "\n"
+            n_steps += 1
+        assert ep[-1].done
+        rets.append(sum(x.reward for x in ep)); lens.append(len(ep)); dones.append(ep[-1].done)
+    assert n_legal >= 20, f"only {n_legal} legal guesses in {n_steps} steps"
+    assert float(summary["reward"]["mean"]) == float(np.mean(np.asarray(rets, np.float32)))
+    assert float(summary["length"]["mean"]) == float(np.mean(lens)) and float(summary["done"]["mean"]) == 1.0
+    # sampler parity on the canonical prompts of a few episodes (prompt tokens = tokenizer.encode(joined history))
+    seeds = seed_stream(0)
+    seed_list = [next(seeds) for _ in range(B + 40)]
+    for i in (0, 17, B + 3):
+        ep = inter[i]
+        logs, j = ep._logs, ep._i
+        for t, tr in enumerate(ep):
+            prompt = tok.encode("".join(x.text for x in tr.pre_action_history))
+            gen = logs.act_tokens[j, t, :logs.act_len[j, t]].tolist()
+            for k, tk in enumerate(gen):
+                logits = og.forward_last_logits(params, prompt + gen[:k], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+                s = og.sample_scores(logits, og.row_key(11, seed_list[i], t, k), 1.0, True)
+                assert s[tk] >= s.max() - 2 * TOL_EMU, (i, t, k)
+    eng.close()
+
+
+def test_generic_act_path_runs_device_env_and_policy(tok):
+    """The non-fused drop-in path: reference-style loop, device env step + device generate per turn."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from lmrl_gym_b200.environment import text_env_eval
+    from oracle.mt19937 import seed_stream
+    cfg = _small_cfg()
+    eng = Engine(max_envs=16, max_input_length=128, max_new_tokens=6, tokenizer=tok)
+    env = B200WordleEnv(eng, "wordle_official_200")
+    pol = B200GPT2Policy(eng, init_gpt2_params(cfg, seed=1), cfg, out_str_process=lambda s: s.removesuffix("\n") + "\n")
+    assert not pol.fusable
+    inter, summary = text_env_eval(env, pol, n_rollouts=20, seed_generator=seed_stream(3), bsize=16, verbose=False)
+    assert len(inter) == 20 and all(len(ep) == 6 and ep[-1].done for ep in inter)
+    assert float(summary["reward"]["mean"]) == -6.0
+    eng.close()

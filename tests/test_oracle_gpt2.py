@@ -1,0 +1,49 @@
+"""The GPT-2 oracle restatement vs transformers' torch GPT2LMHeadModel with identical weights (CPU)."""
+import numpy as np
+import torch
+
+from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params, params_from_hf_state_dict
+from oracle import gpt2 as og
+
+
+def test_oracle_forward_matches_hf_gpt2():
+    from transformers import GPT2Config as HFConfig, GPT2LMHeadModel
+    cfg = GPT2Config(n_layer=3, n_head=4, d_model=256, d_ff=1024, n_vocab=1000, n_vocab_rows=1000, n_pos=64)
+    torch.manual_seed(0)
+    hf = GPT2LMHeadModel(HFConfig(vocab_size=1000, n_positions=64, n_embd=256, n_layer=3, n_head=4, attn_pdrop=0.0, embd_pdrop=0.0,
+                                  resid_pdrop=0.0)).eval()
+    # give biases / LN params non-trivial values so they are exercised
+    with torch.no_grad():
+        for n, p in hf.named_parameters():
+            if "bias" in n or "ln" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    params = params_from_hf_state_dict(hf.state_dict(), cfg)
+    toks = [5, 17, 999, 0, 3, 3, 250, 77, 12]
+    with torch.no_grad():
+        want = hf(torch.tensor([toks])).logits[0, -1].numpy()
+    got = og.forward_last_logits(params, toks, cfg.n_head, cfg.n_vocab, weights_bf16=False)
+    assert np.abs(got - want).max() < 2e-4
+    # bf16 weight rounding (what the engine stores) moves logits by a bounded amount
+    got_bf = og.forward_last_logits(params, toks, cfg.n_head, cfg.n_vocab, weights_bf16=True)
+    assert np.abs(got_bf - want).max() < 0.05
+
+
+def test_sampler_restatement_properties():
+    k = og.row_key(7, 12345, 2, 3)
+    assert k == og.row_key(7, 12345, 2, 3) and k != og.row_key(7, 12345, 2, 4) and k != og.row_key(7, 12346, 2, 3)
+    g = og.gumbel_noise(k, 50257)
+    assert np.isfinite(g).all() and abs(g.mean() - 0.5772) < 0.02 and abs(g.var() - np.pi ** 2 / 6) < 0.05
+    # Gumbel-max is a categorical sampler: empirical frequencies follow softmax(logits)
+    logits = np.array([0.0, 1.0, 2.0, -1.0])
+    p = np.exp(logits) / np.exp(logits).sum()
+    counts = np.zeros(4)
+    for ep in range(4000):
+        counts[int(np.argmax(og.sample_scores(logits, og.row_key(0, ep, 0, 0))))] += 1
+    assert np.abs(counts / 4000 - p).max() < 0.03
+
+
+def test_init_params_shapes():
+    cfg = GPT2Config.small()
+    assert cfg.matmul_params == 123532032
+    p = init_gpt2_params(GPT2Config(n_layer=2, n_head=2, d_model=128, d_ff=512, n_vocab=300, n_vocab_rows=301, n_pos=32), seed=1)
+    assert p["wte"].shape == (301, 128) and p["layers"][1]["fc2_w"].shape == (512, 128)
