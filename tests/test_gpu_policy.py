@@ -28,18 +28,20 @@ def _small_cfg():
     return GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
 
 
-def _steer_to_letters(params, tok, alpha=12.0, newline_bonus=-1.6):
-    """Make the LM head context-free and concentrated on letter tokens + newline (see test docstring below)."""
+def _steer_to_letters(params, tok, logit=15.0, scale=50.0):
+    """Make the LM head context-free and concentrated on letter tokens + newline: the final LN emits a constant vector
+    scale*u (gamma = 0), the (tied) embedding rows of the 52 letter tokens are set to (logit/scale)*u and the newline row
+    a little higher so that P(newline) = 1/6 per step; every other id keeps its N(0, 0.02) row => logit ~ N(0, 1)."""
     letters = [tok.encode(c)[0] for c in "abcdefghijklmnopqrstuvwxyz"] + [tok.encode("x " + c)[1] for c in "abcdefghijklmnopqrstuvwxyz"]
-    from oracle.gpt2 import bf16_round
-    w = bf16_round(params["wte"]).astype(np.float64)
-    b = np.zeros(w.shape[1])
-    for v in letters:
-        b += alpha * w[v] / (w[v] @ w[v])
-    nl = tok.newline_id()
-    b += (alpha + newline_bonus + np.log(len(letters) / 5.0)) * w[nl] / (w[nl] @ w[nl])
+    d = params["wte"].shape[1]
+    u = np.random.default_rng(123).standard_normal(d)
+    u /= np.linalg.norm(u)
+    wte = params["wte"].copy()
+    wte[letters] = (logit / scale) * u
+    wte[tok.newline_id()] = ((logit + np.log(len(letters) / 5.0)) / scale) * u
+    params["wte"] = wte.astype(np.float32)
     params["lnf_g"] = np.zeros_like(params["lnf_g"])
-    params["lnf_b"] = b.astype(np.float32)
+    params["lnf_b"] = (scale * u).astype(np.float32)
     return params
 
 
