@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of batched Wordle rollouts with a GPT-2-small policy (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one batch of B concurrent episodes run to completion through the hot path
+(obs tokens -> policy.generate -> env.step -> reward, up to 6 turns): exactly what one iteration of the reference's
+``text_env_eval`` batch loop does (LLM_RL/environment.py:223-242).  Prints ONE JSON line (rank 0).
+
+  value      whole-job env-steps/s, device-timed (CUDA events on the engine stream), seeds resident in HBM
+  e2e        the same metric through the public API ``text_env_eval(env, policy, ...)`` with host seeds in and host
+             logs out (H2D + D2H inside the timed region), wall clock
+  roofline   the dominant kernel (bf16 GEMM, tensor-bound): algorithmic FLOPs (2*M*N*K of every launch, live M) /
+             summed launch durations from CUDA events recorded around every launch in the timed region
+  cpu_baseline  the CPU restatement of the reference path (oracle port) on a bounded sample, host cores stated
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+WORKLOAD = "wordle_official(2315 words) x GPT-2-small(random init, seed 0), 6 turns, max_new_tokens=6, max_input_length=256"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    power_w_max=max(power) if power else None, samples=len(sm))
+
+
+def build_policy_params():
+    from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params
+    cfg = GPT2Config.small()
+    return cfg, init_gpt2_params(cfg, seed=0)
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path on all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from oracle.cpu_rollout import run_cpu_wordle
+    cfg, params = build_policy_params()
+    tok = ByteTokenizer.synthetic()
+    bs = args.ref_batch
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_wordle(params, cfg, tok, n_rollouts=4, bsize=4)
+    steps_total, secs = 0, 0.0
+    for k in range(args.steps):
+        r = run_cpu_wordle(params, cfg, tok, n_rollouts=bs, bsize=bs, seed=k)
+        steps_total += r["env_steps"]; secs += r["seconds"]
+    value = steps_total / secs
+    sample = f"{args.steps} x text_env_eval(n_rollouts={bs}, bsize={bs}) episodes of the same workload, prompts padded to the longest in the batch"
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * secs / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload=WORKLOAD, batch_per_step=bs, policy="transformers GPT2LMHeadModel.generate torch-CPU fp32"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample, host_cpus=os.cpu_count()),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="concurrent episodes per GPU")
+    ap.add_argument("--ref-batch", type=int, default=32, help="episodes per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from lmrl_gym_b200 import _lib
+    from lmrl_gym_b200.engine import Engine, ENV_WORDLE
+    from lmrl_gym_b200.environment import text_env_eval
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from oracle.mt19937 import seed_stream   # seeds only: the reference's seed_generator(0) stream (maze/env/randomness.py:35-41)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, W = args.batch, args.steps, max(args.warmup, 0)
+    tok = ByteTokenizer.synthetic()
+    cfg, params = build_policy_params()
+    eng = Engine(max_envs=B, device=local, max_input_length=256, max_new_tokens=6, max_turns=6, tokenizer=tok)
+    env = B200WordleEnv(eng, "wordle_official.txt")
+    pol = B200GPT2Policy(eng, params, cfg, seed=0)
+    sampling = pol.sampling()
+
+    # per-episode seeds: the i-th value of ONE seed_generator(0) stream, sharded contiguously over ranks (no collective)
+    n_steps_total = W + K
+    gen = seed_stream(0)
+    all_seeds = np.asarray([next(gen) for _ in range(n_steps_total * world * B)], dtype=np.uint64).reshape(n_steps_total, world, B)
+    seeds_dev = torch.from_numpy(np.ascontiguousarray(all_seeds[:, rank]).view(np.int64)).cuda()           # resident in HBM before timing
+    ep_len_dev = torch.zeros((K, B), dtype=torch.int32, device="cuda")
+    ep_ret_dev = torch.zeros((K, B), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=torch.device("cuda", local))
+
+    def rollout(step_idx, out_k=None):
+        out = None
+        if out_k is not None:
+            out = _lib.lmrl_rollout_out(ep_ret_dev[out_k].data_ptr(), ep_len_dev[out_k].data_ptr(), None, None, None, None, None, None, None)
+        eng.rollout_dev(ENV_WORDLE, seeds_dev[step_idx].data_ptr(), B, sampling, out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(W):
+        rollout(w)
+    eng.sync()
+    barrier()
+    eng.launch_count(reset=True)
+    eng.profile_enable(True)
+    clocks = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(K):
+        rollout(W + k, k)
+    ev1.record(stream)
+    eng.sync()
+    barrier()
+    clock_info = clocks.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count()
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    env_steps = int(ep_len_dev.sum().item())
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    s = torch.tensor([env_steps, launches], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    total_steps, total_launches = int(s[0].item()), int(s[1].item())
+    value = total_steps / (elapsed_ms / 1000.0)
+
+    # ---- e2e: the public API with host buffers (seeds in, logs out), wall clock, max over ranks
+    e2e_seeds = seed_stream(1000 + rank)
+    text_env_eval(env, pol, n_rollouts=B, seed_generator=e2e_seeds, bsize=B, verbose=False)     # warm
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 0
+    d2h = h2d = 0
+    for _ in range(K):
+        inter, summ = text_env_eval(env, pol, n_rollouts=B, seed_generator=e2e_seeds, bsize=B, verbose=False)
+        e2e_steps += int(round(float(summ["length"]["mean"]) * B))
+        h2d, d2h = inter[0]._logs.h2d_bytes, inter[0]._logs.d2h_bytes
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    s = torch.tensor([e2e_steps], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    e2e_value = float(s.item()) / float(t.item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        gemm_ms, gemm_flops = prof["ms"]["gemm"], prof["work"]["gemm"]
+        achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        total_kernel_ms = sum(prof["ms"].values())
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms / K, higher_is_better=True,
+            scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+            config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world} (episodes sharded, no collective)",
+                        l2_policy="inputs larger than L2 (KV cache %.1f GB per GPU)" % (eng.device_bytes / 1e9), tokenizer=tok.name,
+                        policy_variant="2a: random-init GPT-2-small (actions are malformed guesses; every episode runs 6 turns)"),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api="lmrl_gym_b200.text_env_eval"),
+            gpu_launches=total_launches,
+            clocks=clock_info,
+            roofline=dict(bound="tensor", kernel="gemm_bf16_mma_kernel (mma.sync m16n8k16, all epilogues)", achieved=achieved, peak=peak,
+                          unit="TFLOP/s", frac=achieved / peak, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=None,
+                          flops_per_step=gemm_flops / K, launches_per_step=prof["launches"]["gemm"] / K,
+                          share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None),
+            kernel_ms_per_step={k: v / K for k, v in prof["ms"].items()},
+            decoder_rows_per_step=prof["rows"] / K, sampled_tokens_per_step=prof["sampled"] / K,
+            mean_return=float(ep_ret_dev.mean().item()),
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.cpu_rollout import run_cpu_wordle
+            r = run_cpu_wordle(params, cfg, tok, n_rollouts=args.ref_batch, bsize=args.ref_batch)
+            line["cpu_baseline"] = dict(value=r["env_steps_per_s"], unit=UNIT, cores=r["cores"], kind="port", host_cpus=r["host_cpus"],
+                                        sample=f"text_env_eval(n_rollouts={args.ref_batch}, bsize={args.ref_batch}) of the same workload "
+                                               f"({r['env_steps']} env-steps in {r['seconds']:.1f} s), prompts padded to the longest in the batch")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

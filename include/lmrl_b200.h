@@ -158,8 +158,21 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
 int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, int32_t n, float prob_smart,
                                      uint64_t policy_seed, lmrl_rollout_out* out_dev);
 
-/* counters for bench.py: kernels launched by this engine since the last reset, and last GEMM timing hooks */
+/* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);
+
+/* per-launch device timing for the roofline report: CUDA events are recorded on the engine stream around every kernel
+ * launch while enabled.  Categories: 0 GEMM (tensor), 1 attention, 2 element-wise / bookkeeping, 3 env kernels. */
+#define LMRL_PROF_CATS 4
+typedef struct lmrl_profile_out {
+    double ms[LMRL_PROF_CATS];        /* summed launch durations */
+    double work[LMRL_PROF_CATS];      /* algorithmic FLOPs (cat 0: 2*M*N*K with the live row count M of each launch) */
+    int64_t launches[LMRL_PROF_CATS];
+    int64_t rows;                     /* rows that went through the decoder (prefill + decode) */
+    int64_t sampled;                  /* tokens sampled */
+} lmrl_profile_out;
+int lmrl_profile_enable(lmrl_engine* e, int32_t enable);      /* also clears the records */
+int lmrl_profile_read(lmrl_engine* e, lmrl_profile_out* out); /* synchronises the stream */
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,11 @@ class lmrl_sampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64)]
 
 
+class lmrl_profile_out(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("work", C.c_double * 4), ("launches", C.c_int64 * 4), ("rows", C.c_int64),
+                ("sampled", C.c_int64)]
+
+
 class lmrl_rollout_out(C.Structure):
     _fields_ = [("ep_return", C.c_void_p), ("ep_length", C.c_void_p), ("ep_done", C.c_void_p),
                 ("step_reward", C.c_void_p), ("step_valid", C.c_void_p), ("step_feedback", C.c_void_p),
@@ -73,6 +78,8 @@ SYMBOLS = {
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_wordle_scripted_rollout_dev": (C.c_int, [_V, _V, _I, C.c_float, C.c_uint64, C.POINTER(lmrl_rollout_out)]),
     "lmrl_launch_count": (C.c_int64, [_V, _I]),
+    "lmrl_profile_enable": (C.c_int, [_V, _I]),
+    "lmrl_profile_read": (C.c_int, [_V, C.POINTER(lmrl_profile_out)]),
 }
 
 _lib: Optional[C.CDLL] = None

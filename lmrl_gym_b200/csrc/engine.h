@@ -69,6 +69,32 @@ struct lmrl_engine {
 
     lmrl::Gpt2Dev* gpt2 = nullptr;
 
+    // optional per-launch timing (bench.py): CUDA events around every launch, grouped by category
+    struct ProfRec { int cat; int ev; double work_per_row; int count_slot; };   // work = flops (gemm) per live row
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<ProfRec> prof;
+    int32_t* h_counts = nullptr;      // pinned: [2 * max_passes] (rows, slots) per forward pass
+    int n_passes = 0, max_passes = 0;
+    int cur_pass_slot = -1;
+
+    int prof_begin(int cat, double work_per_row = 0.0, int count_kind = 0) {
+        if (!profile) return 0;
+        const int i = (int)prof.size();
+        while ((int)ev_pool.size() < 2 * (i + 1)) {
+            cudaEvent_t ev;
+            if (cudaEventCreate(&ev) != cudaSuccess) return lmrl::fail("cudaEventCreate failed");
+            ev_pool.push_back(ev);
+        }
+        prof.push_back({cat, 2 * i, work_per_row, cur_pass_slot < 0 ? -1 : 2 * cur_pass_slot + count_kind});
+        cudaEventRecord(ev_pool[2 * i], stream);
+        return 0;
+    }
+    void prof_end() {
+        if (!profile) return;
+        cudaEventRecord(ev_pool[prof.back().ev + 1], stream);
+    }
+
     template <typename T>
     int alloc(T** p, size_t count) {
         void* q = nullptr;

@@ -96,16 +96,26 @@ __global__ void log_turn_kernel(int n, int max_turns, GenDev gen, const int32_t*
 }
 
 template <int EPI>
-static int launch_gemm(lmrl_engine* e, const GemmArgs& g) {
+static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_mma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         configured = true;
     }
+    if (e->prof_begin(0, 2.0 * (double)n_true * (double)g.K, count_kind)) return -1;
     gemm_bf16_mma_kernel<EPI><<<e->gpt2->sm_count * 2, GEMM_THREADS, GEMM_SMEM_BYTES, e->stream>>>(g);
+    e->prof_end();
     e->launches++;
     return 0;
 }
+
+#define LMRL_LAUNCH(cat, ...)              \
+    do {                                   \
+        if (e->prof_begin(cat)) return -1; \
+        __VA_ARGS__;                       \
+        e->prof_end();                     \
+        e->launches++;                     \
+    } while (0)
 
 // One forward pass over the current ragged batch + sampling of one token per contributing env.
 // mode 0 = prefill of un-cached stream tokens, mode 1 = single-token decode.
@@ -115,50 +125,47 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     const lmrl_gpt2_dims& D = G.dims;
     cudaStream_t st = e->stream;
     const int ew_blocks = G.sm_count * 8;
-    build_rows_kernel<<<1, 1024, 0, st>>>(mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
-    e->launches++;
-    if (mode == 0) {
-        fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
-        e->launches++;
+    e->cur_pass_slot = -1;
+    LMRL_LAUNCH(2, build_rows_kernel<<<1, 1024, 0, st>>>(mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+    if (e->profile && e->n_passes < e->max_passes) {      // live row / slot counts of this pass, for the FLOP accounting
+        e->cur_pass_slot = e->n_passes++;
+        cudaMemcpyAsync(e->h_counts + 2 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(e->h_counts + 2 * e->cur_pass_slot + 1, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, st);
     }
-    embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x);
-    e->launches++;
+    if (mode == 0)
+        LMRL_LAUNCH(2, fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+    LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x));
     const size_t att_smem = (size_t)G.t_cap * (ATT_KPITCH * 2 + 64 * 2 + 4 * (ATT_THREADS / 32));
     for (int l = 0; l < D.n_layer; ++l) {
         const LayerDev& L = G.layers[l];
-        layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn);
-        e->launches++;
+        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
         GemmArgs a{};
         a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
         a.out = G.q; a.kcache = G.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
         a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
-        if (launch_gemm<EPI_QKV>(e, a)) return -1;
-        attention_kernel<<<dim3(D.n_head, n_env), ATT_THREADS, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                 0.125f, G.att);
-        e->launches++;
+        if (launch_gemm<EPI_QKV>(e, a, a.N, 0)) return -1;
+        LMRL_LAUNCH(1, attention_kernel<<<dim3(D.n_head, n_env), ATT_THREADS, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model,
+                                                                                                G.t_cap, 0.125f, G.att));
         GemmArgs p{};
         p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, p)) return -1;
-        layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn);
-        e->launches++;
+        if (launch_gemm<EPI_RESID>(e, p, p.N, 0)) return -1;
+        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
         GemmArgs f{};
         f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
-        if (launch_gemm<EPI_GELU>(e, f)) return -1;
+        if (launch_gemm<EPI_GELU>(e, f, f.N, 0)) return -1;
         GemmArgs f2{};
         f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, f2)) return -1;
+        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0)) return -1;
     }
-    layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, G.lnf_g, G.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last, G.xl);
-    e->launches++;
-    prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best);
-    e->launches++;
+    LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, G.lnf_g, G.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last, G.xl));
+    LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
     GemmArgs h{};
     h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
-    if (launch_gemm<EPI_SAMPLE>(e, h)) return -1;
-    finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best);
-    e->launches++;
+    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1)) return -1;
+    LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
+    e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
     return 0;
 }
@@ -317,8 +324,7 @@ int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_t
         LMRL_CUDA(cudaMemcpyAsync(G.episode_key, idx.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
         LMRL_CUDA(cudaStreamSynchronize(e->stream));
     }
-    clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
-    e->launches++;
+    LMRL_LAUNCH(2, clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen));
     for (int k = 0; k < e->cfg.max_new_tokens; ++k)
         if (forward_and_sample(e, k == 0 ? 0 : 1, n, nullptr, nullptr, turn, *s, nullptr)) return -1;
     LMRL_CUDA(cudaMemcpyAsync(out_tokens, G.gen.tok, sizeof(int32_t) * (size_t)n * e->cfg.max_new_tokens, cudaMemcpyDeviceToHost, e->stream));
@@ -363,22 +369,19 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
     const int T = e->cfg.max_turns;
     cudaStream_t st = e->stream;
     const int blocks = (n + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK;
-    wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n);
-    init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, nullptr, seeds_dev, G.episode_key,
-                                                        G.ep_return, G.ep_length, G.ep_done);
-    e->launches += 2;
+    LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
+    LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, nullptr, seeds_dev,
+                                                                       G.episode_key, G.ep_return, G.ep_length, G.ep_done));
     ActionSrc src{};
     src.tokens = G.gen.tok; src.ntokens = G.gen.len; src.tpitch = G.gen.max_new;
     for (int turn = 0; turn < T; ++turn) {
-        clear_gen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, G.gen);
-        e->launches++;
+        LMRL_LAUNCH(2, clear_gen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, G.gen));
         for (int k = 0; k < e->cfg.max_new_tokens; ++k)
             if (forward_and_sample(e, k == 0 ? 0 : 1, n, e->wordle.done, e->wordle.n_actions, 0, s, nullptr)) return -1;
-        wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(e->wordle, e->tok, src, nullptr,
-                                                                                                                  e->step, G.stream, n);
-        log_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, G.gen, e->wordle.n_actions, e->step, G.ep_return, G.ep_length, G.ep_done,
-                                                         G.step_reward, G.step_valid, G.step_fb, G.step_aux, G.act_tokens, G.act_len);
-        e->launches += 2;
+        LMRL_LAUNCH(3, wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(
+                           e->wordle, e->tok, src, nullptr, e->step, G.stream, n));
+        LMRL_LAUNCH(3, log_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, G.gen, e->wordle.n_actions, e->step, G.ep_return, G.ep_length, G.ep_done,
+                                                                        G.step_reward, G.step_valid, G.step_fb, G.step_aux, G.act_tokens, G.act_len));
     }
     LMRL_CUDA(cudaGetLastError());
     return 0;
@@ -424,6 +427,36 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
 
 int lmrl_wordle_scripted_rollout_dev(lmrl_engine*, const uint64_t*, int32_t, float, uint64_t, lmrl_rollout_out*) {
     return lmrl::fail("lmrl_wordle_scripted_rollout_dev: not implemented yet");
+}
+
+int lmrl_profile_enable(lmrl_engine* e, int32_t enable) {
+    LMRL_CHECK(e, "null engine");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    e->profile = enable ? 1 : 0;
+    e->prof.clear();
+    e->n_passes = 0;
+    if (enable && !e->h_counts) {
+        e->max_passes = 1 << 16;
+        LMRL_CUDA(cudaMallocHost(&e->h_counts, sizeof(int32_t) * 2 * e->max_passes));
+    }
+    return 0;
+}
+
+int lmrl_profile_read(lmrl_engine* e, lmrl_profile_out* out) {
+    LMRL_CHECK(e && out, "null argument");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    memset(out, 0, sizeof *out);
+    for (const auto& r : e->prof) {
+        float ms = 0.f;
+        LMRL_CUDA(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev + 1]));
+        out->ms[r.cat] += ms;
+        out->launches[r.cat] += 1;
+        if (r.count_slot >= 0) out->work[r.cat] += r.work_per_row * (double)e->h_counts[r.count_slot];
+    }
+    for (int p = 0; p < e->n_passes; ++p) { out->rows += e->h_counts[2 * p]; out->sampled += e->h_counts[2 * p + 1]; }
+    return 0;
 }
 
 }  // extern "C"

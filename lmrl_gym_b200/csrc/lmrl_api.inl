@@ -46,6 +46,8 @@ int lmrl_destroy(lmrl_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
 
     lmrl_gpt2_free(e);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->h_counts) cudaFreeHost(e->h_counts);
     for (void* p : e->allocs) cudaFree(p);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;

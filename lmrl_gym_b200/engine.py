@@ -56,6 +56,25 @@ class Engine:
                                            ptr(hdr), len(hdr)))
         self.tokenizer = tok
 
+    @property
+    def stream_ptr(self) -> int:
+        return int(self.lib.lmrl_stream(self.handle) or 0)
+
+    def profile_enable(self, enable: bool = True):
+        check(self.lib.lmrl_profile_enable(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        out = _lib.lmrl_profile_out()
+        check(self.lib.lmrl_profile_read(self.handle, C.byref(out)))
+        cats = ("gemm", "attention", "elementwise", "env")
+        return dict(ms={c: out.ms[i] for i, c in enumerate(cats)}, work={c: out.work[i] for i, c in enumerate(cats)},
+                    launches={c: int(out.launches[i]) for i, c in enumerate(cats)}, rows=int(out.rows), sampled=int(out.sampled))
+
+    def rollout_dev(self, env_kind: int, seeds_dev_ptr: int, n: int, sampling, out_struct=None):
+        """Enqueue one fused rollout with seeds already resident in HBM; no host synchronisation."""
+        check(self.lib.lmrl_rollout_dev(self.handle, env_kind, seeds_dev_ptr, None, n, C.byref(sampling),
+                                        None if out_struct is None else C.byref(out_struct)))
+
     def sync(self):
         check(self.lib.lmrl_sync(self.handle))
 
