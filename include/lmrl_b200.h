@@ -161,6 +161,12 @@ int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, 
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);
 
+/* GEMM implementation switch (default 1 = tcgen05/TMEM/TMA; 0 = the mma.sync kernel kept as an independent cross-check)
+ * and a unit-test hook: resid[M,N] += A[M,K] · W[N,K]^T + bias through the chosen implementation (bf16 bit patterns in) */
+int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl);
+int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int32_t K, const uint16_t* A_bf16,
+                        const uint16_t* W_bf16, const float* bias, float* resid_inout);
+
 /* per-launch device timing for the roofline report: CUDA events are recorded on the engine stream around every kernel
  * launch while enabled.  Categories: 0 GEMM (tensor), 1 attention, 2 element-wise / bookkeeping, 3 env kernels. */
 #define LMRL_PROF_CATS 4

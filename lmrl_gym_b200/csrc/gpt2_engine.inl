@@ -7,6 +7,8 @@
 // with fused Gumbel arg-max] x max_new_tokens, then the env step kernel.  Row counts and done masks stay on the
 // device; nothing is copied to the host until the rollout is over.
 #include "gpt2_kernels.cuh"
+#include "gemm_tcgen05.cuh"
+#include <map>
 
 namespace lmrl {
 
@@ -43,6 +45,8 @@ struct Gpt2Dev {
     float* step_reward = nullptr; uint8_t* step_valid = nullptr; uint8_t* step_fb = nullptr; int32_t* step_aux = nullptr;
     int32_t* act_tokens = nullptr; int32_t* act_len = nullptr;
     int sm_count = 148;
+    int gemm_impl = 1;                // 1 = tcgen05/TMEM/TMA (default), 0 = mma.sync cross-check path
+    std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (base pointer, box rows) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
 
@@ -95,18 +99,79 @@ __global__ void log_turn_kernel(int n, int max_turns, GenDev gen, const int32_t*
     ep_done[e] = step.done[e];
 }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LMRL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        LMRL_CHECK(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    const cuuint64_t gdim[2] = {K, rows};
+    const cuuint64_t gstride[1] = {K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LMRL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu K=%llu)", (int)r, (unsigned long long)rows,
+               (unsigned long long)K);
+    return 0;
+}
+
 template <int EPI>
-static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind) {
+static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmArgs& g) {
+    static bool configured = false;
+    if (!configured) {
+        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        configured = true;
+    }
+    gemm_bf16_tcgen05_kernel<EPI><<<sm_count, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, g);
+    return 0;
+}
+
+template <int EPI>
+static int launch_gemm_mma(cudaStream_t st, int sm_count, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_mma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         configured = true;
     }
+    gemm_bf16_mma_kernel<EPI><<<sm_count * 2, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+    return 0;
+}
+
+// a_rows / w_rows: allocated rows behind g.A / g.W (TMA bounds)
+template <int EPI>
+static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind, size_t a_rows, size_t w_rows) {
+    Gpt2Dev& G = *e->gpt2;
+    const bool tc = G.gemm_impl == 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
+    const CUtensorMap *ta = nullptr, *tw = nullptr;
+    if (tc) {
+        auto get = [&](const void* base, size_t rows, uint32_t box_rows) -> const CUtensorMap* {
+            auto key = std::make_pair(base, (int)box_rows);
+            auto it = G.tmaps.find(key);
+            if (it == G.tmaps.end()) {
+                CUtensorMap m;
+                if (make_tmap_bf16(&m, base, rows, (uint64_t)g.K, box_rows)) return nullptr;
+                it = G.tmaps.emplace(key, m).first;
+            }
+            return &it->second;
+        };
+        ta = get(g.A, a_rows, TC_BM);
+        tw = get(g.W, w_rows, TC_BN);
+        if (!ta || !tw) return -1;
+    }
     if (e->prof_begin(0, 2.0 * (double)n_true * (double)g.K, count_kind)) return -1;
-    gemm_bf16_mma_kernel<EPI><<<e->gpt2->sm_count * 2, GEMM_THREADS, GEMM_SMEM_BYTES, e->stream>>>(g);
+    const int rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
     e->prof_end();
     e->launches++;
-    return 0;
+    return rc;
 }
 
 #define LMRL_LAUNCH(cat, ...)              \
@@ -135,7 +200,8 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     if (mode == 0)
         LMRL_LAUNCH(2, fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x));
-    const size_t att_smem = (size_t)G.t_cap * (ATT_KPITCH * 2 + 64 * 2 + 4 * (ATT_THREADS / 32));
+    const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
+    const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     for (int l = 0; l < D.n_layer; ++l) {
         const LayerDev& L = G.layers[l];
         LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
@@ -143,19 +209,19 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
         a.out = G.q; a.kcache = G.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
         a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
-        if (launch_gemm<EPI_QKV>(e, a, a.N, 0)) return -1;
-        LMRL_LAUNCH(1, attention_kernel<<<dim3(D.n_head, n_env), ATT_THREADS, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model,
-                                                                                                G.t_cap, 0.125f, G.att));
+        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N)) return -1;
+        LMRL_LAUNCH(1, attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                        0.125f, G.att));
         GemmArgs p{};
         p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, p, p.N, 0)) return -1;
+        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N)) return -1;
         LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
         GemmArgs f{};
         f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
-        if (launch_gemm<EPI_GELU>(e, f, f.N, 0)) return -1;
+        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N)) return -1;
         GemmArgs f2{};
         f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0)) return -1;
+        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N)) return -1;
     }
     LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, G.lnf_g, G.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last, G.xl));
     LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
@@ -163,7 +229,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
-    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1)) return -1;
+    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, (size_t)(e->cfg.max_envs + 127) / 128 * 128, G.v_pad)) return -1;
     LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
     e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
@@ -198,7 +264,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
         e->alloc(&G.step_valid, (size_t)B * T) || e->alloc(&G.step_fb, (size_t)B * T * 5) || e->alloc(&G.step_aux, (size_t)B * T) ||
         e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
         return -1;
-    const size_t att_smem = (size_t)G.t_cap * (ATT_KPITCH * 2 + 64 * 2 + 4 * (ATT_THREADS / 32));
+    const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
     LMRL_CHECK(att_smem <= 227 * 1024, "max_input_length + max_new_tokens = %d positions do not fit the attention kernel's shared memory", G.t_cap);
     LMRL_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
     return 0;
@@ -238,7 +304,7 @@ int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_w
     }
     Gpt2Dev& G = *e->gpt2;
     const int d = dims->d_model, ff = dims->d_ff, L = dims->n_layer;
-    G.v_pad = (dims->n_vocab + 127) / 128 * 128;
+    G.v_pad = (dims->n_vocab + TC_BN - 1) / TC_BN * TC_BN;   // LM-head rows padded to the widest N tile
     // staging buffer for fp32 uploads
     const size_t stage_elems = std::max((size_t)w->n_vocab_rows * d, (size_t)d * std::max(ff, 3 * d));
     float* stage = nullptr;
@@ -427,6 +493,51 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
 
 int lmrl_wordle_scripted_rollout_dev(lmrl_engine*, const uint64_t*, int32_t, float, uint64_t, lmrl_rollout_out*) {
     return lmrl::fail("lmrl_wordle_scripted_rollout_dev: not implemented yet");
+}
+
+int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl) {
+    LMRL_CHECK(e && e->gpt2, "lmrl_set_gemm_impl: no GPT-2 parameters loaded");
+    LMRL_CHECK(impl == 0 || impl == 1, "lmrl_set_gemm_impl: impl must be 0 (mma.sync) or 1 (tcgen05)");
+    e->gpt2->gemm_impl = impl;
+    return 0;
+}
+
+int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int32_t K, const uint16_t* A_bf16, const uint16_t* W_bf16,
+                        const float* bias, float* resid_inout) {
+    LMRL_CHECK(e && A_bf16 && W_bf16 && resid_inout, "lmrl_test_gemm: null argument");
+    LMRL_CHECK(M > 0 && N % 128 == 0 && K % 64 == 0 && (impl == 0 || N % TC_BN == 0), "lmrl_test_gemm: unsupported shape %d x %d x %d", M, N, K);
+    LMRL_CUDA(cudaSetDevice(e->device));
+    const size_t m_pad = ((size_t)M + 127) / 128 * 128;
+    __nv_bfloat16 *dA = nullptr, *dW = nullptr;
+    float *dB = nullptr, *dR = nullptr;
+    int* dM = nullptr;
+    LMRL_CUDA(cudaMalloc(&dA, m_pad * K * 2)); LMRL_CUDA(cudaMalloc(&dW, (size_t)N * K * 2));
+    LMRL_CUDA(cudaMalloc(&dB, (size_t)N * 4)); LMRL_CUDA(cudaMalloc(&dR, m_pad * N * 4)); LMRL_CUDA(cudaMalloc(&dM, 4));
+    LMRL_CUDA(cudaMemsetAsync(dA, 0, m_pad * K * 2, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(dA, A_bf16, (size_t)M * K * 2, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(dW, W_bf16, (size_t)N * K * 2, cudaMemcpyHostToDevice, e->stream));
+    if (bias) LMRL_CUDA(cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(dR, resid_inout, (size_t)M * N * 4, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(dM, &M, 4, cudaMemcpyHostToDevice, e->stream));
+    GemmArgs g{};
+    g.A = dA; g.W = dW; g.bias = bias ? dB : nullptr; g.N = N; g.K = K; g.M_dev = dM; g.resid = dR;
+    cudaDeviceProp prop;
+    LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
+    int rc = 0;
+    if (impl == 1) {
+        CUtensorMap ta, tw;
+        rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC_BN);
+        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, g);
+    } else {
+        rc = launch_gemm_mma<EPI_RESID>(e->stream, prop.multiProcessorCount, g);
+    }
+    e->launches++;
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    if (!rc && err == cudaSuccess) err = cudaMemcpy(resid_inout, dR, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dR); cudaFree(dM);
+    if (rc) return -1;
+    LMRL_CHECK(err == cudaSuccess, "lmrl_test_gemm: %s", cudaGetErrorString(err));
+    return 0;
 }
 
 int lmrl_profile_enable(lmrl_engine* e, int32_t enable) {

@@ -179,87 +179,104 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
-// ---- K3: causal attention over the slab KV cache, one CTA per (slot, head) ------------------------------------------
-// K/V of the (env, head) are staged once in shared memory (cp.async, K rows padded to 144 B so that a lane-per-key
-// 16-byte read pattern is bank-conflict free) and reused by every row of the slot; each warp owns rows w, w+4, ...
-// Scores: lane = key.  Softmax: warp shuffles.  P·V: lane = pair of head dims.
-constexpr int ATT_THREADS = 128;
-constexpr int ATT_KPITCH = 72;   // bf16 elements per staged K row (64 + 8 pad)
+// ---- K3: causal attention over the slab KV cache, one WARP per (slot, head) ----------------------------------------
+// HBM-bound batched GEMV (~93 % of the decode bytes).  A warp streams the (env, head) K then V slabs
+// straight from global memory with 16-byte loads: lane = (key group g = lane/8, dim chunk s = lane%8), i.e. every
+// load instruction of the warp covers 4 consecutive keys x 128 B = 512 contiguous bytes.  Scores go to a per-warp
+// shared buffer, soft-max is two warp reductions, P·V accumulates 8 dims per lane and is folded across the 4 key
+// groups with shuffles.  During prefill the warp loops over the slot's rows (K/V re-reads hit L1/L2).
+constexpr int ATT_WARPS = 8;
 
-__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
-                                                                const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
-                                                                int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
-    const int slot = blockIdx.y, head = blockIdx.x;
-    if (slot >= *rows.n_slots) return;
-    extern __shared__ __align__(16) unsigned char att_smem[];
-    const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
-    const int ctx = rows.row_pos[r0 + n - 1] + 1;        // keys visible to the slot's last row
-    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);
-    __nv_bfloat16* sV = sK + (size_t)t_cap * ATT_KPITCH;
-    float* sP = reinterpret_cast<float*>(sV + (size_t)t_cap * 64);     // [4 warps][t_cap]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const __nv_bfloat16* gK = kcache + ((size_t)e * n_head + head) * t_cap * 64;
-    const __nv_bfloat16* gV = vcache + ((size_t)e * n_head + head) * t_cap * 64;
-    for (int c = tid; c < ctx * 8; c += ATT_THREADS) {
-        const int j = c >> 3, ch = c & 7;
-        cp_async16(smem_u32(sK + j * ATT_KPITCH + ch * 8), gK + j * 64 + ch * 8);
-        cp_async16(smem_u32(sV + j * 64 + ch * 8), gV + j * 64 + ch * 8);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float f[8]) {
+    f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xFFFF0000u);
+    f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xFFFF0000u);
+    f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xFFFF0000u);
+    f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
 
-    float* myP = sP + warp * t_cap;
-    for (int i = warp; i < n; i += ATT_THREADS / 32) {
-        const int r = r0 + i, p = rows.row_pos[r];
-        // q row (64 dims) in registers as 32 packed pairs, pre-scaled
-        uint32_t qreg[32];
-        const uint4* qsrc = reinterpret_cast<const uint4*>(q + (size_t)r * d_model + head * 64);
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                   const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
+                                                                   int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float att_scores[];                      // [ATT_WARPS][t_cap]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, s = lane & 7;
+    const int total = *rows.n_slots * n_head;
+    float* sc = att_scores + warp * t_cap;
+    for (int w = blockIdx.x * ATT_WARPS + warp; w < total; w += gridDim.x * ATT_WARPS) {
+        const int slot = w / n_head, head = w - slot * n_head;
+        const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
+        const uint4* gK = reinterpret_cast<const uint4*>(kcache + ((size_t)e * n_head + head) * t_cap * 64) + s;   // + j*8 per key
+        const uint4* gV = reinterpret_cast<const uint4*>(vcache + ((size_t)e * n_head + head) * t_cap * 64) + s;
+        for (int i = 0; i < n; ++i) {
+            const int r = r0 + i, nkeys = rows.row_pos[r] + 1;
+            float qf[8];
+            {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(q + (size_t)r * d_model + head * 64) + s);
+                bf16x8_to_float(u, qf);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 u = __ldg(qsrc + c);
-            qreg[4 * c] = u.x; qreg[4 * c + 1] = u.y; qreg[4 * c + 2] = u.z; qreg[4 * c + 3] = u.w;
-        }
-        float mx = -INFINITY;
-        const int nkeys = p + 1;
-        for (int j = lane; j < nkeys; j += 32) {
-            const uint4* kr = reinterpret_cast<const uint4*>(sK + j * ATT_KPITCH);
-            float s = 0.f;
+                for (int t = 0; t < 8; ++t) qf[t] *= scale;
+            }
+            float mx = -INFINITY;
+            for (int j0 = 0; j0 < nkeys; j0 += 16) {
+                uint4 kv[4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 u = kr[c];
-                const uint32_t kk[4] = {u.x, u.y, u.z, u.w};
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 4 * u + g;
+                    kv[u] = j < nkeys ? __ldg(gK + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
+                }
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qreg[4 * c + t]));
-                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk[t]));
-                    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s);
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 4 * u + g;
+                    float kf[8];
+                    bf16x8_to_float(kv[u], kf);
+                    float dot = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) dot = fmaf(qf[t], kf[t], dot);
+                    dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 1);
+                    dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 2);
+                    dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 4);
+                    if (j < nkeys) { if (s == 0) sc[j] = dot; mx = fmaxf(mx, dot); }
                 }
             }
-            s *= scale;
-            myP[j] = s;
-            mx = fmaxf(mx, s);
-        }
+            mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
+            __syncwarp();
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float sum = 0.f;
+            for (int j0 = 0; j0 < nkeys; j0 += 16) {
+                uint4 vv[4];
+                float wgt[4];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-        float sum = 0.f;
-        for (int j = lane; j < nkeys; j += 32) {
-            const float w = __expf(myP[j] - mx);
-            myP[j] = w;
-            sum += w;
-        }
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 4 * u + g;
+                    const bool ok = j < nkeys;
+                    vv[u] = ok ? __ldg(gV + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
+                    wgt[u] = ok ? __expf(sc[j] - mx) : 0.f;
+                }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-        __syncwarp();
-        float o0 = 0.f, o1 = 0.f;
-        for (int j = 0; j < nkeys; ++j) {
-            const float w = myP[j];
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + j * 64 + lane * 2));
-            o0 = fmaf(w, v.x, o0); o1 = fmaf(w, v.y, o1);
+                for (int u = 0; u < 4; ++u) {
+                    float vf[8];
+                    bf16x8_to_float(vv[u], vf);
+                    sum += wgt[u];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) acc[t] = fmaf(wgt[u], vf[t], acc[t]);
+                }
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] += __shfl_xor_sync(0xFFFFFFFFu, acc[t], o);
+            }
+            if (g == 0) {
+                const float inv = 1.0f / sum;
+                __nv_bfloat162 o2[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+                *reinterpret_cast<uint4*>(out + (size_t)r * d_model + head * 64 + s * 8) = *reinterpret_cast<const uint4*>(o2);
+            }
+            __syncwarp();
         }
-        const float inv = 1.0f / sum;
-        *reinterpret_cast<__nv_bfloat162*>(out + (size_t)r * d_model + head * 64 + lane * 2) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-        __syncwarp();
     }
 }
 

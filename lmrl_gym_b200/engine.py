@@ -75,6 +75,21 @@ class Engine:
         check(self.lib.lmrl_rollout_dev(self.handle, env_kind, seeds_dev_ptr, None, n, C.byref(sampling),
                                         None if out_struct is None else C.byref(out_struct)))
 
+    def set_gemm_impl(self, impl: int):
+        """1 = tcgen05/TMEM/TMA (default), 0 = the mma.sync kernel (independent cross-check used by the tests)."""
+        check(self.lib.lmrl_set_gemm_impl(self.handle, int(impl)))
+
+    def test_gemm(self, impl: int, A_bf16, W_bf16, bias, resid):
+        """Unit-test hook: returns resid + A @ W.T + bias computed by the chosen GEMM kernel (A, W as bf16 bit patterns)."""
+        import numpy as np
+        M, K = A_bf16.shape
+        N = W_bf16.shape[0]
+        out = np.ascontiguousarray(resid, dtype=np.float32).copy()
+        check(self.lib.lmrl_test_gemm_host(self.handle, int(impl), M, N, K, ptr(np.ascontiguousarray(A_bf16)),
+                                           ptr(np.ascontiguousarray(W_bf16)), None if bias is None else ptr(np.ascontiguousarray(bias, dtype=np.float32)),
+                                           ptr(out)))
+        return out
+
     def sync(self):
         check(self.lib.lmrl_sync(self.handle))
 
