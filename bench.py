@@ -237,11 +237,13 @@ def main():
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api="lmrl_gym_b200.text_env_eval"),
             gpu_launches=total_launches,
             clocks=clock_info,
-            roofline=dict(bound="tensor", kernel="gemm_bf16_mma_kernel (mma.sync m16n8k16, all epilogues)", achieved=achieved, peak=peak,
+            roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (tcgen05.mma UMMA 128x256x16 + TMA + TMEM, all epilogues)", achieved=achieved, peak=peak,
                           unit="TFLOP/s", frac=achieved / peak, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=None,
                           flops_per_step=gemm_flops / K, launches_per_step=prof["launches"]["gemm"] / K,
                           share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None),
             kernel_ms_per_step={k: v / K for k, v in prof["ms"].items()},
+            gemm_attention_split={k: dict(ms_per_step=round(v["ms"] / K, 3), tflops=round(v["work"] / (v["ms"] / 1000.0) / 1e12, 1) if v["ms"] > 0 and v["work"] > 0 else None)
+                                  for k, v in prof["tags"].items()},
             decoder_rows_per_step=prof["rows"] / K, sampled_tokens_per_step=prof["sampled"] / K,
             mean_return=float(ep_ret_dev.mean().item()),
         )

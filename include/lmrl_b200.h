@@ -174,6 +174,10 @@ typedef struct lmrl_profile_out {
     double ms[LMRL_PROF_CATS];        /* summed launch durations */
     double work[LMRL_PROF_CATS];      /* algorithmic FLOPs (cat 0: 2*M*N*K with the live row count M of each launch) */
     int64_t launches[LMRL_PROF_CATS];
+    /* finer split, index = 2*kind + (0 prefill pass | 1 decode pass); kind: 0 QKV GEMM, 1 attn-proj GEMM, 2 FC GEMM,
+     * 3 FC2 GEMM, 4 LM-head GEMM, 5 attention */
+    double tag_ms[12];
+    double tag_work[12];
     int64_t rows;                     /* rows that went through the decoder (prefill + decode) */
     int64_t sampled;                  /* tokens sampled */
 } lmrl_profile_out;

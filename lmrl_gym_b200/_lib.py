@@ -42,7 +42,8 @@ class lmrl_sampling(C.Structure):
 
 
 class lmrl_profile_out(C.Structure):
-    _fields_ = [("ms", C.c_double * 4), ("work", C.c_double * 4), ("launches", C.c_int64 * 4), ("rows", C.c_int64),
+    _fields_ = [("ms", C.c_double * 4), ("work", C.c_double * 4), ("launches", C.c_int64 * 4), ("tag_ms", C.c_double * 12),
+                ("tag_work", C.c_double * 12), ("rows", C.c_int64),
                 ("sampled", C.c_int64)]
 
 

@@ -70,15 +70,16 @@ struct lmrl_engine {
     lmrl::Gpt2Dev* gpt2 = nullptr;
 
     // optional per-launch timing (bench.py): CUDA events around every launch, grouped by category
-    struct ProfRec { int cat; int ev; double work_per_row; int count_slot; };   // work = flops (gemm) per live row
+    struct ProfRec { int cat; int ev; double work_per_row; int count_slot; int tag; };   // work = flops (gemm) per live row
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<ProfRec> prof;
     int32_t* h_counts = nullptr;      // pinned: [2 * max_passes] (rows, slots) per forward pass
     int n_passes = 0, max_passes = 0;
     int cur_pass_slot = -1;
+    int cur_mode = 0;                 // 0 prefill pass, 1 decode pass (profiling tag)
 
-    int prof_begin(int cat, double work_per_row = 0.0, int count_kind = 0) {
+    int prof_begin(int cat, double work_per_row = 0.0, int count_kind = 0, int tag = -1) {
         if (!profile) return 0;
         const int i = (int)prof.size();
         while ((int)ev_pool.size() < 2 * (i + 1)) {
@@ -86,7 +87,7 @@ struct lmrl_engine {
             if (cudaEventCreate(&ev) != cudaSuccess) return lmrl::fail("cudaEventCreate failed");
             ev_pool.push_back(ev);
         }
-        prof.push_back({cat, 2 * i, work_per_row, cur_pass_slot < 0 ? -1 : 2 * cur_pass_slot + count_kind});
+        prof.push_back({cat, 2 * i, work_per_row, cur_pass_slot < 0 ? -1 : 2 * cur_pass_slot + count_kind, tag});
         cudaEventRecord(ev_pool[2 * i], stream);
         return 0;
     }

@@ -148,7 +148,7 @@ static int launch_gemm_mma(cudaStream_t st, int sm_count, const GemmArgs& g) {
 
 // a_rows / w_rows: allocated rows behind g.A / g.W (TMA bounds)
 template <int EPI>
-static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind, size_t a_rows, size_t w_rows) {
+static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind, size_t a_rows, size_t w_rows, int kind) {
     Gpt2Dev& G = *e->gpt2;
     const bool tc = G.gemm_impl == 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
     const CUtensorMap *ta = nullptr, *tw = nullptr;
@@ -167,19 +167,19 @@ static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_
         tw = get(g.W, w_rows, TC_BN);
         if (!ta || !tw) return -1;
     }
-    if (e->prof_begin(0, 2.0 * (double)n_true * (double)g.K, count_kind)) return -1;
+    if (e->prof_begin(0, 2.0 * (double)n_true * (double)g.K, count_kind, 2 * kind + e->cur_mode)) return -1;
     const int rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
     e->prof_end();
     e->launches++;
     return rc;
 }
 
-#define LMRL_LAUNCH(cat, ...)              \
-    do {                                   \
-        if (e->prof_begin(cat)) return -1; \
-        __VA_ARGS__;                       \
-        e->prof_end();                     \
-        e->launches++;                     \
+#define LMRL_LAUNCH(cat, ...)                          \
+    do {                                               \
+        if ((cat) >= 0 && e->prof_begin(cat)) return -1; \
+        __VA_ARGS__;                                   \
+        e->prof_end();                                 \
+        e->launches++;                                 \
     } while (0)
 
 // One forward pass over the current ragged batch + sampling of one token per contributing env.
@@ -191,6 +191,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     cudaStream_t st = e->stream;
     const int ew_blocks = G.sm_count * 8;
     e->cur_pass_slot = -1;
+    e->cur_mode = mode;
     LMRL_LAUNCH(2, build_rows_kernel<<<1, 1024, 0, st>>>(mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     if (e->profile && e->n_passes < e->max_passes) {      // live row / slot counts of this pass, for the FLOP accounting
         e->cur_pass_slot = e->n_passes++;
@@ -209,19 +210,25 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
         a.out = G.q; a.kcache = G.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
         a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
-        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N)) return -1;
-        LMRL_LAUNCH(1, attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                        0.125f, G.att));
+        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
+        if (e->prof_begin(1, 0.0, 0, 10 + mode)) return -1;
+        if (mode == 0)
+            LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
+                                                       ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                          0.125f * 1.4426950408889634f, G.att));
+        else
+            LMRL_LAUNCH(-1, attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                             0.125f, G.att));
         GemmArgs p{};
         p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N)) return -1;
+        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
         LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
         GemmArgs f{};
         f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
-        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N)) return -1;
+        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
         GemmArgs f2{};
         f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N)) return -1;
+        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
     }
     LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, G.lnf_g, G.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last, G.xl));
     LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
@@ -229,7 +236,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
-    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, (size_t)(e->cfg.max_envs + 127) / 128 * 128, G.v_pad)) return -1;
+    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, (size_t)(e->cfg.max_envs + 127) / 128 * 128, G.v_pad, 4)) return -1;
     LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
     e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
@@ -267,6 +274,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
     LMRL_CHECK(att_smem <= 227 * 1024, "max_input_length + max_new_tokens = %d positions do not fit the attention kernel's shared memory", G.t_cap);
     LMRL_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    LMRL_CUDA(cudaFuncSetAttribute(attention_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTP_WARPS * ATTP_WARP_SMEM));
     return 0;
 }
 
@@ -564,7 +572,9 @@ int lmrl_profile_read(lmrl_engine* e, lmrl_profile_out* out) {
         LMRL_CUDA(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev + 1]));
         out->ms[r.cat] += ms;
         out->launches[r.cat] += 1;
-        if (r.count_slot >= 0) out->work[r.cat] += r.work_per_row * (double)e->h_counts[r.count_slot];
+        const double work = r.count_slot >= 0 ? r.work_per_row * (double)e->h_counts[r.count_slot] : 0.0;
+        out->work[r.cat] += work;
+        if (r.tag >= 0 && r.tag < 12) { out->tag_ms[r.tag] += ms; out->tag_work[r.tag] += work; }
     }
     for (int p = 0; p < e->n_passes; ++p) { out->rows += e->h_counts[2 * p]; out->sampled += e->h_counts[2 * p + 1]; }
     return 0;

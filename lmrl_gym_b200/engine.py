@@ -68,7 +68,10 @@ class Engine:
         check(self.lib.lmrl_profile_read(self.handle, C.byref(out)))
         cats = ("gemm", "attention", "elementwise", "env")
         return dict(ms={c: out.ms[i] for i, c in enumerate(cats)}, work={c: out.work[i] for i, c in enumerate(cats)},
-                    launches={c: int(out.launches[i]) for i, c in enumerate(cats)}, rows=int(out.rows), sampled=int(out.sampled))
+                    launches={c: int(out.launches[i]) for i, c in enumerate(cats)}, rows=int(out.rows), sampled=int(out.sampled),
+                    tags={f"{k}_{m}": dict(ms=out.tag_ms[2 * i + j], work=out.tag_work[2 * i + j])
+                          for i, k in enumerate(("gemm_qkv", "gemm_proj", "gemm_fc", "gemm_fc2", "gemm_head", "attention"))
+                          for j, m in enumerate(("prefill", "decode"))})
 
     def rollout_dev(self, env_kind: int, seeds_dev_ptr: int, n: int, sampling, out_struct=None):
         """Enqueue one fused rollout with seeds already resident in HBM; no host synchronisation."""
