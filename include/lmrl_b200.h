@@ -167,6 +167,11 @@ int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl);
 int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int32_t K, const uint16_t* A_bf16,
                         const uint16_t* W_bf16, const float* bias, float* resid_inout);
 
+/* kernel microbenchmark on the engine's own buffers and layer-0 weights: M synthetic rows (M <= max_envs: one row per
+ * env at position ctx-1, i.e. a decode pass; otherwise M/max_envs rows per env ending at position ctx-1, a prefill pass).
+ * ms_out[8] = mean device time of {QKV, attn-proj, FC, FC2, LM-head+sampler GEMMs, attention, LayerNorm, embed}. */
+int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, float* ms_out);
+
 /* per-launch device timing for the roofline report: CUDA events are recorded on the engine stream around every kernel
  * launch while enabled.  Categories: 0 GEMM (tensor), 1 attention, 2 element-wise / bookkeeping, 3 env kernels. */
 #define LMRL_PROF_CATS 4

@@ -81,6 +81,7 @@ SYMBOLS = {
     "lmrl_launch_count": (C.c_int64, [_V, _I]),
     "lmrl_set_gemm_impl": (C.c_int, [_V, _I]),
     "lmrl_test_gemm_host": (C.c_int, [_V, _I, _I, _I, _I, _V, _V, _V, _V]),
+    "lmrl_bench_kernels": (C.c_int, [_V, _I, _I, _I, _V]),
     "lmrl_profile_enable": (C.c_int, [_V, _I]),
     "lmrl_profile_read": (C.c_int, [_V, C.POINTER(lmrl_profile_out)]),
 }

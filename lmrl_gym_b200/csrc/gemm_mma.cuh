@@ -79,12 +79,15 @@ __device__ __host__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
+// two multiply-fold rounds (Philox-style 32x32 -> 64 products): 2 IMAD.WIDE + 3 LOP3 per draw on the sampling epilogue
 __device__ __host__ __forceinline__ uint32_t noise_bits(uint64_t key, uint32_t col) {
-    uint32_t h = fmix32(col ^ (uint32_t)key);
-    return fmix32(h ^ (uint32_t)(key >> 32));
+    uint64_t p = (uint64_t)(col ^ (uint32_t)key) * 0xD2511F53ull;
+    const uint32_t x = (uint32_t)(p >> 32) ^ (uint32_t)p ^ (uint32_t)(key >> 32);
+    p = (uint64_t)x * 0xCD9E8D57ull;
+    return (uint32_t)(p >> 32) ^ (uint32_t)p;
 }
 __device__ __forceinline__ float gumbel_from_bits(uint32_t h) {
-    const float u = ((float)(h >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u = fmaf((float)(h >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f);
     return -__logf(-__logf(u));
 }
 // order-preserving float -> uint32

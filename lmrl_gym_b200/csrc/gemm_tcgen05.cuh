@@ -7,9 +7,12 @@
 //     quadrant each), synchronised only by mbarriers (full/empty per stage, full/empty per accumulator),
 //   * persistent CTAs, one per SM, striding over 128x256 output tiles; the live row count M is read from device memory.
 //
-// Same epilogues as gemm_mma.cuh (EPI_QKV / EPI_RESID / EPI_GELU / EPI_SAMPLE).  For the three storing epilogues each
-// epilogue warp transposes its 32x32 fp32 chunk through a padded shared-memory tile so that global traffic is
-// row-contiguous (8 lanes x 16 B per row); the sampling epilogue works straight from registers, one row per thread.
+// Same epilogues as gemm_mma.cuh (EPI_QKV / EPI_RESID / EPI_GELU / EPI_SAMPLE).  Dense outputs leave through TMA:
+// each epilogue warp parks a 32-row x 128-byte box in swizzled shared memory and one lane issues
+//   * cp.reduce.async.bulk.tensor ... .add  (fp32 residual stream: x += tile + bias, no read of x by the SM),
+//   * cp.async.bulk.tensor store            (bf16 GeLU output, bf16 Q),
+// double buffered per warp.  K / V tiles of the QKV GEMM are scattered to the KV slab straight from registers
+// (64 contiguous bytes per thread per chunk).  The sampling epilogue works from registers, one row per thread.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -20,12 +23,17 @@
 namespace lmrl {
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+// warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  The storing epilogues use 4 warps (one per TMEM lane quadrant);
+// the sampling epilogue is ALU-heavy (hash + 2 MUFU per logit) and uses 8: warps w and w+4 share a quadrant and split the columns.
+template <int EPI> struct TcCfg {
+    static constexpr int EPI_WARPS = (EPI == 3 /*EPI_SAMPLE*/) ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+};
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_EPI_PITCH = 36;                       // floats per staged row (32 + 4 pad: 16-byte aligned, conflict free)
-constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_PITCH * 4;
+constexpr int TC_EPI_BUF = 32 * 128;                   // one staged box: 32 rows x 128 bytes (128B-swizzled, TMA store source)
+constexpr int TC_EPI_BYTES = 4 * 2 * TC_EPI_BUF;       // 4 epilogue warps x double buffer
 constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
 
@@ -92,42 +100,45 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t r[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// row-contiguous store of one transposed 32x32 chunk: this lane owns 4 consecutive columns of row `row`
-template <int EPI>
-__device__ __forceinline__ void epi_store4(const GemmArgs& g, int row, int col, float4 v) {
-    if (g.bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col));
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    }
-    if constexpr (EPI == EPI_RESID) {
-        float4* p = reinterpret_cast<float4*>(g.resid + (size_t)row * g.N + col);
-        float4 r = *p;
-        r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
-        *p = r;
-    } else {
-        __nv_bfloat162 lo, hi;
-        if constexpr (EPI == EPI_GELU) { lo = __floats2bfloat162_rn(gelu_new(v.x), gelu_new(v.y)); hi = __floats2bfloat162_rn(gelu_new(v.z), gelu_new(v.w)); }
-        else { lo = __floats2bfloat162_rn(v.x, v.y); hi = __floats2bfloat162_rn(v.z, v.w); }
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-        if constexpr (EPI == EPI_GELU) {
-            *reinterpret_cast<uint2*>(g.out + (size_t)row * g.N + col) = pk;
-        } else {   // EPI_QKV
-            const int d = g.d_model;
-            const int part = col / d, c = col - part * d;
-            if (part == 0) *reinterpret_cast<uint2*>(g.out + (size_t)row * d + c) = pk;
-            else {
-                const int e = g.row_env[row], p = g.row_pos[row];
-                __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
-                *reinterpret_cast<uint2*>(cache + (((size_t)e * g.n_head + (c >> 6)) * g.t_cap + p) * 64 + (c & 63)) = pk;
-            }
-        }
-    }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_tc(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// one logit of the sampling epilogue: score = logit/T (+ Gumbel noise), running arg-max (lowest column wins ties)
+template <bool NOISE, bool MASK>
+__device__ __forceinline__ void sample_update(float logit, int col, float inv_temp, uint64_t key, int n_vocab, float& best, int& best_col) {
+    float s = logit * inv_temp;
+    if constexpr (NOISE) s += gumbel_from_bits(noise_bits(key, (uint32_t)col));
+    if constexpr (MASK) s = col < n_vocab ? s : -INFINITY;
+    const bool take = s > best;
+    best = take ? s : best;
+    best_col = take ? col : best_col;
+}
+template <bool NOISE, bool MASK>
+__device__ __forceinline__ void sample_chunk(const uint32_t r[32], int col0, float inv_temp, uint64_t key, int n_vocab, float best[4], int best_col[4]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sample_update<NOISE, MASK>(__uint_as_float(r[j]), col0 + j, inv_temp, key, n_vocab, best[j & 3], best_col[j & 3]);
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                         const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+__global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmW,
+                                                                         const __grid_constant__ CUtensorMap tmOut, const GemmArgs g) {
     extern __shared__ unsigned char tc_smem_raw[];
     const int M = *g.M_dev;
     if (M <= 0) return;
@@ -135,7 +146,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tcgen05_kernel(const 
     const uint32_t base = (raw + 1023u) & ~1023u;                        // 128B swizzle atoms need 1024-byte alignment
     unsigned char* base_ptr = tc_smem_raw + (base - raw);
     const uint32_t epi_base = base + TC_STAGES * TC_STAGE_BYTES;
-    float* epi_ptr = reinterpret_cast<float*>(base_ptr + TC_STAGES * TC_STAGE_BYTES);
     const uint32_t bar_base = epi_base + TC_EPI_BYTES;
     // barrier layout (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -149,10 +159,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tcgen05_kernel(const 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TcCfg<EPI>::EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -204,57 +215,124 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tcgen05_kernel(const 
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue warps 2..: TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
-        float* stg = epi_ptr + (warp - 2) * 32 * TC_EPI_PITCH;
+        const uint32_t stg = epi_base + (uint32_t)((warp - 2) & 3) * 2u * TC_EPI_BUF;     // two 4 KB boxes, 1024-byte aligned
+        uint32_t n_boxes = 0;                                                      // boxes issued by this warp (buffer toggle)
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+            const int row = m0 + quad * 32 + lane;                                 // this thread's output row
             if constexpr (EPI == EPI_SAMPLE) {
-                const int row = m0 + quad * 32 + lane;
+                // warps w and w+4 share the lane quadrant; each takes one 128-column half of the tile
+                const int half = (warp - 2) >> 2;
                 const bool live = row < M;
-                const uint64_t key = (live && g.do_sample) ? g.row_key[row] : 0ull;
-                float best = -INFINITY;
-                int best_col = -1;
+                const uint64_t key = live ? g.row_key[row] : 0ull;
+                const bool masked = n0 + TC_BN > g.n_vocab;                         // only the last N tile has padded columns
+                float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                int best_col[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+#pragma unroll 1
+                for (int c0 = half * (TC_BN / 2); c0 < (half + 1) * (TC_BN / 2); c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_addr + c0, r);
+                    const int col0 = n0 + c0;
+                    if (g.logits_out && live) {                                     // parity hook only
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < g.n_vocab) g.logits_out[(size_t)row * g.n_vocab + col0 + j] = __uint_as_float(r[j]);
+                    }
+                    if (g.do_sample) {
+                        if (masked) sample_chunk<true, true>(r, col0, g.inv_temp, key, g.n_vocab, best, best_col);
+                        else sample_chunk<true, false>(r, col0, g.inv_temp, key, g.n_vocab, best, best_col);
+                    } else {
+                        sample_chunk<false, true>(r, col0, g.inv_temp, key, g.n_vocab, best, best_col);
+                    }
+                }
+#pragma unroll
+                for (int q = 1; q < 4; ++q)
+                    if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
+                if (live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
+            } else if (EPI == EPI_QKV && n0 >= g.d_model) {
+                // K / V tile: scatter this thread's row segment into the KV slab at (env, pos)
+                const bool live = row < M;
+                const int part = n0 / g.d_model;                                   // 1 = K, 2 = V (tiles never straddle: d % 256 == 0)
+                __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
+                size_t base_off = 0;
+                if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
                 for (int c0 = 0; c0 < TC_BN; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_addr + c0, r);
                     if (live) {
+                        const int c = n0 + c0 - part * g.d_model;                  // column inside K (or V): head = c / 64
+                        __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * g.t_cap * 64 + (c & 63);
+                        const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = n0 + c0 + j;
-                            if (col < g.n_vocab) {
-                                const float logit = __uint_as_float(r[j]);
-                                if (g.logits_out) g.logits_out[(size_t)row * g.n_vocab + col] = logit;
-                                float s = logit * g.inv_temp;
-                                if (g.do_sample) s += gumbel_from_bits(noise_bits(key, (uint32_t)col));
-                                if (s > best) { best = s; best_col = col; }
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                            uint4 pk;
+                            pk.x = pack_bf16x2_tc(__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
+                            pk.y = pack_bf16x2_tc(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
+                            pk.z = pack_bf16x2_tc(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
+                            pk.w = pack_bf16x2_tc(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
+                            *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
                         }
                     }
                 }
-                if (live && best_col >= 0) atomicMax(g.best + row, pack_best(best, best_col));
-            } else {
+            } else if constexpr (EPI == EPI_RESID) {
+                // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
                 for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+                    const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
+                    if (lane == 0) bulk_wait_read<1>();                            // the box issued two steps ago has been read
+                    __syncwarp();
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_addr + c0, r);
-                    // lane = row of the quadrant: park the 32 columns, then re-read with lane = (row group, column quad)
+                    const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stg + lane * TC_EPI_PITCH + 4 * j) =
-                            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                    __syncwarp();
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = it * 4 + (lane >> 3), cq = lane & 7;
-                        const float4 v = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_PITCH + 4 * cq);
-                        const int row = m0 + quad * 32 + rr;
-                        if (row < M) epi_store4<EPI>(g, row, n0 + c0 + 4 * cq, v);
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (g.bias) b = __ldg(bias4 + j);
+                        st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + b.x),
+                                     __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y), __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z),
+                                     __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w));
                     }
+                    fence_proxy_async();
                     __syncwarp();
+                    if (lane == 0) { tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + quad * 32); bulk_commit(); }
+                    ++n_boxes;
+                }
+            } else {
+                // bf16 outputs (GeLU, Q): 64-column boxes by TMA store
+                for (int c0 = 0; c0 < TC_BN; c0 += 64) {
+                    const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(t_addr + c0 + 32 * half, r);
+                        const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0 + 32 * half);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {                              // 8 columns -> one 16-byte chunk
+                            const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                            float v[8] = {__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y, __uint_as_float(r[8 * j + 2]) + b0.z,
+                                          __uint_as_float(r[8 * j + 3]) + b0.w, __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
+                                          __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+                            if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
+                            }
+                            const int ch = half * 4 + j;
+                            st_shared_v4(buf + lane * 128 + ((ch ^ (lane & 7)) << 4), pack_bf16x2_tc(v[0], v[1]), pack_bf16x2_tc(v[2], v[3]),
+                                         pack_bf16x2_tc(v[4], v[5]), pack_bf16x2_tc(v[6], v[7]));
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmOut, buf, n0 + c0, m0 + quad * 32); bulk_commit(); }
+                    ++n_boxes;
                 }
             }
             tcgen05_fence_before();
@@ -262,6 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_bf16_tcgen05_kernel(const 
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (lane == 0) bulk_wait_all();                                            // all TMA stores / reductions have landed
     }
     tcgen05_fence_before();
     __syncthreads();

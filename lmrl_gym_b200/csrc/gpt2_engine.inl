@@ -99,11 +99,26 @@ __global__ void log_turn_kernel(int n, int max_turns, GenDev gen, const int32_t*
     ep_done[e] = step.done[e];
 }
 
+// ---- kernel microbenchmark helpers (lmrl_bench_kernels): synthetic row map + random activations ----------------------
+__global__ void bench_rows_kernel(int M, int rpe, int ctx, int n_slots, RowsDev rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) { *rows.M = M; *rows.n_slots = n_slots; }
+    if (r >= M) return;
+    const int e = r / rpe, i = r - e * rpe;
+    rows.row_env[r] = e; rows.row_pos[r] = ctx - rpe + i; rows.row_tok[r] = (r * 7919) % 50000;
+    if (i == 0) { rows.slot_env[e] = e; rows.slot_row0[e] = r; rows.slot_nrow[e] = rpe; rows.slot_last[e] = r + rpe - 1; }
+}
+__global__ void bench_fill_bf16_kernel(__nv_bfloat16* dst, size_t n, uint32_t seed, float scale) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16(scale * ((float)(fmix32((uint32_t)i ^ seed) >> 8) * (2.0f / 16777216.0f) - 1.0f));
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+// 2-D row-major tensor map with a 128-byte-swizzled box of (128 bytes) x box_rows: bf16 -> 64 columns, fp32 -> 32 columns
+static int make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool f32) {
     static PFN_encodeTiled encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -112,26 +127,31 @@ static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
         LMRL_CHECK(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from this driver");
         encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    const cuuint64_t gdim[2] = {K, rows};
-    const cuuint64_t gstride[1] = {K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+    const cuuint64_t esz = f32 ? 4 : 2;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {cols * esz};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    LMRL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu K=%llu)", (int)r, (unsigned long long)rows,
-               (unsigned long long)K);
+    const CUresult r = encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                              gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LMRL_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r, (unsigned long long)rows,
+               (unsigned long long)cols);
     return 0;
+}
+static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    return make_tmap(out, base, rows, K, box_rows, false);
 }
 
 template <int EPI>
-static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmArgs& g) {
+static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut,
+                          const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         configured = true;
     }
-    gemm_bf16_tcgen05_kernel<EPI><<<sm_count, TC_THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, g);
+    gemm_bf16_tcgen05_kernel<EPI><<<sm_count, TcCfg<EPI>::THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, tmOut, g);
     return 0;
 }
 
@@ -151,24 +171,29 @@ template <int EPI>
 static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind, size_t a_rows, size_t w_rows, int kind) {
     Gpt2Dev& G = *e->gpt2;
     const bool tc = G.gemm_impl == 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
-    const CUtensorMap *ta = nullptr, *tw = nullptr;
+    const CUtensorMap *ta = nullptr, *tw = nullptr, *to = nullptr;
     if (tc) {
-        auto get = [&](const void* base, size_t rows, uint32_t box_rows) -> const CUtensorMap* {
-            auto key = std::make_pair(base, (int)box_rows);
+        auto get = [&](const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32) -> const CUtensorMap* {
+            auto key = std::make_pair(base, (int)box_rows | (f32 ? 1 << 16 : 0));
             auto it = G.tmaps.find(key);
             if (it == G.tmaps.end()) {
                 CUtensorMap m;
-                if (make_tmap_bf16(&m, base, rows, (uint64_t)g.K, box_rows)) return nullptr;
+                if (make_tmap(&m, base, rows, cols, box_rows, f32)) return nullptr;
                 it = G.tmaps.emplace(key, m).first;
             }
             return &it->second;
         };
-        ta = get(g.A, a_rows, TC_BM);
-        tw = get(g.W, w_rows, TC_BN);
-        if (!ta || !tw) return -1;
+        ta = get(g.A, a_rows, (size_t)g.K, TC_BM, false);
+        tw = get(g.W, w_rows, (size_t)g.K, TC_BN, false);
+        // output map (TMA store / reduce-add source boxes are 32 rows x 128 bytes); the sampling epilogue stores nothing
+        if (EPI == EPI_RESID) to = get(g.resid, a_rows, (size_t)g.N, 32, true);
+        else if (EPI == EPI_GELU) to = get(g.out, a_rows, (size_t)g.N, 32, false);
+        else if (EPI == EPI_QKV) to = get(g.out, a_rows, (size_t)g.d_model, 32, false);
+        else to = ta;
+        if (!ta || !tw || !to) return -1;
     }
     if (e->prof_begin(0, 2.0 * (double)n_true * (double)g.K, count_kind, 2 * kind + e->cur_mode)) return -1;
-    const int rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
+    const int rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *to, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
     e->prof_end();
     e->launches++;
     return rc;
@@ -533,9 +558,9 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
     LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
     int rc = 0;
     if (impl == 1) {
-        CUtensorMap ta, tw;
-        rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC_BN);
-        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, g);
+        CUtensorMap ta, tw, to;
+        rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC_BN) || make_tmap(&to, dR, m_pad, N, 32, true);
+        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, to, g);
     } else {
         rc = launch_gemm_mma<EPI_RESID>(e->stream, prop.multiProcessorCount, g);
     }
@@ -546,6 +571,80 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
     if (rc) return -1;
     LMRL_CHECK(err == cudaSuccess, "lmrl_test_gemm: %s", cudaGetErrorString(err));
     return 0;
+}
+
+int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, float* ms_out) {
+    LMRL_CHECK(e && e->has_gpt2 && ms_out, "lmrl_bench_kernels: engine without GPT-2 parameters or null output");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    const lmrl_gpt2_dims& D = G.dims;
+    const int B = e->cfg.max_envs;
+    LMRL_CHECK(M > 0 && M <= G.m_cap && (M <= B || M % B == 0), "lmrl_bench_kernels: M=%d must be <= max_envs or a multiple of it (capacity %d)", M, G.m_cap);
+    const int rpe = M <= B ? 1 : M / B, n_slots = M <= B ? M : B;
+    LMRL_CHECK(ctx >= rpe && ctx <= G.t_cap && iters > 0, "lmrl_bench_kernels: ctx=%d must be in [%d, %d]", ctx, rpe, G.t_cap);
+    cudaStream_t st = e->stream;
+    bench_rows_kernel<<<(M + 255) / 256, 256, 0, st>>>(M, rpe, ctx, n_slots, G.rows);
+    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.xn, (size_t)M * D.d_model, 0x1234u, 1.0f);
+    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.att, (size_t)M * D.d_model, 0x2345u, 1.0f);
+    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.q, (size_t)M * D.d_model, 0x3456u, 1.0f);
+    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.h, (size_t)M * D.d_ff, 0x4567u, 1.0f);
+    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.xl, (size_t)n_slots * D.d_model, 0x5678u, 1.0f);
+    LMRL_CUDA(cudaMemsetAsync(G.x, 0, (size_t)M * D.d_model * sizeof(float), st));
+    LMRL_CUDA(cudaMemsetAsync(G.best, 0, sizeof(unsigned long long) * n_slots, st));
+    const LayerDev& L = G.layers[0];
+    GemmArgs a{};
+    a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
+    a.out = G.q; a.kcache = G.kv; a.vcache = a.kcache + G.kv_layer_stride / 2;
+    a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+    GemmArgs p{};
+    p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
+    GemmArgs f{};
+    f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
+    GemmArgs f2{};
+    f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
+    GemmArgs h{};
+    h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
+    h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f; h.do_sample = 1; h.n_vocab = D.n_vocab; h.logits_out = nullptr;
+    const size_t xl_rows = (size_t)(B + 127) / 128 * 128;
+    const int ew_blocks = G.sm_count * 8;
+    const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
+    const int att_blocks = std::min((n_slots * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
+    cudaEvent_t ev[2];
+    LMRL_CUDA(cudaEventCreate(&ev[0])); LMRL_CUDA(cudaEventCreate(&ev[1]));
+    const int saved_profile = e->profile;
+    e->profile = 0;
+    int rc = 0;
+    for (int k = 0; k < 8 && !rc; ++k) {
+        for (int it = -2; it < iters && !rc; ++it) {      // two untimed warm-up launches
+            if (it == 0) cudaEventRecord(ev[0], st);
+            switch (k) {
+                case 0: rc = launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0); break;
+                case 1: rc = launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1); break;
+                case 2: rc = launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2); break;
+                case 3: rc = launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3); break;
+                case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4); break;
+                case 5:
+                    if (rpe > 1)
+                        attention_prefill_kernel<<<std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
+                                                   ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                      0.125f * 1.4426950408889634f, G.att);
+                    else
+                        attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
+                    break;
+                case 6: layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn); break;
+                case 7: embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x); break;
+            }
+        }
+        cudaEventRecord(ev[1], st);
+        cudaError_t err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) { e->profile = saved_profile; return lmrl::fail("lmrl_bench_kernels: kernel %d failed: %s", k, cudaGetErrorString(err)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        ms_out[k] = ms / iters;
+    }
+    e->profile = saved_profile;
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    return rc;
 }
 
 int lmrl_profile_enable(lmrl_engine* e, int32_t enable) {

@@ -93,6 +93,12 @@ class Engine:
                                            ptr(out)))
         return out
 
+    def bench_kernels(self, M: int, ctx: int, iters: int = 20):
+        """Mean device ms of the layer kernels on M synthetic rows (see include/lmrl_b200.h::lmrl_bench_kernels)."""
+        out = np.zeros(8, dtype=np.float32)
+        check(self.lib.lmrl_bench_kernels(self.handle, int(M), int(ctx), int(iters), ptr(out)))
+        return dict(zip(("qkv", "proj", "fc", "fc2", "head", "attention", "layernorm", "embed"), out.tolist()))
+
     def sync(self):
         check(self.lib.lmrl_sync(self.handle))
 

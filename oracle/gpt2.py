@@ -110,10 +110,18 @@ def _fmix32(h: np.ndarray) -> np.ndarray:
     return h
 
 
+def noise_bits(key: int, n_vocab: int) -> np.ndarray:
+    """csrc/gemm_mma.cuh::noise_bits — two multiply-fold rounds keyed by the 64-bit row key."""
+    m32 = np.uint64(0xFFFFFFFF)
+    col = np.arange(n_vocab, dtype=np.uint64)
+    p = ((col ^ np.uint64(key & 0xFFFFFFFF)) & m32) * np.uint64(0xD2511F53)
+    x = ((p >> np.uint64(32)) ^ (p & m32) ^ np.uint64(key >> 32)) & m32
+    p = x * np.uint64(0xCD9E8D57)
+    return (((p >> np.uint64(32)) ^ (p & m32)) & m32).astype(np.uint32)
+
+
 def gumbel_noise(key: int, n_vocab: int) -> np.ndarray:
-    col = np.arange(n_vocab, dtype=np.uint32)
-    h = _fmix32(col ^ np.uint32(key & 0xFFFFFFFF))
-    h = _fmix32(h ^ np.uint32(key >> 32))
+    h = noise_bits(key, n_vocab)
     u = ((h >> np.uint32(8)).astype(np.float64) + 0.5) / 16777216.0
     return -np.log(-np.log(u))
 
