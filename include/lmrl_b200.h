@@ -98,14 +98,35 @@ int lmrl_load_wordle(lmrl_engine* e, const uint32_t* packed_words, int32_t n_wor
                      float bad_word_reward);
 
 /* replaces setup_maze_env / MazeEnv.__init__ (maze/env/maze_utils.py:9-52, env.py:134-159).
- * rewards = {at goal, unknown action, otherwise} (env.py:109-131).  obs_tokens/obs_len: token ids of the observation
- * text for every cell y*W+x (only needed by the fused rollout; may be NULL for the text path). */
+ * rewards = {at goal, unknown action, otherwise} (env.py:109-131).  Fused rollout only (all four may be NULL for the
+ * text path): obs_tokens/obs_len = token ids of the observation sentence of every cell y*W+x for the default goal;
+ * act_tokens [4][8] / act_len [4] = canonical ids of 'move left\n', 'move right\n', 'move up\n', 'move down\n'. */
 int lmrl_load_maze(lmrl_engine* e, const uint8_t* grid, int32_t H, int32_t W, int32_t goal_y, int32_t goal_x,
                    int32_t max_steps, int32_t last_k, const float* rewards3,
-                   const int32_t* obs_tokens, const int32_t* obs_len, int32_t obs_pitch);
+                   const int32_t* obs_tokens, const int32_t* obs_len, int32_t obs_pitch,
+                   const int32_t* act_tokens, const int32_t* act_len);
 
 /* replaces load_params / GPT2PPOPolicy.set_params (ppo/gpt2/interface.py:548-549) */
 int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w);
+
+/* ---- ILQL / MC value-perturbed policy (GPT2ValuePolicy, value_rl_base/gpt2/interface.py:281-320) ----------------------
+ * params tuple of the reference = (pi_beta, base, q1_head, q2_head-or-None) (value_rl_base/gpt2/interface.py:101):
+ *   tower 0 = pi_beta, tower 1 = the value base (same architecture, own KV cache), then the Q heads.
+ * Every sampled token uses  logits = pi_beta_logits + beta * min(q1(h), q2(h)),  h = last hidden state (after ln_f) of the
+ * value base (generation.py:87-119);  q_k(h) = dense2_k(relu(dense1_k(h)))  (heads/mlp_head.py:139-148). */
+int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w);
+typedef struct lmrl_mlp_head {
+    const float* w1;   /* [d_model, hidden]  dense1.kernel */
+    const float* b1;   /* [hidden] */
+    const float* w2;   /* [hidden, n_out]    dense2.kernel (n_out >= n_vocab; extra columns are ignored) */
+    const float* b2;   /* [n_out] */
+    int32_t hidden;
+    int32_t n_out;
+} lmrl_mlp_head;
+/* q2 may be NULL (MC returns: one head, wordle/mc/eval_mc_gpt2.py:103-116).  Switches the engine to the value-perturbed policy. */
+int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_head* q2, float beta);
+/* 0 = plain LM policy (logits of tower 0), 1 = value-perturbed policy */
+int lmrl_set_policy_kind(lmrl_engine* e, int32_t kind);
 
 /* ---- environments, text path (BatchedTextEnv.reset / .step, environment.py:56-69) ------------------------------- */
 /* seeds: one uint64 per env (abs(seed) of random.Random(seed), wordle/env/env.py:53) */
@@ -144,7 +165,7 @@ typedef struct lmrl_rollout_out {      /* all HOST pointers for _host, DEVICE po
     float* step_reward;     /* [n][max_turns] */
     uint8_t* step_valid;    /* [n][max_turns] */
     uint8_t* step_feedback; /* [n][max_turns][5]  (Wordle) */
-    int32_t* step_aux;      /* [n][max_turns]  Wordle: filtered size; Maze: cell index after the step */
+    int32_t* step_aux;      /* [n][max_turns]  Wordle: filtered size; Maze: outcome | cell_after << 8 | cell_before << 20 */
     int32_t* act_tokens;    /* [n][max_turns][max_new_tokens]  sampled ids per turn */
     int32_t* act_len;       /* [n][max_turns] */
 } lmrl_rollout_out;

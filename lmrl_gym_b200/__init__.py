@@ -23,7 +23,7 @@ def __getattr__(name):
     if name == "B200MazeEnv":
         from .maze import B200MazeEnv
         return B200MazeEnv
-    if name in ("B200GPT2Policy", "GPT2Config", "init_gpt2_params"):
+    if name in ("B200GPT2Policy", "B200GPT2ValuePolicy", "GPT2Config", "init_gpt2_params", "init_mlp_head_params"):
         from . import gpt2
         return getattr(gpt2, name)
     raise AttributeError(name)

@@ -37,6 +37,10 @@ class lmrl_gpt2_weights(C.Structure):
                 ("lnf_g", _PF), ("lnf_b", _PF)]
 
 
+class lmrl_mlp_head(C.Structure):
+    _fields_ = [("w1", _PF), ("b1", _PF), ("w2", _PF), ("b2", _PF), ("hidden", C.c_int32), ("n_out", C.c_int32)]
+
+
 class lmrl_sampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64)]
 
@@ -66,8 +70,11 @@ SYMBOLS = {
     "lmrl_stream": (_V, [_V]),
     "lmrl_load_tokenizer": (C.c_int, [_V, _V, _V, _I, _V, _V, _V, _I, _I, _V, _I]),
     "lmrl_load_wordle": (C.c_int, [_V, _V, _I, _I, C.c_float]),
-    "lmrl_load_maze": (C.c_int, [_V, _V, _I, _I, _I, _I, _I, _I, _V, _V, _V, _I]),
+    "lmrl_load_maze": (C.c_int, [_V, _V, _I, _I, _I, _I, _I, _I, _V, _V, _V, _I, _V, _V]),
     "lmrl_load_gpt2": (C.c_int, [_V, C.POINTER(lmrl_gpt2_dims), C.POINTER(lmrl_gpt2_weights)]),
+    "lmrl_load_gpt2_tower": (C.c_int, [_V, _I, C.POINTER(lmrl_gpt2_dims), C.POINTER(lmrl_gpt2_weights)]),
+    "lmrl_load_q_heads": (C.c_int, [_V, C.POINTER(lmrl_mlp_head), C.POINTER(lmrl_mlp_head), C.c_float]),
+    "lmrl_set_policy_kind": (C.c_int, [_V, _I]),
     "lmrl_wordle_reset_host": (C.c_int, [_V, _V, _I]),
     "lmrl_wordle_step_host": (C.c_int, [_V, _V, _V, _I, _V, _I, _V, _V, _V, _V, _V]),
     "lmrl_maze_reset_host": (C.c_int, [_V, _V, _V, _V, _I, _V, _V]),

@@ -49,7 +49,19 @@ struct MazeDev {
     int32_t* goal;                // [B][2]
     int32_t* num_steps;           // [B]
     uint8_t* done;                // [B]
+    // fused rollout only: canonical token ids of the closed text set + the sliding last_k window over history items
+    const int32_t* obs_tokens;    // [H*W][obs_pitch] observation sentence of every cell (default goal)
+    const int32_t* obs_len;       // [H*W]
+    int32_t obs_pitch;
+    const int32_t* act_tokens;    // [4][MAZE_ACT_PITCH] canonical ids of 'move left\n' ... (what re-tokenising the history gives)
+    const int32_t* act_len;       // [4]
+    int32_t* item_len;            // [B][MAZE_RING] token length of every history item inside the window, oldest first
+    int32_t* n_items;             // [B]
+    int32_t* cut;                 // [B] leading tokens of the window that LEFT truncation removed from the stream
 };
+constexpr int MAZE_RING = 72;     // last_k <= 64 items (+ the action / observation pair being appended)
+constexpr int MAZE_ACT_PITCH = 8;
+constexpr int MAZE_ACT_BYTES = 64;
 
 // step outputs (one row per env)
 struct StepOut {
@@ -304,6 +316,115 @@ __global__ void maze_step_kernel(MazeDev m, ActionSrc src, const uint8_t* __rest
     out.valid[e] = a >= 0;
     out.aux[e] = r.outcome;
     if (action_id) action_id[e] = a;
+}
+
+// ---- fused Maze loop (policy tokens in, policy tokens out; maze/env/env.py:161-184 + the policy-side string handling) ----
+// window bookkeeping: remove `n_drop` oldest items from the stream of env e (tokens already cut by truncation are accounted first)
+__device__ __forceinline__ int maze_drop_items(MazeDev& m, int e, int n_drop, int32_t* row, int len) {
+    int32_t* il = m.item_len + (size_t)e * MAZE_RING;
+    int n = m.n_items[e], cut = m.cut[e], removed = 0;
+    for (int i = 0; i < n_drop && i < n; ++i) {
+        const int L = il[i];
+        const int gone = min(cut, L);                  // part of this item that truncation had already removed
+        cut -= gone;
+        removed += L - gone;
+    }
+    for (int i = n_drop; i < n; ++i) il[i - n_drop] = il[i];
+    m.n_items[e] = max(n - n_drop, 0);
+    m.cut[e] = cut;
+    if (removed > 0) for (int i = removed; i < len; ++i) row[i - removed] = row[i];
+    return len - removed;
+}
+
+// after maze_reset_kernel: the policy's first prompt is the observation of the start cell (env.py:204-214)
+__global__ void maze_init_stream_kernel(MazeDev m, StreamDev st, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int cell = m.pos[e * 2] * m.cfg.W + m.pos[e * 2 + 1];
+    const int L = m.obs_len[cell];
+    int32_t* row = st.tokens + (size_t)e * st.cap;
+    for (int i = 0; i < L; ++i) row[i] = m.obs_tokens[(size_t)cell * m.obs_pitch + i];
+    int len = L;
+    m.item_len[(size_t)e * MAZE_RING] = L; m.n_items[e] = 1; m.cut[e] = 0;
+    if (len > st.max_input) {
+        const int drop = len - st.max_input;
+        for (int i = 0; i < st.max_input; ++i) row[i] = row[i + drop];
+        len = st.max_input; m.cut[e] = drop;
+    }
+    st.len[e] = len; st.kv_len[e] = 0;
+}
+
+// one env per thread: sampled ids -> action text (decode, `removesuffix('\n') + '\n'` as every reference driver's
+// out_str_process) -> MazeEnv.step -> next prompt window (last_k items, unknown action collapses to the observation)
+__global__ void maze_fused_step_kernel(MazeDev m, TokenizerDev tk, ActionSrc src, StepOut out, StreamDev st, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (m.done[e]) return;
+    uint8_t bytes[MAZE_ACT_BYTES + 2];
+    int nb = 0;
+    bool overflow = false;
+    const int nt = src.ntokens[e];
+    for (int k = 0; k < nt; ++k) {
+        const int t = src.tokens[(size_t)e * src.tpitch + k];
+        if (t < 0 || t >= tk.n_tokens) continue;
+        for (int o = tk.offsets[t]; o < tk.offsets[t + 1]; ++o) {
+            if (nb < MAZE_ACT_BYTES) bytes[nb++] = tk.token_bytes[o];
+            else overflow = true;
+        }
+    }
+    if (nb == 0 || bytes[nb - 1] != (uint8_t)'\n') bytes[nb++] = (uint8_t)'\n';
+    const int a = overflow ? -1 : maze_match_action(bytes, nb);
+    const int steps = m.num_steps[e];
+    const int cell0 = m.pos[e * 2] * m.cfg.W + m.pos[e * 2 + 1];
+    const MazeStep r = maze_step(m.cfg, m.grid, m.pos[e * 2], m.pos[e * 2 + 1], m.goal[e * 2], m.goal[e * 2 + 1], steps, a);
+    m.pos[e * 2] = r.y; m.pos[e * 2 + 1] = r.x;
+    if (r.outcome == 0) m.num_steps[e] = steps + 1;
+    m.done[e] = (uint8_t)r.done;
+    const int cell = r.y * m.cfg.W + r.x;
+    out.reward[e] = r.reward;
+    out.done[e] = (uint8_t)r.done;
+    out.valid[e] = a >= 0;
+    out.aux[e] = r.outcome | (cell << 8) | (cell0 << 20);
+    for (int i = 0; i < 5; ++i) out.fb[e * 5 + i] = 255;
+    if (r.done) return;
+    int32_t* row = st.tokens + (size_t)e * st.cap;
+    int32_t* il = m.item_len + (size_t)e * MAZE_RING;
+    const int oL = m.obs_len[cell];
+    const int32_t* obs = m.obs_tokens + (size_t)cell * m.obs_pitch;
+    int len = st.len[e], kv;
+    if (a < 0) {                                        // env.py:179-180: the history collapses to the new observation
+        for (int i = 0; i < oL; ++i) row[i] = obs[i];
+        len = oL; il[0] = oL; m.n_items[e] = 1; m.cut[e] = 0; kv = 0;
+    } else {
+        kv = len;                                       // everything before the action keeps its KV entries
+        const int aL = m.act_len[a];
+        for (int i = 0; i < aL; ++i) row[len + i] = m.act_tokens[a * MAZE_ACT_PITCH + i];
+        len += aL;
+        for (int i = 0; i < oL; ++i) row[len + i] = obs[i];
+        len += oL;
+        int ni = m.n_items[e];
+        il[ni] = aL; il[ni + 1] = oL; ni += 2;
+        m.n_items[e] = ni;
+        if (ni > m.cfg.last_k) {                        // env.py:183 new_history[-last_k:]
+            len = maze_drop_items(m, e, ni - m.cfg.last_k, row, len);
+            kv = 0;                                     // positions restart at the new window start
+        }
+    }
+    if (len > st.max_input) {                           // LEFT truncation of the policy input (BlockingStrategy)
+        const int drop = len - st.max_input;
+        for (int i = 0; i < st.max_input; ++i) row[i] = row[i + drop];
+        len = st.max_input; m.cut[e] += drop; kv = 0;
+    }
+    st.len[e] = len; st.kv_len[e] = kv;
+}
+
+// live-episode count for the periodic early-exit test of long rollouts
+__global__ void count_live_kernel(const uint8_t* __restrict__ done, int n, int* __restrict__ live) {
+    int c = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) c += done[e] ? 0 : 1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(live, c);
 }
 
 }  // namespace lmrl

@@ -19,7 +19,7 @@
 
 namespace lmrl {
 
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_SAMPLE = 3 };
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_SAMPLE = 3, EPI_RELU = 4 };   // EPI_RELU: tcgen05 kernel only
 
 struct GemmArgs {
     const __nv_bfloat16* A;      // [Mcap, K]
@@ -44,6 +44,17 @@ struct GemmArgs {
     int do_sample;
     int n_vocab;
     float* logits_out;           // optional [rows, n_vocab] fp32 dump (parity hook)
+    // ---- tcgen05 kernel only ----
+    // K segments: the mainloop runs n_seg segments per output tile; segment s multiplies kb_count 64-wide k-blocks of
+    // A starting at k-block a_kb0 with W matrix w_idx (one of up to three [N, K_w] matrices, k-blocks from 0) into
+    // accumulator acc.  An ordinary GEMM is one segment {0, 0, 0, K/64}.  The value-perturbed sampler
+    // (value_rl_base/gpt2/generation.py:112-119) uses A = [h_pi | beta*relu1 | beta*relu2] and two accumulators:
+    //   acc0 = h_pi·wte^T + beta*q1,  acc1 = h_pi·wte^T + beta*q2,  logit = min(acc0 + bias, acc1 + bias2).
+    struct Seg { int acc, a_kb0, w_idx, kb_count; } seg[4];
+    int n_seg, n_acc;
+    const float* bias2;          // bias of accumulator 1 (EPI_SAMPLE with n_acc == 2)
+    int out_col0;                // EPI_RELU / EPI_GELU: column offset of the output box inside the tmOut tensor
+    float out_scale;             // EPI_RELU: out = out_scale * relu(acc + bias)
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 3, GEMM_THREADS = 256;

@@ -7,7 +7,11 @@
 //     quadrant each), synchronised only by mbarriers (full/empty per stage, full/empty per accumulator),
 //   * persistent CTAs, one per SM, striding over 128x256 output tiles; the live row count M is read from device memory.
 //
-// Same epilogues as gemm_mma.cuh (EPI_QKV / EPI_RESID / EPI_GELU / EPI_SAMPLE).  Dense outputs leave through TMA:
+// The mainloop is a list of K segments (GemmArgs::seg): each segment streams k-blocks of A against one of up to three
+// W matrices into one of up to two TMEM accumulators, which is how the ILQL / MC value-perturbed sampler
+// (logits = pi_beta + beta * min(q1, q2)) runs as ONE kernel: acc0 = [h_pi | b*r1]·[wte | W2_1]^T, acc1 = [h_pi | b*r2]·[wte | W2_2]^T.
+//
+// Same epilogues as gemm_mma.cuh (EPI_QKV / EPI_RESID / EPI_GELU / EPI_SAMPLE) plus EPI_RELU.  Dense outputs leave through TMA:
 // each epilogue warp parks a 32-row x 128-byte box in swizzled shared memory and one lane issues
 //   * cp.reduce.async.bulk.tensor ... .add  (fp32 residual stream: x += tile + bias, no read of x by the SM),
 //   * cp.async.bulk.tensor store            (bf16 GeLU output, bf16 Q),
@@ -26,7 +30,7 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 1
 // warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  The storing epilogues use 4 warps (one per TMEM lane quadrant);
 // the sampling epilogue is ALU-heavy (hash + 2 MUFU per logit) and uses 8: warps w and w+4 share a quadrant and split the columns.
 template <int EPI> struct TcCfg {
-    static constexpr int EPI_WARPS = (EPI == 3 /*EPI_SAMPLE*/) ? 8 : 4;
+    static constexpr int EPI_WARPS = (EPI == EPI_SAMPLE) ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
@@ -137,8 +141,11 @@ __device__ __forceinline__ void sample_chunk(const uint32_t r[32], int col0, flo
 
 template <int EPI>
 __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                         const __grid_constant__ CUtensorMap tmW,
-                                                                         const __grid_constant__ CUtensorMap tmOut, const GemmArgs g) {
+                                                                                   const __grid_constant__ CUtensorMap tmW,
+                                                                                   const __grid_constant__ CUtensorMap tmW1,
+                                                                                   const __grid_constant__ CUtensorMap tmW2,
+                                                                                   const __grid_constant__ CUtensorMap tmOut,
+                                                                                   const GemmArgs g) {
     extern __shared__ unsigned char tc_smem_raw[];
     const int M = *g.M_dev;
     if (M <= 0) return;
@@ -155,7 +162,8 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC_STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = g.N / TC_BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = n_tiles * m_tiles, kt = g.K / TC_BK;
+    const int n_tiles = g.N / TC_BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = n_tiles * m_tiles;
+    const int n_acc = g.n_acc, n_stage = n_acc == 2 ? 1 : 2;          // TMEM: 512 columns = n_stage x n_acc accumulators of 256
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -163,6 +171,10 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        if (g.n_seg > 1) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+        }
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
     }
     if (warp == 1) {
@@ -180,13 +192,17 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
-                for (int kb = 0; kb < kt; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-                    const uint32_t sA = base + stage * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
-                    tma_load_2d(sA, &tmA, full_bar(stage), kb * TC_BK, m0);
-                    tma_load_2d(sB, &tmW, full_bar(stage), kb * TC_BK, n0);
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                for (int sg = 0; sg < g.n_seg; ++sg) {
+                    const CUtensorMap* tw = g.seg[sg].w_idx == 0 ? &tmW : (g.seg[sg].w_idx == 1 ? &tmW1 : &tmW2);
+                    const int a_kb0 = g.seg[sg].a_kb0, nkb = g.seg[sg].kb_count;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+                        const uint32_t sA = base + stage * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
+                        tma_load_2d(sA, &tmA, full_bar(stage), (a_kb0 + kb) * TC_BK, m0);
+                        tma_load_2d(sB, tw, full_bar(stage), kb * TC_BK, n0);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
                 }
             }
         }
@@ -196,22 +212,27 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);               // epilogue has drained this accumulator
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);               // epilogue has drained this accumulator stage
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
-                for (int kb = 0; kb < kt; ++kb) {
-                    mbar_wait(full_bar(stage), phase);                    // TMA bytes have landed
-                    tcgen05_fence_after();
-                    const uint32_t sA = base + stage * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
-                    const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
+                uint32_t started = 0;                                     // bit a: accumulator a already holds a partial sum
+                for (int sg = 0; sg < g.n_seg; ++sg) {
+                    const int a = g.seg[sg].acc, nkb = g.seg[sg].kb_count;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((acc * n_acc + a) * TC_BN);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(full_bar(stage), phase);                // TMA bytes have landed
+                        tcgen05_fence_after();
+                        const uint32_t sA = base + stage * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
+                        const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)           // +32 bytes per UMMA_K step inside the swizzle atom
-                        tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC, (kb | k) ? 1u : 0u);
-                    tcgen05_commit(empty_bar(stage));                     // frees the smem slot when these MMAs retire
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                        for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)       // +32 bytes per UMMA_K step inside the swizzle atom
+                            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC, (((started >> a) & 1u) | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
+                        tcgen05_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    started |= 1u << a;
                 }
-                tcgen05_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                tcgen05_commit(tfull_bar(acc));                           // accumulators complete -> epilogue
+                if (++acc == n_stage) { acc = 0; acc_phase ^= 1u; }
             }
         }
     } else {
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
             const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_acc * TC_BN);
             const int row = m0 + quad * 32 + lane;                                 // this thread's output row
             if constexpr (EPI == EPI_SAMPLE) {
                 // warps w and w+4 share the lane quadrant; each takes one 128-column half of the tile
@@ -239,6 +260,16 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_addr + c0, r);
                     const int col0 = n0 + c0;
+                    if (g.bias) {                                                   // value-perturbed sampler: + beta * b2 of the Q head(s)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(g.bias + col0 + j));
+                    }
+                    if (n_acc == 2) {                                               // logit = min over the two Q heads
+                        uint32_t r2[32];
+                        tmem_ld_32x32b_x32(t_addr + TC_BN + c0, r2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fminf(__uint_as_float(r[j]), __uint_as_float(r2[j]) + __ldg(g.bias2 + col0 + j)));
+                    }
                     if (g.logits_out && live) {                                     // parity hook only
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
@@ -324,6 +355,10 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
                             }
+                            if constexpr (EPI == EPI_RELU) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v[q] = g.out_scale * fmaxf(v[q], 0.f);
+                            }
                             const int ch = half * 4 + j;
                             st_shared_v4(buf + lane * 128 + ((ch ^ (lane & 7)) << 4), pack_bf16x2_tc(v[0], v[1]), pack_bf16x2_tc(v[2], v[3]),
                                          pack_bf16x2_tc(v[4], v[5]), pack_bf16x2_tc(v[6], v[7]));
@@ -331,14 +366,14 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d(&tmOut, buf, n0 + c0, m0 + quad * 32); bulk_commit(); }
+                    if (lane == 0) { tma_store_2d(&tmOut, buf, g.out_col0 + n0 + c0, m0 + quad * 32); bulk_commit(); }
                     ++n_boxes;
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (++acc == n_stage) { acc = 0; acc_phase ^= 1u; }
         }
         if (lane == 0) bulk_wait_all();                                            // all TMA stores / reductions have landed
     }

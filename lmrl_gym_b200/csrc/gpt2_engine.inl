@@ -18,20 +18,42 @@ struct LayerDev {
     float *b_qkv, *b_proj, *b_fc, *b_fc2;
 };
 
+// one GPT-2 parameter set + its KV slab.  Tower 0 = the sampled policy (PPO / BC policy, or pi_beta of ILQL / MC);
+// tower 1 = the value base of ILQL / MC (value_rl_base/gpt2/generation.py:77-88), same architecture, own KV cache.
+struct TowerDev {
+    bool loaded = false;
+    __nv_bfloat16 *wte = nullptr, *wpe = nullptr;
+    float *lnf_g = nullptr, *lnf_b = nullptr;
+    std::vector<LayerDev> layers;
+    __nv_bfloat16* kv = nullptr;      // [L][2][B][H][t_cap][64]
+};
+
+// Q heads of the value-perturbed policy: MLPHead = dense2(relu(dense1(h))) (heads/mlp_head.py:139-148), one or two of them
+struct QHeadsDev {
+    int n_q = 0, hidden = 0;
+    float beta = 0.f;
+    __nv_bfloat16* w1cat = nullptr;   // [n_q * hidden][d]   dense1 kernels, transposed, stacked along N
+    float* b1cat = nullptr;           // [n_q * hidden]
+    __nv_bfloat16* w2[2] = {nullptr, nullptr};   // [v_pad][hidden]  dense2 kernel, transposed, zero-padded rows
+    float* b2s[2] = {nullptr, nullptr};          // [v_pad]  beta * dense2 bias
+};
+
 struct Gpt2Dev {
     lmrl_gpt2_dims dims{};
     int v_pad = 0;            // LM-head rows padded to a multiple of 128
     int t_cap = 0;            // KV positions per env
     int m_cap = 0;            // row capacity of the activation buffers
     int stream_cap = 0;
-    __nv_bfloat16 *wte = nullptr, *wpe = nullptr;
-    float *lnf_g = nullptr, *lnf_b = nullptr;
-    std::vector<LayerDev> layers;
-    __nv_bfloat16* kv = nullptr;      // [L][2][B][H][t_cap][64]
+    TowerDev tw[2];
+    QHeadsDev qh;
+    int policy_kind = 0;              // 0 = LM policy (logits of tower 0); 1 = value-perturbed (pi_beta + beta * min q)
     size_t kv_layer_stride = 0;       // elements between layers (covers K and V)
     // activations
     float* x = nullptr;
-    __nv_bfloat16 *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *xl = nullptr;
+    // xl: [B_pad][3 d] = [final-LN hidden of tower 0 | beta*relu(dense1) of Q head 1 | of Q head 2] (A operand of the sampler);
+    // xl1: [B_pad][d] final-LN hidden of the value tower
+    __nv_bfloat16 *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *xl = nullptr, *xl1 = nullptr;
+    int xl_cols = 0;
     RowsDev rows{};
     GenDev gen{};
     StreamDev stream{};
@@ -44,21 +66,23 @@ struct Gpt2Dev {
     float* ep_return = nullptr; int32_t* ep_length = nullptr; uint8_t* ep_done = nullptr;
     float* step_reward = nullptr; uint8_t* step_valid = nullptr; uint8_t* step_fb = nullptr; int32_t* step_aux = nullptr;
     int32_t* act_tokens = nullptr; int32_t* act_len = nullptr;
+    int* live = nullptr;              // [1] scratch of the early-exit test
     int sm_count = 148;
     int gemm_impl = 1;                // 1 = tcgen05/TMEM/TMA (default), 0 = mma.sync cross-check path
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (base pointer, box rows) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
 
-__global__ void transpose_to_bf16_kernel(const float* __restrict__ src, int K, int N, __nv_bfloat16* __restrict__ dst) {
-    // src [K][N] fp32 (HF Conv1D layout) -> dst [N][K] bf16
+__global__ void transpose_to_bf16_kernel(const float* __restrict__ src, int K, int N, __nv_bfloat16* __restrict__ dst, int n_take = -1) {
+    // src [K][N] fp32 (HF Conv1D / flax Dense layout) -> dst [N][K] bf16; only the first n_take columns of src when n_take >= 0
     __shared__ float tile[32][33];
     const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int n_lim = n_take >= 0 ? n_take : N;
     for (int i = threadIdx.y; i < 32; i += blockDim.y)
-        if (k0 + i < K && n0 + threadIdx.x < N) tile[i][threadIdx.x] = src[(size_t)(k0 + i) * N + n0 + threadIdx.x];
+        if (k0 + i < K && n0 + threadIdx.x < n_lim) tile[i][threadIdx.x] = src[(size_t)(k0 + i) * N + n0 + threadIdx.x];
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y)
-        if (n0 + i < N && k0 + threadIdx.x < K) dst[(size_t)(n0 + i) * K + k0 + threadIdx.x] = __float2bfloat16(tile[threadIdx.x][i]);
+        if (n0 + i < n_lim && k0 + threadIdx.x < K) dst[(size_t)(n0 + i) * K + k0 + threadIdx.x] = __float2bfloat16(tile[threadIdx.x][i]);
 }
 
 __global__ void convert_to_bf16_kernel(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
@@ -78,14 +102,14 @@ __global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, in
 }
 
 // after the env step: append this turn's results to the per-episode logs
-__global__ void log_turn_kernel(int n, int max_turns, GenDev gen, const int32_t* __restrict__ n_actions, StepOut step,
+__global__ void log_turn_kernel(int n, int max_turns, GenDev gen, StepOut step,
                                 float* ep_return, int32_t* ep_length, uint8_t* ep_done, float* step_reward, uint8_t* step_valid,
                                 uint8_t* step_fb, int32_t* step_aux, int32_t* act_tokens, int32_t* act_len) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int glen = gen.len[e];
     if (glen <= 0) return;                      // env did not act this turn (already done)
-    const int t = n_actions[e] - 1;
+    const int t = ep_length[e];                 // transitions logged so far == index of this turn
     if (t < 0 || t >= max_turns) return;
     const size_t o = (size_t)e * max_turns + t;
     step_reward[o] = step.reward[e];
@@ -144,14 +168,14 @@ static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
 }
 
 template <int EPI>
-static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut,
-                          const GemmArgs& g) {
+static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmW1,
+                          const CUtensorMap& tmW2, const CUtensorMap& tmOut, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         configured = true;
     }
-    gemm_bf16_tcgen05_kernel<EPI><<<sm_count, TcCfg<EPI>::THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, tmOut, g);
+    gemm_bf16_tcgen05_kernel<EPI><<<sm_count, TcCfg<EPI>::THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, tmW1, tmW2, tmOut, g);
     return 0;
 }
 
@@ -166,12 +190,23 @@ static int launch_gemm_mma(cudaStream_t st, int sm_count, const GemmArgs& g) {
     return 0;
 }
 
+// extra operands of a multi-segment GEMM (the value-perturbed sampler): A row pitch and the two further W matrices
+struct GemmExtra {
+    size_t a_cols = 0;                       // columns of the A tensor (0 = g.K)
+    const __nv_bfloat16* W1 = nullptr; size_t w1_cols = 0;
+    const __nv_bfloat16* W2 = nullptr; size_t w2_cols = 0;
+    size_t out_cols = 0;                     // columns of the output tensor (0 = g.N)
+};
+
 // a_rows / w_rows: allocated rows behind g.A / g.W (TMA bounds)
 template <int EPI>
-static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_kind, size_t a_rows, size_t w_rows, int kind) {
+static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, size_t a_rows, size_t w_rows, int kind,
+                       const GemmExtra& x = GemmExtra()) {
     Gpt2Dev& G = *e->gpt2;
+    if (g.n_seg == 0) { g.n_seg = 1; g.n_acc = 1; g.seg[0] = {0, 0, 0, g.K / TC_BK}; }
     const bool tc = G.gemm_impl == 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
-    const CUtensorMap *ta = nullptr, *tw = nullptr, *to = nullptr;
+    LMRL_CHECK(tc || (g.n_seg == 1 && EPI != EPI_RELU), "this GEMM needs the tcgen05 kernel (multi-segment / ReLU epilogue): N=%d K=%d", g.N, g.K);
+    const CUtensorMap *ta = nullptr, *tw = nullptr, *tw1 = nullptr, *tw2 = nullptr, *to = nullptr;
     if (tc) {
         auto get = [&](const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32) -> const CUtensorMap* {
             auto key = std::make_pair(base, (int)box_rows | (f32 ? 1 << 16 : 0));
@@ -183,17 +218,23 @@ static int launch_gemm(lmrl_engine* e, const GemmArgs& g, int n_true, int count_
             }
             return &it->second;
         };
-        ta = get(g.A, a_rows, (size_t)g.K, TC_BM, false);
+        ta = get(g.A, a_rows, x.a_cols ? x.a_cols : (size_t)g.K, TC_BM, false);
         tw = get(g.W, w_rows, (size_t)g.K, TC_BN, false);
+        tw1 = x.W1 ? get(x.W1, w_rows, x.w1_cols, TC_BN, false) : tw;
+        tw2 = x.W2 ? get(x.W2, w_rows, x.w2_cols, TC_BN, false) : tw;
         // output map (TMA store / reduce-add source boxes are 32 rows x 128 bytes); the sampling epilogue stores nothing
         if (EPI == EPI_RESID) to = get(g.resid, a_rows, (size_t)g.N, 32, true);
-        else if (EPI == EPI_GELU) to = get(g.out, a_rows, (size_t)g.N, 32, false);
+        else if (EPI == EPI_GELU || EPI == EPI_RELU) to = get(g.out, a_rows, x.out_cols ? x.out_cols : (size_t)g.N, 32, false);
         else if (EPI == EPI_QKV) to = get(g.out, a_rows, (size_t)g.d_model, 32, false);
         else to = ta;
-        if (!ta || !tw || !to) return -1;
+        if (!ta || !tw || !tw1 || !tw2 || !to) return -1;
     }
-    if (e->prof_begin(0, 2.0 * (double)n_true * (double)g.K, count_kind, 2 * kind + e->cur_mode)) return -1;
-    const int rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *to, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
+    double k_total = 0.0;
+    for (int i = 0; i < g.n_seg; ++i) k_total += (double)g.seg[i].kb_count * TC_BK;
+    if (e->prof_begin(0, 2.0 * (double)n_true * k_total, count_kind, 2 * kind + e->cur_mode)) return -1;
+    int rc;
+    if constexpr (EPI == EPI_RELU) rc = launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
+    else rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
     e->prof_end();
     e->launches++;
     return rc;
@@ -225,43 +266,72 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     }
     if (mode == 0)
         LMRL_LAUNCH(2, fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
-    LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x));
+    LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
     const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
-    for (int l = 0; l < D.n_layer; ++l) {
-        const LayerDev& L = G.layers[l];
-        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
-        GemmArgs a{};
-        a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
-        a.out = G.q; a.kcache = G.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
-        a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
-        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
-        if (e->prof_begin(1, 0.0, 0, 10 + mode)) return -1;
-        if (mode == 0)
-            LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
-                                                       ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                          0.125f * 1.4426950408889634f, G.att));
-        else
-            LMRL_LAUNCH(-1, attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                             0.125f, G.att));
-        GemmArgs p{};
-        p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
-        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn));
-        GemmArgs f{};
-        f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
-        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
-        GemmArgs f2{};
-        f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
+    const int n_towers = G.policy_kind == 1 ? 2 : 1;
+    const size_t xl_rows = (size_t)(e->cfg.max_envs + 127) / 128 * 128;
+    for (int t = 0; t < n_towers; ++t) {
+        const TowerDev& T = G.tw[t];
+        if (t > 0) LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(T.wte, T.wpe, D.d_model, G.rows, G.x));
+        for (int l = 0; l < D.n_layer; ++l) {
+            const LayerDev& L = T.layers[l];
+            LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+            GemmArgs a{};
+            a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
+            a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
+            a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+            if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
+            if (e->prof_begin(1, 0.0, 0, 10 + mode)) return -1;
+            if (mode == 0)
+                LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
+                                                           ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                              0.125f * 1.4426950408889634f, G.att));
+            else
+                LMRL_LAUNCH(-1, attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                                 0.125f, G.att));
+            GemmArgs p{};
+            p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
+            if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
+            LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+            GemmArgs f{};
+            f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
+            if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
+            GemmArgs f2{};
+            f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
+            if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
+        }
+        // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
+        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last,
+                                                                  t == 0 ? G.xl : G.xl1, t == 0 ? G.xl_cols : D.d_model));
     }
-    LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, G.lnf_g, G.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last, G.xl));
     LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
     GemmArgs h{};
-    h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
+    h.A = G.xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
-    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, (size_t)(e->cfg.max_envs + 127) / 128 * 128, G.v_pad, 4)) return -1;
+    GemmExtra hx;
+    hx.a_cols = (size_t)G.xl_cols;
+    const int kb_d = D.d_model / TC_BK;
+    if (G.policy_kind == 1) {
+        // Q heads, first layer: xl[:, d + k*hidden ...] = beta * relu(xl1 · W1_k^T + b1_k)   (mlp_head.py:146-147; beta folded in here)
+        const QHeadsDev& Q = G.qh;
+        GemmArgs r{};
+        r.A = G.xl1; r.W = Q.w1cat; r.bias = Q.b1cat; r.N = Q.n_q * Q.hidden; r.K = D.d_model; r.M_dev = G.rows.n_slots; r.out = G.xl;
+        r.out_col0 = D.d_model; r.out_scale = Q.beta;
+        GemmExtra rx;
+        rx.out_cols = (size_t)G.xl_cols;
+        if (launch_gemm<EPI_RELU>(e, r, r.N, 1, xl_rows, (size_t)r.N, 4, rx)) return -1;
+        // logits = min_k(h_pi · wte^T + beta * (relu_k · W2_k^T + b2_k))   (generation.py:112-119)
+        const int kb_h = Q.hidden / TC_BK;
+        h.n_acc = Q.n_q; h.n_seg = 2 * Q.n_q;
+        h.seg[0] = {0, 0, 0, kb_d}; h.seg[1] = {0, kb_d, 1, kb_h};
+        h.seg[2] = {1, 0, 0, kb_d}; h.seg[3] = {1, kb_d + kb_h, 2, kb_h};
+        h.bias = Q.b2s[0]; h.bias2 = Q.b2s[1];
+        hx.W1 = Q.w2[0]; hx.w1_cols = (size_t)Q.hidden;
+        if (Q.n_q == 2) { hx.W2 = Q.w2[1]; hx.w2_cols = (size_t)Q.hidden; }
+    }
+    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
     LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
     e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
@@ -277,11 +347,12 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     G.stream_cap = max_in + MAX_LINE_TOKENS;
     G.m_cap = ((size_t)B * max_in + 127) / 128 * 128;
     G.kv_layer_stride = (size_t)2 * B * D.d_model * G.t_cap;
-    if (e->alloc(&G.kv, G.kv_layer_stride * D.n_layer)) return -1;
     if (e->alloc(&G.x, (size_t)G.m_cap * D.d_model) || e->alloc(&G.xn, (size_t)G.m_cap * D.d_model) ||
         e->alloc(&G.q, (size_t)G.m_cap * D.d_model) || e->alloc(&G.att, (size_t)G.m_cap * D.d_model) ||
-        e->alloc(&G.h, (size_t)G.m_cap * D.d_ff) || e->alloc(&G.xl, (size_t)((B + 127) / 128 * 128) * D.d_model))
+        e->alloc(&G.h, (size_t)G.m_cap * D.d_ff) || e->alloc(&G.xl, (size_t)((B + 127) / 128 * 128) * 3 * D.d_model) ||
+        e->alloc(&G.xl1, (size_t)((B + 127) / 128 * 128) * D.d_model))
         return -1;
+    G.xl_cols = 3 * D.d_model;
     if (e->alloc(&G.rows.M, 1) || e->alloc(&G.rows.n_slots, 1) || e->alloc(&G.rows.row_env, G.m_cap) || e->alloc(&G.rows.row_pos, G.m_cap) ||
         e->alloc(&G.rows.row_tok, G.m_cap) || e->alloc(&G.rows.slot_env, B) || e->alloc(&G.rows.slot_row0, B) ||
         e->alloc(&G.rows.slot_nrow, B) || e->alloc(&G.rows.slot_last, B))
@@ -291,7 +362,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     G.gen.eos_id = e->tok.t.newline_id;
     if (e->alloc(&G.stream.tokens, (size_t)B * G.stream_cap) || e->alloc(&G.stream.len, B) || e->alloc(&G.stream.kv_len, B)) return -1;
     G.stream.cap = G.stream_cap; G.stream.max_input = max_in;
-    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.episode_key, B)) return -1;
+    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.episode_key, B) || e->alloc(&G.live, 1)) return -1;
     if (e->alloc(&G.ep_return, B) || e->alloc(&G.ep_length, B) || e->alloc(&G.ep_done, B) || e->alloc(&G.step_reward, (size_t)B * T) ||
         e->alloc(&G.step_valid, (size_t)B * T) || e->alloc(&G.step_fb, (size_t)B * T * 5) || e->alloc(&G.step_aux, (size_t)B * T) ||
         e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
@@ -316,8 +387,12 @@ void lmrl_gpt2_free(lmrl_engine* e) {
 
 extern "C" {
 
-int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) {
+int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) { return lmrl_load_gpt2_tower(e, 0, dims, w); }
+
+int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) {
     LMRL_CHECK(e && dims && w, "lmrl_load_gpt2: null argument");
+    LMRL_CHECK(tower == 0 || tower == 1, "lmrl_load_gpt2_tower: tower must be 0 (policy / pi_beta) or 1 (value base)");
+    LMRL_CHECK(tower == 0 || (e->gpt2 && e->gpt2->tw[0].loaded), "lmrl_load_gpt2_tower: load tower 0 first");
     LMRL_CHECK(e->has_tok, "lmrl_load_gpt2: load the tokenizer tables first (EOS id, header)");
     LMRL_CHECK(dims->d_model % 128 == 0 && dims->d_model <= 1024 && dims->d_model == dims->n_head * 64 && dims->d_ff % 128 == 0,
                "lmrl_load_gpt2: unsupported shape d_model=%d n_head=%d d_ff=%d (need head_dim 64, d_model<=1024, multiples of 128)",
@@ -325,8 +400,8 @@ int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_w
     LMRL_CHECK(w->n_vocab_rows >= dims->n_vocab, "lmrl_load_gpt2: wte has fewer rows than n_vocab");
     LMRL_CHECK(e->cfg.max_input_length + e->cfg.max_new_tokens <= dims->n_pos, "lmrl_load_gpt2: max_input_length + max_new_tokens exceeds n_pos");
     LMRL_CUDA(cudaSetDevice(e->device));
-    const bool fresh = e->gpt2 == nullptr;
-    if (fresh) {
+    const bool first = e->gpt2 == nullptr;
+    if (first) {
         e->gpt2 = new Gpt2Dev();
         e->gpt2->dims = *dims;
         cudaDeviceProp prop;
@@ -335,9 +410,11 @@ int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_w
     } else {
         LMRL_CHECK(memcmp(&e->gpt2->dims, dims, sizeof *dims) == 0, "lmrl_load_gpt2: set_params with a different architecture");
     }
-    Gpt2Dev& G = *e->gpt2;
+    Gpt2Dev& GG = *e->gpt2;
+    TowerDev& G = GG.tw[tower];
+    const bool fresh = !G.loaded;
     const int d = dims->d_model, ff = dims->d_ff, L = dims->n_layer;
-    G.v_pad = (dims->n_vocab + TC_BN - 1) / TC_BN * TC_BN;   // LM-head rows padded to the widest N tile
+    GG.v_pad = (dims->n_vocab + TC_BN - 1) / TC_BN * TC_BN;   // LM-head rows padded to the widest N tile
     // staging buffer for fp32 uploads
     const size_t stage_elems = std::max((size_t)w->n_vocab_rows * d, (size_t)d * std::max(ff, 3 * d));
     float* stage = nullptr;
@@ -359,9 +436,9 @@ int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_w
         return 0;
     };
     int rc = 0;
-    if (fresh) { rc |= e->alloc(&G.wte, (size_t)G.v_pad * d); rc |= e->alloc(&G.wpe, (size_t)dims->n_pos * d); G.layers.resize(L); }
+    if (fresh) { rc |= e->alloc(&G.wte, (size_t)GG.v_pad * d); rc |= e->alloc(&G.wpe, (size_t)dims->n_pos * d); G.layers.resize(L); }
     if (!rc) {
-        const int rows = std::min(w->n_vocab_rows, G.v_pad);
+        const int rows = std::min(w->n_vocab_rows, GG.v_pad);
         rc |= up(w->wte, (size_t)rows * d);
         convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(stage, (size_t)rows * d, G.wte);
         cudaStreamSynchronize(e->stream);
@@ -382,10 +459,64 @@ int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_w
     cudaStreamSynchronize(e->stream);
     cudaFree(stage);
     if (rc) return -1;
-    if (fresh && gpt2_alloc_state(e)) return -1;
+    if (first && gpt2_alloc_state(e)) return -1;
+    if (fresh && e->alloc(&G.kv, GG.kv_layer_stride * L)) return -1;
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     LMRL_CUDA(cudaGetLastError());
+    G.loaded = true;
     e->has_gpt2 = true;
+    return 0;
+}
+
+int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_head* q2, float beta) {
+    LMRL_CHECK(e && e->gpt2 && e->gpt2->tw[0].loaded && e->gpt2->tw[1].loaded, "lmrl_load_q_heads: load pi_beta (tower 0) and the value base (tower 1) first");
+    LMRL_CHECK(q1 && q1->w1 && q1->b1 && q1->w2 && q1->b2, "lmrl_load_q_heads: q1 is required");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    QHeadsDev& Q = G.qh;
+    const int d = G.dims.d_model, hid = q1->hidden, n_q = q2 ? 2 : 1;
+    LMRL_CHECK(hid == d, "lmrl_load_q_heads: hidden_dim %d must equal d_model %d (MLPHeadConfig of train_ilql_gpt2.py:224-231)", hid, d);
+    LMRL_CHECK(!q2 || q2->hidden == hid, "lmrl_load_q_heads: q1 and q2 differ in hidden_dim");
+    LMRL_CHECK(q1->n_out >= G.dims.n_vocab && (!q2 || q2->n_out >= G.dims.n_vocab), "lmrl_load_q_heads: head output_dim is smaller than n_vocab");
+    LMRL_CHECK(Q.n_q == 0 || Q.n_q == n_q, "lmrl_load_q_heads: set_params with a different number of Q heads");
+    const bool fresh = Q.n_q == 0;
+    if (fresh) {
+        if (e->alloc(&Q.w1cat, (size_t)n_q * hid * d) || e->alloc(&Q.b1cat, (size_t)n_q * hid)) return -1;
+        for (int k = 0; k < n_q; ++k)
+            if (e->alloc(&Q.w2[k], (size_t)G.v_pad * hid) || e->alloc(&Q.b2s[k], (size_t)G.v_pad)) return -1;
+    }
+    float* stage = nullptr;
+    LMRL_CUDA(cudaMalloc(&stage, (size_t)hid * std::max(q1->n_out, q2 ? q2->n_out : 0) * sizeof(float)));
+    const lmrl_mlp_head* qs[2] = {q1, q2};
+    for (int k = 0; k < n_q; ++k) {
+        const lmrl_mlp_head* q = qs[k];
+        // dense1 kernel [d][hid] -> rows [k*hid, (k+1)*hid) of w1cat [.][d]
+        LMRL_CUDA(cudaMemcpyAsync(stage, q->w1, (size_t)d * hid * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        transpose_to_bf16_kernel<<<dim3((hid + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, hid, Q.w1cat + (size_t)k * hid * d);
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+        LMRL_CUDA(cudaMemcpyAsync(Q.b1cat + (size_t)k * hid, q->b1, (size_t)hid * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        // dense2 kernel [hid][n_out] -> w2 [v_pad][hid] (rows beyond n_out stay zero; ids beyond n_vocab are masked by the sampler)
+        const int n_rows = std::min(q->n_out, G.v_pad);
+        LMRL_CUDA(cudaMemcpyAsync(stage, q->w2, (size_t)hid * q->n_out * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        transpose_to_bf16_kernel<<<dim3((n_rows + 31) / 32, (hid + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, hid, q->n_out, Q.w2[k], n_rows);
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+        std::vector<float> b2((size_t)G.v_pad, 0.f);
+        for (int i = 0; i < n_rows; ++i) b2[i] = beta * q->b2[i];
+        LMRL_CUDA(cudaMemcpyAsync(Q.b2s[k], b2.data(), b2.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(stage);
+    LMRL_CUDA(cudaGetLastError());
+    Q.n_q = n_q; Q.hidden = hid; Q.beta = beta;
+    G.policy_kind = 1;
+    return 0;
+}
+
+int lmrl_set_policy_kind(lmrl_engine* e, int32_t kind) {
+    LMRL_CHECK(e && e->gpt2 && e->gpt2->tw[0].loaded, "lmrl_set_policy_kind: no GPT-2 parameters loaded");
+    LMRL_CHECK(kind == 0 || (kind == 1 && e->gpt2->tw[1].loaded && e->gpt2->qh.n_q > 0),
+               "lmrl_set_policy_kind: kind 1 (value-perturbed) needs the value tower and Q heads; kind must be 0 or 1");
+    e->gpt2->policy_kind = kind;
     return 0;
 }
 
@@ -459,28 +590,54 @@ int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok
     return 0;
 }
 
-static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, int32_t n, const lmrl_sampling& s) {
+static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, const int32_t* opt_pos_dev, int32_t n, const lmrl_sampling& s) {
     Gpt2Dev& G = *e->gpt2;
-    LMRL_CHECK(env_kind == LMRL_ENV_WORDLE, "fused rollout: only the Wordle env is fused in this build (env_kind=%d)", env_kind);
-    LMRL_CHECK(e->has_wordle, "fused rollout: no Wordle vocabulary loaded");
+    LMRL_CHECK(env_kind == LMRL_ENV_WORDLE || env_kind == LMRL_ENV_MAZE, "fused rollout: unknown env_kind %d", env_kind);
     LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "fused rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
-    LMRL_CHECK(e->cfg.max_new_tokens * e->max_token_bytes <= MAX_ACTION_CP, "fused rollout: max_new_tokens * longest token exceeds %d bytes", MAX_ACTION_CP);
+    const bool wordle = env_kind == LMRL_ENV_WORDLE;
+    if (wordle) {
+        LMRL_CHECK(e->has_wordle, "fused rollout: no Wordle vocabulary loaded");
+        LMRL_CHECK(e->cfg.max_new_tokens * e->max_token_bytes <= MAX_ACTION_CP, "fused rollout: max_new_tokens * longest token exceeds %d bytes", MAX_ACTION_CP);
+    } else {
+        LMRL_CHECK(e->has_maze && e->maze.obs_tokens, "fused rollout: no maze (with its observation token table) loaded");
+        LMRL_CHECK(e->maze.obs_pitch + MAZE_ACT_PITCH + e->cfg.max_input_length <= G.stream_cap, "fused rollout: observation does not fit the token stream");
+    }
     const int T = e->cfg.max_turns;
     cudaStream_t st = e->stream;
     const int blocks = (n + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK;
-    LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
-    LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, nullptr, seeds_dev,
-                                                                       G.episode_key, G.ep_return, G.ep_length, G.ep_done));
+    const uint8_t* done = wordle ? e->wordle.done : e->maze.done;
+    if (wordle) {
+        LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
+        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, nullptr, seeds_dev,
+                                                                           G.episode_key, G.ep_return, G.ep_length, G.ep_done));
+    } else {
+        LMRL_LAUNCH(3, maze_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->maze, seeds_dev, opt_pos_dev, nullptr, n));
+        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, 0, G.stream, nullptr, seeds_dev,
+                                                                           G.episode_key, G.ep_return, G.ep_length, G.ep_done));
+        LMRL_LAUNCH(3, maze_init_stream_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->maze, G.stream, n));
+    }
     ActionSrc src{};
     src.tokens = G.gen.tok; src.ntokens = G.gen.len; src.tpitch = G.gen.max_new;
     for (int turn = 0; turn < T; ++turn) {
         LMRL_LAUNCH(2, clear_gen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, G.gen));
         for (int k = 0; k < e->cfg.max_new_tokens; ++k)
-            if (forward_and_sample(e, k == 0 ? 0 : 1, n, e->wordle.done, e->wordle.n_actions, 0, s, nullptr)) return -1;
-        LMRL_LAUNCH(3, wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(
-                           e->wordle, e->tok, src, nullptr, e->step, G.stream, n));
-        LMRL_LAUNCH(3, log_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, G.gen, e->wordle.n_actions, e->step, G.ep_return, G.ep_length, G.ep_done,
+            if (forward_and_sample(e, k == 0 ? 0 : 1, n, done, G.ep_length, 0, s, nullptr)) return -1;
+        if (wordle)
+            LMRL_LAUNCH(3, wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(
+                               e->wordle, e->tok, src, nullptr, e->step, G.stream, n));
+        else
+            LMRL_LAUNCH(3, maze_fused_step_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->maze, e->tok, src, e->step, G.stream, n));
+        LMRL_LAUNCH(3, log_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, G.gen, e->step, G.ep_return, G.ep_length, G.ep_done,
                                                                         G.step_reward, G.step_valid, G.step_fb, G.step_aux, G.act_tokens, G.act_len));
+        // long episodes (Maze: up to max_steps + 1 turns): every 8th turn ask the device whether anything is still running
+        if (T > 8 && (turn & 7) == 7 && turn + 1 < T) {
+            LMRL_CUDA(cudaMemsetAsync(G.live, 0, sizeof(int), st));
+            LMRL_LAUNCH(2, count_live_kernel<<<32, 256, 0, st>>>(done, n, G.live));
+            int live = 0;
+            LMRL_CUDA(cudaMemcpyAsync(&live, G.live, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LMRL_CUDA(cudaStreamSynchronize(st));
+            if (live == 0) break;
+        }
     }
     LMRL_CUDA(cudaGetLastError());
     return 0;
@@ -502,25 +659,26 @@ static int rollout_export(lmrl_engine* e, int32_t n, lmrl_rollout_out* out, cuda
     return 0;
 }
 
-int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, const int32_t* /*opt_pos*/, int32_t n,
+int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, const int32_t* opt_pos, int32_t n,
                       const lmrl_sampling* s, lmrl_rollout_out* out) {
     LMRL_CHECK(e && e->has_gpt2, "lmrl_rollout: no GPT-2 parameters loaded");
     LMRL_CHECK(seeds && s, "lmrl_rollout: null argument");
     LMRL_CUDA(cudaSetDevice(e->device));
     LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "lmrl_rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
     LMRL_CUDA(cudaMemcpyAsync(e->d_seeds, seeds, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
-    if (rollout_enqueue(e, env_kind, e->d_seeds, n, *s)) return -1;
+    if (opt_pos) LMRL_CUDA(cudaMemcpyAsync(e->d_opt_pos, opt_pos, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, e->stream));
+    if (rollout_enqueue(e, env_kind, e->d_seeds, opt_pos ? e->d_opt_pos : nullptr, n, *s)) return -1;
     if (rollout_export(e, n, out, cudaMemcpyDeviceToHost)) return -1;
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
-int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, const int32_t* /*opt_pos_dev*/, int32_t n,
+int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, const int32_t* opt_pos_dev, int32_t n,
                      const lmrl_sampling* s, lmrl_rollout_out* out_dev) {
     LMRL_CHECK(e && e->has_gpt2, "lmrl_rollout: no GPT-2 parameters loaded");
     LMRL_CHECK(seeds_dev && s, "lmrl_rollout: null argument");
     LMRL_CUDA(cudaSetDevice(e->device));
-    if (rollout_enqueue(e, env_kind, seeds_dev, n, *s)) return -1;
+    if (rollout_enqueue(e, env_kind, seeds_dev, opt_pos_dev, n, *s)) return -1;
     return rollout_export(e, n, out_dev, cudaMemcpyDeviceToDevice);
 }
 
@@ -554,13 +712,14 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
     LMRL_CUDA(cudaMemcpyAsync(dM, &M, 4, cudaMemcpyHostToDevice, e->stream));
     GemmArgs g{};
     g.A = dA; g.W = dW; g.bias = bias ? dB : nullptr; g.N = N; g.K = K; g.M_dev = dM; g.resid = dR;
+    g.n_seg = 1; g.n_acc = 1; g.seg[0] = {0, 0, 0, K / TC_BK};
     cudaDeviceProp prop;
     LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
     int rc = 0;
     if (impl == 1) {
         CUtensorMap ta, tw, to;
         rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC_BN) || make_tmap(&to, dR, m_pad, N, 32, true);
-        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, to, g);
+        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, tw, tw, to, g);
     } else {
         rc = launch_gemm_mma<EPI_RESID>(e->stream, prop.multiProcessorCount, g);
     }
@@ -588,13 +747,13 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.att, (size_t)M * D.d_model, 0x2345u, 1.0f);
     bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.q, (size_t)M * D.d_model, 0x3456u, 1.0f);
     bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.h, (size_t)M * D.d_ff, 0x4567u, 1.0f);
-    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.xl, (size_t)n_slots * D.d_model, 0x5678u, 1.0f);
+    bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.xl, (size_t)n_slots * G.xl_cols, 0x5678u, 1.0f);
     LMRL_CUDA(cudaMemsetAsync(G.x, 0, (size_t)M * D.d_model * sizeof(float), st));
     LMRL_CUDA(cudaMemsetAsync(G.best, 0, sizeof(unsigned long long) * n_slots, st));
-    const LayerDev& L = G.layers[0];
+    const LayerDev& L = G.tw[0].layers[0];
     GemmArgs a{};
     a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
-    a.out = G.q; a.kcache = G.kv; a.vcache = a.kcache + G.kv_layer_stride / 2;
+    a.out = G.q; a.kcache = G.tw[0].kv; a.vcache = a.kcache + G.kv_layer_stride / 2;
     a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
     GemmArgs p{};
     p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
@@ -603,9 +762,11 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     GemmArgs f2{};
     f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
     GemmArgs h{};
-    h.A = G.xl; h.W = G.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
+    h.A = G.xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f; h.do_sample = 1; h.n_vocab = D.n_vocab; h.logits_out = nullptr;
     const size_t xl_rows = (size_t)(B + 127) / 128 * 128;
+    GemmExtra hx;
+    hx.a_cols = (size_t)G.xl_cols;
     const int ew_blocks = G.sm_count * 8;
     const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
     const int att_blocks = std::min((n_slots * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
@@ -622,7 +783,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                 case 1: rc = launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1); break;
                 case 2: rc = launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2); break;
                 case 3: rc = launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3); break;
-                case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4); break;
+                case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx); break;
                 case 5:
                     if (rpe > 1)
                         attention_prefill_kernel<<<std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
@@ -631,8 +792,8 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                     else
                         attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
                     break;
-                case 6: layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn); break;
-                case 7: embed_kernel<<<ew_blocks, 256, 0, st>>>(G.wte, G.wpe, D.d_model, G.rows, G.x); break;
+                case 6: layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model); break;
+                case 7: embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x); break;
             }
         }
         cudaEventRecord(ev[1], st);

@@ -138,7 +138,7 @@ __global__ void embed_kernel(const __nv_bfloat16* __restrict__ wte, const __nv_b
 // gather != nullptr: output row j takes input row gather[j] (final LN of the sampled rows only), count from n_dev
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  int d, float eps, const int* __restrict__ n_dev, const int* __restrict__ gather,
-                                 __nv_bfloat16* __restrict__ out) {
+                                 __nv_bfloat16* __restrict__ out, int out_pitch) {
     const int n = *n_dev;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -164,7 +164,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 #pragma unroll
         for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
         const float rstd = rsqrtf(q / d + eps);
-        __nv_bfloat16* dst = out + (size_t)j * d;
+        __nv_bfloat16* dst = out + (size_t)j * out_pitch;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if (i < nv) {

@@ -110,7 +110,7 @@ int lmrl_load_wordle(lmrl_engine* e, const uint32_t* packed_words, int32_t n_wor
 
 int lmrl_load_maze(lmrl_engine* e, const uint8_t* grid, int32_t H, int32_t W, int32_t goal_y, int32_t goal_x,
                    int32_t max_steps, int32_t last_k, const float* rewards3, const int32_t* obs_tokens,
-                   const int32_t* obs_len, int32_t obs_pitch) {
+                   const int32_t* obs_len, int32_t obs_pitch, const int32_t* act_tokens, const int32_t* act_len) {
     LMRL_CHECK(e && grid && rewards3 && H > 2 && W > 2 && H <= 64 && W <= 64, "lmrl_load_maze: bad argument");
     LMRL_CUDA(cudaSetDevice(e->device));
     const int B = e->cfg.max_envs;
@@ -128,10 +128,20 @@ int lmrl_load_maze(lmrl_engine* e, const uint8_t* grid, int32_t H, int32_t W, in
         if (e->alloc(&m.pos, (size_t)B * 2) || e->alloc(&m.goal, (size_t)B * 2) || e->alloc(&m.num_steps, B) || e->alloc(&m.done, B))
             return -1;
     }
-    if (obs_tokens && obs_len) {
-        if (e->upload(&e->d_maze_obs_tokens, obs_tokens, (size_t)H * W * obs_pitch) || e->upload(&e->d_maze_obs_len, obs_len, (size_t)H * W))
+    if (!e->has_maze) {
+        if (e->alloc(&m.item_len, (size_t)B * MAZE_RING) || e->alloc(&m.n_items, B) || e->alloc(&m.cut, B)) return -1;
+    }
+    m.obs_tokens = nullptr; m.obs_len = nullptr; m.act_tokens = nullptr; m.act_len = nullptr;
+    if (obs_tokens && obs_len && act_tokens && act_len) {
+        LMRL_CHECK(last_k >= 1 && last_k <= 64, "lmrl_load_maze: the fused loop supports 1 <= last_k <= 64 (got %d)", last_k);
+        for (int a = 0; a < 4; ++a) LMRL_CHECK(act_len[a] > 0 && act_len[a] <= MAZE_ACT_PITCH, "lmrl_load_maze: action %d has %d tokens (max %d)", a, act_len[a], MAZE_ACT_PITCH);
+        int32_t *d_at, *d_al;
+        if (e->upload(&e->d_maze_obs_tokens, obs_tokens, (size_t)H * W * obs_pitch) || e->upload(&e->d_maze_obs_len, obs_len, (size_t)H * W) ||
+            e->upload(&d_at, act_tokens, (size_t)4 * MAZE_ACT_PITCH) || e->upload(&d_al, act_len, 4))
             return -1;
         e->maze_obs_pitch = obs_pitch;
+        m.obs_tokens = e->d_maze_obs_tokens; m.obs_len = e->d_maze_obs_len; m.obs_pitch = obs_pitch;
+        m.act_tokens = d_at; m.act_len = d_al;
     }
     e->has_maze = true;
     return 0;

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Callable, Dict, List, Optional
+from typing import Tuple, Callable, Dict, List, Optional
 
 import numpy as np
 
@@ -85,7 +85,23 @@ def params_from_hf_state_dict(sd, cfg: GPT2Config) -> Dict:
 _LAYER_KEYS = ["ln1_g", "ln1_b", "attn_w", "attn_b", "proj_w", "proj_b", "ln2_g", "ln2_b", "fc_w", "fc_b", "fc2_w", "fc2_b"]
 
 
-def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict):
+def init_mlp_head_params(cfg: GPT2Config, seed: int = 0, hidden: Optional[int] = None, n_out: Optional[int] = None,
+                         layer2_bias_init: float = -4.4, init_range: Optional[float] = None) -> Dict:
+    """Seeded init of an ``MLPHead`` (heads/mlp_head.py:99-137) with the ILQL script's config
+    (``MLPHeadConfig(input_dim=d, hidden_dim=d, output_dim=vocab, layer2_bias_init=-4.4)``, train_ilql_gpt2.py:224-231):
+    lecun-normal kernels (std = 1/sqrt(fan_in)) unless ``init_range`` is given, zero dense1 bias, constant dense2 bias."""
+    rng = np.random.default_rng(seed)
+    d = cfg.d_model
+    hidden = hidden or d
+    n_out = n_out or cfg.n_vocab_rows
+    s1 = init_range if init_range is not None else 1.0 / np.sqrt(d)
+    s2 = init_range if init_range is not None else 1.0 / np.sqrt(hidden)
+    return dict(dense1=dict(kernel=rng.standard_normal((d, hidden), dtype=np.float32) * np.float32(s1), bias=np.zeros(hidden, np.float32)),
+                dense2=dict(kernel=rng.standard_normal((hidden, n_out), dtype=np.float32) * np.float32(s2),
+                            bias=np.full(n_out, layer2_bias_init, np.float32)))
+
+
+def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict, tower: int = 0):
     L = cfg.n_layer
     assert len(params["layers"]) == L
     keep = []  # keep contiguous fp32 copies alive during the call
@@ -107,7 +123,27 @@ def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict):
         setattr(w, key, C.cast(ptrs, _lib._PPF))
     dims = _lib.lmrl_gpt2_dims(n_layer=cfg.n_layer, n_head=cfg.n_head, d_model=cfg.d_model, d_ff=cfg.d_ff, n_vocab=cfg.n_vocab,
                                n_pos=cfg.n_pos, ln_eps=cfg.ln_eps)
-    check(engine.lib.lmrl_load_gpt2(engine.handle, C.byref(dims), C.byref(w)))
+    check(engine.lib.lmrl_load_gpt2_tower(engine.handle, int(tower), C.byref(dims), C.byref(w)))
+
+
+def _upload_q_heads(engine: Engine, q1: Dict, q2: Optional[Dict], beta: float):
+    keep = []
+
+    def head(q):
+        if q is None:
+            return None
+        h = _lib.lmrl_mlp_head()
+        for name, a in (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"])):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            setattr(h, name, a.ctypes.data_as(_lib._PF))
+        h.hidden = int(q["dense1"]["kernel"].shape[1])
+        h.n_out = int(q["dense2"]["kernel"].shape[1])
+        keep.append(h)
+        return h
+
+    h1, h2 = head(q1), head(q2)
+    check(engine.lib.lmrl_load_q_heads(engine.handle, C.byref(h1), None if h2 is None else C.byref(h2), float(beta)))
 
 
 def default_out_str_process(s: str) -> str:
@@ -188,3 +224,27 @@ class B200GPT2Policy(BatchedTextPolicy):
                 out[i] = tuple(text_history[i]) + (Text(out_f(tok.decode(g)), True),)
         self._calls += 1
         return out
+
+
+class B200GPT2ValuePolicy(B200GPT2Policy):
+    """``GPT2ValuePolicy`` (LLM_RL/algorithms/value_rl_base/gpt2/interface.py:240-329) on the engine: every sampled token
+    uses ``logits = pi_beta(x) + beta * min(Q1(h), Q2(h))`` with ``h`` the last hidden state of the value base
+    (value_rl_base/gpt2/generation.py:36-121).  ``params`` is the reference's tuple
+    ``(pi_beta_params, base_params, q1_head_params, q2_head_params-or-None)`` (interface.py:101); GPT-2 parameter sets use
+    the dict layout of ``init_gpt2_params``, heads the flax layout ``{'dense1': {'kernel','bias'}, 'dense2': {...}}``.
+    ILQL passes two Q heads (beta 16 in wordle/ilql/eval_ilql_gpt2.py:47), MC returns one (wordle/mc/eval_mc_gpt2.py:103-116)."""
+
+    def __init__(self, engine: Engine, params: Tuple, config: Optional[GPT2Config] = None, beta: float = 16.0, **kw):
+        pi_beta, base, q1, q2 = params
+        if pi_beta is None:
+            raise _lib.LmrlError("B200GPT2ValuePolicy needs pi_beta parameters (the pi_beta=None variant of generation.py:116-119 is not built)")
+        super().__init__(engine, pi_beta, config, **kw)
+        self.beta = float(beta)
+        _upload_params(engine, self.config, base, tower=1)
+        _upload_q_heads(engine, q1, q2, self.beta)
+
+    def set_params(self, policy_params: Tuple) -> None:
+        pi_beta, base, q1, q2 = policy_params
+        _upload_params(self._lmrl_engine, self.config, pi_beta, tower=0)
+        _upload_params(self._lmrl_engine, self.config, base, tower=1)
+        _upload_q_heads(self._lmrl_engine, q1, q2, self.beta)

@@ -87,6 +87,41 @@ def forward_last_logits(params: Dict, tokens: Sequence[int], n_head: int, n_voca
     return (h[-1] @ wte.T).numpy()
 
 
+# ---- ILQL / MC value-perturbed logits -------------------------------------------------------------------------------
+
+def mlp_head(h: "torch.Tensor", q: Dict, weights_bf16: bool = True) -> "torch.Tensor":
+    """MLPHead.__call__ (LLM_RL/heads/mlp_head.py:139-148): dense2(relu(dense1(x)))."""
+    w1, w2 = _t(q["dense1"]["kernel"], weights_bf16), _t(q["dense2"]["kernel"], weights_bf16)
+    b1 = torch.from_numpy(np.ascontiguousarray(q["dense1"]["bias"], dtype=np.float32))
+    b2 = torch.from_numpy(np.ascontiguousarray(q["dense2"]["bias"], dtype=np.float32))
+    return torch.relu(h @ w1 + b1) @ w2 + b2
+
+
+def value_policy_last_logits(params, tokens: Sequence[int], n_head: int, n_vocab: int, beta: float, emulate_bf16: bool = False,
+                             weights_bf16: bool = True, **kw) -> np.ndarray:
+    """GPT2ValueRLGeneration.__call__ (LLM_RL/algorithms/value_rl_base/gpt2/generation.py:36-121) for the last position:
+    logits = pi_beta_logits + beta * min(q1(h), q2(h)) (or beta * q1(h) when q2 is None, :112-119), h = hidden_states[-1]
+    of the value base (:87; HF appends the post-ln_f state last).  ``emulate_bf16`` rounds where the engine rounds: both
+    final hidden states and beta*relu(dense1) are stored as bf16 before the last matmul."""
+    pi_beta, base, q1, q2 = params
+    h_pi = forward_hidden(pi_beta, tokens, n_head, emulate_bf16=emulate_bf16, weights_bf16=weights_bf16, **kw)[-1]
+    h_v = forward_hidden(base, tokens, n_head, emulate_bf16=emulate_bf16, weights_bf16=weights_bf16, **kw)[-1]
+    pi_logits = h_pi @ _t(pi_beta["wte"], weights_bf16)[:n_vocab].T
+    if not emulate_bf16:
+        qs = [mlp_head(h_v, q, weights_bf16)[:n_vocab] for q in (q1, q2) if q is not None]
+        qmin = qs[0] if len(qs) == 1 else torch.minimum(qs[0], qs[1])
+        return (pi_logits + beta * qmin).numpy()
+    outs = []
+    for q in (q1, q2):
+        if q is None:
+            continue
+        b1 = torch.from_numpy(np.ascontiguousarray(q["dense1"]["bias"], dtype=np.float32))
+        b2 = torch.from_numpy(np.ascontiguousarray(q["dense2"]["bias"], dtype=np.float32))
+        r = _r(beta * torch.relu(h_v @ _t(q["dense1"]["kernel"], weights_bf16) + b1), True)
+        outs.append(pi_logits + r @ _t(q["dense2"]["kernel"], weights_bf16)[:, :n_vocab] + beta * b2[:n_vocab])
+    return (outs[0] if len(outs) == 1 else torch.minimum(outs[0], outs[1])).numpy()
+
+
 # ---- the engine's sampler, restated -------------------------------------------------------------------------------
 
 def splitmix64(z: int) -> int:

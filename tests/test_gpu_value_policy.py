@@ -1,0 +1,133 @@
+"""GPU parity of the ILQL / MC value-perturbed policy against the torch-fp32 oracle restatement of
+value_rl_base/gpt2/generation.py:36-121 and heads/mlp_head.py:139-148.
+
+Tolerances: beta multiplies the Q-head output, so the bf16 rounding of beta*relu(dense1) and of the dense2 kernel moves
+the perturbed logits by ~beta * 2^-9 * |q| — the bounds below are for beta = 4 with lecun-normal heads (|beta*q| ~ 3):
+  * vs the oracle that rounds where the engine rounds:  max |diff| <= 4e-2
+  * vs the plain fp32 oracle:                            max |diff| <= 1.5e-1, mean <= 3e-2
+Sampled ids must be the arg-max of the oracle's (logits/T + Gumbel noise) up to twice the emulated tolerance.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params, init_mlp_head_params  # noqa: E402
+from lmrl_gym_b200.tokenizer import ByteTokenizer  # noqa: E402
+from lmrl_gym_b200.vocab import load_vocab_words  # noqa: E402
+
+TOL_EMU, TOL_F32, TOL_F32_MEAN = 4e-2, 1.5e-1, 3e-2
+BETA = 4.0
+
+
+@pytest.fixture(scope="module")
+def tok():
+    return ByteTokenizer.synthetic()
+
+
+def _cfg():
+    return GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+
+
+def _params(cfg, two_heads=True, seed=0):
+    rng = np.random.default_rng(seed + 100)
+    q1 = init_mlp_head_params(cfg, seed=seed + 2)
+    q1["dense1"]["bias"] = (0.1 * rng.standard_normal(cfg.d_model)).astype(np.float32)
+    q2 = init_mlp_head_params(cfg, seed=seed + 3) if two_heads else None
+    return (init_gpt2_params(cfg, seed=seed), init_gpt2_params(cfg, seed=seed + 1), q1, q2)
+
+
+@pytest.mark.parametrize("two_heads", [True, False])
+def test_value_policy_logits_match_oracle(tok, two_heads):
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2ValuePolicy
+    from oracle import gpt2 as og
+    cfg = _cfg()
+    params = _params(cfg, two_heads)
+    eng = Engine(max_envs=160, max_input_length=64, max_new_tokens=4, tokenizer=tok)
+    pol = B200GPT2ValuePolicy(eng, params, cfg, beta=BETA)
+    rng = np.random.default_rng(0)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, 64, size=150)]
+    got = pol.logits(prompts)
+    worst_emu = worst_f32 = 0.0
+    for i in range(0, 150, 6):
+        emu = og.value_policy_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, BETA, emulate_bf16=True)
+        f32 = og.value_policy_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, BETA)
+        worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+        worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+        assert np.abs(got[i] - f32).mean() <= TOL_F32_MEAN
+    print(f"value policy ({'ILQL 2 heads' if two_heads else 'MC 1 head'}): max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
+    assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
+    # the perturbation is really there: the engine's logits differ from pi_beta's own by about beta * q
+    pi_only = og.forward_last_logits(params[0], prompts[0], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+    assert np.abs(got[0] - pi_only).mean() > 1.0
+    eng.close()
+
+
+def test_value_policy_generate_and_set_params(tok):
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2ValuePolicy
+    from oracle import gpt2 as og
+    cfg = _cfg()
+    params = _params(cfg, True, seed=10)
+    eng = Engine(max_envs=64, max_input_length=32, max_new_tokens=5, tokenizer=tok)
+    pol = B200GPT2ValuePolicy(eng, params, cfg, beta=BETA, seed=5)
+    rng = np.random.default_rng(2)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, 32, size=40)]
+    keys = [int(k) for k in rng.integers(0, 2**63, size=40)]
+
+    def check_gens(p):
+        gens = pol.generate_tokens(prompts, episode_keys=keys, turn=1)
+        for i in range(0, 40, 5):
+            for k, t in enumerate(gens[i]):
+                logits = og.value_policy_last_logits(p, prompts[i] + gens[i][:k], cfg.n_head, cfg.n_vocab, BETA, emulate_bf16=True)
+                s = og.sample_scores(logits, og.row_key(5, keys[i], 1, k), 1.0, True)
+                assert s[t] >= s.max() - 2 * TOL_EMU, (i, k)
+        return gens
+
+    g0 = check_gens(params)
+    params2 = _params(cfg, True, seed=20)
+    pol.set_params(params2)
+    g1 = check_gens(params2)
+    assert g0 != g1
+    eng.close()
+
+
+def test_value_policy_fused_rollout_replays_through_oracle_env(tok):
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2ValuePolicy
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from lmrl_gym_b200.environment import text_env_eval
+    from oracle import gpt2 as og
+    from oracle.mt19937 import seed_stream
+    from oracle.wordle import ReformatWordleOracle
+    cfg = _cfg()
+    params = _params(cfg, True, seed=30)
+    B = 128
+    eng = Engine(max_envs=B, max_input_length=128, max_new_tokens=4, max_turns=6, tokenizer=tok)
+    env = B200WordleEnv(eng, "wordle_official.txt")
+    pol = B200GPT2ValuePolicy(eng, params, cfg, beta=BETA, seed=3)
+    inter, summary = text_env_eval(env, pol, n_rollouts=B, seed_generator=seed_stream(0), bsize=B, verbose=False)
+    words = load_vocab_words("wordle_official.txt")
+    seeds = seed_stream(0)
+    seed_list = []
+    for ep in inter:
+        seed = next(seeds)
+        seed_list.append(seed)
+        o = ReformatWordleOracle(words)
+        h = o.reset(seed)
+        for tr in ep:
+            h, r, d = o.step(h + ((tr.post_action_history[-1].text, True),))
+            assert [[x.text, x.is_action] for x in tr.post_transition_history] == [[a, b] for a, b in h]
+            assert tr.reward == r and tr.done == d
+    for i in (0, 77):
+        ep = inter[i]
+        logs, j = ep._logs, ep._i
+        for t, tr in enumerate(ep):
+            prompt = tok.encode("".join(x.text for x in tr.pre_action_history))[-128:]
+            gen = logs.act_tokens[j, t, :logs.act_len[j, t]].tolist()
+            for k, tk in enumerate(gen):
+                logits = og.value_policy_last_logits(params, prompt + gen[:k], cfg.n_head, cfg.n_vocab, BETA, emulate_bf16=True)
+                s = og.sample_scores(logits, og.row_key(3, seed_list[i], t, k), 1.0, True)
+                assert s[tk] >= s.max() - 2 * TOL_EMU, (i, t, k)
+    eng.close()

@@ -47,3 +47,27 @@ def test_init_params_shapes():
     assert cfg.matmul_params == 123532032
     p = init_gpt2_params(GPT2Config(n_layer=2, n_head=2, d_model=128, d_ff=512, n_vocab=300, n_vocab_rows=301, n_pos=32), seed=1)
     assert p["wte"].shape == (301, 128) and p["layers"][1]["fc2_w"].shape == (512, 128)
+
+
+def test_value_policy_restatement_properties():
+    """generation.py:112-119: logits = pi_beta + beta * min(q1, q2); one head -> beta * q1; beta = 0 -> pi_beta."""
+    from lmrl_gym_b200.gpt2 import init_mlp_head_params
+    cfg = GPT2Config(n_layer=1, n_head=2, d_model=64, d_ff=128, n_vocab=97, n_vocab_rows=98, n_pos=16)
+    pi, base = init_gpt2_params(cfg, seed=1), init_gpt2_params(cfg, seed=2)
+    q1, q2 = init_mlp_head_params(cfg, seed=3), init_mlp_head_params(cfg, seed=4)
+    toks = [5, 9, 2, 77]
+    pi_logits = og.forward_last_logits(pi, toks, cfg.n_head, cfg.n_vocab, weights_bf16=False)
+    h_v = og.forward_hidden(base, toks, cfg.n_head, weights_bf16=False)[-1]
+    qa = og.mlp_head(h_v, q1, weights_bf16=False).numpy()[:cfg.n_vocab]
+    qb = og.mlp_head(h_v, q2, weights_bf16=False).numpy()[:cfg.n_vocab]
+    assert abs(qa.mean() + 4.4) < 0.5                      # layer2_bias_init = -4.4 (train_ilql_gpt2.py:224-231)
+    both = og.value_policy_last_logits((pi, base, q1, q2), toks, cfg.n_head, cfg.n_vocab, 16.0, weights_bf16=False)
+    one = og.value_policy_last_logits((pi, base, q1, None), toks, cfg.n_head, cfg.n_vocab, 16.0, weights_bf16=False)
+    assert np.allclose(both, pi_logits + 16.0 * np.minimum(qa, qb), atol=1e-4)
+    assert np.allclose(one, pi_logits + 16.0 * qa, atol=1e-4)
+    zero = og.value_policy_last_logits((pi, base, q1, q2), toks, cfg.n_head, cfg.n_vocab, 0.0, weights_bf16=False)
+    assert np.allclose(zero, pi_logits, atol=1e-5)
+    # the bf16-emulating variant (min of the two per-head sums, beta folded into relu) is the same function up to rounding
+    emu = og.value_policy_last_logits((pi, base, q1, q2), toks, cfg.n_head, cfg.n_vocab, 4.0, emulate_bf16=True)
+    ref = og.value_policy_last_logits((pi, base, q1, q2), toks, cfg.n_head, cfg.n_vocab, 4.0)
+    assert np.abs(emu - ref).max() < 0.2
