@@ -75,7 +75,6 @@ class B200MazeEnv(BatchedTextEnv):
         if reward_function not in REWARDS:
             raise ValueError(f"unknown reward function: {reward_function}")
         self._lmrl_engine = engine
-        self._lmrl_fusable = False  # the fused Maze loop is a later row of the scope table
         self._lmrl_kind = ENV_MAZE
         self.grid = maze_grid(maze_name)
         self.goal_default = GOALS[maze_name]
@@ -84,9 +83,36 @@ class B200MazeEnv(BatchedTextEnv):
         self.max_steps = max_steps
         rewards = np.asarray(REWARDS[reward_function], dtype=np.float32)
         H, W = self.grid.shape
+        # fused rollout tables: canonical token ids of every cell's observation sentence (default goal) and of the 4 actions
+        obs_tok = obs_len = act_tok = act_len = None
+        pitch = 0
+        tok = engine.tokenizer
+        self._lmrl_fusable = tok is not None and 1 <= self.last_k <= 64
+        if self._lmrl_fusable:
+            sent = {}
+            for y in range(H):
+                for x in range(W):
+                    if self.grid[y, x] == 0:
+                        sent[y * W + x] = tok.encode(describe(self.mode, self.grid, (y, x), self.goal_default))
+            pitch = max(len(v) for v in sent.values())
+            obs_tok = np.zeros((H * W, pitch), np.int32)
+            obs_len = np.zeros(H * W, np.int32)
+            for c, v in sent.items():
+                obs_tok[c, :len(v)] = v
+                obs_len[c] = len(v)
+            acts = [tok.encode(a) for a in ACTIONS]
+            if max(len(a) for a in acts) > 8:
+                self._lmrl_fusable = False
+            else:
+                act_tok = np.zeros((4, 8), np.int32)
+                act_len = np.asarray([len(a) for a in acts], np.int32)
+                for i, a in enumerate(acts):
+                    act_tok[i, :len(a)] = a
+        if not self._lmrl_fusable:
+            obs_tok = obs_len = act_tok = act_len = None
         check(engine.lib.lmrl_load_maze(engine.handle, ptr(np.ascontiguousarray(self.grid)), H, W, self.goal_default[0],
                                         self.goal_default[1], -1 if max_steps is None else int(max_steps), self.last_k,
-                                        ptr(rewards), None, None, 0))
+                                        ptr(rewards), ptr(obs_tok), ptr(obs_len), pitch, ptr(act_tok), ptr(act_len)))
         engine.env_kind = ENV_MAZE
         self.n: Optional[int] = None
         self.pos = None
@@ -157,6 +183,27 @@ class B200MazeEnv(BatchedTextEnv):
                     full = tuple(text_history[i]) + (obs,)
                     hist = full[max(0, len(full) - self.last_k):]
             out.append((hist, float(reward[i]), bool(dn[i])))
+        return out
+
+    def describe_cell(self, cell: int) -> str:
+        W = self.grid.shape[1]
+        return describe(self.mode, self.grid, (cell // W, cell % W), self.goal_default)
+
+    def fused_options(self, options) -> Optional[np.ndarray]:
+        """env_options of one batch -> [n][2] init positions for the fused loop (None if no option is given); raises if an
+        option the fused loop does not implement ('goal') is present."""
+        if options is None or all(o is None or len(o) == 0 for o in options):
+            return None
+        out = np.full((len(options), 2), -1, np.int32)
+        for i, o in enumerate(options):
+            if not o:
+                continue
+            if "goal" in o:
+                raise NotImplementedError("the fused Maze loop uses the maze's default goal; pass goal options through the generic loop")
+            if "init_position" in o:
+                p = list(o["init_position"])
+                assert self.grid[p[0], p[1]] == 0 and tuple(p) != tuple(self.goal_default)
+                out[i] = p
         return out
 
     def copy(self):

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check, ptr
-from .engine import ENV_WORDLE
+from .engine import ENV_MAZE, ENV_WORDLE
 from .environment import InteractionTransition, Text, summarize_episodes
 from .gpt2 import default_out_str_process
 from .wordle import HEADER, normalise_action, render_action, seed_to_u64
@@ -53,7 +53,7 @@ class RolloutLogs:
                                       self.step_feedback, self.step_aux, self.act_tokens, self.act_len))
 
 
-def run_fused_batch(engine, env, policy, seeds: Sequence[Optional[int]]) -> RolloutLogs:
+def run_fused_batch(engine, env, policy, seeds: Sequence[Optional[int]], options=None) -> RolloutLogs:
     n = len(seeds)
     if n > engine.max_envs:
         raise _lib.LmrlError(f"batch of {n} episodes exceeds the engine capacity {engine.max_envs}")
@@ -61,7 +61,8 @@ def run_fused_batch(engine, env, policy, seeds: Sequence[Optional[int]]) -> Roll
     seeds_u64 = np.asarray([seed_to_u64(s) for s in seeds], dtype=np.uint64)
     out = logs.as_struct()
     s = policy.sampling()
-    check(engine.lib.lmrl_rollout_host(engine.handle, env._lmrl_kind, ptr(seeds_u64), None, n, C.byref(s), C.byref(out)))
+    opt_pos = env.fused_options(options) if hasattr(env, "fused_options") else None
+    check(engine.lib.lmrl_rollout_host(engine.handle, env._lmrl_kind, ptr(seeds_u64), ptr(opt_pos), n, C.byref(s), C.byref(out)))
     return logs
 
 
@@ -113,11 +114,71 @@ class WordleEpisode(Sequence):
         return iter(self._cache)
 
 
+class MazeEpisode(Sequence):
+    """One Maze episode's ``List[InteractionTransition]`` rebuilt from the device logs (maze/env/env.py:161-184):
+    ``step_aux = outcome | cell_after << 8 | cell_before << 20``, ``step_valid`` = the action string was a known move."""
+
+    def __init__(self, logs: RolloutLogs, i: int, tokenizer, env, out_str_process):
+        self._logs, self._i, self._tok, self._env = logs, i, tokenizer, env
+        self._out = out_str_process or default_out_str_process
+        self._len = int(logs.ep_length[i])
+        self._cache: Optional[List[InteractionTransition]] = None
+
+    def __len__(self):
+        return self._len
+
+    def action_text(self, t: int) -> str:
+        L, i = self._logs, self._i
+        return self._out(self._tok.decode(L.act_tokens[i, t, :L.act_len[i, t]].tolist()))
+
+    def _build(self) -> List[InteractionTransition]:
+        L, i, env = self._logs, self._i, self._env
+        out = []
+        hist: Tuple[Text, ...] = ()
+        for t in range(self._len):
+            aux = int(L.step_aux[i, t])
+            outcome, cell, cell0 = aux & 0xFF, (aux >> 8) & 0xFFF, (aux >> 20) & 0xFFF
+            if t == 0:
+                hist = (Text(env.describe_cell(cell0), False),)
+            post_action = hist + (Text(self.action_text(t), True),)
+            if outcome == 2:
+                nxt: Tuple[Text, ...] = (Text("Failure\n", False),)
+            elif outcome == 1:
+                nxt = (Text("Success\n", False),)
+            else:
+                obs = Text(env.describe_cell(cell), False)
+                if not L.step_valid[i, t]:
+                    nxt = (obs,)
+                else:
+                    full = post_action + (obs,)
+                    nxt = full[max(0, len(full) - env.last_k):]
+            done = bool(L.ep_done[i]) if t == self._len - 1 else False
+            out.append(InteractionTransition(hist, post_action, nxt, float(L.step_reward[i, t]), done))
+            hist = nxt
+        return out
+
+    def __getitem__(self, k):
+        if self._cache is None:
+            self._cache = self._build()
+        return self._cache[k]
+
+    def __iter__(self):
+        if self._cache is None:
+            self._cache = self._build()
+        return iter(self._cache)
+
+
+def _episode_cls(env):
+    return MazeEpisode if env._lmrl_kind == ENV_MAZE else WordleEpisode
+
+
 def episode_returns(logs: RolloutLogs, env) -> np.ndarray:
     """Per-episode sum of rewards in step order, in float64 like the reference's Python ``sum`` (environment.py:238)."""
     n, T = logs.n, logs.T
     r = logs.step_reward.astype(np.float64)
-    if env.require_words_in_vocab:
+    if env._lmrl_kind == ENV_MAZE:
+        pass                                   # Maze rewards are floats as produced (env.py:109-131)
+    elif env.require_words_in_vocab:
         r = np.where(logs.step_valid.astype(bool), r, env.bad_word_reward)
     else:
         # a legal guess outside the vocabulary earns bad_word_reward; the device already wrote that value
@@ -133,8 +194,9 @@ def fused_interact(engine, env, policy, env_seed, env_options, bsize: int):
         raise _lib.LmrlError("policy has custom in/out string processing; use the generic loop")
     seeds = [None] * bsize if env_seed is None else list(env_seed)
     assert len(seeds) == bsize
-    logs = run_fused_batch(engine, env, policy, seeds)
-    return [WordleEpisode(logs, i, engine.tokenizer, env, policy.out_str_process) for i in range(bsize)]
+    logs = run_fused_batch(engine, env, policy, seeds, env_options)
+    cls = _episode_cls(env)
+    return [cls(logs, i, engine.tokenizer, env, policy.out_str_process) for i in range(bsize)]
 
 
 def fused_text_env_eval(engine, env, policy, n_rollouts: int, seed_generator: Optional[Iterator[int]], env_options: Optional[Dict],
@@ -146,8 +208,9 @@ def fused_text_env_eval(engine, env, policy, n_rollouts: int, seed_generator: Op
     while len(interactions) < n_rollouts:
         actual = min(n_rollouts - len(interactions), bsize)
         seeds = [None] * actual if seed_generator is None else [next(seed_generator) for _ in range(actual)]
-        logs = run_fused_batch(engine, env, policy, seeds)
-        eps = [WordleEpisode(logs, i, engine.tokenizer, env, policy.out_str_process) for i in range(actual)]
+        logs = run_fused_batch(engine, env, policy, seeds, None if env_options is None else [env_options] * actual)
+        cls = _episode_cls(env)
+        eps = [cls(logs, i, engine.tokenizer, env, policy.out_str_process) for i in range(actual)]
         interactions.extend(eps)
         rewards.append(episode_returns(logs, env))
         dones.append(logs.ep_done.astype(bool))
