@@ -33,6 +33,9 @@ import numpy as np  # noqa: E402
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 WORKLOAD = "wordle_official(2315 words) x GPT-2-small(random init, seed 0), 6 turns, max_new_tokens=6, max_input_length=256"
+# BASELINE.json configs[2] (not the headline; `--workload maze_po_medium`): partially observed double-T maze, GPT-2-medium shapes
+WORKLOAD_MAZE = ("double_t_maze partially observed (describe_observation_only_walls, last_k=40, max_steps=100) x GPT-2-medium"
+                 "(random init, seed 0), max_new_tokens=3, max_input_length=512")
 
 
 def load_peaks():
@@ -81,10 +84,19 @@ class ClockSampler:
                     power_w_max=max(power) if power else None, samples=len(sm))
 
 
-def build_policy_params():
+def build_policy_params(medium: bool = False):
     from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params
-    cfg = GPT2Config.small()
+    cfg = GPT2Config.medium() if medium else GPT2Config.small()
     return cfg, init_gpt2_params(cfg, seed=0)
+
+
+def cpu_reference_numbers(params, cfg, tok, bs, seed=0):
+    """The CPU restatement of the reference path on all host threads, two ways: *charitable* = prompts padded to the
+    longest in the batch, *faithful* = LEFT-padded to max_input_length=256 as wordle/bc/eval_bc_gpt2.py:100-104 does."""
+    from oracle.cpu_rollout import run_cpu_wordle
+    char = run_cpu_wordle(params, cfg, tok, n_rollouts=bs, bsize=bs, seed=seed)
+    faith = run_cpu_wordle(params, cfg, tok, n_rollouts=max(bs // 4, 4), bsize=max(bs // 4, 4), seed=seed, pad_to_max_input=True)
+    return char, faith
 
 
 def run_reference(args):
@@ -105,11 +117,15 @@ def run_reference(args):
         r = run_cpu_wordle(params, cfg, tok, n_rollouts=bs, bsize=bs, seed=k)
         steps_total += r["env_steps"]; secs += r["seconds"]
     value = steps_total / secs
-    sample = f"{args.steps} x text_env_eval(n_rollouts={bs}, bsize={bs}) episodes of the same workload, prompts padded to the longest in the batch"
+    faith = run_cpu_wordle(params, cfg, tok, n_rollouts=max(bs // 4, 4), bsize=max(bs // 4, 4), seed=0, pad_to_max_input=True)
+    sample = (f"{args.steps} x text_env_eval(n_rollouts={bs}, bsize={bs}) episodes of the same workload, prompts padded to the longest in the batch "
+              f"(charitable); faithful variant (LEFT-padded to 256 tokens, eval_bc_gpt2.py:100-104) on {max(bs // 4, 4)} episodes: "
+              f"{faith['env_steps_per_s']:.2f} env-steps/s")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 * secs / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(workload=WORKLOAD, batch_per_step=bs, policy="transformers GPT2LMHeadModel.generate torch-CPU fp32"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample, host_cpus=os.cpu_count()),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample, host_cpus=os.cpu_count(),
+                                  faithful_value=faith["env_steps_per_s"]),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -123,14 +139,18 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="concurrent episodes per GPU")
     ap.add_argument("--ref-batch", type=int, default=32, help="episodes per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="wordle", choices=["wordle", "maze_po_medium"])
+    ap.add_argument("--no-profile", action="store_true", help="do not record per-launch CUDA events in the timed region")
     args = ap.parse_args()
+    if args.workload == "maze_po_medium" and args.batch == 4096:
+        args.batch = 1024
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
     from lmrl_gym_b200 import _lib
-    from lmrl_gym_b200.engine import Engine, ENV_WORDLE
+    from lmrl_gym_b200.engine import Engine, ENV_MAZE, ENV_WORDLE
     from lmrl_gym_b200.environment import text_env_eval
     from lmrl_gym_b200.gpt2 import B200GPT2Policy
     from lmrl_gym_b200.tokenizer import ByteTokenizer
@@ -146,9 +166,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, K, W = args.batch, args.steps, max(args.warmup, 0)
     tok = ByteTokenizer.synthetic()
-    cfg, params = build_policy_params()
-    eng = Engine(max_envs=B, device=local, max_input_length=256, max_new_tokens=6, max_turns=6, tokenizer=tok)
-    env = B200WordleEnv(eng, "wordle_official.txt")
+    maze = args.workload == "maze_po_medium"
+    cfg, params = build_policy_params(medium=maze)
+    if maze:
+        from lmrl_gym_b200.maze import B200MazeEnv
+        eng = Engine(max_envs=B, device=local, max_input_length=512, max_new_tokens=3, max_turns=101, tokenizer=tok)
+        env = B200MazeEnv(eng, "double_t_maze", "describe_observation_only_walls", "standard_reward", last_k=40, max_steps=100)
+        env_kind, workload = ENV_MAZE, WORKLOAD_MAZE
+    else:
+        eng = Engine(max_envs=B, device=local, max_input_length=256, max_new_tokens=6, max_turns=6, tokenizer=tok)
+        env = B200WordleEnv(eng, "wordle_official.txt")
+        env_kind, workload = ENV_WORDLE, WORKLOAD
     pol = B200GPT2Policy(eng, params, cfg, seed=0)
     sampling = pol.sampling()
 
@@ -165,7 +193,7 @@ def main():
         out = None
         if out_k is not None:
             out = _lib.lmrl_rollout_out(ep_ret_dev[out_k].data_ptr(), ep_len_dev[out_k].data_ptr(), None, None, None, None, None, None, None)
-        eng.rollout_dev(ENV_WORDLE, seeds_dev[step_idx].data_ptr(), B, sampling, out)
+        eng.rollout_dev(env_kind, seeds_dev[step_idx].data_ptr(), B, sampling, out)
 
     def barrier():
         if world > 1:
@@ -177,7 +205,7 @@ def main():
     eng.sync()
     barrier()
     eng.launch_count(reset=True)
-    eng.profile_enable(True)
+    eng.profile_enable(not args.no_profile)
     clocks = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -222,37 +250,71 @@ def main():
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     e2e_value = float(s.item()) / float(t.item())
 
+    # ---- env kernels alone (variant 2b): device RandomMixturePolicy(prob_smart=0.5)-equivalent actions, no policy forward
+    env_only = None
+    if rank == 0 and not maze:
+        out_env = _lib.lmrl_rollout_out(ep_ret_dev[0].data_ptr(), ep_len_dev[0].data_ptr(), torch.zeros(B, dtype=torch.uint8, device="cuda").data_ptr(),
+                                        None, None, None, None, None, None)
+        for _ in range(3):
+            eng.wordle_scripted_rollout_dev(seeds_dev[0].data_ptr(), B, 0.5, 7, out_env)
+        eng.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, env_steps_only = 20, 0
+        e0.record(stream)
+        for r in range(reps):
+            eng.wordle_scripted_rollout_dev(seeds_dev[r % n_steps_total].data_ptr(), B, 0.5, 7 + r, out_env)
+        e1.record(stream)
+        eng.sync()
+        env_steps_only = int(ep_len_dev[0].sum().item()) * reps          # last batch's count x reps (all batches are statistically alike)
+        env_only = dict(value=env_steps_only / (e0.elapsed_time(e1) / 1000.0), unit=UNIT,
+                        variant="2b: env kernels only, device RandomMixturePolicy(prob_smart=0.5) equivalent (every action a legal word)",
+                        mean_episode_length=float(ep_len_dev[0].float().mean().item()), ms_per_batch=e0.elapsed_time(e1) / reps)
+
     if rank == 0:
         peaks = load_peaks()
         gemm_ms, gemm_flops = prof["ms"]["gemm"], prof["work"]["gemm"]
+        att = prof["tags"].get("attention_decode", dict(ms=0.0, work=0.0))
+        att_gbs = att["work"] / (att["ms"] / 1000.0) / 1e9 if att["ms"] > 0 else 0.0
         achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
         total_kernel_ms = sum(prof["ms"].values())
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms / K, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-            config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world} (episodes sharded, no collective)",
+            config=dict(workload=workload, batch_per_gpu=B, global_batch=B * world, parallelism=f"dp{world} (episodes sharded, no collective)",
                         l2_policy="inputs larger than L2 (KV cache %.1f GB per GPU)" % (eng.device_bytes / 1e9), tokenizer=tok.name,
-                        policy_variant="2a: random-init GPT-2-small (actions are malformed guesses; every episode runs 6 turns)"),
+                        policy_variant=("random-init GPT-2-medium (every action is an unknown string: 101 turns, the history collapses to the observation)" if maze else
+                                        "2a: random-init GPT-2-small (actions are malformed guesses; every episode runs 6 turns)"),
+                        per_launch_events_in_timed_region=not args.no_profile),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api="lmrl_gym_b200.text_env_eval"),
             gpu_launches=total_launches,
             clocks=clock_info,
             roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (tcgen05.mma UMMA 128x256x16 + TMA + TMEM, all epilogues)", achieved=achieved, peak=peak,
                           unit="TFLOP/s", frac=achieved / peak, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=None,
                           flops_per_step=gemm_flops / K, launches_per_step=prof["launches"]["gemm"] / K,
-                          share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None),
+                          share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None,
+                          # the HBM-bound batched GEMV of the path (north_star's "decode GEMV"): KV-cache attention of the decode passes
+                          decode_attention_hbm=dict(kernel="attention_kernel (decode passes)", achieved=att_gbs, peak=peaks["hbm_gbs"], unit="GB/s",
+                                                    frac=att_gbs / peaks["hbm_gbs"], bytes_per_step=att["work"] / K,
+                                                    peak_source=f"{peaks['source']} hbm_gbs",
+                                                    algorithmic_bytes="every cached K and V position of the live envs once (bf16) + q / out rows")),
             kernel_ms_per_step={k: v / K for k, v in prof["ms"].items()},
-            gemm_attention_split={k: dict(ms_per_step=round(v["ms"] / K, 3), tflops=round(v["work"] / (v["ms"] / 1000.0) / 1e12, 1) if v["ms"] > 0 and v["work"] > 0 else None)
+            gemm_attention_split={k: dict(ms_per_step=round(v["ms"] / K, 3),
+                                          **({"gbs": round(v["work"] / (v["ms"] / 1000.0) / 1e9, 1)} if k.startswith("attention") else
+                                             {"tflops": round(v["work"] / (v["ms"] / 1000.0) / 1e12, 1)}) if v["ms"] > 0 and v["work"] > 0 else {})
                                   for k, v in prof["tags"].items()},
             decoder_rows_per_step=prof["rows"] / K, sampled_tokens_per_step=prof["sampled"] / K,
             mean_return=float(ep_ret_dev.mean().item()),
         )
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle.cpu_rollout import run_cpu_wordle
-            r = run_cpu_wordle(params, cfg, tok, n_rollouts=args.ref_batch, bsize=args.ref_batch)
+        if env_only is not None:
+            line["env_only"] = env_only
+        if world == 1 and not args.no_cpu_baseline and not maze:
+            r, rf = cpu_reference_numbers(params, cfg, tok, args.ref_batch)
             line["cpu_baseline"] = dict(value=r["env_steps_per_s"], unit=UNIT, cores=r["cores"], kind="port", host_cpus=r["host_cpus"],
                                         sample=f"text_env_eval(n_rollouts={args.ref_batch}, bsize={args.ref_batch}) of the same workload "
-                                               f"({r['env_steps']} env-steps in {r['seconds']:.1f} s), prompts padded to the longest in the batch")
+                                               f"({r['env_steps']} env-steps in {r['seconds']:.1f} s), prompts padded to the longest in the batch (charitable)",
+                                        faithful_value=rf["env_steps_per_s"],
+                                        faithful_sample=f"prompts LEFT-padded to 256 tokens as eval_bc_gpt2.py:100-104 ({rf['env_steps']} env-steps in {rf['seconds']:.1f} s)")
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -70,30 +70,39 @@ struct lmrl_engine {
     lmrl::Gpt2Dev* gpt2 = nullptr;
 
     // optional per-launch timing (bench.py): CUDA events around every launch, grouped by category
-    struct ProfRec { int cat; int ev; double work_per_row; int count_slot; int tag; };   // work = flops (gemm) per live row
+    // work = work_per_row * h_counts[count_slot] (+ work2_per_row * h_counts[count_slot2]): GEMM FLOPs per live row,
+    // attention bytes per cached key position (+ per row)
+    struct ProfRec { int cat; int ev; double work_per_row; int count_slot; int tag; double work2_per_row; int count_slot2; };
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<ProfRec> prof;
-    int32_t* h_counts = nullptr;      // pinned: [2 * max_passes] (rows, slots) per forward pass
+    int32_t* h_counts = nullptr;      // pinned: [3 * max_passes] (rows, slots, sum of context lengths) per forward pass
     int n_passes = 0, max_passes = 0;
     int cur_pass_slot = -1;
     int cur_mode = 0;                 // 0 prefill pass, 1 decode pass (profiling tag)
 
-    int prof_begin(int cat, double work_per_row = 0.0, int count_kind = 0, int tag = -1) {
+    // One event per launch boundary: launch i runs from event i to event i+1 (the next launch's begin, or the closing event that
+    // profile_read records), so a launch's time includes the gap to its successor — two events per launch cost ~6 % of a step.
+    int prof_begin(int cat, double work_per_row = 0.0, int count_kind = 0, int tag = -1, double work2_per_row = 0.0, int count_kind2 = 0) {
         if (!profile) return 0;
         const int i = (int)prof.size();
-        while ((int)ev_pool.size() < 2 * (i + 1)) {
+        while ((int)ev_pool.size() < i + 2) {
             cudaEvent_t ev;
             if (cudaEventCreate(&ev) != cudaSuccess) return lmrl::fail("cudaEventCreate failed");
             ev_pool.push_back(ev);
         }
-        prof.push_back({cat, 2 * i, work_per_row, cur_pass_slot < 0 ? -1 : 2 * cur_pass_slot + count_kind, tag});
-        cudaEventRecord(ev_pool[2 * i], stream);
+        prof.push_back({cat, i, work_per_row, cur_pass_slot < 0 ? -1 : 3 * cur_pass_slot + count_kind, tag, work2_per_row,
+                        cur_pass_slot < 0 ? -1 : 3 * cur_pass_slot + count_kind2});
+        cudaEventRecord(ev_pool[i], stream);
         return 0;
     }
-    void prof_end() {
-        if (!profile) return;
-        cudaEventRecord(ev_pool[prof.back().ev + 1], stream);
+    void prof_end() {}
+    size_t prof_closed_at = 0;
+    // closing event of the most recent launch; the next prof_begin re-records the same event, moving the boundary forward
+    void prof_close() {
+        if (!profile || prof.empty()) return;
+        cudaEventRecord(ev_pool[prof.size()], stream);
+        prof_closed_at = prof.size();
     }
 
     template <typename T>

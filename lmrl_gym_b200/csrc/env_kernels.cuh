@@ -86,7 +86,18 @@ struct ActionSrc {
     const uint8_t* bytes; const int32_t* nbytes; int32_t pitch;
     // fused path: sampled token ids per env (bytes == nullptr)
     const int32_t* tokens; const int32_t* ntokens; int32_t tpitch;
+    // scripted path (env microbenchmark): the device equivalent of RandomMixturePolicy (wordle/env/scripted_policies.py:114-126):
+    // with probability prob_smart a uniformly random word of the FILTERED vocabulary, else of the whole vocabulary;
+    // draws come from a counter hash of (policy_seed, episode seed, turn) instead of the reference's global `random`
+    int32_t scripted; float prob_smart; uint64_t policy_seed; const uint64_t* episode_seed;
 };
+
+__device__ __forceinline__ uint64_t env_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
@@ -176,7 +187,20 @@ __global__ void wordle_step_kernel(WordleDev w, TokenizerDev tk, ActionSrc src, 
 
     // E2: action text -> code points -> strip / de-space -> packed guess
     int ncp = 0;
-    if (lane == 0) {
+    if (src.scripted) {
+        WordleKnow k0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { k0.here[i] = w.know[e * 10 + i]; k0.ban[i] = w.know[e * 10 + 5 + i]; }
+        const uint64_t h = env_mix64(env_mix64(src.policy_seed ^ env_mix64(src.episode_seed[e])) + (uint64_t)w.n_actions[e]);
+        const bool smart = (float)((h >> 40) & 0xFFFFFFull) * (1.0f / 16777216.0f) < src.prob_smart;
+        const int nf = w.n_filtered[e];
+        uint32_t word;
+        if (smart && nf > 0) word = warp_select_kth(wordle_masks(k0), w.words, w.n_words, (int)((uint32_t)h % (uint32_t)nf));
+        else word = __ldg(w.words + (uint32_t)h % (uint32_t)w.n_words);
+        if (lane == 0)
+            for (int i = 0; i < 5; ++i) s.cp[i] = 'a' + ((word >> (5 * i)) & 31u);
+        ncp = 5;
+    } else if (lane == 0) {
         const uint8_t* bytes; int nb;
         if (src.bytes) { bytes = src.bytes + (size_t)e * src.pitch; nb = min(src.nbytes[e], MAX_ACTION_CP); }
         else {
@@ -416,6 +440,30 @@ __global__ void maze_fused_step_kernel(MazeDev m, TokenizerDev tk, ActionSrc src
         len = st.max_input; m.cut[e] += drop; kv = 0;
     }
     st.len[e] = len; st.kv_len[e] = kv;
+}
+
+// scripted rollouts: per-turn log (an env acted this turn iff its action count ran ahead of the logged length)
+__global__ void log_scripted_turn_kernel(int n, int max_turns, int act_pitch, WordleDev w, StepOut step, float* ep_return, int32_t* ep_length,
+                                         uint8_t* ep_done, float* step_reward, uint8_t* step_valid, uint8_t* step_fb, int32_t* step_aux,
+                                         int32_t* act_tokens, int32_t* act_len) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int t = ep_length[e];
+    if (w.n_actions[e] != t + 1 || t >= max_turns) return;
+    const size_t o = (size_t)e * max_turns + t;
+    if (step_reward) step_reward[o] = step.reward[e];
+    if (step_valid) step_valid[o] = step.valid[e];
+    if (step_aux) step_aux[o] = step.aux[e];
+    if (step_fb) for (int i = 0; i < 5; ++i) step_fb[o * 5 + i] = step.fb[e * 5 + i];
+    if (act_tokens) act_tokens[o * act_pitch] = (int32_t)w.hist[e * WORDLE_TRIES + t];      // the packed 5-letter guess
+    if (act_len) act_len[o] = 1;
+    ep_return[e] += step.reward[e];
+    ep_length[e] = t + 1;
+    ep_done[e] = step.done[e];
+}
+__global__ void clear_episode_log_kernel(int n, float* ep_return, int32_t* ep_length, uint8_t* ep_done) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) { ep_return[e] = 0.f; ep_length[e] = 0; ep_done[e] = 0; }
 }
 
 // live-episode count for the periodic early-exit test of long rollouts

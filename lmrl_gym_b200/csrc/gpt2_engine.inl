@@ -261,8 +261,9 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     LMRL_LAUNCH(2, build_rows_kernel<<<1, 1024, 0, st>>>(mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     if (e->profile && e->n_passes < e->max_passes) {      // live row / slot counts of this pass, for the FLOP accounting
         e->cur_pass_slot = e->n_passes++;
-        cudaMemcpyAsync(e->h_counts + 2 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(e->h_counts + 2 * e->cur_pass_slot + 1, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 1, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 2, G.rows.ctx_total, sizeof(int), cudaMemcpyDeviceToHost, st);
     }
     if (mode == 0)
         LMRL_LAUNCH(2, fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
@@ -282,7 +283,8 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
             a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
             a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
             if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
-            if (e->prof_begin(1, 0.0, 0, 10 + mode)) return -1;
+            // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
+            if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
             if (mode == 0)
                 LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
                                                            ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
@@ -353,7 +355,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
         e->alloc(&G.xl1, (size_t)((B + 127) / 128 * 128) * D.d_model))
         return -1;
     G.xl_cols = 3 * D.d_model;
-    if (e->alloc(&G.rows.M, 1) || e->alloc(&G.rows.n_slots, 1) || e->alloc(&G.rows.row_env, G.m_cap) || e->alloc(&G.rows.row_pos, G.m_cap) ||
+    if (e->alloc(&G.rows.M, 1) || e->alloc(&G.rows.n_slots, 1) || e->alloc(&G.rows.ctx_total, 1) || e->alloc(&G.rows.row_env, G.m_cap) || e->alloc(&G.rows.row_pos, G.m_cap) ||
         e->alloc(&G.rows.row_tok, G.m_cap) || e->alloc(&G.rows.slot_env, B) || e->alloc(&G.rows.slot_row0, B) ||
         e->alloc(&G.rows.slot_nrow, B) || e->alloc(&G.rows.slot_last, B))
         return -1;
@@ -639,6 +641,7 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
             if (live == 0) break;
         }
     }
+    e->prof_close();
     LMRL_CUDA(cudaGetLastError());
     return 0;
 }
@@ -682,8 +685,29 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
     return rollout_export(e, n, out_dev, cudaMemcpyDeviceToDevice);
 }
 
-int lmrl_wordle_scripted_rollout_dev(lmrl_engine*, const uint64_t*, int32_t, float, uint64_t, lmrl_rollout_out*) {
-    return lmrl::fail("lmrl_wordle_scripted_rollout_dev: not implemented yet");
+int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, int32_t n, float prob_smart, uint64_t policy_seed,
+                                     lmrl_rollout_out* out) {
+    LMRL_CHECK(e && e->has_wordle, "lmrl_wordle_scripted_rollout: no Wordle vocabulary loaded");
+    LMRL_CHECK(seeds_dev && out && out->ep_return && out->ep_length && out->ep_done, "lmrl_wordle_scripted_rollout: seeds and the per-episode outputs are required");
+    LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "lmrl_wordle_scripted_rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
+    LMRL_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const int T = e->cfg.max_turns;
+    const int blocks = (n + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK;
+    LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
+    LMRL_LAUNCH(3, clear_episode_log_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, out->ep_return, out->ep_length, out->ep_done));
+    ActionSrc src{};
+    src.scripted = 1; src.prob_smart = prob_smart; src.policy_seed = policy_seed; src.episode_seed = seeds_dev;
+    StreamDev none{};
+    for (int turn = 0; turn < std::min(T, (int)WORDLE_TRIES); ++turn) {
+        LMRL_LAUNCH(3, wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(
+                           e->wordle, e->tok, src, nullptr, e->step, none, n));
+        LMRL_LAUNCH(3, log_scripted_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, e->cfg.max_new_tokens, e->wordle, e->step, out->ep_return,
+                                                                                 out->ep_length, out->ep_done, out->step_reward, out->step_valid,
+                                                                                 out->step_feedback, out->step_aux, out->act_tokens, out->act_len));
+    }
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl) {
@@ -814,10 +838,11 @@ int lmrl_profile_enable(lmrl_engine* e, int32_t enable) {
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     e->profile = enable ? 1 : 0;
     e->prof.clear();
+    e->prof_closed_at = 0;
     e->n_passes = 0;
     if (enable && !e->h_counts) {
         e->max_passes = 1 << 16;
-        LMRL_CUDA(cudaMallocHost(&e->h_counts, sizeof(int32_t) * 2 * e->max_passes));
+        LMRL_CUDA(cudaMallocHost(&e->h_counts, sizeof(int32_t) * 3 * e->max_passes));
     }
     return 0;
 }
@@ -825,6 +850,7 @@ int lmrl_profile_enable(lmrl_engine* e, int32_t enable) {
 int lmrl_profile_read(lmrl_engine* e, lmrl_profile_out* out) {
     LMRL_CHECK(e && out, "null argument");
     LMRL_CUDA(cudaSetDevice(e->device));
+    if (e->prof_closed_at != e->prof.size()) e->prof_close();
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     memset(out, 0, sizeof *out);
     for (const auto& r : e->prof) {
@@ -832,11 +858,12 @@ int lmrl_profile_read(lmrl_engine* e, lmrl_profile_out* out) {
         LMRL_CUDA(cudaEventElapsedTime(&ms, e->ev_pool[r.ev], e->ev_pool[r.ev + 1]));
         out->ms[r.cat] += ms;
         out->launches[r.cat] += 1;
-        const double work = r.count_slot >= 0 ? r.work_per_row * (double)e->h_counts[r.count_slot] : 0.0;
+        double work = r.count_slot >= 0 ? r.work_per_row * (double)e->h_counts[r.count_slot] : 0.0;
+        if (r.count_slot2 >= 0 && r.work2_per_row != 0.0) work += r.work2_per_row * (double)e->h_counts[r.count_slot2];
         out->work[r.cat] += work;
         if (r.tag >= 0 && r.tag < 12) { out->tag_ms[r.tag] += ms; out->tag_work[r.tag] += work; }
     }
-    for (int p = 0; p < e->n_passes; ++p) { out->rows += e->h_counts[2 * p]; out->sampled += e->h_counts[2 * p + 1]; }
+    for (int p = 0; p < e->n_passes; ++p) { out->rows += e->h_counts[3 * p]; out->sampled += e->h_counts[3 * p + 1]; }
     return 0;
 }
 

@@ -25,6 +25,7 @@ struct RowsDev {
     int* slot_row0;    // [B]   first row of the slot
     int* slot_nrow;    // [B]
     int* slot_last;    // [B]   row index of the slot's last row (the one that is sampled from)
+    int* ctx_total;    // [1]   sum over slots of (last position + 1): cached key positions attention must read this pass
 };
 
 struct GenDev {
@@ -45,14 +46,15 @@ __global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ d
     __shared__ int warp_sums[2][32];
     __shared__ int carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    if (tid == 0) { carry[0] = 0; carry[1] = 0; }
+    if (tid == 0) { carry[0] = 0; carry[1] = 0; *rows.ctx_total = 0; }
     __syncthreads();
+    int ctx = 0;
     for (int base = 0; base < B; base += blockDim.x) {
         const int e = base + tid;
         int n = 0;
         if (e < B) {
-            if (mode == 0) n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0);
-            else n = gen.active[e] ? 1 : 0;
+            if (mode == 0) { n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0); if (n > 0) ctx += stream_len[e]; }
+            else { n = gen.active[e] ? 1 : 0; if (n > 0) ctx += gen.cur[e] + 1; }
         }
         const int has = n > 0;
         int xs = n, xh = has;      // inclusive warp scans of rows and of slots
@@ -88,6 +90,9 @@ __global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ d
         __syncthreads();
     }
     if (tid == 0) { *rows.M = carry[0]; *rows.n_slots = carry[1]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ctx += __shfl_xor_sync(0xFFFFFFFFu, ctx, o);
+    if (lane == 0 && ctx) atomicAdd(rows.ctx_total, ctx);
 }
 
 // prefill: expand each slot into its rows (one warp per slot); also resets the per-turn generation state

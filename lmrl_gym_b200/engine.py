@@ -78,6 +78,12 @@ class Engine:
         check(self.lib.lmrl_rollout_dev(self.handle, env_kind, seeds_dev_ptr, None, n, C.byref(sampling),
                                         None if out_struct is None else C.byref(out_struct)))
 
+    def wordle_scripted_rollout_dev(self, seeds_dev_ptr: int, n: int, prob_smart: float, policy_seed: int, out_struct):
+        """Env-only rollout with the device equivalent of ``RandomMixturePolicy(prob_smart)`` (scripted_policies.py:114-126);
+        all pointers are device pointers; ``act_tokens[..., 0]`` receives the packed 5-letter guess of every turn."""
+        check(self.lib.lmrl_wordle_scripted_rollout_dev(self.handle, seeds_dev_ptr, n, float(prob_smart), int(policy_seed) & ((1 << 64) - 1),
+                                                        C.byref(out_struct)))
+
     def set_gemm_impl(self, impl: int):
         """1 = tcgen05/TMEM/TMA (default), 0 = the mma.sync kernel (independent cross-check used by the tests)."""
         check(self.lib.lmrl_set_gemm_impl(self.handle, int(impl)))

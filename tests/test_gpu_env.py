@@ -139,3 +139,53 @@ def test_wordle_env_large_batch_vs_oracle():
             assert [[x.text, x.is_action] for x in t.post_transition_history] == [[a, b] for a, b in h]
             assert t.reward == rew and type(t.reward) is type(rew) and t.done == d
     eng.close()
+
+
+def test_scripted_random_mixture_rollout_replays_through_oracle():
+    """Env-only rollout (variant 2b of the bench): device RandomMixturePolicy-equivalent actions (every one a legal word, half of
+    them drawn from the filtered vocabulary) exercise target draw / transition / re-filter / win detection; every
+    transition is replayed through the CPU oracle env bit-exactly."""
+    import torch
+    from lmrl_gym_b200 import _lib
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200.vocab import load_vocab_words
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from oracle.mt19937 import seed_stream
+    from oracle.wordle import ReformatWordleOracle
+    n, T, K = 512, 6, 6
+    eng = Engine(max_envs=n, max_new_tokens=K, max_turns=T, tokenizer=ByteTokenizer.synthetic())
+    B200WordleEnv(eng, "wordle_official.txt")
+    gen = seed_stream(9)
+    seeds = np.asarray([next(gen) for _ in range(n)], dtype=np.uint64)
+    dev = torch.device("cuda", 0)
+    seeds_dev = torch.from_numpy(seeds.view(np.int64)).to(dev)
+    ep_ret = torch.zeros(n, dtype=torch.float32, device=dev); ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+    ep_done = torch.zeros(n, dtype=torch.uint8, device=dev); rew = torch.zeros((n, T), dtype=torch.float32, device=dev)
+    valid = torch.zeros((n, T), dtype=torch.uint8, device=dev); fb = torch.zeros((n, T, 5), dtype=torch.uint8, device=dev)
+    aux = torch.zeros((n, T), dtype=torch.int32, device=dev); act = torch.zeros((n, T, K), dtype=torch.int32, device=dev)
+    alen = torch.zeros((n, T), dtype=torch.int32, device=dev)
+    out = _lib.lmrl_rollout_out(ep_ret.data_ptr(), ep_len.data_ptr(), ep_done.data_ptr(), rew.data_ptr(), valid.data_ptr(), fb.data_ptr(),
+                                aux.data_ptr(), act.data_ptr(), alen.data_ptr())
+    eng.wordle_scripted_rollout_dev(seeds_dev.data_ptr(), n, 0.5, 1234, out)
+    eng.sync()
+    ep_len_h, ep_ret_h, rew_h, fb_h, aux_h, act_h = (t.cpu().numpy() for t in (ep_len, ep_ret, rew, fb, aux, act))
+    words = load_vocab_words("wordle_official.txt")
+    wins = 0
+    for i in range(n):
+        o = ReformatWordleOracle(words)
+        h = o.reset(int(seeds[i]))
+        total = 0.0
+        for t in range(int(ep_len_h[i])):
+            w = int(act_h[i, t, 0]) & 0xFFFFFFFF
+            word = "".join(chr(ord("a") + ((w >> (5 * j)) & 31)) for j in range(5))
+            assert word in words
+            h, r, d = o.step(h + ((" ".join(word) + "\n", True),))
+            assert float(r) == float(rew_h[i, t]) and len(o.inner.filtered) == int(aux_h[i, t]), (i, t)
+            assert h[-1][0] == " ".join("gyb"[c] for c in fb_h[i, t]) + "\n"
+            assert d == (t == ep_len_h[i] - 1)
+            total += r
+        assert total == float(ep_ret_h[i])
+        wins += rew_h[i, ep_len_h[i] - 1] == 0.0
+    assert 1 <= ep_len_h.min() and ep_len_h.max() == 6 and wins > 0
+    eng.close()

@@ -206,3 +206,26 @@ def test_generic_act_path_runs_device_env_and_policy(tok):
     assert len(inter) == 20 and all(len(ep) == 6 and ep[-1].done for ep in inter)
     assert float(summary["reward"]["mean"]) == -6.0
     eng.close()
+
+
+def test_logits_match_oracle_gpt2_medium_shape(tok):
+    """Config 3's architecture (24 layers, 16 heads, d_model 1024): N = 3072 / 1024 / 4096 GEMM shapes, d = 1024 LayerNorm."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    cfg = GPT2Config.medium()
+    params = init_gpt2_params(cfg, seed=0)
+    eng = Engine(max_envs=16, max_input_length=40, max_new_tokens=2, tokenizer=tok)
+    pol = B200GPT2Policy(eng, params, cfg)
+    rng = np.random.default_rng(4)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(3, 40, size=12)]
+    got = pol.logits(prompts)
+    worst_emu = worst_f32 = 0.0
+    for i in (0, 5, 11):
+        emu = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+        f32 = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab)
+        worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+        worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+    print(f"gpt2-medium: max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
+    assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
+    eng.close()
