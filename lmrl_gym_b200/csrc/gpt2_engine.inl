@@ -268,7 +268,6 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     if (mode == 0)
         LMRL_LAUNCH(2, fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
-    const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     const int n_towers = G.policy_kind == 1 ? 2 : 1;
     const size_t xl_rows = (size_t)(e->cfg.max_envs + 127) / 128 * 128;
@@ -290,7 +289,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
                                                            ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                               0.125f * 1.4426950408889634f, G.att));
             else
-                LMRL_LAUNCH(-1, attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                LMRL_LAUNCH(-1, attention_kernel<<<att_blocks, ATT_WARPS * 32, 0, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                                  0.125f, G.att));
             GemmArgs p{};
             p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
@@ -369,9 +368,6 @@ static int gpt2_alloc_state(lmrl_engine* e) {
         e->alloc(&G.step_valid, (size_t)B * T) || e->alloc(&G.step_fb, (size_t)B * T * 5) || e->alloc(&G.step_aux, (size_t)B * T) ||
         e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
         return -1;
-    const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
-    LMRL_CHECK(att_smem <= 227 * 1024, "max_input_length + max_new_tokens = %d positions do not fit the attention kernel's shared memory", G.t_cap);
-    LMRL_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
     LMRL_CUDA(cudaFuncSetAttribute(attention_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTP_WARPS * ATTP_WARP_SMEM));
     return 0;
 }
@@ -792,7 +788,6 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     GemmExtra hx;
     hx.a_cols = (size_t)G.xl_cols;
     const int ew_blocks = G.sm_count * 8;
-    const size_t att_smem = (size_t)G.t_cap * ATT_WARPS * sizeof(float);
     const int att_blocks = std::min((n_slots * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     cudaEvent_t ev[2];
     LMRL_CUDA(cudaEventCreate(&ev[0])); LMRL_CUDA(cudaEventCreate(&ev[1]));
@@ -814,7 +809,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                                                    ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                       0.125f * 1.4426950408889634f, G.att);
                     else
-                        attention_kernel<<<att_blocks, ATT_WARPS * 32, att_smem, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
+                        attention_kernel<<<att_blocks, ATT_WARPS * 32, 0, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
                     break;
                 case 6: layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model); break;
                 case 7: embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x); break;

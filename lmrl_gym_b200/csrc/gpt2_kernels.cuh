@@ -185,11 +185,13 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 }
 
 // ---- K3: causal attention over the slab KV cache, one WARP per (slot, head) ----------------------------------------
-// HBM-bound batched GEMV (~93 % of the decode bytes).  A warp streams the (env, head) K then V slabs
+// HBM-bound batched GEMV (~93 % of the decode bytes).  A warp streams the (env, head) K and V slabs
 // straight from global memory with 16-byte loads: lane = (key group g = lane/8, dim chunk s = lane%8), i.e. every
-// load instruction of the warp covers 4 consecutive keys x 128 B = 512 contiguous bytes.  Scores go to a per-warp
-// shared buffer, soft-max is two warp reductions, P·V accumulates 8 dims per lane and is folded across the 4 key
-// groups with shuffles.  During prefill the warp loops over the slot's rows (K/V re-reads hit L1/L2).
+// load instruction of the warp covers 4 consecutive keys x 128 B = 512 contiguous bytes.  ONE pass with an online
+// soft-max: per step of 16 keys a lane has 4 K and 4 V loads in flight together, the 8 lanes of a key group fold the
+// dot product with shuffles, every key group keeps its own running (max, sum, P·V accumulator) and the four groups
+// are merged once at the end (flash-decoding style).  No shared memory.  During prefill the warp loops over the
+// slot's rows (K/V re-reads hit L1/L2); the tensor-core kernel below is the one used for prefill passes.
 constexpr int ATT_WARPS = 8;
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float f[8]) {
@@ -199,14 +201,12 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float f[8]) {
     f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xFFFF0000u);
 }
 
-__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
-                                                                   const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
-                                                                   int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float att_scores[];                      // [ATT_WARPS][t_cap]
+__global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                      const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
+                                                                      int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, s = lane & 7;
     const int total = *rows.n_slots * n_head;
-    float* sc = att_scores + warp * t_cap;
     for (int w = blockIdx.x * ATT_WARPS + warp; w < total; w += gridDim.x * ATT_WARPS) {
         const int slot = w / n_head, head = w - slot * n_head;
         const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
@@ -221,66 +221,68 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const __nv_bf
 #pragma unroll
                 for (int t = 0; t < 8; ++t) qf[t] *= scale;
             }
-            float mx = -INFINITY;
+            float m = -INFINITY, l = 0.f;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int j0 = 0; j0 < nkeys; j0 += 16) {
-                uint4 kv[4];
+                uint4 kk[4], vv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + 4 * u + g;
-                    kv[u] = j < nkeys ? __ldg(gK + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
+                    const bool ok = j < nkeys;
+                    kk[u] = ok ? __ldg(gK + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
+                    vv[u] = ok ? __ldg(gV + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
                 }
+                float sc[4];
+                float cm = -INFINITY;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + 4 * u + g;
                     float kf[8];
-                    bf16x8_to_float(kv[u], kf);
+                    bf16x8_to_float(kk[u], kf);
                     float dot = 0.f;
 #pragma unroll
                     for (int t = 0; t < 8; ++t) dot = fmaf(qf[t], kf[t], dot);
                     dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 1);
                     dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 2);
                     dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 4);
-                    if (j < nkeys) { if (s == 0) sc[j] = dot; mx = fmaxf(mx, dot); }
+                    sc[u] = (j0 + 4 * u + g < nkeys) ? dot : -INFINITY;
+                    cm = fmaxf(cm, sc[u]);
+                }
+                if (cm > -INFINITY) {                                   // uniform inside a key group
+                    const float m_new = fmaxf(m, cm);
+                    const float corr = __expf(m - m_new);               // m = -inf on the first step: exp(-inf) = 0
+                    l *= corr;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) acc[t] *= corr;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float p = __expf(sc[u] - m_new);          // masked keys: exp(-inf) = 0
+                        float vf[8];
+                        bf16x8_to_float(vv[u], vf);
+                        l += p;
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) acc[t] = fmaf(p, vf[t], acc[t]);
+                    }
+                    m = m_new;
                 }
             }
-            mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 8));
-            mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
-            __syncwarp();
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float sum = 0.f;
-            for (int j0 = 0; j0 < nkeys; j0 += 16) {
-                uint4 vv[4];
-                float wgt[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + 4 * u + g;
-                    const bool ok = j < nkeys;
-                    vv[u] = ok ? __ldg(gV + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
-                    wgt[u] = ok ? __expf(sc[j] - mx) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float vf[8];
-                    bf16x8_to_float(vv[u], vf);
-                    sum += wgt[u];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) acc[t] = fmaf(wgt[u], vf[t], acc[t]);
-                }
-            }
+            // merge the four key groups (lanes differing in bits 3 and 4 hold the same dims)
 #pragma unroll
             for (int o = 8; o <= 16; o <<= 1) {
-                sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                const float m_o = __shfl_xor_sync(0xFFFFFFFFu, m, o), l_o = __shfl_xor_sync(0xFFFFFFFFu, l, o);
+                const float m_n = fmaxf(m, m_o);                        // finite: key 0 always exists
+                const float c1 = m > -INFINITY ? __expf(m - m_n) : 0.f, c2 = m_o > -INFINITY ? __expf(m_o - m_n) : 0.f;
+                l = l * c1 + l_o * c2;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) acc[t] += __shfl_xor_sync(0xFFFFFFFFu, acc[t], o);
+                for (int t = 0; t < 8; ++t) acc[t] = acc[t] * c1 + __shfl_xor_sync(0xFFFFFFFFu, acc[t], o) * c2;
+                m = m_n;
             }
             if (g == 0) {
-                const float inv = 1.0f / sum;
+                const float inv = 1.0f / l;
                 __nv_bfloat162 o2[4];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
                 *reinterpret_cast<uint4*>(out + (size_t)r * d_model + head * 64 + s * 8) = *reinterpret_cast<const uint4*>(o2);
             }
-            __syncwarp();
         }
     }
 }
