@@ -270,6 +270,38 @@ def main():
                         variant="2b: env kernels only, device RandomMixturePolicy(prob_smart=0.5) equivalent (every action a legal word)",
                         mean_episode_length=float(ep_len_dev[0].float().mean().item()), ms_per_batch=e0.elapsed_time(e1) / reps)
 
+    # ---- same engine, policy steered to the token shape of a trained Wordle policy (~5 letter tokens + newline per action):
+    #      prompts grow by ~7 tokens per turn instead of ~20 (SURVEY.md §8d's token counts); secondary number, not the headline
+    letters_variant = None
+    if not maze:
+        from lmrl_gym_b200.gpt2 import steer_to_letters
+        pol.set_params(steer_to_letters(params, tok))
+        for w in range(2):
+            rollout(w)
+        eng.sync()
+        barrier()
+        eng.profile_enable(True)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for k in range(K):
+            rollout(W + k, k)
+        l1.record(stream)
+        eng.sync()
+        barrier()
+        lprof = eng.profile_read()
+        eng.profile_enable(False)
+        lt = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
+        ls = torch.tensor([int(ep_len_dev.sum().item())], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ls, op=dist.ReduceOp.SUM)
+        letters_variant = dict(value=float(ls.item()) / (float(lt.item()) / 1000.0), unit=UNIT, ms_per_step=float(lt.item()) / K,
+                               variant="2d: random-init GPT-2-small with the LM head steered to letter tokens + newline (well-formed 5-letter-ish "
+                                       "guesses, almost never vocabulary words): the token shape of a trained policy",
+                               decoder_rows_per_step=lprof["rows"] / K, sampled_tokens_per_step=lprof["sampled"] / K,
+                               mean_return=float(ep_ret_dev.mean().item()))
+        pol.set_params(params)
+
     if rank == 0:
         peaks = load_peaks()
         gemm_ms, gemm_flops = prof["ms"]["gemm"], prof["work"]["gemm"]
@@ -308,6 +340,8 @@ def main():
         )
         if env_only is not None:
             line["env_only"] = env_only
+        if letters_variant is not None:
+            line["letters_variant"] = letters_variant
         if world == 1 and not args.no_cpu_baseline and not maze:
             r, rf = cpu_reference_numbers(params, cfg, tok, args.ref_batch)
             line["cpu_baseline"] = dict(value=r["env_steps_per_s"], unit=UNIT, cores=r["cores"], kind="port", host_cpus=r["host_cpus"],

@@ -123,6 +123,98 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ---- storing epilogues of one 128 x 256 accumulator (shared by the 1-CTA and the 2-CTA kernel) ----------------------
+// t_addr: TMEM address of this warp's lane quadrant; m0 / n0: origin of the CTA's tile; stg: this warp's two staging boxes
+template <int EPI>
+__device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorMap& tmOut, uint32_t t_addr, int M, int m0, int n0, int quad,
+                                              int lane, uint32_t stg, uint32_t& n_boxes) {
+    const int row = m0 + quad * 32 + lane;                                         // this thread's output row
+    if (EPI == EPI_QKV && n0 >= g.d_model) {
+        // K / V tile: scatter this thread's row segment into the KV slab at (env, pos)
+        const bool live = row < M;
+        const int part = n0 / g.d_model;                                   // 1 = K, 2 = V (tiles never straddle: d % 256 == 0)
+        __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
+        size_t base_off = 0;
+        if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + c0, r);
+            if (live) {
+                const int c = n0 + c0 - part * g.d_model;                  // column inside K (or V): head = c / 64
+                __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * g.t_cap * 64 + (c & 63);
+                const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                    uint4 pk;
+                    pk.x = pack_bf16x2_tc(__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
+                    pk.y = pack_bf16x2_tc(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
+                    pk.z = pack_bf16x2_tc(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
+                    pk.w = pack_bf16x2_tc(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
+                    *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+                }
+            }
+        }
+    } else if constexpr (EPI == EPI_RESID) {
+        // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+            const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
+            if (lane == 0) bulk_wait_read<1>();                            // the box issued two steps ago has been read
+            __syncwarp();
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_addr + c0, r);
+            const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias) b = __ldg(bias4 + j);
+                st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + b.x),
+                             __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y), __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z),
+                             __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + quad * 32); bulk_commit(); }
+            ++n_boxes;
+        }
+    } else {
+        // bf16 outputs (GeLU, Q): 64-column boxes by TMA store
+        for (int c0 = 0; c0 < TC_BN; c0 += 64) {
+            const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_addr + c0 + 32 * half, r);
+                const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0 + 32 * half);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                              // 8 columns -> one 16-byte chunk
+                    const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                    float v[8] = {__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y, __uint_as_float(r[8 * j + 2]) + b0.z,
+                                  __uint_as_float(r[8 * j + 3]) + b0.w, __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
+                                  __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+                    if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
+                    }
+                    if constexpr (EPI == EPI_RELU) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = g.out_scale * fmaxf(v[q], 0.f);
+                    }
+                    const int ch = half * 4 + j;
+                    st_shared_v4(buf + lane * 128 + ((ch ^ (lane & 7)) << 4), pack_bf16x2_tc(v[0], v[1]), pack_bf16x2_tc(v[2], v[3]),
+                                 pack_bf16x2_tc(v[4], v[5]), pack_bf16x2_tc(v[6], v[7]));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tmOut, buf, g.out_col0 + n0 + c0, m0 + quad * 32); bulk_commit(); }
+            ++n_boxes;
+        }
+    }
+}
+
 // one logit of the sampling epilogue: score = logit/T (+ Gumbel noise), running arg-max (lowest column wins ties)
 template <bool NOISE, bool MASK>
 __device__ __forceinline__ void sample_update(float logit, int col, float inv_temp, uint64_t key, int n_vocab, float& best, int& best_col) {
@@ -286,89 +378,8 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                 for (int q = 1; q < 4; ++q)
                     if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
                 if (live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
-            } else if (EPI == EPI_QKV && n0 >= g.d_model) {
-                // K / V tile: scatter this thread's row segment into the KV slab at (env, pos)
-                const bool live = row < M;
-                const int part = n0 / g.d_model;                                   // 1 = K, 2 = V (tiles never straddle: d % 256 == 0)
-                __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
-                size_t base_off = 0;
-                if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_addr + c0, r);
-                    if (live) {
-                        const int c = n0 + c0 - part * g.d_model;                  // column inside K (or V): head = c / 64
-                        __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * g.t_cap * 64 + (c & 63);
-                        const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-                            uint4 pk;
-                            pk.x = pack_bf16x2_tc(__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
-                            pk.y = pack_bf16x2_tc(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
-                            pk.z = pack_bf16x2_tc(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
-                            pk.w = pack_bf16x2_tc(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
-                            *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
-                        }
-                    }
-                }
-            } else if constexpr (EPI == EPI_RESID) {
-                // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                    const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
-                    if (lane == 0) bulk_wait_read<1>();                            // the box issued two steps ago has been read
-                    __syncwarp();
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_addr + c0, r);
-                    const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (g.bias) b = __ldg(bias4 + j);
-                        st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + b.x),
-                                     __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y), __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z),
-                                     __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w));
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + quad * 32); bulk_commit(); }
-                    ++n_boxes;
-                }
             } else {
-                // bf16 outputs (GeLU, Q): 64-column boxes by TMA store
-                for (int c0 = 0; c0 < TC_BN; c0 += 64) {
-                    const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
-                    if (lane == 0) bulk_wait_read<1>();
-                    __syncwarp();
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(t_addr + c0 + 32 * half, r);
-                        const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0 + 32 * half);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {                              // 8 columns -> one 16-byte chunk
-                            const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-                            float v[8] = {__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y, __uint_as_float(r[8 * j + 2]) + b0.z,
-                                          __uint_as_float(r[8 * j + 3]) + b0.w, __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
-                                          __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
-                            if constexpr (EPI == EPI_GELU) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
-                            }
-                            if constexpr (EPI == EPI_RELU) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) v[q] = g.out_scale * fmaxf(v[q], 0.f);
-                            }
-                            const int ch = half * 4 + j;
-                            st_shared_v4(buf + lane * 128 + ((ch ^ (lane & 7)) << 4), pack_bf16x2_tc(v[0], v[1]), pack_bf16x2_tc(v[2], v[3]),
-                                         pack_bf16x2_tc(v[4], v[5]), pack_bf16x2_tc(v[6], v[7]));
-                        }
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) { tma_store_2d(&tmOut, buf, g.out_col0 + n0 + c0, m0 + quad * 32); bulk_commit(); }
-                    ++n_boxes;
-                }
+                tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, n_boxes);
             }
             tcgen05_fence_before();
             __syncwarp();

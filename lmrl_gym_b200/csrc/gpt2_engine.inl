@@ -8,6 +8,7 @@
 // device; nothing is copied to the host until the rollout is over.
 #include "gpt2_kernels.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_tcgen05_2cta.cuh"
 #include <map>
 
 namespace lmrl {
@@ -180,6 +181,27 @@ static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA,
 }
 
 template <int EPI>
+static int launch_gemm_tc2(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut, const GemmArgs& g) {
+    static bool configured = false;
+    if (!configured) {
+        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sm_count & ~1));
+    cfg.blockDim = dim3(TC2_THREADS);
+    cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LMRL_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<EPI>, tmA, tmW, tmOut, g));
+    return 0;
+}
+
+template <int EPI>
 static int launch_gemm_mma(cudaStream_t st, int sm_count, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
@@ -204,9 +226,10 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
                        const GemmExtra& x = GemmExtra()) {
     Gpt2Dev& G = *e->gpt2;
     if (g.n_seg == 0) { g.n_seg = 1; g.n_acc = 1; g.seg[0] = {0, 0, 0, g.K / TC_BK}; }
-    const bool tc = G.gemm_impl == 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
+    const bool tc = G.gemm_impl >= 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
     LMRL_CHECK(tc || (g.n_seg == 1 && EPI != EPI_RELU), "this GEMM needs the tcgen05 kernel (multi-segment / ReLU epilogue): N=%d K=%d", g.N, g.K);
     const CUtensorMap *ta = nullptr, *tw = nullptr, *tw1 = nullptr, *tw2 = nullptr, *to = nullptr;
+    bool use2 = false;
     if (tc) {
         auto get = [&](const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32) -> const CUtensorMap* {
             auto key = std::make_pair(base, (int)box_rows | (f32 ? 1 << 16 : 0));
@@ -218,8 +241,10 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
             }
             return &it->second;
         };
+        // CTA-pair kernel: plain GEMMs of the prefill passes (many rows); each CTA stages 128 of the 256 W rows
+        use2 = G.gemm_impl == 2 && e->cur_mode == 0 && g.n_seg == 1 && EPI != EPI_SAMPLE && !x.W1;
         ta = get(g.A, a_rows, x.a_cols ? x.a_cols : (size_t)g.K, TC_BM, false);
-        tw = get(g.W, w_rows, (size_t)g.K, TC_BN, false);
+        tw = get(g.W, w_rows, (size_t)g.K, use2 ? TC2_B_ROWS : TC_BN, false);
         tw1 = x.W1 ? get(x.W1, w_rows, x.w1_cols, TC_BN, false) : tw;
         tw2 = x.W2 ? get(x.W2, w_rows, x.w2_cols, TC_BN, false) : tw;
         // output map (TMA store / reduce-add source boxes are 32 rows x 128 bytes); the sampling epilogue stores nothing
@@ -233,6 +258,14 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     for (int i = 0; i < g.n_seg; ++i) k_total += (double)g.seg[i].kb_count * TC_BK;
     if (e->prof_begin(0, 2.0 * (double)n_true * k_total, count_kind, 2 * kind + e->cur_mode)) return -1;
     int rc;
+    if constexpr (EPI != EPI_SAMPLE) {
+        if (use2) {
+            rc = launch_gemm_tc2<EPI>(e->stream, G.sm_count, *ta, *tw, *to, g);
+            e->prof_end();
+            e->launches++;
+            return rc;
+        }
+    }
     if constexpr (EPI == EPI_RELU) rc = launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
     else rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
     e->prof_end();
@@ -708,7 +741,7 @@ int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, 
 
 int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl) {
     LMRL_CHECK(e && e->gpt2, "lmrl_set_gemm_impl: no GPT-2 parameters loaded");
-    LMRL_CHECK(impl == 0 || impl == 1, "lmrl_set_gemm_impl: impl must be 0 (mma.sync) or 1 (tcgen05)");
+    LMRL_CHECK(impl >= 0 && impl <= 2, "lmrl_set_gemm_impl: impl must be 0 (mma.sync), 1 (tcgen05, one CTA per tile) or 2 (tcgen05, CTA pairs on prefill passes)");
     e->gpt2->gemm_impl = impl;
     return 0;
 }
@@ -717,8 +750,9 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
                         const float* bias, float* resid_inout) {
     LMRL_CHECK(e && A_bf16 && W_bf16 && resid_inout, "lmrl_test_gemm: null argument");
     LMRL_CHECK(M > 0 && N % 128 == 0 && K % 64 == 0 && (impl == 0 || N % TC_BN == 0), "lmrl_test_gemm: unsupported shape %d x %d x %d", M, N, K);
+    LMRL_CHECK(impl >= 0 && impl <= 2, "lmrl_test_gemm: impl must be 0, 1 or 2");
     LMRL_CUDA(cudaSetDevice(e->device));
-    const size_t m_pad = ((size_t)M + 127) / 128 * 128;
+    const size_t m_pad = ((size_t)M + 255) / 256 * 256;
     __nv_bfloat16 *dA = nullptr, *dW = nullptr;
     float *dB = nullptr, *dR = nullptr;
     int* dM = nullptr;
@@ -736,7 +770,11 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
     cudaDeviceProp prop;
     LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
     int rc = 0;
-    if (impl == 1) {
+    if (impl == 2) {
+        CUtensorMap ta, tw, to;
+        rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC2_B_ROWS) || make_tmap(&to, dR, m_pad, N, 32, true);
+        if (!rc) rc = launch_gemm_tc2<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, to, g);
+    } else if (impl == 1) {
         CUtensorMap ta, tw, to;
         rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC_BN) || make_tmap(&to, dR, m_pad, N, 32, true);
         if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, tw, tw, to, g);
@@ -793,6 +831,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     LMRL_CUDA(cudaEventCreate(&ev[0])); LMRL_CUDA(cudaEventCreate(&ev[1]));
     const int saved_profile = e->profile;
     e->profile = 0;
+    e->cur_mode = rpe > 1 ? 0 : 1;                     // prefill-shaped batches take the prefill kernel selection
     int rc = 0;
     for (int k = 0; k < 8 && !rc; ++k) {
         for (int it = -2; it < iters && !rc; ++it) {      // two untimed warm-up launches

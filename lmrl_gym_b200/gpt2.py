@@ -68,6 +68,26 @@ def init_gpt2_params(cfg: GPT2Config, seed: int = 0) -> Dict:
                 lnf_b=np.zeros(d, np.float32), layers=layers)
 
 
+def steer_to_letters(params: Dict, tokenizer, logit: float = 15.0, scale: float = 50.0, seed: int = 123) -> Dict:
+    """Synthetic-weights utility (no pretrained or trained Wordle policy exists offline): make the tied LM head context-free
+    and concentrated on single-letter tokens + newline, so a random-init GPT-2 emits actions with the TOKEN SHAPE of a
+    trained Wordle policy (about five letters then '\n').  The final LN emits the constant vector scale*u (gamma = 0), the
+    embedding rows of the 52 letter tokens ('c' and ' c') are set to (logit/scale)*u and the newline row a little higher
+    so that P(newline) = 1/6 per step; every other id keeps its N(0, 0.02) row (logit ~ N(0, 1))."""
+    letters = [tokenizer.encode(c)[0] for c in "abcdefghijklmnopqrstuvwxyz"] + [tokenizer.encode("x " + c)[1] for c in "abcdefghijklmnopqrstuvwxyz"]
+    d = params["wte"].shape[1]
+    u = np.random.default_rng(seed).standard_normal(d)
+    u /= np.linalg.norm(u)
+    out = dict(params)
+    wte = params["wte"].copy()
+    wte[letters] = (logit / scale) * u
+    wte[tokenizer.newline_id()] = ((logit + np.log(len(letters) / 5.0)) / scale) * u
+    out["wte"] = wte.astype(np.float32)
+    out["lnf_g"] = np.zeros_like(params["lnf_g"])
+    out["lnf_b"] = (scale * u).astype(np.float32)
+    return out
+
+
 def params_from_hf_state_dict(sd, cfg: GPT2Config) -> Dict:
     """``transformers.GPT2LMHeadModel().state_dict()`` (torch) -> the dict layout above."""
     g = lambda k: np.ascontiguousarray(sd[k].detach().cpu().float().numpy())  # noqa: E731

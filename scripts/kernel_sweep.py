@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--medium", action="store_true")
     ap.add_argument("--shapes", default="1:40,4:8,8:48,24:72")
+    ap.add_argument("--gemm-impl", type=int, default=-1, help="0 mma.sync, 1 tcgen05 one CTA per tile, 2 tcgen05 CTA pairs on prefill shapes")
     args = ap.parse_args()
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
@@ -24,6 +25,8 @@ def main():
     cfg = GPT2Config.medium() if args.medium else GPT2Config.small()
     eng = Engine(max_envs=args.batch, device=0, max_input_length=256, max_new_tokens=6, max_turns=6, tokenizer=ByteTokenizer.synthetic())
     B200GPT2Policy(eng, init_gpt2_params(cfg, seed=0), cfg, seed=0)
+    if args.gemm_impl >= 0:
+        eng.set_gemm_impl(args.gemm_impl)
     d, ff, V, H = cfg.d_model, cfg.d_ff, cfg.n_vocab, cfg.n_head
     for spec in args.shapes.split(","):
         rpe, ctx = (int(x) for x in spec.split(":"))

@@ -29,20 +29,8 @@ def _small_cfg():
 
 
 def _steer_to_letters(params, tok, logit=15.0, scale=50.0):
-    """Make the LM head context-free and concentrated on letter tokens + newline: the final LN emits a constant vector
-    scale*u (gamma = 0), the (tied) embedding rows of the 52 letter tokens are set to (logit/scale)*u and the newline row
-    a little higher so that P(newline) = 1/6 per step; every other id keeps its N(0, 0.02) row => logit ~ N(0, 1)."""
-    letters = [tok.encode(c)[0] for c in "abcdefghijklmnopqrstuvwxyz"] + [tok.encode("x " + c)[1] for c in "abcdefghijklmnopqrstuvwxyz"]
-    d = params["wte"].shape[1]
-    u = np.random.default_rng(123).standard_normal(d)
-    u /= np.linalg.norm(u)
-    wte = params["wte"].copy()
-    wte[letters] = (logit / scale) * u
-    wte[tok.newline_id()] = ((logit + np.log(len(letters) / 5.0)) / scale) * u
-    params["wte"] = wte.astype(np.float32)
-    params["lnf_g"] = np.zeros_like(params["lnf_g"])
-    params["lnf_b"] = (scale * u).astype(np.float32)
-    return params
+    from lmrl_gym_b200.gpt2 import steer_to_letters
+    return steer_to_letters(params, tok, logit, scale)
 
 
 def test_logits_match_oracle_small_and_ragged(tok):
