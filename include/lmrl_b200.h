@@ -157,6 +157,13 @@ int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_t
 int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
                      float* logits /*[n][n_vocab]*/);
 
+/* teacher-forced scoring (build_bc_score_fn / build_ppo_score_fn, ppo/score_fn.py:69-126): for every sequence the sum over
+ * t >= prefix_len of log softmax(logits_{t-1} / temperature)[token_t] under the loaded policy (plain LM or value-perturbed);
+ * ids >= n_vocab are masked to -inf (ppo/gpt2/interface.py:330).  Sequences longer than max_input_length are rejected.
+ * token_logprobs (optional): the individual terms, sequence by sequence, in token order. */
+int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
+                    const int32_t* prefix_len, float temperature, float* logprob_sum /*[n]*/, float* token_logprobs);
+
 /* ---- fused rollout (interact_environment's while-loop, environment.py:176-206, with no host round trip) -------- */
 typedef struct lmrl_rollout_out {      /* all HOST pointers for _host, DEVICE pointers for _dev; any may be NULL */
     float* ep_return;       /* [n]  sum of rewards (fp32 accumulation in step order)            :238 */

@@ -82,6 +82,7 @@ SYMBOLS = {
     "lmrl_wordle_peek_host": (C.c_int, [_V, _I, _V, _V, _V]),
     "lmrl_generate_host": (C.c_int, [_V, _V, _V, _I, _I, _V, _I, C.POINTER(lmrl_sampling), _V, _V]),
     "lmrl_logits_host": (C.c_int, [_V, _V, _V, _I, _I, _V]),
+    "lmrl_score_host": (C.c_int, [_V, _V, _V, _I, _I, _V, C.c_float, _V, _V]),
     "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_wordle_scripted_rollout_dev": (C.c_int, [_V, _V, _I, C.c_float, C.c_uint64, C.POINTER(lmrl_rollout_out)]),

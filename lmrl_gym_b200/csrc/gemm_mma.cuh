@@ -19,7 +19,7 @@
 
 namespace lmrl {
 
-enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_SAMPLE = 3, EPI_RELU = 4 };   // EPI_RELU: tcgen05 kernel only
+enum { EPI_QKV = 0, EPI_RESID = 1, EPI_GELU = 2, EPI_SAMPLE = 3, EPI_RELU = 4, EPI_LOGPROB = 5 };   // RELU / LOGPROB: tcgen05 kernel only
 
 struct GemmArgs {
     const __nv_bfloat16* A;      // [Mcap, K]
@@ -53,6 +53,11 @@ struct GemmArgs {
     struct Seg { int acc, a_kb0, w_idx, kb_count; } seg[4];
     int n_seg, n_acc;
     const float* bias2;          // bias of accumulator 1 (EPI_SAMPLE with n_acc == 2)
+    // EPI_LOGPROB (teacher-forced scoring): per row, per 128-column half tile, the running (max, sum exp(logit/T - max)) of the
+    // masked logits, and the scaled logit of the row's target token; merged over tiles by logprob_finalize_kernel
+    float2* lp_partial;          // [rows][2 * N / 256]
+    const int* lp_target;        // [rows] target token id
+    float* lp_tlogit;            // [rows] logit/T of the target
     int out_col0;                // EPI_RELU / EPI_GELU: column offset of the output box inside the tmOut tensor
     float out_scale;             // EPI_RELU: out = out_scale * relu(acc + bias)
 };

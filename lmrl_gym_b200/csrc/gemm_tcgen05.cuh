@@ -30,7 +30,7 @@ constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 1
 // warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  The storing epilogues use 4 warps (one per TMEM lane quadrant);
 // the sampling epilogue is ALU-heavy (hash + 2 MUFU per logit) and uses 8: warps w and w+4 share a quadrant and split the columns.
 template <int EPI> struct TcCfg {
-    static constexpr int EPI_WARPS = (EPI == EPI_SAMPLE) ? 8 : 4;
+    static constexpr int EPI_WARPS = (EPI == EPI_SAMPLE || EPI == EPI_LOGPROB) ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
@@ -339,14 +339,16 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_acc * TC_BN);
             const int row = m0 + quad * 32 + lane;                                 // this thread's output row
-            if constexpr (EPI == EPI_SAMPLE) {
+            if constexpr (EPI == EPI_SAMPLE || EPI == EPI_LOGPROB) {
                 // warps w and w+4 share the lane quadrant; each takes one 128-column half of the tile
                 const int half = (warp - 2) >> 2;
                 const bool live = row < M;
-                const uint64_t key = live ? g.row_key[row] : 0ull;
+                const uint64_t key = (live && EPI == EPI_SAMPLE) ? g.row_key[row] : 0ull;
                 const bool masked = n0 + TC_BN > g.n_vocab;                         // only the last N tile has padded columns
                 float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 int best_col[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+                float lp_m = -INFINITY, lp_s = 0.f;                                 // EPI_LOGPROB: running max / sum of exp
+                const int lp_tgt = (EPI == EPI_LOGPROB && live) ? g.lp_target[row] : -1;
 #pragma unroll 1
                 for (int c0 = half * (TC_BN / 2); c0 < (half + 1) * (TC_BN / 2); c0 += 32) {
                     uint32_t r[32];
@@ -367,17 +369,37 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                         for (int j = 0; j < 32; ++j)
                             if (col0 + j < g.n_vocab) g.logits_out[(size_t)row * g.n_vocab + col0 + j] = __uint_as_float(r[j]);
                     }
-                    if (g.do_sample) {
+                    if constexpr (EPI == EPI_LOGPROB) {
+                        float cm = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = (col0 + j < g.n_vocab) ? __uint_as_float(r[j]) * g.inv_temp : -INFINITY;
+                            r[j] = __float_as_uint(v);
+                            cm = fmaxf(cm, v);
+                            if (col0 + j == lp_tgt) g.lp_tlogit[row] = v;
+                        }
+                        if (cm > -INFINITY) {
+                            const float m_new = fmaxf(lp_m, cm);
+                            float add = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) add += __expf(__uint_as_float(r[j]) - m_new);
+                            lp_s = lp_s * __expf(lp_m - m_new) + add;
+                            lp_m = m_new;
+                        }
+                    } else if (g.do_sample) {
                         if (masked) sample_chunk<true, true>(r, col0, g.inv_temp, key, g.n_vocab, best, best_col);
                         else sample_chunk<true, false>(r, col0, g.inv_temp, key, g.n_vocab, best, best_col);
                     } else {
                         sample_chunk<false, true>(r, col0, g.inv_temp, key, g.n_vocab, best, best_col);
                     }
                 }
+                if constexpr (EPI == EPI_LOGPROB) {
+                    if (live) g.lp_partial[(size_t)row * (2 * n_tiles) + 2 * (n0 / TC_BN) + half] = make_float2(lp_m, lp_s);
+                }
 #pragma unroll
                 for (int q = 1; q < 4; ++q)
                     if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
-                if (live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
+                if (EPI == EPI_SAMPLE && live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
             } else {
                 tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, n_boxes);
             }

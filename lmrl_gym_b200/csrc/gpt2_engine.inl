@@ -55,6 +55,11 @@ struct Gpt2Dev {
     // xl1: [B_pad][d] final-LN hidden of the value tower
     __nv_bfloat16 *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *xl = nullptr, *xl1 = nullptr;
     int xl_cols = 0;
+    // teacher-forced scoring (lmrl_score_host): head operands for up to s_cap scored rows, partial log-sum-exp pairs, results
+    __nv_bfloat16 *xs = nullptr, *xs1 = nullptr;
+    int s_cap = 0;
+    float2* lp_partial = nullptr; float* lp_tlogit = nullptr; float* lp_out = nullptr;
+    int *score_rows = nullptr, *score_targets = nullptr, *score_n = nullptr;
     RowsDev rows{};
     GenDev gen{};
     StreamDev stream{};
@@ -227,7 +232,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     Gpt2Dev& G = *e->gpt2;
     if (g.n_seg == 0) { g.n_seg = 1; g.n_acc = 1; g.seg[0] = {0, 0, 0, g.K / TC_BK}; }
     const bool tc = G.gemm_impl >= 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
-    LMRL_CHECK(tc || (g.n_seg == 1 && EPI != EPI_RELU), "this GEMM needs the tcgen05 kernel (multi-segment / ReLU epilogue): N=%d K=%d", g.N, g.K);
+    LMRL_CHECK(tc || (g.n_seg == 1 && EPI != EPI_RELU && EPI != EPI_LOGPROB), "this GEMM needs the tcgen05 kernel (multi-segment / ReLU epilogue): N=%d K=%d", g.N, g.K);
     const CUtensorMap *ta = nullptr, *tw = nullptr, *tw1 = nullptr, *tw2 = nullptr, *to = nullptr;
     bool use2 = false;
     if (tc) {
@@ -242,7 +247,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
             return &it->second;
         };
         // CTA-pair kernel: plain GEMMs of the prefill passes (many rows); each CTA stages 128 of the 256 W rows
-        use2 = G.gemm_impl == 2 && e->cur_mode == 0 && g.n_seg == 1 && EPI != EPI_SAMPLE && !x.W1;
+        use2 = G.gemm_impl == 2 && e->cur_mode == 0 && g.n_seg == 1 && EPI != EPI_SAMPLE && EPI != EPI_LOGPROB && !x.W1;
         ta = get(g.A, a_rows, x.a_cols ? x.a_cols : (size_t)g.K, TC_BM, false);
         tw = get(g.W, w_rows, (size_t)g.K, use2 ? TC2_B_ROWS : TC_BN, false);
         tw1 = x.W1 ? get(x.W1, w_rows, x.w1_cols, TC_BN, false) : tw;
@@ -258,7 +263,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     for (int i = 0; i < g.n_seg; ++i) k_total += (double)g.seg[i].kb_count * TC_BK;
     if (e->prof_begin(0, 2.0 * (double)n_true * k_total, count_kind, 2 * kind + e->cur_mode)) return -1;
     int rc;
-    if constexpr (EPI != EPI_SAMPLE) {
+    if constexpr (EPI != EPI_SAMPLE && EPI != EPI_LOGPROB) {
         if (use2) {
             rc = launch_gemm_tc2<EPI>(e->stream, G.sm_count, *ta, *tw, *to, g);
             e->prof_end();
@@ -266,7 +271,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
             return rc;
         }
     }
-    if constexpr (EPI == EPI_RELU) rc = launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
+    if constexpr (EPI == EPI_RELU || EPI == EPI_LOGPROB) rc = launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
     else rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
     e->prof_end();
     e->launches++;
@@ -281,10 +286,47 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
         e->launches++;                                 \
     } while (0)
 
+// teacher-forced scoring request: which rows of the pass feed the LM head and which token each is scored against
+struct ScoreReq {
+    const int* rows;       // [n_score] row indices (device)
+    const int* targets;    // [n_score] target token of every scored row (device)
+    const int* n_dev;      // [1] n_score (device)
+    float* out;            // [n_score] log p(target | prefix) (device)
+    int n_score;           // host copy (grid sizing only)
+};
+
+// merge the per-(tile, half) partial (max, sum) pairs of one row: out = logit_target - logsumexp
+__global__ void logprob_finalize_kernel(const float2* __restrict__ partial, int n_part, const float* __restrict__ tlogit, const int* __restrict__ n_dev,
+                                        float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int n = *n_dev;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        float m = -INFINITY, s = 0.f;
+        for (int i = lane; i < n_part; i += 32) {
+            const float2 p = partial[(size_t)r * n_part + i];
+            if (p.x > -INFINITY) {
+                const float mn = fmaxf(m, p.x);
+                s = s * __expf(m - mn) + p.y * __expf(p.x - mn);
+                m = mn;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float mo = __shfl_xor_sync(0xFFFFFFFFu, m, o), so = __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            const float mn = fmaxf(m, mo);
+            const float a = m > -INFINITY ? s * __expf(m - mn) : 0.f, b = mo > -INFINITY ? so * __expf(mo - mn) : 0.f;
+            s = a + b; m = mn;
+        }
+        if (lane == 0) out[r] = tlogit[r] - (m + __logf(s));
+    }
+}
+
 // One forward pass over the current ragged batch + sampling of one token per contributing env.
 // mode 0 = prefill of un-cached stream tokens, mode 1 = single-token decode.
+// score != nullptr: no sampling; the LM head runs over score->rows and writes log-probabilities of score->targets instead.
 static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t* done, const int32_t* turn_of_env, int turn_const,
-                              const lmrl_sampling& s, float* logits_out) {
+                              const lmrl_sampling& s, float* logits_out, const ScoreReq* score = nullptr) {
     Gpt2Dev& G = *e->gpt2;
     const lmrl_gpt2_dims& D = G.dims;
     cudaStream_t st = e->stream;
@@ -303,7 +345,12 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     const int n_towers = G.policy_kind == 1 ? 2 : 1;
-    const size_t xl_rows = (size_t)(e->cfg.max_envs + 127) / 128 * 128;
+    // head operand buffers: the per-env sampling buffers, or the (larger) scoring buffers
+    __nv_bfloat16* xl = score ? G.xs : G.xl;
+    __nv_bfloat16* xl1 = score ? G.xs1 : G.xl1;
+    const size_t xl_rows = score ? (size_t)G.s_cap : (size_t)(e->cfg.max_envs + 127) / 128 * 128;
+    const int* head_n = score ? score->n_dev : G.rows.n_slots;
+    const int* head_gather = score ? score->rows : G.rows.slot_last;
     for (int t = 0; t < n_towers; ++t) {
         const TowerDev& T = G.tw[t];
         if (t > 0) LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(T.wte, T.wpe, D.d_model, G.rows, G.x));
@@ -336,12 +383,13 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
             if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
         }
         // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
-        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, G.rows.n_slots, G.rows.slot_last,
-                                                                  t == 0 ? G.xl : G.xl1, t == 0 ? G.xl_cols : D.d_model));
+        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
+                                                                  t == 0 ? xl : xl1, t == 0 ? G.xl_cols : D.d_model));
     }
-    LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
+    if (!score)
+        LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
     GemmArgs h{};
-    h.A = G.xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
+    h.A = xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = head_n;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
     GemmExtra hx;
@@ -351,7 +399,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         // Q heads, first layer: xl[:, d + k*hidden ...] = beta * relu(xl1 · W1_k^T + b1_k)   (mlp_head.py:146-147; beta folded in here)
         const QHeadsDev& Q = G.qh;
         GemmArgs r{};
-        r.A = G.xl1; r.W = Q.w1cat; r.bias = Q.b1cat; r.N = Q.n_q * Q.hidden; r.K = D.d_model; r.M_dev = G.rows.n_slots; r.out = G.xl;
+        r.A = xl1; r.W = Q.w1cat; r.bias = Q.b1cat; r.N = Q.n_q * Q.hidden; r.K = D.d_model; r.M_dev = head_n; r.out = xl;
         r.out_col0 = D.d_model; r.out_scale = Q.beta;
         GemmExtra rx;
         rx.out_cols = (size_t)G.xl_cols;
@@ -365,8 +413,15 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         hx.W1 = Q.w2[0]; hx.w1_cols = (size_t)Q.hidden;
         if (Q.n_q == 2) { hx.W2 = Q.w2[1]; hx.w2_cols = (size_t)Q.hidden; }
     }
-    if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
-    LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
+    if (score) {
+        h.lp_partial = G.lp_partial; h.lp_target = score->targets; h.lp_tlogit = G.lp_tlogit;
+        if (launch_gemm<EPI_LOGPROB>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
+        LMRL_LAUNCH(2, logprob_finalize_kernel<<<std::max(1, std::min((score->n_score + 7) / 8, G.sm_count * 8)), 256, 0, st>>>(
+                           G.lp_partial, 2 * (G.v_pad / TC_BN), G.lp_tlogit, score->n_dev, score->out));
+    } else {
+        if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
+        LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
+    }
     e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
     return 0;
@@ -618,6 +673,66 @@ int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok
         LMRL_CUDA(cudaMemcpyAsync(logits + (size_t)slot_env[j] * G.dims.n_vocab, G.logits + (size_t)j * G.dims.n_vocab,
                                   sizeof(float) * G.dims.n_vocab, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+}  // extern "C" (reopened below)
+
+static int score_alloc(lmrl_engine* e) {
+    Gpt2Dev& G = *e->gpt2;
+    if (G.s_cap) return 0;
+    const int B = e->cfg.max_envs;
+    const int cap = std::max(4096, (8 * B + 127) / 128 * 128);
+    const size_t n_part = (size_t)2 * (G.v_pad / TC_BN);
+    if (e->alloc(&G.xs, (size_t)cap * G.xl_cols) || e->alloc(&G.xs1, (size_t)cap * G.dims.d_model) || e->alloc(&G.lp_partial, (size_t)cap * n_part) ||
+        e->alloc(&G.lp_tlogit, cap) || e->alloc(&G.lp_out, cap) || e->alloc(&G.score_rows, cap) || e->alloc(&G.score_targets, cap) ||
+        e->alloc(&G.score_n, 1))
+        return -1;
+    G.s_cap = cap;
+    return 0;
+}
+
+extern "C" {
+
+int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const int32_t* prefix_len,
+                    float temperature, float* logprob_sum, float* token_logprobs) {
+    LMRL_CHECK(e && e->has_gpt2, "lmrl_score: no GPT-2 parameters loaded");
+    LMRL_CHECK(tokens && n_tok && prefix_len && logprob_sum, "lmrl_score: null argument");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    if (score_alloc(e)) return -1;
+    const int max_in = e->cfg.max_input_length;
+    // rows are assigned in env order, n_tok[i] rows for sequence i (positions 0..n_tok-1): scored rows are the positions
+    // prefix_len-1 .. n_tok-2, each against the next token (ppo/score_fn.py:112-118)
+    std::vector<int32_t> rows, targets, owner;
+    int row0 = 0;
+    for (int i = 0; i < n; ++i) {
+        LMRL_CHECK(n_tok[i] >= 0 && n_tok[i] <= max_in && n_tok[i] <= pitch, "lmrl_score: sequence %d has %d tokens (max_input_length %d)", i, n_tok[i], max_in);
+        LMRL_CHECK(prefix_len[i] >= 1 && prefix_len[i] <= n_tok[i], "lmrl_score: sequence %d: prefix_len %d must be in [1, %d]", i, prefix_len[i], n_tok[i]);
+        for (int t = prefix_len[i] - 1; t + 1 < n_tok[i]; ++t) {
+            rows.push_back(row0 + t);
+            targets.push_back(tokens[(size_t)i * pitch + t + 1]);
+            owner.push_back(i);
+        }
+        row0 += n_tok[i];
+    }
+    const int n_score = (int)rows.size();
+    LMRL_CHECK(n_score <= G.s_cap, "lmrl_score: %d scored tokens exceed the capacity %d of one call", n_score, G.s_cap);
+    for (int i = 0; i < n; ++i) logprob_sum[i] = 0.f;
+    if (n_score == 0) return 0;
+    if (load_prompts(e, tokens, n_tok, pitch, n)) return -1;
+    LMRL_CUDA(cudaMemcpyAsync(G.score_rows, rows.data(), sizeof(int32_t) * n_score, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(G.score_targets, targets.data(), sizeof(int32_t) * n_score, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaMemcpyAsync(G.score_n, &n_score, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
+    lmrl_sampling s{temperature, 0, 0};
+    ScoreReq req{G.score_rows, G.score_targets, G.score_n, G.lp_out, n_score};
+    if (forward_and_sample(e, 0, n, nullptr, nullptr, 0, s, nullptr, &req)) return -1;
+    std::vector<float> lp(n_score);
+    LMRL_CUDA(cudaMemcpyAsync(lp.data(), G.lp_out, sizeof(float) * n_score, cudaMemcpyDeviceToHost, e->stream));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    for (int j = 0; j < n_score; ++j) logprob_sum[owner[j]] += lp[j];          // fp32 sum in token order, as .sum(axis=0) of the reference
+    if (token_logprobs) memcpy(token_logprobs, lp.data(), sizeof(float) * n_score);
     return 0;
 }
 

@@ -87,6 +87,14 @@ def forward_last_logits(params: Dict, tokens: Sequence[int], n_head: int, n_voca
     return (h[-1] @ wte.T).numpy()
 
 
+def sequence_logprob(params: Dict, tokens: Sequence[int], prefix_len: int, n_head: int, n_vocab: int, temperature: float = 1.0, **kw) -> np.ndarray:
+    """build_bc_score_fn (LLM_RL/algorithms/ppo/score_fn.py:112-118): log softmax(logits_{t-1})[token_t] for t >= prefix_len."""
+    h = forward_hidden(params, tokens, n_head, **kw)
+    wte = _t(params["wte"], kw.get("weights_bf16", True))[:n_vocab]
+    logp = torch.log_softmax((h @ wte.T).double() / temperature, dim=-1).numpy()
+    return np.asarray([logp[t - 1, tokens[t]] for t in range(max(prefix_len, 1), len(tokens))], dtype=np.float64)
+
+
 # ---- ILQL / MC value-perturbed logits -------------------------------------------------------------------------------
 
 def mlp_head(h: "torch.Tensor", q: Dict, weights_bf16: bool = True) -> "torch.Tensor":
