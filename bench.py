@@ -204,8 +204,9 @@ def main():
         rollout(w)
     eng.sync()
     barrier()
+    # ---- timed region: exactly K steps on the production path (CUDA-graph replay, no per-launch events)
     eng.launch_count(reset=True)
-    eng.profile_enable(not args.no_profile)
+    eng.profile_enable(False)
     clocks = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -218,9 +219,21 @@ def main():
     clock_info = clocks.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count()
-    prof = eng.profile_read()
-    eng.profile_enable(False)
+    # ---- the same K steps again with one CUDA event per launch boundary (eager launches): per-kernel times for the roofline
+    prof, profiled_ms = None, None
+    if not args.no_profile:
+        eng.profile_enable(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for k in range(K):
+            rollout(W + k, k)
+        p1.record(stream)
+        eng.sync()
+        prof = eng.profile_read()
+        profiled_ms = p0.elapsed_time(p1) / K
+        eng.profile_enable(False)
     env_steps = int(ep_len_dev.sum().item())
+    mean_return = float(ep_ret_dev.mean().item())
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([env_steps, launches], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -280,7 +293,6 @@ def main():
             rollout(w)
         eng.sync()
         barrier()
-        eng.profile_enable(True)
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0.record(stream)
         for k in range(K):
@@ -288,6 +300,9 @@ def main():
         l1.record(stream)
         eng.sync()
         barrier()
+        letters_return = float(ep_ret_dev.mean().item())
+        eng.profile_enable(True)                      # one more step, eagerly, only for the row / token counts
+        rollout(W, 0)
         lprof = eng.profile_read()
         eng.profile_enable(False)
         lt = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
@@ -298,12 +313,13 @@ def main():
         letters_variant = dict(value=float(ls.item()) / (float(lt.item()) / 1000.0), unit=UNIT, ms_per_step=float(lt.item()) / K,
                                variant="2d: random-init GPT-2-small with the LM head steered to letter tokens + newline (well-formed 5-letter-ish "
                                        "guesses, almost never vocabulary words): the token shape of a trained policy",
-                               decoder_rows_per_step=lprof["rows"] / K, sampled_tokens_per_step=lprof["sampled"] / K,
-                               mean_return=float(ep_ret_dev.mean().item()))
+                               decoder_rows_per_step=lprof["rows"], sampled_tokens_per_step=lprof["sampled"], mean_return=letters_return)
         pol.set_params(params)
 
     if rank == 0:
         peaks = load_peaks()
+        if prof is None:
+            prof = dict(ms=dict(gemm=0.0, attention=0.0, elementwise=0.0, env=0.0), work=dict(gemm=0.0), launches=dict(gemm=0), tags={}, rows=0, sampled=0)
         gemm_ms, gemm_flops = prof["ms"]["gemm"], prof["work"]["gemm"]
         att = prof["tags"].get("attention_decode", dict(ms=0.0, work=0.0))
         att_gbs = att["work"] / (att["ms"] / 1000.0) / 1e9 if att["ms"] > 0 else 0.0
@@ -317,12 +333,13 @@ def main():
                         l2_policy="inputs larger than L2 (KV cache %.1f GB per GPU)" % (eng.device_bytes / 1e9), tokenizer=tok.name,
                         policy_variant=("random-init GPT-2-medium (every action is an unknown string: 101 turns, the history collapses to the observation)" if maze else
                                         "2a: random-init GPT-2-small (actions are malformed guesses; every episode runs 6 turns)"),
-                        per_launch_events_in_timed_region=not args.no_profile),
+                        timed_region="K fused rollouts replayed from a CUDA graph, no per-launch events",
+                        roofline_pass=("the same K steps re-run eagerly with one CUDA event per launch boundary: %.2f ms/step" % profiled_ms) if prof else None),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api="lmrl_gym_b200.text_env_eval"),
             gpu_launches=total_launches,
             clocks=clock_info,
             roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (tcgen05.mma UMMA 128x256x16 + TMA + TMEM, all epilogues)", achieved=achieved, peak=peak,
-                          unit="TFLOP/s", frac=achieved / peak, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=None,
+                          unit="TFLOP/s", frac=achieved / peak if peak else None, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=None,
                           flops_per_step=gemm_flops / K, launches_per_step=prof["launches"]["gemm"] / K,
                           share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None,
                           # the HBM-bound batched GEMV of the path (north_star's "decode GEMV"): KV-cache attention of the decode passes
@@ -336,7 +353,7 @@ def main():
                                              {"tflops": round(v["work"] / (v["ms"] / 1000.0) / 1e12, 1)}) if v["ms"] > 0 and v["work"] > 0 else {})
                                   for k, v in prof["tags"].items()},
             decoder_rows_per_step=prof["rows"] / K, sampled_tokens_per_step=prof["sampled"] / K,
-            mean_return=float(ep_ret_dev.mean().item()),
+            mean_return=mean_return,
         )
         if env_only is not None:
             line["env_only"] = env_only

@@ -186,6 +186,10 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
 int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, int32_t n, float prob_smart,
                                      uint64_t policy_seed, lmrl_rollout_out* out_dev);
 
+/* fused rollouts of up to 8 turns are captured into a CUDA graph on the second use of a configuration and replayed afterwards
+ * (default on; per-launch profiling runs eagerly) */
+int lmrl_set_use_graphs(lmrl_engine* e, int32_t enable);
+
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);
 

@@ -73,6 +73,21 @@ struct Gpt2Dev {
     float* step_reward = nullptr; uint8_t* step_valid = nullptr; uint8_t* step_fb = nullptr; int32_t* step_aux = nullptr;
     int32_t* act_tokens = nullptr; int32_t* act_len = nullptr;
     int* live = nullptr;              // [1] scratch of the early-exit test
+    // CUDA graph of one whole fused rollout (every launch is static: row counts live on the device).  A configuration is run
+    // eagerly once (first-use attribute calls, tensor-map creation), captured on its second use and replayed afterwards.
+    struct RolloutKey {
+        int env_kind, n, do_sample, policy_kind, gemm_impl, has_opt;
+        float temperature; uint64_t seed;
+        bool operator==(const RolloutKey& o) const {
+            return env_kind == o.env_kind && n == o.n && do_sample == o.do_sample && policy_kind == o.policy_kind && gemm_impl == o.gemm_impl &&
+                   has_opt == o.has_opt && temperature == o.temperature && seed == o.seed;
+        }
+    };
+    cudaGraphExec_t graph_exec = nullptr;
+    RolloutKey graph_key{}, warm_key{};
+    bool warm_valid = false;
+    int64_t graph_launches = 0;
+    int use_graphs = 1;
     int sm_count = 148;
     int gemm_impl = 1;                // 1 = tcgen05/TMEM/TMA (default), 0 = mma.sync cross-check path
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (base pointer, box rows) -> descriptor
@@ -466,6 +481,7 @@ using namespace lmrl;
 
 void lmrl_gpt2_free(lmrl_engine* e) {
     if (!e || !e->gpt2) return;
+    if (e->gpt2->graph_exec) cudaGraphExecDestroy(e->gpt2->graph_exec);
     for (void* p : e->gpt2->owned) cudaFree(p);
     delete e->gpt2;
     e->gpt2 = nullptr;
@@ -806,6 +822,51 @@ static int rollout_export(lmrl_engine* e, int32_t n, lmrl_rollout_out* out, cuda
     return 0;
 }
 
+}  // extern "C" (reopened below)
+
+// seeds / options already sit in e->d_seeds / e->d_opt_pos: run the rollout eagerly, or replay its CUDA graph
+static int rollout_run(lmrl_engine* e, int32_t env_kind, bool has_opt, int32_t n, const lmrl_sampling& s) {
+    Gpt2Dev& G = *e->gpt2;
+    const int32_t* opt = has_opt ? e->d_opt_pos : nullptr;
+    const bool graphable = G.use_graphs && !e->profile && e->cfg.max_turns <= 8;     // longer rollouts poll the device for early exit
+    if (!graphable) return rollout_enqueue(e, env_kind, e->d_seeds, opt, n, s);
+    const Gpt2Dev::RolloutKey key{env_kind, n, s.do_sample, G.policy_kind, G.gemm_impl, has_opt ? 1 : 0, s.temperature, s.seed};
+    if (G.graph_exec && G.graph_key == key) {
+        LMRL_CUDA(cudaGraphLaunch(G.graph_exec, e->stream));
+        e->launches += G.graph_launches;
+        return 0;
+    }
+    if (!(G.warm_valid && G.warm_key == key)) {            // first use of this configuration: eager
+        G.warm_key = key; G.warm_valid = true;
+        return rollout_enqueue(e, env_kind, e->d_seeds, opt, n, s);
+    }
+    if (G.graph_exec) { cudaGraphExecDestroy(G.graph_exec); G.graph_exec = nullptr; }
+    const int64_t before = e->launches;
+    LMRL_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = rollout_enqueue(e, env_kind, e->d_seeds, opt, n, s);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+    LMRL_CHECK(err == cudaSuccess && graph, "fused rollout: CUDA graph capture failed: %s", cudaGetErrorString(err));
+    G.graph_launches = e->launches - before;
+    e->launches = before;
+    const cudaError_t ierr = cudaGraphInstantiate(&G.graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    LMRL_CHECK(ierr == cudaSuccess, "fused rollout: cudaGraphInstantiate failed: %s", cudaGetErrorString(ierr));
+    G.graph_key = key;
+    LMRL_CUDA(cudaGraphLaunch(G.graph_exec, e->stream));
+    e->launches += G.graph_launches;
+    return 0;
+}
+
+extern "C" {
+
+int lmrl_set_use_graphs(lmrl_engine* e, int32_t enable) {
+    LMRL_CHECK(e && e->gpt2, "lmrl_set_use_graphs: no GPT-2 parameters loaded");
+    e->gpt2->use_graphs = enable ? 1 : 0;
+    return 0;
+}
+
 int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, const int32_t* opt_pos, int32_t n,
                       const lmrl_sampling* s, lmrl_rollout_out* out) {
     LMRL_CHECK(e && e->has_gpt2, "lmrl_rollout: no GPT-2 parameters loaded");
@@ -814,7 +875,7 @@ int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, c
     LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "lmrl_rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
     LMRL_CUDA(cudaMemcpyAsync(e->d_seeds, seeds, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
     if (opt_pos) LMRL_CUDA(cudaMemcpyAsync(e->d_opt_pos, opt_pos, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, e->stream));
-    if (rollout_enqueue(e, env_kind, e->d_seeds, opt_pos ? e->d_opt_pos : nullptr, n, *s)) return -1;
+    if (rollout_run(e, env_kind, opt_pos != nullptr, n, *s)) return -1;
     if (rollout_export(e, n, out, cudaMemcpyDeviceToHost)) return -1;
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
@@ -825,7 +886,11 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
     LMRL_CHECK(e && e->has_gpt2, "lmrl_rollout: no GPT-2 parameters loaded");
     LMRL_CHECK(seeds_dev && s, "lmrl_rollout: null argument");
     LMRL_CUDA(cudaSetDevice(e->device));
-    if (rollout_enqueue(e, env_kind, seeds_dev, opt_pos_dev, n, *s)) return -1;
+    LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "lmrl_rollout: %d envs exceed engine capacity %d", n, e->cfg.max_envs);
+    if (seeds_dev != e->d_seeds) LMRL_CUDA(cudaMemcpyAsync(e->d_seeds, seeds_dev, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+    if (opt_pos_dev && opt_pos_dev != e->d_opt_pos)
+        LMRL_CUDA(cudaMemcpyAsync(e->d_opt_pos, opt_pos_dev, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToDevice, e->stream));
+    if (rollout_run(e, env_kind, opt_pos_dev != nullptr, n, *s)) return -1;
     return rollout_export(e, n, out_dev, cudaMemcpyDeviceToDevice);
 }
 

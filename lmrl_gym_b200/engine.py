@@ -84,6 +84,10 @@ class Engine:
         check(self.lib.lmrl_wordle_scripted_rollout_dev(self.handle, seeds_dev_ptr, n, float(prob_smart), int(policy_seed) & ((1 << 64) - 1),
                                                         C.byref(out_struct)))
 
+    def set_use_graphs(self, enable: bool):
+        """CUDA-graph replay of fused rollouts (default on)."""
+        check(self.lib.lmrl_set_use_graphs(self.handle, 1 if enable else 0))
+
     def set_gemm_impl(self, impl: int):
         """1 = tcgen05/TMEM/TMA (default), 0 = the mma.sync kernel (independent cross-check used by the tests)."""
         check(self.lib.lmrl_set_gemm_impl(self.handle, int(impl)))
