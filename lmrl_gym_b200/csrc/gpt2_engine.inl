@@ -380,7 +380,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
             // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
             if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
             if (mode == 0)
-                LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
+                LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32,
                                                            ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                               0.125f * 1.4426950408889634f, G.att));
             else
@@ -1024,7 +1024,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                 case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx); break;
                 case 5:
                     if (rpe > 1)
-                        attention_prefill_kernel<<<std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 3), ATTP_WARPS * 32,
+                        attention_prefill_kernel<<<std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32,
                                                    ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                       0.125f * 1.4426950408889634f, G.att);
                     else

@@ -288,14 +288,15 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv
 }
 
 // ---- K3 (prefill): tensor-core attention for slots that bring many rows ------------------------------------------
-// One warp per (slot, head).  Up to 32 query rows of the slot (two m16 tiles) are held as mma A fragments; the
-// (env, head) K / V slabs are staged 32 keys at a time into per-warp shared memory (cp.async, 128-byte rows,
-// XOR-swizzled 16-byte chunks) and consumed with ldmatrix (K) / ldmatrix.trans (V) by mma.sync m16n8k16 with a
-// flash-style online soft-max (fp32 running max / sum, P re-packed from the S accumulators as the next A operand).
-// Every K / V byte is therefore read once per 32 query rows instead of once per row.
-constexpr int ATTP_WARPS = 8;
+// One warp per (slot, head).  16 query rows of the slot (one m16 tile) are held as mma A fragments; the (env, head)
+// K / V slabs are staged 32 keys at a time into per-warp shared memory (cp.async, 128-byte rows, XOR-swizzled 16-byte
+// chunks), double buffered so the next key block is in flight while the current one is consumed with ldmatrix (K) /
+// ldmatrix.trans (V) by mma.sync m16n8k16 with a flash-style online soft-max (fp32 running max / sum, P re-packed from
+// the S accumulators as the next A operand).  Every K / V byte is read from HBM once per slot (slots with more than 16
+// rows re-read it from L1/L2).  One m-tile instead of two keeps the kernel under 128 registers: two CTAs per SM.
+constexpr int ATTP_WARPS = 7;                                   // 7 x 16 KB of staging: two CTAs (14 warps) per SM
 constexpr int ATTP_KEYS = 32;                                   // keys per staged block
-constexpr int ATTP_WARP_SMEM = 2 * ATTP_KEYS * 128;            // K block + V block
+constexpr int ATTP_WARP_SMEM = 2 * 2 * ATTP_KEYS * 128;        // 2 buffers x (K block + V block)
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -305,14 +306,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(ATTP_WARPS * 32) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
-                                                                            const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
-                                                                            int d_model, int t_cap, float scale_log2e,
-                                                                            __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(ATTP_WARPS * 32, 2) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                               const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
+                                                                               int d_model, int t_cap, float scale_log2e,
+                                                                               __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char attp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t sK = smem_u32(attp_smem) + warp * ATTP_WARP_SMEM, sV = sK + ATTP_KEYS * 128;
+    const uint32_t sbase = smem_u32(attp_smem) + warp * ATTP_WARP_SMEM;
     const int total = *rows.n_slots * n_head;
     for (int w = blockIdx.x * ATTP_WARPS + warp; w < total; w += gridDim.x * ATTP_WARPS) {
         const int slot = w / n_head, head = w - slot * n_head;
@@ -320,56 +321,53 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32) attention_prefill_kernel(cons
         const int p0 = rows.row_pos[r0];
         const __nv_bfloat16* gK = kcache + ((size_t)e * n_head + head) * t_cap * 64;
         const __nv_bfloat16* gV = vcache + ((size_t)e * n_head + head) * t_cap * 64;
-        for (int rb = 0; rb < n; rb += 32) {
-            const int nr = min(32, n - rb);                    // live query rows in this block
-            const int n_keys = p0 + rb + nr;                   // keys visible to the last live row
-            // Q fragments: qa[mt][kk][0..3]
-            uint32_t qa[2][4][4];
+        auto stage = [&](int buf, int k0) {                    // 32 keys of K and V: 2 x 256 chunks of 16 B, 16 per lane
+            const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int i = rb + mt * 16 + g + hh * 8;
-                    const uint32_t* src = reinterpret_cast<const uint32_t*>(q + (size_t)(r0 + i) * d_model + head * 64);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        qa[mt][kk][hh] = i < n ? __ldg(src + kk * 8 + t) : 0u;            // dims 16kk + 2t, +1
-                        qa[mt][kk][hh + 2] = i < n ? __ldg(src + kk * 8 + 4 + t) : 0u;    // dims 16kk + 8 + 2t, +1
-                    }
-                }
-            float o[2][8][4];
-            float mrow[2][2], lrow[2][2];
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) { mrow[mt][hh] = -INFINITY; lrow[mt][hh] = 0.f; }
-#pragma unroll
-                for (int d8 = 0; d8 < 8; ++d8)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) o[mt][d8][c] = 0.f;
+            for (int c = 0; c < 8; ++c) {
+                const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
+                const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
+                const int kk = min(k0 + key, t_cap - 1);
+                cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
+                cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
             }
-            for (int k0 = 0; k0 < n_keys; k0 += ATTP_KEYS) {
-                __syncwarp();
-                // stage 32 keys of K and V: 2 x 256 chunks of 16 B, 16 per lane
+            cp_async_commit();
+        };
+        for (int rb = 0; rb < n; rb += 16) {
+            const int nr = min(16, n - rb);                    // live query rows in this block
+            const int n_keys = p0 + rb + nr;                   // keys visible to the last live row
+            __syncwarp();
+            stage(0, 0);
+            // Q fragments: qa[kk][0..3]
+            uint32_t qa[4][4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
-                    const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
-                    const int kk = min(k0 + key, t_cap - 1);
-                    cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
-                    cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
+            for (int hh = 0; hh < 2; ++hh) {
+                const int i = rb + g + hh * 8;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(q + (size_t)(r0 + i) * d_model + head * 64);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    qa[kk][hh] = i < n ? __ldg(src + kk * 8 + t) : 0u;            // dims 16kk + 2t, +1
+                    qa[kk][hh + 2] = i < n ? __ldg(src + kk * 8 + 4 + t) : 0u;    // dims 16kk + 8 + 2t, +1
                 }
-                cp_async_commit();
-                cp_async_wait<0>();
+            }
+            float o[8][4];
+            float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+#pragma unroll
+            for (int d8 = 0; d8 < 8; ++d8)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) o[d8][c] = 0.f;
+            int buf = 0;
+            for (int k0 = 0; k0 < n_keys; k0 += ATTP_KEYS, buf ^= 1) {
+                if (k0 + ATTP_KEYS < n_keys) { stage(buf ^ 1, k0 + ATTP_KEYS); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
                 __syncwarp();
-                // S = Q K^T  (2 m-tiles x 4 key n8-blocks)
-                float sacc[2][4][4];
+                const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
+                // S = Q K^T  (4 key n8-blocks)
+                float sacc[4][4];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) sacc[mt][j][c] = 0.f;
+                    for (int c = 0; c < 4; ++c) sacc[j][c] = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -377,89 +375,77 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32) attention_prefill_kernel(cons
                         const int key = j * 8 + (lane & 7), ch = kp * 4 + (lane >> 3);
                         uint32_t b0, b1, b2, b3;
                         ldmatrix_x4(sK + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            mma_bf16(sacc[mt][j], qa[mt][2 * kp], b0, b1);
-                            mma_bf16(sacc[mt][j], qa[mt][2 * kp + 1], b2, b3);
-                        }
+                        mma_bf16(sacc[j], qa[2 * kp], b0, b1);
+                        mma_bf16(sacc[j], qa[2 * kp + 1], b2, b3);
                     }
                 }
                 // scale, causal mask, online soft-max
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int pos = p0 + rb + g + hh * 8;
+                    float bm = -INFINITY;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int pos = p0 + rb + mt * 16 + g + hh * 8;
-                        float bm = -INFINITY;
+                    for (int j = 0; j < 4; ++j)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int c = 0; c < 2; ++c) {
+                            const int key = k0 + j * 8 + 2 * t + c;
+                            float v = sacc[j][hh * 2 + c] * scale_log2e;
+                            v = key <= pos ? v : -INFINITY;
+                            sacc[j][hh * 2 + c] = v;
+                            bm = fmaxf(bm, v);
+                        }
+                    bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 1));
+                    bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 2));
+                    const float m_new = fmaxf(mrow[hh], bm);              // finite: key 0 is visible to every row
+                    const float alpha = exp2f(mrow[hh] - m_new);
+                    mrow[hh] = m_new;
+                    float ls = 0.f;
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const int key = k0 + j * 8 + 2 * t + c;
-                                float v = sacc[mt][j][hh * 2 + c] * scale_log2e;
-                                v = key <= pos ? v : -INFINITY;
-                                sacc[mt][j][hh * 2 + c] = v;
-                                bm = fmaxf(bm, v);
-                            }
-                        bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 1));
-                        bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 2));
-                        const float m_new = fmaxf(mrow[mt][hh], bm);          // finite: key 0 is visible to every row
-                        const float alpha = exp2f(mrow[mt][hh] - m_new);
-                        mrow[mt][hh] = m_new;
-                        float ls = 0.f;
+                    for (int j = 0; j < 4; ++j)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int c = 0; c < 2; ++c) {
+                            const float pz = exp2f(sacc[j][hh * 2 + c] - m_new);
+                            sacc[j][hh * 2 + c] = pz;
+                            ls += pz;
+                        }
+                    lrow[hh] = lrow[hh] * alpha + ls;
 #pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const float pz = exp2f(sacc[mt][j][hh * 2 + c] - m_new);
-                                sacc[mt][j][hh * 2 + c] = pz;
-                                ls += pz;
-                            }
-                        lrow[mt][hh] = lrow[mt][hh] * alpha + ls;
-#pragma unroll
-                        for (int d8 = 0; d8 < 8; ++d8) { o[mt][d8][hh * 2] *= alpha; o[mt][d8][hh * 2 + 1] *= alpha; }
-                    }
+                    for (int d8 = 0; d8 < 8; ++d8) { o[d8][hh * 2] *= alpha; o[d8][hh * 2 + 1] *= alpha; }
+                }
                 // O += P V   (two k16 key steps x 8 dim n8-blocks)
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    uint32_t pa[2][4];
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        pa[mt][0] = pack_bf16x2(sacc[mt][2 * ks][0], sacc[mt][2 * ks][1]);
-                        pa[mt][1] = pack_bf16x2(sacc[mt][2 * ks][2], sacc[mt][2 * ks][3]);
-                        pa[mt][2] = pack_bf16x2(sacc[mt][2 * ks + 1][0], sacc[mt][2 * ks + 1][1]);
-                        pa[mt][3] = pack_bf16x2(sacc[mt][2 * ks + 1][2], sacc[mt][2 * ks + 1][3]);
-                    }
+                    uint32_t pa[4];
+                    pa[0] = pack_bf16x2(sacc[2 * ks][0], sacc[2 * ks][1]);
+                    pa[1] = pack_bf16x2(sacc[2 * ks][2], sacc[2 * ks][3]);
+                    pa[2] = pack_bf16x2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+                    pa[3] = pack_bf16x2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
 #pragma unroll
                     for (int dp = 0; dp < 4; ++dp) {           // two dim n8-blocks per ldmatrix.x4.trans
                         const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ch = dp * 2 + (lane >> 4);
                         uint32_t b0, b1, b2, b3;
                         ldmatrix_x4_trans(sV + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            mma_bf16(o[mt][2 * dp], pa[mt], b0, b1);
-                            mma_bf16(o[mt][2 * dp + 1], pa[mt], b2, b3);
-                        }
+                        mma_bf16(o[2 * dp], pa, b0, b1);
+                        mma_bf16(o[2 * dp + 1], pa, b2, b3);
                     }
                 }
+                __syncwarp();                                  // everyone is done with this buffer before it is refilled
             }
             // normalise and store
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int hh = 0; hh < 2; ++hh) {
+                float l = lrow[hh];
+                l += __shfl_xor_sync(0xFFFFFFFFu, l, 1);
+                l += __shfl_xor_sync(0xFFFFFFFFu, l, 2);
+                const int i = rb + g + hh * 8;
+                if (i < n) {
+                    const float inv = 1.0f / l;
+                    __nv_bfloat16* dst = out + (size_t)(r0 + i) * d_model + head * 64;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float l = lrow[mt][hh];
-                    l += __shfl_xor_sync(0xFFFFFFFFu, l, 1);
-                    l += __shfl_xor_sync(0xFFFFFFFFu, l, 2);
-                    const int i = rb + mt * 16 + g + hh * 8;
-                    if (i < n) {
-                        const float inv = 1.0f / l;
-                        __nv_bfloat16* dst = out + (size_t)(r0 + i) * d_model + head * 64;
-#pragma unroll
-                        for (int d8 = 0; d8 < 8; ++d8)
-                            *reinterpret_cast<uint32_t*>(dst + d8 * 8 + 2 * t) = pack_bf16x2(o[mt][d8][hh * 2] * inv, o[mt][d8][hh * 2 + 1] * inv);
-                    }
+                    for (int d8 = 0; d8 < 8; ++d8)
+                        *reinterpret_cast<uint32_t*>(dst + d8 * 8 + 2 * t) = pack_bf16x2(o[d8][hh * 2] * inv, o[d8][hh * 2 + 1] * inv);
                 }
+            }
         }
     }
 }
