@@ -73,6 +73,8 @@ typedef struct lmrl_sampling {
     float temperature;     /* GenerationConfig.temperature (None -> 1.0) */
     int32_t do_sample;     /* 0 = greedy argmax */
     uint64_t seed;         /* base of the counter-based sampling RNG, keyed by (seed, episode seed, turn, token) */
+    int32_t top_k;         /* GenerationConfig.top_k (None / 0 = off): keep the k highest scores (FlaxTopKLogitsWarper) */
+    float top_p;           /* GenerationConfig.top_p (None / 0 / >= 1 = off): nucleus filtering (FlaxTopPLogitsWarper), after top_k */
 } lmrl_sampling;
 
 const char* lmrl_last_error(void);

@@ -42,7 +42,7 @@ class lmrl_mlp_head(C.Structure):
 
 
 class lmrl_sampling(C.Structure):
-    _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64)]
+    _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64), ("top_k", C.c_int32), ("top_p", C.c_float)]
 
 
 class lmrl_profile_out(C.Structure):

@@ -65,6 +65,7 @@ struct Gpt2Dev {
     StreamDev stream{};
     uint64_t* row_key = nullptr;
     unsigned long long* best = nullptr;
+    unsigned long long* best_scratch = nullptr;   // sink for the fused arg-max when top-k / top-p re-samples from dumped logits
     uint64_t* episode_key = nullptr;  // [B]
     float* logits = nullptr;          // parity hook buffer, allocated on first use
     size_t logits_rows = 0;
@@ -77,9 +78,9 @@ struct Gpt2Dev {
     // eagerly once (first-use attribute calls, tensor-map creation), captured on its second use and replayed afterwards.
     struct RolloutKey {
         int env_kind, n, do_sample, policy_kind, gemm_impl, has_opt;
-        float temperature; uint64_t seed;
+        float temperature; uint64_t seed; int top_k; float top_p;
         bool operator==(const RolloutKey& o) const {
-            return env_kind == o.env_kind && n == o.n && do_sample == o.do_sample && policy_kind == o.policy_kind && gemm_impl == o.gemm_impl &&
+            return top_k == o.top_k && top_p == o.top_p && env_kind == o.env_kind && n == o.n && do_sample == o.do_sample && policy_kind == o.policy_kind && gemm_impl == o.gemm_impl &&
                    has_opt == o.has_opt && temperature == o.temperature && seed == o.seed;
         }
     };
@@ -401,11 +402,23 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
                                                                   t == 0 ? xl : xl1, t == 0 ? G.xl_cols : D.d_model));
     }
+    // top-k / top-p: the LM head dumps fp32 logits and a per-row filter kernel samples from the survivors (slow path)
+    const bool filtered = !score && (s.top_k > 0 || (s.top_p > 0.f && s.top_p < 1.f));
+    if (filtered && !logits_out) {
+        const size_t need = (size_t)e->cfg.max_envs * D.n_vocab;
+        if (G.logits_rows < need) {
+            LMRL_CUDA(cudaMalloc(&G.logits, need * sizeof(float)));
+            G.owned.push_back(G.logits);
+            G.logits_rows = need;
+        }
+        logits_out = G.logits;
+    }
     if (!score)
         LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
     GemmArgs h{};
     h.A = xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = head_n;
-    h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f); h.do_sample = s.do_sample;
+    h.best = filtered ? G.best_scratch : G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f);
+    h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
     GemmExtra hx;
     hx.a_cols = (size_t)G.xl_cols;
@@ -435,6 +448,17 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
                            G.lp_partial, 2 * (G.v_pad / TC_BN), G.lp_tlogit, score->n_dev, score->out));
     } else {
         if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
+        if (filtered) {
+            static bool configured = false;
+            const size_t fs_smem = (size_t)D.n_vocab * sizeof(float);
+            LMRL_CHECK(fs_smem <= 220 * 1024, "top-k / top-p sampling keeps one row of logits in shared memory: n_vocab %d is too large", D.n_vocab);
+            if (!configured) {
+                LMRL_CUDA(cudaFuncSetAttribute(filtered_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem));
+                configured = true;
+            }
+            LMRL_LAUNCH(2, filtered_sample_kernel<<<n_env, FS_THREADS, fs_smem, st>>>(logits_out, D.n_vocab, G.rows, G.row_key, h.inv_temp, s.do_sample,
+                                                                                    s.top_k, s.top_p, G.best));
+        }
         LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
     }
     e->cur_pass_slot = -1;
@@ -466,7 +490,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     G.gen.eos_id = e->tok.t.newline_id;
     if (e->alloc(&G.stream.tokens, (size_t)B * G.stream_cap) || e->alloc(&G.stream.len, B) || e->alloc(&G.stream.kv_len, B)) return -1;
     G.stream.cap = G.stream_cap; G.stream.max_input = max_in;
-    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.episode_key, B) || e->alloc(&G.live, 1)) return -1;
+    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.best_scratch, B) || e->alloc(&G.episode_key, B) || e->alloc(&G.live, 1)) return -1;
     if (e->alloc(&G.ep_return, B) || e->alloc(&G.ep_length, B) || e->alloc(&G.ep_done, B) || e->alloc(&G.step_reward, (size_t)B * T) ||
         e->alloc(&G.step_valid, (size_t)B * T) || e->alloc(&G.step_fb, (size_t)B * T * 5) || e->alloc(&G.step_aux, (size_t)B * T) ||
         e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
@@ -677,7 +701,7 @@ int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok
         G.logits_rows = need;
     }
     clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
-    lmrl_sampling s{1.0f, 0, 0};
+    lmrl_sampling s{1.0f, 0, 0, 0, 0.f};
     if (forward_and_sample(e, 0, n, nullptr, nullptr, 0, s, G.logits)) return -1;
     // rows come back in slot order == env order for envs with tokens; scatter on the host
     std::vector<int32_t> slot_env(n);
@@ -741,7 +765,7 @@ int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok,
     LMRL_CUDA(cudaMemcpyAsync(G.score_targets, targets.data(), sizeof(int32_t) * n_score, cudaMemcpyHostToDevice, e->stream));
     LMRL_CUDA(cudaMemcpyAsync(G.score_n, &n_score, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
     clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
-    lmrl_sampling s{temperature, 0, 0};
+    lmrl_sampling s{temperature, 0, 0, 0, 0.f};
     ScoreReq req{G.score_rows, G.score_targets, G.score_n, G.lp_out, n_score};
     if (forward_and_sample(e, 0, n, nullptr, nullptr, 0, s, nullptr, &req)) return -1;
     std::vector<float> lp(n_score);
@@ -830,7 +854,7 @@ static int rollout_run(lmrl_engine* e, int32_t env_kind, bool has_opt, int32_t n
     const int32_t* opt = has_opt ? e->d_opt_pos : nullptr;
     const bool graphable = G.use_graphs && !e->profile && e->cfg.max_turns <= 8;     // longer rollouts poll the device for early exit
     if (!graphable) return rollout_enqueue(e, env_kind, e->d_seeds, opt, n, s);
-    const Gpt2Dev::RolloutKey key{env_kind, n, s.do_sample, G.policy_kind, G.gemm_impl, has_opt ? 1 : 0, s.temperature, s.seed};
+    const Gpt2Dev::RolloutKey key{env_kind, n, s.do_sample, G.policy_kind, G.gemm_impl, has_opt ? 1 : 0, s.temperature, s.seed, s.top_k, s.top_p};
     if (G.graph_exec && G.graph_key == key) {
         LMRL_CUDA(cudaGraphLaunch(G.graph_exec, e->stream));
         e->launches += G.graph_launches;

@@ -470,6 +470,134 @@ __global__ void prepare_sample_kernel(RowsDev rows, GenDev gen, const uint64_t* 
     best[j] = 0ull;
 }
 
+// ---- top-k / top-p filtered sampling (HF logits warpers; None in every reference Wordle / Maze driver, so this is the slow path) ----
+// One CTA per sampled row.  The row's fp32 logits (already dumped by the LM-head GEMM) are scaled by 1/T and parked in shared
+// memory (n_vocab floats), then
+//   top-k (FlaxTopKLogitsWarper): the k-th largest value is found by bisection on the order-preserving integer image of the
+//          floats (32 counting passes over shared memory); ties at the threshold keep the lowest indices, as lax.top_k does;
+//   top-p (FlaxTopPLogitsWarper): in descending order a token is kept iff the probability mass of the tokens ranked before it
+//          is < top_p (the token that crosses top_p is kept); the cut value is found by the same bisection on the mass of
+//          strictly larger scores, ties again resolved by index;
+//   the survivor set is sampled with the engine's Gumbel-max noise (same (row key, column) counter hash as the fused path).
+// Kept set and arg-max are written as the packed `best` word finalize_sample_kernel expects.
+constexpr int FS_THREADS = 256;
+
+__device__ __forceinline__ float block_sum_f(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < FS_THREADS / 32; ++i) t += red[i];
+    return t;
+}
+__device__ __forceinline__ float block_max_f(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = -INFINITY;
+    for (int i = 0; i < FS_THREADS / 32; ++i) t = fmaxf(t, red[i]);
+    return t;
+}
+// exclusive prefix of `v` over threads in thread order (each thread owns a contiguous index range, so this is index order)
+__device__ __forceinline__ int block_excl_scan_i(int v, int* red, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= o) x += y; }
+    __syncthreads();
+    if (lane == 31) red[warp] = x;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int i = 0; i < FS_THREADS / 32; ++i) { if (i < warp) base += red[i]; tot += red[i]; }
+    *total = tot;
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(FS_THREADS) filtered_sample_kernel(const float* __restrict__ logits, int n_vocab, RowsDev rows, const uint64_t* __restrict__ row_key,
+                                                                     float inv_temp, int do_sample, int top_k, float top_p,
+                                                                     unsigned long long* __restrict__ best) {
+    extern __shared__ float fs_row[];                  // [n_vocab] scaled logits; -inf once filtered out
+    __shared__ float red_f[FS_THREADS / 32];
+    __shared__ int red_i[FS_THREADS / 32];
+    const int j = blockIdx.x;
+    if (j >= *rows.n_slots) return;
+    const int tid = threadIdx.x;
+    const int per = (n_vocab + FS_THREADS - 1) / FS_THREADS, lo = min(tid * per, n_vocab), hi = min(lo + per, n_vocab);   // my index range
+    const float* src = logits + (size_t)j * n_vocab;
+    float mx = -INFINITY;
+    for (int i = tid; i < n_vocab; i += FS_THREADS) { const float v = src[i] * inv_temp; fs_row[i] = v; mx = fmaxf(mx, v); }
+    mx = block_max_f(mx, red_f);                       // (contains the __syncthreads that publish fs_row)
+    if (top_k > 0 && top_k < n_vocab) {
+        // largest key T with count(x >= T) >= k  == the k-th largest value
+        uint32_t klo = 0u, khi = 0xFFFFFFFFu;
+        while (klo < khi) {
+            const uint32_t mid = klo + (uint32_t)(((uint64_t)khi - klo + 1) >> 1);
+            int c = 0;
+            for (int i = tid; i < n_vocab; i += FS_THREADS) c += float_ordered(fs_row[i]) >= mid;
+            int tot;
+            (void)block_excl_scan_i(c, red_i, &tot);
+            if (tot >= top_k) klo = mid; else khi = mid - 1;
+        }
+        int c_gt = 0, c_eq = 0;
+        for (int i = lo; i < hi; ++i) { const uint32_t u = float_ordered(fs_row[i]); c_gt += u > klo; c_eq += u == klo; }
+        int tot_gt, tot_eq;
+        (void)block_excl_scan_i(c_gt, red_i, &tot_gt);
+        int rank = block_excl_scan_i(c_eq, red_i, &tot_eq);          // how many threshold-valued entries precede my range
+        const int keep_eq = top_k - tot_gt;                          // lowest-index ties that still fit
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t u = float_ordered(fs_row[i]);
+            if (u < klo) fs_row[i] = -INFINITY;
+            else if (u == klo) { if (rank >= keep_eq) fs_row[i] = -INFINITY; ++rank; }
+        }
+        __syncthreads();
+    }
+    if (top_p > 0.f && top_p < 1.f) {
+        float z = 0.f;
+        for (int i = tid; i < n_vocab; i += FS_THREADS) z += __expf(fs_row[i] - mx);
+        z = block_sum_f(z, red_f);
+        const float target = top_p * z;                              // compare unnormalised masses
+        // smallest key T with mass(x > T) < top_p: every value >= T has less than top_p ranked before its first occurrence
+        uint32_t klo = 0u, khi = 0xFFFFFFFFu;
+        while (klo < khi) {
+            const uint32_t mid = klo + (uint32_t)(((uint64_t)khi - klo) >> 1);
+            float m = 0.f;
+            for (int i = tid; i < n_vocab; i += FS_THREADS) { const float v = fs_row[i]; m += float_ordered(v) > mid ? __expf(v - mx) : 0.f; }
+            m = block_sum_f(m, red_f);
+            if (m < target) khi = mid; else klo = mid + 1;
+        }
+        // ties at the cut value: the r-th of them (index order) is kept iff mass_gt + r * p(value) < top_p
+        float m_gt = 0.f; int c_eq = 0; float p_eq = 0.f;
+        for (int i = lo; i < hi; ++i) { const float v = fs_row[i]; const uint32_t u = float_ordered(v); if (u > klo) m_gt += __expf(v - mx); else if (u == klo) { ++c_eq; p_eq = __expf(v - mx); } }
+        m_gt = block_sum_f(m_gt, red_f);
+        p_eq = block_max_f(p_eq, red_f);
+        int tot_eq;
+        int rank = block_excl_scan_i(c_eq, red_i, &tot_eq);
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t u = float_ordered(fs_row[i]);
+            if (u < klo) fs_row[i] = -INFINITY;
+            else if (u == klo) { if (!(m_gt + (float)rank * p_eq < target) && rank > 0) fs_row[i] = -INFINITY; ++rank; }
+        }
+        __syncthreads();
+    }
+    // Gumbel-max over the survivors (lowest column wins ties, like the fused sampler)
+    const uint64_t key = row_key[j];
+    float bs = -INFINITY; int bc = 0x7FFFFFFF;
+    for (int i = tid; i < n_vocab; i += FS_THREADS) {
+        float v = fs_row[i];
+        if (v > -INFINITY) {
+            if (do_sample) v += gumbel_from_bits(noise_bits(key, (uint32_t)i));
+            if (v > bs) { bs = v; bc = i; }
+        }
+    }
+    if (bc != 0x7FFFFFFF) atomicMax(best + j, pack_best(bs, bc));
+}
+
 __global__ void finalize_sample_kernel(RowsDev rows, GenDev gen, const unsigned long long* __restrict__ best) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= *rows.n_slots) return;

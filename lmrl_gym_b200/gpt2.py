@@ -174,7 +174,7 @@ def default_out_str_process(s: str) -> str:
 class B200GPT2Policy(BatchedTextPolicy):
     def __init__(self, engine: Engine, params: Dict, config: Optional[GPT2Config] = None, do_sample: bool = True,
                  temperature: Optional[float] = None, seed: int = 0, in_str_process: Optional[Callable[[str], str]] = None,
-                 out_str_process: Optional[Callable[[str], str]] = None):
+                 out_str_process: Optional[Callable[[str], str]] = None, top_k: Optional[int] = None, top_p: Optional[float] = None):
         if engine.tokenizer is None:
             raise _lib.LmrlError("Engine needs a tokenizer before a policy can be bound to it")
         self._lmrl_engine = engine
@@ -182,6 +182,10 @@ class B200GPT2Policy(BatchedTextPolicy):
         self.do_sample = bool(do_sample)
         self.temperature = 1.0 if temperature is None else float(temperature)
         self.seed = int(seed)
+        # GenerationConfig.top_k / top_p (eval_bc_gpt2.py:42-44, 90-95; None in every shipped driver): HF warper order is
+        # temperature -> top_k -> top_p
+        self.top_k = 0 if top_k is None else int(top_k)
+        self.top_p = 0.0 if top_p is None else float(top_p)
         self.in_str_process = in_str_process
         self.out_str_process = out_str_process
         self._calls = 0
@@ -192,7 +196,8 @@ class B200GPT2Policy(BatchedTextPolicy):
         return self.in_str_process is None and self.out_str_process is None
 
     def sampling(self) -> "_lib.lmrl_sampling":
-        return _lib.lmrl_sampling(temperature=self.temperature, do_sample=int(self.do_sample), seed=self.seed & ((1 << 64) - 1))
+        return _lib.lmrl_sampling(temperature=self.temperature, do_sample=int(self.do_sample), seed=self.seed & ((1 << 64) - 1),
+                                  top_k=self.top_k, top_p=self.top_p)
 
     def set_params(self, params: Dict) -> None:
         _upload_params(self._lmrl_engine, self.config, params)

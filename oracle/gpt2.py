@@ -169,8 +169,38 @@ def gumbel_noise(key: int, n_vocab: int) -> np.ndarray:
     return -np.log(-np.log(u))
 
 
-def sample_scores(logits: np.ndarray, key: int, temperature: float = 1.0, do_sample: bool = True) -> np.ndarray:
+def warp_top_k(scores: np.ndarray, top_k: int) -> np.ndarray:
+    """FlaxTopKLogitsWarper (transformers 4.26.1 generation/flax_logits_process.py): keep the top_k scores, the rest -> -inf;
+    lax.top_k resolves ties by the lower index."""
+    k = min(max(int(top_k), 1), scores.shape[-1])
+    order = np.argsort(-scores, kind="stable")          # descending, lower index first among equals
+    out = np.full_like(scores, -np.inf)
+    out[order[:k]] = scores[order[:k]]
+    return out
+
+
+def warp_top_p(scores: np.ndarray, top_p: float) -> np.ndarray:
+    """FlaxTopPLogitsWarper: sort descending, keep a token iff the cumulative probability of the tokens before it is
+    < top_p (so the token that crosses top_p is kept; min_tokens_to_keep = 1)."""
+    order = np.argsort(-scores, kind="stable")
+    s = scores[order].astype(np.float64)
+    p = np.exp(s - s.max())
+    p /= p.sum()
+    before = np.concatenate(([0.0], np.cumsum(p)[:-1]))
+    keep = before < top_p
+    keep[0] = True
+    out = np.full_like(scores, -np.inf)
+    out[order[keep]] = scores[order[keep]]
+    return out
+
+
+def sample_scores(logits: np.ndarray, key: int, temperature: float = 1.0, do_sample: bool = True, top_k: int = 0,
+                  top_p: float = 0.0) -> np.ndarray:
     s = logits.astype(np.float64) / (temperature if temperature and temperature > 0 else 1.0)
+    if top_k and top_k > 0:
+        s = warp_top_k(s, top_k)
+    if top_p and 0.0 < top_p < 1.0:
+        s = warp_top_p(s, top_p)
     if do_sample:
         s = s + gumbel_noise(key, len(logits))
     return s

@@ -217,3 +217,36 @@ def test_logits_match_oracle_gpt2_medium_shape(tok):
     print(f"gpt2-medium: max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
     assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
     eng.close()
+
+
+def test_top_k_top_p_sampling_matches_oracle_warpers(tok):
+    """HF warpers on the device (slow path): with the engine's own fp32 logits as input, the sampled id is exactly the arg-max of
+    (warped scores + Gumbel noise) of the numpy restatement (pinned to transformers' warpers in tests/test_oracle_gpt2.py)."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    cfg = _small_cfg()
+    params = init_gpt2_params(cfg, seed=5)
+    eng = Engine(max_envs=64, max_input_length=32, max_new_tokens=1, tokenizer=tok)
+    rng = np.random.default_rng(7)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, 32, size=48)]
+    keys = [int(k) for k in rng.integers(0, 2**63, size=48)]
+    base = B200GPT2Policy(eng, params, cfg)
+    logits = base.logits(prompts)
+    # kept-set sizes with these random-init logits (std 0.3): top_p 0.9 -> ~40k ids, 0.5 @ T 0.7 -> ~16k, 0.02 @ T 0.3 -> a few dozen
+    for top_k, top_p, temperature, do_sample in [(5, None, 1.0, True), (None, 0.9, 1.0, True), (None, 0.5, 0.7, True), (None, 0.02, 0.3, True),
+                                                 (50, 0.5, 0.7, True), (1, None, 1.0, True), (3, 0.99, 1.3, False)]:
+        pol = B200GPT2Policy(eng, params, cfg, do_sample=do_sample, temperature=temperature, seed=42, top_k=top_k, top_p=top_p)
+        gens = pol.generate_tokens(prompts, episode_keys=keys, turn=2)
+        sizes = []
+        for i in range(48):
+            s = og.sample_scores(logits[i], og.row_key(42, keys[i], 2, 0), temperature, do_sample, top_k or 0, top_p or 0.0)
+            kept = np.isfinite(s)
+            sizes.append(int(kept.sum()))
+            t = gens[i][0]
+            assert kept[t], (top_k, top_p, i, t)
+            assert s[t] >= s.max() - 1e-4, (top_k, top_p, i)
+            if top_k:
+                assert kept.sum() <= top_k
+        print(f"top_k={top_k} top_p={top_p} T={temperature}: kept-set sizes {min(sizes)}..{max(sizes)}")
+    eng.close()

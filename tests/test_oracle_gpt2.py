@@ -71,3 +71,28 @@ def test_value_policy_restatement_properties():
     emu = og.value_policy_last_logits((pi, base, q1, q2), toks, cfg.n_head, cfg.n_vocab, 4.0, emulate_bf16=True)
     ref = og.value_policy_last_logits((pi, base, q1, q2), toks, cfg.n_head, cfg.n_vocab, 4.0)
     assert np.abs(emu - ref).max() < 0.2
+
+
+def test_top_k_top_p_restatement_matches_hf_warpers():
+    """The numpy restatement of the Flax warpers agrees with transformers' torch TopK / TopP warpers (same published
+    semantics: the token that crosses top_p is kept, at least one token survives)."""
+    import torch
+    from transformers.generation.logits_process import TopKLogitsWarper, TopPLogitsWarper
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        x = (rng.standard_normal(997) * 3).astype(np.float32)
+        k = int(rng.integers(1, 50))
+        p = float(rng.uniform(0.05, 0.99))
+        tk = TopKLogitsWarper(top_k=k)(None, torch.from_numpy(x)[None].clone())[0].numpy()
+        assert np.array_equal(np.isfinite(og.warp_top_k(x, k)), np.isfinite(tk))
+        tp = TopPLogitsWarper(top_p=p)(None, torch.from_numpy(x)[None].clone())[0].numpy()
+        mine = np.isfinite(og.warp_top_p(x, p))
+        theirs = np.isfinite(tp)
+        # identical up to the single boundary token when the cumulative mass lands within float32 rounding of top_p
+        assert (mine != theirs).sum() <= 1, (trial, (mine != theirs).sum())
+        assert mine.sum() >= 1
+    # ties: the lower index wins in top_k; the tie that crosses top_p is kept, later ones are not
+    x = np.array([1.0, 2.0, 2.0, 2.0, 0.0], np.float32)
+    assert np.isfinite(og.warp_top_k(x, 2)).tolist() == [False, True, True, False, False]
+    q = np.log(np.array([0.1, 0.3, 0.3, 0.3], np.float64)).astype(np.float32)
+    assert np.isfinite(og.warp_top_p(q, 0.5)).tolist() == [False, True, True, False]
