@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py — env-steps/sec of batched Wordle rollouts with a GPT-2-small policy (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--workload wordle|maze_po_medium]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one batch of B concurrent episodes run to completion through the hot path
 (obs tokens -> policy.generate -> env.step -> reward, up to 6 turns): exactly what one iteration of the reference's
 ``text_env_eval`` batch loop does (LLM_RL/environment.py:223-242).  Prints ONE JSON line (rank 0).
 
-  value      whole-job env-steps/s, device-timed (CUDA events on the engine stream), seeds resident in HBM
+  value      whole-job env-steps/s over exactly K steps, device-timed (CUDA events on the engine stream, max over ranks),
+             seeds resident in HBM, the production launch path (the fused rollout replayed from its CUDA graph)
   e2e        the same metric through the public API ``text_env_eval(env, policy, ...)`` with host seeds in and host
              logs out (H2D + D2H inside the timed region), wall clock
-  roofline   the dominant kernel (bf16 GEMM, tensor-bound): algorithmic FLOPs (2*M*N*K of every launch, live M) /
-             summed launch durations from CUDA events recorded around every launch in the timed region
-  cpu_baseline  the CPU restatement of the reference path (oracle port) on a bounded sample, host cores stated
+  roofline   the dominant kernel (bf16 GEMM, tensor-bound): algorithmic FLOPs (2*M*N*K of every launch, live M read back
+             from the device) / summed launch durations, from a second pass over the same K steps launched eagerly with
+             one CUDA event per launch boundary; ``decode_attention_hbm`` is the HBM fraction of the decode-pass KV
+             attention (the path's batched GEMV)
+  env_only   env kernels alone with scripted RandomMixturePolicy-equivalent actions (variant 2b)
+  letters_variant  the same engine with the LM head steered to letter tokens: the token shape of a trained policy (2d)
+  cpu_baseline  the CPU restatement of the reference path (oracle port) on a bounded sample, host cores stated,
+             charitable (pad to longest) and faithful (LEFT-pad to 256) variants
 """
 from __future__ import annotations
 

@@ -111,7 +111,7 @@ __global__ void convert_to_bf16_kernel(const float* __restrict__ src, size_t n, 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
 }
 
-__global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, int n_header, StreamDev st, Gpt2Dev* /*unused*/,
+__global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, int n_header, StreamDev st,
                                    const uint64_t* __restrict__ seeds, uint64_t* __restrict__ episode_key, float* ep_return,
                                    int32_t* ep_length, uint8_t* ep_done) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -794,11 +794,11 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
     const uint8_t* done = wordle ? e->wordle.done : e->maze.done;
     if (wordle) {
         LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
-        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, nullptr, seeds_dev,
+        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, seeds_dev,
                                                                            G.episode_key, G.ep_return, G.ep_length, G.ep_done));
     } else {
         LMRL_LAUNCH(3, maze_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->maze, seeds_dev, opt_pos_dev, nullptr, n));
-        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, 0, G.stream, nullptr, seeds_dev,
+        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, 0, G.stream, seeds_dev,
                                                                            G.episode_key, G.ep_return, G.ep_length, G.ep_done));
         LMRL_LAUNCH(3, maze_init_stream_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->maze, G.stream, n));
     }

@@ -11,7 +11,7 @@ using namespace lmrl;
 extern "C" {
 
 const char* lmrl_last_error(void) { return g_last_error.c_str(); }
-int lmrl_abi_version(void) { return 1; }
+int lmrl_abi_version(void) { return 2; }
 
 int lmrl_create(const lmrl_config* cfg, lmrl_engine** out) {
     LMRL_CHECK(cfg && out, "lmrl_create: null argument");

@@ -124,4 +124,4 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.lmrl_abi_version.restype = C.c_int
-    assert lib.lmrl_abi_version() == 1
+    assert lib.lmrl_abi_version() == 2
