@@ -296,7 +296,7 @@ def main():
         from lmrl_gym_b200.gpt2 import steer_to_letters
         pol.set_params(steer_to_letters(params, tok))
         for w in range(2):
-            rollout(w)
+            rollout(w % n_steps_total)
         eng.sync()
         barrier()
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -308,7 +308,7 @@ def main():
         barrier()
         letters_return = float(ep_ret_dev.mean().item())
         eng.profile_enable(True)                      # one more step, eagerly, only for the row / token counts
-        rollout(W, 0)
+        rollout(W % n_steps_total, 0)
         lprof = eng.profile_read()
         eng.profile_enable(False)
         lt = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device="cuda")
