@@ -191,6 +191,10 @@ int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, 
 /* fused rollouts of up to 8 turns are captured into a CUDA graph on the second use of a configuration and replayed afterwards
  * (default on; per-launch profiling runs eagerly) */
 int lmrl_set_use_graphs(lmrl_engine* e, int32_t enable);
+/* programmatic dependent launch between the kernels of a pass (default OFF — measured slower on B200 for this path): a kernel's
+ * CTAs are scheduled and run their prologue behind the tail of the previous kernel, then wait for its completion before touching
+ * global memory */
+int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
 
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);

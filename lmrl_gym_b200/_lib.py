@@ -87,6 +87,7 @@ SYMBOLS = {
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_wordle_scripted_rollout_dev": (C.c_int, [_V, _V, _I, C.c_float, C.c_uint64, C.POINTER(lmrl_rollout_out)]),
     "lmrl_set_use_graphs": (C.c_int, [_V, _I]),
+    "lmrl_set_use_pdl": (C.c_int, [_V, _I]),
     "lmrl_launch_count": (C.c_int64, [_V, _I]),
     "lmrl_set_gemm_impl": (C.c_int, [_V, _I]),
     "lmrl_test_gemm_host": (C.c_int, [_V, _I, _I, _I, _I, _V, _V, _V, _V]),

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "env_core.h"
+#include "pdl.cuh"
 
 namespace lmrl {
 
@@ -103,6 +104,7 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 // ---- E1: reset -------------------------------------------------------------------------------------------
 __global__ void wordle_reset_kernel(WordleDev w, const uint64_t* __restrict__ seeds, int n) {
+    pdl_enter();
     extern __shared__ uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int e = blockIdx.x * ENV_WARPS_PER_BLOCK + warp;
@@ -178,6 +180,7 @@ struct WordleScratch {
 
 __global__ void wordle_step_kernel(WordleDev w, TokenizerDev tk, ActionSrc src, const uint8_t* __restrict__ skip,
                                    StepOut out, StreamDev st, int n) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int e = blockIdx.x * ENV_WARPS_PER_BLOCK + warp;
@@ -294,6 +297,7 @@ __global__ void wordle_step_kernel(WordleDev w, TokenizerDev tk, ActionSrc src, 
 // unless options carry them (env.py:186-202).  opt_pos/opt_goal: [B][2], -1 = not given.
 __global__ void maze_reset_kernel(MazeDev m, const uint64_t* __restrict__ seeds, const int32_t* __restrict__ opt_pos,
                                   const int32_t* __restrict__ opt_goal, int n) {
+    pdl_enter();
     extern __shared__ uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int e = blockIdx.x * ENV_WARPS_PER_BLOCK + warp;
@@ -362,6 +366,7 @@ __device__ __forceinline__ int maze_drop_items(MazeDev& m, int e, int n_drop, in
 
 // after maze_reset_kernel: the policy's first prompt is the observation of the start cell (env.py:204-214)
 __global__ void maze_init_stream_kernel(MazeDev m, StreamDev st, int n) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int cell = m.pos[e * 2] * m.cfg.W + m.pos[e * 2 + 1];
@@ -381,6 +386,7 @@ __global__ void maze_init_stream_kernel(MazeDev m, StreamDev st, int n) {
 // one env per thread: sampled ids -> action text (decode, `removesuffix('\n') + '\n'` as every reference driver's
 // out_str_process) -> MazeEnv.step -> next prompt window (last_k items, unknown action collapses to the observation)
 __global__ void maze_fused_step_kernel(MazeDev m, TokenizerDev tk, ActionSrc src, StepOut out, StreamDev st, int n) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (m.done[e]) return;
@@ -446,6 +452,7 @@ __global__ void maze_fused_step_kernel(MazeDev m, TokenizerDev tk, ActionSrc src
 __global__ void log_scripted_turn_kernel(int n, int max_turns, int act_pitch, WordleDev w, StepOut step, float* ep_return, int32_t* ep_length,
                                          uint8_t* ep_done, float* step_reward, uint8_t* step_valid, uint8_t* step_fb, int32_t* step_aux,
                                          int32_t* act_tokens, int32_t* act_len) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int t = ep_length[e];
@@ -462,12 +469,14 @@ __global__ void log_scripted_turn_kernel(int n, int max_turns, int act_pitch, Wo
     ep_done[e] = step.done[e];
 }
 __global__ void clear_episode_log_kernel(int n, float* ep_return, int32_t* ep_length, uint8_t* ep_done) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) { ep_return[e] = 0.f; ep_length[e] = 0; ep_done[e] = 0; }
 }
 
 // live-episode count for the periodic early-exit test of long rollouts
 __global__ void count_live_kernel(const uint8_t* __restrict__ done, int n, int* __restrict__ live) {
+    pdl_enter();
     int c = 0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) c += done[e] ? 0 : 1;
 #pragma unroll

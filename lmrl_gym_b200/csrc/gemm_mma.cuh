@@ -16,6 +16,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
+#include "pdl.cuh"
 
 namespace lmrl {
 
@@ -148,6 +150,7 @@ __device__ __forceinline__ void epi_store(const GemmArgs& g, int row, int col, f
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_mma_kernel(const GemmArgs g) {
     extern __shared__ __align__(128) unsigned char gemm_smem[];
+    pdl_enter();
     const int M = *g.M_dev;
     if (M <= 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

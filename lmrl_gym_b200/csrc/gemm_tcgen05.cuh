@@ -239,8 +239,7 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                                                                                    const __grid_constant__ CUtensorMap tmOut,
                                                                                    const GemmArgs g) {
     extern __shared__ unsigned char tc_smem_raw[];
-    const int M = *g.M_dev;
-    if (M <= 0) return;
+    pdl_trigger();                                                       // the next kernel may start its prologue behind my tail
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                        // 128B swizzle atoms need 1024-byte alignment
     unsigned char* base_ptr = tc_smem_raw + (base - raw);
@@ -254,7 +253,6 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC_STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = g.N / TC_BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = n_tiles * m_tiles;
     const int n_acc = g.n_acc, n_stage = n_acc == 2 ? 1 : 2;          // TMEM: 512 columns = n_stage x n_acc accumulators of 256
 
     if (threadIdx.x == 0) {
@@ -277,6 +275,10 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched only shared memory / TMEM / kernel parameters; global memory of the predecessor from here on
+    pdl_wait();
+    const int M = *g.M_dev;
+    const int n_tiles = g.N / TC_BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = M > 0 ? n_tiles * m_tiles : 0;
 
     if (warp == 0) {
         // ===== TMA producer =====

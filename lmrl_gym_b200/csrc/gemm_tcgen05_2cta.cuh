@@ -59,8 +59,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
                                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                                 const __grid_constant__ CUtensorMap tmOut, const GemmArgs g) {
     extern __shared__ unsigned char tc2_smem_raw[];
-    const int M = *g.M_dev;
-    if (M <= 0) return;                                                  // uniform over the grid: no cluster barrier is left hanging
+    pdl_trigger();
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const uint32_t raw = smem_u32(tc2_smem_raw);
@@ -76,7 +75,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC2_STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = g.N / TC_BN, m_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM), total = n_tiles * m_tiles, kt = g.K / TC_BK;
+    const int kt = g.K / TC_BK;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
@@ -95,6 +94,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
     cluster_sync_all();                                                  // barriers of both CTAs are initialised, TMEM is allocated
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                                          // first access to the predecessor's global memory is below
+    const int M = *g.M_dev;
+    const int n_tiles = g.N / TC_BN, m_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM), total = M > 0 ? n_tiles * m_tiles : 0;
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): my 128 rows of A, my 128 rows of the W tile; bytes complete on the LEADER's barrier =====

@@ -89,6 +89,9 @@ struct Gpt2Dev {
     bool warm_valid = false;
     int64_t graph_launches = 0;
     int use_graphs = 1;
+    // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
+    // for this path (4096-episode Wordle rollout: 208.2 ms with graphs and no PDL, 223.8 ms with PDL; letters variant 81.0 vs 84.2)
+    int use_pdl = 0;
     int sm_count = 148;
     int gemm_impl = 1;                // 1 = tcgen05/TMEM/TMA (default), 0 = mma.sync cross-check path
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (base pointer, box rows) -> descriptor
@@ -114,6 +117,7 @@ __global__ void convert_to_bf16_kernel(const float* __restrict__ src, size_t n, 
 __global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, int n_header, StreamDev st,
                                    const uint64_t* __restrict__ seeds, uint64_t* __restrict__ episode_key, float* ep_return,
                                    int32_t* ep_length, uint8_t* ep_done) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     for (int i = 0; i < n_header; ++i) st.tokens[(size_t)e * st.cap + i] = header[i];
@@ -127,6 +131,7 @@ __global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, in
 __global__ void log_turn_kernel(int n, int max_turns, GenDev gen, StepOut step,
                                 float* ep_return, int32_t* ep_length, uint8_t* ep_done, float* step_reward, uint8_t* step_valid,
                                 uint8_t* step_fb, int32_t* step_aux, int32_t* act_tokens, int32_t* act_len) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int glen = gen.len[e];
@@ -190,46 +195,36 @@ static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
 }
 
 template <int EPI>
-static int launch_gemm_tc(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmW1,
+static int launch_gemm_tc(cudaStream_t st, int pdl, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmW1,
                           const CUtensorMap& tmW2, const CUtensorMap& tmOut, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         configured = true;
     }
-    gemm_bf16_tcgen05_kernel<EPI><<<sm_count, TcCfg<EPI>::THREADS, TC_SMEM_BYTES, st>>>(tmA, tmW, tmW1, tmW2, tmOut, g);
+    LMRL_CUDA(launch_k(pdl, 1, gemm_bf16_tcgen05_kernel<EPI>, dim3(sm_count), dim3(TcCfg<EPI>::THREADS), (size_t)TC_SMEM_BYTES, st, tmA, tmW, tmW1, tmW2, tmOut, g));
     return 0;
 }
 
 template <int EPI>
-static int launch_gemm_tc2(cudaStream_t st, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut, const GemmArgs& g) {
+static int launch_gemm_tc2(cudaStream_t st, int pdl, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmOut, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         configured = true;
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(sm_count & ~1));
-    cfg.blockDim = dim3(TC2_THREADS);
-    cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LMRL_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<EPI>, tmA, tmW, tmOut, g));
+    LMRL_CUDA(launch_k(pdl, 2, gemm_bf16_tcgen05_2cta_kernel<EPI>, dim3((unsigned)(sm_count & ~1)), dim3(TC2_THREADS), (size_t)TC2_SMEM_BYTES, st, tmA, tmW, tmOut, g));
     return 0;
 }
 
 template <int EPI>
-static int launch_gemm_mma(cudaStream_t st, int sm_count, const GemmArgs& g) {
+static int launch_gemm_mma(cudaStream_t st, int pdl, int sm_count, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
         LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_mma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         configured = true;
     }
-    gemm_bf16_mma_kernel<EPI><<<sm_count * 2, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+    LMRL_CUDA(launch_k(pdl, 1, gemm_bf16_mma_kernel<EPI>, dim3(sm_count * 2), dim3(GEMM_THREADS), (size_t)GEMM_SMEM_BYTES, st, g));
     return 0;
 }
 
@@ -281,18 +276,22 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     int rc;
     if constexpr (EPI != EPI_SAMPLE && EPI != EPI_LOGPROB) {
         if (use2) {
-            rc = launch_gemm_tc2<EPI>(e->stream, G.sm_count, *ta, *tw, *to, g);
+            rc = launch_gemm_tc2<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *to, g);
             e->prof_end();
             e->launches++;
             return rc;
         }
     }
-    if constexpr (EPI == EPI_RELU || EPI == EPI_LOGPROB) rc = launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
-    else rc = tc ? launch_gemm_tc<EPI>(e->stream, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(e->stream, G.sm_count, g);
+    if constexpr (EPI == EPI_RELU || EPI == EPI_LOGPROB) rc = launch_gemm_tc<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
+    else rc = tc ? launch_gemm_tc<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(e->stream, G.use_pdl, G.sm_count, g);
     e->prof_end();
     e->launches++;
     return rc;
 }
+
+// every kernel of the rollout path is launched through launch_k so that programmatic dependent launch can be switched on
+#define LMRL_K(kernel, grid, block, smem, st, ...) \
+    ::lmrl::launch_k((e && e->gpt2) ? e->gpt2->use_pdl : 0, 1, kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 
 #define LMRL_LAUNCH(cat, ...)                          \
     do {                                               \
@@ -314,6 +313,7 @@ struct ScoreReq {
 // merge the per-(tile, half) partial (max, sum) pairs of one row: out = logit_target - logsumexp
 __global__ void logprob_finalize_kernel(const float2* __restrict__ partial, int n_part, const float* __restrict__ tlogit, const int* __restrict__ n_dev,
                                         float* __restrict__ out) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int n = *n_dev;
@@ -349,7 +349,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     const int ew_blocks = G.sm_count * 8;
     e->cur_pass_slot = -1;
     e->cur_mode = mode;
-    LMRL_LAUNCH(2, build_rows_kernel<<<1, 1024, 0, st>>>(mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     if (e->profile && e->n_passes < e->max_passes) {      // live row / slot counts of this pass, for the FLOP accounting
         e->cur_pass_slot = e->n_passes++;
         cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -357,8 +357,8 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 2, G.rows.ctx_total, sizeof(int), cudaMemcpyDeviceToHost, st);
     }
     if (mode == 0)
-        LMRL_LAUNCH(2, fill_prefill_rows_kernel<<<(n_env * 32 + 255) / 256, 256, 0, st>>>(G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
-    LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
+        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+    LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     const int n_towers = G.policy_kind == 1 ? 2 : 1;
     // head operand buffers: the per-env sampling buffers, or the (larger) scoring buffers
@@ -369,10 +369,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     const int* head_gather = score ? score->rows : G.rows.slot_last;
     for (int t = 0; t < n_towers; ++t) {
         const TowerDev& T = G.tw[t];
-        if (t > 0) LMRL_LAUNCH(2, embed_kernel<<<ew_blocks, 256, 0, st>>>(T.wte, T.wpe, D.d_model, G.rows, G.x));
+        if (t > 0) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
         for (int l = 0; l < D.n_layer; ++l) {
             const LayerDev& L = T.layers[l];
-            LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+            LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
             GemmArgs a{};
             a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
             a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
@@ -381,16 +381,15 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
             // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
             if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
             if (mode == 0)
-                LMRL_LAUNCH(-1, attention_prefill_kernel<<<std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32,
-                                                           ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                               0.125f * 1.4426950408889634f, G.att));
             else
-                LMRL_LAUNCH(-1, attention_kernel<<<att_blocks, ATT_WARPS * 32, 0, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                                  0.125f, G.att));
             GemmArgs p{};
             p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
             if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
-            LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+            LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
             GemmArgs f{};
             f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
             if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
@@ -399,7 +398,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
             if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
         }
         // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
-        LMRL_LAUNCH(2, layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
+        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
                                                                   t == 0 ? xl : xl1, t == 0 ? G.xl_cols : D.d_model));
     }
     // top-k / top-p: the LM head dumps fp32 logits and a per-row filter kernel samples from the survivors (slow path)
@@ -414,7 +413,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         logits_out = G.logits;
     }
     if (!score)
-        LMRL_LAUNCH(2, prepare_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
+        LMRL_LAUNCH(2, LMRL_K(prepare_sample_kernel, (n_env + 255) / 256, 256, 0, st, G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
     GemmArgs h{};
     h.A = xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = head_n;
     h.best = filtered ? G.best_scratch : G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f);
@@ -444,7 +443,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     if (score) {
         h.lp_partial = G.lp_partial; h.lp_target = score->targets; h.lp_tlogit = G.lp_tlogit;
         if (launch_gemm<EPI_LOGPROB>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
-        LMRL_LAUNCH(2, logprob_finalize_kernel<<<std::max(1, std::min((score->n_score + 7) / 8, G.sm_count * 8)), 256, 0, st>>>(
+        LMRL_LAUNCH(2, LMRL_K(logprob_finalize_kernel, std::max(1, std::min((score->n_score + 7) / 8, G.sm_count * 8)), 256, 0, st, 
                            G.lp_partial, 2 * (G.v_pad / TC_BN), G.lp_tlogit, score->n_dev, score->out));
     } else {
         if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx)) return -1;
@@ -456,10 +455,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
                 LMRL_CUDA(cudaFuncSetAttribute(filtered_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem));
                 configured = true;
             }
-            LMRL_LAUNCH(2, filtered_sample_kernel<<<n_env, FS_THREADS, fs_smem, st>>>(logits_out, D.n_vocab, G.rows, G.row_key, h.inv_temp, s.do_sample,
+            LMRL_LAUNCH(2, LMRL_K(filtered_sample_kernel, n_env, FS_THREADS, fs_smem, st, logits_out, D.n_vocab, G.rows, G.row_key, h.inv_temp, s.do_sample,
                                                                                     s.top_k, s.top_p, G.best));
         }
-        LMRL_LAUNCH(2, finalize_sample_kernel<<<(n_env + 255) / 256, 256, 0, st>>>(G.rows, G.gen, G.best));
+        LMRL_LAUNCH(2, LMRL_K(finalize_sample_kernel, (n_env + 255) / 256, 256, 0, st, G.rows, G.gen, G.best));
     }
     e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
@@ -680,7 +679,7 @@ int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_t
         LMRL_CUDA(cudaMemcpyAsync(G.episode_key, idx.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, e->stream));
         LMRL_CUDA(cudaStreamSynchronize(e->stream));
     }
-    LMRL_LAUNCH(2, clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen));
+    LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, e->stream, n, G.gen));
     for (int k = 0; k < e->cfg.max_new_tokens; ++k)
         if (forward_and_sample(e, k == 0 ? 0 : 1, n, nullptr, nullptr, turn, *s, nullptr)) return -1;
     LMRL_CUDA(cudaMemcpyAsync(out_tokens, G.gen.tok, sizeof(int32_t) * (size_t)n * e->cfg.max_new_tokens, cudaMemcpyDeviceToHost, e->stream));
@@ -700,7 +699,7 @@ int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok
         G.owned.push_back(G.logits);
         G.logits_rows = need;
     }
-    clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
+    LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, e->stream, n, G.gen);
     lmrl_sampling s{1.0f, 0, 0, 0, 0.f};
     if (forward_and_sample(e, 0, n, nullptr, nullptr, 0, s, G.logits)) return -1;
     // rows come back in slot order == env order for envs with tokens; scatter on the host
@@ -764,7 +763,7 @@ int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok,
     LMRL_CUDA(cudaMemcpyAsync(G.score_rows, rows.data(), sizeof(int32_t) * n_score, cudaMemcpyHostToDevice, e->stream));
     LMRL_CUDA(cudaMemcpyAsync(G.score_targets, targets.data(), sizeof(int32_t) * n_score, cudaMemcpyHostToDevice, e->stream));
     LMRL_CUDA(cudaMemcpyAsync(G.score_n, &n_score, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-    clear_gen_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(n, G.gen);
+    LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, e->stream, n, G.gen);
     lmrl_sampling s{temperature, 0, 0, 0, 0.f};
     ScoreReq req{G.score_rows, G.score_targets, G.score_n, G.lp_out, n_score};
     if (forward_and_sample(e, 0, n, nullptr, nullptr, 0, s, nullptr, &req)) return -1;
@@ -793,32 +792,32 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
     const int blocks = (n + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK;
     const uint8_t* done = wordle ? e->wordle.done : e->maze.done;
     if (wordle) {
-        LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
-        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, (int)e->header_tokens.size(), G.stream, seeds_dev,
+        LMRL_LAUNCH(3, LMRL_K(wordle_reset_kernel, blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st, e->wordle, seeds_dev, n));
+        LMRL_LAUNCH(3, LMRL_K(init_stream_kernel, (n + 255) / 256, 256, 0, st, n, e->d_header, (int)e->header_tokens.size(), G.stream, seeds_dev,
                                                                            G.episode_key, G.ep_return, G.ep_length, G.ep_done));
     } else {
-        LMRL_LAUNCH(3, maze_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->maze, seeds_dev, opt_pos_dev, nullptr, n));
-        LMRL_LAUNCH(3, init_stream_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, e->d_header, 0, G.stream, seeds_dev,
+        LMRL_LAUNCH(3, LMRL_K(maze_reset_kernel, blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st, e->maze, seeds_dev, opt_pos_dev, nullptr, n));
+        LMRL_LAUNCH(3, LMRL_K(init_stream_kernel, (n + 255) / 256, 256, 0, st, n, e->d_header, 0, G.stream, seeds_dev,
                                                                            G.episode_key, G.ep_return, G.ep_length, G.ep_done));
-        LMRL_LAUNCH(3, maze_init_stream_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->maze, G.stream, n));
+        LMRL_LAUNCH(3, LMRL_K(maze_init_stream_kernel, (n + 127) / 128, 128, 0, st, e->maze, G.stream, n));
     }
     ActionSrc src{};
     src.tokens = G.gen.tok; src.ntokens = G.gen.len; src.tpitch = G.gen.max_new;
     for (int turn = 0; turn < T; ++turn) {
-        LMRL_LAUNCH(2, clear_gen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, G.gen));
+        LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen));
         for (int k = 0; k < e->cfg.max_new_tokens; ++k)
             if (forward_and_sample(e, k == 0 ? 0 : 1, n, done, G.ep_length, 0, s, nullptr)) return -1;
         if (wordle)
-            LMRL_LAUNCH(3, wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(
+            LMRL_LAUNCH(3, LMRL_K(wordle_step_kernel, blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st, 
                                e->wordle, e->tok, src, nullptr, e->step, G.stream, n));
         else
-            LMRL_LAUNCH(3, maze_fused_step_kernel<<<(n + 127) / 128, 128, 0, st>>>(e->maze, e->tok, src, e->step, G.stream, n));
-        LMRL_LAUNCH(3, log_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, G.gen, e->step, G.ep_return, G.ep_length, G.ep_done,
+            LMRL_LAUNCH(3, LMRL_K(maze_fused_step_kernel, (n + 127) / 128, 128, 0, st, e->maze, e->tok, src, e->step, G.stream, n));
+        LMRL_LAUNCH(3, LMRL_K(log_turn_kernel, (n + 255) / 256, 256, 0, st, n, T, G.gen, e->step, G.ep_return, G.ep_length, G.ep_done,
                                                                         G.step_reward, G.step_valid, G.step_fb, G.step_aux, G.act_tokens, G.act_len));
         // long episodes (Maze: up to max_steps + 1 turns): every 8th turn ask the device whether anything is still running
         if (T > 8 && (turn & 7) == 7 && turn + 1 < T) {
             LMRL_CUDA(cudaMemsetAsync(G.live, 0, sizeof(int), st));
-            LMRL_LAUNCH(2, count_live_kernel<<<32, 256, 0, st>>>(done, n, G.live));
+            LMRL_LAUNCH(2, LMRL_K(count_live_kernel, 32, 256, 0, st, done, n, G.live));
             int live = 0;
             LMRL_CUDA(cudaMemcpyAsync(&live, G.live, sizeof(int), cudaMemcpyDeviceToHost, st));
             LMRL_CUDA(cudaStreamSynchronize(st));
@@ -885,6 +884,14 @@ static int rollout_run(lmrl_engine* e, int32_t env_kind, bool has_opt, int32_t n
 
 extern "C" {
 
+int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable) {
+    LMRL_CHECK(e && e->gpt2, "lmrl_set_use_pdl: no GPT-2 parameters loaded");
+    e->gpt2->use_pdl = enable ? 1 : 0;
+    if (e->gpt2->graph_exec) { cudaGraphExecDestroy(e->gpt2->graph_exec); e->gpt2->graph_exec = nullptr; }
+    e->gpt2->warm_valid = false;
+    return 0;
+}
+
 int lmrl_set_use_graphs(lmrl_engine* e, int32_t enable) {
     LMRL_CHECK(e && e->gpt2, "lmrl_set_use_graphs: no GPT-2 parameters loaded");
     e->gpt2->use_graphs = enable ? 1 : 0;
@@ -927,15 +934,15 @@ int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, 
     cudaStream_t st = e->stream;
     const int T = e->cfg.max_turns;
     const int blocks = (n + ENV_WARPS_PER_BLOCK - 1) / ENV_WARPS_PER_BLOCK;
-    LMRL_LAUNCH(3, wordle_reset_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st>>>(e->wordle, seeds_dev, n));
-    LMRL_LAUNCH(3, clear_episode_log_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, out->ep_return, out->ep_length, out->ep_done));
+    LMRL_LAUNCH(3, LMRL_K(wordle_reset_kernel, blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * MT_N * sizeof(uint32_t), st, e->wordle, seeds_dev, n));
+    LMRL_LAUNCH(3, LMRL_K(clear_episode_log_kernel, (n + 255) / 256, 256, 0, st, n, out->ep_return, out->ep_length, out->ep_done));
     ActionSrc src{};
     src.scripted = 1; src.prob_smart = prob_smart; src.policy_seed = policy_seed; src.episode_seed = seeds_dev;
     StreamDev none{};
     for (int turn = 0; turn < std::min(T, (int)WORDLE_TRIES); ++turn) {
-        LMRL_LAUNCH(3, wordle_step_kernel<<<blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st>>>(
+        LMRL_LAUNCH(3, LMRL_K(wordle_step_kernel, blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st, 
                            e->wordle, e->tok, src, nullptr, e->step, none, n));
-        LMRL_LAUNCH(3, log_scripted_turn_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, T, e->cfg.max_new_tokens, e->wordle, e->step, out->ep_return,
+        LMRL_LAUNCH(3, LMRL_K(log_scripted_turn_kernel, (n + 255) / 256, 256, 0, st, n, T, e->cfg.max_new_tokens, e->wordle, e->step, out->ep_return,
                                                                                  out->ep_length, out->ep_done, out->step_reward, out->step_valid,
                                                                                  out->step_feedback, out->step_aux, out->act_tokens, out->act_len));
     }
@@ -977,13 +984,13 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
     if (impl == 2) {
         CUtensorMap ta, tw, to;
         rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC2_B_ROWS) || make_tmap(&to, dR, m_pad, N, 32, true);
-        if (!rc) rc = launch_gemm_tc2<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, to, g);
+        if (!rc) rc = launch_gemm_tc2<EPI_RESID>(e->stream, 0, prop.multiProcessorCount, ta, tw, to, g);
     } else if (impl == 1) {
         CUtensorMap ta, tw, to;
         rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC_BN) || make_tmap(&to, dR, m_pad, N, 32, true);
-        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, prop.multiProcessorCount, ta, tw, tw, tw, to, g);
+        if (!rc) rc = launch_gemm_tc<EPI_RESID>(e->stream, 0, prop.multiProcessorCount, ta, tw, tw, tw, to, g);
     } else {
-        rc = launch_gemm_mma<EPI_RESID>(e->stream, prop.multiProcessorCount, g);
+        rc = launch_gemm_mma<EPI_RESID>(e->stream, 0, prop.multiProcessorCount, g);
     }
     e->launches++;
     cudaError_t err = cudaStreamSynchronize(e->stream);
@@ -1048,14 +1055,13 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                 case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx); break;
                 case 5:
                     if (rpe > 1)
-                        attention_prefill_kernel<<<std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32,
-                                                   ATTP_WARPS * ATTP_WARP_SMEM, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                        LMRL_K(attention_prefill_kernel, std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
                                                                                       0.125f * 1.4426950408889634f, G.att);
                     else
-                        attention_kernel<<<att_blocks, ATT_WARPS * 32, 0, st>>>(G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
+                        LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
                     break;
-                case 6: layernorm_kernel<<<ew_blocks, 256, 0, st>>>(G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model); break;
-                case 7: embed_kernel<<<ew_blocks, 256, 0, st>>>(G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x); break;
+                case 6: LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model); break;
+                case 7: LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x); break;
             }
         }
         cudaEventRecord(ev[1], st);

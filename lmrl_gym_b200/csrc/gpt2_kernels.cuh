@@ -43,6 +43,7 @@ struct GenDev {
 __global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ done, const int32_t* __restrict__ stream_tok,
                                   const int32_t* __restrict__ stream_len, const int32_t* __restrict__ kv_len, int stream_cap,
                                   GenDev gen, RowsDev rows) {
+    pdl_enter();
     __shared__ int warp_sums[2][32];
     __shared__ int carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
@@ -98,6 +99,7 @@ __global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ d
 // prefill: expand each slot into its rows (one warp per slot); also resets the per-turn generation state
 __global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok, const int32_t* __restrict__ stream_len,
                                          int32_t* __restrict__ kv_len, int stream_cap, GenDev gen, RowsDev rows) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= *rows.n_slots) return;
@@ -109,6 +111,7 @@ __global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok,
 }
 
 __global__ void clear_gen_kernel(int B, GenDev gen) {
+    pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < B) { gen.active[e] = 0; gen.len[e] = 0; }
 }
@@ -116,6 +119,7 @@ __global__ void clear_gen_kernel(int B, GenDev gen) {
 // ---- K1: x = wte[tok] + wpe[pos] (fp32 residual stream) ------------------------------------------------------------
 __global__ void embed_kernel(const __nv_bfloat16* __restrict__ wte, const __nv_bfloat16* __restrict__ wpe, int d, RowsDev rows,
                              float* __restrict__ x) {
+    pdl_enter();
     const int M = *rows.M;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -144,6 +148,7 @@ __global__ void embed_kernel(const __nv_bfloat16* __restrict__ wte, const __nv_b
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  int d, float eps, const int* __restrict__ n_dev, const int* __restrict__ gather,
                                  __nv_bfloat16* __restrict__ out, int out_pitch) {
+    pdl_enter();
     const int n = *n_dev;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -204,6 +209,7 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float f[8]) {
 __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                       const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
                                                                       int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, s = lane & 7;
     const int total = *rows.n_slots * n_head;
@@ -310,6 +316,7 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32, 2) attention_prefill_kernel(c
                                                                                const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
                                                                                int d_model, int t_cap, float scale_log2e,
                                                                                __nv_bfloat16* __restrict__ out) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char attp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -461,6 +468,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
 
 __global__ void prepare_sample_kernel(RowsDev rows, GenDev gen, const uint64_t* __restrict__ episode_key, const int32_t* __restrict__ turn_of_env,
                                       int turn_const, uint64_t base_seed, uint64_t* __restrict__ row_key, unsigned long long* __restrict__ best) {
+    pdl_enter();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= *rows.n_slots) return;
     const int e = rows.slot_env[j];
@@ -522,6 +530,7 @@ __device__ __forceinline__ int block_excl_scan_i(int v, int* red, int* total) {
 __global__ void __launch_bounds__(FS_THREADS) filtered_sample_kernel(const float* __restrict__ logits, int n_vocab, RowsDev rows, const uint64_t* __restrict__ row_key,
                                                                      float inv_temp, int do_sample, int top_k, float top_p,
                                                                      unsigned long long* __restrict__ best) {
+    pdl_enter();
     extern __shared__ float fs_row[];                  // [n_vocab] scaled logits; -inf once filtered out
     __shared__ float red_f[FS_THREADS / 32];
     __shared__ int red_i[FS_THREADS / 32];
@@ -599,6 +608,7 @@ __global__ void __launch_bounds__(FS_THREADS) filtered_sample_kernel(const float
 }
 
 __global__ void finalize_sample_kernel(RowsDev rows, GenDev gen, const unsigned long long* __restrict__ best) {
+    pdl_enter();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= *rows.n_slots) return;
     const int e = rows.slot_env[j];

@@ -88,6 +88,10 @@ class Engine:
         """CUDA-graph replay of fused rollouts (default on)."""
         check(self.lib.lmrl_set_use_graphs(self.handle, 1 if enable else 0))
 
+    def set_use_pdl(self, enable: bool):
+        """Programmatic dependent launch between the kernels of a pass (default off: measured slower on B200)."""
+        check(self.lib.lmrl_set_use_pdl(self.handle, 1 if enable else 0))
+
     def set_gemm_impl(self, impl: int):
         """1 = tcgen05/TMEM/TMA (default), 0 = the mma.sync kernel (independent cross-check used by the tests)."""
         check(self.lib.lmrl_set_gemm_impl(self.handle, int(impl)))
