@@ -199,8 +199,10 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);
 
-/* GEMM implementation switch (default 1 = tcgen05/TMEM/TMA; 0 = the mma.sync kernel kept as an independent cross-check)
- * and a unit-test hook: resid[M,N] += A[M,K] · W[N,K]^T + bias through the chosen implementation (bf16 bit patterns in) */
+/* GEMM implementation switch (default 1 = tcgen05/TMEM/TMA, one CTA per 128x256 tile; 2 = CTA pairs (cta_group::2, 256x256) on
+ * prefill passes; 0 = the mma.sync kernel kept as an independent cross-check) and a unit-test hook:
+ * resid[M,N] += A[M,K] · W[N,K]^T + bias through the chosen implementation (bf16 bit patterns in); the hook also accepts
+ * impl 3 = the 128x192-tile tcgen05 kernel the engine uses for the N = 768 GEMMs of decode passes */
 int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl);
 int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int32_t K, const uint16_t* A_bf16,
                         const uint16_t* W_bf16, const float* bias, float* resid_inout);

@@ -40,6 +40,16 @@ constexpr int TC_EPI_BUF = 32 * 128;                   // one staged box: 32 row
 constexpr int TC_EPI_BYTES = 4 * 2 * TC_EPI_BUF;       // 4 epilogue warps x double buffer
 constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
+// per tile width BN (256 by default; 192 for the N = 768 GEMMs of a decode pass: 4 x 32 = 128 tiles fill 148 SMs in one wave of
+// 3/4-size tiles where 256-wide tiles give 96 full-size ones)
+template <int BN> struct TcTile {
+    static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "tile width: a multiple of 64 up to 256 (2 x BN TMEM columns)");
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/;
+    // kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major, N = BN, M = 128
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+};
 
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major, N = 256, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -125,7 +135,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // ---- storing epilogues of one 128 x 256 accumulator (shared by the 1-CTA and the 2-CTA kernel) ----------------------
 // t_addr: TMEM address of this warp's lane quadrant; m0 / n0: origin of the CTA's tile; stg: this warp's two staging boxes
-template <int EPI>
+template <int EPI, int BN = TC_BN>
 __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorMap& tmOut, uint32_t t_addr, int M, int m0, int n0, int quad,
                                               int lane, uint32_t stg, uint32_t& n_boxes) {
     const int row = m0 + quad * 32 + lane;                                         // this thread's output row
@@ -136,7 +146,7 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
         __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
         size_t base_off = 0;
         if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_addr + c0, r);
             if (live) {
@@ -157,7 +167,7 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
         }
     } else if constexpr (EPI == EPI_RESID) {
         // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
-        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
             const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
             if (lane == 0) bulk_wait_read<1>();                            // the box issued two steps ago has been read
             __syncwarp();
@@ -179,7 +189,7 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
         }
     } else {
         // bf16 outputs (GeLU, Q): 64-column boxes by TMA store
-        for (int c0 = 0; c0 < TC_BN; c0 += 64) {
+        for (int c0 = 0; c0 < BN; c0 += 64) {
             const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
@@ -231,7 +241,7 @@ __device__ __forceinline__ void sample_chunk(const uint32_t r[32], int col0, flo
     for (int j = 0; j < 32; ++j) sample_update<NOISE, MASK>(__uint_as_float(r[j]), col0 + j, inv_temp, key, n_vocab, best[j & 3], best_col[j & 3]);
 }
 
-template <int EPI>
+template <int EPI, int BN = TC_BN>
 __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                                    const __grid_constant__ CUtensorMap tmW,
                                                                                    const __grid_constant__ CUtensorMap tmW1,
@@ -243,14 +253,14 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                        // 128B swizzle atoms need 1024-byte alignment
     unsigned char* base_ptr = tc_smem_raw + (base - raw);
-    const uint32_t epi_base = base + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t epi_base = base + TC_STAGES * TcTile<BN>::STAGE_BYTES;
     const uint32_t bar_base = epi_base + TC_EPI_BYTES;
     // barrier layout (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC_STAGES + 4));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC_STAGES * TcTile<BN>::STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC_STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_acc = g.n_acc, n_stage = n_acc == 2 ? 1 : 2;          // TMEM: 512 columns = n_stage x n_acc accumulators of 256
@@ -278,21 +288,21 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
     // everything above touched only shared memory / TMEM / kernel parameters; global memory of the predecessor from here on
     pdl_wait();
     const int M = *g.M_dev;
-    const int n_tiles = g.N / TC_BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = M > 0 ? n_tiles * m_tiles : 0;
+    const int n_tiles = g.N / BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = M > 0 ? n_tiles * m_tiles : 0;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
+                const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
                 for (int sg = 0; sg < g.n_seg; ++sg) {
                     const CUtensorMap* tw = g.seg[sg].w_idx == 0 ? &tmW : (g.seg[sg].w_idx == 1 ? &tmW1 : &tmW2);
                     const int a_kb0 = g.seg[sg].a_kb0, nkb = g.seg[sg].kb_count;
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-                        const uint32_t sA = base + stage * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
+                        mbar_expect_tx(full_bar(stage), TcTile<BN>::STAGE_BYTES);
+                        const uint32_t sA = base + stage * TcTile<BN>::STAGE_BYTES, sB = sA + TC_A_BYTES;
                         tma_load_2d(sA, &tmA, full_bar(stage), (a_kb0 + kb) * TC_BK, m0);
                         tma_load_2d(sB, tw, full_bar(stage), kb * TC_BK, n0);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
@@ -311,15 +321,15 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                 uint32_t started = 0;                                     // bit a: accumulator a already holds a partial sum
                 for (int sg = 0; sg < g.n_seg; ++sg) {
                     const int a = g.seg[sg].acc, nkb = g.seg[sg].kb_count;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)((acc * n_acc + a) * TC_BN);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)((acc * n_acc + a) * BN);
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait(full_bar(stage), phase);                // TMA bytes have landed
                         tcgen05_fence_after();
-                        const uint32_t sA = base + stage * TC_STAGE_BYTES, sB = sA + TC_A_BYTES;
+                        const uint32_t sA = base + stage * TcTile<BN>::STAGE_BYTES, sB = sA + TC_A_BYTES;
                         const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
 #pragma unroll
                         for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)       // +32 bytes per UMMA_K step inside the swizzle atom
-                            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TC_IDESC, (((started >> a) & 1u) | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
+                            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), TcTile<BN>::IDESC, (((started >> a) & 1u) | (uint32_t)kb | (uint32_t)k) ? 1u : 0u);
                         tcgen05_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -336,23 +346,23 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
         uint32_t n_boxes = 0;                                                      // boxes issued by this warp (buffer toggle)
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * TC_BN;
+            const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_acc * TC_BN);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_acc * BN);
             const int row = m0 + quad * 32 + lane;                                 // this thread's output row
             if constexpr (EPI == EPI_SAMPLE || EPI == EPI_LOGPROB) {
                 // warps w and w+4 share the lane quadrant; each takes one 128-column half of the tile
                 const int half = (warp - 2) >> 2;
                 const bool live = row < M;
                 const uint64_t key = (live && EPI == EPI_SAMPLE) ? g.row_key[row] : 0ull;
-                const bool masked = n0 + TC_BN > g.n_vocab;                         // only the last N tile has padded columns
+                const bool masked = n0 + BN > g.n_vocab;                         // only the last N tile has padded columns
                 float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 int best_col[4] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
                 float lp_m = -INFINITY, lp_s = 0.f;                                 // EPI_LOGPROB: running max / sum of exp
                 const int lp_tgt = (EPI == EPI_LOGPROB && live) ? g.lp_target[row] : -1;
 #pragma unroll 1
-                for (int c0 = half * (TC_BN / 2); c0 < (half + 1) * (TC_BN / 2); c0 += 32) {
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(t_addr + c0, r);
                     const int col0 = n0 + c0;
@@ -362,7 +372,7 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                     }
                     if (n_acc == 2) {                                               // logit = min over the two Q heads
                         uint32_t r2[32];
-                        tmem_ld_32x32b_x32(t_addr + TC_BN + c0, r2);
+                        tmem_ld_32x32b_x32(t_addr + BN + c0, r2);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fminf(__uint_as_float(r[j]), __uint_as_float(r2[j]) + __ldg(g.bias2 + col0 + j)));
                     }
@@ -396,14 +406,14 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                     }
                 }
                 if constexpr (EPI == EPI_LOGPROB) {
-                    if (live) g.lp_partial[(size_t)row * (2 * n_tiles) + 2 * (n0 / TC_BN) + half] = make_float2(lp_m, lp_s);
+                    if (live) g.lp_partial[(size_t)row * (2 * n_tiles) + 2 * (n0 / BN) + half] = make_float2(lp_m, lp_s);
                 }
 #pragma unroll
                 for (int q = 1; q < 4; ++q)
                     if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
                 if (EPI == EPI_SAMPLE && live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
             } else {
-                tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, n_boxes);
+                tc_store_tile<EPI, BN>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, n_boxes);
             }
             tcgen05_fence_before();
             __syncwarp();

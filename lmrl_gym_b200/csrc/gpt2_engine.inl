@@ -89,6 +89,7 @@ struct Gpt2Dev {
     bool warm_valid = false;
     int64_t graph_launches = 0;
     int use_graphs = 1;
+    int narrow_decode_tiles = 1;      // 128 x 192 tiles for the N = 768 residual GEMMs of decode passes
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
     // for this path (4096-episode Wordle rollout: 208.2 ms with graphs and no PDL, 223.8 ms with PDL; letters variant 81.0 vs 84.2)
     int use_pdl = 0;
@@ -194,15 +195,16 @@ static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
     return make_tmap(out, base, rows, K, box_rows, false);
 }
 
-template <int EPI>
+template <int EPI, int BN = TC_BN>
 static int launch_gemm_tc(cudaStream_t st, int pdl, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmW1,
                           const CUtensorMap& tmW2, const CUtensorMap& tmOut, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
-        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTile<BN>::SMEM_BYTES));
         configured = true;
     }
-    LMRL_CUDA(launch_k(pdl, 1, gemm_bf16_tcgen05_kernel<EPI>, dim3(sm_count), dim3(TcCfg<EPI>::THREADS), (size_t)TC_SMEM_BYTES, st, tmA, tmW, tmW1, tmW2, tmOut, g));
+    LMRL_CUDA(launch_k(pdl, 1, gemm_bf16_tcgen05_kernel<EPI, BN>, dim3(sm_count), dim3(TcCfg<EPI>::THREADS), (size_t)TcTile<BN>::SMEM_BYTES, st, tmA, tmW,
+                       tmW1, tmW2, tmOut, g));
     return 0;
 }
 
@@ -245,7 +247,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     const bool tc = G.gemm_impl >= 1 && g.N % TC_BN == 0 && g.K % TC_BK == 0;
     LMRL_CHECK(tc || (g.n_seg == 1 && EPI != EPI_RELU && EPI != EPI_LOGPROB), "this GEMM needs the tcgen05 kernel (multi-segment / ReLU epilogue): N=%d K=%d", g.N, g.K);
     const CUtensorMap *ta = nullptr, *tw = nullptr, *tw1 = nullptr, *tw2 = nullptr, *to = nullptr;
-    bool use2 = false;
+    bool use2 = false, narrow = false;
     if (tc) {
         auto get = [&](const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32) -> const CUtensorMap* {
             auto key = std::make_pair(base, (int)box_rows | (f32 ? 1 << 16 : 0));
@@ -259,8 +261,10 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
         };
         // CTA-pair kernel: plain GEMMs of the prefill passes (many rows); each CTA stages 128 of the 256 W rows
         use2 = G.gemm_impl == 2 && e->cur_mode == 0 && g.n_seg == 1 && EPI != EPI_SAMPLE && EPI != EPI_LOGPROB && !x.W1;
+        // decode pass (one row per env), N = 768 residual GEMMs: 192-wide tiles fill the SMs better than 256-wide ones
+        narrow = EPI == EPI_RESID && G.narrow_decode_tiles && e->cur_mode == 1 && g.N == 768 && g.n_seg == 1 && !use2;
         ta = get(g.A, a_rows, x.a_cols ? x.a_cols : (size_t)g.K, TC_BM, false);
-        tw = get(g.W, w_rows, (size_t)g.K, use2 ? TC2_B_ROWS : TC_BN, false);
+        tw = get(g.W, w_rows, (size_t)g.K, use2 ? TC2_B_ROWS : (narrow ? 192 : TC_BN), false);
         tw1 = x.W1 ? get(x.W1, w_rows, x.w1_cols, TC_BN, false) : tw;
         tw2 = x.W2 ? get(x.W2, w_rows, x.w2_cols, TC_BN, false) : tw;
         // output map (TMA store / reduce-add source boxes are 32 rows x 128 bytes); the sampling epilogue stores nothing
@@ -277,6 +281,14 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     if constexpr (EPI != EPI_SAMPLE && EPI != EPI_LOGPROB) {
         if (use2) {
             rc = launch_gemm_tc2<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *to, g);
+            e->prof_end();
+            e->launches++;
+            return rc;
+        }
+    }
+    if constexpr (EPI == EPI_RESID) {
+        if (narrow) {
+            rc = launch_gemm_tc<EPI_RESID, 192>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g);
             e->prof_end();
             e->launches++;
             return rc;
@@ -960,8 +972,10 @@ int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl) {
 int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int32_t K, const uint16_t* A_bf16, const uint16_t* W_bf16,
                         const float* bias, float* resid_inout) {
     LMRL_CHECK(e && A_bf16 && W_bf16 && resid_inout, "lmrl_test_gemm: null argument");
-    LMRL_CHECK(M > 0 && N % 128 == 0 && K % 64 == 0 && (impl == 0 || N % TC_BN == 0), "lmrl_test_gemm: unsupported shape %d x %d x %d", M, N, K);
-    LMRL_CHECK(impl >= 0 && impl <= 2, "lmrl_test_gemm: impl must be 0, 1 or 2");
+    LMRL_CHECK(M > 0 && N % 64 == 0 && K % 64 == 0 && (impl == 3 || N % 128 == 0) && (impl == 0 || impl == 3 || N % TC_BN == 0),
+               "lmrl_test_gemm: unsupported shape %d x %d x %d", M, N, K);
+    LMRL_CHECK(impl >= 0 && impl <= 3, "lmrl_test_gemm: impl must be 0, 1, 2 or 3");
+    LMRL_CHECK(impl != 3 || N % 192 == 0, "lmrl_test_gemm: impl 3 (192-wide tiles) needs N %% 192 == 0");
     LMRL_CUDA(cudaSetDevice(e->device));
     const size_t m_pad = ((size_t)M + 255) / 256 * 256;
     __nv_bfloat16 *dA = nullptr, *dW = nullptr;
@@ -981,7 +995,11 @@ int lmrl_test_gemm_host(lmrl_engine* e, int32_t impl, int32_t M, int32_t N, int3
     cudaDeviceProp prop;
     LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
     int rc = 0;
-    if (impl == 2) {
+    if (impl == 3) {
+        CUtensorMap ta, tw, to;
+        rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, 192) || make_tmap(&to, dR, m_pad, N, 32, true);
+        if (!rc) rc = launch_gemm_tc<EPI_RESID, 192>(e->stream, 0, prop.multiProcessorCount, ta, tw, tw, tw, to, g);
+    } else if (impl == 2) {
         CUtensorMap ta, tw, to;
         rc = make_tmap_bf16(&ta, dA, m_pad, K, TC_BM) || make_tmap_bf16(&tw, dW, N, K, TC2_B_ROWS) || make_tmap(&to, dR, m_pad, N, 32, true);
         if (!rc) rc = launch_gemm_tc2<EPI_RESID>(e->stream, 0, prop.multiProcessorCount, ta, tw, to, g);
