@@ -27,17 +27,18 @@
 namespace lmrl {
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 4, TC_UMMA_K = 16;
-// warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  The storing epilogues use 4 warps (one per TMEM lane quadrant);
-// the sampling epilogue is ALU-heavy (hash + 2 MUFU per logit) and uses 8: warps w and w+4 share a quadrant and split the columns.
+// warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue.  Eight epilogue warps: warps w and w+4 share a TMEM lane quadrant and
+// split the tile's columns.  With K = 768 a tile's mainloop is only ~6 k cycles, and four warps draining 128 x 256 fp32 (bias,
+// GeLU / Gumbel hash, shared-memory staging) took about as long — tensor activity of the K = 768 GEMMs was epilogue-bound.
 template <int EPI> struct TcCfg {
-    static constexpr int EPI_WARPS = (EPI == EPI_SAMPLE || EPI == EPI_LOGPROB) ? 8 : 4;
+    static constexpr int EPI_WARPS = 8;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_EPI_BUF = 32 * 128;                   // one staged box: 32 rows x 128 bytes (128B-swizzled, TMA store source)
-constexpr int TC_EPI_BYTES = 4 * 2 * TC_EPI_BUF;       // 4 epilogue warps x double buffer
+constexpr int TC_EPI_BYTES = 8 * TC_EPI_BUF;           // one staging box per epilogue warp
 constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
 // per tile width BN (256 by default; 192 for the N = 768 GEMMs of a decode pass: 4 x 32 = 128 tiles fill 148 SMs in one wave of
@@ -133,20 +134,22 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// ---- storing epilogues of one 128 x 256 accumulator (shared by the 1-CTA and the 2-CTA kernel) ----------------------
-// t_addr: TMEM address of this warp's lane quadrant; m0 / n0: origin of the CTA's tile; stg: this warp's two staging boxes
+// ---- storing epilogues of one 128 x BN accumulator (shared by the 1-CTA and the 2-CTA kernel) ------------------------
+// t_addr: TMEM address of this warp's lane quadrant; m0 / n0: origin of the CTA's tile; [c_beg, c_end): this warp's columns of
+// the tile; stg: this warp's staging box (32 rows x 128 bytes, 128B-swizzled).  The box is single buffered: TMEM load, bias and
+// activation happen in registers first, then the warp waits for the TMA engine to have read the previous box and refills it.
 template <int EPI, int BN = TC_BN>
 __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorMap& tmOut, uint32_t t_addr, int M, int m0, int n0, int quad,
-                                              int lane, uint32_t stg, uint32_t& n_boxes) {
+                                              int lane, uint32_t stg, int c_beg, int c_end) {
     const int row = m0 + quad * 32 + lane;                                         // this thread's output row
     if (EPI == EPI_QKV && n0 >= g.d_model) {
         // K / V tile: scatter this thread's row segment into the KV slab at (env, pos)
         const bool live = row < M;
-        const int part = n0 / g.d_model;                                   // 1 = K, 2 = V (tiles never straddle: d % 256 == 0)
+        const int part = n0 / g.d_model;                                   // 1 = K, 2 = V (tiles never straddle: d % BN == 0)
         __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
         size_t base_off = 0;
         if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_addr + c0, r);
             if (live) {
@@ -167,32 +170,31 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
         }
     } else if constexpr (EPI == EPI_RESID) {
         // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
-            if (lane == 0) bulk_wait_read<1>();                            // the box issued two steps ago has been read
-            __syncwarp();
+        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_addr + c0, r);
-            const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
+            if (g.bias) {
+                const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.bias) b = __ldg(bias4 + j);
-                st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * j]) + b.x),
-                             __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y), __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z),
-                             __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w));
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(bias4 + j);
+                    r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + b.x); r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y);
+                    r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z); r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w);
+                }
             }
+            if (lane == 0) bulk_wait_read<0>();                            // the TMA engine has read the previous box
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + quad * 32); bulk_commit(); }
-            ++n_boxes;
+            if (lane == 0) { tma_reduce_add_2d(&tmOut, stg, n0 + c0, m0 + quad * 32); bulk_commit(); }
         }
     } else {
-        // bf16 outputs (GeLU, Q): 64-column boxes by TMA store
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-            const uint32_t buf = stg + (n_boxes & 1u) * TC_EPI_BUF;
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
+        // bf16 outputs (GeLU, ReLU, Q): 64-column boxes by TMA store
+        static_assert(EPI == EPI_RESID || (BN / 2) % 64 == 0, "bf16 epilogues store 64-column boxes: BN / 2 must be a multiple of 64");
+        for (int c0 = c_beg; c0 < c_end; c0 += 64) {
+            uint32_t pk[32];                                               // 64 columns of this row, packed bf16
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t r[32];
@@ -213,14 +215,17 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
                         for (int q = 0; q < 8; ++q) v[q] = g.out_scale * fmaxf(v[q], 0.f);
                     }
                     const int ch = half * 4 + j;
-                    st_shared_v4(buf + lane * 128 + ((ch ^ (lane & 7)) << 4), pack_bf16x2_tc(v[0], v[1]), pack_bf16x2_tc(v[2], v[3]),
-                                 pack_bf16x2_tc(v[4], v[5]), pack_bf16x2_tc(v[6], v[7]));
+                    pk[4 * ch] = pack_bf16x2_tc(v[0], v[1]); pk[4 * ch + 1] = pack_bf16x2_tc(v[2], v[3]);
+                    pk[4 * ch + 2] = pack_bf16x2_tc(v[4], v[5]); pk[4 * ch + 3] = pack_bf16x2_tc(v[6], v[7]);
                 }
             }
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) st_shared_v4(stg + lane * 128 + ((ch ^ (lane & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { tma_store_2d(&tmOut, buf, g.out_col0 + n0 + c0, m0 + quad * 32); bulk_commit(); }
-            ++n_boxes;
+            if (lane == 0) { tma_store_2d(&tmOut, stg, g.out_col0 + n0 + c0, m0 + quad * 32); bulk_commit(); }
         }
     }
 }
@@ -342,8 +347,8 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
     } else {
         // ===== epilogue warps 2..: TMEM lane quadrant = warp % 4 =====
         const int quad = warp & 3;
-        const uint32_t stg = epi_base + (uint32_t)((warp - 2) & 3) * 2u * TC_EPI_BUF;     // two 4 KB boxes, 1024-byte aligned
-        uint32_t n_boxes = 0;                                                      // boxes issued by this warp (buffer toggle)
+        const uint32_t stg = epi_base + (uint32_t)(warp - 2) * TC_EPI_BUF;         // this warp's 4 KB staging box, 1024-byte aligned
+        const int half = (warp - 2) >> 2;                                          // which half of the tile's columns this warp drains
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
@@ -353,7 +358,6 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
             const int row = m0 + quad * 32 + lane;                                 // this thread's output row
             if constexpr (EPI == EPI_SAMPLE || EPI == EPI_LOGPROB) {
                 // warps w and w+4 share the lane quadrant; each takes one 128-column half of the tile
-                const int half = (warp - 2) >> 2;
                 const bool live = row < M;
                 const uint64_t key = (live && EPI == EPI_SAMPLE) ? g.row_key[row] : 0ull;
                 const bool masked = n0 + BN > g.n_vocab;                         // only the last N tile has padded columns
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kern
                     if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
                 if (EPI == EPI_SAMPLE && live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
             } else {
-                tc_store_tile<EPI, BN>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, n_boxes);
+                tc_store_tile<EPI, BN>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (BN / 2), (half + 1) * (BN / 2));
             }
             tcgen05_fence_before();
             __syncwarp();

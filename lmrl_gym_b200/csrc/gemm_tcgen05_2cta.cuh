@@ -19,7 +19,7 @@ constexpr int TC2_STAGES = 6;
 constexpr int TC2_B_ROWS = TC_BN / 2;                                  // W rows staged per CTA
 constexpr int TC2_STAGE_BYTES = TC_A_BYTES + TC2_B_ROWS * TC_BK * 2;   // 16 KB + 16 KB
 constexpr int TC2_SMEM_BYTES = 1024 + TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_BYTES + 256;
-constexpr int TC2_THREADS = 192;
+constexpr int TC2_THREADS = 64 + 32 * 8;                                // producer, MMA issuer, 8 epilogue warps
 // instruction descriptor of the pair: M = 256, N = 256
 constexpr uint32_t TC2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }   // 4 epilogue warps x 2 CTAs
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // 8 epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -140,17 +140,17 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
             }
         }
     } else {
-        // ===== epilogue warps 2..5 of both CTAs: my CTA's 128 rows x 256 columns =====
+        // ===== epilogue warps 2..9 of both CTAs: my CTA's 128 rows x 256 columns, two warps per lane quadrant =====
         const int quad = warp & 3;
-        const uint32_t stg = epi_base + (uint32_t)((warp - 2) & 3) * 2u * TC_EPI_BUF;
-        uint32_t n_boxes = 0;
+        const uint32_t stg = epi_base + (uint32_t)(warp - 2) * TC_EPI_BUF;
+        const int half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < total; tile += n_clusters) {
             const int m0 = (tile / n_tiles) * 2 * TC_BM + (int)rank * TC_BM, n0 = (tile % n_tiles) * TC_BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
-            tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, n_boxes);
+            tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (TC_BN / 2), (half + 1) * (TC_BN / 2));
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));

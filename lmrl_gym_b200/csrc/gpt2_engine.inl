@@ -94,7 +94,9 @@ struct Gpt2Dev {
     // for this path (4096-episode Wordle rollout: 208.2 ms with graphs and no PDL, 223.8 ms with PDL; letters variant 81.0 vs 84.2)
     int use_pdl = 0;
     int sm_count = 148;
-    int gemm_impl = 1;                // 1 = tcgen05/TMEM/TMA (default), 0 = mma.sync cross-check path
+    // 1 = tcgen05, one CTA per tile (default); 2 = CTA pairs on prefill passes (3-12 % faster per GEMM at M ~ 100 k rows in
+    // isolation, no gain over a whole rollout: 211.4 vs 207.6 ms); 0 = mma.sync cross-check
+    int gemm_impl = 1;
     std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (base pointer, box rows) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
