@@ -161,7 +161,7 @@ def main():
     from lmrl_gym_b200.gpt2 import B200GPT2Policy
     from lmrl_gym_b200.tokenizer import ByteTokenizer
     from lmrl_gym_b200.wordle import B200WordleEnv
-    from oracle.mt19937 import seed_stream   # seeds only: the reference's seed_generator(0) stream (maze/env/randomness.py:35-41)
+    from lmrl_gym_b200.randomness import seed_generator as seed_stream   # the reference's seed_generator(0) stream (maze/env/randomness.py:35-41)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

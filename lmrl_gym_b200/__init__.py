@@ -10,6 +10,7 @@ from .environment import (  # noqa: F401
     InteractionTransition, interact_environment, text_env_eval, text_history_to_str, summarize_episodes,
 )
 from .tokenizer import ByteTokenizer  # noqa: F401
+from .randomness import seed_generator  # noqa: F401
 from ._lib import LmrlError  # noqa: F401
 
 

@@ -125,3 +125,25 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.lmrl_abi_version.restype = C.c_int
     assert lib.lmrl_abi_version() == 2
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under lmrl_gym_b200/ or scripts/ may import it, and in bench.py only the CPU
+    reference legs may (cpu_baseline, --impl reference)."""
+    import ast
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "lmrl_gym_b200", "*.py")) + glob.glob(os.path.join(ROOT, "scripts", "*.py")):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), (path, mods)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
+        if uses:
+            assert fn.name in ("run_reference", "cpu_reference_numbers"), fn.name

@@ -32,3 +32,19 @@ def test_seed_generator_golden(golden_dir):
     for s, vals in gold.items():
         g = seed_stream(int(s))
         assert [next(g) for _ in range(len(vals))] == vals
+
+
+def test_product_seed_generator_equals_oracle_stream_and_goldens(golden_dir):
+    """lmrl_gym_b200.randomness.seed_generator (the product's mirror of maze/env/randomness.py:35-41) == the oracle MT19937 stream
+    == the streams recorded from the reference."""
+    import json
+    import os
+    from itertools import islice
+    from lmrl_gym_b200.randomness import seed_generator
+    from oracle.mt19937 import seed_stream
+    for seed in (0, 1, 12345, 2**40 + 7):
+        assert list(islice(seed_generator(seed), 50)) == list(islice(seed_stream(seed), 50))
+    gold = json.load(open(os.path.join(golden_dir, "seed_streams.json")))
+    items = gold.items() if isinstance(gold, dict) else [(g["seed"], g["values"]) for g in gold]
+    for seed, values in items:
+        assert list(islice(seed_generator(int(seed)), len(values))) == [int(v) for v in values]
