@@ -166,6 +166,35 @@ int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok
 int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
                     const int32_t* prefix_len, float temperature, float* logprob_sum /*[n]*/, float* token_logprobs);
 
+/* ---- teacher-forced per-position forward (SURVEY.md §8 f1 advantage scoring, f2 PPO data path) ---------------------
+ * Replaces, for one tower and one head set, ValueRLInference.forward (value_rl_base/base_interface.py:129-168: q1 / q2 / v of
+ * every position), ILQLInference.forward (ilql/base_interface.py:313-344: value_inference + target_value_inference),
+ * GPT2Inference.get_logits_from_tokens + log_softmax + take_along_axis (ilql/gpt2/score_fn.py:60-64) and PPOInference.forward
+ * + token_logprobs_from_logits (ppo/base_interface.py:404-411, 519-529) — without materialising [rows, vocab] logits or Q values.
+ *
+ * Towers: 0 = policy / pi_beta, 1 = value base (ILQL / MC) or the PPO initial policy, 2 = target value base (forward only).
+ * Head sets: 0 = online heads (q1, q2, v), 1 = target heads (q1_target, q2_target).  A head set is independent of the
+ * beta-scaled Q heads lmrl_load_q_heads installs for sampling. */
+typedef struct lmrl_value_heads {
+    const lmrl_mlp_head* q1;      /* MLPHead d -> hidden -> n_out (>= n_vocab), or NULL */
+    const lmrl_mlp_head* q2;      /* or NULL */
+    const lmrl_mlp_head* v;       /* MLPHead d -> hidden -> 1 (ILQL V head), or NULL */
+    const float* v_linear_w;      /* LinearHead kernel [d_model] (output_dim 1; the PPO value head), or NULL */
+    const float* v_linear_b;      /* [1], or NULL when use_bias = False */
+} lmrl_value_heads;
+int lmrl_load_value_heads(lmrl_engine* e, int32_t head_set, const lmrl_value_heads* h);
+
+typedef struct lmrl_forward_out {  /* HOST pointers, each [n][pitch] fp32, any may be NULL; unwritten cells are set to 0 */
+    float* token_logprobs;  /* [i][t] = log softmax(lm_logits_t / temperature)[tokens[i][t+1]]   for t in [0, n_tok[i] - 1) */
+    float* v;               /* [i][t] = V head of position t                                      for t in [0, n_tok[i]) */
+    float* q1;              /* [i][t] = Q1(h_t)[tokens[i][t+1]]                                   for t in [0, n_tok[i] - 1) */
+    float* q2;              /* [i][t] = Q2(h_t)[tokens[i][t+1]] */
+} lmrl_forward_out;
+/* Sequences start at position 0 (RIGHT padding of the reference: pad cells simply do not exist here); n_tok[i] <= max_input_length.
+ * Any n: the call walks the batch in chunks of at most max_envs sequences / the engine's row capacity. */
+int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int32_t* tokens, const int32_t* n_tok, int32_t pitch,
+                      int32_t n, float temperature, lmrl_forward_out* out);
+
 /* ---- fused rollout (interact_environment's while-loop, environment.py:176-206, with no host round trip) -------- */
 typedef struct lmrl_rollout_out {      /* all HOST pointers for _host, DEVICE pointers for _dev; any may be NULL */
     float* ep_return;       /* [n]  sum of rewards (fp32 accumulation in step order)            :238 */

@@ -41,6 +41,15 @@ class lmrl_mlp_head(C.Structure):
     _fields_ = [("w1", _PF), ("b1", _PF), ("w2", _PF), ("b2", _PF), ("hidden", C.c_int32), ("n_out", C.c_int32)]
 
 
+class lmrl_value_heads(C.Structure):
+    _fields_ = [("q1", C.POINTER(lmrl_mlp_head)), ("q2", C.POINTER(lmrl_mlp_head)), ("v", C.POINTER(lmrl_mlp_head)),
+                ("v_linear_w", _PF), ("v_linear_b", _PF)]
+
+
+class lmrl_forward_out(C.Structure):
+    _fields_ = [("token_logprobs", C.c_void_p), ("v", C.c_void_p), ("q1", C.c_void_p), ("q2", C.c_void_p)]
+
+
 class lmrl_sampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64), ("top_k", C.c_int32), ("top_p", C.c_float)]
 
@@ -83,6 +92,8 @@ SYMBOLS = {
     "lmrl_generate_host": (C.c_int, [_V, _V, _V, _I, _I, _V, _I, C.POINTER(lmrl_sampling), _V, _V]),
     "lmrl_logits_host": (C.c_int, [_V, _V, _V, _I, _I, _V]),
     "lmrl_score_host": (C.c_int, [_V, _V, _V, _I, _I, _V, C.c_float, _V, _V]),
+    "lmrl_load_value_heads": (C.c_int, [_V, _I, C.POINTER(lmrl_value_heads)]),
+    "lmrl_forward_host": (C.c_int, [_V, _I, _I, _V, _V, _I, _I, C.c_float, C.POINTER(lmrl_forward_out)]),
     "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_wordle_scripted_rollout_dev": (C.c_int, [_V, _V, _I, C.c_float, C.c_uint64, C.POINTER(lmrl_rollout_out)]),

@@ -39,14 +39,31 @@ struct QHeadsDev {
     float* b2s[2] = {nullptr, nullptr};          // [v_pad]  beta * dense2 bias
 };
 
+// value heads used by the teacher-forced per-position forward (lmrl_forward_host): up to two Q heads and one V head, each an
+// MLPHead (heads/mlp_head.py:139-148), or a LinearHead V (heads/linear_head.py:112-119: the PPO value head).  Unlike QHeadsDev
+// nothing is scaled by beta: these return the raw head outputs (ilql/gpt2/score_fn.py:45-58, ppo/base_interface.py:529).
+struct ValueHeadsDev {
+    int n_mlp = 0, hidden = 0;        // MLP heads stacked in w1cat, in the order q1, q2, v (absent ones skipped)
+    int slot_q1 = -1, slot_q2 = -1, slot_v = -1;     // index of each head inside w1cat / the ReLU buffer
+    __nv_bfloat16* w1cat = nullptr;   // [3 * hidden][d]
+    float* b1cat = nullptr;           // [3 * hidden]
+    __nv_bfloat16* w2q[2] = {nullptr, nullptr};      // [v_pad][hidden] dense2 kernels of the Q heads, transposed
+    float* b2q[2] = {nullptr, nullptr};              // [v_pad]
+    float* w2v = nullptr;             // [hidden] dense2 kernel of the V MLP head (output_dim 1)
+    float* lin_w = nullptr;           // [d] LinearHead kernel
+    float b2v = 0.f, lin_b = 0.f;
+    bool has_lin = false, allocated = false;
+};
+
 struct Gpt2Dev {
     lmrl_gpt2_dims dims{};
     int v_pad = 0;            // LM-head rows padded to a multiple of 128
     int t_cap = 0;            // KV positions per env
     int m_cap = 0;            // row capacity of the activation buffers
     int stream_cap = 0;
-    TowerDev tw[2];
+    TowerDev tw[3];                   // 0 policy / pi_beta, 1 value base (or PPO initial policy), 2 target value base (forward only; shares tower 1's KV slab)
     QHeadsDev qh;
+    ValueHeadsDev vh[2];              // head sets of lmrl_forward_host: 0 online, 1 target
     int policy_kind = 0;              // 0 = LM policy (logits of tower 0); 1 = value-perturbed (pi_beta + beta * min q)
     size_t kv_layer_stride = 0;       // elements between layers (covers K and V)
     // activations
@@ -60,6 +77,12 @@ struct Gpt2Dev {
     int s_cap = 0;
     float2* lp_partial = nullptr; float* lp_tlogit = nullptr; float* lp_out = nullptr;
     int *score_rows = nullptr, *score_targets = nullptr, *score_n = nullptr;
+    // per-position forward (lmrl_forward_host): final-LN hidden of every row, ReLU(dense1) of the value heads, per-row outputs
+    int f_cap = 0;
+    __nv_bfloat16 *fx = nullptr, *fr = nullptr;
+    int* f_targets = nullptr;
+    float2* f_lp_partial = nullptr;
+    float *f_tlogit = nullptr, *f_lp = nullptr, *f_q1 = nullptr, *f_q2 = nullptr, *f_v = nullptr;
     RowsDev rows{};
     GenDev gen{};
     StreamDev stream{};
@@ -352,6 +375,43 @@ __global__ void logprob_finalize_kernel(const float2* __restrict__ partial, int 
     }
 }
 
+// the decoder layers of one tower over the current row map: x (fp32 residual stream, already embedded) -> x
+static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) {
+    Gpt2Dev& G = *e->gpt2;
+    const lmrl_gpt2_dims& D = G.dims;
+    cudaStream_t st = e->stream;
+    const int ew_blocks = G.sm_count * 8;
+    const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
+    for (int l = 0; l < D.n_layer; ++l) {
+        const LayerDev& L = T.layers[l];
+        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+        GemmArgs a{};
+        a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
+        a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
+        a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
+        // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
+        if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
+        if (mode == 0)
+            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                          0.125f * 1.4426950408889634f, G.att));
+        else
+            LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                             0.125f, G.att));
+        GemmArgs p{};
+        p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
+        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
+        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+        GemmArgs f{};
+        f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
+        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
+        GemmArgs f2{};
+        f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
+        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
+    }
+    return 0;
+}
+
 // One forward pass over the current ragged batch + sampling of one token per contributing env.
 // mode 0 = prefill of un-cached stream tokens, mode 1 = single-token decode.
 // score != nullptr: no sampling; the LM head runs over score->rows and writes log-probabilities of score->targets instead.
@@ -373,7 +433,6 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     if (mode == 0)
         LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
-    const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     const int n_towers = G.policy_kind == 1 ? 2 : 1;
     // head operand buffers: the per-env sampling buffers, or the (larger) scoring buffers
     __nv_bfloat16* xl = score ? G.xs : G.xl;
@@ -384,33 +443,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     for (int t = 0; t < n_towers; ++t) {
         const TowerDev& T = G.tw[t];
         if (t > 0) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
-        for (int l = 0; l < D.n_layer; ++l) {
-            const LayerDev& L = T.layers[l];
-            LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
-            GemmArgs a{};
-            a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
-            a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
-            a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
-            if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
-            // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
-            if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
-            if (mode == 0)
-                LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                              0.125f * 1.4426950408889634f, G.att));
-            else
-                LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                                 0.125f, G.att));
-            GemmArgs p{};
-            p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
-            if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
-            LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
-            GemmArgs f{};
-            f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
-            if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
-            GemmArgs f2{};
-            f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-            if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
-        }
+        if (tower_layers(e, T, mode, n_env)) return -1;
         // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
         LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
                                                                   t == 0 ? xl : xl1, t == 0 ? G.xl_cols : D.d_model));
@@ -530,7 +563,7 @@ int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_w
 
 int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) {
     LMRL_CHECK(e && dims && w, "lmrl_load_gpt2: null argument");
-    LMRL_CHECK(tower == 0 || tower == 1, "lmrl_load_gpt2_tower: tower must be 0 (policy / pi_beta) or 1 (value base)");
+    LMRL_CHECK(tower >= 0 && tower <= 2, "lmrl_load_gpt2_tower: tower must be 0 (policy / pi_beta), 1 (value base / initial policy) or 2 (target value base)");
     LMRL_CHECK(tower == 0 || (e->gpt2 && e->gpt2->tw[0].loaded), "lmrl_load_gpt2_tower: load tower 0 first");
     LMRL_CHECK(e->has_tok, "lmrl_load_gpt2: load the tokenizer tables first (EOS id, header)");
     LMRL_CHECK(dims->d_model % 128 == 0 && dims->d_model <= 1024 && dims->d_model == dims->n_head * 64 && dims->d_ff % 128 == 0,
@@ -599,7 +632,9 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     cudaFree(stage);
     if (rc) return -1;
     if (first && gpt2_alloc_state(e)) return -1;
-    if (fresh && e->alloc(&G.kv, GG.kv_layer_stride * L)) return -1;
+    // tower 2 is only ever run by the self-contained per-position forward (kv_len = 0 on entry): it borrows tower 1's slab
+    if (fresh && tower == 2 && GG.tw[1].kv) G.kv = GG.tw[1].kv;
+    else if (fresh && e->alloc(&G.kv, GG.kv_layer_stride * L)) return -1;
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     LMRL_CUDA(cudaGetLastError());
     G.loaded = true;
@@ -786,6 +821,183 @@ int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok,
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     for (int j = 0; j < n_score; ++j) logprob_sum[owner[j]] += lp[j];          // fp32 sum in token order, as .sum(axis=0) of the reference
     if (token_logprobs) memcpy(token_logprobs, lp.data(), sizeof(float) * n_score);
+    return 0;
+}
+
+}  // extern "C" (reopened below)
+
+static int forward_alloc(lmrl_engine* e) {
+    Gpt2Dev& G = *e->gpt2;
+    if (G.f_cap) return 0;
+    const int B = e->cfg.max_envs, d = G.dims.d_model;
+    const int cap = (int)std::min<size_t>((size_t)G.m_cap, (size_t)(std::max(8192, 16 * B) + 127) / 128 * 128);
+    const size_t n_part = (size_t)2 * (G.v_pad / TC_BN);
+    if (e->alloc(&G.fx, (size_t)cap * d) || e->alloc(&G.fr, (size_t)cap * 3 * d) || e->alloc(&G.f_targets, cap) ||
+        e->alloc(&G.f_lp_partial, (size_t)cap * n_part) || e->alloc(&G.f_tlogit, cap) || e->alloc(&G.f_lp, cap) || e->alloc(&G.f_q1, cap) ||
+        e->alloc(&G.f_q2, cap) || e->alloc(&G.f_v, cap))
+        return -1;
+    G.f_cap = cap;
+    return 0;
+}
+
+extern "C" {
+
+int lmrl_load_value_heads(lmrl_engine* e, int32_t head_set, const lmrl_value_heads* h) {
+    LMRL_CHECK(e && e->gpt2 && e->gpt2->tw[0].loaded, "lmrl_load_value_heads: load GPT-2 parameters first");
+    LMRL_CHECK(h && (head_set == 0 || head_set == 1), "lmrl_load_value_heads: head_set must be 0 (online) or 1 (target)");
+    LMRL_CHECK(!(h->v && h->v_linear_w), "lmrl_load_value_heads: give the V head either as an MLPHead or as a LinearHead, not both");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    ValueHeadsDev& H = G.vh[head_set];
+    const int d = G.dims.d_model;
+    const lmrl_mlp_head* mlp[3] = {h->q1, h->q2, h->v};
+    for (int k = 0; k < 3; ++k) {
+        if (!mlp[k]) continue;
+        LMRL_CHECK(mlp[k]->w1 && mlp[k]->b1 && mlp[k]->w2 && mlp[k]->b2, "lmrl_load_value_heads: head %d has a null array", k);
+        LMRL_CHECK(mlp[k]->hidden == d, "lmrl_load_value_heads: hidden_dim %d must equal d_model %d", mlp[k]->hidden, d);
+        LMRL_CHECK(k == 2 ? mlp[k]->n_out == 1 : mlp[k]->n_out >= G.dims.n_vocab, "lmrl_load_value_heads: head %d has output_dim %d", k, mlp[k]->n_out);
+    }
+    LMRL_CHECK((3 * d) % TC_BN == 0 && d % TC_BN == 0, "lmrl_load_value_heads: d_model %d must be a multiple of %d", d, TC_BN);
+    if (!H.allocated) {
+        if (e->alloc(&H.w1cat, (size_t)3 * d * d) || e->alloc(&H.b1cat, (size_t)3 * d) || e->alloc(&H.w2v, d) || e->alloc(&H.lin_w, d)) return -1;
+        for (int k = 0; k < 2; ++k)
+            if (e->alloc(&H.w2q[k], (size_t)G.v_pad * d) || e->alloc(&H.b2q[k], (size_t)G.v_pad)) return -1;
+        H.allocated = true;
+    }
+    int n_out_max = 1;
+    for (int k = 0; k < 2; ++k) if (mlp[k]) n_out_max = std::max(n_out_max, mlp[k]->n_out);
+    float* stage = nullptr;
+    LMRL_CUDA(cudaMalloc(&stage, (size_t)d * std::max(n_out_max, d) * sizeof(float)));
+    H.n_mlp = 0; H.hidden = d; H.slot_q1 = H.slot_q2 = H.slot_v = -1; H.has_lin = false;
+    for (int k = 0; k < 3; ++k) {
+        const lmrl_mlp_head* q = mlp[k];
+        if (!q) continue;
+        const int slot = H.n_mlp++;
+        (k == 0 ? H.slot_q1 : k == 1 ? H.slot_q2 : H.slot_v) = slot;
+        LMRL_CUDA(cudaMemcpyAsync(stage, q->w1, (size_t)d * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        transpose_to_bf16_kernel<<<dim3((d + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, d, H.w1cat + (size_t)slot * d * d);
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+        LMRL_CUDA(cudaMemcpyAsync(H.b1cat + (size_t)slot * d, q->b1, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (k < 2) {
+            const int n_rows = std::min(q->n_out, G.v_pad);
+            LMRL_CUDA(cudaMemcpyAsync(stage, q->w2, (size_t)d * q->n_out * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            transpose_to_bf16_kernel<<<dim3((n_rows + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, q->n_out, H.w2q[k], n_rows);
+            LMRL_CUDA(cudaStreamSynchronize(e->stream));
+            LMRL_CUDA(cudaMemsetAsync(H.b2q[k], 0, (size_t)G.v_pad * sizeof(float), e->stream));
+            LMRL_CUDA(cudaMemcpyAsync(H.b2q[k], q->b2, (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        } else {
+            LMRL_CUDA(cudaMemcpyAsync(H.w2v, q->w2, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            H.b2v = q->b2[0];
+        }
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    // unused ReLU columns must not hold stale weights of an earlier, larger head set: the GEMM only covers n_mlp * d columns
+    if (h->v_linear_w) {
+        LMRL_CUDA(cudaMemcpyAsync(H.lin_w, h->v_linear_w, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        H.lin_b = h->v_linear_b ? h->v_linear_b[0] : 0.f;
+        H.has_lin = true;
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(stage);
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n,
+                      float temperature, lmrl_forward_out* out) {
+    LMRL_CHECK(e && e->has_gpt2, "lmrl_forward: no GPT-2 parameters loaded");
+    LMRL_CHECK(tokens && n_tok && out && n >= 0 && pitch > 0, "lmrl_forward: null argument");
+    LMRL_CHECK(tower >= 0 && tower <= 2 && e->gpt2->tw[tower].loaded, "lmrl_forward: tower %d is not loaded", tower);
+    LMRL_CHECK(head_set == 0 || head_set == 1, "lmrl_forward: head_set must be 0 or 1");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    const lmrl_gpt2_dims& D = G.dims;
+    const ValueHeadsDev& H = G.vh[head_set];
+    const bool want_lp = out->token_logprobs != nullptr, want_v = out->v != nullptr, want_q1 = out->q1 != nullptr, want_q2 = out->q2 != nullptr;
+    LMRL_CHECK(!want_q1 || H.slot_q1 >= 0, "lmrl_forward: q1 requested but head set %d has no Q1 head", head_set);
+    LMRL_CHECK(!want_q2 || H.slot_q2 >= 0, "lmrl_forward: q2 requested but head set %d has no Q2 head", head_set);
+    LMRL_CHECK(!want_v || H.slot_v >= 0 || H.has_lin, "lmrl_forward: v requested but head set %d has no V head", head_set);
+    if (forward_alloc(e)) return -1;
+    const int max_in = e->cfg.max_input_length;
+    for (int i = 0; i < n; ++i) {
+        LMRL_CHECK(n_tok[i] >= 0 && n_tok[i] <= max_in && n_tok[i] <= pitch, "lmrl_forward: sequence %d has %d tokens (max_input_length %d, pitch %d)", i, n_tok[i], max_in, pitch);
+        for (int t = 0; t < n_tok[i]; ++t)
+            LMRL_CHECK(tokens[(size_t)i * pitch + t] >= 0 && tokens[(size_t)i * pitch + t] < G.v_pad, "lmrl_forward: sequence %d position %d: token id %d out of range", i, t, tokens[(size_t)i * pitch + t]);
+    }
+    float* outs[4] = {out->token_logprobs, out->v, out->q1, out->q2};
+    for (float* o : outs) if (o) memset(o, 0, sizeof(float) * (size_t)n * pitch);
+    const TowerDev& T = G.tw[tower];
+    cudaStream_t st = e->stream;
+    const int ew_blocks = G.sm_count * 8;
+    const bool need_mlp = (want_q1 || want_q2 || (want_v && H.slot_v >= 0)) && H.n_mlp > 0;
+    std::vector<int32_t> targets;
+    std::vector<float> host[4];
+    for (int i0 = 0; i0 < n;) {
+        int i1 = i0, rows = 0;
+        while (i1 < n && i1 - i0 < e->cfg.max_envs && rows + n_tok[i1] <= G.f_cap) { rows += n_tok[i1]; ++i1; }
+        LMRL_CHECK(i1 > i0, "lmrl_forward: sequence %d does not fit the row capacity %d", i0, G.f_cap);
+        const int nc = i1 - i0;
+        if (rows > 0) {
+            targets.assign(rows, 0);
+            for (int i = i0, r = 0; i < i1; ++i)
+                for (int t = 0; t < n_tok[i]; ++t, ++r) targets[r] = t + 1 < n_tok[i] ? std::min(tokens[(size_t)i * pitch + t + 1], G.v_pad - 1) : 0;
+            if (load_prompts(e, tokens + (size_t)i0 * pitch, n_tok + i0, pitch, nc)) return -1;
+            LMRL_CUDA(cudaMemcpyAsync(G.f_targets, targets.data(), sizeof(int32_t) * rows, cudaMemcpyHostToDevice, st));
+            e->cur_pass_slot = -1;
+            e->cur_mode = 0;
+            LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (nc + 255) / 256, 256, 0, st, nc, G.gen));
+            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+            LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+            LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
+            if (tower_layers(e, T, 0, nc)) return -1;
+            if (want_lp || need_mlp)
+                LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, G.rows.M, (const int*)nullptr, G.fx, D.d_model));
+            if (want_lp) {
+                GemmArgs h{};
+                h.A = G.fx; h.W = T.wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.M;
+                h.inv_temp = 1.0f / (temperature > 0.f ? temperature : 1.0f); h.n_vocab = D.n_vocab;
+                h.lp_partial = G.f_lp_partial; h.lp_target = G.f_targets; h.lp_tlogit = G.f_tlogit;
+                if (launch_gemm<EPI_LOGPROB>(e, h, D.n_vocab, 0, (size_t)G.f_cap, G.v_pad, 4)) return -1;
+                LMRL_LAUNCH(2, LMRL_K(logprob_finalize_kernel, std::max(1, std::min((rows + 7) / 8, G.sm_count * 8)), 256, 0, st, G.f_lp_partial, 2 * (G.v_pad / TC_BN),
+                                      G.f_tlogit, G.rows.M, G.f_lp));
+            }
+            if (need_mlp) {
+                GemmArgs r{};
+                r.A = G.fx; r.W = H.w1cat; r.bias = H.b1cat; r.N = H.n_mlp * H.hidden; r.K = D.d_model; r.M_dev = G.rows.M; r.out = G.fr;
+                r.out_col0 = 0; r.out_scale = 1.0f;
+                GemmExtra rx;
+                rx.out_cols = (size_t)3 * D.d_model;
+                if (launch_gemm<EPI_RELU>(e, r, r.N, 0, (size_t)G.f_cap, (size_t)3 * D.d_model, 4, rx)) return -1;
+            }
+            if (want_v || want_q1 || want_q2) {
+                ValueHeadArgs a{};
+                a.fr = G.fr; a.fr_pitch = 3 * D.d_model; a.hidden = H.hidden;
+                a.slot_q1 = want_q1 ? H.slot_q1 : -1; a.slot_q2 = want_q2 ? H.slot_q2 : -1; a.slot_v = want_v ? H.slot_v : -1;
+                a.w2q1 = H.w2q[0]; a.b2q1 = H.b2q[0]; a.w2q2 = H.w2q[1]; a.b2q2 = H.b2q[1]; a.w2v = H.w2v; a.b2v = H.b2v;
+                a.targets = G.f_targets;
+                a.x = G.x; a.lnf_g = T.lnf_g; a.lnf_b = T.lnf_b; a.lin_w = H.lin_w; a.lin_b = H.lin_b; a.d = D.d_model; a.eps = D.ln_eps;
+                a.has_lin = (want_v && H.slot_v < 0 && H.has_lin) ? 1 : 0;
+                a.q1_out = G.f_q1; a.q2_out = G.f_q2; a.v_out = G.f_v;
+                LMRL_LAUNCH(2, LMRL_K(value_heads_kernel, std::max(1, std::min((rows + 7) / 8, G.sm_count * 8)), 256, 0, st, G.rows.M, a));
+            }
+            const float* dev[4] = {G.f_lp, G.f_v, G.f_q1, G.f_q2};
+            for (int k = 0; k < 4; ++k)
+                if (outs[k]) { host[k].resize(rows); LMRL_CUDA(cudaMemcpyAsync(host[k].data(), dev[k], sizeof(float) * rows, cudaMemcpyDeviceToHost, st)); }
+            LMRL_CUDA(cudaStreamSynchronize(st));
+            LMRL_CUDA(cudaGetLastError());
+            for (int i = i0, r = 0; i < i1; ++i)
+                for (int t = 0; t < n_tok[i]; ++t, ++r) {
+                    const bool has_next = t + 1 < n_tok[i];
+                    const size_t o = (size_t)i * pitch + t;
+                    if (outs[0] && has_next) outs[0][o] = host[0][r];
+                    if (outs[1]) outs[1][o] = host[1][r];
+                    if (outs[2] && has_next) outs[2][o] = host[2][r];
+                    if (outs[3] && has_next) outs[3][o] = host[3][r];
+                }
+        }
+        i0 = i1;
+    }
+    e->prof_close();
     return 0;
 }
 

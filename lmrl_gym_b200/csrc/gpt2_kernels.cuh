@@ -189,6 +189,82 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+// ---- value heads of the per-position forward (lmrl_forward_host): one warp per row ---------------------------------
+// Q heads: q_k(h_t)[a] with a = the NEXT token of the sequence — dense2 is never applied to the whole vocabulary, the warp
+// reads the one dense2 column it needs (row `a` of the transposed [v_pad][hidden] bf16 matrix, 1.5 KB) and folds it with the
+// row's relu(dense1) (bf16, written by the ReLU-epilogue GEMM).  V head: MLPHead with output_dim 1 (same fold with its single
+// dense2 column), or LinearHead on the final-LN hidden, recomputed here in fp32 from the residual stream (ppo value head).
+// HBM-bound: per row (n_heads + 1) * hidden * 2 B of operands -> 4..12 B of results.
+struct ValueHeadArgs {
+    const __nv_bfloat16* fr; int fr_pitch; int hidden;
+    int slot_q1, slot_q2, slot_v;
+    const __nv_bfloat16* w2q1; const float* b2q1;
+    const __nv_bfloat16* w2q2; const float* b2q2;
+    const float* w2v; float b2v;
+    const int* targets;
+    const float* x; const float* lnf_g; const float* lnf_b; const float* lin_w; float lin_b; int d; float eps; int has_lin;
+    float* q1_out; float* q2_out; float* v_out;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float dot_bf16_bf16(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, int n, int lane) {
+    float acc = 0.f;
+    for (int c = lane * 8; c < n; c += 256) {
+        const uint4 ua = *reinterpret_cast<const uint4*>(a + c), ub = *reinterpret_cast<const uint4*>(b + c);
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ua);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 fa = __bfloat1622float2(pa[q]), fb = __bfloat1622float2(pb[q]);
+            acc = fmaf(fa.x, fb.x, acc); acc = fmaf(fa.y, fb.y, acc);
+        }
+    }
+    return warp_sum(acc);
+}
+
+__global__ void value_heads_kernel(const int* __restrict__ n_dev, ValueHeadArgs a) {
+    pdl_enter();
+    const int n = *n_dev;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const int tgt = a.targets[r];
+        const __nv_bfloat16* rr = a.fr + (size_t)r * a.fr_pitch;
+        if (a.slot_q1 >= 0) {
+            const float q = dot_bf16_bf16(rr + a.slot_q1 * a.hidden, a.w2q1 + (size_t)tgt * a.hidden, a.hidden, lane);
+            if (lane == 0) a.q1_out[r] = q + a.b2q1[tgt];
+        }
+        if (a.slot_q2 >= 0) {
+            const float q = dot_bf16_bf16(rr + a.slot_q2 * a.hidden, a.w2q2 + (size_t)tgt * a.hidden, a.hidden, lane);
+            if (lane == 0) a.q2_out[r] = q + a.b2q2[tgt];
+        }
+        if (a.slot_v >= 0) {
+            const __nv_bfloat16* rv = rr + a.slot_v * a.hidden;
+            float acc = 0.f;
+            for (int c = lane; c < a.hidden; c += 32) acc = fmaf(__bfloat162float(rv[c]), a.w2v[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) a.v_out[r] = acc + a.b2v;
+        } else if (a.has_lin) {
+            const float* xr = a.x + (size_t)r * a.d;
+            float s = 0.f;
+            for (int c = lane; c < a.d; c += 32) s += xr[c];
+            const float mean = warp_sum(s) / a.d;
+            float q = 0.f;
+            for (int c = lane; c < a.d; c += 32) { const float t = xr[c] - mean; q = fmaf(t, t, q); }
+            const float rstd = rsqrtf(warp_sum(q) / a.d + a.eps);
+            float acc = 0.f;
+            for (int c = lane; c < a.d; c += 32) acc = fmaf((xr[c] - mean) * rstd * a.lnf_g[c] + a.lnf_b[c], a.lin_w[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) a.v_out[r] = acc + a.lin_b;
+        }
+    }
+}
+
 // ---- K3: causal attention over the slab KV cache, one WARP per (slot, head) ----------------------------------------
 // HBM-bound batched GEMV (~93 % of the decode bytes).  A warp streams the (env, head) K and V slabs
 // straight from global memory with 16-byte loads: lane = (key group g = lane/8, dim chunk s = lane%8), i.e. every

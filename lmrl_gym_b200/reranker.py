@@ -7,8 +7,10 @@ moves), every candidate is scored by the sum of the log-probabilities of its act
 (teacher-forced, one prefill-only pass: ``lmrl_score_host``), and the best (or a softmax sample) is returned.  Used by
 the Maze drivers' "move accuracy" evaluation (maze/bc/eval_bc.py:182-212).
 
-The advantage-based score functions of ILQL / MC (``ilql/gpt2/score_fn.py``, ``mc_returns/score_fn.py``: Q - V of the
-value heads) are not built; a ``B200GPT2ValuePolicy`` is scored with the log-softmax of its perturbed logits.
+``build_ilql_score_fn`` / ``build_mc_score_fn`` are the advantage-based score functions of ILQL / MC
+(``ilql/gpt2/score_fn.py:11-68``, ``mc_returns/score_fn.py:11-60``): value_weight * sum over the action tokens of
+(min(Q1, Q2)(s, a) - V(s)) [ILQL] or Q1(s, a) [MC], plus logit_weight * the summed pi_beta log-probabilities — on the
+per-position device forward (``lmrl_forward_host``, value_inference.py).
 """
 from __future__ import annotations
 
@@ -90,6 +92,67 @@ def build_bc_score_fn(policy, max_length: Optional[int] = None, bsize: Optional[
 
 
 build_ppo_score_fn = build_bc_score_fn
+
+
+def _block_right(token_histories: Sequence[Sequence[int]], max_length: int, pad_token_id: int) -> np.ndarray:
+    """``tokens[-max_length:]`` then RIGHT padding to max_length (ilql/gpt2/score_fn.py:32)."""
+    out = np.full((len(token_histories), max_length), pad_token_id, dtype=np.int32)
+    for i, t in enumerate(token_histories):
+        t = list(t)[-max_length:]
+        out[i, :len(t)] = t
+    return out
+
+
+def _advantage_score_fn(kind: str, inference, pi_beta_policy, tokenizer, max_length: int, value_weight: float,
+                        logit_weight: Optional[float], bsize: int):
+    assert (pi_beta_policy is None and logit_weight is None) or (pi_beta_policy is not None and logit_weight is not None)
+    from .value_inference import token_logprobs
+    pad = tokenizer.pad_token_id
+
+    def score_fn(text_histories: List[TextHistory], done: Optional[List] = None) -> List[float]:
+        assert all(h[-1].is_action for h in text_histories)
+        prefix_lens = [len(token_history(h[:-1], tokenizer)) for h in text_histories]
+        tokens = _block_right([token_history(h, tokenizer) for h in text_histories], max_length, pad)
+        advantages: List[float] = []
+        for i in range(0, len(text_histories), bsize):
+            batch = tokens[i:i + bsize]
+            mask = (batch != pad).astype(np.float32)
+            values = inference.forward(batch)
+            if kind == "ilql":
+                # score_fn.py:45-48: the target networks' Q when the inference has them, else the online ones; V is always online
+                tgt = getattr(values, "target_output", None)
+                out = getattr(values, "output", values)
+                qsrc = tgt if tgt is not None else out
+                qsa = np.minimum(qsrc.q1sa, qsrc.q2sa)
+                per_tok = (qsa - out.v[:, :-1]) * mask[:, 1:]
+            else:
+                per_tok = values.q1sa * mask[:, 1:]                      # mc_returns/score_fn.py:44-49
+            advs = np.empty(batch.shape[0], np.float32)
+            for x in range(batch.shape[0]):
+                # the reference indexes the (possibly LEFT-truncated) row with the UNtruncated prefix length (score_fn.py:54)
+                advs[x] = np.float32(value_weight) * per_tok[x][(prefix_lens[i + x] - 1):].sum(axis=0, dtype=np.float32)
+            if logit_weight is not None:
+                lp = token_logprobs(pi_beta_policy._lmrl_engine, 0, batch, pad) * mask[:, 1:]
+                for x in range(batch.shape[0]):
+                    advs[x] += np.float32(logit_weight) * lp[x][(prefix_lens[i + x] - 1):].sum(axis=0, dtype=np.float32)
+            advantages.extend(advs.tolist())
+        return advantages
+
+    return score_fn
+
+
+def build_ilql_score_fn(inference, pi_beta_inference, tokenizer, max_length: int, value_weight: float, logit_weight: Optional[float],
+                        bsize: int):
+    """``build_ilql_score_fn`` (ilql/gpt2/score_fn.py:11-68).  ``inference``: a ``B200ILQLInference`` (Q from the target networks,
+    V from the online one) or a bare ``B200ValueRLInference`` (the reference's AttributeError fallback, :47-48, :57-58);
+    ``pi_beta_inference``: a ``B200GPT2Policy`` on the same engine (tower 0) or None."""
+    return _advantage_score_fn("ilql", inference, pi_beta_inference, tokenizer, max_length, value_weight, logit_weight, bsize)
+
+
+def build_mc_score_fn(inference, pi_beta_inference, tokenizer, max_length: int, value_weight: float, logit_weight: Optional[float],
+                      bsize: int):
+    """``build_mc_score_fn`` (mc_returns/score_fn.py:11-60): value_weight * sum of Q1(s, a) over the action tokens."""
+    return _advantage_score_fn("mc", inference, pi_beta_inference, tokenizer, max_length, value_weight, logit_weight, bsize)
 
 
 class ReRankerPolicy(TextPolicy):

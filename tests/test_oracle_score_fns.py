@@ -1,0 +1,86 @@
+"""ILQL / MC advantage score functions: the oracle restatement AND the product's host logic (lmrl_gym_b200/reranker.py, with a
+table-driven stand-in for the device forward) against vectors produced by the reference's own build_ilql_score_fn /
+build_mc_score_fn (tests/golden/score_fns.json, written by oracle/gen_golden_algos.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import score_fns as O
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "score_fns.json")))
+V, PAD = G["vocab"], G["pad"]
+TAB = {k: np.asarray(v, np.float32).reshape((V, V) if len(v) == V * V else (V,)) for k, v in G["tables"].items()}
+
+
+def enc(text):
+    return [ord(c) % (V - 1) for c in text]
+
+
+class Tok:
+    pad_token_id = PAD
+    encode = staticmethod(enc)
+
+
+def table_q(tab, batch):
+    t = np.arange(batch.shape[1], dtype=np.float32)[None, :, None]
+    return (tab[batch] * (1.0 + 0.01 * t)).astype(np.float32)
+
+
+def table_v(batch):
+    return (TAB["v"][batch] + 0.02 * np.arange(batch.shape[1], dtype=np.float32)[None]).astype(np.float32)
+
+
+def token_histories():
+    full, pre = [], []
+    for h in G["histories"]:
+        full.append([i for t, _ in h for i in enc(t)])
+        pre.append(len([i for t, _ in h[:-1] for i in enc(t)]))
+    return full, pre
+
+
+@pytest.mark.parametrize("case", G["cases"], ids=lambda c: f"{c['kind']}-{c['max_length']}-{c['logit_weight']}")
+def test_oracle_matches_reference(case):
+    full, pre = token_histories()
+    kind = "mc" if case["kind"] == "mc" else "ilql"
+    qk = ("tq1", "tq2") if case["kind"] == "ilql_target" else ("q1", "q2")
+    got = O.score_histories(kind, full, pre, PAD, case["max_length"], case["value_weight"], case["logit_weight"], case["bsize"],
+                            q_fn=lambda b: (table_q(TAB[qk[0]], b), table_q(TAB[qk[1]], b)), v_fn=table_v, pi_fn=lambda b: table_q(TAB["pi"], b))
+    np.testing.assert_allclose(got, case["scores"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", G["cases"], ids=lambda c: f"{c['kind']}-{c['max_length']}-{c['logit_weight']}")
+def test_product_host_logic_matches_reference(case, monkeypatch):
+    """reranker.build_ilql_score_fn / build_mc_score_fn with the device forward replaced by the same toy tables."""
+    from lmrl_gym_b200 import reranker, value_inference as VI
+    from lmrl_gym_b200.environment import Text
+
+    def gathered(q1k, q2k, batch):
+        sa = lambda tab: np.take_along_axis(table_q(TAB[tab], batch)[:, :-1], batch[:, 1:][..., None], axis=2)[..., 0]  # noqa: E731
+        return VI.ValueRLGatheredOutput(q1sa=sa(q1k), q2sa=sa(q2k), v=table_v(batch))
+
+    class Bare:
+        def forward(self, batch):
+            return gathered("q1", "q2", batch)
+
+    class WithTarget:
+        def forward(self, batch):
+            return VI.ILQLGatheredOutput(output=gathered("q1", "q2", batch), target_output=gathered("tq1", "tq2", batch))
+
+    def fake_logprobs(engine, tower, batch, pad, temperature=1.0):
+        x = table_q(TAB["pi"], batch)
+        m = x.max(-1, keepdims=True)
+        lp = x - m - np.log(np.exp(x - m).sum(-1, keepdims=True))
+        return np.take_along_axis(lp[:, :-1], batch[:, 1:][..., None], axis=2)[..., 0]
+
+    monkeypatch.setattr(VI, "token_logprobs", fake_logprobs)
+
+    class Pi:
+        _lmrl_engine = None
+
+    inf = WithTarget() if case["kind"] == "ilql_target" else Bare()
+    build = reranker.build_mc_score_fn if case["kind"] == "mc" else reranker.build_ilql_score_fn
+    fn = build(inf, Pi() if case["logit_weight"] is not None else None, Tok, case["max_length"], case["value_weight"], case["logit_weight"], case["bsize"])
+    got = fn([tuple(Text(t, a) for t, a in h) for h in G["histories"]])
+    np.testing.assert_allclose(got, case["scores"], rtol=2e-5, atol=2e-5)
