@@ -195,6 +195,25 @@ typedef struct lmrl_forward_out {  /* HOST pointers, each [n][pitch] fp32, any m
 int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int32_t* tokens, const int32_t* n_tok, int32_t pitch,
                       int32_t n, float temperature, lmrl_forward_out* out);
 
+/* ---- PPO data path after the forward passes ------------------------------------------------------
+ * Replaces the host loops of PPOInference.get_ppo_data_from_token_trajectory_chain (ppo/base_interface.py:572-669): KL-shaped
+ * rewards  r - kl_weight * (logp - logp0) * is_action  (:572-584), get_action_state_next_state_idxs (:230-243), the GAE scan
+ * get_advantages_and_returns (:253-293) over ACTION tokens only, and whitening over the whole batch (:245-251, :608-615).
+ * Chains are flattened in CombinedTokenTrajectoryChain order (:303-334): chain c owns output tokens [chain_off[c], chain_off[c+1])
+ * of the [N] arrays and values[chain_off[c] + c .. chain_off[c+1] + c] (its N_c state values followed by ONE bootstrap slot =
+ * last value * (1 - done), :555-570).  Outputs are [N]; non-action tokens get 0.  kls = exp(lr) - 1 - lr at action tokens (:577-579).
+ * gamma / lam / kl_weight are python scalars in the reference ("weak" against float32 arrays): cast to float once, float32 maths. */
+int lmrl_ppo_advantages_host(lmrl_engine* e, int32_t n_chains, const int64_t* chain_off, const float* policy_logprobs,
+                             const float* initial_logprobs, const float* values /*[N + n_chains]*/, const float* rewards,
+                             const uint8_t* should_take_action, double gamma, double lam, double kl_weight, int32_t whiten,
+                             float* advantages, float* returns, float* kls);
+/* ppo_loss_fn (ppo/base_interface.py:71-142) over n = batch * (time - 1) elements; mask = should_take_action * attention_mask.
+ * out[0..12] = total_loss, policy_loss, value_loss, values_error, value clipfrac, approx_kl, policy clipfrac, ratio,
+ * padding_percentage, mean values, mean old_values, mean returns, n (mask sum). */
+int lmrl_ppo_loss_host(lmrl_engine* e, int64_t n, const float* mask, const float* logprobs, const float* values,
+                       const float* old_logprobs, const float* old_values, const float* old_advantages, const float* old_returns,
+                       double cliprange_value, double cliprange, double value_loss_coef, double* out /*[16]*/);
+
 /* ---- fused rollout (interact_environment's while-loop, environment.py:176-206, with no host round trip) -------- */
 typedef struct lmrl_rollout_out {      /* all HOST pointers for _host, DEVICE pointers for _dev; any may be NULL */
     float* ep_return;       /* [n]  sum of rewards (fp32 accumulation in step order)            :238 */

@@ -3,9 +3,11 @@
 //   env_core.h        per-env integer logic (host+device)
 //   env_kernels.cuh   Wordle / Maze kernels
 //   lmrl_api.inl      C ABI: lifecycle, tables, text-path envs
-//   gpt2_engine.inl   C ABI: GPT-2 decoder, sampler, fused rollout
+//   gpt2_engine.inl   C ABI: GPT-2 decoder, sampler, fused rollout, per-position forward
+//   ppo_kernels.inl   C ABI: PPO data path after the forward passes (KL rewards, GAE, whitening, clipped loss)
 #include <stdarg.h>
 #include <algorithm>
 #include "engine.h"
 #include "gpt2_engine.inl"
 #include "lmrl_api.inl"
+#include "ppo_kernels.inl"

@@ -50,7 +50,7 @@ def layer_norm(x, g, b, eps):
 
 
 def forward_hidden(params: Dict, tokens: Sequence[int], n_head: int, eps: float = 1e-5, weights_bf16: bool = True,
-                   emulate_bf16: bool = False) -> torch.Tensor:
+                   emulate_bf16: bool = False, _residual_only: bool = False) -> torch.Tensor:
     """Full causal forward of one sequence; returns the final-LN hidden states [T, d].
 
     weights_bf16: matrices/embeddings rounded to bf16 first (what the engine stores), biases/LN params stay fp32.
@@ -78,7 +78,14 @@ def forward_hidden(params: Dict, tokens: Sequence[int], n_head: int, eps: float 
         xn = _r(layer_norm(x, F(L["ln2_g"]), F(L["ln2_b"]), eps), emulate_bf16)
         h = _r(gelu_new(xn @ W(L["fc_w"]) + F(L["fc_b"])), emulate_bf16)
         x = x + h @ W(L["fc2_w"]) + F(L["fc2_b"])
+    if _residual_only:
+        return x
     return _r(layer_norm(x, F(params["lnf_g"]), F(params["lnf_b"]), eps), emulate_bf16)
+
+
+def _forward_residual(params: Dict, tokens: Sequence[int], n_head: int, **kw) -> torch.Tensor:
+    """The fp32 residual stream after the last block (before ln_f)."""
+    return forward_hidden(params, tokens, n_head, _residual_only=True, **kw)
 
 
 def forward_last_logits(params: Dict, tokens: Sequence[int], n_head: int, n_vocab: int, **kw) -> np.ndarray:
@@ -128,6 +135,50 @@ def value_policy_last_logits(params, tokens: Sequence[int], n_head: int, n_vocab
         r = _r(beta * torch.relu(h_v @ _t(q["dense1"]["kernel"], weights_bf16) + b1), True)
         outs.append(pi_logits + r @ _t(q["dense2"]["kernel"], weights_bf16)[:, :n_vocab] + beta * b2[:n_vocab])
     return (outs[0] if len(outs) == 1 else torch.minimum(outs[0], outs[1])).numpy()
+
+
+# ---- per-position teacher-forced forward: value heads and token log-probs (lmrl_forward_host) ------------------------
+
+def value_forward_gathered(base: Dict, q1: Optional[Dict], q2: Optional[Dict], v: Optional[Dict], tokens: Sequence[int], n_head: int,
+                           emulate_bf16: bool = False, weights_bf16: bool = True) -> Dict[str, np.ndarray]:
+    """ValueRLInference._forward (LLM_RL/algorithms/value_rl_base/gpt2/interface.py:150-230) for one sequence, reduced to what
+    every consumer gathers: q_k(h_t)[tok_{t+1}] for t < T-1 (ilql/gpt2/score_fn.py:49) and v(h_t) for every t.
+    ``emulate_bf16`` rounds relu(dense1) to bf16 like the engine's ReLU-epilogue GEMM."""
+    h = forward_hidden(base, tokens, n_head, emulate_bf16=emulate_bf16, weights_bf16=weights_bf16)
+    nxt = torch.as_tensor(list(tokens[1:]), dtype=torch.long)
+    out: Dict[str, np.ndarray] = {}
+    for name, q in (("q1", q1), ("q2", q2)):
+        if q is None:
+            continue
+        b1 = torch.from_numpy(np.ascontiguousarray(q["dense1"]["bias"], dtype=np.float32))
+        b2 = torch.from_numpy(np.ascontiguousarray(q["dense2"]["bias"], dtype=np.float32))
+        r = _r(torch.relu(h[:-1] @ _t(q["dense1"]["kernel"], weights_bf16) + b1), emulate_bf16)
+        w2 = _t(q["dense2"]["kernel"], weights_bf16)[:, nxt]                 # [hidden, T-1]: the one dense2 column each position needs
+        out[name] = ((r * w2.T).sum(-1) + b2[nxt]).numpy()
+    if v is not None:
+        b1 = torch.from_numpy(np.ascontiguousarray(v["dense1"]["bias"], dtype=np.float32))
+        r = _r(torch.relu(h @ _t(v["dense1"]["kernel"], weights_bf16) + b1), emulate_bf16)
+        w2 = torch.from_numpy(np.ascontiguousarray(v["dense2"]["kernel"], dtype=np.float32))[:, 0]
+        out["v"] = (r @ w2 + float(np.asarray(v["dense2"]["bias"]).reshape(-1)[0])).numpy()
+    return out
+
+
+def linear_value_forward(params: Dict, v_linear: Dict, tokens: Sequence[int], n_head: int, emulate_bf16: bool = False, weights_bf16: bool = True) -> np.ndarray:
+    """PPO value head: LinearHead (LLM_RL/heads/linear_head.py:112-119) on the policy's last hidden state, every position
+    (ppo/gpt2/interface.py forward: ``value_head_model.apply(..., policy_output.hidden_states[-1])``).  The engine recomputes the final
+    LayerNorm in fp32 for this head, so no rounding of its output is emulated."""
+    F = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))  # noqa: E731
+    x = _forward_residual(params, tokens, n_head, weights_bf16=weights_bf16, emulate_bf16=emulate_bf16)
+    hn = layer_norm(x, F(params["lnf_g"]), F(params["lnf_b"]), 1e-5)
+    w = F(np.asarray(v_linear["dense"]["kernel"]).reshape(-1))
+    b = float(np.asarray(v_linear["dense"].get("bias", [0.0])).reshape(-1)[0]) if v_linear["dense"].get("bias") is not None else 0.0
+    return (hn @ w + b).numpy()
+
+
+def token_logprobs_all(params: Dict, tokens: Sequence[int], n_head: int, n_vocab: int, temperature: float = 1.0, **kw) -> np.ndarray:
+    """PPOInference.token_logprobs_from_logits (ppo/base_interface.py:404-411): log softmax(logits_t)[tok_{t+1}], t < T-1; ids beyond
+    n_vocab masked to -inf (ppo/gpt2/interface.py:330)."""
+    return sequence_logprob(params, tokens, 1, n_head, n_vocab, temperature, **kw)
 
 
 # ---- the engine's sampler, restated -------------------------------------------------------------------------------

@@ -96,3 +96,29 @@ def test_top_k_top_p_restatement_matches_hf_warpers():
     assert np.isfinite(og.warp_top_k(x, 2)).tolist() == [False, True, True, False, False]
     q = np.log(np.array([0.1, 0.3, 0.3, 0.3], np.float64)).astype(np.float32)
     assert np.isfinite(og.warp_top_p(q, 0.5)).tolist() == [False, True, True, False]
+
+
+def test_value_forward_gathered_equals_full_heads():
+    """q_k(h_t)[tok_{t+1}] computed from one dense2 column == the gather of the full MLPHead output
+    (take_along_axis(qs[:, :-1], batch[:, 1:]), ilql/gpt2/score_fn.py:49); V and the linear PPO value head likewise."""
+    import torch
+    from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params, init_mlp_head_params
+    from oracle import gpt2 as og
+    cfg = GPT2Config(n_layer=2, n_head=2, d_model=64, d_ff=128, n_vocab=97, n_vocab_rows=98, n_pos=32)
+    base = init_gpt2_params(cfg, seed=4)
+    q1, q2 = init_mlp_head_params(cfg, seed=5), init_mlp_head_params(cfg, seed=6)
+    v = init_mlp_head_params(cfg, seed=7, n_out=1, layer2_bias_init=0.3)
+    toks = np.random.default_rng(0).integers(0, cfg.n_vocab, size=13).tolist()
+    got = og.value_forward_gathered(base, q1, q2, v, toks, cfg.n_head)
+    h = og.forward_hidden(base, toks, cfg.n_head)
+    for name, q in (("q1", q1), ("q2", q2)):
+        full = og.mlp_head(h, q).numpy()
+        np.testing.assert_allclose(got[name], full[np.arange(12), toks[1:]], rtol=1e-5, atol=1e-5)
+    # the engine keeps the V head's single dense2 column in fp32 (dense1 in bf16 like every GEMM operand)
+    v_mixed = dict(dense1=dict(kernel=og.bf16_round(v["dense1"]["kernel"]), bias=v["dense1"]["bias"]), dense2=v["dense2"])
+    np.testing.assert_allclose(got["v"], og.mlp_head(h, v_mixed, weights_bf16=False).numpy()[:, 0], rtol=1e-4, atol=1e-4)
+    lin = dict(dense=dict(kernel=np.random.default_rng(1).standard_normal((64, 1)).astype(np.float32), bias=np.asarray([0.25], np.float32)))
+    lv = og.linear_value_forward(base, lin, toks, cfg.n_head)
+    np.testing.assert_allclose(lv, (h @ torch.from_numpy(lin["dense"]["kernel"]))[:, 0].numpy() + 0.25, rtol=1e-4, atol=1e-5)
+    lp = og.token_logprobs_all(base, toks, cfg.n_head, cfg.n_vocab)
+    assert lp.shape == (12,) and (lp < 0).all()
