@@ -375,6 +375,16 @@ __global__ void logprob_finalize_kernel(const float2* __restrict__ partial, int 
     }
 }
 
+// profiling: copy the live row / slot / context counts of the pass just built to the pinned host array (FLOP and byte accounting)
+static void note_pass_counts(lmrl_engine* e) {
+    Gpt2Dev& G = *e->gpt2;
+    if (!(e->profile && e->n_passes < e->max_passes)) return;
+    e->cur_pass_slot = e->n_passes++;
+    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 1, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 2, G.rows.ctx_total, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+}
+
 // the decoder layers of one tower over the current row map: x (fp32 residual stream, already embedded) -> x
 static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) {
     Gpt2Dev& G = *e->gpt2;
@@ -424,12 +434,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     e->cur_pass_slot = -1;
     e->cur_mode = mode;
     LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
-    if (e->profile && e->n_passes < e->max_passes) {      // live row / slot counts of this pass, for the FLOP accounting
-        e->cur_pass_slot = e->n_passes++;
-        cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 1, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 2, G.rows.ctx_total, sizeof(int), cudaMemcpyDeviceToHost, st);
-    }
+    note_pass_counts(e);
     if (mode == 0)
         LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
     LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
@@ -947,6 +952,7 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
             e->cur_mode = 0;
             LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (nc + 255) / 256, 256, 0, st, nc, G.gen));
             LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+            note_pass_counts(e);
             LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
             LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
             if (tower_layers(e, T, 0, nc)) return -1;
