@@ -47,7 +47,9 @@ typedef struct lmrl_gpt2_dims {
     int32_t reserved;
 } lmrl_gpt2_dims;
 
-/* fp32 host weights in HF GPT-2 layout (Conv1D: [in, out]); converted to bf16 device layout at load */
+/* fp32 weights in HF GPT-2 layout (Conv1D: [in, out]); converted to bf16 device layout at load.  The arrays may live in host OR
+ * device memory (copied with cudaMemcpyDefault): a trainer that keeps fp32 master weights on the GPU hands its pointers over
+ * directly (the caller orders its own stream before the call). */
 typedef struct lmrl_gpt2_weights {
     const float* wte;            /* [n_vocab_rows, d]   (n_vocab_rows >= n_vocab; extra rows = padding ids) */
     int32_t n_vocab_rows;

@@ -597,12 +597,12 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     float* stage = nullptr;
     LMRL_CUDA(cudaMalloc(&stage, stage_elems * sizeof(float)));
     auto up = [&](const float* host, size_t n) -> int {
-        LMRL_CUDA(cudaMemcpyAsync(stage, host, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        LMRL_CUDA(cudaMemcpyAsync(stage, host, n * sizeof(float), cudaMemcpyDefault, e->stream));
         return 0;
     };
     auto vec = [&](float** dst, const float* host, size_t n) -> int {
         if (fresh && e->alloc(dst, n)) return -1;
-        LMRL_CUDA(cudaMemcpyAsync(*dst, host, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        LMRL_CUDA(cudaMemcpyAsync(*dst, host, n * sizeof(float), cudaMemcpyDefault, e->stream));
         return 0;
     };
     auto mat_t = [&](__nv_bfloat16** dst, const float* host, int K, int N) -> int {   // [K][N] fp32 -> [N][K] bf16

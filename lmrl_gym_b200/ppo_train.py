@@ -1,0 +1,236 @@
+"""PPO round = device rollout + device PPO data path + gradient step (BASELINE.json configs[4]).
+
+Mirrors the data flow of ``LLM_RL/algorithms/ppo/train.py::train_loop`` (:138-477) as driven by
+``llm_rl_scripts/wordle/ppo/train_ppo_gpt2.py`` (:297-353): every round
+
+    text_env_eval(env, policy)                        -> fused rollout on the engine (csrc/gpt2_engine.inl)
+    episodes -> TextTrajectoryChain                   -> train_ppo_gpt2.py:307-335 (one trajectory per episode, reward on actions)
+    get_ppo_data_from_text_trajectory_chain           -> device forward of policy / initial policy / value head + device GAE (ppo.py)
+    kl_controller.update(mean_kl, train_bsize)        -> :352-353
+    epochs x minibatches of PPOTrain.step             -> ** LIBRARY PATH, see below **
+    policy.set_params(new params)                     -> ppo/train.py:244, 438 (device-to-device weight hand-over)
+
+THE GRADIENT STEP IS NOT HAND-WRITTEN CUDA.  ``TorchPPOTrain.step`` restates ``GPT2PPOTrain._step`` (ppo/gpt2/interface.py:72-211:
+policy forward, LinearHead values, ``ppo_loss_fn``, AdamW(b1 0.9, b2 0.95, eps 1e-8, weight decay masked off LayerNorm and
+biases, train_ppo_gpt2.py:144-165)) with torch autograd on torch/cuBLAS kernels, and averages gradients over ranks with
+``torch.distributed.all_reduce`` (NCCL) where the reference relies on pjit data parallelism.  It exists so the PPO loop runs end to end
+on the engine; it is the baseline a hand-written backward would have to beat, and no performance claim is made for it.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import replace
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .engine import Engine
+from .environment import Text, TextTrajectory, TextTrajectoryChain, text_env_eval
+from .gpt2 import GPT2Config, _LAYER_KEYS
+from .ppo import B200PPOInference, PPOData, TokenTrajectory, _block_right
+from .value_inference import upload_value_heads
+
+import ctypes as C
+
+
+def episodes_to_chains(raw_results, tokenizer, max_length: int, gamma: float) -> List[TextTrajectoryChain]:
+    """train_ppo_gpt2.py:307-335: one TextTrajectory per episode over its final history, rewards [0, r_0, 0, r_1, ...]; histories
+    too long for ``max_length`` drop their last (action, observation) pair — its discounted reward folded into the previous action —
+    until they fit; episodes that still do not fit, or that have no full turn, are skipped."""
+    chains = []
+    for ep in raw_results:
+        if len(ep) == 0:
+            continue
+        hist = tuple(ep[-1].post_transition_history)
+        rewards = [0.0]
+        for tr in ep:
+            rewards += [float(tr.reward), 0.0]
+        traj = TextTrajectory(hist, tuple(rewards), bool(ep[-1].done))
+        n_tok = lambda t: TokenTrajectory.from_text_trajectory(t, tokenizer).tokens.shape[0]  # noqa: E731
+        while len(traj.text_history) > 3 and n_tok(traj) >= max_length:
+            r = list(traj.reward[:-2])
+            r[-2] += sum(traj.reward[-2:]) * gamma
+            traj = TextTrajectory(traj.text_history[:-2], tuple(r), False)
+        if len(traj.text_history) < 3 or n_tok(traj) >= max_length:
+            continue
+        chains.append(TextTrajectoryChain(traj, None))
+    return chains
+
+
+def block_ppo_data(datas: List[PPOData], pad_token_id: int, max_length: int) -> Dict[str, np.ndarray]:
+    """``PPOData.block`` (ppo/data.py:18-60): RIGHT pad / RIGHT truncate to max_length (ids) and max_length - 1 (per-output arrays)."""
+    return dict(
+        input_ids=_block_right([d.input_ids for d in datas], pad_token_id, max_length, np.int32),
+        should_take_action=_block_right([d.should_take_action for d in datas], False, max_length - 1, np.bool_),
+        old_logprobs=_block_right([d.old_logprobs for d in datas], 0.0, max_length - 1, np.float32),
+        old_values=_block_right([d.old_values for d in datas], 0.0, max_length - 1, np.float32),
+        old_advantages=_block_right([d.old_advantages for d in datas], 0.0, max_length - 1, np.float32),
+        old_returns=_block_right([d.old_returns for d in datas], 0.0, max_length - 1, np.float32))
+
+
+class TorchPPOTrain:
+    """fp32 master weights on the GPU as torch tensors (HF GPT-2 layout, the same dict layout as ``init_gpt2_params``) + LinearHead."""
+
+    def __init__(self, engine: Engine, policy_params: Dict, value_head_params: Dict, config: Optional[GPT2Config] = None, *, lr: float = 1e-5,
+                 weight_decay: float = 0.0, cliprange_value: float = 0.2, cliprange: float = 0.2, value_loss_coef: float = 1.0,
+                 pad_token_id: Optional[int] = None, activation_dtype: str = "bf16"):
+        import torch
+        self.torch = torch
+        self._lmrl_engine = engine                      # None: no rollout engine attached (CPU tests of the update itself)
+        self.config = config or GPT2Config.small()
+        self.device = torch.device("cuda", engine.device) if engine is not None else torch.device("cpu")
+        self.pad_token_id = int(pad_token_id if pad_token_id is not None else self.config.n_vocab)
+        self.cliprange_value, self.cliprange, self.value_loss_coef = cliprange_value, cliprange, value_loss_coef
+        self.autocast = torch.bfloat16 if activation_dtype == "bf16" else None
+        t = lambda a: torch.nn.Parameter(torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.device))  # noqa: E731
+        self.p = dict(wte=t(policy_params["wte"]), wpe=t(policy_params["wpe"]), lnf_g=t(policy_params["lnf_g"]), lnf_b=t(policy_params["lnf_b"]),
+                      layers=[{k: t(L[k]) for k in _LAYER_KEYS} for L in policy_params["layers"]])
+        self.vh_w = t(np.asarray(value_head_params["dense"]["kernel"]).reshape(-1, 1))
+        self.vh_b = t(np.asarray(value_head_params["dense"].get("bias", np.zeros(1))).reshape(1))
+        decay, no_decay = [], []
+        for name, prm in self.named_parameters():
+            (no_decay if (name.endswith("_b") or name.endswith("_g") or name == "vh_b") else decay).append(prm)
+        self.opt = torch.optim.AdamW([dict(params=decay, weight_decay=weight_decay), dict(params=no_decay, weight_decay=0.0)],
+                                     lr=lr, betas=(0.9, 0.95), eps=1e-8)
+        self.steps = 0
+
+    def named_parameters(self):
+        for k in ("wte", "wpe", "lnf_g", "lnf_b"):
+            yield k, self.p[k]
+        for i, L in enumerate(self.p["layers"]):
+            for k in _LAYER_KEYS:
+                yield f"h{i}.{k}", L[k]
+        yield "vh_w", self.vh_w
+        yield "vh_b", self.vh_b
+
+    # ---- model -------------------------------------------------------------------------------------------------------
+    def _hidden(self, ids, attn_mask):
+        torch, F = self.torch, self.torch.nn.functional
+        cfg = self.config
+        b, T = ids.shape
+        pos = torch.arange(T, device=ids.device)
+        x = self.p["wte"][ids.clamp(max=self.p["wte"].shape[0] - 1)] + self.p["wpe"][pos][None]
+        causal = torch.tril(torch.ones(T, T, dtype=torch.bool, device=ids.device))
+        mask = causal[None, None] & attn_mask[:, None, None, :]
+        for L in self.p["layers"]:
+            h = F.layer_norm(x, (cfg.d_model,), L["ln1_g"], L["ln1_b"], cfg.ln_eps)
+            qkv = h @ L["attn_w"] + L["attn_b"]
+            q, k, v = (z.view(b, T, cfg.n_head, -1).transpose(1, 2) for z in qkv.split(cfg.d_model, dim=-1))
+            a = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+            x = x + a.transpose(1, 2).reshape(b, T, cfg.d_model) @ L["proj_w"] + L["proj_b"]
+            h = F.layer_norm(x, (cfg.d_model,), L["ln2_g"], L["ln2_b"], cfg.ln_eps)
+            x = x + F.gelu(h @ L["fc_w"] + L["fc_b"], approximate="tanh") @ L["fc2_w"] + L["fc2_b"]
+        return F.layer_norm(x, (cfg.d_model,), self.p["lnf_g"], self.p["lnf_b"], cfg.ln_eps)
+
+    def loss(self, batch: Dict[str, np.ndarray]):
+        """ppo/gpt2/interface.py:106-146 + ppo_loss_fn (ppo/base_interface.py:71-142)."""
+        torch = self.torch
+        dev = self.device
+        ids = torch.as_tensor(batch["input_ids"], device=dev).long()
+        attn = ids != self.pad_token_id
+        sta = torch.as_tensor(batch["should_take_action"], device=dev)
+        old_lp, old_v, old_adv, old_ret = (torch.as_tensor(batch[k], device=dev).float() for k in ("old_logprobs", "old_values", "old_advantages", "old_returns"))
+        with torch.autocast(self.device.type, dtype=self.autocast, enabled=self.autocast is not None):
+            h = self._hidden(ids, attn)
+            logits = h @ self.p["wte"][:self.config.n_vocab].T
+        values = (h.float() @ self.vh_w + self.vh_b)[:, :-1, 0]
+        logprobs = -torch.nn.functional.cross_entropy(logits[:, :-1].float().reshape(-1, logits.shape[-1]), ids[:, 1:].clamp(max=self.config.n_vocab - 1).reshape(-1),
+                                                      reduction="none").view(ids.shape[0], -1)
+        mask = sta.float() * attn[:, 1:].float()
+        n = mask.sum()
+        v_clipped = torch.maximum(torch.minimum(values, old_v + self.cliprange_value), old_v - self.cliprange_value)
+        vf1, vf2 = (values - old_ret) ** 2, (v_clipped - old_ret) ** 2
+        vf_loss = 0.5 * (torch.maximum(vf1, vf2) * mask).sum() / n
+        log_ratio = (logprobs - old_lp) * mask
+        ratio = torch.exp(log_ratio)
+        pg1, pg2 = -old_adv * ratio, -old_adv * torch.clamp(ratio, 1.0 - self.cliprange, 1.0 + self.cliprange)
+        pg_loss = (torch.maximum(pg1, pg2) * mask).sum() / n
+        loss = pg_loss + self.value_loss_coef * vf_loss
+        logs = dict(total_loss=loss.detach(), policy_loss=pg_loss.detach(), value_loss=vf_loss.detach(),
+                    approx_kl=(((ratio - 1) - log_ratio).sum() / n).detach(), policy_clipfrac=(((pg2 > pg1).float() * mask).sum() / n).detach(),
+                    value_clipfrac=(((vf2 > vf1).float() * mask).sum() / n).detach(), ratio=((ratio * mask).sum() / n).detach())
+        return loss, logs
+
+    def step(self, batch: Dict[str, np.ndarray]) -> Tuple[float, Dict[str, float]]:
+        """One optimizer step on one minibatch (``PPOTrain.step``, ppo/base_interface.py:183-228); gradients are averaged over ranks."""
+        torch = self.torch
+        self.opt.zero_grad(set_to_none=True)
+        loss, logs = self.loss(batch)
+        loss.backward()
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            grads = [p.grad for _, p in self.named_parameters() if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            torch.distributed.all_reduce(flat)
+            flat /= torch.distributed.get_world_size()
+            o = 0
+            for g in grads:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+        self.opt.step()
+        self.steps += 1
+        return float(loss.detach()), {k: float(v) for k, v in logs.items()}
+
+    # ---- weight hand-over to the rollout engine (device to device; policy.set_params of ppo/train.py:244, 438) -------
+    def push_to_engine(self, tower: int = 0, head_set: int = 0) -> None:
+        torch = self.torch
+        cfg, L = self.config, self.config.n_layer
+        assert self._lmrl_engine is not None, "no engine attached"
+        torch.cuda.synchronize(self.device)
+        keep = []
+        fp = lambda t: C.cast(C.c_void_p(t.detach().contiguous().data_ptr()), _lib._PF)  # noqa: E731
+        w = _lib.lmrl_gpt2_weights()
+        w.wte, w.n_vocab_rows, w.wpe = fp(self.p["wte"]), int(self.p["wte"].shape[0]), fp(self.p["wpe"])
+        w.lnf_g, w.lnf_b = fp(self.p["lnf_g"]), fp(self.p["lnf_b"])
+        for key in _LAYER_KEYS:
+            ptrs = (_lib._PF * L)(*[fp(layer[key]) for layer in self.p["layers"]])
+            keep.append(ptrs)
+            setattr(w, key, C.cast(ptrs, _lib._PPF))
+        dims = _lib.lmrl_gpt2_dims(n_layer=cfg.n_layer, n_head=cfg.n_head, d_model=cfg.d_model, d_ff=cfg.d_ff, n_vocab=cfg.n_vocab, n_pos=cfg.n_pos, ln_eps=cfg.ln_eps)
+        e = self._lmrl_engine
+        check(e.lib.lmrl_load_gpt2_tower(e.handle, int(tower), C.byref(dims), C.byref(w)))
+        upload_value_heads(e, head_set, v_linear=dict(dense=dict(kernel=self.vh_w.detach().cpu().numpy(), bias=self.vh_b.detach().cpu().numpy())))
+
+    def params_numpy(self) -> Dict:
+        g = lambda t: t.detach().cpu().numpy()  # noqa: E731
+        return dict(wte=g(self.p["wte"]), wpe=g(self.p["wpe"]), lnf_g=g(self.p["lnf_g"]), lnf_b=g(self.p["lnf_b"]),
+                    layers=[{k: g(L[k]) for k in _LAYER_KEYS} for L in self.p["layers"]])
+
+
+def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
+                   epochs: int = 1, train_bsize: int = 32, max_length: int = 128, gamma: float = 1.0, lam: float = 0.95,
+                   use_advantage_whitening: bool = True, seed_generator=None, rng: Optional[np.random.Generator] = None,
+                   on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:
+    """ppo/train.py:138-477 reduced to its data flow (no checkpointing / wandb): returns one log dict per round."""
+    import time
+    import torch
+    rng = rng or np.random.default_rng(0)
+    tok = inference.tokenizer
+    history: List[Dict] = []
+    for rnd in range(n_rounds):
+        t0 = time.perf_counter()
+        raw, summary = text_env_eval(env, policy, n_rollouts=n_rollouts, bsize=rollout_bsize, seed_generator=seed_generator, verbose=False)
+        t1 = time.perf_counter()
+        chains = episodes_to_chains(raw, tok, max_length, gamma)
+        datas, kls = inference.get_ppo_data_from_text_trajectory_chain(chains, bsize=1 << 20, max_length=max_length, gamma=gamma, lam=lam,
+                                                                       kl_weight=kl_controller.value, use_advantage_whitening=use_advantage_whitening, verbose=False)
+        mean_kl = float(np.mean(kls)) if len(kls) else 0.0
+        kl_controller.update(mean_kl, train_bsize)
+        t2 = time.perf_counter()
+        losses = []
+        for _ in range(epochs):
+            order = rng.permutation(len(datas))
+            for lo in range(0, len(order) - train_bsize + 1, train_bsize):
+                batch = block_ppo_data([datas[i] for i in order[lo:lo + train_bsize]], inference.pad_token_id, max_length)
+                losses.append(trainer.step(batch)[0])
+        trainer.push_to_engine()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        log = dict(round=rnd, reward_mean=float(summary["reward"]["mean"]), env_steps=int(sum(len(ep) for ep in raw)), mean_kl=mean_kl,
+                   kl_coef=float(kl_controller.value), n_ppo_data=len(datas), updates=len(losses), loss=float(np.mean(losses)) if losses else None,
+                   rollout_s=t1 - t0, ppo_data_s=t2 - t1, update_s=t3 - t2)
+        history.append(log)
+        if on_round is not None:
+            on_round(rnd, log)
+    return history

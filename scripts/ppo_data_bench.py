@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measure the rows either side of the rollout on one B200 — not the headline bench.
 
-    python scripts/ppo_data_bench.py [--chains 4096] [--cpu-chains 8]
+    python scripts/ppo_data_bench.py [--chains 4096]
 
   ppo_data   one PPO collection pass over `--chains` Wordle-shaped token-trajectory chains (6 turns, the token shape of the letters
              variant): per-token log-probs of the policy and the initial policy + LinearHead values (two teacher-forced GPT-2-small
@@ -9,8 +9,8 @@
              Reported: tokens/s through B200PPOInference.get_ppo_data_from_token_trajectory_chain (host chains in, host records out,
              wall clock) and the device share (kernels of the two forwards, CUDA events).
   score      ILQL advantage re-ranking (build_ilql_score_fn): four Maze proposals per history, histories/s.
-  cpu        the oracle port (torch-CPU GPT-2 + oracle/ppo.py) on `--cpu-chains` chains, host threads stated.
-Prints one JSON line.
+Prints one JSON line.  The CPU port of the same pass is timed by tests/test_gpu_ppo.py::test_ppo_data_throughput_vs_cpu_port (the
+oracle is test infrastructure and is not importable from scripts/).
 """
 from __future__ import annotations
 
@@ -53,10 +53,7 @@ def wordle_chains(tok, n, rng):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chains", type=int, default=4096)
-    ap.add_argument("--cpu-chains", type=int, default=8)
-    ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    import torch
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params, init_mlp_head_params
     from lmrl_gym_b200.tokenizer import ByteTokenizer
@@ -107,26 +104,6 @@ def main():
     wall = time.perf_counter() - t0
     out["score"] = dict(histories=len(hists), proposals=len(props), wall_s=round(wall, 3), histories_per_s=round(len(hists) / wall, 1))
     eng.close()
-    if not args.no_cpu:
-        from oracle import gpt2 as og, ppo as O
-        torch.set_num_threads(os.cpu_count() or 1)
-        sub = chains[:args.cpu_chains]
-
-        def fwd(tokens):
-            a = np.zeros((tokens.shape[0], tokens.shape[1] - 1), np.float32); b = np.zeros_like(a); vv = np.zeros(tokens.shape, np.float32)
-            for i, row in enumerate(tokens):
-                n = int((row != tok.pad_token_id).sum()); s = row[:n].tolist()
-                a[i, :n - 1] = og.token_logprobs_all(ini, s, cfg.n_head, cfg.n_vocab)
-                b[i, :n - 1] = og.token_logprobs_all(pol, s, cfg.n_head, cfg.n_vocab)
-                vv[i, :n] = og.linear_value_forward(pol, lin, s, cfg.n_head)
-            return a, b, vv
-
-        oc = [[(t.tokens, t.is_action, t.reward, bool(t.done)) for t in c.to_list()] for c in sub]
-        n_sub = sum(t[0].shape[0] for c in oc for t in c)
-        t0 = time.perf_counter()
-        O.ppo_data_from_chains(oc, fwd, tok.pad_token_id, 64, 128, gamma=1.0, lam=0.95, kl_weight=0.001)
-        cw = time.perf_counter() - t0
-        out["cpu"] = dict(kind="port", cores=torch.get_num_threads(), chains=len(sub), tokens=n_sub, wall_s=round(cw, 2), tokens_per_s=round(n_sub / cw, 1))
     print(json.dumps(out))
 
 

@@ -162,3 +162,57 @@ def test_ppo_inference_end_to_end_against_oracle(eng):
     assert abs(logs["ratio"] - 1.0) < 1e-6 and abs(logs["approx_kl"]) < 1e-6 and logs["policy_clipfrac"] == 0.0 and logs["value_clipfrac"] == 0.0
     adv_mean = float(np.concatenate([d.old_advantages[d.should_take_action.astype(bool)] for d in datas]).mean())
     assert abs(logs["policy_loss"] + adv_mean) < 1e-5
+
+
+def test_ppo_data_throughput_vs_cpu_port():
+    """Measurement, not parity: the same PPO collection pass (GPT-2-small, Wordle-shaped chains) through B200PPOInference and through
+    the CPU port (torch-CPU GPT-2 oracle + oracle/ppo.py on all host threads, bounded sample).  Printed for DESIGN.md; the only
+    assertion is the sanity bound GPU >= 50x CPU port."""
+    import os
+    import time
+    import torch
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    sys_path_scripts = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ppo_data_bench", os.path.join(sys_path_scripts, "ppo_data_bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    tok = ByteTokenizer.synthetic()
+    cfg = GPT2Config.small()
+    rng = np.random.default_rng(0)
+    e = Engine(max_envs=512, max_input_length=128, max_new_tokens=6, tokenizer=tok)
+    pol, ini = init_gpt2_params(cfg, seed=0), init_gpt2_params(cfg, seed=1)
+    lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 28).astype(np.float32), bias=np.zeros(1, np.float32)))
+    B200GPT2Policy(e, pol, cfg)
+    inf = P.B200PPOInference(e, None, lin, initial_policy_params=ini, config=cfg, pad_token_id=tok.pad_token_id)
+    chains = mod.wordle_chains(tok, 512, rng)
+    kw = dict(max_length=128, gamma=1.0, lam=0.95, kl_weight=0.001, use_advantage_whitening=True)
+    inf.get_ppo_data_from_token_trajectory_chain(chains[:64], bsize=1 << 20, verbose=False, **kw)
+    n_tok = sum(t.tokens.shape[0] for c in chains for t in c.to_list())
+    t0 = time.perf_counter()
+    datas, _ = inf.get_ppo_data_from_token_trajectory_chain(chains, bsize=1 << 20, verbose=False, **kw)
+    gpu = n_tok / (time.perf_counter() - t0)
+    e.close()
+    torch.set_num_threads(os.cpu_count() or 1)
+    sub = chains[:6]
+
+    def fwd(tokens):
+        a = np.zeros((tokens.shape[0], tokens.shape[1] - 1), np.float32); b = np.zeros_like(a); vv = np.zeros(tokens.shape, np.float32)
+        for i, row in enumerate(tokens):
+            n = int((row != tok.pad_token_id).sum()); s = row[:n].tolist()
+            a[i, :n - 1] = og.token_logprobs_all(ini, s, cfg.n_head, cfg.n_vocab)
+            b[i, :n - 1] = og.token_logprobs_all(pol, s, cfg.n_head, cfg.n_vocab)
+            vv[i, :n] = og.linear_value_forward(pol, lin, s, cfg.n_head)
+        return a, b, vv
+
+    oc = [[(t.tokens, t.is_action, t.reward, bool(t.done)) for t in c.to_list()] for c in sub]
+    n_sub = sum(t[0].shape[0] for c in oc for t in c)
+    t0 = time.perf_counter()
+    o_datas, _ = O.ppo_data_from_chains(oc, fwd, tok.pad_token_id, 64, 128, gamma=1.0, lam=0.95, kl_weight=0.001)
+    cpu = n_sub / (time.perf_counter() - t0)
+    print(f"PPO data pass: B200 {gpu:.0f} tokens/s (512 chains, host in / host out) vs CPU port {cpu:.0f} tokens/s ({torch.get_num_threads()} threads, {len(sub)} chains)")
+    for d, o in zip(datas[:len(o_datas)], o_datas):
+        assert np.abs(d.old_returns - o.old_returns).max() < 0.3
+    assert gpu > 50 * cpu

@@ -1,0 +1,120 @@
+"""The PPO gradient step (lmrl_gym_b200/ppo_train.py::TorchPPOTrain — the torch-autograd LIBRARY path, see its docstring) on the CPU:
+its forward equals the oracle GPT-2, its loss equals the reference-pinned oracle ppo_loss, a step lowers the loss, and with two gloo
+ranks the all-reduced update keeps the replicas identical (the role of the NCCL gradient all-reduce in BASELINE.json configs[4])."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from lmrl_gym_b200.gpt2 import GPT2Config, init_gpt2_params
+from lmrl_gym_b200 import ppo_train as T
+from lmrl_gym_b200 import ppo as P
+from oracle import gpt2 as og, ppo as O
+
+CFG = GPT2Config(n_layer=2, n_head=2, d_model=64, d_ff=128, n_vocab=97, n_vocab_rows=98, n_pos=32)
+PAD = 97
+
+
+def make_batch(rng, b=6, t=12):
+    ids = np.full((b, t), PAD, np.int32)
+    sta = np.zeros((b, t - 1), bool)
+    for i in range(b):
+        n = int(rng.integers(4, t + 1))
+        ids[i, :n] = rng.integers(0, CFG.n_vocab, n)
+        sta[i, 1:n - 1] = rng.random(n - 2) < 0.6
+    sta[0, 1] = True
+    f = lambda: rng.standard_normal((b, t - 1)).astype(np.float32)  # noqa: E731
+    return dict(input_ids=ids, should_take_action=sta, old_logprobs=-np.abs(f()) - 3.0, old_values=f(), old_advantages=f(), old_returns=f())
+
+
+def make_trainer(seed=0, lr=1e-3):
+    params = init_gpt2_params(CFG, seed=seed)
+    lin = dict(dense=dict(kernel=(np.random.default_rng(seed + 1).standard_normal((CFG.d_model, 1)) / 8).astype(np.float32), bias=np.asarray([0.1], np.float32)))
+    return T.TorchPPOTrain(None, params, lin, CFG, lr=lr, pad_token_id=PAD, activation_dtype="f32"), params, lin
+
+
+def test_forward_and_loss_match_oracle():
+    tr, params, lin = make_trainer()
+    batch = make_batch(np.random.default_rng(0))
+    ids = torch.as_tensor(batch["input_ids"]).long()
+    h = tr._hidden(ids, ids != PAD).detach().numpy()
+    lp = np.zeros((ids.shape[0], ids.shape[1] - 1), np.float32)
+    vals = np.zeros_like(lp)
+    for i, row in enumerate(batch["input_ids"]):
+        n = int((row != PAD).sum())
+        s = row[:n].tolist()
+        ho = og.forward_hidden(params, s, CFG.n_head, weights_bf16=False).numpy()
+        np.testing.assert_allclose(h[i, :n], ho, rtol=2e-4, atol=2e-4)
+        lp[i, :n - 1] = og.token_logprobs_all(params, s, CFG.n_head, CFG.n_vocab, weights_bf16=False)
+        vals[i, :n - 1] = og.linear_value_forward(params, lin, s, CFG.n_head, weights_bf16=False)[:-1]
+    loss, logs = tr.loss(batch)
+    mask = (batch["input_ids"] != PAD)[:, 1:].astype(np.float32)
+    o_loss, o_logs = O.ppo_loss(mask, lp, vals, batch["should_take_action"], batch["old_logprobs"], batch["old_values"], batch["old_advantages"], batch["old_returns"],
+                                cliprange_value=0.2, cliprange=0.2, value_loss_coef=1.0)
+    assert abs(float(loss) - float(o_loss)) <= 2e-4 * max(1.0, abs(float(o_loss)))
+    for k in ("policy_loss", "value_loss", "approx_kl", "ratio"):
+        assert abs(float(logs[k]) - o_logs[k]) <= 5e-4 * max(1.0, abs(o_logs[k])), k
+
+
+def test_steps_lower_the_loss_and_respect_weight_decay_mask():
+    tr, _, _ = make_trainer(lr=3e-3)
+    batch = make_batch(np.random.default_rng(1))
+    first = tr.step(batch)[0]
+    for _ in range(15):
+        last = tr.step(batch)[0]
+    assert last < first
+    groups = tr.opt.param_groups
+    assert len(groups[1]["params"]) == 2 + 8 * CFG.n_layer + 1 and groups[1]["weight_decay"] == 0.0      # LN scales/biases + all biases + value bias
+
+
+def test_episodes_to_chains_and_block():
+    from lmrl_gym_b200.environment import Text, InteractionTransition
+
+    class Tok:
+        @staticmethod
+        def encode(s):
+            return [ord(c) % 90 for c in s]
+    h0 = (Text("Wordle:\n", False),)
+    ep = []
+    h = h0
+    for k, r in enumerate((-1.0, -1.0, 0.0)):
+        pa = h + (Text("c r a n e\n", True),)
+        pt = pa + (Text("b y g b b\n", False),)
+        ep.append(InteractionTransition(pre_action_history=h, post_action_history=pa, post_transition_history=pt, reward=r, done=k == 2))
+        h = pt
+    chains = T.episodes_to_chains([ep], Tok, max_length=200, gamma=0.5)
+    tt = chains[0].text_trajectory
+    assert tt.reward == (0.0, -1.0, 0.0, -1.0, 0.0, 0.0, 0.0) and tt.done and chains[0].next is None
+    short = T.episodes_to_chains([ep], Tok, max_length=60, gamma=0.5)[0].text_trajectory          # 68 tokens -> drop the last turn
+    assert len(short.text_history) == 5 and short.reward == (0.0, -1.0, 0.0, -1.0, 0.0) and not short.done
+    assert T.episodes_to_chains([ep], Tok, max_length=20, gamma=0.5) == []
+    d = P.PPOData(np.arange(5, dtype=np.int32), np.ones(4, bool), np.ones(4, np.float32), np.ones(4, np.float32), np.ones(4, np.float32), np.ones(4, np.float32))
+    blk = T.block_ppo_data([d, d._replace(input_ids=np.arange(3, dtype=np.int32), should_take_action=np.ones(2, bool))], PAD, 8)
+    assert blk["input_ids"].shape == (2, 8) and blk["old_returns"].shape == (2, 7) and blk["input_ids"][1, 3] == PAD and not blk["should_take_action"][1, 2]
+
+
+def _rank_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tr, _, _ = make_trainer(lr=1e-3)
+    for s in range(3):
+        tr.step(make_batch(np.random.default_rng(100 + 10 * s + rank)))          # different data per rank
+    flat = torch.cat([p.detach().reshape(-1) for _, p in tr.named_parameters()]).numpy()
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), flat)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_keeps_replicas_identical(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "r0.npy"), np.load(tmp_path / "r1.npy")
+    np.testing.assert_array_equal(a, b)
+    single, _, _ = make_trainer(lr=1e-3)
+    for s in range(3):
+        single.step(make_batch(np.random.default_rng(100 + 10 * s)))
+    c = torch.cat([p.detach().reshape(-1) for _, p in single.named_parameters()]).numpy()
+    assert np.abs(a - c).max() > 0          # the other rank's gradients really entered the update
