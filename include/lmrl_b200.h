@@ -197,6 +197,18 @@ typedef struct lmrl_forward_out {  /* HOST pointers, each [n][pitch] fp32, any m
 int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int32_t* tokens, const int32_t* n_tok, int32_t pitch,
                       int32_t n, float temperature, lmrl_forward_out* out);
 
+/* ---- Text-Nav (llm_rl_scripts/text_nav/env/env.py:13-72 over the TextWorld game of env/make_game.py:30-107) --------------
+ * Device-resident int32 state, 12 words per env: {room, loc[7 objects], open-container mask, score, done, moves}; encodings in
+ * csrc/textnav_core.h.  reset: start room = random.Random(seed).choice(rooms) (make_game.py:82-83) unless start_room[i] >= 0.
+ * step: `command.strip()` (env.py:38), exact match against the command strings TextWorld lists; reward = current score, done =
+ * game over (env.py:69-70).  applied[i] = command code, -1 unknown text, -2 not possible here, -3 skipped / game already over.
+ * adm [n][32] / n_adm [n]: codes of the admissible commands in TextWorld's (alphabetical) order, from which the host renders
+ * "Admissible commands: ..." (env.py:44-45).  All pointers HOST; state / applied / adm / n_adm may be NULL. */
+int lmrl_textnav_reset_host(lmrl_engine* e, const uint64_t* seeds, const int32_t* start_room, int32_t n, int32_t* state /*[n][12]*/,
+                            int32_t* adm, int32_t* n_adm);
+int lmrl_textnav_step_host(lmrl_engine* e, const uint8_t* action_bytes, const int32_t* action_len, int32_t pitch, const uint8_t* skip,
+                           int32_t n, float* reward, uint8_t* done, int32_t* applied, int32_t* state, int32_t* adm, int32_t* n_adm);
+
 /* ---- PPO data path after the forward passes ------------------------------------------------------
  * Replaces the host loops of PPOInference.get_ppo_data_from_token_trajectory_chain (ppo/base_interface.py:572-669): KL-shaped
  * rewards  r - kl_weight * (logp - logp0) * is_action  (:572-584), get_action_state_next_state_idxs (:230-243), the GAE scan

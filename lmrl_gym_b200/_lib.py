@@ -94,6 +94,8 @@ SYMBOLS = {
     "lmrl_score_host": (C.c_int, [_V, _V, _V, _I, _I, _V, C.c_float, _V, _V]),
     "lmrl_load_value_heads": (C.c_int, [_V, _I, C.POINTER(lmrl_value_heads)]),
     "lmrl_forward_host": (C.c_int, [_V, _I, _I, _V, _V, _I, _I, C.c_float, C.POINTER(lmrl_forward_out)]),
+    "lmrl_textnav_reset_host": (C.c_int, [_V, _V, _V, _I, _V, _V, _V]),
+    "lmrl_textnav_step_host": (C.c_int, [_V, _V, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V]),
     "lmrl_ppo_advantages_host": (C.c_int, [_V, _I, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _I, _V, _V, _V]),
     "lmrl_ppo_loss_host": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _V]),
     "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),

@@ -69,6 +69,9 @@ struct lmrl_engine {
 
     lmrl::Gpt2Dev* gpt2 = nullptr;
 
+    // Text-Nav (textnav_kernels.inl): [B][12] state, last applied command code, admissible command codes [B][32] + counts, start-room options
+    struct TextNavDev { int32_t *state = nullptr, *applied = nullptr, *adm = nullptr, *n_adm = nullptr, *start = nullptr; bool ready = false, reset_done = false; } textnav;
+
     // optional per-launch timing (bench.py): CUDA events around every launch, grouped by category
     // work = work_per_row * h_counts[count_slot] (+ work2_per_row * h_counts[count_slot2]): GEMM FLOPs per live row,
     // attention bytes per cached key position (+ per row)

@@ -121,3 +121,35 @@ int hc_maze_episode(const uint8_t* grid, int H, int W, int goal_y, int goal_x, i
 }
 
 }  // extern "C"
+
+// ---- Text-Nav (textnav_core.h): one episode on the host, for tests/test_textnav_host.py ---------------------------------
+#include "textnav_core.h"
+extern "C" {
+
+int hc_textnav_start_room(uint64_t seed) {
+    std::vector<uint32_t> mt(MT_N);
+    int idx;
+    mt_seed(mt.data(), &idx, seed);
+    return tn_choice_room((int)mt_randbelow(mt.data(), &idx, 8u));
+}
+
+// commands concatenated in `bytes` with lengths `lens`; per step: applied code, state (12 ints), admissible codes (32) + count.
+// states[0] / adm[0] describe the state after reset.  Returns steps taken.
+int hc_textnav_episode(int start_room, const uint8_t* bytes, const int32_t* lens, int n_cmds, int32_t* applied, int32_t* states, int32_t* adm, int32_t* n_adm) {
+    int32_t s[TN_STATE];
+    tn_reset(s, start_room);
+    memcpy(states, s, sizeof s);
+    n_adm[0] = tn_admissible(s, adm);
+    int off = 0;
+    for (int k = 0; k < n_cmds; ++k) {
+        applied[k] = tn_step(s, bytes + off, lens[k]);
+        off += lens[k];
+        memcpy(states + (size_t)(k + 1) * TN_STATE, s, sizeof s);
+        n_adm[k + 1] = tn_admissible(s, adm + (size_t)(k + 1) * TN_MAX_ADM);
+    }
+    return n_cmds;
+}
+
+int hc_textnav_cmd_string(int code, uint8_t* out) { return tn_cmd_string(code >> 8, (code >> 4) & 15, code & 15, out); }
+
+}

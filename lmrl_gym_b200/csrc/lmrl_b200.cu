@@ -4,6 +4,7 @@
 //   env_kernels.cuh   Wordle / Maze kernels
 //   lmrl_api.inl      C ABI: lifecycle, tables, text-path envs
 //   gpt2_engine.inl   C ABI: GPT-2 decoder, sampler, fused rollout, per-position forward
+//   textnav_core.h / textnav_kernels.inl   Text-Nav int32 state machine (host+device logic, kernels, C ABI)
 //   ppo_kernels.inl   C ABI: PPO data path after the forward passes (KL rewards, GAE, whitening, clipped loss)
 #include <stdarg.h>
 #include <algorithm>
@@ -11,3 +12,4 @@
 #include "gpt2_engine.inl"
 #include "lmrl_api.inl"
 #include "ppo_kernels.inl"
+#include "textnav_kernels.inl"

@@ -201,7 +201,7 @@ class TorchPPOTrain:
 def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
                    epochs: int = 1, train_bsize: int = 32, max_length: int = 128, gamma: float = 1.0, lam: float = 0.95,
                    use_advantage_whitening: bool = True, seed_generator=None, rng: Optional[np.random.Generator] = None,
-                   on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:
+                   max_steps_per_round: Optional[int] = None, on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:
     """ppo/train.py:138-477 reduced to its data flow (no checkpointing / wandb): returns one log dict per round."""
     import time
     import torch
@@ -222,6 +222,8 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTr
         for _ in range(epochs):
             order = rng.permutation(len(datas))
             for lo in range(0, len(order) - train_bsize + 1, train_bsize):
+                if max_steps_per_round is not None and len(losses) >= max_steps_per_round:
+                    break
                 batch = block_ppo_data([datas[i] for i in order[lo:lo + train_bsize]], inference.pad_token_id, max_length)
                 losses.append(trainer.step(batch)[0])
         trainer.push_to_engine()

@@ -57,32 +57,18 @@ def main():
     for _ in range(rank * B * args.rounds):          # contiguous shards of one seed stream
         next(seeds)
 
-    class Capped(T.TorchPPOTrain):
-        pass
-
-    n_updates = [0]
-    real_step = trainer.step
-
-    def capped_step(batch):
-        if n_updates[0] >= args.max_updates:
-            return (float("nan"), {})
-        n_updates[0] += 1
-        return real_step(batch)
-
-    trainer.step = capped_step
     logs = []
 
     def on_round(r, log):
-        n_updates[0] = 0
         logs.append(log)
 
     T.ppo_train_loop(env, pol, inf, trainer, P.AdaptiveKLController(0.001, 0.1, 10000), n_rounds=args.rounds, n_rollouts=B, rollout_bsize=B, epochs=1,
-                     train_bsize=args.train_bsize, max_length=256 + 6, gamma=1.0, lam=0.95, seed_generator=seeds, on_round=on_round)
+                     train_bsize=args.train_bsize, max_length=256 + 6, gamma=1.0, lam=0.95, seed_generator=seeds, max_steps_per_round=args.max_updates, on_round=on_round)
     if world > 1:
         dist.barrier()
     if rank == 0:
         last = logs[-1]
-        upd = min(last["updates"], args.max_updates)
+        upd = last["updates"]
         print(json.dumps(dict(workload="PPO round: Wordle x GPT-2-small, %d rollouts/GPU, train_bsize %d, %d optimizer steps/round (capped)" % (B, args.train_bsize, upd),
                               n_gpus=world, rounds=logs, env_steps_per_s_rollout=round(world * last["env_steps"] / last["rollout_s"], 1),
                               update_s_per_step=round(last["update_s"] / max(upd, 1), 4),
