@@ -107,7 +107,7 @@ def test_walkthrough_policy_wins_from_every_room(eng):
             elif "close fridge" in adm and "take stale food from fridge" in adm:
                 cmd = "close fridge"
             else:
-                room = next(r for r in ROOMS if f"-= {r.title()} =-" in text_history[-1].text)
+                room = next(r for item in reversed(text_history) for r in ROOMS if f"-= {r.title()} =-" in item.text)
                 if room in route:
                     cmd = route[room]
                 elif room == "living room":
