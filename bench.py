@@ -44,6 +44,18 @@ WORKLOAD_MAZE = ("double_t_maze partially observed (describe_observation_only_wa
                  "(random init, seed 0), max_new_tokens=3, max_input_length=512")
 
 
+def load_traffic():
+    """DRAM bytes per launch of the kernel families, from the committed ncu launch list of this same command
+    (profiles/r01_traffic.json, written by scripts/ncu_summarize.py traffic); None when no capture has been committed."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))["families"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -332,6 +344,9 @@ def main():
         achieved = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
         total_kernel_ms = sum(prof["ms"].values())
+        fam = load_traffic() or {}
+        gemm_traffic = fam.get("gemm_bf16_tcgen05_kernel", {}).get("dram_bytes_per_launch")
+        att_traffic = fam.get("attention_kernel", {}).get("dram_bytes_per_launch")
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms / K, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
@@ -345,12 +360,13 @@ def main():
             gpu_launches=total_launches,
             clocks=clock_info,
             roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (tcgen05.mma UMMA 128x256x16 + TMA + TMEM, all epilogues)", achieved=achieved, peak=peak,
-                          unit="TFLOP/s", frac=achieved / peak if peak else None, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=None,
+                          unit="TFLOP/s", frac=achieved / peak if peak else None, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=gemm_traffic,
+                          traffic_source="profiles/r01_traffic.json: mean dram__bytes_read.sum + dram__bytes_write.sum per launch over every GEMM launch of one ncu-profiled step" if gemm_traffic else None,
                           flops_per_step=gemm_flops / K, launches_per_step=prof["launches"]["gemm"] / K,
                           share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None,
                           # the HBM-bound batched GEMV of the path (north_star's "decode GEMV"): KV-cache attention of the decode passes
                           decode_attention_hbm=dict(kernel="attention_kernel (decode passes)", achieved=att_gbs, peak=peaks["hbm_gbs"], unit="GB/s",
-                                                    frac=att_gbs / peaks["hbm_gbs"], bytes_per_step=att["work"] / K,
+                                                    frac=att_gbs / peaks["hbm_gbs"], bytes_per_step=att["work"] / K, traffic=att_traffic,
                                                     peak_source=f"{peaks['source']} hbm_gbs",
                                                     algorithmic_bytes="every cached K and V position of the live envs once (bf16) + q / out rows")),
             kernel_ms_per_step={k: v / K for k, v in prof["ms"].items()},

@@ -3,6 +3,7 @@
 
     python scripts/ncu_summarize.py launches <launches.csv>            # per-kernel totals / shares of one launch list
     python scripts/ncu_summarize.py full <report.ncu-rep> [metric ...]  # selected raw metrics per captured launch
+    python scripts/ncu_summarize.py traffic <launches.csv> <out.json>  # per-kernel DRAM bytes per launch (dram__bytes_read/write.sum)
 """
 import csv
 import io
@@ -62,8 +63,45 @@ def full(path, metrics):
             print(f"      {m:75s} {r[idx[m]]:>18s} {units[idx[m]]}")
 
 
+def traffic(path, out_path):
+    """Launch list captured with --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum -> per kernel family the
+    mean DRAM bytes (read + write) and mean duration per launch; bench.py reads the JSON for roofline.traffic."""
+    import json
+    with open(path, newline="") as f:
+        lines = [l for l in f if l.startswith('"')]
+    by = defaultdict(lambda: dict(launches=0, read=0.0, write=0.0, ms=0.0))
+    scale_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    scale_t = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        k, m = short(r["Kernel Name"]), r.get("Metric Name")
+        v = float(r["Metric Value"].replace(",", ""))
+        if m == "gpu__time_duration.sum":
+            by[k]["ms"] += v * scale_t.get(r.get("Metric Unit", "ns"), 1e-6)
+            by[k]["launches"] += 1
+        elif m == "dram__bytes_read.sum":
+            by[k]["read"] += v * scale_b.get(r.get("Metric Unit", "byte"), 1.0)
+        elif m == "dram__bytes_write.sum":
+            by[k]["write"] += v * scale_b.get(r.get("Metric Unit", "byte"), 1.0)
+    out = {}
+    for k, d in by.items():
+        n = max(d["launches"], 1)
+        out[k] = dict(launches=d["launches"], dram_bytes_per_launch=(d["read"] + d["write"]) / n, dram_read_per_launch=d["read"] / n,
+                      dram_write_per_launch=d["write"] / n, us_per_launch=1000.0 * d["ms"] / n)
+    fam = defaultdict(lambda: dict(launches=0, bytes=0.0))
+    for k, d in out.items():
+        f = "gemm_bf16_tcgen05_kernel" if "gemm_bf16_tcgen05" in k else k
+        fam[f]["launches"] += d["launches"]
+        fam[f]["bytes"] += d["dram_bytes_per_launch"] * d["launches"]
+    summary = {f: dict(launches=d["launches"], dram_bytes_per_launch=d["bytes"] / max(d["launches"], 1)) for f, d in fam.items()}
+    json.dump(dict(source=path, kernels=out, families=summary), open(out_path, "w"), indent=1)
+    for f, d in sorted(summary.items(), key=lambda kv: -kv[1]["dram_bytes_per_launch"] * kv[1]["launches"]):
+        print(f"{f:60s} n={d['launches']:5d}  {d['dram_bytes_per_launch'] / 1e6:10.2f} MB/launch")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
     else:
         full(sys.argv[2], sys.argv[3:] or DEFAULT_METRICS)
