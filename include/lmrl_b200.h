@@ -253,6 +253,10 @@ int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, 
 /* fused rollouts of up to 8 turns are captured into a CUDA graph on the second use of a configuration and replayed afterwards
  * (default on; per-launch profiling runs eagerly) */
 int lmrl_set_use_graphs(lmrl_engine* e, int32_t enable);
+/* fused rollouts run the two halves of the batch as two concurrent lanes on two streams (HBM-bound attention of one half overlaps the
+ * tensor-bound GEMMs of the other; results are identical — every env's arithmetic is independent of the batch split).  Default OFF:
+ * measured slower on B200 (the GEMM and attention CTAs do not fit one SM together, so the lanes serialise). */
+int lmrl_set_two_lanes(lmrl_engine* e, int32_t enable);
 /* programmatic dependent launch between the kernels of a pass (default OFF — measured slower on B200 for this path): a kernel's
  * CTAs are scheduled and run their prologue behind the tail of the previous kernel, then wait for its completion before touching
  * global memory */

@@ -102,6 +102,7 @@ SYMBOLS = {
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_wordle_scripted_rollout_dev": (C.c_int, [_V, _V, _I, C.c_float, C.c_uint64, C.POINTER(lmrl_rollout_out)]),
     "lmrl_set_use_graphs": (C.c_int, [_V, _I]),
+    "lmrl_set_two_lanes": (C.c_int, [_V, _I]),
     "lmrl_set_use_pdl": (C.c_int, [_V, _I]),
     "lmrl_launch_count": (C.c_int64, [_V, _I]),
     "lmrl_set_gemm_impl": (C.c_int, [_V, _I]),

@@ -10,6 +10,7 @@
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
 #include <map>
+#include <tuple>
 
 namespace lmrl {
 
@@ -55,6 +56,22 @@ struct ValueHeadsDev {
     bool has_lin = false, allocated = false;
 };
 
+// One lane = the activation buffers, row map and sampling scratch of one forward pass in flight.  Lane 0 is the whole batch (every
+// host-facing call, profiled runs); lanes 1 and 2 are the two halves of lane 0's buffers, each with its own stream, used by the fused
+// rollout to run two half-batches concurrently: while one half is in its HBM-bound kernels (KV attention, LayerNorm) the other
+// half's tensor-bound GEMMs keep the tensor pipe busy, and the tail of every one-wave decode GEMM is filled by the other lane.
+struct Lane {
+    float* x = nullptr;
+    __nv_bfloat16 *xn = nullptr, *q = nullptr, *att = nullptr, *h = nullptr, *xl = nullptr, *xl1 = nullptr;
+    RowsDev rows{};
+    uint64_t* row_key = nullptr;
+    unsigned long long *best = nullptr, *best_scratch = nullptr;
+    cudaStream_t st = nullptr;
+    int e0 = 0;               // first env of the lane
+    size_t m_cap = 0;         // row capacity of the lane's activation buffers
+    size_t xl_rows = 0;       // rows behind xl / xl1
+};
+
 struct Gpt2Dev {
     lmrl_gpt2_dims dims{};
     int v_pad = 0;            // LM-head rows padded to a multiple of 128
@@ -84,6 +101,16 @@ struct Gpt2Dev {
     float2* f_lp_partial = nullptr;
     float *f_tlogit = nullptr, *f_lp = nullptr, *f_q1 = nullptr, *f_q2 = nullptr, *f_v = nullptr;
     RowsDev rows{};
+    Lane lane[3];
+    Lane* cur = nullptr;              // lane the next tower_layers / forward_and_sample call runs on
+    // fused rollouts may split the batch over lanes 1 and 2 (see lanes_usable).  Off by default: measured on B200 it is SLOWER
+    // (4096-episode Wordle rollout, graphs on: 215.1 ms one lane, 220.1 ms two lanes; letters variant 80.4 vs 82.6): a GEMM CTA
+    // (320 threads x 138 registers, 200 KB of shared memory) and an attention CTA (256 x 85 registers) do not fit one SM together, so
+    // the lanes' kernels serialise and each half-batch kernel is less efficient than the full-batch one.  Results are bit-identical.
+    int two_lanes = 0;
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int* lane_counts = nullptr;       // [6] M / n_slots / ctx_total of lanes 1 and 2
     GenDev gen{};
     StreamDev stream{};
     uint64_t* row_key = nullptr;
@@ -100,11 +127,11 @@ struct Gpt2Dev {
     // CUDA graph of one whole fused rollout (every launch is static: row counts live on the device).  A configuration is run
     // eagerly once (first-use attribute calls, tensor-map creation), captured on its second use and replayed afterwards.
     struct RolloutKey {
-        int env_kind, n, do_sample, policy_kind, gemm_impl, has_opt;
+        int env_kind, n, do_sample, policy_kind, gemm_impl, has_opt, two_lanes;
         float temperature; uint64_t seed; int top_k; float top_p;
         bool operator==(const RolloutKey& o) const {
             return top_k == o.top_k && top_p == o.top_p && env_kind == o.env_kind && n == o.n && do_sample == o.do_sample && policy_kind == o.policy_kind && gemm_impl == o.gemm_impl &&
-                   has_opt == o.has_opt && temperature == o.temperature && seed == o.seed;
+                   has_opt == o.has_opt && two_lanes == o.two_lanes && temperature == o.temperature && seed == o.seed;
         }
     };
     cudaGraphExec_t graph_exec = nullptr;
@@ -120,7 +147,7 @@ struct Gpt2Dev {
     // 1 = tcgen05, one CTA per tile (default); 2 = CTA pairs on prefill passes (3-12 % faster per GEMM at M ~ 100 k rows in
     // isolation, no gain over a whole rollout: 211.4 vs 207.6 ms); 0 = mma.sync cross-check
     int gemm_impl = 1;
-    std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (base pointer, box rows) -> descriptor
+    std::map<std::tuple<const void*, size_t, int>, CUtensorMap> tmaps;   // (base pointer, row bound, box rows | f32 flag) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
 
@@ -275,7 +302,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     bool use2 = false, narrow = false;
     if (tc) {
         auto get = [&](const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32) -> const CUtensorMap* {
-            auto key = std::make_pair(base, (int)box_rows | (f32 ? 1 << 16 : 0));
+            auto key = std::make_tuple(base, rows, (int)box_rows | (f32 ? 1 << 16 : 0));
             auto it = G.tmaps.find(key);
             if (it == G.tmaps.end()) {
                 CUtensorMap m;
@@ -305,7 +332,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     int rc;
     if constexpr (EPI != EPI_SAMPLE && EPI != EPI_LOGPROB) {
         if (use2) {
-            rc = launch_gemm_tc2<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *to, g);
+            rc = launch_gemm_tc2<EPI>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *to, g);
             e->prof_end();
             e->launches++;
             return rc;
@@ -313,14 +340,14 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     }
     if constexpr (EPI == EPI_RESID) {
         if (narrow) {
-            rc = launch_gemm_tc<EPI_RESID, 192>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g);
+            rc = launch_gemm_tc<EPI_RESID, 192>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g);
             e->prof_end();
             e->launches++;
             return rc;
         }
     }
-    if constexpr (EPI == EPI_RELU || EPI == EPI_LOGPROB) rc = launch_gemm_tc<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
-    else rc = tc ? launch_gemm_tc<EPI>(e->stream, G.use_pdl, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(e->stream, G.use_pdl, G.sm_count, g);
+    if constexpr (EPI == EPI_RELU || EPI == EPI_LOGPROB) rc = launch_gemm_tc<EPI>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g);
+    else rc = tc ? launch_gemm_tc<EPI>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw1, *tw2, *to, g) : launch_gemm_mma<EPI>(G.cur->st, G.use_pdl, G.sm_count, g);
     e->prof_end();
     e->launches++;
     return rc;
@@ -380,44 +407,46 @@ static void note_pass_counts(lmrl_engine* e) {
     Gpt2Dev& G = *e->gpt2;
     if (!(e->profile && e->n_passes < e->max_passes)) return;
     e->cur_pass_slot = e->n_passes++;
-    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot, G.rows.M, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 1, G.rows.n_slots, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 2, G.rows.ctx_total, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    const RowsDev& R = G.cur->rows;
+    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot, R.M, sizeof(int), cudaMemcpyDeviceToHost, G.cur->st);
+    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 1, R.n_slots, sizeof(int), cudaMemcpyDeviceToHost, G.cur->st);
+    cudaMemcpyAsync(e->h_counts + 3 * e->cur_pass_slot + 2, R.ctx_total, sizeof(int), cudaMemcpyDeviceToHost, G.cur->st);
 }
 
 // the decoder layers of one tower over the current row map: x (fp32 residual stream, already embedded) -> x
 static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) {
     Gpt2Dev& G = *e->gpt2;
+    Lane& Ln = *G.cur;
     const lmrl_gpt2_dims& D = G.dims;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = Ln.st;
     const int ew_blocks = G.sm_count * 8;
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
     for (int l = 0; l < D.n_layer; ++l) {
         const LayerDev& L = T.layers[l];
-        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
         GemmArgs a{};
-        a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
-        a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
-        a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
-        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, G.m_cap, a.N, 0)) return -1;
+        a.A = Ln.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = Ln.rows.M;
+        a.out = Ln.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
+        a.row_env = Ln.rows.row_env; a.row_pos = Ln.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+        if (launch_gemm<EPI_QKV>(e, a, a.N, 0, Ln.m_cap, a.N, 0)) return -1;
         // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
         if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
         if (mode == 0)
-            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                          0.125f * 1.4426950408889634f, G.att));
+            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                          0.125f * 1.4426950408889634f, Ln.att));
         else
-            LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                             0.125f, G.att));
+            LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                             0.125f, Ln.att));
         GemmArgs p{};
-        p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
-        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model));
+        p.A = Ln.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = Ln.rows.M; p.resid = Ln.x;
+        if (launch_gemm<EPI_RESID>(e, p, p.N, 0, Ln.m_cap, p.N, 1)) return -1;
+        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
         GemmArgs f{};
-        f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
-        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, G.m_cap, f.N, 2)) return -1;
+        f.A = Ln.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = Ln.rows.M; f.out = Ln.h;
+        if (launch_gemm<EPI_GELU>(e, f, f.N, 0, Ln.m_cap, f.N, 2)) return -1;
         GemmArgs f2{};
-        f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
+        f2.A = Ln.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = Ln.rows.M; f2.resid = Ln.x;
+        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, Ln.m_cap, f2.N, 3)) return -1;
     }
     return 0;
 }
@@ -428,29 +457,30 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
 static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t* done, const int32_t* turn_of_env, int turn_const,
                               const lmrl_sampling& s, float* logits_out, const ScoreReq* score = nullptr) {
     Gpt2Dev& G = *e->gpt2;
+    Lane& Ln = *G.cur;
     const lmrl_gpt2_dims& D = G.dims;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = Ln.st;
     const int ew_blocks = G.sm_count * 8;
     e->cur_pass_slot = -1;
     e->cur_mode = mode;
-    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, Ln.e0, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows));
     note_pass_counts(e);
     if (mode == 0)
-        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
-    LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x));
+        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows));
+    LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, Ln.rows, Ln.x));
     const int n_towers = G.policy_kind == 1 ? 2 : 1;
     // head operand buffers: the per-env sampling buffers, or the (larger) scoring buffers
-    __nv_bfloat16* xl = score ? G.xs : G.xl;
-    __nv_bfloat16* xl1 = score ? G.xs1 : G.xl1;
-    const size_t xl_rows = score ? (size_t)G.s_cap : (size_t)(e->cfg.max_envs + 127) / 128 * 128;
-    const int* head_n = score ? score->n_dev : G.rows.n_slots;
-    const int* head_gather = score ? score->rows : G.rows.slot_last;
+    __nv_bfloat16* xl = score ? G.xs : Ln.xl;
+    __nv_bfloat16* xl1 = score ? G.xs1 : Ln.xl1;
+    const size_t xl_rows = score ? (size_t)G.s_cap : Ln.xl_rows;
+    const int* head_n = score ? score->n_dev : Ln.rows.n_slots;
+    const int* head_gather = score ? score->rows : Ln.rows.slot_last;
     for (int t = 0; t < n_towers; ++t) {
         const TowerDev& T = G.tw[t];
-        if (t > 0) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
+        if (t > 0) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, Ln.rows, Ln.x));
         if (tower_layers(e, T, mode, n_env)) return -1;
         // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
-        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
+        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
                                                                   t == 0 ? xl : xl1, t == 0 ? G.xl_cols : D.d_model));
     }
     // top-k / top-p: the LM head dumps fp32 logits and a per-row filter kernel samples from the survivors (slow path)
@@ -465,10 +495,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         logits_out = G.logits;
     }
     if (!score)
-        LMRL_LAUNCH(2, LMRL_K(prepare_sample_kernel, (n_env + 255) / 256, 256, 0, st, G.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, G.row_key, G.best));
+        LMRL_LAUNCH(2, LMRL_K(prepare_sample_kernel, (n_env + 255) / 256, 256, 0, st, Ln.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, Ln.row_key, Ln.best));
     GemmArgs h{};
     h.A = xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = head_n;
-    h.best = filtered ? G.best_scratch : G.best; h.row_key = G.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f);
+    h.best = filtered ? Ln.best_scratch : Ln.best; h.row_key = Ln.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f);
     h.do_sample = s.do_sample;
     h.n_vocab = D.n_vocab; h.logits_out = logits_out;
     GemmExtra hx;
@@ -507,10 +537,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
                 LMRL_CUDA(cudaFuncSetAttribute(filtered_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem));
                 configured = true;
             }
-            LMRL_LAUNCH(2, LMRL_K(filtered_sample_kernel, n_env, FS_THREADS, fs_smem, st, logits_out, D.n_vocab, G.rows, G.row_key, h.inv_temp, s.do_sample,
-                                                                                    s.top_k, s.top_p, G.best));
+            LMRL_LAUNCH(2, LMRL_K(filtered_sample_kernel, n_env, FS_THREADS, fs_smem, st, logits_out, D.n_vocab, Ln.rows, Ln.row_key, h.inv_temp, s.do_sample,
+                                                                                    s.top_k, s.top_p, Ln.best));
         }
-        LMRL_LAUNCH(2, LMRL_K(finalize_sample_kernel, (n_env + 255) / 256, 256, 0, st, G.rows, G.gen, G.best));
+        LMRL_LAUNCH(2, LMRL_K(finalize_sample_kernel, (n_env + 255) / 256, 256, 0, st, Ln.rows, G.gen, Ln.best));
     }
     e->cur_pass_slot = -1;
     LMRL_CUDA(cudaGetLastError());
@@ -547,7 +577,36 @@ static int gpt2_alloc_state(lmrl_engine* e) {
         e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
         return -1;
     LMRL_CUDA(cudaFuncSetAttribute(attention_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTP_WARPS * ATTP_WARP_SMEM));
+    // lanes: 0 = the whole batch; 1 / 2 = the two halves of the same buffers (usable when both halves stay tile-aligned)
+    Lane& L0 = G.lane[0];
+    L0.x = G.x; L0.xn = G.xn; L0.q = G.q; L0.att = G.att; L0.h = G.h; L0.xl = G.xl; L0.xl1 = G.xl1; L0.rows = G.rows; L0.row_key = G.row_key;
+    L0.best = G.best; L0.best_scratch = G.best_scratch; L0.st = e->stream; L0.e0 = 0; L0.m_cap = (size_t)G.m_cap; L0.xl_rows = (size_t)(B + 127) / 128 * 128;
+    G.cur = &G.lane[0];
+    if (e->alloc(&G.lane_counts, 6)) return -1;
+    LMRL_CUDA(cudaStreamCreateWithFlags(&G.stream_b, cudaStreamNonBlocking));
+    LMRL_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
+    LMRL_CUDA(cudaEventCreateWithFlags(&G.ev_join, cudaEventDisableTiming));
+    const size_t half_rows = (size_t)(B / 2) * max_in, hb = (size_t)(B / 2);
+    for (int k = 1; k <= 2; ++k) {
+        Lane& L = G.lane[k];
+        const size_t ro = k == 2 ? half_rows : 0, so = k == 2 ? hb : 0;      // row / slot offset of the half
+        L.x = G.x + ro * D.d_model; L.xn = G.xn + ro * D.d_model; L.q = G.q + ro * D.d_model; L.att = G.att + ro * D.d_model; L.h = G.h + ro * D.d_ff;
+        L.xl = G.xl + so * G.xl_cols; L.xl1 = G.xl1 + so * D.d_model;
+        L.rows = G.rows;
+        L.rows.M = G.lane_counts + 3 * (k - 1); L.rows.n_slots = L.rows.M + 1; L.rows.ctx_total = L.rows.M + 2;
+        L.rows.row_env += ro; L.rows.row_pos += ro; L.rows.row_tok += ro;
+        L.rows.slot_env += so; L.rows.slot_row0 += so; L.rows.slot_nrow += so; L.rows.slot_last += so;
+        L.row_key = G.row_key + so; L.best = G.best + so; L.best_scratch = G.best_scratch + so;
+        L.st = k == 2 ? G.stream_b : e->stream;
+        L.m_cap = half_rows; L.xl_rows = hb;
+    }
     return 0;
+}
+
+// two half-batch lanes need tile-aligned halves: B/2 slots a multiple of 128 (xl rows) and (B/2) * max_input rows a multiple of 128
+static bool lanes_usable(const lmrl_engine* e) {
+    const int B = e->cfg.max_envs;
+    return B % 256 == 0 && ((size_t)(B / 2) * e->cfg.max_input_length) % 128 == 0;
 }
 
 }  // namespace lmrl
@@ -557,6 +616,9 @@ using namespace lmrl;
 void lmrl_gpt2_free(lmrl_engine* e) {
     if (!e || !e->gpt2) return;
     if (e->gpt2->graph_exec) cudaGraphExecDestroy(e->gpt2->graph_exec);
+    if (e->gpt2->stream_b) cudaStreamDestroy(e->gpt2->stream_b);
+    if (e->gpt2->ev_fork) cudaEventDestroy(e->gpt2->ev_fork);
+    if (e->gpt2->ev_join) cudaEventDestroy(e->gpt2->ev_join);
     for (void* p : e->gpt2->owned) cudaFree(p);
     delete e->gpt2;
     e->gpt2 = nullptr;
@@ -951,7 +1013,7 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
             e->cur_pass_slot = -1;
             e->cur_mode = 0;
             LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (nc + 255) / 256, 256, 0, st, nc, G.gen));
-            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
             note_pass_counts(e);
             LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
             LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
@@ -1035,10 +1097,32 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
     }
     ActionSrc src{};
     src.tokens = G.gen.tok; src.ntokens = G.gen.len; src.tpitch = G.gen.max_new;
+    // two half-batch lanes on two streams (see struct Lane); not under the per-launch profiler (its events live on one stream) and not
+    // with top-k / top-p (one shared logits dump)
+    const bool filtered = s.top_k > 0 || (s.top_p > 0.f && s.top_p < 1.f);
+    const bool split = G.two_lanes && lanes_usable(e) && !e->profile && !filtered && n >= 256;
+    const int n1 = std::min(e->cfg.max_envs / 2, (n + 1) / 2);
+    G.lane[1].e0 = 0; G.lane[2].e0 = n1;
+    struct RestoreLane { Gpt2Dev& g; ~RestoreLane() { g.cur = &g.lane[0]; } } restore_lane{G};
     for (int turn = 0; turn < T; ++turn) {
         LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen));
-        for (int k = 0; k < e->cfg.max_new_tokens; ++k)
-            if (forward_and_sample(e, k == 0 ? 0 : 1, n, done, G.ep_length, 0, s, nullptr)) return -1;
+        if (!split) {
+            for (int k = 0; k < e->cfg.max_new_tokens; ++k)
+                if (forward_and_sample(e, k == 0 ? 0 : 1, n, done, G.ep_length, 0, s, nullptr)) return -1;
+        } else {
+            // fork: lane 2 (second half of the envs) runs on its own stream next to lane 1; join before the env step
+            LMRL_CUDA(cudaEventRecord(G.ev_fork, st));
+            LMRL_CUDA(cudaStreamWaitEvent(G.stream_b, G.ev_fork, 0));
+            for (int k = 0; k < e->cfg.max_new_tokens; ++k) {
+                G.cur = &G.lane[1];
+                if (forward_and_sample(e, k == 0 ? 0 : 1, n1, done, G.ep_length, 0, s, nullptr)) return -1;
+                G.cur = &G.lane[2];
+                if (forward_and_sample(e, k == 0 ? 0 : 1, n - n1, done, G.ep_length, 0, s, nullptr)) return -1;
+            }
+            G.cur = &G.lane[0];
+            LMRL_CUDA(cudaEventRecord(G.ev_join, G.stream_b));
+            LMRL_CUDA(cudaStreamWaitEvent(st, G.ev_join, 0));
+        }
         if (wordle)
             LMRL_LAUNCH(3, LMRL_K(wordle_step_kernel, blocks, ENV_WARPS_PER_BLOCK * 32, ENV_WARPS_PER_BLOCK * sizeof(WordleScratch), st, 
                                e->wordle, e->tok, src, nullptr, e->step, G.stream, n));
@@ -1085,7 +1169,7 @@ static int rollout_run(lmrl_engine* e, int32_t env_kind, bool has_opt, int32_t n
     const int32_t* opt = has_opt ? e->d_opt_pos : nullptr;
     const bool graphable = G.use_graphs && !e->profile && e->cfg.max_turns <= 8;     // longer rollouts poll the device for early exit
     if (!graphable) return rollout_enqueue(e, env_kind, e->d_seeds, opt, n, s);
-    const Gpt2Dev::RolloutKey key{env_kind, n, s.do_sample, G.policy_kind, G.gemm_impl, has_opt ? 1 : 0, s.temperature, s.seed, s.top_k, s.top_p};
+    const Gpt2Dev::RolloutKey key{env_kind, n, s.do_sample, G.policy_kind, G.gemm_impl, has_opt ? 1 : 0, G.two_lanes, s.temperature, s.seed, s.top_k, s.top_p};
     if (G.graph_exec && G.graph_key == key) {
         LMRL_CUDA(cudaGraphLaunch(G.graph_exec, e->stream));
         e->launches += G.graph_launches;
@@ -1121,6 +1205,12 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable) {
     e->gpt2->use_pdl = enable ? 1 : 0;
     if (e->gpt2->graph_exec) { cudaGraphExecDestroy(e->gpt2->graph_exec); e->gpt2->graph_exec = nullptr; }
     e->gpt2->warm_valid = false;
+    return 0;
+}
+
+int lmrl_set_two_lanes(lmrl_engine* e, int32_t enable) {
+    LMRL_CHECK(e && e->gpt2, "lmrl_set_two_lanes: no GPT-2 parameters loaded");
+    e->gpt2->two_lanes = enable ? 1 : 0;
     return 0;
 }
 

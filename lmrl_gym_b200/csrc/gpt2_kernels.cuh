@@ -40,7 +40,8 @@ struct GenDev {
 // ---- row builder: exclusive scan over envs (single CTA; B <= 16384) ---------------------------------------------
 // mode 0 (prefill): env e contributes stream tokens [kv_len[e], len[e]) if it is not done
 // mode 1 (decode) : env e contributes its last sampled token at position cur[e] if it is still generating
-__global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ done, const int32_t* __restrict__ stream_tok,
+// e0 / B: the env range of the calling lane (the whole batch: 0 / n)
+__global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __restrict__ done, const int32_t* __restrict__ stream_tok,
                                   const int32_t* __restrict__ stream_len, const int32_t* __restrict__ kv_len, int stream_cap,
                                   GenDev gen, RowsDev rows) {
     pdl_enter();
@@ -50,10 +51,10 @@ __global__ void build_rows_kernel(int mode, int B, const uint8_t* __restrict__ d
     if (tid == 0) { carry[0] = 0; carry[1] = 0; *rows.ctx_total = 0; }
     __syncthreads();
     int ctx = 0;
-    for (int base = 0; base < B; base += blockDim.x) {
-        const int e = base + tid;
+    for (int base = 0; base < B; base += blockDim.x) {          // envs [e0, e0 + B): the lane's share of the batch
+        const int e = e0 + base + tid;
         int n = 0;
-        if (e < B) {
+        if (base + tid < B) {
             if (mode == 0) { n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0); if (n > 0) ctx += stream_len[e]; }
             else { n = gen.active[e] ? 1 : 0; if (n > 0) ctx += gen.cur[e] + 1; }
         }

@@ -88,6 +88,10 @@ class Engine:
         """CUDA-graph replay of fused rollouts (default on)."""
         check(self.lib.lmrl_set_use_graphs(self.handle, 1 if enable else 0))
 
+    def set_two_lanes(self, enable: bool):
+        """Two concurrent half-batch lanes inside fused rollouts (default off: measured slower on B200, results identical)."""
+        check(self.lib.lmrl_set_two_lanes(self.handle, 1 if enable else 0))
+
     def set_use_pdl(self, enable: bool):
         """Programmatic dependent launch between the kernels of a pass (default off: measured slower on B200)."""
         check(self.lib.lmrl_set_use_pdl(self.handle, 1 if enable else 0))

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A/B timing of the fused Wordle rollout (4096 episodes, GPT-2-small): CUDA graphs x programmatic dependent launch.
+"""A/B timing of the fused Wordle rollout (4096 episodes, GPT-2-small): CUDA graphs x two half-batch lanes (x programmatic dependent launch).
 
     python scripts/rollout_timing.py [--batch 4096] [--reps 4] [--letters]
 """
@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=4)
     ap.add_argument("--letters", action="store_true")
+    ap.add_argument("--pdl", action="store_true")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -35,10 +36,11 @@ def main():
     s = pol.sampling()
     seeds = torch.from_numpy(np.random.default_rng(0).integers(0, 2**63, size=B, dtype=np.int64)).cuda()
     stream = torch.cuda.ExternalStream(eng.stream_ptr, device=torch.device("cuda", 0))
-    for graphs in (0, 1):
-        for pdl in (0, 1):
+    for graphs, pdl, lanes in ((0, 0, 0), (0, 0, 1), (1, 0, 0), (1, 0, 1)) + (((1, 1, 1),) if args.pdl else ()):
+        if True:
             eng.set_use_graphs(bool(graphs))
             eng.set_use_pdl(bool(pdl))
+            eng.set_two_lanes(bool(lanes))
             for _ in range(3):
                 eng.rollout_dev(ENV_WORDLE, seeds.data_ptr(), B, s, None)
             eng.sync()
@@ -48,7 +50,7 @@ def main():
                 eng.rollout_dev(ENV_WORDLE, seeds.data_ptr(), B, s, None)
             e1.record(stream)
             eng.sync()
-            print(json.dumps(dict(graphs=graphs, pdl=pdl, ms_per_rollout=e0.elapsed_time(e1) / args.reps)), flush=True)
+            print(json.dumps(dict(graphs=graphs, pdl=pdl, two_lanes=lanes, ms_per_rollout=e0.elapsed_time(e1) / args.reps)), flush=True)
     eng.close()
 
 

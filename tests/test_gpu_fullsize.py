@@ -1,7 +1,8 @@
 """Full-size properties (BASELINE.json configs[1]: 4096 concurrent Wordle episodes, GPT-2-small shapes) that do not need the
 oracle to run 4096 episodes:
 
-  * determinism: the same seeds give bit-identical logs, eagerly launched and replayed from the CUDA graph;
+  * determinism: the same seeds give bit-identical logs, eagerly launched and replayed from the CUDA graph, as one lane or as two
+    concurrent half-batch lanes on two streams, at the full batch and at a ragged one;
   * batch-layout independence: sampling noise is keyed by (seed, turn, token) and no kernel mixes rows, so permuting the
     seeds permutes the per-episode logs exactly — the property that makes multi-GPU sharding result-invariant;
   * a random sample of the 4096 episodes replays bit-exactly through the CPU oracle env (texts, rewards, done, return);
@@ -26,6 +27,13 @@ def _logs_equal(a, b, perm=None):
     return None
 
 
+def _logs_equal_prefix(a, b, n):
+    for name in ("ep_return", "ep_length", "ep_done", "step_reward", "step_valid", "step_feedback", "step_aux", "act_tokens", "act_len"):
+        if not np.array_equal(getattr(a, name)[:n], getattr(b, name)[:n]):
+            return name
+    return None
+
+
 def test_full_size_rollout_properties():
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params, steer_to_letters
@@ -45,7 +53,15 @@ def test_full_size_rollout_properties():
     gen = seed_stream(0)
     seeds = [next(gen) for _ in range(B)]
     eng.set_use_graphs(False)
-    eager = run_fused_batch(eng, env, pol, seeds)
+    eng.set_two_lanes(False)
+    one_lane = run_fused_batch(eng, env, pol, seeds)       # the whole batch as one lane on one stream
+    eng.set_two_lanes(True)
+    two = run_fused_batch(eng, env, pol, seeds)            # two concurrent half-batch lanes on two streams
+    assert _logs_equal(one_lane, two) is None, _logs_equal(one_lane, two)
+    ragged = run_fused_batch(eng, env, pol, seeds[:1001])   # odd batch: lanes of 501 and 500 envs
+    assert _logs_equal_prefix(one_lane, ragged, 1001) is None
+    eng.set_two_lanes(False)
+    eager = one_lane
     eng.set_use_graphs(True)
     first = run_fused_batch(eng, env, pol, seeds)          # eager again (first use of the configuration with graphs on)
     captured = run_fused_batch(eng, env, pol, seeds)       # captured + launched
