@@ -228,6 +228,12 @@ int lmrl_ppo_loss_host(lmrl_engine* e, int64_t n, const float* mask, const float
                        const float* old_logprobs, const float* old_values, const float* old_advantages, const float* old_returns,
                        double cliprange_value, double cliprange, double value_loss_coef, double* out /*[16]*/);
 
+/* optax.adamw(learning_rate, b1, b2, eps, weight_decay[, mask]) (train_ppo_gpt2.py:144-165) over one flat fp32 segment, in place.
+ * DEVICE pointers, enqueued on the engine stream (lmrl_stream), no synchronisation; step is 1-based; grad_scale multiplies the
+ * gradient first (1 / world_size after a summing all-reduce).  Segments under the weight-decay mask pass weight_decay = 0. */
+int lmrl_adamw_dev(lmrl_engine* e, float* params, const float* grads, float* m, float* v, int64_t n, double lr, double b1, double b2,
+                   double eps, double weight_decay, int64_t step, double grad_scale);
+
 /* ---- fused rollout (interact_environment's while-loop, environment.py:176-206, with no host round trip) -------- */
 typedef struct lmrl_rollout_out {      /* all HOST pointers for _host, DEVICE pointers for _dev; any may be NULL */
     float* ep_return;       /* [n]  sum of rewards (fp32 accumulation in step order)            :238 */

@@ -243,3 +243,41 @@ int lmrl_ppo_loss_host(lmrl_engine* e, int64_t n, const float* mask, const float
 }
 
 }  // extern "C"
+
+// ---- AdamW (the optimizer of the PPO / BC / ILQL drivers: optax.adamw(lr, b1 0.9, b2 0.95, eps 1e-8, weight_decay, mask), ------
+// train_ppo_gpt2.py:144-165) as ONE streaming kernel over a flat fp32 parameter segment: reads p, g, m, v (16 B), writes p, m, v (12 B)
+// per parameter — HBM-bound, 28 B / parameter.  optax order of operations: m, v moments; bias-corrected m_hat / (sqrt(v_hat) + eps);
+// + weight_decay * p; * (-lr).
+namespace lmrl {
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float grad_scale) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float upd = (mi / bc1) / (sqrtf(vi / bc2) + eps) + wd * p[i];
+        p[i] -= lr * upd;
+    }
+}
+}  // namespace lmrl
+
+extern "C" {
+
+// All pointers are DEVICE pointers (fp32, n elements); enqueued on the engine stream, no synchronisation.  step is 1-based.
+// grad_scale multiplies the gradient first (1 / world_size after a summing all-reduce, or a loss-scale inverse).
+int lmrl_adamw_dev(lmrl_engine* e, float* params, const float* grads, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps,
+                   double weight_decay, int64_t step, double grad_scale) {
+    LMRL_CHECK(e && params && grads && m && v, "lmrl_adamw: null argument");
+    LMRL_CHECK(n >= 0 && step >= 1, "lmrl_adamw: n must be >= 0 and step >= 1");
+    if (n == 0) return 0;
+    LMRL_CUDA(cudaSetDevice(e->device));
+    const float bc1 = (float)(1.0 - pow(b1, (double)step)), bc2 = (float)(1.0 - pow(b2, (double)step));
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    adamw_kernel<<<blocks, 256, 0, e->stream>>>(params, grads, m, v, n, (float)lr, (float)b1, (float)b2, (float)eps, (float)weight_decay, bc1, bc2, (float)grad_scale);
+    e->launches++;
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -84,37 +84,71 @@ class TorchPPOTrain:
         self.pad_token_id = int(pad_token_id if pad_token_id is not None else self.config.n_vocab)
         self.cliprange_value, self.cliprange, self.value_loss_coef = cliprange_value, cliprange, value_loss_coef
         self.autocast = torch.bfloat16 if activation_dtype == "bf16" else None
-        t = lambda a: torch.nn.Parameter(torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.device))  # noqa: E731
-        self.p = dict(wte=t(policy_params["wte"]), wpe=t(policy_params["wpe"]), lnf_g=t(policy_params["lnf_g"]), lnf_b=t(policy_params["lnf_b"]),
-                      layers=[{k: t(L[k]) for k in _LAYER_KEYS} for L in policy_params["layers"]])
-        self.vh_w = t(np.asarray(value_head_params["dense"]["kernel"]).reshape(-1, 1))
-        self.vh_b = t(np.asarray(value_head_params["dense"].get("bias", np.zeros(1))).reshape(1))
-        decay, no_decay = [], []
-        for name, prm in self.named_parameters():
-            (no_decay if (name.endswith("_b") or name.endswith("_g") or name == "vh_b") else decay).append(prm)
-        self.opt = torch.optim.AdamW([dict(params=decay, weight_decay=weight_decay), dict(params=no_decay, weight_decay=0.0)],
-                                     lr=lr, betas=(0.9, 0.95), eps=1e-8)
+        # fp32 master weights live in TWO flat buffers (weight-decayed matrices / embeddings; LayerNorm scales and every bias, which
+        # train_ppo_gpt2.py:144-151 masks out of the decay); the per-tensor parameters are views, so autograd accumulates straight
+        # into flat gradients: one all-reduce and one AdamW launch per buffer.
+        entries = [("wte", policy_params["wte"]), ("wpe", policy_params["wpe"]), ("lnf_g", policy_params["lnf_g"]), ("lnf_b", policy_params["lnf_b"])]
+        for i, L in enumerate(policy_params["layers"]):
+            entries += [(f"h{i}.{k}", L[k]) for k in _LAYER_KEYS]
+        entries += [("vh_w", np.asarray(value_head_params["dense"]["kernel"]).reshape(-1, 1)),
+                    ("vh_b", np.asarray(value_head_params["dense"].get("bias", np.zeros(1))).reshape(1))]
+        no_decay = lambda name: name.endswith("_b") or name.endswith("_g") or name == "vh_b"  # noqa: E731
+        self.flat, self._views, self._names = [], {}, [[], []]
+        for grp in (0, 1):
+            chosen = [(n, np.ascontiguousarray(a, dtype=np.float32)) for n, a in entries if int(no_decay(n)) == grp]
+            flat = torch.nn.Parameter(torch.cat([torch.from_numpy(a.reshape(-1)) for _, a in chosen]).to(self.device))
+            self.flat.append(flat)
+            o = 0
+            for n, a in chosen:
+                self._views[n] = (grp, o, a.shape)
+                self._names[grp].append(n)
+                o += a.size
+        self.weight_decay, self.lr, self.betas, self.eps = float(weight_decay), float(lr), (0.9, 0.95), 1e-8
+        self.use_device_adamw = engine is not None
+        if self.use_device_adamw:
+            self.m = [torch.zeros_like(f.data) for f in self.flat]
+            self.v = [torch.zeros_like(f.data) for f in self.flat]
+            self.opt = None
+        else:
+            self.opt = torch.optim.AdamW([dict(params=[self.flat[0]], weight_decay=weight_decay), dict(params=[self.flat[1]], weight_decay=0.0)],
+                                         lr=lr, betas=self.betas, eps=self.eps)
         self.steps = 0
 
+    def _view(self, name):
+        grp, o, shape = self._views[name]
+        n = int(np.prod(shape))
+        return self.flat[grp][o:o + n].view(*shape)
+
+    @property
+    def p(self) -> Dict:
+        """The parameter dict (HF GPT-2 layout) as views of the flat master buffers — rebuilt per access so autograd sees fresh views."""
+        return dict(wte=self._view("wte"), wpe=self._view("wpe"), lnf_g=self._view("lnf_g"), lnf_b=self._view("lnf_b"),
+                    layers=[{k: self._view(f"h{i}.{k}") for k in _LAYER_KEYS} for i in range(self.config.n_layer)])
+
+    @property
+    def vh_w(self):
+        return self._view("vh_w")
+
+    @property
+    def vh_b(self):
+        return self._view("vh_b")
+
     def named_parameters(self):
-        for k in ("wte", "wpe", "lnf_g", "lnf_b"):
-            yield k, self.p[k]
-        for i, L in enumerate(self.p["layers"]):
-            for k in _LAYER_KEYS:
-                yield f"h{i}.{k}", L[k]
-        yield "vh_w", self.vh_w
-        yield "vh_b", self.vh_b
+        for grp in (0, 1):
+            for n in self._names[grp]:
+                yield n, self._view(n)
 
     # ---- model -------------------------------------------------------------------------------------------------------
-    def _hidden(self, ids, attn_mask):
+    def _hidden(self, ids, attn_mask, params=None):
         torch, F = self.torch, self.torch.nn.functional
         cfg = self.config
+        P = params if params is not None else self.p
         b, T = ids.shape
         pos = torch.arange(T, device=ids.device)
-        x = self.p["wte"][ids.clamp(max=self.p["wte"].shape[0] - 1)] + self.p["wpe"][pos][None]
+        x = P["wte"][ids.clamp(max=P["wte"].shape[0] - 1)] + P["wpe"][pos][None]
         causal = torch.tril(torch.ones(T, T, dtype=torch.bool, device=ids.device))
         mask = causal[None, None] & attn_mask[:, None, None, :]
-        for L in self.p["layers"]:
+        for L in P["layers"]:
             h = F.layer_norm(x, (cfg.d_model,), L["ln1_g"], L["ln1_b"], cfg.ln_eps)
             qkv = h @ L["attn_w"] + L["attn_b"]
             q, k, v = (z.view(b, T, cfg.n_head, -1).transpose(1, 2) for z in qkv.split(cfg.d_model, dim=-1))
@@ -122,7 +156,7 @@ class TorchPPOTrain:
             x = x + a.transpose(1, 2).reshape(b, T, cfg.d_model) @ L["proj_w"] + L["proj_b"]
             h = F.layer_norm(x, (cfg.d_model,), L["ln2_g"], L["ln2_b"], cfg.ln_eps)
             x = x + F.gelu(h @ L["fc_w"] + L["fc_b"], approximate="tanh") @ L["fc2_w"] + L["fc2_b"]
-        return F.layer_norm(x, (cfg.d_model,), self.p["lnf_g"], self.p["lnf_b"], cfg.ln_eps)
+        return F.layer_norm(x, (cfg.d_model,), P["lnf_g"], P["lnf_b"], cfg.ln_eps)
 
     def loss(self, batch: Dict[str, np.ndarray]):
         """ppo/gpt2/interface.py:106-146 + ppo_loss_fn (ppo/base_interface.py:71-142)."""
@@ -133,8 +167,9 @@ class TorchPPOTrain:
         sta = torch.as_tensor(batch["should_take_action"], device=dev)
         old_lp, old_v, old_adv, old_ret = (torch.as_tensor(batch[k], device=dev).float() for k in ("old_logprobs", "old_values", "old_advantages", "old_returns"))
         with torch.autocast(self.device.type, dtype=self.autocast, enabled=self.autocast is not None):
-            h = self._hidden(ids, attn)
-            logits = h @ self.p["wte"][:self.config.n_vocab].T
+            P = self.p
+            h = self._hidden(ids, attn, P)
+            logits = h @ P["wte"][:self.config.n_vocab].T
         values = (h.float() @ self.vh_w + self.vh_b)[:, :-1, 0]
         logprobs = -torch.nn.functional.cross_entropy(logits[:, :-1].float().reshape(-1, logits.shape[-1]), ids[:, 1:].clamp(max=self.config.n_vocab - 1).reshape(-1),
                                                       reduction="none").view(ids.shape[0], -1)
@@ -154,22 +189,32 @@ class TorchPPOTrain:
         return loss, logs
 
     def step(self, batch: Dict[str, np.ndarray]) -> Tuple[float, Dict[str, float]]:
-        """One optimizer step on one minibatch (``PPOTrain.step``, ppo/base_interface.py:183-228); gradients are averaged over ranks."""
+        """One optimizer step on one minibatch (``PPOTrain.step``, ppo/base_interface.py:183-228): torch autograd for the gradients
+        (library path), a summing all-reduce of the two flat gradient buffers over the ranks, then AdamW — the hand-written streaming
+        kernel ``lmrl_adamw_dev`` when an engine is attached, ``torch.optim.AdamW`` otherwise (CPU tests)."""
         torch = self.torch
-        self.opt.zero_grad(set_to_none=True)
+        for f in self.flat:
+            f.grad = None
         loss, logs = self.loss(batch)
         loss.backward()
+        world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            grads = [p.grad for _, p in self.named_parameters() if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            torch.distributed.all_reduce(flat)
-            flat /= torch.distributed.get_world_size()
-            o = 0
-            for g in grads:
-                g.copy_(flat[o:o + g.numel()].view_as(g))
-                o += g.numel()
-        self.opt.step()
+            world = torch.distributed.get_world_size()
+            for f in self.flat:
+                torch.distributed.all_reduce(f.grad)
         self.steps += 1
+        if self.use_device_adamw:
+            e = self._lmrl_engine
+            torch.cuda.synchronize(self.device)
+            for grp, f in enumerate(self.flat):
+                check(e.lib.lmrl_adamw_dev(e.handle, f.data.data_ptr(), f.grad.data_ptr(), self.m[grp].data_ptr(), self.v[grp].data_ptr(), f.numel(),
+                                           self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay if grp == 0 else 0.0, self.steps, 1.0 / world))
+            e.sync()
+        else:
+            if world > 1:
+                for f in self.flat:
+                    f.grad /= world
+            self.opt.step()
         return float(loss.detach()), {k: float(v) for k, v in logs.items()}
 
     # ---- weight hand-over to the rollout engine (device to device; policy.set_params of ppo/train.py:244, 438) -------
@@ -181,10 +226,11 @@ class TorchPPOTrain:
         keep = []
         fp = lambda t: C.cast(C.c_void_p(t.detach().contiguous().data_ptr()), _lib._PF)  # noqa: E731
         w = _lib.lmrl_gpt2_weights()
-        w.wte, w.n_vocab_rows, w.wpe = fp(self.p["wte"]), int(self.p["wte"].shape[0]), fp(self.p["wpe"])
-        w.lnf_g, w.lnf_b = fp(self.p["lnf_g"]), fp(self.p["lnf_b"])
+        P = self.p
+        w.wte, w.n_vocab_rows, w.wpe = fp(P["wte"]), int(P["wte"].shape[0]), fp(P["wpe"])
+        w.lnf_g, w.lnf_b = fp(P["lnf_g"]), fp(P["lnf_b"])
         for key in _LAYER_KEYS:
-            ptrs = (_lib._PF * L)(*[fp(layer[key]) for layer in self.p["layers"]])
+            ptrs = (_lib._PF * L)(*[fp(layer[key]) for layer in P["layers"]])
             keep.append(ptrs)
             setattr(w, key, C.cast(ptrs, _lib._PPF))
         dims = _lib.lmrl_gpt2_dims(n_layer=cfg.n_layer, n_head=cfg.n_head, d_model=cfg.d_model, d_ff=cfg.d_ff, n_vocab=cfg.n_vocab, n_pos=cfg.n_pos, ln_eps=cfg.ln_eps)
@@ -193,9 +239,9 @@ class TorchPPOTrain:
         upload_value_heads(e, head_set, v_linear=dict(dense=dict(kernel=self.vh_w.detach().cpu().numpy(), bias=self.vh_b.detach().cpu().numpy())))
 
     def params_numpy(self) -> Dict:
-        g = lambda t: t.detach().cpu().numpy()  # noqa: E731
-        return dict(wte=g(self.p["wte"]), wpe=g(self.p["wpe"]), lnf_g=g(self.p["lnf_g"]), lnf_b=g(self.p["lnf_b"]),
-                    layers=[{k: g(L[k]) for k in _LAYER_KEYS} for L in self.p["layers"]])
+        g = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731
+        P = self.p
+        return dict(wte=g(P["wte"]), wpe=g(P["wpe"]), lnf_g=g(P["lnf_g"]), lnf_b=g(P["lnf_b"]), layers=[{k: g(L[k]) for k in _LAYER_KEYS} for L in P["layers"]])
 
 
 def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,

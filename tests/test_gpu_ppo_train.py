@@ -41,3 +41,49 @@ def test_ppo_rounds_update_the_engine_policy():
             want = (h @ trainer.p["wte"][:cfg.n_vocab].T).float().cpu().numpy()
             assert np.abs(after[i] - want).max() <= 6e-2, np.abs(after[i] - want).max()
     eng.close()
+
+
+def test_device_adamw_matches_optax_formula_and_torch():
+    """lmrl_adamw_dev against the optax.adamw update written out in float64 numpy (the formula of the reference's optimizer,
+    train_ppo_gpt2.py:144-165) and against torch.optim.AdamW, over 5 steps on 3.3 M parameters; tolerance 2e-6 relative to the update size
+    (the kernel's fast division / sqrt)."""
+    import torch
+    from lmrl_gym_b200._lib import check
+    from lmrl_gym_b200.engine import Engine
+    eng = Engine(max_envs=8, max_input_length=16, max_new_tokens=2)
+    n = 3_300_001
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(n).astype(np.float32)
+    lr, b1, b2, eps, wd = 1e-3, 0.9, 0.95, 1e-8, 0.01
+    dev = torch.device("cuda", 0)
+    p = torch.from_numpy(p0.copy()).to(dev)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    pt = torch.nn.Parameter(torch.from_numpy(p0.copy()).to(dev))
+    opt = torch.optim.AdamW([pt], lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd)
+    p64, m64, v64 = p0.astype(np.float64), np.zeros(n), np.zeros(n)
+    for step in range(1, 6):
+        g = (rng.standard_normal(n) * 0.1).astype(np.float32)
+        gd = torch.from_numpy(g).to(dev)
+        torch.cuda.synchronize()
+        check(eng.lib.lmrl_adamw_dev(eng.handle, p.data_ptr(), (gd * 2).data_ptr() if False else gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps, wd, step, 1.0))
+        eng.sync()
+        pt.grad = gd.clone()
+        opt.step()
+        m64 = b1 * m64 + (1 - b1) * g
+        v64 = b2 * v64 + (1 - b2) * g.astype(np.float64) ** 2
+        p64 = p64 - lr * ((m64 / (1 - b1 ** step)) / (np.sqrt(v64 / (1 - b2 ** step)) + eps) + wd * p64)
+    got = p.cpu().numpy()
+    assert np.abs(got - p64).max() <= 5 * lr * 2e-4            # 5 updates of size ~lr each, relative error of the fast maths
+    assert np.abs(got - pt.detach().cpu().numpy()).max() <= 5 * lr * 2e-4
+    assert np.abs(got - p0).max() > lr                          # it moved
+    # grad_scale: a summed gradient of 2 ranks scaled by 1/2 is the same update
+    p2 = torch.from_numpy(p0.copy()).to(dev); m2, v2 = torch.zeros_like(p2), torch.zeros_like(p2)
+    p3 = torch.from_numpy(p0.copy()).to(dev); m3, v3 = torch.zeros_like(p3), torch.zeros_like(p3)
+    g1 = torch.from_numpy((rng.standard_normal(n) * 0.1).astype(np.float32)).to(dev)
+    g2 = g1 * 2
+    torch.cuda.synchronize()
+    check(eng.lib.lmrl_adamw_dev(eng.handle, p2.data_ptr(), g1.data_ptr(), m2.data_ptr(), v2.data_ptr(), n, lr, b1, b2, eps, 0.0, 1, 1.0))
+    check(eng.lib.lmrl_adamw_dev(eng.handle, p3.data_ptr(), g2.data_ptr(), m3.data_ptr(), v3.data_ptr(), n, lr, b1, b2, eps, 0.0, 1, 0.5))
+    eng.sync()
+    assert torch.equal(p2, p3)
+    eng.close()

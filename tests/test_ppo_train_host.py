@@ -66,7 +66,8 @@ def test_steps_lower_the_loss_and_respect_weight_decay_mask():
         last = tr.step(batch)[0]
     assert last < first
     groups = tr.opt.param_groups
-    assert len(groups[1]["params"]) == 2 + 8 * CFG.n_layer + 1 and groups[1]["weight_decay"] == 0.0      # LN scales/biases + all biases + value bias
+    assert groups[1]["weight_decay"] == 0.0 and len(tr._names[1]) == 2 + 8 * CFG.n_layer + 1      # LN scales/biases + all biases + value bias
+    assert set(tr._names[0]) == {"wte", "wpe", "vh_w"} | {f"h{i}.{k}" for i in range(CFG.n_layer) for k in ("attn_w", "proj_w", "fc_w", "fc2_w")}
 
 
 def test_episodes_to_chains_and_block():
