@@ -45,8 +45,8 @@ def test_ppo_rounds_update_the_engine_policy():
 
 def test_device_adamw_matches_optax_formula_and_torch():
     """lmrl_adamw_dev against the optax.adamw update written out in float64 numpy (the formula of the reference's optimizer,
-    train_ppo_gpt2.py:144-165) and against torch.optim.AdamW, over 5 steps on 3.3 M parameters; tolerance 2e-6 relative to the update size
-    (the kernel's fast division / sqrt)."""
+    train_ppo_gpt2.py:144-165) and against torch.optim.AdamW, over 5 steps on 3.3 M parameters; tolerance per step = 2e-4 of the
+    update size (the kernel's fast division / sqrt) + one float32 rounding of the parameter."""
     import torch
     from lmrl_gym_b200._lib import check
     from lmrl_gym_b200.engine import Engine
@@ -65,7 +65,7 @@ def test_device_adamw_matches_optax_formula_and_torch():
         g = (rng.standard_normal(n) * 0.1).astype(np.float32)
         gd = torch.from_numpy(g).to(dev)
         torch.cuda.synchronize()
-        check(eng.lib.lmrl_adamw_dev(eng.handle, p.data_ptr(), (gd * 2).data_ptr() if False else gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps, wd, step, 1.0))
+        check(eng.lib.lmrl_adamw_dev(eng.handle, p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr, b1, b2, eps, wd, step, 1.0))
         eng.sync()
         pt.grad = gd.clone()
         opt.step()
@@ -73,8 +73,9 @@ def test_device_adamw_matches_optax_formula_and_torch():
         v64 = b2 * v64 + (1 - b2) * g.astype(np.float64) ** 2
         p64 = p64 - lr * ((m64 / (1 - b1 ** step)) / (np.sqrt(v64 / (1 - b2 ** step)) + eps) + wd * p64)
     got = p.cpu().numpy()
-    assert np.abs(got - p64).max() <= 5 * lr * 2e-4            # 5 updates of size ~lr each, relative error of the fast maths
-    assert np.abs(got - pt.detach().cpu().numpy()).max() <= 5 * lr * 2e-4
+    tol = 5 * (lr * 2e-4 + np.spacing(np.float32(np.abs(p0).max())))          # per step: fast-maths error of an update of size ~lr + one fp32 rounding of p
+    assert np.abs(got - p64).max() <= tol
+    assert np.abs(got - pt.detach().cpu().numpy()).max() <= tol
     assert np.abs(got - p0).max() > lr                          # it moved
     # grad_scale: a summed gradient of 2 ranks scaled by 1/2 is the same update
     p2 = torch.from_numpy(p0.copy()).to(dev); m2, v2 = torch.zeros_like(p2), torch.zeros_like(p2)
