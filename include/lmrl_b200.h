@@ -228,6 +228,14 @@ int lmrl_ppo_loss_host(lmrl_engine* e, int64_t n, const float* mask, const float
                        const float* old_logprobs, const float* old_values, const float* old_advantages, const float* old_returns,
                        double cliprange_value, double cliprange, double value_loss_coef, double* out /*[16]*/);
 
+/* trajectory -> token chain on the device: after a fused WORDLE rollout the engine still holds every episode's canonical token stream;
+ * this exports it annotated as a TokenTrajectory (environment.py:346-383; the PPO driver's one-trajectory-per-episode conversion,
+ * wordle/ppo/train_ppo_gpt2.py:307-335): tokens [n][pitch], n_tok [n], is_action [n][pitch], reward [n][pitch] (an action's reward on
+ * its last token), done [n], truncated [n] (the stream was LEFT-truncated during the rollout and no longer starts at the first
+ * token: the caller falls back to the text path for that episode).  No tokeniser runs on the host.  HOST pointers. */
+int lmrl_rollout_chains_host(lmrl_engine* e, int32_t n, int32_t pitch, int32_t* tokens, int32_t* n_tok, uint8_t* is_action, float* reward,
+                             uint8_t* done, uint8_t* truncated);
+
 /* optax.adamw(learning_rate, b1, b2, eps, weight_decay[, mask]) (train_ppo_gpt2.py:144-165) over one flat fp32 segment, in place.
  * DEVICE pointers, enqueued on the engine stream (lmrl_stream), no synchronisation; step is 1-based; grad_scale multiplies the
  * gradient first (1 / world_size after a summing all-reduce).  Segments under the weight-decay mask pass weight_decay = 0. */

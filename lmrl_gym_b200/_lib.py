@@ -98,6 +98,7 @@ SYMBOLS = {
     "lmrl_textnav_step_host": (C.c_int, [_V, _V, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V]),
     "lmrl_ppo_advantages_host": (C.c_int, [_V, _I, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _I, _V, _V, _V]),
     "lmrl_ppo_loss_host": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _V]),
+    "lmrl_rollout_chains_host": (C.c_int, [_V, _I, _I, _V, _V, _V, _V, _V, _V]),
     "lmrl_adamw_dev": (C.c_int, [_V, _V, _V, _V, _V, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double]),
     "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),

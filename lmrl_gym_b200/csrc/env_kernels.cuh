@@ -80,6 +80,10 @@ struct StreamDev {
     int32_t* kv_len;      // [B]  leading tokens whose KV entries are valid
     int32_t cap;          // row pitch
     int32_t max_input;    // LEFT truncation length (BlockingStrategy max_length); stream is shifted when exceeded
+    // token-trajectory annotations of the stream (PPO data path: TokenTrajectory.from_text_trajectory, environment.py:346-383), Wordle only:
+    uint8_t* is_action;   // [B][cap] the token belongs to an action Text, or nullptr
+    float* tok_reward;    // [B][cap] the Text item's reward on its LAST token, 0 elsewhere
+    uint8_t* truncated;   // [B] the stream was LEFT-truncated at least once (it no longer starts at the episode's first token)
 };
 
 struct ActionSrc {
@@ -278,11 +282,24 @@ __global__ void wordle_step_kernel(WordleDev w, TokenizerDev tk, ActionSrc src, 
             int len = st.len[e];
             const int keep = len;                       // KV of everything before the action stays valid
             len += render_spaced_line(s.cp, ncp, tk.t, row + len, st.cap - len);
+            const int act_end = len;
             len += render_feedback_line(fb, valid, tk.t, row + len, st.cap - len);
+            if (st.is_action) {                         // the action Text carries the step's reward on its last token, the feedback none
+                uint8_t* ia = st.is_action + (size_t)e * st.cap;
+                float* tr = st.tok_reward + (size_t)e * st.cap;
+                for (int i = keep; i < len; ++i) { ia[i] = i < act_end ? 1 : 0; tr[i] = 0.f; }
+                if (act_end > keep) tr[act_end - 1] = reward;
+            }
             int kv = keep;
             if (len > st.max_input) {                   // LEFT truncation (BlockingStrategy, eval_bc_gpt2.py:100-104)
                 const int drop = len - st.max_input;
                 for (int i = 0; i < st.max_input; ++i) row[i] = row[i + drop];
+                if (st.is_action) {
+                    uint8_t* ia = st.is_action + (size_t)e * st.cap;
+                    float* tr = st.tok_reward + (size_t)e * st.cap;
+                    for (int i = 0; i < st.max_input; ++i) { ia[i] = ia[i + drop]; tr[i] = tr[i + drop]; }
+                    st.truncated[e] = 1;
+                }
                 len = st.max_input;
                 kv = 0;                                 // positions shifted: the whole window is re-prefilled
             }

@@ -173,7 +173,11 @@ __global__ void init_stream_kernel(int n, const int32_t* __restrict__ header, in
     pdl_enter();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
-    for (int i = 0; i < n_header; ++i) st.tokens[(size_t)e * st.cap + i] = header[i];
+    for (int i = 0; i < n_header; ++i) {
+        st.tokens[(size_t)e * st.cap + i] = header[i];
+        if (st.is_action) { st.is_action[(size_t)e * st.cap + i] = 0; st.tok_reward[(size_t)e * st.cap + i] = 0.f; }
+    }
+    if (st.truncated) st.truncated[e] = 0;
     st.len[e] = n_header;
     st.kv_len[e] = 0;
     episode_key[e] = seeds[e];
@@ -569,7 +573,9 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     if (e->alloc(&G.gen.tok, (size_t)B * max_new) || e->alloc(&G.gen.len, B) || e->alloc(&G.gen.active, B) || e->alloc(&G.gen.cur, B)) return -1;
     G.gen.max_new = max_new;
     G.gen.eos_id = e->tok.t.newline_id;
-    if (e->alloc(&G.stream.tokens, (size_t)B * G.stream_cap) || e->alloc(&G.stream.len, B) || e->alloc(&G.stream.kv_len, B)) return -1;
+    if (e->alloc(&G.stream.tokens, (size_t)B * G.stream_cap) || e->alloc(&G.stream.len, B) || e->alloc(&G.stream.kv_len, B) ||
+        e->alloc(&G.stream.is_action, (size_t)B * G.stream_cap) || e->alloc(&G.stream.tok_reward, (size_t)B * G.stream_cap) || e->alloc(&G.stream.truncated, B))
+        return -1;
     G.stream.cap = G.stream_cap; G.stream.max_input = max_in;
     if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.best_scratch, B) || e->alloc(&G.episode_key, B) || e->alloc(&G.live, 1)) return -1;
     if (e->alloc(&G.ep_return, B) || e->alloc(&G.ep_length, B) || e->alloc(&G.ep_done, B) || e->alloc(&G.step_reward, (size_t)B * T) ||
@@ -1245,6 +1251,26 @@ int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev
         LMRL_CUDA(cudaMemcpyAsync(e->d_opt_pos, opt_pos_dev, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToDevice, e->stream));
     if (rollout_run(e, env_kind, opt_pos_dev != nullptr, n, *s)) return -1;
     return rollout_export(e, n, out_dev, cudaMemcpyDeviceToDevice);
+}
+
+int lmrl_rollout_chains_host(lmrl_engine* e, int32_t n, int32_t pitch, int32_t* tokens, int32_t* n_tok, uint8_t* is_action, float* reward, uint8_t* done,
+                             uint8_t* truncated) {
+    LMRL_CHECK(e && e->has_gpt2 && e->has_wordle, "lmrl_rollout_chains: needs a Wordle engine with a policy (run a fused Wordle rollout first)");
+    LMRL_CHECK(tokens && n_tok && is_action && reward && done && truncated, "lmrl_rollout_chains: null argument");
+    LMRL_CHECK(n > 0 && n <= e->cfg.max_envs && pitch > 0, "lmrl_rollout_chains: bad batch %d / pitch %d", n, pitch);
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    cudaStream_t st = e->stream;
+    const int w = std::min(pitch, G.stream.cap);
+    LMRL_CUDA(cudaMemcpy2DAsync(tokens, sizeof(int32_t) * pitch, G.stream.tokens, sizeof(int32_t) * G.stream.cap, sizeof(int32_t) * w, n, cudaMemcpyDeviceToHost, st));
+    LMRL_CUDA(cudaMemcpy2DAsync(is_action, pitch, G.stream.is_action, G.stream.cap, w, n, cudaMemcpyDeviceToHost, st));
+    LMRL_CUDA(cudaMemcpy2DAsync(reward, sizeof(float) * pitch, G.stream.tok_reward, sizeof(float) * G.stream.cap, sizeof(float) * w, n, cudaMemcpyDeviceToHost, st));
+    LMRL_CUDA(cudaMemcpyAsync(n_tok, G.stream.len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    LMRL_CUDA(cudaMemcpyAsync(done, G.ep_done, n, cudaMemcpyDeviceToHost, st));
+    LMRL_CUDA(cudaMemcpyAsync(truncated, G.stream.truncated, n, cudaMemcpyDeviceToHost, st));
+    LMRL_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; ++i) LMRL_CHECK(n_tok[i] <= pitch, "lmrl_rollout_chains: episode %d has %d tokens, pitch is %d", i, n_tok[i], pitch);
+    return 0;
 }
 
 int lmrl_wordle_scripted_rollout_dev(lmrl_engine* e, const uint64_t* seeds_dev, int32_t n, float prob_smart, uint64_t policy_seed,

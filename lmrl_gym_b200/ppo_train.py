@@ -29,7 +29,7 @@ from ._lib import check
 from .engine import Engine
 from .environment import Text, TextTrajectory, TextTrajectoryChain, text_env_eval
 from .gpt2 import GPT2Config, _LAYER_KEYS
-from .ppo import B200PPOInference, PPOData, TokenTrajectory, _block_right
+from .ppo import B200PPOInference, PPOData, TokenTrajectory, TokenTrajectoryChain, _block_right
 from .value_inference import upload_value_heads
 
 import ctypes as C
@@ -57,6 +57,30 @@ def episodes_to_chains(raw_results, tokenizer, max_length: int, gamma: float) ->
             continue
         chains.append(TextTrajectoryChain(traj, None))
     return chains
+
+
+def device_token_chains(engine: Engine, n: int, max_length: int) -> List[Optional["TokenTrajectoryChain"]]:
+    """trajectory -> token chain WITHOUT a host tokeniser: after a fused Wordle rollout of ``n`` episodes the engine's canonical token
+    streams are exported with their is_action / reward annotations (``lmrl_rollout_chains_host``) — exactly
+    ``TokenTrajectory.from_text_trajectory`` of the trajectory ``episodes_to_chains`` builds.  Entries are None for episodes the device
+    cannot represent (stream LEFT-truncated during the rollout, or >= max_length tokens: the reference drops trailing turns there,
+    train_ppo_gpt2.py:317-331) — the caller converts those through the text path."""
+    pitch = int(engine.max_input_length + 8)
+    toks = np.zeros((n, pitch), np.int32)
+    n_tok = np.zeros(n, np.int32)
+    act = np.zeros((n, pitch), np.uint8)
+    rew = np.zeros((n, pitch), np.float32)
+    done, trunc = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    check(engine.lib.lmrl_rollout_chains_host(engine.handle, n, pitch, toks.ctypes.data, n_tok.ctypes.data, act.ctypes.data, rew.ctypes.data,
+                                              done.ctypes.data, trunc.ctypes.data))
+    out: List[Optional[TokenTrajectoryChain]] = []
+    for i in range(n):
+        k = int(n_tok[i])
+        if trunc[i] or k >= max_length or not act[i, :k].any():
+            out.append(None)
+            continue
+        out.append(TokenTrajectoryChain(TokenTrajectory(toks[i, :k].copy(), act[i, :k].astype(np.bool_), rew[i, :k].copy(), np.array(bool(done[i]), dtype=np.bool_)), None))
+    return out
 
 
 def block_ppo_data(datas: List[PPOData], pad_token_id: int, max_length: int) -> Dict[str, np.ndarray]:
@@ -247,7 +271,7 @@ class TorchPPOTrain:
 def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
                    epochs: int = 1, train_bsize: int = 32, max_length: int = 128, gamma: float = 1.0, lam: float = 0.95,
                    use_advantage_whitening: bool = True, seed_generator=None, rng: Optional[np.random.Generator] = None,
-                   max_steps_per_round: Optional[int] = None, on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:
+                   max_steps_per_round: Optional[int] = None, use_device_chains: bool = True, on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:
     """ppo/train.py:138-477 reduced to its data flow (no checkpointing / wandb): returns one log dict per round."""
     import time
     import torch
@@ -256,11 +280,32 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTr
     history: List[Dict] = []
     for rnd in range(n_rounds):
         t0 = time.perf_counter()
-        raw, summary = text_env_eval(env, policy, n_rollouts=n_rollouts, bsize=rollout_bsize, seed_generator=seed_generator, verbose=False)
-        t1 = time.perf_counter()
-        chains = episodes_to_chains(raw, tok, max_length, gamma)
-        datas, kls = inference.get_ppo_data_from_text_trajectory_chain(chains, bsize=1 << 20, max_length=max_length, gamma=gamma, lam=lam,
-                                                                       kl_weight=kl_controller.value, use_advantage_whitening=use_advantage_whitening, verbose=False)
+        fused_wordle = getattr(env, "_lmrl_kind", None) == 1 and getattr(env, "_lmrl_engine", None) is inference._lmrl_engine and \
+            getattr(env, "_lmrl_fusable", False) and getattr(policy, "fusable", False) and use_device_chains
+        raw, token_chains, rollout_s = [], [], 0.0
+        for lo in range(0, n_rollouts, rollout_bsize):
+            nb = min(rollout_bsize, n_rollouts - lo)
+            tb = time.perf_counter()
+            r, _ = text_env_eval(env, policy, n_rollouts=nb, bsize=nb, seed_generator=seed_generator, verbose=False)
+            rollout_s += time.perf_counter() - tb
+            raw += list(r)
+            if fused_wordle:
+                # the engine still holds this batch's token streams: trajectory -> token chain without a host tokeniser
+                dev = device_token_chains(inference._lmrl_engine, nb, max_length)
+                for ep, ch in zip(r, dev):
+                    if ch is None:
+                        tc = episodes_to_chains([ep], tok, max_length, gamma)
+                        ch = TokenTrajectoryChain.from_text_trajectory_chain(tc[0], tok) if tc else None
+                    if ch is not None:
+                        token_chains.append(ch)
+        env_steps = int(sum(len(ep) for ep in raw))
+        reward_mean = float(np.mean([float(sum(t.reward for t in ep)) for ep in raw])) if not fused_wordle else \
+            float(np.mean([float(c.token_trajectory.reward.sum()) for c in token_chains])) if token_chains else 0.0
+        t1 = t0 + rollout_s
+        if not fused_wordle:
+            token_chains = [TokenTrajectoryChain.from_text_trajectory_chain(c, tok) for c in episodes_to_chains(raw, tok, max_length, gamma)]
+        datas, kls = inference.get_ppo_data_from_token_trajectory_chain(token_chains, bsize=1 << 20, max_length=max_length, gamma=gamma, lam=lam,
+                                                                        kl_weight=kl_controller.value, use_advantage_whitening=use_advantage_whitening, verbose=False)
         mean_kl = float(np.mean(kls)) if len(kls) else 0.0
         kl_controller.update(mean_kl, train_bsize)
         t2 = time.perf_counter()
@@ -275,7 +320,7 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTr
         trainer.push_to_engine()
         torch.cuda.synchronize()
         t3 = time.perf_counter()
-        log = dict(round=rnd, reward_mean=float(summary["reward"]["mean"]), env_steps=int(sum(len(ep) for ep in raw)), mean_kl=mean_kl,
+        log = dict(round=rnd, reward_mean=reward_mean, env_steps=env_steps, mean_kl=mean_kl,
                    kl_coef=float(kl_controller.value), n_ppo_data=len(datas), updates=len(losses), loss=float(np.mean(losses)) if losses else None,
                    rollout_s=t1 - t0, ppo_data_s=t2 - t1, update_s=t3 - t2)
         history.append(log)

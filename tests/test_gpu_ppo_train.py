@@ -88,3 +88,43 @@ def test_device_adamw_matches_optax_formula_and_torch():
     eng.sync()
     assert torch.equal(p2, p3)
     eng.close()
+
+
+def test_device_token_chains_equal_the_text_path():
+    """trajectory -> token chain on the device (lmrl_rollout_chains_host) == tokenising the episode's final history item by item
+    (TokenTrajectory.from_text_trajectory of the trajectory train_ppo_gpt2.py:307-335 builds): ids, is_action, per-token rewards, done —
+    for a policy that mixes legal guesses, illegal strings and wins, and with a short max_input_length so some streams get LEFT-truncated
+    (those must come back as None)."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.environment import text_env_eval
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params, steer_to_letters
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from lmrl_gym_b200 import ppo as P, ppo_train as T
+    from lmrl_gym_b200.randomness import seed_generator
+    tok = ByteTokenizer.synthetic()
+    cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+    params = steer_to_letters(init_gpt2_params(cfg, seed=0), tok)
+    for max_in, expect_trunc in ((192, False), (48, True)):
+        B = 128
+        eng = Engine(max_envs=B, max_input_length=max_in, max_new_tokens=6, max_turns=6, tokenizer=tok)
+        env = B200WordleEnv(eng, "wordle_official.txt", require_words_in_vocab=False, bad_word_reward=-10.0)
+        pol = B200GPT2Policy(eng, params, cfg, seed=1)
+        raw, _ = text_env_eval(env, pol, n_rollouts=B, bsize=B, seed_generator=seed_generator(3), verbose=False)
+        dev = T.device_token_chains(eng, B, max_length=max_in + 6)
+        n_none = 0
+        for ep, ch in zip(raw, dev):
+            hist = ep[-1].post_transition_history
+            n_tok_text = sum(len(tok.encode(t.text)) for t in hist)
+            if ch is None:
+                n_none += 1
+                assert n_tok_text > max_in or n_tok_text >= max_in + 6
+                continue
+            ref = T.episodes_to_chains([ep], tok, max_length=10 ** 6, gamma=1.0)[0]
+            tt = P.TokenTrajectory.from_text_trajectory(ref.text_trajectory, tok)
+            got = ch.token_trajectory
+            assert got.tokens.tolist() == tt.tokens.tolist()
+            assert got.is_action.tolist() == tt.is_action.tolist()
+            assert got.reward.tolist() == tt.reward.tolist() and bool(got.done) == bool(tt.done)
+        assert (n_none > 0) == expect_trunc
+        eng.close()
