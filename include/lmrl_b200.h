@@ -236,6 +236,27 @@ int lmrl_ppo_loss_host(lmrl_engine* e, int64_t n, const float* mask, const float
 int lmrl_rollout_chains_host(lmrl_engine* e, int32_t n, int32_t pitch, int32_t* tokens, int32_t* n_tok, uint8_t* is_action, float* reward,
                              uint8_t* done, uint8_t* truncated);
 
+/* ---- gradient step of the policy + value head (GPT2PPOTrain._step, ppo/gpt2/interface.py:72-211) ----------------------------------
+ * The chain rule is split at the per-token quantities: the caller supplies dL/dlogprob and dL/dvalue (the closed-form derivative of
+ * ppo_loss_fn) and the engine back-propagates them through the tied LM head, the LinearHead value head (head set 0) and the decoder
+ * stack of tower 0, ACCUMULATING fp32 gradients into the caller's DEVICE arrays (HF GPT-2 layout, same shapes as lmrl_gpt2_weights).
+ * dlogprob[i][t] = dL/d log p(tokens[i][t+1] | tokens[i][..t]) for t < n_tok[i] - 1;  dvalue[i][t] = dL/d value(position t). */
+typedef struct lmrl_gpt2_grads {
+    float* wte;                  /* [n_vocab_rows, d] */
+    int32_t n_vocab_rows;
+    int32_t reserved;
+    float* wpe;                  /* [n_pos, d] */
+    float* const* ln1_g; float* const* ln1_b; float* const* attn_w; float* const* attn_b; float* const* proj_w; float* const* proj_b;
+    float* const* ln2_g; float* const* ln2_b; float* const* fc_w; float* const* fc_b; float* const* fc2_w; float* const* fc2_b;   /* [L] -> as lmrl_gpt2_weights */
+    float* lnf_g; float* lnf_b;
+    float* vh_w;                 /* [d]  LinearHead kernel gradient, or NULL */
+    float* vh_b;                 /* [1] */
+} lmrl_gpt2_grads;
+/* allocate the training buffers (row / scored-row capacities of one lmrl_policy_grad_host call) and the HF-layout weight copies */
+int lmrl_train_enable(lmrl_engine* e, int32_t max_rows, int32_t max_scored_rows);
+int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const float* dlogprob,
+                          const float* dvalue, float temperature, const lmrl_gpt2_grads* grads);
+
 /* optax.adamw(learning_rate, b1, b2, eps, weight_decay[, mask]) (train_ppo_gpt2.py:144-165) over one flat fp32 segment, in place.
  * DEVICE pointers, enqueued on the engine stream (lmrl_stream), no synchronisation; step is 1-based; grad_scale multiplies the
  * gradient first (1 / world_size after a summing all-reduce).  Segments under the weight-decay mask pass weight_decay = 0. */

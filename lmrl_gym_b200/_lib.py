@@ -50,6 +50,13 @@ class lmrl_forward_out(C.Structure):
     _fields_ = [("token_logprobs", C.c_void_p), ("v", C.c_void_p), ("q1", C.c_void_p), ("q2", C.c_void_p)]
 
 
+class lmrl_gpt2_grads(C.Structure):
+    _fields_ = [("wte", _PF), ("n_vocab_rows", C.c_int32), ("reserved", C.c_int32), ("wpe", _PF),
+                ("ln1_g", _PPF), ("ln1_b", _PPF), ("attn_w", _PPF), ("attn_b", _PPF), ("proj_w", _PPF), ("proj_b", _PPF),
+                ("ln2_g", _PPF), ("ln2_b", _PPF), ("fc_w", _PPF), ("fc_b", _PPF), ("fc2_w", _PPF), ("fc2_b", _PPF),
+                ("lnf_g", _PF), ("lnf_b", _PF), ("vh_w", _PF), ("vh_b", _PF)]
+
+
 class lmrl_sampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64), ("top_k", C.c_int32), ("top_p", C.c_float)]
 
@@ -99,6 +106,8 @@ SYMBOLS = {
     "lmrl_ppo_advantages_host": (C.c_int, [_V, _I, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _I, _V, _V, _V]),
     "lmrl_ppo_loss_host": (C.c_int, [_V, C.c_int64, _V, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _V]),
     "lmrl_rollout_chains_host": (C.c_int, [_V, _I, _I, _V, _V, _V, _V, _V, _V]),
+    "lmrl_train_enable": (C.c_int, [_V, _I, _I]),
+    "lmrl_policy_grad_host": (C.c_int, [_V, _V, _V, _I, _I, _V, _V, C.c_float, C.POINTER(lmrl_gpt2_grads)]),
     "lmrl_adamw_dev": (C.c_int, [_V, _V, _V, _V, _V, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double]),
     "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),

@@ -56,6 +56,13 @@ struct ValueHeadsDev {
     bool has_lin = false, allocated = false;
 };
 
+struct TrainDev;                          // train_kernels.inl: buffers of the hand-written backward pass
+struct Gpt2Dev;
+}  // namespace lmrl
+void lmrl_train_free(lmrl::Gpt2Dev* g);
+static int train_refresh_weight_copies(lmrl_engine* e);
+namespace lmrl {
+
 // One lane = the activation buffers, row map and sampling scratch of one forward pass in flight.  Lane 0 is the whole batch (every
 // host-facing call, profiled runs); lanes 1 and 2 are the two halves of lane 0's buffers, each with its own stream, used by the fused
 // rollout to run two half-batches concurrently: while one half is in its HBM-bound kernels (KV attention, LayerNorm) the other
@@ -101,6 +108,7 @@ struct Gpt2Dev {
     float2* f_lp_partial = nullptr;
     float *f_tlogit = nullptr, *f_lp = nullptr, *f_q1 = nullptr, *f_q2 = nullptr, *f_v = nullptr;
     RowsDev rows{};
+    TrainDev* train = nullptr;
     Lane lane[3];
     Lane* cur = nullptr;              // lane the next tower_layers / forward_and_sample call runs on
     // fused rollouts may split the batch over lanes 1 and 2 (see lanes_usable).  Off by default: measured on B200 it is SLOWER
@@ -147,7 +155,7 @@ struct Gpt2Dev {
     // 1 = tcgen05, one CTA per tile (default); 2 = CTA pairs on prefill passes (3-12 % faster per GEMM at M ~ 100 k rows in
     // isolation, no gain over a whole rollout: 211.4 vs 207.6 ms); 0 = mma.sync cross-check
     int gemm_impl = 1;
-    std::map<std::tuple<const void*, size_t, int>, CUtensorMap> tmaps;   // (base pointer, row bound, box rows | f32 flag) -> descriptor
+    std::map<std::tuple<const void*, size_t, size_t, int>, CUtensorMap> tmaps;   // (base pointer, row bound, columns, box rows | f32 flag) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
 
@@ -306,7 +314,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     bool use2 = false, narrow = false;
     if (tc) {
         auto get = [&](const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32) -> const CUtensorMap* {
-            auto key = std::make_tuple(base, rows, (int)box_rows | (f32 ? 1 << 16 : 0));
+            auto key = std::make_tuple(base, rows, cols, (int)box_rows | (f32 ? 1 << 16 : 0));
             auto it = G.tmaps.find(key);
             if (it == G.tmaps.end()) {
                 CUtensorMap m;
@@ -622,6 +630,7 @@ using namespace lmrl;
 void lmrl_gpt2_free(lmrl_engine* e) {
     if (!e || !e->gpt2) return;
     if (e->gpt2->graph_exec) cudaGraphExecDestroy(e->gpt2->graph_exec);
+    if (e->gpt2->train) lmrl_train_free(e->gpt2);
     if (e->gpt2->stream_b) cudaStreamDestroy(e->gpt2->stream_b);
     if (e->gpt2->ev_fork) cudaEventDestroy(e->gpt2->ev_fork);
     if (e->gpt2->ev_join) cudaEventDestroy(e->gpt2->ev_join);
@@ -712,6 +721,7 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     LMRL_CUDA(cudaGetLastError());
     G.loaded = true;
     e->has_gpt2 = true;
+    if (tower == 0 && GG.train) return train_refresh_weight_copies(e);      // the backward pass keeps HF-layout copies of tower 0
     return 0;
 }
 

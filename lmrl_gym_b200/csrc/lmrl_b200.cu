@@ -5,11 +5,13 @@
 //   lmrl_api.inl      C ABI: lifecycle, tables, text-path envs
 //   gpt2_engine.inl   C ABI: GPT-2 decoder, sampler, fused rollout, per-position forward
 //   textnav_core.h / textnav_kernels.inl   Text-Nav int32 state machine (host+device logic, kernels, C ABI)
+//   train_kernels.inl C ABI: hand-written backward pass of the policy + value head (PPO gradient step)
 //   ppo_kernels.inl   C ABI: PPO data path after the forward passes (KL rewards, GAE, whitening, clipped loss)
 #include <stdarg.h>
 #include <algorithm>
 #include "engine.h"
 #include "gpt2_engine.inl"
+#include "train_kernels.inl"
 #include "lmrl_api.inl"
 #include "ppo_kernels.inl"
 #include "textnav_kernels.inl"

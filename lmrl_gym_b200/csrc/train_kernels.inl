@@ -1,0 +1,627 @@
+// train_kernels.inl — hand-written backward pass of the GPT-2 policy + value head for the PPO gradient step (C ABI part 5).
+//
+// Reference: GPT2PPOTrain._step (LLM_RL/algorithms/ppo/gpt2/interface.py:72-211): jax.value_and_grad of
+//   loss(policy_params, value_head_params) = ppo_loss_fn(logprobs(policy(input_ids)), values(LinearHead(hidden[-1])), ...)
+// Here the chain rule is split at the per-token quantities: the caller supplies dL/dlogprob[t] and dL/dvalue[t] (the derivative of
+// ppo_loss_fn, a closed-form elementwise expression — lmrl_gym_b200/ppo_train.py::ppo_loss_grads) and this file propagates them
+// through the LM head, the value head and the decoder stack into fp32 parameter gradients (HF GPT-2 layout, accumulated):
+//
+//   forward  : the engine's own prefill pass (gpt2_engine.inl) with the residual stream saved before every layer;
+//   backward : per layer, the layer is recomputed from its saved input (activation checkpointing: 37 KB per row for 12 layers instead
+//              of ~290 KB), then   dgrad  dX = dY · W      -> gemm_bf16_tcgen05 (A = dY, W operand = the HF-layout copy of the weight)
+//                                  wgrad  dW = X^T · dY    -> gemm_bf16_tcgen05 over TRANSPOSED operands, fp32 accumulation straight into
+//                                                             the gradient by the TMA reduce-add epilogue
+//              plus small HBM-bound kernels: LayerNorm / GeLU / causal-attention backward, column sums for the biases, transposes.
+// Operands are bf16, accumulation fp32 (the usual mixed-precision recipe; the reference trains in fp32 or bf16 activations).
+#include <cuda_bf16.h>
+
+namespace lmrl {
+
+// ---- small kernels --------------------------------------------------------------------------------------------------------
+// src [M][C] (bf16, or fp32 converted on the fly) -> dst [C][Mp] bf16, columns >= M zero-filled (Mp = row count padded to 64)
+template <typename T>
+__global__ void transpose_to_bf16_rows_kernel(const T* __restrict__ src, const int* __restrict__ M_dev, int C, __nv_bfloat16* __restrict__ dst, int Mp,
+                                              __nv_bfloat16* __restrict__ copy /* optional row-major bf16 copy [M][C] */) {
+    __shared__ float tile[32][33];
+    const int M = *M_dev;
+    const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int m = m0 + i, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (m < M && c < C) {
+            if constexpr (sizeof(T) == 4) v = src[(size_t)m * C + c]; else v = __bfloat162float(src[(size_t)m * C + c]);
+            if (copy) copy[(size_t)m * C + c] = __float2bfloat16(v);
+        }
+        tile[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, m = m0 + threadIdx.x;
+        if (c < C && m < Mp) dst[(size_t)c * Mp + m] = __float2bfloat16(tile[threadIdx.x][i]);
+    }
+}
+
+// out[c] += sum over rows of src[m][c]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ src, const int* __restrict__ M_dev, int C, float* __restrict__ out) {
+    const int M = *M_dev;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float acc = 0.f;
+    for (int m = blockIdx.y; m < M; m += gridDim.y) {
+        if constexpr (sizeof(T) == 4) acc += src[(size_t)m * C + c]; else acc += __bfloat162float(src[(size_t)m * C + c]);
+    }
+    if (acc != 0.f) atomicAdd(out + c, acc);
+}
+
+__device__ __forceinline__ float gelu_new_grad(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float t = tanhf(k0 * (x + k1 * x * x * x));
+    return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x * x);
+}
+// h = gelu_new(hpre)   (forward recompute: the FC GEMM stores the pre-activation, this makes the FC2 operand)
+__global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ hpre, const int* __restrict__ M_dev, int C, __nv_bfloat16* __restrict__ h) {
+    const size_t n = (size_t)*M_dev * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        h[i] = __float2bfloat16(gelu_new(__bfloat162float(hpre[i])));
+}
+// dhpre = dh * gelu'(hpre), in place over dh
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ hpre, const int* __restrict__ M_dev, int C, __nv_bfloat16* __restrict__ dh) {
+    const size_t n = (size_t)*M_dev * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dh[i] = __float2bfloat16(__bfloat162float(dh[i]) * gelu_new_grad(__bfloat162float(hpre[i])));
+}
+
+// LayerNorm backward, one warp per row:  y = (x - mean) * rstd * g + b
+//   dx (+)= rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));   dg += dy * xhat;   db += dy      (CTA-level smem partials, then atomics)
+template <typename TDY>
+__global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const TDY* __restrict__ dy, int d, float eps,
+                              const int* __restrict__ M_dev, float* __restrict__ dx, int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ float ln_sm[];            // [2][d]
+    const int M = *M_dev;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) ln_sm[c] = 0.f;
+    __syncthreads();
+    for (int r = blockIdx.x * nwarp + warp; r < M; r += gridDim.x * nwarp) {
+        const float* xr = x + (size_t)r * d;
+        const TDY* dr = dy + (size_t)r * d;
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / d;
+        float q = 0.f;
+        for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+        const float rstd = rsqrtf(warp_sum(q) / d + eps);
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            float dyc;
+            if constexpr (sizeof(TDY) == 4) dyc = dr[c]; else dyc = __bfloat162float(dr[c]);
+            const float xh = (xr[c] - mean) * rstd, dg = dyc * gamma[c];
+            s1 += dg; s2 += dg * xh;
+            atomicAdd(ln_sm + c, dyc * xh);
+            atomicAdd(ln_sm + d + c, dyc);
+        }
+        s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
+        float* o = dx + (size_t)r * d;
+        for (int c = lane; c < d; c += 32) {
+            float dyc;
+            if constexpr (sizeof(TDY) == 4) dyc = dr[c]; else dyc = __bfloat162float(dr[c]);
+            const float xh = (xr[c] - mean) * rstd;
+            const float v = rstd * (dyc * gamma[c] - s1 - xh * s2);
+            o[c] = accumulate ? o[c] + v : v;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        if (ln_sm[c] != 0.f) atomicAdd(dgamma + c, ln_sm[c]);
+        if (ln_sm[d + c] != 0.f) atomicAdd(dbeta + c, ln_sm[d + c]);
+    }
+}
+
+// causal self-attention backward for full sequences (every slot starts at position 0), one CTA per (slot, head).
+//   P = softmax(scale * Q K^T) (causal);  O = P V;   given dO:  dV = P^T dO,  dP = dO V^T,  dS = P * (dP - rowsum(P * dP)) * scale,
+//   dQ = dS K,  dK = dS^T Q.   Query rows are walked sequentially; thread j owns keys j, j + blockDim, ...; dK / dV accumulate in shared
+//   memory (fp32 [T][64] each), dQ of a row is reduced over the threads through shared memory.  Latency/ALU-bound; attention is ~3 % of
+//   the training FLOPs at these sequence lengths, so no tensor cores here.
+constexpr int ATTB_THREADS = 128;
+__global__ void __launch_bounds__(ATTB_THREADS) attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout, RowsDev rows,
+                                                                int n_head, int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ dqkv) {
+    extern __shared__ float ab_sm[];
+    const int slot = blockIdx.x / n_head, head = blockIdx.x % n_head;
+    if (slot >= *rows.n_slots) return;
+    const int env = rows.slot_env[slot], r0 = rows.slot_row0[slot], T = rows.slot_nrow[slot];
+    float* dK = ab_sm;                       // [T][64]
+    float* dV = dK + (size_t)T * 64;         // [T][64]
+    float* qi = dV + (size_t)T * 64;         // [64]
+    float* doi = qi + 64;                    // [64]
+    float* red = doi + 64;                   // [ATTB_THREADS]
+    float* dqp = red + ATTB_THREADS;         // [4 warps][64]
+    float* prob = dqp + 4 * 64;              // [T] p_j, then ds_j
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __nv_bfloat16* Kb = kcache + ((size_t)env * n_head + head) * t_cap * 64;
+    const __nv_bfloat16* Vb = vcache + ((size_t)env * n_head + head) * t_cap * 64;
+    for (int i = tid; i < T * 128; i += ATTB_THREADS) ab_sm[i] = 0.f;
+    __syncthreads();
+    for (int i = 0; i < T; ++i) {
+        const size_t row = (size_t)(r0 + i);
+        if (tid < 64) { qi[tid] = __bfloat162float(q[row * d_model + head * 64 + tid]); doi[tid] = __bfloat162float(dout[row * d_model + head * 64 + tid]); }
+        __syncthreads();
+        // scores and dP for my keys
+        float mx = -INFINITY;
+        for (int j = tid; j <= i; j += ATTB_THREADS) {
+            const __nv_bfloat162* kj = reinterpret_cast<const __nv_bfloat162*>(Kb + (size_t)j * 64);
+            float s = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) { const float2 f = __bfloat1622float2(kj[c]); s += qi[2 * c] * f.x + qi[2 * c + 1] * f.y; }
+            s *= scale;
+            prob[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        red[tid] = mx;
+        __syncthreads();
+        for (int o = ATTB_THREADS / 2; o; o >>= 1) { if (tid < o) red[tid] = fmaxf(red[tid], red[tid + o]); __syncthreads(); }
+        mx = red[0];
+        __syncthreads();
+        float sum = 0.f;
+        for (int j = tid; j <= i; j += ATTB_THREADS) { const float p = __expf(prob[j] - mx); prob[j] = p; sum += p; }
+        red[tid] = sum;
+        __syncthreads();
+        for (int o = ATTB_THREADS / 2; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+        const float inv = 1.f / red[0];
+        __syncthreads();
+        // dP_j = dO_i . V_j;  D = sum_j p_j dP_j
+        float dsum = 0.f;
+        float dpl[4];                                   // T <= 4 * ATTB_THREADS keys per thread
+        int nk = 0;
+        for (int j = tid; j <= i; j += ATTB_THREADS, ++nk) {
+            const __nv_bfloat162* vj = reinterpret_cast<const __nv_bfloat162*>(Vb + (size_t)j * 64);
+            float dp = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) { const float2 f = __bfloat1622float2(vj[c]); dp += doi[2 * c] * f.x + doi[2 * c + 1] * f.y; }
+            const float p = prob[j] * inv;
+            prob[j] = p;
+            dpl[nk] = dp;
+            dsum += p * dp;
+        }
+        red[tid] = dsum;
+        __syncthreads();
+        for (int o = ATTB_THREADS / 2; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+        const float D = red[0];
+        // my keys: dV_j += p_j dO_i;  dK_j += ds_j q_i;  partial dQ_i += ds_j K_j
+        float dq[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) dq[c] = 0.f;
+        nk = 0;
+        for (int j = tid; j <= i; j += ATTB_THREADS, ++nk) {
+            const float p = prob[j];
+            const float ds = p * (dpl[nk] - D) * scale;
+            const __nv_bfloat162* kj = reinterpret_cast<const __nv_bfloat162*>(Kb + (size_t)j * 64);
+            float* dKj = dK + (size_t)j * 64;
+            float* dVj = dV + (size_t)j * 64;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float2 f = __bfloat1622float2(kj[c]);
+                dq[2 * c] += ds * f.x; dq[2 * c + 1] += ds * f.y;
+                dKj[2 * c] += ds * qi[2 * c]; dKj[2 * c + 1] += ds * qi[2 * c + 1];
+                dVj[2 * c] += p * doi[2 * c]; dVj[2 * c + 1] += p * doi[2 * c + 1];
+            }
+        }
+        // reduce dq over the CTA: warp shuffles, then the four warps through shared memory
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+            const float v = warp_sum(dq[c]);
+            if (lane == 0) dqp[warp * 64 + c] = v;
+        }
+        __syncthreads();
+        if (tid < 64) dqkv[row * 3 * d_model + head * 64 + tid] = __float2bfloat16(dqp[tid] + dqp[64 + tid] + dqp[128 + tid] + dqp[192 + tid]);
+        __syncthreads();
+    }
+    for (int i = tid; i < T * 64; i += ATTB_THREADS) {
+        const int j = i >> 6, c = i & 63;
+        const size_t row = (size_t)(r0 + j);
+        dqkv[row * 3 * d_model + d_model + head * 64 + c] = __float2bfloat16(dK[i]);
+        dqkv[row * 3 * d_model + 2 * d_model + head * 64 + c] = __float2bfloat16(dV[i]);
+    }
+}
+
+// dwte[tok] += dx_row, dwpe[pos] += dx_row   (one warp per row)
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, RowsDev rows, int d, float* __restrict__ dwte, float* __restrict__ dwpe) {
+    const int M = *rows.M;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps) {
+        float* a = dwte + (size_t)rows.row_tok[r] * d;
+        float* b = dwpe + (size_t)rows.row_pos[r] * d;
+        for (int c = lane; c < d; c += 32) { const float v = dx[(size_t)r * d + c]; atomicAdd(a + c, v); atomicAdd(b + c, v); }
+    }
+}
+
+// LM head: logits row (fp32, dumped by the head GEMM) -> dlogits = g * (onehot(target) - softmax) as bf16 [v_pad] (padding columns 0).
+// One CTA per scored row.
+__global__ void dlogits_kernel(const float* __restrict__ logits, int n_vocab, int v_pad, const int* __restrict__ targets, const float* __restrict__ g,
+                               const int* __restrict__ n_dev, float inv_temp, __nv_bfloat16* __restrict__ dl) {
+    __shared__ float red[256];
+    const int r = blockIdx.x;
+    __nv_bfloat16* o = dl + (size_t)r * v_pad;
+    if (r >= *n_dev) { for (int c = threadIdx.x; c < v_pad; c += blockDim.x) o[c] = __float2bfloat16(0.f); return; }
+    const float* l = logits + (size_t)r * n_vocab;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < n_vocab; c += blockDim.x) mx = fmaxf(mx, l[c] * inv_temp);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    mx = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < n_vocab; c += blockDim.x) sum += __expf(l[c] * inv_temp - mx);
+    red[threadIdx.x] = sum;
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    const float inv = 1.f / red[0], gr = g[r] * inv_temp;
+    const int tgt = targets[r];
+    for (int c = threadIdx.x; c < v_pad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < n_vocab) v = gr * ((c == tgt ? 1.f : 0.f) - __expf(l[c] * inv_temp - mx) * inv);
+        o[c] = __float2bfloat16(v);
+    }
+}
+
+// dst[idx[r]] += src[r]   (rows of d floats)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, const int* __restrict__ n_dev, int d, float* __restrict__ dst) {
+    const int n = *n_dev;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps)
+        for (int c = lane; c < d; c += 32) dst[(size_t)idx[r] * d + c] += src[(size_t)r * d + c];
+}
+
+// LinearHead value v_t = LN_f(x_t) . w + b  (fp32, as value_heads_kernel computes it):  dfx[t] += dv_t w;  dw += dv_t LN_f(x_t);  db += dv_t
+__global__ void value_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ lnf_g, const float* __restrict__ lnf_b, const float* __restrict__ w,
+                                      const float* __restrict__ dv, int d, float eps, const int* __restrict__ M_dev, float* __restrict__ dfx,
+                                      float* __restrict__ dw, float* __restrict__ db) {
+    extern __shared__ float vh_sm[];             // [d + 1]
+    const int M = *M_dev;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int c = threadIdx.x; c <= d; c += blockDim.x) vh_sm[c] = 0.f;
+    __syncthreads();
+    for (int r = blockIdx.x * nwarp + warp; r < M; r += gridDim.x * nwarp) {
+        const float g = dv[r];
+        if (g == 0.f) continue;
+        const float* xr = x + (size_t)r * d;
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / d;
+        float q = 0.f;
+        for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+        const float rstd = rsqrtf(warp_sum(q) / d + eps);
+        for (int c = lane; c < d; c += 32) {
+            atomicAdd(vh_sm + c, g * ((xr[c] - mean) * rstd * lnf_g[c] + lnf_b[c]));
+            dfx[(size_t)r * d + c] += g * w[c];
+        }
+        if (lane == 0) atomicAdd(vh_sm + d, g);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) if (vh_sm[c] != 0.f) atomicAdd(dw + c, vh_sm[c]);
+    if (threadIdx.x == 0 && vh_sm[d] != 0.f) atomicAdd(db, vh_sm[d]);
+}
+
+// out[r][c] = in[r][c] as bf16 (rows < M)
+__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ src, const int* __restrict__ M_dev, int C, __nv_bfloat16* __restrict__ dst) {
+    const size_t n = (size_t)*M_dev * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16(src[i]);
+}
+
+// ---- training state -----------------------------------------------------------------------------------------------------------
+struct TrainLayerT { __nv_bfloat16 *w_qkv, *w_proj, *w_fc, *w_fc2; };      // HF-layout ([in][out]) bf16 copies: the W operand of the dgrad GEMMs
+struct TrainDev {
+    bool ready = false;
+    int m_cap = 0, lp_cap = 0;                 // row capacity / scored-row capacity
+    std::vector<TrainLayerT> wt;
+    __nv_bfloat16* wte_t = nullptr;            // [d][v_pad] transposed embedding (dgrad of the tied LM head)
+    float* xsave = nullptr;                    // [L + 1][m_cap][d] residual stream before every layer and after the last
+    float *dx = nullptr, *dfx = nullptr;       // [m_cap][d] gradient of the residual stream / of the final-LN output
+    __nv_bfloat16 *xn1 = nullptr, *hpre = nullptr, *dxb = nullptr, *dxn = nullptr, *datt = nullptr, *dqkv = nullptr, *dh = nullptr;
+    __nv_bfloat16 *tA = nullptr, *tB = nullptr;  // transposed operands of the wgrad GEMMs: [<= max(4d, v_pad)][Mp] each
+    float* zero_bias = nullptr;                // zeros, the bias of the plain-store GEMM epilogue
+    int* consts = nullptr;                     // device ints: {d, 3d, 4d, n_vocab_rows, n_lp}
+    // LM head
+    float* lp_logits = nullptr;                // [lp_cap][n_vocab] fp32
+    __nv_bfloat16* dl = nullptr;               // [lp_cap][v_pad]
+    float* dxs = nullptr;                      // [lp_cap][d] fp32
+    int *lp_rows = nullptr, *lp_targets = nullptr;
+    float *lp_g = nullptr, *dv = nullptr;      // [lp_cap], [m_cap]
+    unsigned long long* best = nullptr;
+    uint64_t* row_key = nullptr;
+};
+
+}  // namespace lmrl
+
+using namespace lmrl;
+
+void lmrl_train_free(Gpt2Dev* g) {
+    delete g->train;
+    g->train = nullptr;
+}
+
+// bf16 HF-layout copies of tower 0's matrices (the engine stores W as [out][in]; dgrad needs [in][out] as its K-major W operand)
+static int train_refresh_weight_copies(lmrl_engine* e) {
+    Gpt2Dev& G = *e->gpt2;
+    if (!G.train || !G.train->ready) return 0;
+    TrainDev& Tr = *G.train;
+    const lmrl_gpt2_dims& D = G.dims;
+    const int d = D.d_model, ff = D.d_ff;
+    cudaStream_t st = e->stream;
+    auto tr = [&](const __nv_bfloat16* src, int rows, int cols, __nv_bfloat16* dst, const int* rows_dev) {     // [rows][cols] -> [cols][rows]
+        transpose_to_bf16_rows_kernel<__nv_bfloat16><<<dim3((rows + 31) / 32, (cols + 31) / 32), dim3(32, 8), 0, st>>>(src, rows_dev, cols, dst, rows, nullptr);
+    };
+    for (int l = 0; l < D.n_layer; ++l) {
+        const LayerDev& L = G.tw[0].layers[l];
+        tr(L.w_qkv, 3 * d, d, Tr.wt[l].w_qkv, Tr.consts + 1);
+        tr(L.w_proj, d, d, Tr.wt[l].w_proj, Tr.consts + 0);
+        tr(L.w_fc, ff, d, Tr.wt[l].w_fc, Tr.consts + 2);
+        tr(L.w_fc2, d, ff, Tr.wt[l].w_fc2, Tr.consts + 0);
+    }
+    tr(G.tw[0].wte, G.v_pad, d, Tr.wte_t, Tr.consts + 5);
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int lmrl_train_enable(lmrl_engine* e, int32_t max_rows, int32_t max_scored_rows) {
+    LMRL_CHECK(e && e->gpt2 && e->gpt2->tw[0].loaded, "lmrl_train_enable: load the policy (tower 0) first");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    if (G.train && G.train->ready) return 0;
+    const lmrl_gpt2_dims& D = G.dims;
+    const int d = D.d_model, ff = D.d_ff, L = D.n_layer;
+    LMRL_CHECK(e->cfg.max_input_length <= 384, "lmrl_train_enable: the attention backward kernel keeps dK / dV of one sequence in shared memory: max_input_length %d > 384",
+               e->cfg.max_input_length);
+    LMRL_CHECK(d % 256 == 0 && ff % 256 == 0, "lmrl_train_enable: d_model and d_ff must be multiples of 256");
+    if (!G.train) G.train = new TrainDev();
+    TrainDev& Tr = *G.train;
+    Tr.m_cap = (int)std::min<size_t>((size_t)G.m_cap, ((size_t)std::max(max_rows, 128) + 127) / 128 * 128);
+    Tr.lp_cap = (std::max(max_scored_rows, 128) + 127) / 128 * 128;
+    const size_t M = (size_t)Tr.m_cap, P = (size_t)Tr.lp_cap;
+    Tr.wt.resize(L);
+    int rc = 0;
+    for (int l = 0; l < L && !rc; ++l)
+        rc |= e->alloc(&Tr.wt[l].w_qkv, (size_t)3 * d * d) | e->alloc(&Tr.wt[l].w_proj, (size_t)d * d) | e->alloc(&Tr.wt[l].w_fc, (size_t)d * ff) | e->alloc(&Tr.wt[l].w_fc2, (size_t)d * ff);
+    const size_t t_elems = std::max((size_t)G.v_pad * P, (size_t)std::max(ff, 3 * d) * M);
+    rc |= e->alloc(&Tr.wte_t, (size_t)d * G.v_pad) | e->alloc(&Tr.xsave, (size_t)(L + 1) * M * d) | e->alloc(&Tr.dx, M * d) | e->alloc(&Tr.dfx, M * d) |
+          e->alloc(&Tr.xn1, M * d) | e->alloc(&Tr.hpre, M * ff) | e->alloc(&Tr.dxb, M * d) | e->alloc(&Tr.dxn, M * d) | e->alloc(&Tr.datt, M * d) |
+          e->alloc(&Tr.dqkv, M * 3 * d) | e->alloc(&Tr.dh, M * ff) | e->alloc(&Tr.tA, t_elems) | e->alloc(&Tr.tB, (size_t)std::max(ff, 3 * d) * M) |
+          e->alloc(&Tr.zero_bias, (size_t)std::max(ff, G.v_pad)) | e->alloc(&Tr.consts, 8) | e->alloc(&Tr.lp_logits, P * D.n_vocab) | e->alloc(&Tr.dl, P * G.v_pad) |
+          e->alloc(&Tr.dxs, P * d) | e->alloc(&Tr.lp_rows, P) | e->alloc(&Tr.lp_targets, P) | e->alloc(&Tr.lp_g, P) | e->alloc(&Tr.dv, M) | e->alloc(&Tr.best, P) |
+          e->alloc(&Tr.row_key, P);
+    if (rc) return -1;
+    const int consts[8] = {d, 3 * d, ff, (int)G.v_pad, 0, (int)G.v_pad, 0, 0};      // [4] scored rows, [6] wte rows of the gradient: per call
+    LMRL_CUDA(cudaMemcpyAsync(Tr.consts, consts, sizeof consts, cudaMemcpyHostToDevice, e->stream));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    Tr.ready = true;
+    return train_refresh_weight_copies(e);
+}
+
+}  // extern "C"
+
+// one decoder layer forward for training: like tower_layers' body, but LN1's output and the FC pre-activation are kept
+// (Tr.xn1, Tr.hpre) and the residual stream G.x ends as x_mid (with_fc2 = false) or as the layer output (true)
+static int train_layer_forward(lmrl_engine* e, int l, int n_seq, bool with_fc2) {
+    Gpt2Dev& G = *e->gpt2;
+    TrainDev& Tr = *G.train;
+    const lmrl_gpt2_dims& D = G.dims;
+    const TowerDev& T = G.tw[0];
+    const LayerDev& L = T.layers[l];
+    cudaStream_t st = e->stream;
+    const int ew = G.sm_count * 8;
+    LMRL_K(layernorm_kernel, ew, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, (const int*)nullptr, Tr.xn1, D.d_model);
+    GemmArgs a{};
+    a.A = Tr.xn1; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
+    a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
+    a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+    if (launch_gemm<EPI_QKV>(e, a, a.N, 0, (size_t)Tr.m_cap, a.N, 0)) return -1;
+    LMRL_K(attention_prefill_kernel, std::min((n_seq * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q,
+           a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f * 1.4426950408889634f, G.att);
+    GemmArgs p{};
+    p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
+    if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
+    LMRL_K(layernorm_kernel, ew, 256, 0, st, G.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, G.rows.M, (const int*)nullptr, G.xn, D.d_model);
+    GemmArgs f{};                                   // plain store of the pre-activation: the QKV epilogue with every tile a "Q" tile
+    f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = Tr.hpre; f.d_model = D.d_ff;
+    if (launch_gemm<EPI_QKV>(e, f, f.N, 0, (size_t)Tr.m_cap, f.N, 2)) return -1;
+    gelu_fwd_kernel<<<ew, 256, 0, st>>>(Tr.hpre, G.rows.M, D.d_ff, G.h);
+    if (with_fc2) {
+        GemmArgs f2{};
+        f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
+        if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, G.m_cap, f2.N, 3)) return -1;
+    }
+    e->launches += 5;
+    return 0;
+}
+
+struct LayerGrads { float *ln1_g, *ln1_b, *attn_w, *attn_b, *proj_w, *proj_b, *ln2_g, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b; };
+
+// backward of layer l.  On entry Tr.dx = dL/d(layer output); on exit Tr.dx = dL/d(layer input).  The layer has just been recomputed
+// (train_layer_forward(l, false)): G.x = x_mid, Tr.xn1, G.q / KV slab, G.att, G.xn = xn2, Tr.hpre, G.h are live.
+static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const LayerGrads& gr) {
+    Gpt2Dev& G = *e->gpt2;
+    TrainDev& Tr = *G.train;
+    const lmrl_gpt2_dims& D = G.dims;
+    const LayerDev& L = G.tw[0].layers[l];
+    const TrainLayerT& W = Tr.wt[l];
+    cudaStream_t st = e->stream;
+    const int d = D.d_model, ff = D.d_ff, ew = G.sm_count * 8;
+    const int* M_dev = G.rows.M;
+    const int* c_d = Tr.consts + 0;
+    const int* c_ff = Tr.consts + 2;
+    auto tgrid = [&](int C) { return dim3((Mp + 31) / 32, (C + 31) / 32); };
+    // dgrad: out[M][n_out] (bf16) = A[M][k_in] . W_hf[n_out][k_in]^T
+    auto dgrad = [&](const __nv_bfloat16* A, int k_in, const __nv_bfloat16* W_hf, int n_out, __nv_bfloat16* out) -> int {
+        GemmArgs g{};
+        g.A = A; g.W = W_hf; g.bias = Tr.zero_bias; g.N = n_out; g.K = k_in; g.M_dev = M_dev; g.out = out; g.d_model = n_out;
+        return launch_gemm<EPI_QKV>(e, g, n_out, 0, (size_t)Tr.m_cap, (size_t)n_out, 0);
+    };
+    // wgrad: grad[k_in][n_out] (fp32, HF layout) += Xt[k_in][Mp] . dYt[n_out][Mp]^T
+    auto wgrad = [&](const __nv_bfloat16* Xt, int k_in, const int* k_in_dev, const __nv_bfloat16* dYt, int n_out, float* grad) -> int {
+        GemmArgs g{};
+        g.A = Xt; g.W = dYt; g.bias = nullptr; g.N = n_out; g.K = Mp; g.M_dev = k_in_dev; g.resid = grad;
+        return launch_gemm<EPI_RESID>(e, g, n_out, 0, (size_t)k_in, (size_t)n_out, 1);
+    };
+    // ---- mlp.c_proj (fc2): x_out = x_mid + h . Wfc2 + b
+    transpose_to_bf16_rows_kernel<float><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.dx, M_dev, d, Tr.tB, Mp, Tr.dxb);          // dxb = bf16(dx), tB = dx^T
+    transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(ff), dim3(32, 8), 0, st>>>(G.h, M_dev, ff, Tr.tA, Mp, nullptr);  // tA = h^T
+    if (wgrad(Tr.tA, ff, c_ff, Tr.tB, d, gr.fc2_w)) return -1;
+    colsum_kernel<float><<<dim3((d + 127) / 128, 64), 128, 0, st>>>(Tr.dx, M_dev, d, gr.fc2_b);
+    if (dgrad(Tr.dxb, d, W.w_fc2, ff, Tr.dh)) return -1;                                                                  // dh = dx . Wfc2^T
+    gelu_bwd_kernel<<<ew, 256, 0, st>>>(Tr.hpre, M_dev, ff, Tr.dh);                                                       // dh := dhpre
+    // ---- mlp.c_fc: hpre = xn2 . Wfc + b
+    transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(G.xn, M_dev, d, Tr.tA, Mp, nullptr);   // tA = xn2^T
+    transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(ff), dim3(32, 8), 0, st>>>(Tr.dh, M_dev, ff, Tr.tB, Mp, nullptr); // tB = dhpre^T
+    if (wgrad(Tr.tA, d, c_d, Tr.tB, ff, gr.fc_w)) return -1;
+    colsum_kernel<__nv_bfloat16><<<dim3((ff + 127) / 128, 64), 128, 0, st>>>(Tr.dh, M_dev, ff, gr.fc_b);
+    if (dgrad(Tr.dh, ff, W.w_fc, d, Tr.dxn)) return -1;                                                                   // dxn2
+    // ---- ln_2:  dx += LN'(x_mid) dxn2
+    ln_bwd_kernel<__nv_bfloat16><<<G.sm_count * 2, 256, 2 * d * sizeof(float), st>>>(G.x, L.ln2_g, Tr.dxn, d, D.ln_eps, M_dev, Tr.dx, 1, gr.ln2_g, gr.ln2_b);
+    // ---- attn.c_proj: x_mid = x_in + att . Wproj + b
+    transpose_to_bf16_rows_kernel<float><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.dx, M_dev, d, Tr.tB, Mp, Tr.dxb);
+    transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(G.att, M_dev, d, Tr.tA, Mp, nullptr);
+    if (wgrad(Tr.tA, d, c_d, Tr.tB, d, gr.proj_w)) return -1;
+    colsum_kernel<float><<<dim3((d + 127) / 128, 64), 128, 0, st>>>(Tr.dx, M_dev, d, gr.proj_b);
+    if (dgrad(Tr.dxb, d, W.w_proj, d, Tr.datt)) return -1;
+    // ---- attention
+    {
+        const __nv_bfloat16* kc = G.tw[0].kv + (size_t)l * G.kv_layer_stride;
+        const size_t smem = ((size_t)e->cfg.max_input_length * 129 + 64 + 64 + ATTB_THREADS + 256) * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)384 * 129 + 64 + 64 + ATTB_THREADS + 256) * sizeof(float))));
+            configured = true;
+        }
+        attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.t_cap, 0.125f, Tr.dqkv);
+    }
+    // ---- attn.c_attn: qkv = xn1 . Wqkv + b
+    transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.xn1, M_dev, d, Tr.tA, Mp, nullptr);
+    transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(3 * d), dim3(32, 8), 0, st>>>(Tr.dqkv, M_dev, 3 * d, Tr.tB, Mp, nullptr);
+    if (wgrad(Tr.tA, d, c_d, Tr.tB, 3 * d, gr.attn_w)) return -1;
+    colsum_kernel<__nv_bfloat16><<<dim3((3 * d + 127) / 128, 64), 128, 0, st>>>(Tr.dqkv, M_dev, 3 * d, gr.attn_b);
+    if (dgrad(Tr.dqkv, 3 * d, W.w_qkv, d, Tr.dxn)) return -1;                                                             // dxn1
+    // ---- ln_1:  dx += LN'(x_in) dxn1
+    ln_bwd_kernel<__nv_bfloat16><<<G.sm_count * 2, 256, 2 * d * sizeof(float), st>>>(Tr.xsave + (size_t)l * Tr.m_cap * d, L.ln1_g, Tr.dxn, d, D.ln_eps, M_dev, Tr.dx, 1,
+                                                                                      gr.ln1_g, gr.ln1_b);
+    e->launches += 16;
+    LMRL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const float* dlogprob, const float* dvalue,
+                          float temperature, const lmrl_gpt2_grads* grads) {
+    LMRL_CHECK(e && e->has_gpt2 && e->gpt2->train && e->gpt2->train->ready, "lmrl_policy_grad: call lmrl_train_enable first");
+    LMRL_CHECK(tokens && n_tok && dlogprob && dvalue && grads, "lmrl_policy_grad: null argument");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    Gpt2Dev& G = *e->gpt2;
+    TrainDev& Tr = *G.train;
+    const lmrl_gpt2_dims& D = G.dims;
+    const TowerDev& T = G.tw[0];
+    const int d = D.d_model, L = D.n_layer;
+    const int max_in = e->cfg.max_input_length;
+    cudaStream_t st = e->stream;
+    // rows in env order; scored rows = positions with a non-zero upstream log-prob gradient
+    std::vector<int32_t> lp_rows, lp_targets;
+    std::vector<float> lp_g, dv;
+    int M = 0;
+    for (int i = 0; i < n; ++i) {
+        LMRL_CHECK(n_tok[i] >= 0 && n_tok[i] <= max_in && n_tok[i] <= pitch, "lmrl_policy_grad: sequence %d has %d tokens (max_input_length %d)", i, n_tok[i], max_in);
+        for (int t = 0; t < n_tok[i]; ++t) {
+            const size_t o = (size_t)i * pitch + t;
+            LMRL_CHECK(tokens[o] >= 0 && tokens[o] < G.v_pad, "lmrl_policy_grad: token id %d out of range", tokens[o]);
+            dv.push_back(dvalue[o]);
+            if (t + 1 < n_tok[i] && dlogprob[o] != 0.f) {
+                LMRL_CHECK(tokens[o + 1] < D.n_vocab, "lmrl_policy_grad: scored target id %d is a padding id", tokens[o + 1]);
+                lp_rows.push_back(M + t); lp_targets.push_back(tokens[o + 1]); lp_g.push_back(dlogprob[o]);
+            }
+        }
+        M += n_tok[i];
+    }
+    const int n_lp = (int)lp_rows.size();
+    LMRL_CHECK(M > 0 && M <= Tr.m_cap, "lmrl_policy_grad: %d rows exceed the training capacity %d (lmrl_train_enable)", M, Tr.m_cap);
+    LMRL_CHECK(n_lp <= Tr.lp_cap, "lmrl_policy_grad: %d scored tokens exceed the capacity %d (lmrl_train_enable)", n_lp, Tr.lp_cap);
+    LMRL_CHECK(n <= e->cfg.max_envs, "lmrl_policy_grad: %d sequences exceed engine capacity %d", n, e->cfg.max_envs);
+    const int Mp = (M + 63) / 64 * 64;
+    if (load_prompts(e, tokens, n_tok, pitch, n)) return -1;
+    LMRL_CUDA(cudaMemcpyAsync(Tr.dv, dv.data(), sizeof(float) * M, cudaMemcpyHostToDevice, st));
+    if (n_lp) {
+        LMRL_CUDA(cudaMemcpyAsync(Tr.lp_rows, lp_rows.data(), sizeof(int32_t) * n_lp, cudaMemcpyHostToDevice, st));
+        LMRL_CUDA(cudaMemcpyAsync(Tr.lp_targets, lp_targets.data(), sizeof(int32_t) * n_lp, cudaMemcpyHostToDevice, st));
+        LMRL_CUDA(cudaMemcpyAsync(Tr.lp_g, lp_g.data(), sizeof(float) * n_lp, cudaMemcpyHostToDevice, st));
+    }
+    const int call_consts[3] = {n_lp, (int)G.v_pad, grads->n_vocab_rows};
+    LMRL_CHECK(grads->n_vocab_rows > 0 && grads->n_vocab_rows <= G.v_pad, "lmrl_policy_grad: grads->n_vocab_rows %d out of range", grads->n_vocab_rows);
+    LMRL_CHECK(!grads->vh_w || G.vh[0].has_lin, "lmrl_policy_grad: value-head gradients requested but no LinearHead is loaded in head set 0");
+    LMRL_CUDA(cudaMemcpyAsync(Tr.consts + 4, call_consts, sizeof call_consts, cudaMemcpyHostToDevice, st));
+    LMRL_CUDA(cudaStreamSynchronize(st));                      // host vectors die at return; the rest is enqueued asynchronously
+    const int saved_profile = e->profile;
+    e->profile = 0;
+    struct Restore { lmrl_engine* e; int p; ~Restore() { e->profile = p; } } restore{e, saved_profile};
+    G.cur = &G.lane[0];
+    e->cur_pass_slot = -1;
+    e->cur_mode = 0;
+    const int ew = G.sm_count * 8;
+    // ---- forward, saving the residual stream before every layer
+    LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen);
+    LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, n, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
+    LMRL_K(fill_prefill_rows_kernel, (n * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
+    LMRL_K(embed_kernel, ew, 256, 0, st, T.wte, T.wpe, d, G.rows, G.x);
+    const size_t xbytes = sizeof(float) * (size_t)M * d, xstride = (size_t)Tr.m_cap * d;
+    for (int l = 0; l < L; ++l) {
+        LMRL_CUDA(cudaMemcpyAsync(Tr.xsave + (size_t)l * xstride, G.x, xbytes, cudaMemcpyDeviceToDevice, st));
+        if (train_layer_forward(e, l, n, true)) return -1;
+    }
+    LMRL_CUDA(cudaMemcpyAsync(Tr.xsave + (size_t)L * xstride, G.x, xbytes, cudaMemcpyDeviceToDevice, st));
+    LMRL_CUDA(cudaMemsetAsync(Tr.dfx, 0, xbytes, st));
+    // ---- tied LM head: dlogits = g (onehot - softmax) on the scored rows
+    if (n_lp) {
+        const int* n_lp_dev = Tr.consts + 4;
+        const int Kp = (n_lp + 63) / 64 * 64, n_lp_pad = (n_lp + 127) / 128 * 128;
+        LMRL_K(layernorm_kernel, ew, 256, 0, st, G.x, T.lnf_g, T.lnf_b, d, D.ln_eps, n_lp_dev, (const int*)Tr.lp_rows, Tr.dxn, d);       // dxn := LN_f of the scored rows
+        LMRL_CUDA(cudaMemsetAsync(Tr.best, 0, sizeof(unsigned long long) * n_lp, st));
+        GemmArgs h{};
+        h.A = Tr.dxn; h.W = T.wte; h.bias = nullptr; h.N = G.v_pad; h.K = d; h.M_dev = n_lp_dev; h.best = Tr.best; h.row_key = Tr.row_key; h.inv_temp = 1.0f;
+        h.do_sample = 0; h.n_vocab = D.n_vocab; h.logits_out = Tr.lp_logits;
+        if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, (size_t)Tr.m_cap, G.v_pad, 4)) return -1;
+        const float inv_temp = 1.0f / (temperature > 0.f ? temperature : 1.0f);
+        dlogits_kernel<<<n_lp_pad, 256, 0, st>>>(Tr.lp_logits, D.n_vocab, G.v_pad, Tr.lp_targets, Tr.lp_g, n_lp_dev, inv_temp, Tr.dl);
+        // dgrad: d(LN_f out)[scored rows] = dl . wte      (fp32, then scattered into dfx)
+        LMRL_CUDA(cudaMemsetAsync(Tr.dxs, 0, sizeof(float) * (size_t)n_lp_pad * d, st));
+        GemmArgs g{};
+        g.A = Tr.dl; g.W = Tr.wte_t; g.bias = nullptr; g.N = d; g.K = G.v_pad; g.M_dev = n_lp_dev; g.resid = Tr.dxs;
+        if (launch_gemm<EPI_RESID>(e, g, d, 0, (size_t)Tr.lp_cap, (size_t)d, 1)) return -1;
+        scatter_add_rows_kernel<<<ew, 256, 0, st>>>(Tr.dxs, Tr.lp_rows, n_lp_dev, d, Tr.dfx);
+        // wgrad: dwte += dl^T . LN_f(x)
+        transpose_to_bf16_rows_kernel<__nv_bfloat16><<<dim3((Kp + 31) / 32, (G.v_pad + 31) / 32), dim3(32, 8), 0, st>>>(Tr.dl, n_lp_dev, G.v_pad, Tr.tA, Kp, nullptr);
+        transpose_to_bf16_rows_kernel<__nv_bfloat16><<<dim3((Kp + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, st>>>(Tr.dxn, n_lp_dev, d, Tr.tB, Kp, nullptr);
+        GemmArgs wg{};
+        wg.A = Tr.tA; wg.W = Tr.tB; wg.bias = nullptr; wg.N = d; wg.K = Kp; wg.M_dev = Tr.consts + 6; wg.resid = grads->wte;
+        if (launch_gemm<EPI_RESID>(e, wg, d, 0, (size_t)grads->n_vocab_rows, (size_t)d, 1)) return -1;
+    }
+    // ---- value head (LinearHead on the fp32 final LayerNorm), then ln_f
+    if (grads->vh_w)
+        value_head_bwd_kernel<<<G.sm_count * 2, 256, (d + 1) * sizeof(float), st>>>(G.x, T.lnf_g, T.lnf_b, G.vh[0].lin_w, Tr.dv, d, D.ln_eps, G.rows.M, Tr.dfx,
+                                                                                     grads->vh_w, grads->vh_b);
+    ln_bwd_kernel<float><<<G.sm_count * 2, 256, 2 * d * sizeof(float), st>>>(G.x, T.lnf_g, Tr.dfx, d, D.ln_eps, G.rows.M, Tr.dx, 0, grads->lnf_g, grads->lnf_b);
+    // ---- decoder layers, last to first: recompute the layer from its saved input, then its backward
+    for (int l = L - 1; l >= 0; --l) {
+        LMRL_CUDA(cudaMemcpyAsync(G.x, Tr.xsave + (size_t)l * xstride, xbytes, cudaMemcpyDeviceToDevice, st));
+        if (train_layer_forward(e, l, n, false)) return -1;
+        const LayerGrads gr{grads->ln1_g[l], grads->ln1_b[l], grads->attn_w[l], grads->attn_b[l], grads->proj_w[l], grads->proj_b[l],
+                            grads->ln2_g[l], grads->ln2_b[l], grads->fc_w[l], grads->fc_b[l], grads->fc2_w[l], grads->fc2_b[l]};
+        if (train_layer_backward(e, l, n, Mp, gr)) return -1;
+    }
+    embed_bwd_kernel<<<ew, 256, 0, st>>>(Tr.dx, G.rows, d, grads->wte, grads->wpe);
+    LMRL_CUDA(cudaGetLastError());
+    LMRL_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -94,12 +94,42 @@ def block_ppo_data(datas: List[PPOData], pad_token_id: int, max_length: int) -> 
         old_returns=_block_right([d.old_returns for d in datas], 0.0, max_length - 1, np.float32))
 
 
+def ppo_loss_grads(attention_mask, logprobs, values, should_take_action, old_logprobs, old_values, old_advantages, old_returns, *,
+                   cliprange_value: float, cliprange: float, value_loss_coef: float):
+    """``ppo_loss_fn`` (ppo/base_interface.py:71-142) and its closed-form derivative with respect to the per-token ``logprobs`` and
+    ``values`` (what ``jax.value_and_grad`` propagates into the networks, ppo/gpt2/interface.py:106-164).  All arrays [b, t-1].
+    Returns (loss, logs, dL/dlogprobs, dL/dvalues)."""
+    f = lambda a: np.asarray(a, dtype=np.float64)  # noqa: E731
+    lp, v, olp, ov, adv, ret = map(f, (logprobs, values, old_logprobs, old_values, old_advantages, old_returns))
+    mask = np.asarray(should_take_action, dtype=np.float64) * f(attention_mask)
+    n = mask.sum()
+    vc = np.clip(v, ov - cliprange_value, ov + cliprange_value)
+    vf1, vf2 = (v - ret) ** 2, (vc - ret) ** 2
+    vf_loss = 0.5 * (np.maximum(vf1, vf2) * mask).sum() / n
+    inside_v = (v >= ov - cliprange_value) & (v <= ov + cliprange_value)
+    dvf = np.where(vf2 > vf1, 2.0 * (vc - ret) * inside_v, 2.0 * (v - ret))
+    dvalues = value_loss_coef * 0.5 * dvf * mask / n
+    log_ratio = (lp - olp) * mask
+    ratio = np.exp(log_ratio)
+    clipped = np.clip(ratio, 1.0 - cliprange, 1.0 + cliprange)
+    pg1, pg2 = -adv * ratio, -adv * clipped
+    pg_loss = (np.maximum(pg1, pg2) * mask).sum() / n
+    inside_r = (ratio >= 1.0 - cliprange) & (ratio <= 1.0 + cliprange)
+    dpg = np.where(pg2 > pg1, -adv * ratio * inside_r, -adv * ratio) * mask           # d ratio / d logprob = ratio * mask
+    dlogprobs = dpg * mask / n
+    loss = pg_loss + value_loss_coef * vf_loss
+    logs = dict(total_loss=loss, policy_loss=pg_loss, value_loss=vf_loss, approx_kl=((ratio - 1) - log_ratio).sum() / n,
+                policy_clipfrac=((pg2 > pg1) * mask).sum() / n, value_clipfrac=((vf2 > vf1) * mask).sum() / n, ratio=(ratio * mask).sum() / n)
+    return float(loss), {k: float(x) for k, x in logs.items()}, dlogprobs.astype(np.float32), dvalues.astype(np.float32)
+
+
 class TorchPPOTrain:
     """fp32 master weights on the GPU as torch tensors (HF GPT-2 layout, the same dict layout as ``init_gpt2_params``) + LinearHead."""
 
     def __init__(self, engine: Engine, policy_params: Dict, value_head_params: Dict, config: Optional[GPT2Config] = None, *, lr: float = 1e-5,
                  weight_decay: float = 0.0, cliprange_value: float = 0.2, cliprange: float = 0.2, value_loss_coef: float = 1.0,
-                 pad_token_id: Optional[int] = None, activation_dtype: str = "bf16"):
+                 pad_token_id: Optional[int] = None, activation_dtype: str = "bf16", backward: str = "torch", max_rows: int = 16384,
+                 max_scored_rows: int = 8192):
         import torch
         self.torch = torch
         self._lmrl_engine = engine                      # None: no rollout engine attached (CPU tests of the update itself)
@@ -137,6 +167,13 @@ class TorchPPOTrain:
             self.opt = torch.optim.AdamW([dict(params=[self.flat[0]], weight_decay=weight_decay), dict(params=[self.flat[1]], weight_decay=0.0)],
                                          lr=lr, betas=self.betas, eps=self.eps)
         self.steps = 0
+        # backward = "b200": gradients from the engine's hand-written backward pass (csrc/train_kernels.inl) instead of torch autograd
+        self.backward = backward
+        if backward == "b200":
+            assert engine is not None, "the hand-written backward pass runs on the engine"
+            self.gflat = [torch.zeros_like(f.data) for f in self.flat]
+            self.push_to_engine()
+            check(engine.lib.lmrl_train_enable(engine.handle, int(max_rows), int(max_scored_rows)))
 
     def _view(self, name):
         grp, o, shape = self._views[name]
@@ -217,10 +254,16 @@ class TorchPPOTrain:
         (library path), a summing all-reduce of the two flat gradient buffers over the ranks, then AdamW — the hand-written streaming
         kernel ``lmrl_adamw_dev`` when an engine is attached, ``torch.optim.AdamW`` otherwise (CPU tests)."""
         torch = self.torch
-        for f in self.flat:
-            f.grad = None
-        loss, logs = self.loss(batch)
-        loss.backward()
+        if self.backward == "b200":
+            loss, logs = self._b200_grads(batch)
+            for f, g in zip(self.flat, self.gflat):
+                f.grad = g
+        else:
+            for f in self.flat:
+                f.grad = None
+            loss, logs = self.loss(batch)
+            loss.backward()
+            loss = float(loss.detach())
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             world = torch.distributed.get_world_size()
@@ -239,7 +282,49 @@ class TorchPPOTrain:
                 for f in self.flat:
                     f.grad /= world
             self.opt.step()
-        return float(loss.detach()), {k: float(v) for k, v in logs.items()}
+        if self.backward == "b200":
+            self.push_to_engine()           # the next forward / backward (and the next rollout) run on the updated weights
+        return float(loss), {k: float(v) for k, v in logs.items()}
+
+    def _grad_view(self, name):
+        grp, o, shape = self._views[name]
+        return self.gflat[grp][o:o + int(np.prod(shape))]
+
+    def _b200_grads(self, batch: Dict[str, np.ndarray]):
+        """Forward (token log-probs + values) and backward on the engine: ``lmrl_forward_host`` -> ``ppo_loss_grads`` (closed form) ->
+        ``lmrl_policy_grad_host`` accumulating into the flat gradient buffers."""
+        from .value_inference import forward_tokens
+        e = self._lmrl_engine
+        ids = np.asarray(batch["input_ids"])
+        real = ids != self.pad_token_id
+        lens = real.sum(axis=1).astype(np.int32)
+        seqs = [ids[i, :lens[i]] for i in range(ids.shape[0])]
+        T = ids.shape[1]
+        pitch = max(8, T)
+        fw = forward_tokens(e, 0, 0, seqs, logprobs=True, v=True, pitch=pitch)
+        loss, logs, dlp, dv = ppo_loss_grads(real[:, 1:].astype(np.float32), fw["logprobs"][:, :T - 1], fw["v"][:, :T - 1], batch["should_take_action"],
+                                             batch["old_logprobs"], batch["old_values"], batch["old_advantages"], batch["old_returns"],
+                                             cliprange_value=self.cliprange_value, cliprange=self.cliprange, value_loss_coef=self.value_loss_coef)
+        toks = np.zeros((ids.shape[0], pitch), np.int32)
+        toks[:, :T] = np.where(real, ids, 0)
+        dlp_p, dv_p = np.zeros((ids.shape[0], pitch), np.float32), np.zeros((ids.shape[0], pitch), np.float32)
+        dlp_p[:, :T - 1], dv_p[:, :T - 1] = dlp, dv
+        for g in self.gflat:
+            g.zero_()
+        self.torch.cuda.synchronize(self.device)
+        L = self.config.n_layer
+        keep = []
+        fp = lambda name: C.cast(C.c_void_p(self._grad_view(name).data_ptr()), _lib._PF)  # noqa: E731
+        gs = _lib.lmrl_gpt2_grads()
+        gs.wte, gs.n_vocab_rows, gs.wpe = fp("wte"), int(self._views["wte"][2][0]), fp("wpe")
+        gs.lnf_g, gs.lnf_b, gs.vh_w, gs.vh_b = fp("lnf_g"), fp("lnf_b"), fp("vh_w"), fp("vh_b")
+        for key in _LAYER_KEYS:
+            ptrs = (_lib._PF * L)(*[fp(f"h{i}.{key}") for i in range(L)])
+            keep.append(ptrs)
+            setattr(gs, key, C.cast(ptrs, _lib._PPF))
+        check(e.lib.lmrl_policy_grad_host(e.handle, toks.ctypes.data, lens.ctypes.data, pitch, ids.shape[0], dlp_p.ctypes.data, dv_p.ctypes.data,
+                                          C.c_float(1.0), C.byref(gs)))
+        return loss, logs
 
     # ---- weight hand-over to the rollout engine (device to device; policy.set_params of ppo/train.py:244, 438) -------
     def push_to_engine(self, tower: int = 0, head_set: int = 0) -> None:

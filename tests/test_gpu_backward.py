@@ -1,0 +1,83 @@
+"""The hand-written backward pass of the policy + value head (csrc/train_kernels.inl, lmrl_policy_grad_host) against torch autograd of
+the same network in fp32 on the GPU (the library path of ppo_train.TorchPPOTrain, itself checked against the oracle GPT-2 on the CPU):
+every parameter gradient of a PPO minibatch — embeddings, all four matrices + biases and both LayerNorms of every layer, ln_f, the tied
+LM head (through wte) and the LinearHead value head.  The engine computes with bf16 operands and fp32 accumulation, so the bar is a
+relative L2 error <= 5e-2 and a cosine >= 0.998 per tensor (weights are rounded to bf16 first so both sides hold the same numbers)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make_batch(rng, cfg, pad, lp_fn, b=12, t=48):
+    ids = np.full((b, t), pad, np.int32)
+    sta = np.zeros((b, t - 1), bool)
+    for i in range(b):
+        n = int(rng.integers(6, t + 1))
+        ids[i, :n] = rng.integers(0, cfg.n_vocab, n)
+        sta[i, 1:n - 1] = rng.random(n - 2) < 0.5
+    sta[0, 1] = True
+    f = lambda s: (s * rng.standard_normal((b, t - 1))).astype(np.float32)  # noqa: E731
+    return dict(input_ids=ids, should_take_action=sta, old_logprobs=None, old_values=f(0.3), old_advantages=f(1.0), old_returns=f(0.5))
+
+
+def test_handwritten_backward_matches_autograd():
+    import torch
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200 import ppo_train as T
+    from lmrl_gym_b200.value_inference import forward_tokens
+    from oracle.gpt2 import bf16_round
+    tok = ByteTokenizer.synthetic()
+    cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+    rng = np.random.default_rng(0)
+    params = init_gpt2_params(cfg, seed=3)
+    for k in ("wte", "wpe"):
+        params[k] = bf16_round(params[k])
+    for L in params["layers"]:
+        for k in ("attn_w", "proj_w", "fc_w", "fc2_w"):
+            L[k] = bf16_round(L[k])
+        for k in ("attn_b", "proj_b", "fc_b", "fc2_b", "ln1_b", "ln2_b"):
+            L[k] = (0.02 * rng.standard_normal(L[k].shape)).astype(np.float32)
+        for k in ("ln1_g", "ln2_g"):
+            L[k] = (1.0 + 0.05 * rng.standard_normal(L[k].shape)).astype(np.float32)
+    lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 16).astype(np.float32), bias=np.asarray([0.1], np.float32)))
+    eng = Engine(max_envs=32, max_input_length=64, max_new_tokens=4, tokenizer=tok)
+    B200GPT2Policy(eng, params, cfg)
+    ref = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch")
+    b2 = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", max_rows=2048, max_scored_rows=1024)
+    batch = make_batch(rng, cfg, tok.pad_token_id, None)
+    # old log-probs near the current ones so that both the clipped and the unclipped branch of the policy loss are taken
+    ids = batch["input_ids"]
+    lens = (ids != tok.pad_token_id).sum(1)
+    cur = forward_tokens(eng, 0, 0, [ids[i, :lens[i]] for i in range(ids.shape[0])], logprobs=True, pitch=ids.shape[1])["logprobs"][:, :ids.shape[1] - 1]
+    batch["old_logprobs"] = (cur + 0.25 * rng.standard_normal(cur.shape)).astype(np.float32)
+    for f in ref.flat:
+        f.grad = None
+    loss_ref, logs_ref = ref.loss(batch)
+    loss_ref.backward()
+    loss_b, logs_b = b2._b200_grads(batch)
+    torch.cuda.synchronize()
+    assert abs(float(loss_ref.detach()) - loss_b) <= 2e-2 * max(1.0, abs(loss_b)), (float(loss_ref.detach()), loss_b)
+    assert 0.05 < logs_b["policy_clipfrac"] < 0.95
+    worst = []
+    for name in [n for grp in ref._names for n in grp]:
+        grp, o, shape = ref._views[name]
+        n = int(np.prod(shape))
+        g_ref = ref.flat[grp].grad[o:o + n].double().cpu().numpy()
+        g_b = b2.gflat[grp][o:o + n].double().cpu().numpy()
+        if name == "wte":                       # only rows of tokens that occur (or are scored) carry signal worth comparing: all rows here
+            pass
+        nr = np.linalg.norm(g_ref)
+        rel = np.linalg.norm(g_b - g_ref) / max(nr, 1e-12)
+        cos = float(g_b @ g_ref / max(np.linalg.norm(g_b) * nr, 1e-20))
+        worst.append((rel, cos, name, nr))
+    worst.sort(reverse=True)
+    print("hand-written backward vs autograd (rel L2 err, cosine, tensor, |g|):")
+    for rel, cos, name, nr in worst[:8]:
+        print(f"  {rel:.4f}  {cos:.5f}  {name:12s} {nr:.3e}")
+    for rel, cos, name, nr in worst:
+        assert nr > 0, name
+        assert rel <= 5e-2 and cos >= 0.998, (name, rel, cos)
+    eng.close()

@@ -119,3 +119,30 @@ def test_two_rank_gloo_allreduce_keeps_replicas_identical(tmp_path):
         single.step(make_batch(np.random.default_rng(100 + 10 * s)))
     c = torch.cat([p.detach().reshape(-1) for _, p in single.named_parameters()]).numpy()
     assert np.abs(a - c).max() > 0          # the other rank's gradients really entered the update
+
+
+def test_ppo_loss_grads_match_autograd():
+    """ppo_train.ppo_loss_grads (the closed-form derivative handed to the engine's backward pass) against torch autograd of the same
+    ppo_loss_fn expression, and its loss value against the reference-pinned oracle."""
+    rng = np.random.default_rng(0)
+    b, t = 5, 11
+    am = (rng.random((b, t)) < 0.9).astype(np.float32)
+    sta = rng.random((b, t)) < 0.6
+    lp = -np.abs(rng.standard_normal((b, t))).astype(np.float32)
+    olp = (lp + 0.3 * rng.standard_normal((b, t))).astype(np.float32)
+    v, ov, adv, ret = (rng.standard_normal((b, t)).astype(np.float32) for _ in range(4))
+    loss, logs, dlp, dv = T.ppo_loss_grads(am, lp, v, sta, olp, ov, adv, ret, cliprange_value=0.2, cliprange=0.2, value_loss_coef=0.7)
+    o_loss, _ = O.ppo_loss(am, lp, v, sta, olp, ov, adv, ret, cliprange_value=0.2, cliprange=0.2, value_loss_coef=0.7)
+    assert abs(loss - float(o_loss)) < 1e-5
+    LP = torch.tensor(lp, dtype=torch.float64, requires_grad=True)
+    V = torch.tensor(v, dtype=torch.float64, requires_grad=True)
+    m = torch.tensor(sta.astype(np.float64) * am)
+    n = m.sum()
+    OV, RET, ADV, OLP = (torch.tensor(x, dtype=torch.float64) for x in (ov, ret, adv, olp))
+    vc = torch.maximum(torch.minimum(V, OV + 0.2), OV - 0.2)
+    vf = 0.5 * (torch.maximum((V - RET) ** 2, (vc - RET) ** 2) * m).sum() / n
+    r = torch.exp((LP - OLP) * m)
+    pg = (torch.maximum(-ADV * r, -ADV * torch.clamp(r, 0.8, 1.2)) * m).sum() / n
+    (pg + 0.7 * vf).backward()
+    assert np.abs(LP.grad.numpy() - dlp).max() < 1e-7 and np.abs(V.grad.numpy() - dv).max() < 1e-7
+    assert np.abs(dlp).max() > 0 and np.abs(dv).max() > 0
