@@ -2,7 +2,7 @@
 the same network in fp32 on the GPU (the library path of ppo_train.TorchPPOTrain, itself checked against the oracle GPT-2 on the CPU):
 every parameter gradient of a PPO minibatch — embeddings, all four matrices + biases and both LayerNorms of every layer, ln_f, the tied
 LM head (through wte) and the LinearHead value head.  The engine computes with bf16 operands and fp32 accumulation, so the bar is a
-relative L2 error <= 5e-2 and a cosine >= 0.998 per tensor (weights are rounded to bf16 first so both sides hold the same numbers)."""
+relative L2 error <= 2e-2 and a cosine >= 0.9995 per tensor (measured: worst 4e-3 / 0.99999) (weights are rounded to bf16 first so both sides hold the same numbers)."""
 import numpy as np
 import pytest
 
@@ -79,5 +79,61 @@ def test_handwritten_backward_matches_autograd():
         print(f"  {rel:.4f}  {cos:.5f}  {name:12s} {nr:.3e}")
     for rel, cos, name, nr in worst:
         assert nr > 0, name
-        assert rel <= 5e-2 and cos >= 0.998, (name, rel, cos)
+        assert rel <= 2e-2 and cos >= 0.9995, (name, rel, cos)
+    eng.close()
+
+
+def test_handwritten_backward_gpt2_small_and_training_step():
+    """GPT-2-small shapes (12 layers, d = 768), a PPO minibatch of 32 sequences: gradients vs autograd (bf16-autocast library path is the
+    comparison here, so the bar is looser: cosine >= 0.99 per tensor), then three optimizer steps on the hand-written path lower the loss
+    and leave the engine's rollout policy on the updated weights."""
+    import time
+    import torch
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200 import ppo_train as T
+    from lmrl_gym_b200.value_inference import forward_tokens
+    tok = ByteTokenizer.synthetic()
+    cfg = GPT2Config.small()
+    rng = np.random.default_rng(1)
+    params = init_gpt2_params(cfg, seed=5)
+    lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 28).astype(np.float32), bias=np.zeros(1, np.float32)))
+    eng = Engine(max_envs=64, max_input_length=128, max_new_tokens=6, tokenizer=tok)
+    pol = B200GPT2Policy(eng, params, cfg)
+    ref = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch")
+    b2 = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-4, max_rows=8192, max_scored_rows=4096)
+    batch = make_batch(rng, cfg, tok.pad_token_id, None, b=32, t=128)
+    ids = batch["input_ids"]
+    lens = (ids != tok.pad_token_id).sum(1)
+    cur = forward_tokens(eng, 0, 0, [ids[i, :lens[i]] for i in range(ids.shape[0])], logprobs=True, pitch=ids.shape[1])["logprobs"][:, :ids.shape[1] - 1]
+    batch["old_logprobs"] = (cur + 0.25 * rng.standard_normal(cur.shape)).astype(np.float32)
+    for f in ref.flat:
+        f.grad = None
+    loss_ref, _ = ref.loss(batch)
+    loss_ref.backward()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss_b, _ = b2._b200_grads(batch)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    worst = (0.0, 1.0, "")
+    for name in [n for grp in ref._names for n in grp]:
+        grp, o, shape = ref._views[name]
+        n = int(np.prod(shape))
+        g_ref = ref.flat[grp].grad[o:o + n].double()
+        g_b = b2.gflat[grp][o:o + n].double()
+        rel = float((g_b - g_ref).norm() / g_ref.norm().clamp_min(1e-12))
+        cos = float((g_b @ g_ref) / (g_b.norm() * g_ref.norm()).clamp_min(1e-20))
+        if rel > worst[0]:
+            worst = (rel, cos, name)
+        assert cos >= 0.99 and rel <= 0.1, (name, rel, cos)
+    print(f"GPT-2-small backward: worst tensor {worst[2]} rel {worst[0]:.4f} cos {worst[1]:.5f}; forward + loss + backward of {int(lens.sum())} rows in {dt * 1e3:.1f} ms")
+    before = pol.logits([ids[0, :8].tolist()])
+    l0 = b2.step(batch)[0]
+    for _ in range(2):
+        l1 = b2.step(batch)[0]
+    assert l1 < l0
+    after = pol.logits([ids[0, :8].tolist()])
+    assert np.abs(after - before).max() > 1e-4          # the rollout policy runs on the trained weights
     eng.close()
