@@ -4,17 +4,23 @@ Mirrors the data flow of ``LLM_RL/algorithms/ppo/train.py::train_loop`` (:138-47
 ``llm_rl_scripts/wordle/ppo/train_ppo_gpt2.py`` (:297-353): every round
 
     text_env_eval(env, policy)                        -> fused rollout on the engine (csrc/gpt2_engine.inl)
-    episodes -> TextTrajectoryChain                   -> train_ppo_gpt2.py:307-335 (one trajectory per episode, reward on actions)
-    get_ppo_data_from_text_trajectory_chain           -> device forward of policy / initial policy / value head + device GAE (ppo.py)
-    kl_controller.update(mean_kl, train_bsize)        -> :352-353
-    epochs x minibatches of PPOTrain.step             -> ** LIBRARY PATH, see below **
+    episodes -> token trajectory chains               -> exported by the device (lmrl_rollout_chains_host); text path as fall-back
+    get_ppo_data_from_token_trajectory_chain          -> device forward of policy / initial policy / value head + device GAE (ppo.py)
+    kl_controller.update(mean_kl, train_bsize)        -> train_ppo_gpt2.py:352-353
+    epochs x minibatches of PPOTrain.step             -> ``TorchPPOTrain.step`` below
     policy.set_params(new params)                     -> ppo/train.py:244, 438 (device-to-device weight hand-over)
 
-THE GRADIENT STEP IS NOT HAND-WRITTEN CUDA.  ``TorchPPOTrain.step`` restates ``GPT2PPOTrain._step`` (ppo/gpt2/interface.py:72-211:
-policy forward, LinearHead values, ``ppo_loss_fn``, AdamW(b1 0.9, b2 0.95, eps 1e-8, weight decay masked off LayerNorm and
-biases, train_ppo_gpt2.py:144-165)) with torch autograd on torch/cuBLAS kernels, and averages gradients over ranks with
-``torch.distributed.all_reduce`` (NCCL) where the reference relies on pjit data parallelism.  It exists so the PPO loop runs end to end
-on the engine; it is the baseline a hand-written backward would have to beat, and no performance claim is made for it.
+The gradient step restates ``GPT2PPOTrain._step`` (ppo/gpt2/interface.py:72-211: policy forward, LinearHead values, ``ppo_loss_fn``,
+AdamW(b1 0.9, b2 0.95, eps 1e-8, weight decay masked off LayerNorm and biases, train_ppo_gpt2.py:144-165)) in two interchangeable ways:
+
+  backward="b200"   HAND-WRITTEN: forward on the engine (``lmrl_forward_host``), the closed-form derivative of ``ppo_loss_fn`` with
+                    respect to the per-token log-probs / values (``ppo_loss_grads``), the engine's backward pass through LM head, value
+                    head and decoder stack (``lmrl_policy_grad_host``, csrc/train_kernels.inl: tcgen05 dgrad / wgrad GEMMs, LayerNorm /
+                    GeLU / attention backward kernels), ``lmrl_adamw_dev``.  Checked against autograd in tests/test_gpu_backward.py.
+  backward="torch"  LIBRARY path: torch autograd on torch/cuBLAS kernels — the comparison baseline (and the CPU test vehicle).
+
+Gradients are summed over ranks with ``torch.distributed.all_reduce`` (NCCL; plumbing) where the reference relies on pjit data parallelism.
+The class keeps its historical name; fp32 master weights live in torch tensors either way.
 """
 from __future__ import annotations
 

@@ -5,8 +5,8 @@ reported SEPARATELY.  Not the headline bench.
     python scripts/ppo_round_bench.py [--rollouts 4096] [--rounds 2] [--train-bsize 32] [--max-updates 32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/ppo_round_bench.py ...
 
-rollout and PPO data run on the engine (hand-written CUDA); the update is the torch-autograd LIBRARY path of lmrl_gym_b200/ppo_train.py
-with an NCCL all-reduce of the fp32 gradients when launched under torchrun.  Prints one JSON line (rank 0).
+rollout, PPO data AND the gradient step run on the engine (hand-written CUDA: --backward b200, the default); --backward torch selects the
+torch-autograd library path for comparison.  Under torchrun the fp32 gradients are all-reduced over NCCL.  Prints one JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=2)
     ap.add_argument("--train-bsize", type=int, default=32)
     ap.add_argument("--max-updates", type=int, default=32, help="cap on optimizer steps per round (the reference's max_steps), to bound the run")
+    ap.add_argument("--backward", choices=("b200", "torch"), default="b200", help="b200 = hand-written backward pass (csrc/train_kernels.inl); torch = autograd library path")
     ap.add_argument("--letters", action="store_true", help="steer the LM head to letter tokens (token shape of a trained policy)")
     args = ap.parse_args()
     import torch
@@ -52,7 +53,7 @@ def main():
     env = B200WordleEnv(eng, "wordle_official.txt", bad_word_reward=-10.0)          # train_ppo_gpt2.py:211
     pol = B200GPT2Policy(eng, params, cfg, seed=rank)
     inf = P.B200PPOInference(eng, None, lin, initial_policy_params=params, config=cfg, pad_token_id=tok.pad_token_id)
-    trainer = T.TorchPPOTrain(eng, params, lin, cfg, lr=1e-5, pad_token_id=tok.pad_token_id)
+    trainer = T.TorchPPOTrain(eng, params, lin, cfg, lr=1e-5, pad_token_id=tok.pad_token_id, backward=args.backward, max_rows=args.train_bsize * 264, max_scored_rows=args.train_bsize * 264)
     seeds = seed_generator(0)
     for _ in range(rank * B * args.rounds):          # contiguous shards of one seed stream
         next(seeds)
@@ -72,7 +73,8 @@ def main():
         print(json.dumps(dict(workload="PPO round: Wordle x GPT-2-small, %d rollouts/GPU, train_bsize %d, %d optimizer steps/round (capped)" % (B, args.train_bsize, upd),
                               n_gpus=world, rounds=logs, env_steps_per_s_rollout=round(world * last["env_steps"] / last["rollout_s"], 1),
                               update_s_per_step=round(last["update_s"] / max(upd, 1), 4),
-                              update_impl="torch autograd (library path) + NCCL all-reduce" if world > 1 else "torch autograd (library path)")))
+                              update_impl=("hand-written backward (train_kernels.inl) + lmrl_adamw_dev" if args.backward == "b200" else "torch autograd (library path) + lmrl_adamw_dev") +
+                              (" + NCCL all-reduce" if world > 1 else ""))))
     eng.close()
     if world > 1:
         dist.destroy_process_group()

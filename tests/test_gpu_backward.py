@@ -85,8 +85,8 @@ def test_handwritten_backward_matches_autograd():
 
 def test_handwritten_backward_gpt2_small_and_training_step():
     """GPT-2-small shapes (12 layers, d = 768), a PPO minibatch of 32 sequences: gradients vs autograd (bf16-autocast library path is the
-    comparison here, so the bar is looser: cosine >= 0.99 per tensor), then three optimizer steps on the hand-written path lower the loss
-    and leave the engine's rollout policy on the updated weights."""
+    comparison here, so the bar is looser: cosine >= 0.99 per tensor), then three optimizer steps on the hand-written path track the
+    library path's loss and parameters and leave the engine's rollout policy on the updated weights."""
     import time
     import torch
     from lmrl_gym_b200.engine import Engine
@@ -101,8 +101,8 @@ def test_handwritten_backward_gpt2_small_and_training_step():
     lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 28).astype(np.float32), bias=np.zeros(1, np.float32)))
     eng = Engine(max_envs=64, max_input_length=128, max_new_tokens=6, tokenizer=tok)
     pol = B200GPT2Policy(eng, params, cfg)
-    ref = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch")
-    b2 = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-4, max_rows=8192, max_scored_rows=4096)
+    ref = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch", lr=1e-5)
+    b2 = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-5, max_rows=8192, max_scored_rows=4096)
     batch = make_batch(rng, cfg, tok.pad_token_id, None, b=32, t=128)
     ids = batch["input_ids"]
     lens = (ids != tok.pad_token_id).sum(1)
@@ -129,11 +129,18 @@ def test_handwritten_backward_gpt2_small_and_training_step():
             worst = (rel, cos, name)
         assert cos >= 0.99 and rel <= 0.1, (name, rel, cos)
     print(f"GPT-2-small backward: worst tensor {worst[2]} rel {worst[0]:.4f} cos {worst[1]:.5f}; forward + loss + backward of {int(lens.sum())} rows in {dt * 1e3:.1f} ms")
+    # three optimizer steps on the same minibatch: the hand-written path tracks the library path (same AdamW kernel, same start)
     before = pol.logits([ids[0, :8].tolist()])
-    l0 = b2.step(batch)[0]
-    for _ in range(2):
-        l1 = b2.step(batch)[0]
-    assert l1 < l0
+    traj_b, traj_r = [], []
+    for _ in range(3):
+        traj_b.append(b2.step(batch)[0])
+        traj_r.append(ref.step(batch)[0])
+    print("loss per step, hand-written backward:", [round(x, 4) for x in traj_b], " autograd:", [round(x, 4) for x in traj_r])
+    for a, b in zip(traj_b, traj_r):
+        assert abs(a - b) <= 0.05 * max(1.0, abs(b)), (traj_b, traj_r)
+    pb = torch.cat([f.data.reshape(-1) for f in b2.flat]).double()
+    pr = torch.cat([f.data.reshape(-1) for f in ref.flat]).double()
+    assert float((pb - pr).abs().max()) <= 3 * 3 * 1e-5          # at most lr per step apart, and mostly identical signs:
     after = pol.logits([ids[0, :8].tolist()])
-    assert np.abs(after - before).max() > 1e-4          # the rollout policy runs on the trained weights
+    assert np.abs(after - before).max() > 1e-5          # the rollout policy runs on the trained weights
     eng.close()

@@ -1,13 +1,15 @@
 """One small PPO loop on the GPU (BASELINE.json configs[4] data flow, lmrl_gym_b200/ppo_train.py): fused Wordle rollouts -> trajectory
-chains -> device PPO data -> TorchPPOTrain steps (the torch-autograd LIBRARY path) -> device-to-device weight hand-over, after which
-the rollout engine must compute with the UPDATED weights (its logits equal the trainer's own forward)."""
+chains -> device PPO data -> optimizer steps (hand-written backward pass, or the torch-autograd library path for comparison) ->
+device-to-device weight hand-over, after which the rollout engine must compute with the UPDATED weights (its logits equal the trainer's
+own forward)."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 
-def test_ppo_rounds_update_the_engine_policy():
+@pytest.mark.parametrize("backward", ["b200", "torch"])
+def test_ppo_rounds_update_the_engine_policy(backward):
     import torch
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
@@ -24,7 +26,8 @@ def test_ppo_rounds_update_the_engine_policy():
     env = B200WordleEnv(eng, "wordle_official.txt", bad_word_reward=-10.0)
     pol = B200GPT2Policy(eng, params, cfg, seed=0)
     inf = P.B200PPOInference(eng, None, lin, initial_policy_params=params, config=cfg, pad_token_id=tok.pad_token_id)
-    trainer = T.TorchPPOTrain(eng, params, lin, cfg, lr=1e-4, pad_token_id=tok.pad_token_id, activation_dtype="f32")
+    trainer = T.TorchPPOTrain(eng, params, lin, cfg, lr=1e-4, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward=backward, max_rows=16 * 192,
+                              max_scored_rows=16 * 192)
     prompts = [tok.encode("Wordle:\n"), tok.encode("Wordle:\nc r a n e\nb y g b b\n")]
     before = pol.logits(prompts)
     logs = T.ppo_train_loop(env, pol, inf, trainer, P.AdaptiveKLController(0.001, 0.1, 10000), n_rounds=2, n_rollouts=B, rollout_bsize=B, epochs=1,
