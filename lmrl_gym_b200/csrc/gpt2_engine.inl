@@ -673,8 +673,18 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     const size_t stage_elems = std::max((size_t)w->n_vocab_rows * d, (size_t)d * std::max(ff, 3 * d));
     float* stage = nullptr;
     LMRL_CUDA(cudaMalloc(&stage, stage_elems * sizeof(float)));
+    // device-resident sources (a trainer's fp32 master weights) are converted in place: no staging copy, no per-matrix synchronisation
+    auto on_device = [&](const void* p) -> bool {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeDevice;
+    };
+    const bool dev_src = on_device(w->wte);
+    const float* cur_src = nullptr;
     auto up = [&](const float* host, size_t n) -> int {
+        if (dev_src) { cur_src = host; return 0; }
         LMRL_CUDA(cudaMemcpyAsync(stage, host, n * sizeof(float), cudaMemcpyDefault, e->stream));
+        cur_src = stage;
         return 0;
     };
     auto vec = [&](float** dst, const float* host, size_t n) -> int {
@@ -685,8 +695,8 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     auto mat_t = [&](__nv_bfloat16** dst, const float* host, int K, int N) -> int {   // [K][N] fp32 -> [N][K] bf16
         if (fresh && e->alloc(dst, (size_t)K * N)) return -1;
         if (up(host, (size_t)K * N)) return -1;
-        transpose_to_bf16_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, K, N, *dst);
-        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+        transpose_to_bf16_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, e->stream>>>(cur_src, K, N, *dst);
+        if (!dev_src) LMRL_CUDA(cudaStreamSynchronize(e->stream));      // the staging buffer is reused by the next matrix
         return 0;
     };
     int rc = 0;
@@ -694,11 +704,11 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     if (!rc) {
         const int rows = std::min(w->n_vocab_rows, GG.v_pad);
         rc |= up(w->wte, (size_t)rows * d);
-        convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(stage, (size_t)rows * d, G.wte);
-        cudaStreamSynchronize(e->stream);
+        convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(cur_src, (size_t)rows * d, G.wte);
+        if (!dev_src) cudaStreamSynchronize(e->stream);
         rc |= up(w->wpe, (size_t)dims->n_pos * d);
-        convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(stage, (size_t)dims->n_pos * d, G.wpe);
-        cudaStreamSynchronize(e->stream);
+        convert_to_bf16_kernel<<<1024, 256, 0, e->stream>>>(cur_src, (size_t)dims->n_pos * d, G.wpe);
+        if (!dev_src) cudaStreamSynchronize(e->stream);
         rc |= vec(&G.lnf_g, w->lnf_g, d); rc |= vec(&G.lnf_b, w->lnf_b, d);
     }
     for (int l = 0; l < L && !rc; ++l) {

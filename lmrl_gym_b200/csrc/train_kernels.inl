@@ -119,108 +119,150 @@ __global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restri
 
 // causal self-attention backward for full sequences (every slot starts at position 0), one CTA per (slot, head).
 //   P = softmax(scale * Q K^T) (causal);  O = P V;   given dO:  dV = P^T dO,  dP = dO V^T,  dS = P * (dP - rowsum(P * dP)) * scale,
-//   dQ = dS K,  dK = dS^T Q.   Query rows are walked sequentially; thread j owns keys j, j + blockDim, ...; dK / dV accumulate in shared
-//   memory (fp32 [T][64] each), dQ of a row is reduced over the threads through shared memory.  Latency/ALU-bound; attention is ~3 % of
-//   the training FLOPs at these sequence lengths, so no tensor cores here.
-constexpr int ATTB_THREADS = 128;
-__global__ void __launch_bounds__(ATTB_THREADS) attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
-                                                                const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout, RowsDev rows,
-                                                                int n_head, int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ dqkv) {
-    extern __shared__ float ab_sm[];
+//   dQ = dS K,  dK = dS^T Q.
+// The Q, K, V, dO tiles of the (sequence, head) are staged in shared memory as bf16 with a 33-word row pitch (lanes that walk rows hit
+// 32 different banks).  Phase 1: one warp per query row, lanes over the keys j <= i: scores, soft-max statistics, dP, D_i and
+// dQ_i (64 fp32 accumulators per lane, reduced with shuffles); the row statistics stay in shared memory.  Phase 2: one warp per key
+// row, lanes over the queries i >= j: dK_j and dV_j (128 accumulators per lane).  No atomics, no tensor cores: attention is ~3 % of the
+// training FLOPs at these sequence lengths (T <= 384).
+constexpr int ATTB_THREADS = 256;
+constexpr int ATTB_PITCH = 66;                     // bf16 elements per staged row (64 + 2 padding)
+constexpr int ATTB_MAX_T = 384;
+__device__ __forceinline__ float attb_dot(const __nv_bfloat16* a, const __nv_bfloat16* b) {
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(a);
+    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(b);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { const float2 x = __bfloat1622float2(pa[c]), y = __bfloat1622float2(pb[c]); s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); }
+    return s;
+}
+__global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                   const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout, RowsDev rows,
+                                                                   int n_head, int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ dqkv) {
+    extern __shared__ __align__(16) unsigned char ab_raw[];
     const int slot = blockIdx.x / n_head, head = blockIdx.x % n_head;
     if (slot >= *rows.n_slots) return;
     const int env = rows.slot_env[slot], r0 = rows.slot_row0[slot], T = rows.slot_nrow[slot];
-    float* dK = ab_sm;                       // [T][64]
-    float* dV = dK + (size_t)T * 64;         // [T][64]
-    float* qi = dV + (size_t)T * 64;         // [64]
-    float* doi = qi + 64;                    // [64]
-    float* red = doi + 64;                   // [ATTB_THREADS]
-    float* dqp = red + ATTB_THREADS;         // [4 warps][64]
-    float* prob = dqp + 4 * 64;              // [T] p_j, then ds_j
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(ab_raw);
+    __nv_bfloat16* Ks = Qs + (size_t)T * ATTB_PITCH;
+    __nv_bfloat16* Vs = Ks + (size_t)T * ATTB_PITCH;
+    __nv_bfloat16* Os = Vs + (size_t)T * ATTB_PITCH;
+    float* st_m = reinterpret_cast<float*>(Os + (size_t)T * ATTB_PITCH + (((size_t)T * ATTB_PITCH * 4) & 1));   // 4-byte aligned: T * 66 * 4 elements is even
+    float* st_l = st_m + T;
+    float* st_D = st_l + T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATTB_THREADS >> 5;
     const __nv_bfloat16* Kb = kcache + ((size_t)env * n_head + head) * t_cap * 64;
     const __nv_bfloat16* Vb = vcache + ((size_t)env * n_head + head) * t_cap * 64;
-    for (int i = tid; i < T * 128; i += ATTB_THREADS) ab_sm[i] = 0.f;
+    for (int i = tid; i < T * 32; i += ATTB_THREADS) {                       // one bf16x2 word per thread per step
+        const int r = i >> 5, w = i & 31;
+        const size_t grow = (size_t)(r0 + r) * d_model + head * 64 + 2 * w;
+        reinterpret_cast<uint32_t*>(Qs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(q + grow);
+        reinterpret_cast<uint32_t*>(Os + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(dout + grow);
+        reinterpret_cast<uint32_t*>(Ks + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(Kb + (size_t)r * 64 + 2 * w);
+        reinterpret_cast<uint32_t*>(Vs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(Vb + (size_t)r * 64 + 2 * w);
+    }
     __syncthreads();
-    for (int i = 0; i < T; ++i) {
-        const size_t row = (size_t)(r0 + i);
-        if (tid < 64) { qi[tid] = __bfloat162float(q[row * d_model + head * 64 + tid]); doi[tid] = __bfloat162float(dout[row * d_model + head * 64 + tid]); }
-        __syncthreads();
-        // scores and dP for my keys
-        float mx = -INFINITY;
-        for (int j = tid; j <= i; j += ATTB_THREADS) {
-            const __nv_bfloat162* kj = reinterpret_cast<const __nv_bfloat162*>(Kb + (size_t)j * 64);
+    // ---- phase 1: dQ and the row statistics
+    for (int i = warp; i < T; i += nwarp) {
+        // the warp's query row and its dO row, packed bf16x2 in registers (every lane needs all 64 dims)
+        uint32_t qreg[32], oreg[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            qreg[c] = reinterpret_cast<const uint32_t*>(Qs + (size_t)i * ATTB_PITCH)[c];
+            oreg[c] = reinterpret_cast<const uint32_t*>(Os + (size_t)i * ATTB_PITCH)[c];
+        }
+        auto dot_reg = [](const uint32_t (&a)[32], const __nv_bfloat16* b) {
+            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(b);
             float s = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < 32; ++c) { const float2 f = __bfloat1622float2(kj[c]); s += qi[2 * c] * f.x + qi[2 * c + 1] * f.y; }
-            s *= scale;
-            prob[j] = s;
-            mx = fmaxf(mx, s);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a[c])), y = __bfloat1622float2(pb[c]);
+                s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s);
+            }
+            return s;
+        };
+        float sc[ATTB_MAX_T / 32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < ATTB_MAX_T / 32; ++k) {
+            const int j = lane + 32 * k;
+            sc[k] = -INFINITY;
+            if (32 * k <= i) {                                               // warp-uniform: chunks past the diagonal are skipped
+                if (j <= i) { sc[k] = dot_reg(qreg, Ks + (size_t)j * ATTB_PITCH) * scale; mx = fmaxf(mx, sc[k]); }
+            }
         }
-        red[tid] = mx;
-        __syncthreads();
-        for (int o = ATTB_THREADS / 2; o; o >>= 1) { if (tid < o) red[tid] = fmaxf(red[tid], red[tid + o]); __syncthreads(); }
-        mx = red[0];
-        __syncthreads();
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         float sum = 0.f;
-        for (int j = tid; j <= i; j += ATTB_THREADS) { const float p = __expf(prob[j] - mx); prob[j] = p; sum += p; }
-        red[tid] = sum;
-        __syncthreads();
-        for (int o = ATTB_THREADS / 2; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-        const float inv = 1.f / red[0];
-        __syncthreads();
-        // dP_j = dO_i . V_j;  D = sum_j p_j dP_j
-        float dsum = 0.f;
-        float dpl[4];                                   // T <= 4 * ATTB_THREADS keys per thread
-        int nk = 0;
-        for (int j = tid; j <= i; j += ATTB_THREADS, ++nk) {
-            const __nv_bfloat162* vj = reinterpret_cast<const __nv_bfloat162*>(Vb + (size_t)j * 64);
-            float dp = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < 32; ++c) { const float2 f = __bfloat1622float2(vj[c]); dp += doi[2 * c] * f.x + doi[2 * c + 1] * f.y; }
-            const float p = prob[j] * inv;
-            prob[j] = p;
-            dpl[nk] = dp;
-            dsum += p * dp;
+#pragma unroll
+        for (int k = 0; k < ATTB_MAX_T / 32; ++k) { sc[k] = (lane + 32 * k <= i) ? __expf(sc[k] - mx) : 0.f; sum += sc[k]; }
+        const float linv = 1.f / warp_sum(sum);
+        float dp[ATTB_MAX_T / 32];
+        float Dp = 0.f;
+#pragma unroll
+        for (int k = 0; k < ATTB_MAX_T / 32; ++k) {
+            const int j = lane + 32 * k;
+            dp[k] = 0.f;
+            if (32 * k <= i) {
+                if (j <= i) { sc[k] *= linv; dp[k] = dot_reg(oreg, Vs + (size_t)j * ATTB_PITCH); Dp += sc[k] * dp[k]; }
+            }
         }
-        red[tid] = dsum;
-        __syncthreads();
-        for (int o = ATTB_THREADS / 2; o; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-        const float D = red[0];
-        // my keys: dV_j += p_j dO_i;  dK_j += ds_j q_i;  partial dQ_i += ds_j K_j
+        const float D = warp_sum(Dp);
         float dq[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) dq[c] = 0.f;
-        nk = 0;
-        for (int j = tid; j <= i; j += ATTB_THREADS, ++nk) {
-            const float p = prob[j];
-            const float ds = p * (dpl[nk] - D) * scale;
-            const __nv_bfloat162* kj = reinterpret_cast<const __nv_bfloat162*>(Kb + (size_t)j * 64);
-            float* dKj = dK + (size_t)j * 64;
-            float* dVj = dV + (size_t)j * 64;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float2 f = __bfloat1622float2(kj[c]);
-                dq[2 * c] += ds * f.x; dq[2 * c + 1] += ds * f.y;
-                dKj[2 * c] += ds * qi[2 * c]; dKj[2 * c + 1] += ds * qi[2 * c + 1];
-                dVj[2 * c] += p * doi[2 * c]; dVj[2 * c + 1] += p * doi[2 * c + 1];
+        for (int k = 0; k < ATTB_MAX_T / 32; ++k) {
+            const int j = lane + 32 * k;
+            if (32 * k <= i) {
+                if (j <= i) {
+                    const float ds = sc[k] * (dp[k] - D) * scale;
+                    const __nv_bfloat162* kj = reinterpret_cast<const __nv_bfloat162*>(Ks + (size_t)j * ATTB_PITCH);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) { const float2 f = __bfloat1622float2(kj[c]); dq[2 * c] = fmaf(ds, f.x, dq[2 * c]); dq[2 * c + 1] = fmaf(ds, f.y, dq[2 * c + 1]); }
+                }
             }
         }
-        // reduce dq over the CTA: warp shuffles, then the four warps through shared memory
+        if (lane == 0) { st_m[i] = mx; st_l[i] = linv; st_D[i] = D; }
+        float mine0 = 0.f, mine1 = 0.f;                                      // lane l keeps dims 2l, 2l + 1 of the reduced row
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
             const float v = warp_sum(dq[c]);
-            if (lane == 0) dqp[warp * 64 + c] = v;
+            if ((c >> 1) == lane) { if (c & 1) mine1 = v; else mine0 = v; }
         }
-        __syncthreads();
-        if (tid < 64) dqkv[row * 3 * d_model + head * 64 + tid] = __float2bfloat16(dqp[tid] + dqp[64 + tid] + dqp[128 + tid] + dqp[192 + tid]);
-        __syncthreads();
+        *reinterpret_cast<__nv_bfloat162*>(dqkv + (size_t)(r0 + i) * 3 * d_model + head * 64 + 2 * lane) = __floats2bfloat162_rn(mine0, mine1);
     }
-    for (int i = tid; i < T * 64; i += ATTB_THREADS) {
-        const int j = i >> 6, c = i & 63;
-        const size_t row = (size_t)(r0 + j);
-        dqkv[row * 3 * d_model + d_model + head * 64 + c] = __float2bfloat16(dK[i]);
-        dqkv[row * 3 * d_model + 2 * d_model + head * 64 + c] = __float2bfloat16(dV[i]);
+    __syncthreads();
+    // ---- phase 2: dK and dV
+    for (int j = warp; j < T; j += nwarp) {
+        const __nv_bfloat16* kj = Ks + (size_t)j * ATTB_PITCH;
+        const __nv_bfloat16* vj = Vs + (size_t)j * ATTB_PITCH;
+        float dk[64], dv[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+        for (int i = j + lane; i < T; i += 32) {
+            const __nv_bfloat16* qi = Qs + (size_t)i * ATTB_PITCH;
+            const __nv_bfloat16* oi = Os + (size_t)i * ATTB_PITCH;
+            const float p = __expf(attb_dot(qi, kj) * scale - st_m[i]) * st_l[i];
+            const float ds = p * (attb_dot(oi, vj) - st_D[i]) * scale;
+            const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(qi);
+            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(oi);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float2 fq = __bfloat1622float2(q2[c]), fo = __bfloat1622float2(o2[c]);
+                dk[2 * c] = fmaf(ds, fq.x, dk[2 * c]); dk[2 * c + 1] = fmaf(ds, fq.y, dk[2 * c + 1]);
+                dv[2 * c] = fmaf(p, fo.x, dv[2 * c]); dv[2 * c + 1] = fmaf(p, fo.y, dv[2 * c + 1]);
+            }
+        }
+        float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+            const float a = warp_sum(dk[c]), b = warp_sum(dv[c]);
+            if ((c >> 1) == lane) { if (c & 1) { k1 = a; v1 = b; } else { k0 = a; v0 = b; } }
+        }
+        __nv_bfloat16* o = dqkv + (size_t)(r0 + j) * 3 * d_model + head * 64 + 2 * lane;
+        *reinterpret_cast<__nv_bfloat162*>(o + d_model) = __floats2bfloat162_rn(k0, k1);
+        *reinterpret_cast<__nv_bfloat162*>(o + 2 * d_model) = __floats2bfloat162_rn(v0, v1);
     }
 }
 
@@ -491,10 +533,11 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
     // ---- attention
     {
         const __nv_bfloat16* kc = G.tw[0].kv + (size_t)l * G.kv_layer_stride;
-        const size_t smem = ((size_t)e->cfg.max_input_length * 129 + 64 + 64 + ATTB_THREADS + 256) * sizeof(float);
+        auto smem_for = [](size_t T) { return T * ATTB_PITCH * 2 * 4 + T * 3 * sizeof(float) + 16; };
+        const size_t smem = smem_for((size_t)e->cfg.max_input_length);
         static bool configured = false;
         if (!configured) {
-            LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)384 * 129 + 64 + 64 + ATTB_THREADS + 256) * sizeof(float))));
+            LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ATTB_MAX_T)));
             configured = true;
         }
         attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.t_cap, 0.125f, Tr.dqkv);
@@ -568,6 +611,17 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
     e->cur_pass_slot = -1;
     e->cur_mode = 0;
     const int ew = G.sm_count * 8;
+    // LMRL_TRAIN_TIMING=1: CUDA-event timing of the sections, printed to stderr (diagnostics only)
+    const bool timing = getenv("LMRL_TRAIN_TIMING") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* name) {
+        if (!timing) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        marks.push_back({name, ev});
+    };
+    mark("start");
     // ---- forward, saving the residual stream before every layer
     LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen);
     LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, n, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
@@ -580,6 +634,7 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
     }
     LMRL_CUDA(cudaMemcpyAsync(Tr.xsave + (size_t)L * xstride, G.x, xbytes, cudaMemcpyDeviceToDevice, st));
     LMRL_CUDA(cudaMemsetAsync(Tr.dfx, 0, xbytes, st));
+    mark("forward");
     // ---- tied LM head: dlogits = g (onehot - softmax) on the scored rows
     if (n_lp) {
         const int* n_lp_dev = Tr.consts + 4;
@@ -605,6 +660,7 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
         wg.A = Tr.tA; wg.W = Tr.tB; wg.bias = nullptr; wg.N = d; wg.K = Kp; wg.M_dev = Tr.consts + 6; wg.resid = grads->wte;
         if (launch_gemm<EPI_RESID>(e, wg, d, 0, (size_t)grads->n_vocab_rows, (size_t)d, 1)) return -1;
     }
+    mark("lm_head_backward");
     // ---- value head (LinearHead on the fp32 final LayerNorm), then ln_f
     if (grads->vh_w)
         value_head_bwd_kernel<<<G.sm_count * 2, 256, (d + 1) * sizeof(float), st>>>(G.x, T.lnf_g, T.lnf_b, G.vh[0].lin_w, Tr.dv, d, D.ln_eps, G.rows.M, Tr.dfx,
@@ -614,13 +670,27 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
     for (int l = L - 1; l >= 0; --l) {
         LMRL_CUDA(cudaMemcpyAsync(G.x, Tr.xsave + (size_t)l * xstride, xbytes, cudaMemcpyDeviceToDevice, st));
         if (train_layer_forward(e, l, n, false)) return -1;
+        if (l == L - 1) mark("recompute_last_layer");
         const LayerGrads gr{grads->ln1_g[l], grads->ln1_b[l], grads->attn_w[l], grads->attn_b[l], grads->proj_w[l], grads->proj_b[l],
                             grads->ln2_g[l], grads->ln2_b[l], grads->fc_w[l], grads->fc_b[l], grads->fc2_w[l], grads->fc2_b[l]};
         if (train_layer_backward(e, l, n, Mp, gr)) return -1;
+        if (l == L - 1) mark("backward_last_layer");
     }
+    mark("layers_backward");
     embed_bwd_kernel<<<ew, 256, 0, st>>>(Tr.dx, G.rows, d, grads->wte, grads->wpe);
+    mark("embedding_backward");
     LMRL_CUDA(cudaGetLastError());
     LMRL_CUDA(cudaStreamSynchronize(st));
+    if (timing) {
+        fprintf(stderr, "[lmrl_policy_grad] rows=%d scored=%d:", M, n_lp);
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, " %s %.2f ms", marks[i].first, ms);
+        }
+        fprintf(stderr, "\n");
+        for (auto& m : marks) cudaEventDestroy(m.second);
+    }
     return 0;
 }
 
