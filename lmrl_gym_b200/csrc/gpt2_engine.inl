@@ -672,7 +672,6 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     // staging buffer for fp32 uploads
     const size_t stage_elems = std::max((size_t)w->n_vocab_rows * d, (size_t)d * std::max(ff, 3 * d));
     float* stage = nullptr;
-    LMRL_CUDA(cudaMalloc(&stage, stage_elems * sizeof(float)));
     // device-resident sources (a trainer's fp32 master weights) are converted in place: no staging copy, no per-matrix synchronisation
     auto on_device = [&](const void* p) -> bool {
         cudaPointerAttributes at{};
@@ -680,6 +679,7 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         return at.type == cudaMemoryTypeDevice;
     };
     const bool dev_src = on_device(w->wte);
+    if (!dev_src) LMRL_CUDA(cudaMalloc(&stage, stage_elems * sizeof(float)));
     const float* cur_src = nullptr;
     auto up = [&](const float* host, size_t n) -> int {
         if (dev_src) { cur_src = host; return 0; }

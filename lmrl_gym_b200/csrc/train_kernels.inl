@@ -120,21 +120,33 @@ __global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restri
 // causal self-attention backward for full sequences (every slot starts at position 0), one CTA per (slot, head).
 //   P = softmax(scale * Q K^T) (causal);  O = P V;   given dO:  dV = P^T dO,  dP = dO V^T,  dS = P * (dP - rowsum(P * dP)) * scale,
 //   dQ = dS K,  dK = dS^T Q.
-// The Q, K, V, dO tiles of the (sequence, head) are staged in shared memory as bf16 with a 33-word row pitch (lanes that walk rows hit
-// 32 different banks).  Phase 1: one warp per query row, lanes over the keys j <= i: scores, soft-max statistics, dP, D_i and
+// The Q, K, V, dO tiles of the (sequence, head) are staged in shared memory as bf16 with a 144-byte row pitch, read with 16-byte loads (conflict-free for lanes
+// that walk rows).  Phase 1: one warp per query row, lanes over the keys j <= i: scores, soft-max statistics, dP, D_i and
 // dQ_i (64 fp32 accumulators per lane, reduced with shuffles); the row statistics stay in shared memory.  Phase 2: one warp per key
 // row, lanes over the queries i >= j: dK_j and dV_j (128 accumulators per lane).  No atomics, no tensor cores: attention is ~3 % of the
 // training FLOPs at these sequence lengths (T <= 384).
 constexpr int ATTB_THREADS = 256;
-constexpr int ATTB_PITCH = 66;                     // bf16 elements per staged row (64 + 2 padding)
+constexpr int ATTB_PITCH = 72;                     // bf16 elements per staged row: 64 + 8 padding -> 144 B, 16-byte aligned, and the 8 lanes of a
+                                                   // quarter-warp reading 16 B each from consecutive rows cover all 32 banks (36 j + 4 c mod 32)
 constexpr int ATTB_MAX_T = 384;
-__device__ __forceinline__ float attb_dot(const __nv_bfloat16* a, const __nv_bfloat16* b) {
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(a);
-    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(b);
-    float s = 0.f;
+struct Bf8 { uint4 v; };                           // eight bf16
+__device__ __forceinline__ void bf8_unpack(const uint4& u, float (&f)[8]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) { const float2 x = __bfloat1622float2(pa[c]), y = __bfloat1622float2(pb[c]); s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); }
-    return s;
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+// dot of a register-resident row (8 x uint4) with a shared-memory row
+__device__ __forceinline__ float attb_dot_rs(const uint4 (&a)[8], const __nv_bfloat16* b) {
+    const uint4* pb = reinterpret_cast<const uint4*>(b);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};                 // eight independent chains: the warp count per SM is low, ILP hides the FMA latency
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float x[8], y[8];
+        bf8_unpack(a[c], x); bf8_unpack(pb[c], y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = fmaf(x[i], y[i], s[i]);
+    }
+    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                    const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout, RowsDev rows,
@@ -147,40 +159,29 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
     __nv_bfloat16* Ks = Qs + (size_t)T * ATTB_PITCH;
     __nv_bfloat16* Vs = Ks + (size_t)T * ATTB_PITCH;
     __nv_bfloat16* Os = Vs + (size_t)T * ATTB_PITCH;
-    float* st_m = reinterpret_cast<float*>(Os + (size_t)T * ATTB_PITCH + (((size_t)T * ATTB_PITCH * 4) & 1));   // 4-byte aligned: T * 66 * 4 elements is even
+    float* st_m = reinterpret_cast<float*>(Os + (size_t)T * ATTB_PITCH);          // T * 144 B per tile: 16-byte aligned
     float* st_l = st_m + T;
     float* st_D = st_l + T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATTB_THREADS >> 5;
     const __nv_bfloat16* Kb = kcache + ((size_t)env * n_head + head) * t_cap * 64;
     const __nv_bfloat16* Vb = vcache + ((size_t)env * n_head + head) * t_cap * 64;
-    for (int i = tid; i < T * 32; i += ATTB_THREADS) {                       // one bf16x2 word per thread per step
-        const int r = i >> 5, w = i & 31;
-        const size_t grow = (size_t)(r0 + r) * d_model + head * 64 + 2 * w;
-        reinterpret_cast<uint32_t*>(Qs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(q + grow);
-        reinterpret_cast<uint32_t*>(Os + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(dout + grow);
-        reinterpret_cast<uint32_t*>(Ks + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(Kb + (size_t)r * 64 + 2 * w);
-        reinterpret_cast<uint32_t*>(Vs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint32_t*>(Vb + (size_t)r * 64 + 2 * w);
+    for (int i = tid; i < T * 8; i += ATTB_THREADS) {                        // one 16-byte chunk per thread per step
+        const int r = i >> 3, w = i & 7;
+        const size_t grow = (size_t)(r0 + r) * d_model + head * 64 + 8 * w;
+        reinterpret_cast<uint4*>(Qs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(q + grow);
+        reinterpret_cast<uint4*>(Os + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(dout + grow);
+        reinterpret_cast<uint4*>(Ks + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(Kb + (size_t)r * 64 + 8 * w);
+        reinterpret_cast<uint4*>(Vs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(Vb + (size_t)r * 64 + 8 * w);
     }
     __syncthreads();
-    // ---- phase 1: dQ and the row statistics
+    // ---- phase 1: dQ and the row statistics (warp per query row, lanes over keys)
     for (int i = warp; i < T; i += nwarp) {
-        // the warp's query row and its dO row, packed bf16x2 in registers (every lane needs all 64 dims)
-        uint32_t qreg[32], oreg[32];
+        uint4 qreg[8], oreg[8];                                              // the row and its dO, packed, in registers
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            qreg[c] = reinterpret_cast<const uint32_t*>(Qs + (size_t)i * ATTB_PITCH)[c];
-            oreg[c] = reinterpret_cast<const uint32_t*>(Os + (size_t)i * ATTB_PITCH)[c];
+        for (int c = 0; c < 8; ++c) {
+            qreg[c] = reinterpret_cast<const uint4*>(Qs + (size_t)i * ATTB_PITCH)[c];
+            oreg[c] = reinterpret_cast<const uint4*>(Os + (size_t)i * ATTB_PITCH)[c];
         }
-        auto dot_reg = [](const uint32_t (&a)[32], const __nv_bfloat16* b) {
-            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(b);
-            float s = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a[c])), y = __bfloat1622float2(pb[c]);
-                s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s);
-            }
-            return s;
-        };
         float sc[ATTB_MAX_T / 32];
         float mx = -INFINITY;
 #pragma unroll
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
             const int j = lane + 32 * k;
             sc[k] = -INFINITY;
             if (32 * k <= i) {                                               // warp-uniform: chunks past the diagonal are skipped
-                if (j <= i) { sc[k] = dot_reg(qreg, Ks + (size_t)j * ATTB_PITCH) * scale; mx = fmaxf(mx, sc[k]); }
+                if (j <= i) { sc[k] = attb_dot_rs(qreg, Ks + (size_t)j * ATTB_PITCH) * scale; mx = fmaxf(mx, sc[k]); }
             }
         }
 #pragma unroll
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
             const int j = lane + 32 * k;
             dp[k] = 0.f;
             if (32 * k <= i) {
-                if (j <= i) { sc[k] *= linv; dp[k] = dot_reg(oreg, Vs + (size_t)j * ATTB_PITCH); Dp += sc[k] * dp[k]; }
+                if (j <= i) { sc[k] *= linv; dp[k] = attb_dot_rs(oreg, Vs + (size_t)j * ATTB_PITCH); Dp += sc[k] * dp[k]; }
             }
         }
         const float D = warp_sum(Dp);
@@ -217,9 +218,14 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
             if (32 * k <= i) {
                 if (j <= i) {
                     const float ds = sc[k] * (dp[k] - D) * scale;
-                    const __nv_bfloat162* kj = reinterpret_cast<const __nv_bfloat162*>(Ks + (size_t)j * ATTB_PITCH);
+                    const uint4* kj = reinterpret_cast<const uint4*>(Ks + (size_t)j * ATTB_PITCH);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) { const float2 f = __bfloat1622float2(kj[c]); dq[2 * c] = fmaf(ds, f.x, dq[2 * c]); dq[2 * c + 1] = fmaf(ds, f.y, dq[2 * c + 1]); }
+                    for (int c = 0; c < 8; ++c) {
+                        float f[8];
+                        bf8_unpack(kj[c], f);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) dq[8 * c + u] = fmaf(ds, f[u], dq[8 * c + u]);
+                    }
                 }
             }
         }
@@ -233,25 +239,30 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
         *reinterpret_cast<__nv_bfloat162*>(dqkv + (size_t)(r0 + i) * 3 * d_model + head * 64 + 2 * lane) = __floats2bfloat162_rn(mine0, mine1);
     }
     __syncthreads();
-    // ---- phase 2: dK and dV
+    // ---- phase 2: dK and dV (warp per key row, lanes over the queries i >= j)
     for (int j = warp; j < T; j += nwarp) {
-        const __nv_bfloat16* kj = Ks + (size_t)j * ATTB_PITCH;
-        const __nv_bfloat16* vj = Vs + (size_t)j * ATTB_PITCH;
+        uint4 kreg[8], vreg[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            kreg[c] = reinterpret_cast<const uint4*>(Ks + (size_t)j * ATTB_PITCH)[c];
+            vreg[c] = reinterpret_cast<const uint4*>(Vs + (size_t)j * ATTB_PITCH)[c];
+        }
         float dk[64], dv[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
         for (int i = j + lane; i < T; i += 32) {
             const __nv_bfloat16* qi = Qs + (size_t)i * ATTB_PITCH;
             const __nv_bfloat16* oi = Os + (size_t)i * ATTB_PITCH;
-            const float p = __expf(attb_dot(qi, kj) * scale - st_m[i]) * st_l[i];
-            const float ds = p * (attb_dot(oi, vj) - st_D[i]) * scale;
-            const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(qi);
-            const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(oi);
+            const float p = __expf(attb_dot_rs(kreg, qi) * scale - st_m[i]) * st_l[i];
+            const float ds = p * (attb_dot_rs(vreg, oi) - st_D[i]) * scale;
+            const uint4* q4 = reinterpret_cast<const uint4*>(qi);
+            const uint4* o4 = reinterpret_cast<const uint4*>(oi);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float2 fq = __bfloat1622float2(q2[c]), fo = __bfloat1622float2(o2[c]);
-                dk[2 * c] = fmaf(ds, fq.x, dk[2 * c]); dk[2 * c + 1] = fmaf(ds, fq.y, dk[2 * c + 1]);
-                dv[2 * c] = fmaf(p, fo.x, dv[2 * c]); dv[2 * c + 1] = fmaf(p, fo.y, dv[2 * c + 1]);
+            for (int c = 0; c < 8; ++c) {
+                float fq[8], fo[8];
+                bf8_unpack(q4[c], fq); bf8_unpack(o4[c], fo);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { dk[8 * c + u] = fmaf(ds, fq[u], dk[8 * c + u]); dv[8 * c + u] = fmaf(p, fo[u], dv[8 * c + u]); }
             }
         }
         float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
