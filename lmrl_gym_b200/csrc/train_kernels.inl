@@ -277,6 +277,183 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
     }
 }
 
+// ---- tensor-core version of the same computation (mma.sync m16n8k16, bf16 in / fp32 accumulate) --------------------------------
+// Same staging and the same two phases, in 16-row blocks per warp:
+//   phase 1 (query block): pass A  S = Q K^T -> running row max / sum;   pass B  S again, dP = dO V^T, dS = P (dP - D) scale,
+//                          dQ += dS K  (dS re-used straight from the accumulator fragments as the A operand, K through ldmatrix.trans);
+//   phase 2 (key block)  : S^T = K Q^T and dP^T = V dO^T directly (no transposes), P^T / dS^T from the per-query statistics,
+//                          dK += dS^T Q,  dV += P^T dO.
+// D_i = rowsum(P * dP) = dO_i . O_i is taken from the forward output (the FlashAttention-2 identity).  Rows >= T of the last block are
+// zero-filled in shared memory and masked.
+__device__ __forceinline__ void attb_load_a(const __nv_bfloat16* tile, int row0, int g, int t, uint32_t (&a)[4][4]) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t* r0p = reinterpret_cast<const uint32_t*>(tile + (size_t)(row0 + g) * ATTB_PITCH);
+        const uint32_t* r1p = reinterpret_cast<const uint32_t*>(tile + (size_t)(row0 + g + 8) * ATTB_PITCH);
+        a[kk][0] = r0p[8 * kk + t]; a[kk][1] = r1p[8 * kk + t]; a[kk][2] = r0p[8 * kk + 4 + t]; a[kk][3] = r1p[8 * kk + 4 + t];
+    }
+}
+// acc[4] = A_blk (16 x 64, fragments a) . B_rows[n0 .. n0+7]^T   (B rows are k-contiguous in shared memory)
+__device__ __forceinline__ void attb_mma_rowsT(const uint32_t (&a)[4][4], const __nv_bfloat16* tile, int n0, int g, int t, float (&acc)[4]) {
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    const uint32_t* rp = reinterpret_cast<const uint32_t*>(tile + (size_t)(n0 + g) * ATTB_PITCH);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) mma_bf16(acc, a[kk], rp[8 * kk + t], rp[8 * kk + 4 + t]);
+}
+// out[8][4] += A (16 x 16, fragment a) . tile[k0 .. k0+15][0 .. 63]   (tile rows are the k index: B through ldmatrix.trans)
+__device__ __forceinline__ void attb_mma_rows(const uint32_t (&a)[4], uint32_t tile_addr, int k0, int lane, float (&out)[8][4]) {
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+        const int row = k0 + (lane & 7) + ((lane >> 3) & 1) * 8, col = 16 * dp + (lane >> 4) * 8;
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(tile_addr + (uint32_t)(row * ATTB_PITCH + col) * 2u, b0, b1, b2, b3);
+        mma_bf16(out[2 * dp], a, b0, b1);
+        mma_bf16(out[2 * dp + 1], a, b2, b3);
+    }
+}
+__global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                       const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout,
+                                                                       const __nv_bfloat16* __restrict__ att, RowsDev rows, int n_head, int d_model, int t_cap,
+                                                                       float scale, __nv_bfloat16* __restrict__ dqkv) {
+    extern __shared__ __align__(16) unsigned char ab_raw[];
+    const int slot = blockIdx.x / n_head, head = blockIdx.x % n_head;
+    if (slot >= *rows.n_slots) return;
+    const int env = rows.slot_env[slot], r0 = rows.slot_row0[slot], T = rows.slot_nrow[slot];
+    const int Tp = (T + 15) & ~15, nblk = Tp >> 4;
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(ab_raw);
+    __nv_bfloat16* Ks = Qs + (size_t)Tp * ATTB_PITCH;
+    __nv_bfloat16* Vs = Ks + (size_t)Tp * ATTB_PITCH;
+    __nv_bfloat16* Os = Vs + (size_t)Tp * ATTB_PITCH;
+    float* st_m = reinterpret_cast<float*>(Os + (size_t)Tp * ATTB_PITCH);
+    float* st_l = st_m + Tp;
+    float* st_D = st_l + Tp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATTB_THREADS >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* Kb = kcache + ((size_t)env * n_head + head) * t_cap * 64;
+    const __nv_bfloat16* Vb = vcache + ((size_t)env * n_head + head) * t_cap * 64;
+    for (int i = tid; i < Tp * 8; i += ATTB_THREADS) {
+        const int r = i >> 3, w = i & 7;
+        uint4 vq = make_uint4(0, 0, 0, 0), vo = vq, vk = vq, vv = vq;
+        if (r < T) {
+            const size_t grow = (size_t)(r0 + r) * d_model + head * 64 + 8 * w;
+            vq = *reinterpret_cast<const uint4*>(q + grow);
+            vo = *reinterpret_cast<const uint4*>(dout + grow);
+            vk = *reinterpret_cast<const uint4*>(Kb + (size_t)r * 64 + 8 * w);
+            vv = *reinterpret_cast<const uint4*>(Vb + (size_t)r * 64 + 8 * w);
+        }
+        reinterpret_cast<uint4*>(Qs + (size_t)r * ATTB_PITCH)[w] = vq;
+        reinterpret_cast<uint4*>(Os + (size_t)r * ATTB_PITCH)[w] = vo;
+        reinterpret_cast<uint4*>(Ks + (size_t)r * ATTB_PITCH)[w] = vk;
+        reinterpret_cast<uint4*>(Vs + (size_t)r * ATTB_PITCH)[w] = vv;
+    }
+    for (int i = tid; i < Tp; i += ATTB_THREADS) {                            // D_i = dO_i . O_i
+        float D = 0.f;
+        if (i < T) {
+            const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(dout + (size_t)(r0 + i) * d_model + head * 64);
+            const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(att + (size_t)(r0 + i) * d_model + head * 64);
+#pragma unroll 8
+            for (int c = 0; c < 32; ++c) { const float2 x = __bfloat1622float2(a[c]), y = __bfloat1622float2(b[c]); D = fmaf(x.x, y.x, D); D = fmaf(x.y, y.y, D); }
+        }
+        st_D[i] = D;
+    }
+    __syncthreads();
+    const uint32_t Ks_addr = smem_u32(Ks), Qs_addr = smem_u32(Qs), Os_addr = smem_u32(Os);
+    // ---- phase 1: query blocks (heaviest first so the warps finish together)
+    for (int qb = nblk - 1 - warp; qb >= 0; qb -= nwarp) {
+        const int i0 = 16 * qb;
+        uint32_t qa[4][4], oa[4][4];
+        attb_load_a(Qs, i0, g, t, qa);
+        attb_load_a(Os, i0, g, t, oa);
+        const int rowa = i0 + g, rowb = i0 + g + 8;
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        for (int jb = 0; jb < 2 * (qb + 1); ++jb) {                           // pass A: row statistics
+            float s[4];
+            attb_mma_rowsT(qa, Ks, 8 * jb, g, t, s);
+            const int key = 8 * jb + 2 * t;
+            s[0] = key <= rowa ? s[0] * scale : -INFINITY; s[1] = key + 1 <= rowa ? s[1] * scale : -INFINITY;
+            s[2] = key <= rowb ? s[2] * scale : -INFINITY; s[3] = key + 1 <= rowb ? s[3] * scale : -INFINITY;
+            float b0 = fmaxf(s[0], s[1]), b1 = fmaxf(s[2], s[3]);
+            b0 = fmaxf(b0, __shfl_xor_sync(0xFFFFFFFFu, b0, 1)); b0 = fmaxf(b0, __shfl_xor_sync(0xFFFFFFFFu, b0, 2));
+            b1 = fmaxf(b1, __shfl_xor_sync(0xFFFFFFFFu, b1, 1)); b1 = fmaxf(b1, __shfl_xor_sync(0xFFFFFFFFu, b1, 2));
+            const float n0 = fmaxf(m0, b0), n1 = fmaxf(m1, b1);
+            if (n0 > -INFINITY) { l0 = l0 * __expf(m0 - n0) + __expf(s[0] - n0) + __expf(s[1] - n0); m0 = n0; }
+            if (n1 > -INFINITY) { l1 = l1 * __expf(m1 - n1) + __expf(s[2] - n1) + __expf(s[3] - n1); m1 = n1; }
+        }
+        l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 1); l0 += __shfl_xor_sync(0xFFFFFFFFu, l0, 2);
+        l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 1); l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, 2);
+        const float li0 = l0 > 0.f ? 1.f / l0 : 0.f, li1 = l1 > 0.f ? 1.f / l1 : 0.f;
+        if (t == 0) { st_m[rowa] = m0; st_l[rowa] = li0; st_m[rowb] = m1; st_l[rowb] = li1; }
+        const float D0 = st_D[rowa], D1 = st_D[rowb];
+        float dq[8][4];
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8) { dq[d8][0] = dq[d8][1] = dq[d8][2] = dq[d8][3] = 0.f; }
+        for (int kb = 0; kb <= qb; ++kb) {                                    // pass B: dS and dQ += dS K, sixteen keys at a time
+            uint32_t a[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float s[4], dp[4];
+                attb_mma_rowsT(qa, Ks, 16 * kb + 8 * h, g, t, s);
+                attb_mma_rowsT(oa, Vs, 16 * kb + 8 * h, g, t, dp);
+                const int key = 16 * kb + 8 * h + 2 * t;
+                const float p0 = key <= rowa ? __expf(s[0] * scale - m0) * li0 : 0.f, p1 = key + 1 <= rowa ? __expf(s[1] * scale - m0) * li0 : 0.f;
+                const float p2 = key <= rowb ? __expf(s[2] * scale - m1) * li1 : 0.f, p3 = key + 1 <= rowb ? __expf(s[3] * scale - m1) * li1 : 0.f;
+                a[2 * h] = pack_bf16x2(p0 * (dp[0] - D0) * scale, p1 * (dp[1] - D0) * scale);
+                a[2 * h + 1] = pack_bf16x2(p2 * (dp[2] - D1) * scale, p3 * (dp[3] - D1) * scale);
+            }
+            attb_mma_rows(a, Ks_addr, 16 * kb, lane, dq);
+        }
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8) {
+            if (rowa < T) *reinterpret_cast<__nv_bfloat162*>(dqkv + (size_t)(r0 + rowa) * 3 * d_model + head * 64 + 8 * d8 + 2 * t) = __floats2bfloat162_rn(dq[d8][0], dq[d8][1]);
+            if (rowb < T) *reinterpret_cast<__nv_bfloat162*>(dqkv + (size_t)(r0 + rowb) * 3 * d_model + head * 64 + 8 * d8 + 2 * t) = __floats2bfloat162_rn(dq[d8][2], dq[d8][3]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: key blocks (heaviest = first block, first)
+    for (int kb = warp; kb < nblk; kb += nwarp) {
+        const int j0 = 16 * kb;
+        uint32_t ka[4][4], va[4][4];
+        attb_load_a(Ks, j0, g, t, ka);
+        attb_load_a(Vs, j0, g, t, va);
+        const int keya = j0 + g, keyb = j0 + g + 8;
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8) { dk[d8][0] = dk[d8][1] = dk[d8][2] = dk[d8][3] = 0.f; dv[d8][0] = dv[d8][1] = dv[d8][2] = dv[d8][3] = 0.f; }
+        for (int qb = kb; qb < nblk; ++qb) {                                  // sixteen queries at a time
+            uint32_t pa[4], da[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float s[4], dp[4];
+                attb_mma_rowsT(ka, Qs, 16 * qb + 8 * h, g, t, s);              // S^T block: rows = keys, columns = queries
+                attb_mma_rowsT(va, Os, 16 * qb + 8 * h, g, t, dp);             // dP^T block
+                const int qq = 16 * qb + 8 * h + 2 * t;
+                const float mq0 = st_m[qq], lq0 = st_l[qq], Dq0 = st_D[qq], mq1 = st_m[qq + 1], lq1 = st_l[qq + 1], Dq1 = st_D[qq + 1];
+                const bool v0 = qq < T, v1 = qq + 1 < T;
+                const float p0 = (v0 && qq >= keya) ? __expf(s[0] * scale - mq0) * lq0 : 0.f, p1 = (v1 && qq + 1 >= keya) ? __expf(s[1] * scale - mq1) * lq1 : 0.f;
+                const float p2 = (v0 && qq >= keyb) ? __expf(s[2] * scale - mq0) * lq0 : 0.f, p3 = (v1 && qq + 1 >= keyb) ? __expf(s[3] * scale - mq1) * lq1 : 0.f;
+                pa[2 * h] = pack_bf16x2(p0, p1); pa[2 * h + 1] = pack_bf16x2(p2, p3);
+                da[2 * h] = pack_bf16x2(p0 * (dp[0] - Dq0) * scale, p1 * (dp[1] - Dq1) * scale);
+                da[2 * h + 1] = pack_bf16x2(p2 * (dp[2] - Dq0) * scale, p3 * (dp[3] - Dq1) * scale);
+            }
+            attb_mma_rows(da, Qs_addr, 16 * qb, lane, dk);
+            attb_mma_rows(pa, Os_addr, 16 * qb, lane, dv);
+        }
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8) {
+            if (keya < T) {
+                __nv_bfloat16* o = dqkv + (size_t)(r0 + keya) * 3 * d_model + head * 64 + 8 * d8 + 2 * t;
+                *reinterpret_cast<__nv_bfloat162*>(o + d_model) = __floats2bfloat162_rn(dk[d8][0], dk[d8][1]);
+                *reinterpret_cast<__nv_bfloat162*>(o + 2 * d_model) = __floats2bfloat162_rn(dv[d8][0], dv[d8][1]);
+            }
+            if (keyb < T) {
+                __nv_bfloat16* o = dqkv + (size_t)(r0 + keyb) * 3 * d_model + head * 64 + 8 * d8 + 2 * t;
+                *reinterpret_cast<__nv_bfloat162*>(o + d_model) = __floats2bfloat162_rn(dk[d8][2], dk[d8][3]);
+                *reinterpret_cast<__nv_bfloat162*>(o + 2 * d_model) = __floats2bfloat162_rn(dv[d8][2], dv[d8][3]);
+            }
+        }
+    }
+}
+
 // dwte[tok] += dx_row, dwpe[pos] += dx_row   (one warp per row)
 __global__ void embed_bwd_kernel(const float* __restrict__ dx, RowsDev rows, int d, float* __restrict__ dwte, float* __restrict__ dwpe) {
     const int M = *rows.M;
@@ -544,14 +721,22 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
     // ---- attention
     {
         const __nv_bfloat16* kc = G.tw[0].kv + (size_t)l * G.kv_layer_stride;
-        auto smem_for = [](size_t T) { return T * ATTB_PITCH * 2 * 4 + T * 3 * sizeof(float) + 16; };
+        auto smem_for = [](size_t T) { const size_t Tp = (T + 15) / 16 * 16; return Tp * ATTB_PITCH * 2 * 4 + Tp * 3 * sizeof(float) + 16; };
         const size_t smem = smem_for((size_t)e->cfg.max_input_length);
         static bool configured = false;
+        static bool use_cuda_cores = false;
         if (!configured) {
             LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ATTB_MAX_T)));
+            LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ATTB_MAX_T)));
+            const char* sel = getenv("LMRL_ATTN_BWD");                    // "cuda" selects the CUDA-core kernel (cross-check in the tests)
+            use_cuda_cores = sel && sel[0] == 'c';
             configured = true;
         }
-        attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.t_cap, 0.125f, Tr.dqkv);
+        if (use_cuda_cores)
+            attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.t_cap, 0.125f, Tr.dqkv);
+        else
+            attn_bwd_mma_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.att, G.rows, D.n_head, d, G.t_cap, 0.125f,
+                                                                              Tr.dqkv);
     }
     // ---- attn.c_attn: qkv = xn1 . Wqkv + b
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.xn1, M_dev, d, Tr.tA, Mp, nullptr);
