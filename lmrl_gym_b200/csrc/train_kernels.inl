@@ -724,15 +724,13 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
         auto smem_for = [](size_t T) { const size_t Tp = (T + 15) / 16 * 16; return Tp * ATTB_PITCH * 2 * 4 + Tp * 3 * sizeof(float) + 16; };
         const size_t smem = smem_for((size_t)e->cfg.max_input_length);
         static bool configured = false;
-        static bool use_cuda_cores = false;
         if (!configured) {
             LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ATTB_MAX_T)));
             LMRL_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(ATTB_MAX_T)));
-            const char* sel = getenv("LMRL_ATTN_BWD");                    // "cuda" selects the CUDA-core kernel (cross-check in the tests)
-            use_cuda_cores = sel && sel[0] == 'c';
             configured = true;
         }
-        if (use_cuda_cores)
+        const char* sel = getenv("LMRL_ATTN_BWD");                        // "cuda" selects the CUDA-core kernel (cross-check in the tests)
+        if (sel && sel[0] == 'c')
             attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.t_cap, 0.125f, Tr.dqkv);
         else
             attn_bwd_mma_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.att, G.rows, D.n_head, d, G.t_cap, 0.125f,
