@@ -257,6 +257,20 @@ int lmrl_train_enable(lmrl_engine* e, int32_t max_rows, int32_t max_scored_rows)
 int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const float* dlogprob,
                           const float* dvalue, float temperature, const lmrl_gpt2_grads* grads);
 
+/* the same with ppo_loss_fn (ppo/base_interface.py:71-142) differentiated ON THE DEVICE: one forward with saved activations yields the
+ * log-probs of the action tokens and the LinearHead values, the loss gradient with respect to them is formed in the LM-head / value
+ * kernels, and the backward pass continues as in lmrl_policy_grad_host.  HOST arrays [n][pitch], index t = quantities of position t
+ * (the token predicted there is tokens[t+1]); should_take_action[t] != 0 marks the action tokens (the loss mask).
+ * loss_out[0..12] as lmrl_ppo_loss_host (total, policy, value, values_error, value clipfrac, approx_kl, policy clipfrac, ratio, ...). */
+typedef struct lmrl_ppo_batch {
+    const uint8_t* should_take_action;
+    const float* old_logprobs; const float* old_values; const float* old_advantages; const float* old_returns;
+    double cliprange_value, cliprange, value_loss_coef;
+    double* loss_out;            /* [16] or NULL */
+} lmrl_ppo_batch;
+int lmrl_ppo_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const lmrl_ppo_batch* batch,
+                       const lmrl_gpt2_grads* grads);
+
 /* optax.adamw(learning_rate, b1, b2, eps, weight_decay[, mask]) (train_ppo_gpt2.py:144-165) over one flat fp32 segment, in place.
  * DEVICE pointers, enqueued on the engine stream (lmrl_stream), no synchronisation; step is 1-based; grad_scale multiplies the
  * gradient first (1 / world_size after a summing all-reduce).  Segments under the weight-decay mask pass weight_decay = 0. */

@@ -57,6 +57,12 @@ class lmrl_gpt2_grads(C.Structure):
                 ("lnf_g", _PF), ("lnf_b", _PF), ("vh_w", _PF), ("vh_b", _PF)]
 
 
+class lmrl_ppo_batch(C.Structure):
+    _fields_ = [("should_take_action", C.c_void_p), ("old_logprobs", C.c_void_p), ("old_values", C.c_void_p), ("old_advantages", C.c_void_p),
+                ("old_returns", C.c_void_p), ("cliprange_value", C.c_double), ("cliprange", C.c_double), ("value_loss_coef", C.c_double),
+                ("loss_out", C.c_void_p)]
+
+
 class lmrl_sampling(C.Structure):
     _fields_ = [("temperature", C.c_float), ("do_sample", C.c_int32), ("seed", C.c_uint64), ("top_k", C.c_int32), ("top_p", C.c_float)]
 
@@ -108,6 +114,7 @@ SYMBOLS = {
     "lmrl_rollout_chains_host": (C.c_int, [_V, _I, _I, _V, _V, _V, _V, _V, _V]),
     "lmrl_train_enable": (C.c_int, [_V, _I, _I]),
     "lmrl_policy_grad_host": (C.c_int, [_V, _V, _V, _I, _I, _V, _V, C.c_float, C.POINTER(lmrl_gpt2_grads)]),
+    "lmrl_ppo_grad_host": (C.c_int, [_V, _V, _V, _I, _I, C.POINTER(lmrl_ppo_batch), C.POINTER(lmrl_gpt2_grads)]),
     "lmrl_adamw_dev": (C.c_int, [_V, _V, _V, _V, _V, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_double]),
     "lmrl_rollout_host": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),
     "lmrl_rollout_dev": (C.c_int, [_V, _I, _V, _V, _I, C.POINTER(lmrl_sampling), C.POINTER(lmrl_rollout_out)]),

@@ -496,6 +496,66 @@ __global__ void dlogits_kernel(const float* __restrict__ logits, int n_vocab, in
     }
 }
 
+// Fused PPO variant of dlogits_kernel: the row's log-prob is formed from the dumped logits and the policy part of ppo_loss_fn
+// (ppo/base_interface.py:113-127) is differentiated in place:  ratio = exp(lp - old_lp),  loss term = max(-A ratio, -A clip(ratio)),
+// g = d term / d lp / n.  acc[0..3] (double) += policy term, ratio - 1 - log ratio, clip indicator, ratio.
+__global__ void dlogits_ppo_kernel(const float* __restrict__ logits, int n_vocab, int v_pad, const int* __restrict__ targets, const float* __restrict__ old_lp,
+                                   const float* __restrict__ adv, const int* __restrict__ n_dev, float ratio_lo, float ratio_hi, __nv_bfloat16* __restrict__ dl,
+                                   double* __restrict__ acc) {
+    __shared__ float red[256];
+    const int r = blockIdx.x;
+    __nv_bfloat16* o = dl + (size_t)r * v_pad;
+    const int n = *n_dev;
+    if (r >= n) { for (int c = threadIdx.x; c < v_pad; c += blockDim.x) o[c] = __float2bfloat16(0.f); return; }
+    const float* l = logits + (size_t)r * n_vocab;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < n_vocab; c += blockDim.x) mx = fmaxf(mx, l[c]);
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    mx = red[0];
+    __syncthreads();
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < n_vocab; c += blockDim.x) sum += __expf(l[c] - mx);
+    red[threadIdx.x] = sum;
+    __syncthreads();
+    for (int s = 128; s; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    const float total = red[0], inv = 1.f / total;
+    const int tgt = targets[r];
+    const float lp = l[tgt] - mx - logf(total);
+    const float lr = lp - old_lp[r], ratio = expf(lr), A = adv[r];
+    const float pg1 = -A * ratio, pg2 = -A * fminf(fmaxf(ratio, ratio_lo), ratio_hi);
+    const bool clipped = pg2 > pg1;
+    const float dterm = (clipped && !(ratio >= ratio_lo && ratio <= ratio_hi)) ? 0.f : -A * ratio;
+    const float gr = dterm / (float)n;
+    if (threadIdx.x == 0) {
+        atomicAdd(acc + 0, (double)fmaxf(pg1, pg2)); atomicAdd(acc + 1, (double)((ratio - 1.f) - lr)); atomicAdd(acc + 2, clipped ? 1.0 : 0.0);
+        atomicAdd(acc + 3, (double)ratio);
+    }
+    for (int c = threadIdx.x; c < v_pad; c += blockDim.x) {
+        float v = 0.f;
+        if (c < n_vocab) v = gr * ((c == tgt ? 1.f : 0.f) - __expf(l[c] - mx) * inv);
+        o[c] = __float2bfloat16(v);
+    }
+}
+// value part of ppo_loss_fn (:101-111) on the scored rows: dv[row] = coef * 0.5 * d max((v - R)^2, (clip(v) - R)^2) / dv / n;
+// acc[4] += max(vf1, vf2), acc[5] += clip indicator, acc[6] += (v - R)^2, acc[7] += v
+__global__ void ppo_value_grad_kernel(const float* __restrict__ values, const int* __restrict__ rows, const float* __restrict__ old_v, const float* __restrict__ ret,
+                                      const int* __restrict__ n_dev, float cliprange_value, float coef, float* __restrict__ dv, double* __restrict__ acc) {
+    const int n = *n_dev;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int row = rows[r];
+    const float v = values[row], ov = old_v[r], R = ret[r];
+    const float lo = ov - cliprange_value, hi = ov + cliprange_value;
+    const float vc = fminf(fmaxf(v, lo), hi);
+    const float vf1 = (v - R) * (v - R), vf2 = (vc - R) * (vc - R);
+    const bool clipped = vf2 > vf1;
+    const float d = clipped ? ((v >= lo && v <= hi) ? 2.f * (vc - R) : 0.f) : 2.f * (v - R);
+    dv[row] = coef * 0.5f * d / (float)n;
+    atomicAdd(acc + 4, (double)fmaxf(vf1, vf2)); atomicAdd(acc + 5, clipped ? 1.0 : 0.0); atomicAdd(acc + 6, (double)vf1); atomicAdd(acc + 7, (double)v);
+}
+
 // dst[idx[r]] += src[r]   (rows of d floats)
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, const int* __restrict__ n_dev, int d, float* __restrict__ dst) {
     const int n = *n_dev;
@@ -560,6 +620,9 @@ struct TrainDev {
     float* dxs = nullptr;                      // [lp_cap][d] fp32
     int *lp_rows = nullptr, *lp_targets = nullptr;
     float *lp_g = nullptr, *dv = nullptr;      // [lp_cap], [m_cap]
+    float *lp_aux = nullptr;                   // [4][lp_cap] fused PPO step: old log-probs, advantages, old values, returns of the scored rows
+    float* values = nullptr;                   // [m_cap] LinearHead value of every row (fused PPO step)
+    double* loss_acc = nullptr;                // [8] loss sums of the fused PPO step
     unsigned long long* best = nullptr;
     uint64_t* row_key = nullptr;
 };
@@ -622,7 +685,7 @@ int lmrl_train_enable(lmrl_engine* e, int32_t max_rows, int32_t max_scored_rows)
           e->alloc(&Tr.xn1, M * d) | e->alloc(&Tr.hpre, M * ff) | e->alloc(&Tr.dxb, M * d) | e->alloc(&Tr.dxn, M * d) | e->alloc(&Tr.datt, M * d) |
           e->alloc(&Tr.dqkv, M * 3 * d) | e->alloc(&Tr.dh, M * ff) | e->alloc(&Tr.tA, t_elems) | e->alloc(&Tr.tB, (size_t)std::max(ff, 3 * d) * M) |
           e->alloc(&Tr.zero_bias, (size_t)std::max(ff, G.v_pad)) | e->alloc(&Tr.consts, 8) | e->alloc(&Tr.lp_logits, P * D.n_vocab) | e->alloc(&Tr.dl, P * G.v_pad) |
-          e->alloc(&Tr.dxs, P * d) | e->alloc(&Tr.lp_rows, P) | e->alloc(&Tr.lp_targets, P) | e->alloc(&Tr.lp_g, P) | e->alloc(&Tr.dv, M) | e->alloc(&Tr.best, P) |
+          e->alloc(&Tr.dxs, P * d) | e->alloc(&Tr.lp_rows, P) | e->alloc(&Tr.lp_targets, P) | e->alloc(&Tr.lp_g, P) | e->alloc(&Tr.dv, M) | e->alloc(&Tr.lp_aux, 4 * P) | e->alloc(&Tr.values, M) | e->alloc(&Tr.loss_acc, 8) | e->alloc(&Tr.best, P) |
           e->alloc(&Tr.row_key, P);
     if (rc) return -1;
     const int consts[8] = {d, 3 * d, ff, (int)G.v_pad, 0, (int)G.v_pad, 0, 0};      // [4] scored rows, [6] wte rows of the gradient: per call
@@ -750,12 +813,11 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
     return 0;
 }
 
-extern "C" {
-
-int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const float* dlogprob, const float* dvalue,
-                          float temperature, const lmrl_gpt2_grads* grads) {
+static int policy_grad_impl(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const float* dlogprob, const float* dvalue,
+                            float temperature, const lmrl_gpt2_grads* grads, const lmrl_ppo_batch* ppo) {
     LMRL_CHECK(e && e->has_gpt2 && e->gpt2->train && e->gpt2->train->ready, "lmrl_policy_grad: call lmrl_train_enable first");
-    LMRL_CHECK(tokens && n_tok && dlogprob && dvalue && grads, "lmrl_policy_grad: null argument");
+    LMRL_CHECK(tokens && n_tok && grads && (ppo || (dlogprob && dvalue)), "lmrl_policy_grad: null argument");
+    LMRL_CHECK(!ppo || (ppo->should_take_action && ppo->old_logprobs && ppo->old_values && ppo->old_advantages && ppo->old_returns), "lmrl_ppo_grad: null batch array");
     LMRL_CUDA(cudaSetDevice(e->device));
     Gpt2Dev& G = *e->gpt2;
     TrainDev& Tr = *G.train;
@@ -766,17 +828,19 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
     cudaStream_t st = e->stream;
     // rows in env order; scored rows = positions with a non-zero upstream log-prob gradient
     std::vector<int32_t> lp_rows, lp_targets;
-    std::vector<float> lp_g, dv;
+    std::vector<float> lp_g, dv, aux[4];
     int M = 0;
     for (int i = 0; i < n; ++i) {
         LMRL_CHECK(n_tok[i] >= 0 && n_tok[i] <= max_in && n_tok[i] <= pitch, "lmrl_policy_grad: sequence %d has %d tokens (max_input_length %d)", i, n_tok[i], max_in);
         for (int t = 0; t < n_tok[i]; ++t) {
             const size_t o = (size_t)i * pitch + t;
             LMRL_CHECK(tokens[o] >= 0 && tokens[o] < G.v_pad, "lmrl_policy_grad: token id %d out of range", tokens[o]);
-            dv.push_back(dvalue[o]);
-            if (t + 1 < n_tok[i] && dlogprob[o] != 0.f) {
+            if (!ppo) dv.push_back(dvalue[o]);
+            if (t + 1 < n_tok[i] && (ppo ? ppo->should_take_action[o] != 0 : dlogprob[o] != 0.f)) {
                 LMRL_CHECK(tokens[o + 1] < D.n_vocab, "lmrl_policy_grad: scored target id %d is a padding id", tokens[o + 1]);
-                lp_rows.push_back(M + t); lp_targets.push_back(tokens[o + 1]); lp_g.push_back(dlogprob[o]);
+                lp_rows.push_back(M + t); lp_targets.push_back(tokens[o + 1]);
+                if (ppo) { aux[0].push_back(ppo->old_logprobs[o]); aux[1].push_back(ppo->old_advantages[o]); aux[2].push_back(ppo->old_values[o]); aux[3].push_back(ppo->old_returns[o]); }
+                else lp_g.push_back(dlogprob[o]);
             }
         }
         M += n_tok[i];
@@ -787,11 +851,21 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
     LMRL_CHECK(n <= e->cfg.max_envs, "lmrl_policy_grad: %d sequences exceed engine capacity %d", n, e->cfg.max_envs);
     const int Mp = (M + 63) / 64 * 64;
     if (load_prompts(e, tokens, n_tok, pitch, n)) return -1;
-    LMRL_CUDA(cudaMemcpyAsync(Tr.dv, dv.data(), sizeof(float) * M, cudaMemcpyHostToDevice, st));
+    if (ppo) {
+        LMRL_CUDA(cudaMemsetAsync(Tr.dv, 0, sizeof(float) * M, st));
+        LMRL_CUDA(cudaMemsetAsync(Tr.loss_acc, 0, sizeof(double) * 8, st));
+    } else {
+        LMRL_CUDA(cudaMemcpyAsync(Tr.dv, dv.data(), sizeof(float) * M, cudaMemcpyHostToDevice, st));
+    }
     if (n_lp) {
         LMRL_CUDA(cudaMemcpyAsync(Tr.lp_rows, lp_rows.data(), sizeof(int32_t) * n_lp, cudaMemcpyHostToDevice, st));
         LMRL_CUDA(cudaMemcpyAsync(Tr.lp_targets, lp_targets.data(), sizeof(int32_t) * n_lp, cudaMemcpyHostToDevice, st));
-        LMRL_CUDA(cudaMemcpyAsync(Tr.lp_g, lp_g.data(), sizeof(float) * n_lp, cudaMemcpyHostToDevice, st));
+        if (ppo) {
+            for (int k = 0; k < 4; ++k)
+                LMRL_CUDA(cudaMemcpyAsync(Tr.lp_aux + (size_t)k * Tr.lp_cap, aux[k].data(), sizeof(float) * n_lp, cudaMemcpyHostToDevice, st));
+        } else {
+            LMRL_CUDA(cudaMemcpyAsync(Tr.lp_g, lp_g.data(), sizeof(float) * n_lp, cudaMemcpyHostToDevice, st));
+        }
     }
     const int call_consts[3] = {n_lp, (int)G.v_pad, grads->n_vocab_rows};
     LMRL_CHECK(grads->n_vocab_rows > 0 && grads->n_vocab_rows <= G.v_pad, "lmrl_policy_grad: grads->n_vocab_rows %d out of range", grads->n_vocab_rows);
@@ -840,7 +914,11 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
         h.do_sample = 0; h.n_vocab = D.n_vocab; h.logits_out = Tr.lp_logits;
         if (launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, (size_t)Tr.m_cap, G.v_pad, 4)) return -1;
         const float inv_temp = 1.0f / (temperature > 0.f ? temperature : 1.0f);
-        dlogits_kernel<<<n_lp_pad, 256, 0, st>>>(Tr.lp_logits, D.n_vocab, G.v_pad, Tr.lp_targets, Tr.lp_g, n_lp_dev, inv_temp, Tr.dl);
+        if (ppo)
+            dlogits_ppo_kernel<<<n_lp_pad, 256, 0, st>>>(Tr.lp_logits, D.n_vocab, G.v_pad, Tr.lp_targets, Tr.lp_aux, Tr.lp_aux + Tr.lp_cap, n_lp_dev,
+                                                         (float)(1.0 - ppo->cliprange), (float)(1.0 + ppo->cliprange), Tr.dl, Tr.loss_acc);
+        else
+            dlogits_kernel<<<n_lp_pad, 256, 0, st>>>(Tr.lp_logits, D.n_vocab, G.v_pad, Tr.lp_targets, Tr.lp_g, n_lp_dev, inv_temp, Tr.dl);
         // dgrad: d(LN_f out)[scored rows] = dl . wte      (fp32, then scattered into dfx)
         LMRL_CUDA(cudaMemsetAsync(Tr.dxs, 0, sizeof(float) * (size_t)n_lp_pad * d, st));
         GemmArgs g{};
@@ -856,6 +934,15 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
     }
     mark("lm_head_backward");
     // ---- value head (LinearHead on the fp32 final LayerNorm), then ln_f
+    if (ppo && n_lp) {                               // values of every row, then the value part of the loss on the scored rows
+        ValueHeadArgs va{};
+        va.slot_q1 = va.slot_q2 = va.slot_v = -1; va.targets = G.rows.row_tok;
+        va.x = G.x; va.lnf_g = T.lnf_g; va.lnf_b = T.lnf_b; va.lin_w = G.vh[0].lin_w; va.lin_b = G.vh[0].lin_b; va.d = d; va.eps = D.ln_eps; va.has_lin = 1;
+        va.v_out = Tr.values;
+        LMRL_K(value_heads_kernel, std::max(1, std::min((M + 7) / 8, G.sm_count * 8)), 256, 0, st, G.rows.M, va);
+        ppo_value_grad_kernel<<<(n_lp + 255) / 256, 256, 0, st>>>(Tr.values, Tr.lp_rows, Tr.lp_aux + 2 * (size_t)Tr.lp_cap, Tr.lp_aux + 3 * (size_t)Tr.lp_cap, Tr.consts + 4,
+                                                                  (float)ppo->cliprange_value, (float)ppo->value_loss_coef, Tr.dv, Tr.loss_acc);
+    }
     if (grads->vh_w)
         value_head_bwd_kernel<<<G.sm_count * 2, 256, (d + 1) * sizeof(float), st>>>(G.x, T.lnf_g, T.lnf_b, G.vh[0].lin_w, Tr.dv, d, D.ln_eps, G.rows.M, Tr.dfx,
                                                                                      grads->vh_w, grads->vh_b);
@@ -885,7 +972,30 @@ int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* 
         fprintf(stderr, "\n");
         for (auto& m : marks) cudaEventDestroy(m.second);
     }
+    if (ppo && ppo->loss_out) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        LMRL_CUDA(cudaMemcpy(acc, Tr.loss_acc, sizeof acc, cudaMemcpyDeviceToHost));
+        const double cnt = n_lp > 0 ? (double)n_lp : 1.0;
+        const double pg = acc[0] / cnt, vf = 0.5 * acc[4] / cnt;
+        double* o = ppo->loss_out;
+        o[0] = pg + ppo->value_loss_coef * vf; o[1] = pg; o[2] = vf; o[3] = acc[6] / cnt; o[4] = acc[5] / cnt; o[5] = acc[1] / cnt; o[6] = acc[2] / cnt;
+        o[7] = acc[3] / cnt; o[8] = cnt / std::max(1.0, (double)M); o[9] = acc[7] / cnt; o[10] = 0.0; o[11] = 0.0; o[12] = (double)n_lp;
+        o[13] = o[14] = o[15] = 0.0;
+    }
     return 0;
+}
+
+extern "C" {
+
+int lmrl_policy_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const float* dlogprob, const float* dvalue,
+                          float temperature, const lmrl_gpt2_grads* grads) {
+    return policy_grad_impl(e, tokens, n_tok, pitch, n, dlogprob, dvalue, temperature, grads, nullptr);
+}
+
+int lmrl_ppo_grad_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, const lmrl_ppo_batch* batch, const lmrl_gpt2_grads* grads) {
+    LMRL_CHECK(batch, "lmrl_ppo_grad: null batch");
+    LMRL_CHECK(e && e->gpt2 && e->gpt2->vh[0].has_lin, "lmrl_ppo_grad: the LinearHead value head (head set 0) is not loaded");
+    return policy_grad_impl(e, tokens, n_tok, pitch, n, nullptr, nullptr, 1.0f, grads, batch);
 }
 
 }  // extern "C"

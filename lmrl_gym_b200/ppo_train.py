@@ -7,7 +7,7 @@ Mirrors the data flow of ``LLM_RL/algorithms/ppo/train.py::train_loop`` (:138-47
     episodes -> token trajectory chains               -> exported by the device (lmrl_rollout_chains_host); text path as fall-back
     get_ppo_data_from_token_trajectory_chain          -> device forward of policy / initial policy / value head + device GAE (ppo.py)
     kl_controller.update(mean_kl, train_bsize)        -> train_ppo_gpt2.py:352-353
-    epochs x minibatches of PPOTrain.step             -> ``TorchPPOTrain.step`` below
+    epochs x minibatches of PPOTrain.step             -> ``B200PPOTrain.step`` below
     policy.set_params(new params)                     -> ppo/train.py:244, 438 (device-to-device weight hand-over)
 
 The gradient step restates ``GPT2PPOTrain._step`` (ppo/gpt2/interface.py:72-211: policy forward, LinearHead values, ``ppo_loss_fn``,
@@ -20,7 +20,7 @@ AdamW(b1 0.9, b2 0.95, eps 1e-8, weight decay masked off LayerNorm and biases, t
   backward="torch"  LIBRARY path: torch autograd on torch/cuBLAS kernels — the comparison baseline (and the CPU test vehicle).
 
 Gradients are summed over ranks with ``torch.distributed.all_reduce`` (NCCL; plumbing) where the reference relies on pjit data parallelism.
-The class keeps its historical name; fp32 master weights live in torch tensors either way.
+fp32 master weights live in torch tensors (device memory, plumbing) either way.
 """
 from __future__ import annotations
 
@@ -129,7 +129,7 @@ def ppo_loss_grads(attention_mask, logprobs, values, should_take_action, old_log
     return float(loss), {k: float(x) for k, x in logs.items()}, dlogprobs.astype(np.float32), dvalues.astype(np.float32)
 
 
-class TorchPPOTrain:
+class B200PPOTrain:
     """fp32 master weights on the GPU as torch tensors (HF GPT-2 layout, the same dict layout as ``init_gpt2_params``) + LinearHead."""
 
     def __init__(self, engine: Engine, policy_params: Dict, value_head_params: Dict, config: Optional[GPT2Config] = None, *, lr: float = 1e-5,
@@ -296,30 +296,8 @@ class TorchPPOTrain:
         grp, o, shape = self._views[name]
         return self.gflat[grp][o:o + int(np.prod(shape))]
 
-    def _b200_grads(self, batch: Dict[str, np.ndarray]):
-        """Forward (token log-probs + values) and backward on the engine: ``lmrl_forward_host`` -> ``ppo_loss_grads`` (closed form) ->
-        ``lmrl_policy_grad_host`` accumulating into the flat gradient buffers."""
-        from .value_inference import forward_tokens
-        e = self._lmrl_engine
-        ids = np.asarray(batch["input_ids"])
-        real = ids != self.pad_token_id
-        lens = real.sum(axis=1).astype(np.int32)
-        seqs = [ids[i, :lens[i]] for i in range(ids.shape[0])]
-        T = ids.shape[1]
-        pitch = max(8, T)
-        fw = forward_tokens(e, 0, 0, seqs, logprobs=True, v=True, pitch=pitch)
-        loss, logs, dlp, dv = ppo_loss_grads(real[:, 1:].astype(np.float32), fw["logprobs"][:, :T - 1], fw["v"][:, :T - 1], batch["should_take_action"],
-                                             batch["old_logprobs"], batch["old_values"], batch["old_advantages"], batch["old_returns"],
-                                             cliprange_value=self.cliprange_value, cliprange=self.cliprange, value_loss_coef=self.value_loss_coef)
-        toks = np.zeros((ids.shape[0], pitch), np.int32)
-        toks[:, :T] = np.where(real, ids, 0)
-        dlp_p, dv_p = np.zeros((ids.shape[0], pitch), np.float32), np.zeros((ids.shape[0], pitch), np.float32)
-        dlp_p[:, :T - 1], dv_p[:, :T - 1] = dlp, dv
-        for g in self.gflat:
-            g.zero_()
-        self.torch.cuda.synchronize(self.device)
+    def _grad_struct(self, keep: list):
         L = self.config.n_layer
-        keep = []
         fp = lambda name: C.cast(C.c_void_p(self._grad_view(name).data_ptr()), _lib._PF)  # noqa: E731
         gs = _lib.lmrl_gpt2_grads()
         gs.wte, gs.n_vocab_rows, gs.wpe = fp("wte"), int(self._views["wte"][2][0]), fp("wpe")
@@ -328,8 +306,52 @@ class TorchPPOTrain:
             ptrs = (_lib._PF * L)(*[fp(f"h{i}.{key}") for i in range(L)])
             keep.append(ptrs)
             setattr(gs, key, C.cast(ptrs, _lib._PPF))
-        check(e.lib.lmrl_policy_grad_host(e.handle, toks.ctypes.data, lens.ctypes.data, pitch, ids.shape[0], dlp_p.ctypes.data, dv_p.ctypes.data,
-                                          C.c_float(1.0), C.byref(gs)))
+        return gs
+
+    def _b200_grads(self, batch: Dict[str, np.ndarray], fused: bool = True):
+        """Gradients of the PPO minibatch loss into the flat gradient buffers, on the engine.
+
+        fused=True   one call (``lmrl_ppo_grad_host``): a single forward with saved activations, ``ppo_loss_fn`` differentiated on the
+                     device inside the LM-head / value kernels, backward pass.
+        fused=False  the chain rule split on the host: ``lmrl_forward_host`` -> ``ppo_loss_grads`` (closed form, numpy float64) ->
+                     ``lmrl_policy_grad_host``; kept as the cross-check of the fused kernels."""
+        from .value_inference import forward_tokens
+        e = self._lmrl_engine
+        ids = np.asarray(batch["input_ids"])
+        real = ids != self.pad_token_id
+        lens = np.ascontiguousarray(real.sum(axis=1).astype(np.int32))
+        n, T = ids.shape
+        pitch = max(8, T)
+        toks = np.zeros((n, pitch), np.int32)
+        toks[:, :T] = np.where(real, ids, 0)
+        for g in self.gflat:
+            g.zero_()
+        keep: list = []
+        gs = self._grad_struct(keep)
+        if fused:
+            def pad(a, dtype):
+                out = np.zeros((n, pitch), dtype)
+                out[:, :T - 1] = a
+                return out
+            sta = pad(np.asarray(batch["should_take_action"], dtype=bool) & real[:, 1:], np.uint8)
+            arrs = [pad(np.asarray(batch[k], dtype=np.float32), np.float32) for k in ("old_logprobs", "old_values", "old_advantages", "old_returns")]
+            out = np.zeros(16, np.float64)
+            pb = _lib.lmrl_ppo_batch(should_take_action=sta.ctypes.data, old_logprobs=arrs[0].ctypes.data, old_values=arrs[1].ctypes.data,
+                                     old_advantages=arrs[2].ctypes.data, old_returns=arrs[3].ctypes.data, cliprange_value=self.cliprange_value,
+                                     cliprange=self.cliprange, value_loss_coef=self.value_loss_coef, loss_out=out.ctypes.data)
+            self.torch.cuda.synchronize(self.device)
+            check(e.lib.lmrl_ppo_grad_host(e.handle, toks.ctypes.data, lens.ctypes.data, pitch, n, C.byref(pb), C.byref(gs)))
+            logs = dict(total_loss=out[0], policy_loss=out[1], value_loss=out[2], approx_kl=out[5], policy_clipfrac=out[6], value_clipfrac=out[4], ratio=out[7])
+            return float(out[0]), {k: float(v) for k, v in logs.items()}
+        seqs = [ids[i, :lens[i]] for i in range(n)]
+        fw = forward_tokens(e, 0, 0, seqs, logprobs=True, v=True, pitch=pitch)
+        loss, logs, dlp, dv = ppo_loss_grads(real[:, 1:].astype(np.float32), fw["logprobs"][:, :T - 1], fw["v"][:, :T - 1], batch["should_take_action"],
+                                             batch["old_logprobs"], batch["old_values"], batch["old_advantages"], batch["old_returns"],
+                                             cliprange_value=self.cliprange_value, cliprange=self.cliprange, value_loss_coef=self.value_loss_coef)
+        dlp_p, dv_p = np.zeros((n, pitch), np.float32), np.zeros((n, pitch), np.float32)
+        dlp_p[:, :T - 1], dv_p[:, :T - 1] = dlp, dv
+        self.torch.cuda.synchronize(self.device)
+        check(e.lib.lmrl_policy_grad_host(e.handle, toks.ctypes.data, lens.ctypes.data, pitch, n, dlp_p.ctypes.data, dv_p.ctypes.data, C.c_float(1.0), C.byref(gs)))
         return loss, logs
 
     # ---- weight hand-over to the rollout engine (device to device; policy.set_params of ppo/train.py:244, 438) -------
@@ -359,7 +381,10 @@ class TorchPPOTrain:
         return dict(wte=g(P["wte"]), wpe=g(P["wpe"]), lnf_g=g(P["lnf_g"]), lnf_b=g(P["lnf_b"]), layers=[{k: g(L[k]) for k in _LAYER_KEYS} for L in P["layers"]])
 
 
-def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: TorchPPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
+TorchPPOTrain = B200PPOTrain          # earlier name, kept for callers that select backward="torch"
+
+
+def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
                    epochs: int = 1, train_bsize: int = 32, max_length: int = 128, gamma: float = 1.0, lam: float = 0.95,
                    use_advantage_whitening: bool = True, seed_generator=None, rng: Optional[np.random.Generator] = None,
                    max_steps_per_round: Optional[int] = None, use_device_chains: bool = True, on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:

@@ -53,7 +53,7 @@ def main():
     env = B200WordleEnv(eng, "wordle_official.txt", bad_word_reward=-10.0)          # train_ppo_gpt2.py:211
     pol = B200GPT2Policy(eng, params, cfg, seed=rank)
     inf = P.B200PPOInference(eng, None, lin, initial_policy_params=params, config=cfg, pad_token_id=tok.pad_token_id)
-    trainer = T.TorchPPOTrain(eng, params, lin, cfg, lr=1e-5, pad_token_id=tok.pad_token_id, backward=args.backward, max_rows=args.train_bsize * 264, max_scored_rows=args.train_bsize * 264)
+    trainer = T.B200PPOTrain(eng, params, lin, cfg, lr=1e-5, pad_token_id=tok.pad_token_id, backward=args.backward, max_rows=args.train_bsize * 264, max_scored_rows=args.train_bsize * 264)
     seeds = seed_generator(0)
     for _ in range(rank * B * args.rounds):          # contiguous shards of one seed stream
         next(seeds)

@@ -10,7 +10,7 @@ params = init_gpt2_params(cfg, seed=5)
 lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 28).astype(np.float32), bias=np.zeros(1, np.float32)))
 eng = Engine(max_envs=64, max_input_length=264, max_new_tokens=6, tokenizer=tok)
 B200GPT2Policy(eng, params, cfg)
-tr = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-5, max_rows=32 * 264, max_scored_rows=32 * 264)
+tr = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-5, max_rows=32 * 264, max_scored_rows=32 * 264)
 b, t = 32, 262
 ids = rng.integers(0, cfg.n_vocab, (b, t)).astype(np.int32)
 sta = rng.random((b, t - 1)) < 0.45

@@ -1,5 +1,5 @@
 """The hand-written backward pass of the policy + value head (csrc/train_kernels.inl, lmrl_policy_grad_host) against torch autograd of
-the same network in fp32 on the GPU (the library path of ppo_train.TorchPPOTrain, itself checked against the oracle GPT-2 on the CPU):
+the same network in fp32 on the GPU (the library path of ppo_train.B200PPOTrain, itself checked against the oracle GPT-2 on the CPU):
 every parameter gradient of a PPO minibatch — embeddings, all four matrices + biases and both LayerNorms of every layer, ln_f, the tied
 LM head (through wte) and the LinearHead value head.  The engine computes with bf16 operands and fp32 accumulation, so the bar is a
 relative L2 error <= 2e-2 and a cosine >= 0.9995 per tensor (measured: worst 4e-3 / 0.99999) (weights are rounded to bf16 first so both sides hold the same numbers)."""
@@ -45,8 +45,8 @@ def test_handwritten_backward_matches_autograd():
     lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 16).astype(np.float32), bias=np.asarray([0.1], np.float32)))
     eng = Engine(max_envs=32, max_input_length=64, max_new_tokens=4, tokenizer=tok)
     B200GPT2Policy(eng, params, cfg)
-    ref = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch")
-    b2 = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", max_rows=2048, max_scored_rows=1024)
+    ref = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch")
+    b2 = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", max_rows=2048, max_scored_rows=1024)
     batch = make_batch(rng, cfg, tok.pad_token_id, None)
     # old log-probs near the current ones so that both the clipped and the unclipped branch of the policy loss are taken
     ids = batch["input_ids"]
@@ -57,8 +57,18 @@ def test_handwritten_backward_matches_autograd():
         f.grad = None
     loss_ref, logs_ref = ref.loss(batch)
     loss_ref.backward()
+    # split path (host-side closed-form loss gradients) first, then the fused device path: same gradients, same loss
+    loss_s, logs_s = b2._b200_grads(batch, fused=False)
+    torch.cuda.synchronize()
+    g_split = [g.clone() for g in b2.gflat]
     loss_b, logs_b = b2._b200_grads(batch)
     torch.cuda.synchronize()
+    assert abs(loss_s - loss_b) <= 2e-3 * max(1.0, abs(loss_s)), (loss_s, loss_b)
+    for k in ("policy_loss", "value_loss", "approx_kl", "policy_clipfrac", "value_clipfrac", "ratio"):
+        assert abs(logs_s[k] - logs_b[k]) <= 2e-3 * max(1.0, abs(logs_s[k])), (k, logs_s[k], logs_b[k])
+    for a, c in zip(g_split, b2.gflat):
+        rel = float((a.double() - c.double()).norm() / a.double().norm())
+        assert rel <= 1e-2, rel
     assert abs(float(loss_ref.detach()) - loss_b) <= 2e-2 * max(1.0, abs(loss_b)), (float(loss_ref.detach()), loss_b)
     assert 0.05 < logs_b["policy_clipfrac"] < 0.95
     worst = []
@@ -115,8 +125,8 @@ def test_handwritten_backward_gpt2_small_and_training_step():
     lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 28).astype(np.float32), bias=np.zeros(1, np.float32)))
     eng = Engine(max_envs=64, max_input_length=128, max_new_tokens=6, tokenizer=tok)
     pol = B200GPT2Policy(eng, params, cfg)
-    ref = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch", lr=1e-5)
-    b2 = T.TorchPPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-5, max_rows=8192, max_scored_rows=4096)
+    ref = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch", lr=1e-5)
+    b2 = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", lr=1e-5, max_rows=8192, max_scored_rows=4096)
     batch = make_batch(rng, cfg, tok.pad_token_id, None, b=32, t=128)
     ids = batch["input_ids"]
     lens = (ids != tok.pad_token_id).sum(1)

@@ -26,7 +26,7 @@ def test_ppo_rounds_update_the_engine_policy(backward):
     env = B200WordleEnv(eng, "wordle_official.txt", bad_word_reward=-10.0)
     pol = B200GPT2Policy(eng, params, cfg, seed=0)
     inf = P.B200PPOInference(eng, None, lin, initial_policy_params=params, config=cfg, pad_token_id=tok.pad_token_id)
-    trainer = T.TorchPPOTrain(eng, params, lin, cfg, lr=1e-4, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward=backward, max_rows=16 * 192,
+    trainer = T.B200PPOTrain(eng, params, lin, cfg, lr=1e-4, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward=backward, max_rows=16 * 192,
                               max_scored_rows=16 * 192)
     prompts = [tok.encode("Wordle:\n"), tok.encode("Wordle:\nc r a n e\nb y g b b\n")]
     before = pol.logits(prompts)

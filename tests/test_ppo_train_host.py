@@ -1,4 +1,4 @@
-"""The PPO gradient step (lmrl_gym_b200/ppo_train.py::TorchPPOTrain — the torch-autograd LIBRARY path, see its docstring) on the CPU:
+"""The PPO gradient step (lmrl_gym_b200/ppo_train.py::B200PPOTrain — the torch-autograd LIBRARY path, see its docstring) on the CPU:
 its forward equals the oracle GPT-2, its loss equals the reference-pinned oracle ppo_loss, a step lowers the loss, and with two gloo
 ranks the all-reduced update keeps the replicas identical (the role of the NCCL gradient all-reduce in BASELINE.json configs[4])."""
 import os
@@ -32,7 +32,7 @@ def make_batch(rng, b=6, t=12):
 def make_trainer(seed=0, lr=1e-3):
     params = init_gpt2_params(CFG, seed=seed)
     lin = dict(dense=dict(kernel=(np.random.default_rng(seed + 1).standard_normal((CFG.d_model, 1)) / 8).astype(np.float32), bias=np.asarray([0.1], np.float32)))
-    return T.TorchPPOTrain(None, params, lin, CFG, lr=lr, pad_token_id=PAD, activation_dtype="f32"), params, lin
+    return T.B200PPOTrain(None, params, lin, CFG, lr=lr, pad_token_id=PAD, activation_dtype="f32"), params, lin
 
 
 def test_forward_and_loss_match_oracle():
