@@ -41,16 +41,21 @@ __global__ void transpose_to_bf16_rows_kernel(const T* __restrict__ src, const i
     }
 }
 
-// out[c] += sum over rows of src[m][c]
+// out[c] += sum over rows of src[m][c].  Launched with enough row groups (gridDim.y) that a thread walks only a few rows, four loads in flight.
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ src, const int* __restrict__ M_dev, int C, float* __restrict__ out) {
     const int M = *M_dev;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    float acc = 0.f;
-    for (int m = blockIdx.y; m < M; m += gridDim.y) {
-        if constexpr (sizeof(T) == 4) acc += src[(size_t)m * C + c]; else acc += __bfloat162float(src[(size_t)m * C + c]);
-    }
+    auto ld = [&](int m) -> float {
+        if constexpr (sizeof(T) == 4) return src[(size_t)m * C + c]; else return __bfloat162float(src[(size_t)m * C + c]);
+    };
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int step = gridDim.y;
+    int m = blockIdx.y;
+    for (; m + 3 * step < M; m += 4 * step) { a0 += ld(m); a1 += ld(m + step); a2 += ld(m + 2 * step); a3 += ld(m + 3 * step); }
+    for (; m < M; m += step) a0 += ld(m);
+    const float acc = (a0 + a1) + (a2 + a3);
     if (acc != 0.f) atomicAdd(out + c, acc);
 }
 
@@ -59,21 +64,42 @@ __device__ __forceinline__ float gelu_new_grad(float x) {
     const float t = tanhf(k0 * (x + k1 * x * x * x));
     return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x * x);
 }
-// h = gelu_new(hpre)   (forward recompute: the FC GEMM stores the pre-activation, this makes the FC2 operand)
+// h = gelu_new(hpre)   (forward recompute: the FC GEMM stores the pre-activation, this makes the FC2 operand); 16-byte accesses, C % 8 == 0
 __global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ hpre, const int* __restrict__ M_dev, int C, __nv_bfloat16* __restrict__ h) {
-    const size_t n = (size_t)*M_dev * C;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        h[i] = __float2bfloat16(gelu_new(__bfloat162float(hpre[i])));
+    const size_t n8 = ((size_t)*M_dev * C) >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(hpre);
+    uint4* dst = reinterpret_cast<uint4*>(h);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 u = src[i];
+        __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(p[k]); p[k] = __floats2bfloat162_rn(gelu_new(f.x), gelu_new(f.y)); }
+        dst[i] = u;
+    }
 }
 // dhpre = dh * gelu'(hpre), in place over dh
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ hpre, const int* __restrict__ M_dev, int C, __nv_bfloat16* __restrict__ dh) {
-    const size_t n = (size_t)*M_dev * C;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dh[i] = __float2bfloat16(__bfloat162float(dh[i]) * gelu_new_grad(__bfloat162float(hpre[i])));
+    const size_t n8 = ((size_t)*M_dev * C) >> 3;
+    const uint4* src = reinterpret_cast<const uint4*>(hpre);
+    uint4* dst = reinterpret_cast<uint4*>(dh);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 x = src[i];
+        uint4 g = dst[i];
+        const __nv_bfloat162* px = reinterpret_cast<const __nv_bfloat162*>(&x);
+        __nv_bfloat162* pg = reinterpret_cast<__nv_bfloat162*>(&g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fx = __bfloat1622float2(px[k]), fg = __bfloat1622float2(pg[k]);
+            pg[k] = __floats2bfloat162_rn(fg.x * gelu_new_grad(fx.x), fg.y * gelu_new_grad(fx.y));
+        }
+        dst[i] = g;
+    }
 }
 
 // LayerNorm backward, one warp per row:  y = (x - mean) * rstd * g + b
-//   dx (+)= rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));   dg += dy * xhat;   db += dy      (CTA-level smem partials, then atomics)
+//   dx (+)= rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat));   dg += dy * xhat;   db += dy
+// A lane owns the columns lane, lane + 32, ...: its dg / db partial sums stay in registers over all the rows its warp visits and are
+// folded into the CTA's shared-memory row, then into global memory, once at the end.  d <= 1024.
 template <typename TDY>
 __global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const TDY* __restrict__ dy, int d, float eps,
                               const int* __restrict__ M_dev, float* __restrict__ dx, int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -82,33 +108,55 @@ __global__ void ln_bwd_kernel(const float* __restrict__ x, const float* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) ln_sm[c] = 0.f;
     __syncthreads();
+    float dgr[32], dbr[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { dgr[k] = 0.f; dbr[k] = 0.f; }
     for (int r = blockIdx.x * nwarp + warp; r < M; r += gridDim.x * nwarp) {
         const float* xr = x + (size_t)r * d;
         const TDY* dr = dy + (size_t)r * d;
+        float xv[32], dv[32];
         float s = 0.f;
-        for (int c = lane; c < d; c += 32) s += xr[c];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int c = lane + 32 * k;
+            xv[k] = 0.f; dv[k] = 0.f;
+            if (c < d) {
+                xv[k] = xr[c];
+                if constexpr (sizeof(TDY) == 4) dv[k] = dr[c]; else dv[k] = __bfloat162float(dr[c]);
+                s += xv[k];
+            }
+        }
         const float mean = warp_sum(s) / d;
         float q = 0.f;
-        for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) if (lane + 32 * k < d) { const float t = xv[k] - mean; q += t * t; }
         const float rstd = rsqrtf(warp_sum(q) / d + eps);
         float s1 = 0.f, s2 = 0.f;
-        for (int c = lane; c < d; c += 32) {
-            float dyc;
-            if constexpr (sizeof(TDY) == 4) dyc = dr[c]; else dyc = __bfloat162float(dr[c]);
-            const float xh = (xr[c] - mean) * rstd, dg = dyc * gamma[c];
-            s1 += dg; s2 += dg * xh;
-            atomicAdd(ln_sm + c, dyc * xh);
-            atomicAdd(ln_sm + d + c, dyc);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d) {
+                const float xh = (xv[k] - mean) * rstd, dg = dv[k] * gamma[c];
+                xv[k] = xh;
+                s1 += dg; s2 += dg * xh;
+                dgr[k] += dv[k] * xh; dbr[k] += dv[k];
+            }
         }
         s1 = warp_sum(s1) / d; s2 = warp_sum(s2) / d;
         float* o = dx + (size_t)r * d;
-        for (int c = lane; c < d; c += 32) {
-            float dyc;
-            if constexpr (sizeof(TDY) == 4) dyc = dr[c]; else dyc = __bfloat162float(dr[c]);
-            const float xh = (xr[c] - mean) * rstd;
-            const float v = rstd * (dyc * gamma[c] - s1 - xh * s2);
-            o[c] = accumulate ? o[c] + v : v;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d) {
+                const float v = rstd * (dv[k] * gamma[c] - s1 - xv[k] * s2);
+                o[c] = accumulate ? o[c] + v : v;
+            }
         }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const int c = lane + 32 * k;
+        if (c < d) { atomicAdd(ln_sm + c, dgr[k]); atomicAdd(ln_sm + d + c, dbr[k]); }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -764,14 +812,14 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
     transpose_to_bf16_rows_kernel<float><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.dx, M_dev, d, Tr.tB, Mp, Tr.dxb);          // dxb = bf16(dx), tB = dx^T
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(ff), dim3(32, 8), 0, st>>>(G.h, M_dev, ff, Tr.tA, Mp, nullptr);  // tA = h^T
     if (wgrad(Tr.tA, ff, c_ff, Tr.tB, d, gr.fc2_w)) return -1;
-    colsum_kernel<float><<<dim3((d + 127) / 128, 64), 128, 0, st>>>(Tr.dx, M_dev, d, gr.fc2_b);
+    colsum_kernel<float><<<dim3((d + 127) / 128, 512), 128, 0, st>>>(Tr.dx, M_dev, d, gr.fc2_b);
     if (dgrad(Tr.dxb, d, W.w_fc2, ff, Tr.dh)) return -1;                                                                  // dh = dx . Wfc2^T
     gelu_bwd_kernel<<<ew, 256, 0, st>>>(Tr.hpre, M_dev, ff, Tr.dh);                                                       // dh := dhpre
     // ---- mlp.c_fc: hpre = xn2 . Wfc + b
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(G.xn, M_dev, d, Tr.tA, Mp, nullptr);   // tA = xn2^T
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(ff), dim3(32, 8), 0, st>>>(Tr.dh, M_dev, ff, Tr.tB, Mp, nullptr); // tB = dhpre^T
     if (wgrad(Tr.tA, d, c_d, Tr.tB, ff, gr.fc_w)) return -1;
-    colsum_kernel<__nv_bfloat16><<<dim3((ff + 127) / 128, 64), 128, 0, st>>>(Tr.dh, M_dev, ff, gr.fc_b);
+    colsum_kernel<__nv_bfloat16><<<dim3((ff + 127) / 128, 256), 128, 0, st>>>(Tr.dh, M_dev, ff, gr.fc_b);
     if (dgrad(Tr.dh, ff, W.w_fc, d, Tr.dxn)) return -1;                                                                   // dxn2
     // ---- ln_2:  dx += LN'(x_mid) dxn2
     ln_bwd_kernel<__nv_bfloat16><<<G.sm_count * 2, 256, 2 * d * sizeof(float), st>>>(G.x, L.ln2_g, Tr.dxn, d, D.ln_eps, M_dev, Tr.dx, 1, gr.ln2_g, gr.ln2_b);
@@ -779,7 +827,7 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
     transpose_to_bf16_rows_kernel<float><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.dx, M_dev, d, Tr.tB, Mp, Tr.dxb);
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(G.att, M_dev, d, Tr.tA, Mp, nullptr);
     if (wgrad(Tr.tA, d, c_d, Tr.tB, d, gr.proj_w)) return -1;
-    colsum_kernel<float><<<dim3((d + 127) / 128, 64), 128, 0, st>>>(Tr.dx, M_dev, d, gr.proj_b);
+    colsum_kernel<float><<<dim3((d + 127) / 128, 512), 128, 0, st>>>(Tr.dx, M_dev, d, gr.proj_b);
     if (dgrad(Tr.dxb, d, W.w_proj, d, Tr.datt)) return -1;
     // ---- attention
     {
@@ -803,7 +851,7 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(d), dim3(32, 8), 0, st>>>(Tr.xn1, M_dev, d, Tr.tA, Mp, nullptr);
     transpose_to_bf16_rows_kernel<__nv_bfloat16><<<tgrid(3 * d), dim3(32, 8), 0, st>>>(Tr.dqkv, M_dev, 3 * d, Tr.tB, Mp, nullptr);
     if (wgrad(Tr.tA, d, c_d, Tr.tB, 3 * d, gr.attn_w)) return -1;
-    colsum_kernel<__nv_bfloat16><<<dim3((3 * d + 127) / 128, 64), 128, 0, st>>>(Tr.dqkv, M_dev, 3 * d, gr.attn_b);
+    colsum_kernel<__nv_bfloat16><<<dim3((3 * d + 127) / 128, 256), 128, 0, st>>>(Tr.dqkv, M_dev, 3 * d, gr.attn_b);
     if (dgrad(Tr.dqkv, 3 * d, W.w_qkv, d, Tr.dxn)) return -1;                                                             // dxn1
     // ---- ln_1:  dx += LN'(x_in) dxn1
     ln_bwd_kernel<__nv_bfloat16><<<G.sm_count * 2, 256, 2 * d * sizeof(float), st>>>(Tr.xsave + (size_t)l * Tr.m_cap * d, L.ln1_g, Tr.dxn, d, D.ln_eps, M_dev, Tr.dx, 1,
