@@ -134,7 +134,7 @@ class B200PPOTrain:
 
     def __init__(self, engine: Engine, policy_params: Dict, value_head_params: Dict, config: Optional[GPT2Config] = None, *, lr: float = 1e-5,
                  weight_decay: float = 0.0, cliprange_value: float = 0.2, cliprange: float = 0.2, value_loss_coef: float = 1.0,
-                 pad_token_id: Optional[int] = None, activation_dtype: str = "bf16", backward: str = "torch", max_rows: int = 16384,
+                 pad_token_id: Optional[int] = None, activation_dtype: str = "bf16", backward: Optional[str] = None, max_rows: int = 16384,
                  max_scored_rows: int = 8192):
         import torch
         self.torch = torch
@@ -174,6 +174,7 @@ class B200PPOTrain:
                                          lr=lr, betas=self.betas, eps=self.eps)
         self.steps = 0
         # backward = "b200": gradients from the engine's hand-written backward pass (csrc/train_kernels.inl) instead of torch autograd
+        backward = backward or ("b200" if engine is not None else "torch")
         self.backward = backward
         if backward == "b200":
             assert engine is not None, "the hand-written backward pass runs on the engine"
