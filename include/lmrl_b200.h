@@ -129,7 +129,8 @@ typedef struct lmrl_mlp_head {
 } lmrl_mlp_head;
 /* q2 may be NULL (MC returns: one head, wordle/mc/eval_mc_gpt2.py:103-116).  Switches the engine to the value-perturbed policy. */
 int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_head* q2, float beta);
-/* 0 = plain LM policy (logits of tower 0), 1 = value-perturbed policy */
+/* 0 = plain LM policy (logits of tower 0), 1 = value-perturbed policy (pi_beta + beta * min q),
+ * 2 = the pi_beta = None variant (logits = beta * min q, generation.py:118-119: only the value tower runs) */
 int lmrl_set_policy_kind(lmrl_engine* e, int32_t kind);
 
 /* ---- environments, text path (BatchedTextEnv.reset / .step, environment.py:56-69) ------------------------------- */

@@ -88,7 +88,7 @@ struct Gpt2Dev {
     TowerDev tw[3];                   // 0 policy / pi_beta, 1 value base (or PPO initial policy), 2 target value base (forward only; shares tower 1's KV slab)
     QHeadsDev qh;
     ValueHeadsDev vh[2];              // head sets of lmrl_forward_host: 0 online, 1 target
-    int policy_kind = 0;              // 0 = LM policy (logits of tower 0); 1 = value-perturbed (pi_beta + beta * min q)
+    int policy_kind = 0;              // 0 = LM policy (logits of tower 0); 1 = value-perturbed (pi_beta + beta * min q); 2 = beta * min q alone (pi_beta None)
     size_t kv_layer_stride = 0;       // elements between layers (covers K and V)
     // activations
     float* x = nullptr;
@@ -479,17 +479,18 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     note_pass_counts(e);
     if (mode == 0)
         LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows));
-    LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, Ln.rows, Ln.x));
-    const int n_towers = G.policy_kind == 1 ? 2 : 1;
+    // towers of this policy: 0 = LM policy; 0 and 1 = pi_beta + value base (kind 1); 1 alone = value base without pi_beta (kind 2)
+    const int t_first = G.policy_kind == 2 ? 1 : 0, t_last = G.policy_kind >= 1 ? 1 : 0;
+    LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[t_first].wte, G.tw[t_first].wpe, D.d_model, Ln.rows, Ln.x));
     // head operand buffers: the per-env sampling buffers, or the (larger) scoring buffers
     __nv_bfloat16* xl = score ? G.xs : Ln.xl;
     __nv_bfloat16* xl1 = score ? G.xs1 : Ln.xl1;
     const size_t xl_rows = score ? (size_t)G.s_cap : Ln.xl_rows;
     const int* head_n = score ? score->n_dev : Ln.rows.n_slots;
     const int* head_gather = score ? score->rows : Ln.rows.slot_last;
-    for (int t = 0; t < n_towers; ++t) {
+    for (int t = t_first; t <= t_last; ++t) {
         const TowerDev& T = G.tw[t];
-        if (t > 0) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, Ln.rows, Ln.x));
+        if (t > t_first) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, Ln.rows, Ln.x));
         if (tower_layers(e, T, mode, n_env)) return -1;
         // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
         LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
@@ -516,7 +517,7 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     GemmExtra hx;
     hx.a_cols = (size_t)G.xl_cols;
     const int kb_d = D.d_model / TC_BK;
-    if (G.policy_kind == 1) {
+    if (G.policy_kind >= 1) {
         // Q heads, first layer: xl[:, d + k*hidden ...] = beta * relu(xl1 · W1_k^T + b1_k)   (mlp_head.py:146-147; beta folded in here)
         const QHeadsDev& Q = G.qh;
         GemmArgs r{};
@@ -530,6 +531,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         h.n_acc = Q.n_q; h.n_seg = 2 * Q.n_q;
         h.seg[0] = {0, 0, 0, kb_d}; h.seg[1] = {0, kb_d, 1, kb_h};
         h.seg[2] = {1, 0, 0, kb_d}; h.seg[3] = {1, kb_d + kb_h, 2, kb_h};
+        if (G.policy_kind == 2) {                     // pi_beta is None: logits = beta * min_k q_k (generation.py:118-119) — no LM-head segment
+            h.n_seg = Q.n_q;
+            h.seg[0] = {0, kb_d, 1, kb_h}; h.seg[1] = {1, kb_d + kb_h, 2, kb_h};
+        }
         h.bias = Q.b2s[0]; h.bias2 = Q.b2s[1];
         hx.W1 = Q.w2[0]; hx.w1_cols = (size_t)Q.hidden;
         if (Q.n_q == 2) { hx.W2 = Q.w2[1]; hx.w2_cols = (size_t)Q.hidden; }
@@ -781,8 +786,8 @@ int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_he
 
 int lmrl_set_policy_kind(lmrl_engine* e, int32_t kind) {
     LMRL_CHECK(e && e->gpt2 && e->gpt2->tw[0].loaded, "lmrl_set_policy_kind: no GPT-2 parameters loaded");
-    LMRL_CHECK(kind == 0 || (kind == 1 && e->gpt2->tw[1].loaded && e->gpt2->qh.n_q > 0),
-               "lmrl_set_policy_kind: kind 1 (value-perturbed) needs the value tower and Q heads; kind must be 0 or 1");
+    LMRL_CHECK(kind == 0 || ((kind == 1 || kind == 2) && e->gpt2->tw[1].loaded && e->gpt2->qh.n_q > 0),
+               "lmrl_set_policy_kind: kinds 1 / 2 (value-perturbed with / without pi_beta) need the value tower and Q heads; kind must be 0, 1 or 2");
     e->gpt2->policy_kind = kind;
     return 0;
 }

@@ -261,15 +261,19 @@ class B200GPT2ValuePolicy(B200GPT2Policy):
 
     def __init__(self, engine: Engine, params: Tuple, config: Optional[GPT2Config] = None, beta: float = 16.0, **kw):
         pi_beta, base, q1, q2 = params
-        if pi_beta is None:
-            raise _lib.LmrlError("B200GPT2ValuePolicy needs pi_beta parameters (the pi_beta=None variant of generation.py:116-119 is not built)")
-        super().__init__(engine, pi_beta, config, **kw)
+        # pi_beta = None (generation.py:116-119: logits = beta * min q): the engine still wants a tower 0 (embedding tables of the row
+        # builder, buffer shapes), so the value base stands in for it and policy kind 2 skips its layer stack and its LM-head segment
+        super().__init__(engine, pi_beta if pi_beta is not None else base, config, **kw)
         self.beta = float(beta)
         _upload_params(engine, self.config, base, tower=1)
         _upload_q_heads(engine, q1, q2, self.beta)
+        if pi_beta is None:
+            check(engine.lib.lmrl_set_policy_kind(engine.handle, 2))
 
     def set_params(self, policy_params: Tuple) -> None:
         pi_beta, base, q1, q2 = policy_params
-        _upload_params(self._lmrl_engine, self.config, pi_beta, tower=0)
+        _upload_params(self._lmrl_engine, self.config, pi_beta if pi_beta is not None else base, tower=0)
         _upload_params(self._lmrl_engine, self.config, base, tower=1)
         _upload_q_heads(self._lmrl_engine, q1, q2, self.beta)
+        if pi_beta is None:
+            check(self._lmrl_engine.lib.lmrl_set_policy_kind(self._lmrl_engine.handle, 2))

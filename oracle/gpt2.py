@@ -119,9 +119,12 @@ def value_policy_last_logits(params, tokens: Sequence[int], n_head: int, n_vocab
     of the value base (:87; HF appends the post-ln_f state last).  ``emulate_bf16`` rounds where the engine rounds: both
     final hidden states and beta*relu(dense1) are stored as bf16 before the last matmul."""
     pi_beta, base, q1, q2 = params
-    h_pi = forward_hidden(pi_beta, tokens, n_head, emulate_bf16=emulate_bf16, weights_bf16=weights_bf16, **kw)[-1]
     h_v = forward_hidden(base, tokens, n_head, emulate_bf16=emulate_bf16, weights_bf16=weights_bf16, **kw)[-1]
-    pi_logits = h_pi @ _t(pi_beta["wte"], weights_bf16)[:n_vocab].T
+    if pi_beta is None:                      # generation.py:118-119: logits = beta * q
+        pi_logits = torch.zeros(n_vocab)
+    else:
+        h_pi = forward_hidden(pi_beta, tokens, n_head, emulate_bf16=emulate_bf16, weights_bf16=weights_bf16, **kw)[-1]
+        pi_logits = h_pi @ _t(pi_beta["wte"], weights_bf16)[:n_vocab].T
     if not emulate_bf16:
         qs = [mlp_head(h_v, q, weights_bf16)[:n_vocab] for q in (q1, q2) if q is not None]
         qmin = qs[0] if len(qs) == 1 else torch.minimum(qs[0], qs[1])

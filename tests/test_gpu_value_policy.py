@@ -39,13 +39,15 @@ def _params(cfg, two_heads=True, seed=0):
     return (init_gpt2_params(cfg, seed=seed), init_gpt2_params(cfg, seed=seed + 1), q1, q2)
 
 
-@pytest.mark.parametrize("two_heads", [True, False])
-def test_value_policy_logits_match_oracle(tok, two_heads):
+@pytest.mark.parametrize("two_heads,with_pi_beta", [(True, True), (False, True), (True, False), (False, False)])
+def test_value_policy_logits_match_oracle(tok, two_heads, with_pi_beta):
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2ValuePolicy
     from oracle import gpt2 as og
     cfg = _cfg()
     params = _params(cfg, two_heads)
+    if not with_pi_beta:
+        params = (None,) + params[1:]          # the pi_beta = None variant: logits = beta * min q (generation.py:118-119)
     eng = Engine(max_envs=160, max_input_length=64, max_new_tokens=4, tokenizer=tok)
     pol = B200GPT2ValuePolicy(eng, params, cfg, beta=BETA)
     rng = np.random.default_rng(0)
@@ -61,8 +63,9 @@ def test_value_policy_logits_match_oracle(tok, two_heads):
     print(f"value policy ({'ILQL 2 heads' if two_heads else 'MC 1 head'}): max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
     assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
     # the perturbation is really there: the engine's logits differ from pi_beta's own by about beta * q
-    pi_only = og.forward_last_logits(params[0], prompts[0], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
-    assert np.abs(got[0] - pi_only).mean() > 1.0
+    if with_pi_beta:
+        pi_only = og.forward_last_logits(params[0], prompts[0], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+        assert np.abs(got[0] - pi_only).mean() > 1.0
     eng.close()
 
 
