@@ -247,7 +247,8 @@ __device__ __forceinline__ void sample_chunk(const uint32_t r[32], int col0, flo
 }
 
 template <int EPI, int BN = TC_BN>
-__global__ void __launch_bounds__(TcCfg<EPI>::THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+// 128 registers per thread hold every epilogue without spills and leave room for an attention CTA beside the GEMM CTA on the same SM
+__global__ void __maxnreg__(128) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                                    const __grid_constant__ CUtensorMap tmW,
                                                                                    const __grid_constant__ CUtensorMap tmW1,
                                                                                    const __grid_constant__ CUtensorMap tmW2,

@@ -112,9 +112,10 @@ struct Gpt2Dev {
     Lane lane[3];
     Lane* cur = nullptr;              // lane the next tower_layers / forward_and_sample call runs on
     // fused rollouts may split the batch over lanes 1 and 2 (see lanes_usable).  Off by default: measured on B200 it is SLOWER
-    // (4096-episode Wordle rollout, graphs on: 215.1 ms one lane, 220.1 ms two lanes; letters variant 80.4 vs 82.6): a GEMM CTA
-    // (320 threads x 138 registers, 200 KB of shared memory) and an attention CTA (256 x 85 registers) do not fit one SM together, so
-    // the lanes' kernels serialise and each half-batch kernel is less efficient than the full-batch one.  Results are bit-identical.
+    // (4096-episode Wordle rollout, graphs on: 215.1 ms one lane, 220.1 ms two lanes; letters variant 80.4 vs 82.6).  With the GEMM
+    // capped at 128 registers (__maxnreg__, no spills) a GEMM CTA and an attention CTA do fit one SM together, and the gap narrows
+    // (213.7 vs 217.2 ms; 81.4 vs 81.6) but does not close: the half-batch GEMMs of a decode pass (16 m-tiles) are less efficient
+    // than the full-batch ones and that outweighs the overlap.  Results are bit-identical either way.
     int two_lanes = 0;
     cudaStream_t stream_b = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
