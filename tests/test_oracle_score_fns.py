@@ -84,3 +84,55 @@ def test_product_host_logic_matches_reference(case, monkeypatch):
     fn = build(inf, Pi() if case["logit_weight"] is not None else None, Tok, case["max_length"], case["value_weight"], case["logit_weight"], case["bsize"])
     got = fn([tuple(Text(t, a) for t, a in h) for h in G["histories"]])
     np.testing.assert_allclose(got, case["scores"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_product_host_logic_equals_oracle_on_random_histories(seed, monkeypatch):
+    """Random histories / weights / truncation lengths beyond the reference-generated cases: reranker's host logic (device forward replaced
+    by the toy tables) == the reference-pinned oracle score function."""
+    import random
+    from lmrl_gym_b200 import reranker, value_inference as VI
+    from lmrl_gym_b200.environment import Text
+    rng = random.Random(seed)
+    alphabet = "abcdefghij klmnop\n"
+    hists = []
+    for _ in range(rng.randint(1, 9)):
+        h = []
+        for k in range(rng.randint(0, 3)):
+            h.append(("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 12))), False))
+            h.append(("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 6))), True))
+        h.append(("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 12))), False))
+        h.append(("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 6))), True))
+        hists.append(h)
+    kind = ("ilql", "mc")[seed % 2]
+    max_length, vw = rng.choice([8, 20, 64]), rng.choice([1.0, 0.3])
+    lw = rng.choice([None, 0.5])
+    bsize = rng.randint(1, 5)
+
+    def gathered(batch):
+        sa = lambda tab: np.take_along_axis(table_q(TAB[tab], batch)[:, :-1], batch[:, 1:][..., None], axis=2)[..., 0]  # noqa: E731
+        return VI.ValueRLGatheredOutput(q1sa=sa("q1"), q2sa=sa("q2"), v=table_v(batch))
+
+    class Inf:
+        def forward(self, batch):
+            return gathered(batch)
+
+    def fake_logprobs(engine, tower, batch, pad, temperature=1.0):
+        x = table_q(TAB["pi"], batch)
+        m = x.max(-1, keepdims=True)
+        lp = x - m - np.log(np.exp(x - m).sum(-1, keepdims=True))
+        return np.take_along_axis(lp[:, :-1], batch[:, 1:][..., None], axis=2)[..., 0]
+
+    monkeypatch.setattr(VI, "token_logprobs", fake_logprobs)
+
+    class Pi:
+        _lmrl_engine = None
+
+    build = reranker.build_mc_score_fn if kind == "mc" else reranker.build_ilql_score_fn
+    fn = build(Inf(), Pi() if lw is not None else None, Tok, max_length, vw, lw, bsize)
+    got = fn([tuple(Text(t, a) for t, a in h) for h in hists])
+    full = [[i for t, _ in h for i in enc(t)] for h in hists]
+    pre = [len([i for t, _ in h[:-1] for i in enc(t)]) for h in hists]
+    want = O.score_histories(kind, full, pre, PAD, max_length, vw, lw, bsize, q_fn=lambda b: (table_q(TAB["q1"], b), table_q(TAB["q2"], b)), v_fn=table_v,
+                             pi_fn=lambda b: table_q(TAB["pi"], b))
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)

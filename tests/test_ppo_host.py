@@ -89,3 +89,43 @@ def test_kl_controller():
     for g in G["kl_controller"]:
         ctl.update(g["current"], g["n_steps"])
         assert ctl.value == pytest.approx(g["value"], rel=1e-12)
+
+
+def _random_chains(rng, n_chains):
+    """Rollout-shaped chains: every later trajectory of a chain extends the previous one (the history grows), rewards on action ends."""
+    chains = []
+    for _ in range(n_chains):
+        toks, act, rew = [], [], []
+        chain = []
+        n_traj = 1 + int(rng.integers(0, 4))
+        for k in range(n_traj):
+            ns, na = 1 + int(rng.integers(0, 7)), 1 + int(rng.integers(0, 5))
+            toks += rng.integers(0, 30, ns).tolist(); act += [False] * ns; rew += [0.0] * ns
+            toks += rng.integers(0, 30, na).tolist(); act += [True] * na; rew += [0.0] * (na - 1) + [float(np.float32(rng.normal()))]
+            done = bool(k == n_traj - 1 and rng.random() < 0.5)
+            chain.append(dict(tokens=list(toks), is_action=list(act), reward=list(rew), done=done))
+        chains.append(chain)
+    return chains
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ppo_data_host_logic_equals_oracle_on_random_chains(seed):
+    """Beyond the four reference-generated cases: random growing-history chains, with and without whitening / padding — the product's
+    chain combination + flattening + slicing (device calls stubbed) must equal the reference-pinned oracle on the same table model."""
+    rng = np.random.default_rng(seed)
+    chains = _random_chains(rng, 1 + int(rng.integers(0, 9)))
+    longest = max(len(t["tokens"]) for c in chains for t in c)
+    max_length = None if seed % 2 else longest + int(rng.integers(1, 5))
+    kw = dict(gamma=float(rng.choice([1.0, 0.99, 0.9])), lam=float(rng.choice([1.0, 0.95, 0.5])), kl_weight=float(rng.choice([0.0, 0.001, 0.1])))
+    whiten = bool(seed % 3)
+    inf = FakeInference()
+    datas, kls = inf.get_ppo_data_from_token_trajectory_chain([ref_chain(c) for c in chains], bsize=3, max_length=max_length, use_advantage_whitening=whiten,
+                                                              _forward=table_forward, _advantages=numpy_advantages, **kw)
+    o_chains = [[(np.asarray(t["tokens"], np.int32), np.asarray(t["is_action"], bool), np.asarray(t["reward"], np.float32), bool(t["done"])) for t in c] for c in chains]
+    o_datas, o_kls = O.ppo_data_from_chains(o_chains, table_forward, PAD, 3, max_length, use_advantage_whitening=whiten, **kw)
+    np.testing.assert_allclose(kls, o_kls, rtol=1e-6, atol=1e-7)
+    assert len(datas) == len(o_datas)
+    for d, o in zip(datas, o_datas):
+        assert d.input_ids.tolist() == o.input_ids.tolist() and np.asarray(d.should_take_action).tolist() == o.should_take_action.tolist()
+        for k in ("old_logprobs", "old_values", "old_advantages", "old_returns"):
+            np.testing.assert_allclose(getattr(d, k), getattr(o, k), rtol=2e-6, atol=2e-6, err_msg=k)
