@@ -381,6 +381,18 @@ constexpr int ATTP_WARPS = 7;                                   // 7 x 16 KB of 
 constexpr int ATTP_KEYS = 32;                                   // keys per staged block
 constexpr int ATTP_WARP_SMEM = 2 * 2 * ATTP_KEYS * 128;        // 2 buffers x (K block + V block)
 
+// cp.async with an L2 eviction-priority hint: a slot with more than 16 new rows streams its K / V once per 16-row block; the blocks
+// that will be followed by another one ask L2 to keep the lines (evict_last); the final (or only) block uses the default policy
+// (measured: 24 new rows at context 72, 0.325 -> 0.293 ms; single-block slots unchanged)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(policy));
+}
+
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
@@ -399,12 +411,14 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32, 2) attention_prefill_kernel(c
     const int g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(attp_smem) + warp * ATTP_WARP_SMEM;
     const int total = *rows.n_slots * n_head;
+    const uint64_t pol_last = l2_policy_evict_last();
     for (int w = blockIdx.x * ATTP_WARPS + warp; w < total; w += gridDim.x * ATTP_WARPS) {
         const int slot = w / n_head, head = w - slot * n_head;
         const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
         const int p0 = rows.row_pos[r0];
         const __nv_bfloat16* gK = kcache + ((size_t)e * n_head + head) * t_cap * 64;
         const __nv_bfloat16* gV = vcache + ((size_t)e * n_head + head) * t_cap * 64;
+        bool keep = false;                                     // set per row block below
         auto stage = [&](int buf, int k0) {                    // 32 keys of K and V: 2 x 256 chunks of 16 B, 16 per lane
             const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
 #pragma unroll
@@ -412,14 +426,20 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32, 2) attention_prefill_kernel(c
                 const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
                 const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
                 const int kk = min(k0 + key, t_cap - 1);
-                cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
-                cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
+                if (keep) {
+                    cp_async16_hint(sK + off, gK + (size_t)kk * 64 + ch * 8, pol_last);
+                    cp_async16_hint(sV + off, gV + (size_t)kk * 64 + ch * 8, pol_last);
+                } else {
+                    cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
+                    cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
+                }
             }
             cp_async_commit();
         };
         for (int rb = 0; rb < n; rb += 16) {
             const int nr = min(16, n - rb);                    // live query rows in this block
             const int n_keys = p0 + rb + nr;                   // keys visible to the last live row
+            keep = rb + 16 < n;                                // another block will stream the same K / V again: ask L2 to keep the lines
             __syncwarp();
             stage(0, 0);
             // Q fragments: qa[kk][0..3]
