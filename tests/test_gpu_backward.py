@@ -168,3 +168,75 @@ def test_handwritten_backward_gpt2_small_and_training_step():
     after = pol.logits([ids[0, :8].tolist()])
     assert np.abs(after - before).max() > 1e-5          # the rollout policy runs on the trained weights
     eng.close()
+
+
+def test_policy_grad_edge_cases():
+    """No scored token (value-only gradient), single-token sequences, a batch of one — the backward pass must run and give the
+    gradients autograd gives; misuse is reported through LmrlError, never a crash."""
+    import torch
+    from lmrl_gym_b200._lib import LmrlError
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200 import ppo_train as T
+    from lmrl_gym_b200.value_inference import forward_tokens
+    tok = ByteTokenizer.synthetic()
+    cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+    rng = np.random.default_rng(7)
+    params = init_gpt2_params(cfg, seed=9)
+    lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 16).astype(np.float32), bias=np.zeros(1, np.float32)))
+    eng = Engine(max_envs=8, max_input_length=32, max_new_tokens=4, tokenizer=tok)
+    B200GPT2Policy(eng, params, cfg)
+    ref = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch")
+    b2 = T.B200PPOTrain(eng, params, lin, cfg, pad_token_id=tok.pad_token_id, backward="b200", max_rows=256, max_scored_rows=128)
+    pad = tok.pad_token_id
+    # batch of one sequence of length 5, one action token; plus a one-token sequence (no output position at all)
+    ids = np.full((2, 6), pad, np.int32)
+    ids[0, :5] = rng.integers(0, cfg.n_vocab, 5)
+    ids[1, :1] = rng.integers(0, cfg.n_vocab, 1)
+    sta = np.zeros((2, 5), bool)
+    sta[0, 3] = True
+    f = lambda: rng.standard_normal((2, 5)).astype(np.float32)  # noqa: E731
+    cur = forward_tokens(eng, 0, 0, [ids[0, :5], ids[1, :1]], logprobs=True, pitch=8)["logprobs"][:, :5]
+    batch = dict(input_ids=ids, should_take_action=sta, old_logprobs=(cur + 0.05).astype(np.float32), old_values=f(), old_advantages=f(), old_returns=f())
+    for fz in ref.flat:
+        fz.grad = None
+    loss_ref, _ = ref.loss(batch)
+    loss_ref.backward()
+    loss_b, _ = b2._b200_grads(batch)
+    torch.cuda.synchronize()
+    assert abs(float(loss_ref.detach()) - loss_b) <= 2e-2 * max(1.0, abs(loss_b))
+    for grp in (0, 1):
+        a, c = ref.flat[grp].grad.double(), b2.gflat[grp].double()
+        assert float((a - c).norm() / a.norm()) <= 3e-2
+    # value-only: upstream gradient on the values alone (lmrl_policy_grad_host with all-zero dlogprob)
+    import ctypes as C
+    from lmrl_gym_b200._lib import check
+    toks = np.zeros((2, 8), np.int32)
+    toks[:, :6] = np.where(ids != pad, ids, 0)
+    lens = np.asarray([5, 1], np.int32)
+    dlp, dv = np.zeros((2, 8), np.float32), np.zeros((2, 8), np.float32)
+    dv[0, :5] = 0.1
+    dv[1, 0] = -0.2
+    for g in b2.gflat:
+        g.zero_()
+    keep = []
+    gs = b2._grad_struct(keep)
+    torch.cuda.synchronize()
+    check(eng.lib.lmrl_policy_grad_host(eng.handle, toks.ctypes.data, lens.ctypes.data, 8, 2, dlp.ctypes.data, dv.ctypes.data, C.c_float(1.0), C.byref(gs)))
+    torch.cuda.synchronize()
+    idt = torch.as_tensor(ids, device=ref.device).long()
+    for fz in ref.flat:
+        fz.grad = None
+    h = ref._hidden(idt, idt != pad)
+    vals = (h.float() @ ref.vh_w + ref.vh_b)[..., 0]
+    (vals[0, :5].sum() * 0.1 - 0.2 * vals[1, 0]).backward()
+    for grp in (0, 1):
+        a, c = ref.flat[grp].grad.double(), b2.gflat[grp].double()
+        assert float((a - c).norm() / a.norm()) <= 3e-2, grp
+    # misuse: more rows than the training capacity
+    big = np.zeros((8, 40), np.int32)
+    with pytest.raises(LmrlError):
+        check(eng.lib.lmrl_policy_grad_host(eng.handle, big.ctypes.data, np.full(8, 40, np.int32).ctypes.data, 40, 8, np.zeros((8, 40), np.float32).ctypes.data,
+                                            np.zeros((8, 40), np.float32).ctypes.data, C.c_float(1.0), C.byref(gs)))
+    eng.close()
