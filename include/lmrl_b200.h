@@ -210,6 +210,28 @@ int lmrl_textnav_reset_host(lmrl_engine* e, const uint64_t* seeds, const int32_t
 int lmrl_textnav_step_host(lmrl_engine* e, const uint8_t* action_bytes, const int32_t* action_len, int32_t pitch, const uint8_t* skip,
                            int32_t n, float* reward, uint8_t* done, int32_t* applied, int32_t* state, int32_t* adm, int32_t* n_adm);
 
+/* ---- chess rules for the Chess-endgames environment (llm_rl_scripts/chess/env/env.py:29-186; python-chess is not a dependency) ---
+ * HOST-side: the env's opponent is a UCI engine process, the GPU runs the policy.  One lmrl_chess = one board with its move stack.
+ * lmrl_chess_fen            board.fen(): en-passant square only when a legal en-passant capture exists, cleaned castling rights
+ * lmrl_chess_push_san       board.push_san(): 0 pushed, 1 null move (reported, not pushed; env.py:116-118), -1 illegal / ambiguous /
+ *                           malformed (board unchanged, text in lmrl_last_error)
+ * lmrl_chess_push_uci       board.san(move) into san_out, then board.push(move) (the opponent's reply, env.py:163-170)
+ * lmrl_chess_status         bit 0 checkmate, 1 stalemate, 2 insufficient material, 3 seventy-five moves, 4 fivefold repetition
+ *                           (any of them = board.is_game_over()), bit 5 = side to move in check
+ * lmrl_chess_perft          leaf count of the legal-move tree (known-answer test hook) */
+typedef struct lmrl_chess lmrl_chess;
+lmrl_chess* lmrl_chess_new(const char* fen /* NULL = initial position */);
+void lmrl_chess_free(lmrl_chess* c);
+int lmrl_chess_fen(lmrl_chess* c, char* out, int32_t cap);
+int lmrl_chess_legal_moves(lmrl_chess* c, char* out_uci /* space separated */, int32_t cap);
+int lmrl_chess_push_san(lmrl_chess* c, const char* san, char* uci_out, int32_t cap);
+int lmrl_chess_push_uci(lmrl_chess* c, const char* uci, char* san_out, int32_t cap);
+int lmrl_chess_pop(lmrl_chess* c);
+int lmrl_chess_status(lmrl_chess* c);
+int lmrl_chess_turn(lmrl_chess* c);          /* 0 white, 1 black */
+int lmrl_chess_is_valid(lmrl_chess* c);      /* board.is_valid() as far as generated endgames need it (env.py:227-243) */
+int64_t lmrl_chess_perft(lmrl_chess* c, int32_t depth);
+
 /* ---- PPO data path after the forward passes ------------------------------------------------------
  * Replaces the host loops of PPOInference.get_ppo_data_from_token_trajectory_chain (ppo/base_interface.py:572-669): KL-shaped
  * rewards  r - kl_weight * (logp - logp0) * is_action  (:572-584), get_action_state_next_state_idxs (:230-243), the GAE scan

@@ -107,6 +107,17 @@ SYMBOLS = {
     "lmrl_score_host": (C.c_int, [_V, _V, _V, _I, _I, _V, C.c_float, _V, _V]),
     "lmrl_load_value_heads": (C.c_int, [_V, _I, C.POINTER(lmrl_value_heads)]),
     "lmrl_forward_host": (C.c_int, [_V, _I, _I, _V, _V, _I, _I, C.c_float, C.POINTER(lmrl_forward_out)]),
+    "lmrl_chess_new": (_V, [C.c_char_p]),
+    "lmrl_chess_free": (None, [_V]),
+    "lmrl_chess_fen": (C.c_int, [_V, C.c_char_p, _I]),
+    "lmrl_chess_legal_moves": (C.c_int, [_V, C.c_char_p, _I]),
+    "lmrl_chess_push_san": (C.c_int, [_V, C.c_char_p, C.c_char_p, _I]),
+    "lmrl_chess_push_uci": (C.c_int, [_V, C.c_char_p, C.c_char_p, _I]),
+    "lmrl_chess_pop": (C.c_int, [_V]),
+    "lmrl_chess_status": (C.c_int, [_V]),
+    "lmrl_chess_turn": (C.c_int, [_V]),
+    "lmrl_chess_is_valid": (C.c_int, [_V]),
+    "lmrl_chess_perft": (C.c_int64, [_V, _I]),
     "lmrl_textnav_reset_host": (C.c_int, [_V, _V, _V, _I, _V, _V, _V]),
     "lmrl_textnav_step_host": (C.c_int, [_V, _V, _V, _I, _V, _I, _V, _V, _V, _V, _V, _V]),
     "lmrl_ppo_advantages_host": (C.c_int, [_V, _I, _V, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double, _I, _V, _V, _V]),

@@ -6,6 +6,7 @@
 //   gpt2_engine.inl   C ABI: GPT-2 decoder, sampler, fused rollout, per-position forward
 //   textnav_core.h / textnav_kernels.inl   Text-Nav int32 state machine (host+device logic, kernels, C ABI)
 //   train_kernels.inl C ABI: hand-written backward pass of the policy + value head (PPO gradient step)
+//   chess_core.h / chess_api.inl   host-side chess rules (FEN, SAN, legal moves, game state) for the Chess-endgames env
 //   ppo_kernels.inl   C ABI: PPO data path after the forward passes (KL rewards, GAE, whitening, clipped loss)
 #include <stdarg.h>
 #include <algorithm>
@@ -15,3 +16,4 @@
 #include "lmrl_api.inl"
 #include "ppo_kernels.inl"
 #include "textnav_kernels.inl"
+#include "chess_api.inl"

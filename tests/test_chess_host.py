@@ -1,0 +1,182 @@
+"""Chess rules (csrc/chess_core.h through the C ABI) and the Chess-endgames env mirror (lmrl_gym_b200/chess_env.py; reference
+llm_rl_scripts/chess/env/env.py).  python-chess is not available, so the anchors are the published perft counts of the standard test
+positions (move generation incl. castling, en passant, promotions, pins), and SAN / FEN / game-end facts that follow from the rules."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from lmrl_gym_b200 import chess_env as CE
+from lmrl_gym_b200.environment import Text, TextPolicy, interact_environment
+
+PERFT = [
+    (None, [20, 400, 8902, 197281, 4865609]),
+    ("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1", [48, 2039, 97862, 4085603]),
+    ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1", [14, 191, 2812, 43238, 674624]),
+    ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1", [6, 264, 9467, 422333]),
+    ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8", [44, 1486, 62379, 2103487]),
+    ("r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10", [46, 2079, 89890, 3894594]),
+]
+
+
+@pytest.mark.parametrize("fen,counts", PERFT, ids=["start", "kiwipete", "pos3", "pos4", "pos5", "pos6"])
+def test_perft_known_answers(fen, counts):
+    b = CE.ChessBoard(fen)
+    for d, want in enumerate(counts, start=1):
+        assert b.perft(d) == want, (fen, d)
+
+
+def play(board, sans):
+    return [board.push_san(s) for s in sans]
+
+
+def test_fen_follows_python_chess_conventions():
+    b = CE.ChessBoard()
+    assert b.fen() == CE.START_FEN
+    play(b, ["e4"])
+    assert b.fen() == "rnbqkbnr/pppppppp/8/8/4P3/8/PPPP1PPP/RNBQKBNR b KQkq - 0 1"        # no legal en-passant capture: '-' (not e3)
+    play(b, ["d5", "e5", "f5"])
+    assert b.fen() == "rnbqkbnr/ppp1p1pp/8/3pPp2/8/8/PPPP1PPP/RNBQKBNR w KQkq f6 0 3"    # exf6 is legal: the square is shown
+    assert play(b, ["exf6"]) == ["e5f6"]
+    assert b.fen() == "rnbqkbnr/ppp1p1pp/5P2/3p4/8/8/PPPP1PPP/RNBQKBNR b KQkq - 0 3"
+    play(b, ["Nc6", "Ke2"])                                                               # the king moved: white's rights are gone
+    assert b.fen().split()[2] == "kq"
+    b.pop()
+    assert b.fen().split()[2] == "KQkq"
+    # castling rights are cleaned against the pieces actually standing on their squares
+    assert CE.ChessBoard("4k3/8/8/8/8/8/8/4K2R w KQkq - 3 9").fen() == "4k3/8/8/8/8/8/8/4K2R w K - 3 9"
+    with pytest.raises(ValueError):
+        CE.ChessBoard("8/8/8/8 w - - 0 1")
+
+
+def test_san_generation_and_parsing():
+    two_knights = "4k3/8/8/8/8/5N2/8/1N2K3 w - - 0 1"
+    b = CE.ChessBoard(two_knights)
+    with pytest.raises(CE.IllegalMove):
+        b.push_san("Nd2")                                   # ambiguous
+    assert b.push_san("Nbd2") == "b1d2"
+    b = CE.ChessBoard(two_knights)
+    assert b.push_uci("f3d2") == "Nfd2"
+    b = CE.ChessBoard("4k3/8/8/R7/8/8/8/R3K3 w - - 0 1")
+    assert b.push_uci("a1a3") == "R1a3"                     # same file: disambiguate by rank
+    b.pop()
+    assert b.push_san("R5a3") == "a5a3"
+    b = CE.ChessBoard("8/P7/8/8/8/8/8/k1K5 w - - 0 1")
+    assert b.push_uci("a7a8q") == "a8=Q#"                   # a2 is covered by the new queen, b1 / b2 by the king: mate
+    b.pop()
+    assert b.push_uci("a7a8n") == "a8=N"
+    b.pop()
+    assert b.push_san("a8Q") == "a7a8q"                     # '=' is optional in the grammar
+    b.pop()
+    with pytest.raises(CE.IllegalMove):
+        b.push_san("a8")                                    # a promotion needs its piece
+    b = CE.ChessBoard()
+    play(b, ["f3", "e5", "g4"])
+    assert b.push_uci("d8h4") == "Qh4#"
+    assert b.is_checkmate() and b.is_game_over() and b.legal_moves() == []
+    b = CE.ChessBoard("r3k2r/8/8/8/8/8/8/R3K2R w KQkq - 0 1")
+    assert b.push_san("O-O") == "e1g1"
+    assert b.push_san("0-0-0") == "e8c8"
+    assert b.fen() == "2kr3r/8/8/8/8/8/8/R4RK1 w - - 2 2"
+    b = CE.ChessBoard()
+    for bad in ["e5", "Ke2", "Nf4", "e4e5", "", "hello", "O-O", "exd5", "e9", "Pe4"]:
+        with pytest.raises(CE.IllegalMove):
+            b.push_san(bad)
+    assert b.fen() == CE.START_FEN                           # nothing was pushed
+    assert b.push_san("--") is None and b.fen() == CE.START_FEN
+    assert b.push_san("Nf3+") == "g1f3"                      # a spurious check mark is tolerated by the grammar
+    assert b.push_san("xe5") == "e7e5"                       # ... and so is a capture mark on a quiet move ([-x]? carries no meaning)
+    assert sorted(CE.ChessBoard().legal_moves())[:3] == ["a2a3", "a2a4", "b1a3"]
+
+
+def test_game_end_conditions():
+    S = CE.ChessBoard
+    st = S("7k/5Q2/6K1/8/8/8/8/8 b - - 0 1")
+    assert st.status() & S.STALEMATE and st.is_game_over() and not st.is_checkmate()
+    assert S("8/8/8/4k3/8/8/8/4K3 w - - 0 1").status() & S.INSUFFICIENT
+    assert S("8/8/8/4k3/8/8/8/4KN2 w - - 0 1").status() & S.INSUFFICIENT
+    assert S("8/8/8/4k1b1/8/8/8/2B1K3 w - - 0 1").status() & S.INSUFFICIENT            # bishops on the same colour
+    assert not S("8/8/8/4kb2/8/8/8/2B1K3 w - - 0 1").status() & S.INSUFFICIENT         # opposite colours can still mate
+    assert not S("8/8/8/4k3/8/8/8/4KR2 w - - 0 1").is_game_over()
+    assert S("8/8/8/4k3/8/8/8/4KR2 w - - 150 90").status() & S.SEVENTYFIVE
+    assert not S("8/8/8/4k3/8/8/8/4KR2 w - - 149 90").is_game_over()
+    b = S()
+    for _ in range(4):
+        play(b, ["Nf3", "Nf6", "Ng1", "Ng8"])
+        assert bool(b.status() & S.FIVEFOLD) == (_ == 3)                                 # the start position has now occurred five times
+    assert b.is_game_over()
+
+
+def test_chess_env_step_semantics():
+    # mate in one: reward 1, done
+    env = CE.ChessEnv(from_position="6k1/5ppp/8/8/8/8/8/R3K3 w - - 0 1", random_opponent=True, rng=np.random.default_rng(0))
+    st, r, d, info = env.step("Qa8")
+    assert (r, d) == (-1, 0) and st == env.starting_position                              # illegal: -1 and the game goes on
+    st, r, d, info = env.step("--")
+    assert (r, d) == (-1, True)                                                           # null move ends the episode
+    st, r, d, info = env.step("Ra8#")
+    assert (r, d) == (1, 1) and st.startswith("R5k1/")
+    # a quiet move: the opponent answers, reward 0
+    env = CE.ChessEnv(from_position="6k1/5ppp/8/8/8/8/8/R3K3 w - - 0 1", random_opponent=True, rng=np.random.default_rng(1))
+    st, r, d, info = env.step("Ra2")
+    assert (r, bool(d)) == (0, False) and info["opponent move"] and st.split()[1] == "w" and st.split()[5] == "2"
+    # stalemating the opponent: a draw is reward 0, done
+    env = CE.ChessEnv(from_position="7k/8/5QK1/8/8/8/8/8 w - - 0 1", random_opponent=True)
+    st, r, d, info = env.step("Qf7")
+    assert (r, d) == (0, 1)
+    # the opponent mates the agent: reward -1
+    class Mater:
+        def best_move(self, board, start_fen, moves):
+            return "d8h4"
+    b_env = CE.ChessEnv(from_position="rnbqkbnr/pppp1ppp/8/4p3/8/5P2/PPPPP1PP/RNBQKBNR w KQkq - 0 2", opponent=Mater())
+    st, r, d, info = b_env.step("g4")
+    assert (r, d) == (-1, True) and info["opponent move"] == "Qh4#"
+
+
+def test_fen_history_env_and_eval_loop():
+    fen = "6k1/5ppp/8/8/8/8/8/R3K3 w - - 0 1"
+
+    class MateInOne(TextPolicy):
+        def act(self, text_history):
+            assert CE.postprocess_state(text_history[-1].text) == fen
+            return text_history + (Text(CE.preprocess_move("Ra8#"), True),)
+
+    env = CE.FenChessHistoryEnv(from_position=fen, random_opponent=True)
+    obs = env.reset()
+    assert obs == (Text(" ".join(fen), False),)
+    inter, summary = CE.text_env_eval_chess_positions([fen, fen], MateInOne(), n_rollouts=3, bsize=2, verbose=False, random_opponent=True)
+    assert len(inter) == 6 and summary["victories"]["mean"] == 1.0 and summary["reward"]["mean"] == 1.0 and summary["episode_length"]["max"] == 1
+    assert summary["percent_illegals"]["max"] == 0.0
+
+    class Illegal(TextPolicy):
+        def act(self, text_history):
+            return text_history + (Text("z z\n", True),)
+    inter, summary = CE.text_env_eval_chess_positions([fen], Illegal(), n_rollouts=1, bsize=1, verbose=False, random_opponent=True, max_moves=4)
+    assert summary["episode_length"]["mean"] == 5 and summary["reward"]["mean"] == -5.0 and summary["victories"]["mean"] == 0
+    st = CE.FenChessHistoryEnvSingleTurn((Text("Play white.\n", False),), from_position=fen, random_opponent=True)
+    assert st.reset() == (Text("Play white.\n", False), Text(" ".join(fen) + "\n", False))
+
+
+def test_random_endgames_are_valid():
+    rng = np.random.default_rng(0)
+    for pieces in ("kQK", "kRK", "kqKQ", "kPK"):
+        for _ in range(10):
+            fen = CE.large_piece_random_endgame(pieces, rng)
+            b = CE.ChessBoard(fen)
+            assert b.is_valid() and not b.is_check() and b.turn_white
+            placed = [c for c in fen.split()[0] if c.isalpha()]
+            assert sorted(placed) == sorted(pieces)
+
+
+def test_uci_opponent_against_a_fake_engine():
+    engine = [sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fake_uci_engine.py")]
+    opp = CE.UciOpponent(engine, nodes=1)
+    try:
+        env = CE.ChessEnv(from_position="6k1/5ppp/8/8/8/8/8/R3K3 w - - 0 1", opponent=opp)
+        st, r, d, info = env.step("Ra2")
+        assert (r, bool(d)) == (0, False) and info["opponent move"] == "f5"             # smallest legal uci move of black: f7f5
+        st, r, d, info = env.step("Ra8+")
+        assert info["opponent move"] == "Kf7" and st.split()[1] == "w"
+    finally:
+        opp.close()
