@@ -21,7 +21,8 @@ def make_batch(rng, cfg, pad, lp_fn, b=12, t=48):
     return dict(input_ids=ids, should_take_action=sta, old_logprobs=None, old_values=f(0.3), old_advantages=f(1.0), old_returns=f(0.5))
 
 
-def test_handwritten_backward_matches_autograd():
+@pytest.mark.parametrize("d_model,n_head,d_ff", [(256, 4, 1024), (1024, 16, 4096)], ids=["d256", "d1024-medium-width"])
+def test_handwritten_backward_matches_autograd(d_model, n_head, d_ff):
     import torch
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
@@ -30,7 +31,7 @@ def test_handwritten_backward_matches_autograd():
     from lmrl_gym_b200.value_inference import forward_tokens
     from oracle.gpt2 import bf16_round
     tok = ByteTokenizer.synthetic()
-    cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+    cfg = GPT2Config(n_layer=2, n_head=n_head, d_model=d_model, d_ff=d_ff)
     rng = np.random.default_rng(0)
     params = init_gpt2_params(cfg, seed=3)
     for k in ("wte", "wpe"):
