@@ -12,6 +12,14 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is git-ignored (it travels to the GPU box as a built file): build it once if a fresh checkout has none
+    lib = os.path.join(ROOT, "lmrl_gym_b200", "csrc", "liblmrl_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from lmrl_gym_b200 import build as _b
+            _b.build_cuda()
+            _b.build_host()
 
 
 def pytest_collection_modifyitems(config, items):
