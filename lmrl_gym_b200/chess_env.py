@@ -23,7 +23,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Tuple, Union
 import numpy as np
 
 from . import _lib
-from .environment import BatchedTextPolicy, Text, TextEnv, TextHistory, TextPolicy, interact_environment
+from .environment import BatchedTextEnv, BatchedTextPolicy, Text, TextEnv, TextHistory, TextPolicy, interact_environment
 
 START_FEN = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"
 
@@ -339,3 +339,105 @@ def text_env_eval_chess_positions(positions: List[str], policy: Union[TextPolicy
     stats = lambda a: dict(mean=np.mean(a), std=np.std(a), min=np.min(a), max=np.max(a))  # noqa: E731
     return interactions, dict(reward=stats(rs), done=stats(dones), victories=stats(victories), percent_illegals=stats(percent_illegals),
                               episode_length=stats(episode_length))
+
+
+# ---- batched env with an engine pool ----------------------------------------------------------------------------------------
+
+class UciOpponentPool:
+    """``n_workers`` UCI engine processes answering the replies of one batch step concurrently (threads block on the engines' pipes, so
+    the engines search in parallel on the host cores while the caller — and the GPU, busy with other work — is not held per game)."""
+
+    def __init__(self, path, n_workers: int, **kw):
+        self.engines = [UciOpponent(path, **kw) for _ in range(n_workers)]
+
+    def best_moves(self, requests: List[Tuple[str, List[str]]]) -> List[str]:
+        """requests: (start_fen, uci moves so far) per game -> the engine's reply per game, in order."""
+        import queue
+        import threading
+        out: List[Optional[str]] = [None] * len(requests)
+        q: "queue.Queue[int]" = queue.Queue()
+        for i in range(len(requests)):
+            q.put(i)
+        errors: List[BaseException] = []
+
+        def work(engine: UciOpponent):
+            while True:
+                try:
+                    i = q.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    out[i] = engine.best_move(None, requests[i][0], requests[i][1])
+                except BaseException as e:      # noqa: BLE001 - re-raised in the caller
+                    errors.append(e)
+                    return
+
+        threads = [threading.Thread(target=work, args=(e,)) for e in self.engines[:max(1, min(len(self.engines), len(requests)))]]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out  # type: ignore[return-value]
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+
+class BatchedFenChessHistoryEnv(BatchedTextEnv):
+    """``FenChessHistoryEnv`` (env.py:215-243) for a whole batch: same observations, rewards and done flags per game as
+    ``TextEnvToBatchedTextEnv(FenChessHistoryEnv(...))``, but one ``step`` first plays every agent move (C rules), then asks the engine
+    pool for all the replies at once.  ``opponent`` is a ``UciOpponentPool``, any object with ``best_move(board, fen, moves)``, or None with
+    ``random_opponent=True``."""
+
+    def __init__(self, max_moves=400, from_position=None, opponent=None, random_opponent=False, rng: Optional[np.random.Generator] = None):
+        self.max_moves, self.from_position = max_moves, from_position
+        self.opponent = opponent if opponent is not None else (RandomOpponent(rng) if random_opponent else None)
+        self.envs: Optional[List[ChessEnv]] = None
+
+    def reset(self, seed: Optional[List[Optional[int]]] = None, options: Optional[List[Optional[Dict]]] = None) -> List[TextHistory]:
+        n = len(seed) if seed is not None else (len(options) if options is not None else 1)
+        self.envs = [ChessEnv(from_position=self.from_position, opponent=self.opponent) for _ in range(n)]
+        self.num_moves_made = [0] * n
+        return [(Text(preprocess_state_og(e.starting_position), False),) for e in self.envs]
+
+    def step(self, text_history: List[Optional[TextHistory]], done: Optional[List[bool]] = None):
+        assert self.envs is not None, "reset must be called before step"
+        assert len(text_history) == len(self.envs), "batch size must be the same as the number of environments initalized"
+        if done is None:
+            done = [False] * len(text_history)
+        results: List[Optional[Tuple]] = [None] * len(self.envs)
+        pending: List[int] = []
+        for i, (h, d) in enumerate(zip(text_history, done)):
+            if d or h is None:
+                continue
+            assert h[-1].is_action
+            st, reward, dn, info = self.envs[i].step(postprocess_move(h[-1].text), opponent_move=False)
+            legal_and_open = (reward, dn) == (0, 0) and self.envs[i].uci_moves and not self.envs[i].board.turn_white
+            if legal_and_open:
+                pending.append(i)
+            results[i] = (st, reward, dn)
+        if pending:
+            assert self.opponent is not None, "no opponent configured"
+            if isinstance(self.opponent, UciOpponentPool):
+                replies = self.opponent.best_moves([(self.envs[i].starting_position, self.envs[i].uci_moves) for i in pending])
+            else:
+                replies = [self.opponent.best_move(self.envs[i].board, self.envs[i].starting_position, self.envs[i].uci_moves) for i in pending]
+            for i, reply in zip(pending, replies):
+                env = self.envs[i]
+                env.board.push_uci(reply)
+                env.uci_moves.append(reply)
+                results[i] = (env.board.fen(), -1 if env.board.is_checkmate() else 0, env.board.is_game_over())
+        out: List[Optional[Tuple]] = []
+        for i, r in enumerate(results):
+            if r is None:
+                out.append(None)
+                continue
+            st, reward, dn = r
+            self.num_moves_made[i] += 1
+            if self.num_moves_made[i] > self.max_moves:
+                dn = 1
+            out.append(((Text(preprocess_state_og(st), False),), reward, dn))
+        return out

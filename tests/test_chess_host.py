@@ -180,3 +180,37 @@ def test_uci_opponent_against_a_fake_engine():
         assert info["opponent move"] == "Kf7" and st.split()[1] == "w"
     finally:
         opp.close()
+
+
+def test_batched_env_with_engine_pool_equals_the_per_game_env():
+    """BatchedFenChessHistoryEnv + UciOpponentPool (replies of a batch step fetched concurrently) gives, game by game, what
+    TextEnvToBatchedTextEnv(FenChessHistoryEnv) with one engine gives: observations, rewards, done flags."""
+    from lmrl_gym_b200.environment import BatchedTextPolicy
+    engine = [sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fake_uci_engine.py")]
+    fen = "6k1/5ppp/8/8/8/8/8/R3K3 w - - 0 1"
+    scripts = [["Ra2", "Ra8+", "zz", "Rb8"], ["Ra8#"], ["--"], ["Kd2", "Kc3", "Ra7", "Ra8+"], ["e4", "Ra3", "Ra4", "Ra5"]]
+
+    class Scripted(BatchedTextPolicy):
+        def __init__(self):
+            self.t = 0
+
+        def act(self, text_history, done=None):
+            out = []
+            for i, (h, d) in enumerate(zip(text_history, done)):
+                out.append(None if d else tuple(h) + (Text(CE.preprocess_move(scripts[i][min(self.t, len(scripts[i]) - 1)]), True),))
+            self.t += 1
+            return out
+
+    pool = CE.UciOpponentPool(engine, n_workers=3, nodes=1)
+    single = CE.UciOpponent(engine, nodes=1)
+    try:
+        a = interact_environment(CE.BatchedFenChessHistoryEnv(max_moves=3, from_position=fen, opponent=pool), Scripted(), env_seed=[None] * 5, env_options=[None] * 5, bsize=5)
+        b = interact_environment(CE.FenChessHistoryEnv(max_moves=3, from_position=fen, opponent=single), Scripted(), env_seed=[None] * 5, env_options=[None] * 5, bsize=5)
+    finally:
+        pool.close()
+        single.close()
+    assert [len(ep) for ep in a] == [len(ep) for ep in b] == [4, 1, 1, 4, 4]
+    for ea, eb in zip(a, b):
+        for ta, tb in zip(ea, eb):
+            assert ta.post_transition_history == tb.post_transition_history and ta.reward == tb.reward and bool(ta.done) == bool(tb.done)
+    assert a[1][0].reward == 1 and a[2][0].reward == -1 and a[4][0].reward == -1          # mate in one; null move; illegal first move
