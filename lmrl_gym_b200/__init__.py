@@ -27,4 +27,12 @@ def __getattr__(name):
     if name in ("B200GPT2Policy", "B200GPT2ValuePolicy", "GPT2Config", "init_gpt2_params", "init_mlp_head_params"):
         from . import gpt2
         return getattr(gpt2, name)
+    lazy = {"B200TextNavEnv": "textnav", "B200PPOInference": "ppo", "AdaptiveKLController": "ppo", "FixedKLController": "ppo", "PPOData": "ppo",
+            "B200PPOTrain": "ppo_train", "ppo_train_loop": "ppo_train", "B200ValueRLInference": "value_inference", "B200ILQLInference": "value_inference",
+            "ReRankerPolicy": "reranker", "ReRankerSamplePolicy": "reranker", "build_bc_score_fn": "reranker", "build_ilql_score_fn": "reranker",
+            "build_mc_score_fn": "reranker", "FenChessHistoryEnv": "chess_env", "BatchedFenChessHistoryEnv": "chess_env", "ChessEnv": "chess_env",
+            "text_env_eval_chess_positions": "chess_env"}
+    if name in lazy:
+        import importlib
+        return getattr(importlib.import_module("." + lazy[name], __name__), name)
     raise AttributeError(name)
