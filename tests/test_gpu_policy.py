@@ -250,3 +250,45 @@ def test_top_k_top_p_sampling_matches_oracle_warpers(tok):
                 assert kept.sum() <= top_k
         print(f"top_k={top_k} top_p={top_p} T={temperature}: kept-set sizes {min(sizes)}..{max(sizes)}")
     eng.close()
+
+
+def test_sampler_distribution_matches_softmax(tok):
+    """The reference samples with jax.random.categorical; the engine with Gumbel-max over a counter hash — bit parity is impossible, so
+    the claim is distributional: over 4096 independent episode keys the first sampled token of one prompt follows
+    softmax(logits / T).  The logits are the engine's own (their parity with the oracle is the tests above), the temperature is chosen
+    so that the most likely token has probability ~0.3; the 12 most likely tokens must each land within 5 sigma of their binomial
+    expectation, and so must the total mass of the rest."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    cfg = _small_cfg()
+    params = init_gpt2_params(cfg, seed=8)
+    N = 4096
+    eng = Engine(max_envs=N, max_input_length=16, max_new_tokens=1, tokenizer=tok)
+    prompt = [11, 22, 33, 44, 55]
+    logits = B200GPT2Policy(eng, params, cfg, do_sample=False).logits([prompt])[0].astype(np.float64)
+
+    def softmax_at(T):
+        z = logits / T
+        q = np.exp(z - z.max())
+        return q / q.sum()
+    lo, hi = 1e-3, 10.0
+    for _ in range(40):                                                             # bisection on the temperature: max prob = 0.3
+        mid = np.sqrt(lo * hi)
+        lo, hi = (mid, hi) if softmax_at(mid).max() > 0.3 else (lo, mid)
+    T = float(hi)
+    p = softmax_at(T)
+    pol = B200GPT2Policy(eng, params, cfg, do_sample=True, temperature=T, seed=4242)
+    gens = pol.generate_tokens([prompt] * N, episode_keys=list(range(1000, 1000 + N)), turn=0)
+    first = np.asarray([g[0] for g in gens])
+    top = np.argsort(-p)[:12]
+    counts = np.bincount(first, minlength=cfg.n_vocab)
+    for t in top:
+        exp, sd = N * p[t], np.sqrt(N * p[t] * (1 - p[t]))
+        assert abs(counts[t] - exp) <= 5 * sd + 1, (int(t), int(counts[t]), exp, sd, T)
+    m = p[top].sum()
+    assert abs((N - counts[top].sum()) - N * (1 - m)) <= 5 * np.sqrt(N * m * (1 - m)) + 1
+    assert len(set(first.tolist())) > 12                                            # it really samples
+    # same keys, same turn -> the same draws (the sampler is a pure function of (seed, episode key, turn, position))
+    again = pol.generate_tokens([prompt] * 64, episode_keys=list(range(1000, 1064)), turn=0)
+    assert [g[0] for g in again] == first[:64].tolist()
+    eng.close()
