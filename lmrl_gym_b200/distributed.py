@@ -98,3 +98,19 @@ def reduce_throughput(units: int, seconds: float, group=None) -> Tuple[int, floa
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
     return int(u.item()), float(t.item())
+
+
+def init_from_env() -> Tuple[int, int, int]:
+    """(rank, world, local device) of a driver process: under torchrun (RANK / WORLD_SIZE / LOCAL_RANK set) joins the NCCL process
+    group, one process per GPU; otherwise a single process on device 0."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1, 0
+    import torch
+    dist = _dist()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+    return dist.get_rank(), dist.get_world_size(), local

@@ -63,6 +63,45 @@ def describe(mode: int, grid: np.ndarray, pos, goal) -> str:
     return f"{walls}\n"
 
 
+def maze_solver(grid: np.ndarray, goal_positions) -> Dict[Tuple[int, int], str]:
+    """Optimal first move of every free cell: breadth-first from the goals (maze_utils.py:91-116, which takes the INVERTED grid; this
+    one takes the wall grid, 1 = wall).  Neighbours are expanded down, right, up, left — the reference's order — so cells with two
+    shortest paths get the same move."""
+    H, W = grid.shape
+    goals = [tuple(int(v) for v in g) for g in goal_positions]
+    assert all(grid[g] == 0 for g in goals), "goal must be a free cell"
+    moves: Dict[Tuple[int, int], str] = {}
+    seen = set(goals)
+    frontier = list(goals)
+    while frontier:
+        nxt = []
+        for (y, x) in frontier:
+            for dy, dx, back in ((1, 0, "move up\n"), (0, 1, "move left\n"), (-1, 0, "move down\n"), (0, -1, "move right\n")):
+                c = (y + dy, x + dx)
+                if c in seen or not (0 <= c[0] < H and 0 <= c[1] < W) or grid[c] == 1:
+                    continue
+                seen.add(c)
+                moves[c] = back
+                nxt.append(c)
+        frontier = nxt
+    return moves
+
+
+def compute_move_accuracy(policy, reranker: bool = False, maze_name: str = "double_t_maze") -> float:
+    """Percentage of free cells (goal excluded) on which ``policy``'s action for the fully-observed description is the optimal move
+    (maze_utils.py:63-89; the reference hard-codes the double-T maze and its hand-written table, which equals ``maze_solver``'s)."""
+    grid, goal = maze_grid(maze_name), GOALS[maze_name]
+    best = maze_solver(grid, [goal])
+    cells = [tuple(int(v) for v in c) for c in np.argwhere(grid == 0)]
+    hists = [(Text(describe(1, grid, c, goal), False),) for c in cells if c != tuple(goal)]
+    if reranker:
+        preds = [policy.act(h)[-1].text for h in hists]
+    else:                                                        # one batched call instead of the reference's one call per cell
+        preds = [h[-1].text for h in policy.act(hists, done=[False] * len(hists))]
+    correct = sum(p == best[c] for p, c in zip(preds, [c for c in cells if c != tuple(goal)]))
+    return 100.0 * correct / len(hists)
+
+
 class B200MazeEnv(BatchedTextEnv):
     def __init__(self, engine: Engine, maze_name: str = "double_t_maze",
                  describe_function: str = "describe_observation_give_position",
