@@ -135,9 +135,10 @@ class B200PPOTrain:
     def __init__(self, engine: Engine, policy_params: Dict, value_head_params: Dict, config: Optional[GPT2Config] = None, *, lr: float = 1e-5,
                  weight_decay: float = 0.0, cliprange_value: float = 0.2, cliprange: float = 0.2, value_loss_coef: float = 1.0,
                  pad_token_id: Optional[int] = None, activation_dtype: str = "bf16", backward: Optional[str] = None, max_rows: int = 16384,
-                 max_scored_rows: int = 8192):
+                 max_scored_rows: int = 8192, bc_loss_weight: float = 0.0):
         import torch
         self.torch = torch
+        self.bc_loss_weight = float(bc_loss_weight)      # weight of the optional BC term (GPT2PPOTrain bc_loss_weight, ppo/gpt2/interface.py:36)
         self._lmrl_engine = engine                      # None: no rollout engine attached (CPU tests of the update itself)
         self.config = config or GPT2Config.small()
         self.device = torch.device("cuda", engine.device) if engine is not None else torch.device("cpu")
@@ -226,6 +227,22 @@ class B200PPOTrain:
             x = x + F.gelu(h @ L["fc_w"] + L["fc_b"], approximate="tanh") @ L["fc2_w"] + L["fc2_b"]
         return F.layer_norm(x, (cfg.d_model,), P["lnf_g"], P["lnf_b"], cfg.ln_eps)
 
+    def bc_loss(self, bc_batch: Dict[str, np.ndarray]):
+        """The BC term of the PPO step (``bc_loss_fn``; every driver passes JaxSeq's ``loss_fn_mask``, train_ppo_gpt2.py:36, 288): masked
+        next-token cross-entropy, sum(CE * m) / sum(m) with m = input_training_mask[:, 1:].  JaxSeq is not vendored by the reference: this
+        restates its published definition (parity unpinned)."""
+        torch = self.torch
+        dev = self.device
+        ids = torch.as_tensor(bc_batch["input_ids"], device=dev).long()
+        attn = ids != self.pad_token_id
+        m = torch.as_tensor(np.asarray(bc_batch["input_training_mask"], dtype=np.float32), device=dev)[:, 1:] * attn[:, 1:].float()
+        with torch.autocast(self.device.type, dtype=self.autocast, enabled=self.autocast is not None):
+            P = self.p
+            logits = self._hidden(ids, attn, P) @ P["wte"][:self.config.n_vocab].T
+        ce = torch.nn.functional.cross_entropy(logits[:, :-1].float().reshape(-1, logits.shape[-1]), ids[:, 1:].clamp(max=self.config.n_vocab - 1).reshape(-1),
+                                               reduction="none").view(ids.shape[0], -1)
+        return (ce * m).sum() / m.sum()
+
     def loss(self, batch: Dict[str, np.ndarray]):
         """ppo/gpt2/interface.py:106-146 + ppo_loss_fn (ppo/base_interface.py:71-142)."""
         torch = self.torch
@@ -256,19 +273,28 @@ class B200PPOTrain:
                     value_clipfrac=(((vf2 > vf1).float() * mask).sum() / n).detach(), ratio=((ratio * mask).sum() / n).detach())
         return loss, logs
 
-    def step(self, batch: Dict[str, np.ndarray]) -> Tuple[float, Dict[str, float]]:
+    def step(self, batch: Dict[str, np.ndarray], bc_batch: Optional[Dict[str, np.ndarray]] = None) -> Tuple[float, Dict[str, float]]:
         """One optimizer step on one minibatch (``PPOTrain.step``, ppo/base_interface.py:183-228): torch autograd for the gradients
         (library path), a summing all-reduce of the two flat gradient buffers over the ranks, then AdamW — the hand-written streaming
         kernel ``lmrl_adamw_dev`` when an engine is attached, ``torch.optim.AdamW`` otherwise (CPU tests)."""
         torch = self.torch
+        # optional BC term (ppo/gpt2/interface.py:183-205): loss + w * bc_loss, policy gradients + w * bc gradients
+        use_bc = bc_batch is not None and self.bc_loss_weight != 0.0
         if self.backward == "b200":
             loss, logs = self._b200_grads(batch)
+            if use_bc:
+                bc = self._b200_bc_grads(bc_batch)
+                loss, logs = loss + self.bc_loss_weight * bc, dict(logs, bc_loss=bc, ppo_loss=loss, total_loss=loss + self.bc_loss_weight * bc)
             for f, g in zip(self.flat, self.gflat):
                 f.grad = g
         else:
             for f in self.flat:
                 f.grad = None
             loss, logs = self.loss(batch)
+            if use_bc:
+                bc = self.bc_loss(bc_batch)
+                logs = dict(logs, bc_loss=bc.detach(), ppo_loss=loss.detach(), total_loss=(loss + self.bc_loss_weight * bc).detach())
+                loss = loss + self.bc_loss_weight * bc
             loss.backward()
             loss = float(loss.detach())
         world = 1
@@ -355,6 +381,32 @@ class B200PPOTrain:
         check(e.lib.lmrl_policy_grad_host(e.handle, toks.ctypes.data, lens.ctypes.data, pitch, n, dlp_p.ctypes.data, dv_p.ctypes.data, C.c_float(1.0), C.byref(gs)))
         return loss, logs
 
+    def _b200_bc_grads(self, bc_batch: Dict[str, np.ndarray]) -> float:
+        """BC term on the engine: bc_loss = -sum(m * logp) / sum(m) from one teacher-forced forward, and its gradient through
+        ``lmrl_policy_grad_host`` with dL/dlogprob = -w * m / sum(m), ACCUMULATED onto the PPO gradients already in the flat buffers."""
+        from .value_inference import forward_tokens
+        e = self._lmrl_engine
+        ids = np.asarray(bc_batch["input_ids"])
+        real = ids != self.pad_token_id
+        lens = np.ascontiguousarray(real.sum(axis=1).astype(np.int32))
+        assert (real == (np.arange(ids.shape[1])[None, :] < lens[:, None])).all(), "BC batches are RIGHT-padded (train_ppo_gpt2.py:139-143)"
+        n, T = ids.shape
+        pitch = max(8, T)
+        toks = np.zeros((n, pitch), np.int32)
+        toks[:, :T] = np.where(real, ids, 0)
+        m = np.asarray(bc_batch["input_training_mask"], dtype=np.float64)[:, 1:] * real[:, 1:]
+        fw = forward_tokens(e, 0, 0, [ids[i, :lens[i]] for i in range(n)], logprobs=True, pitch=pitch)
+        total = m.sum()
+        bc = float(-(fw["logprobs"][:, :T - 1].astype(np.float64) * m).sum() / total)
+        dlp = np.zeros((n, pitch), np.float32)
+        dlp[:, :T - 1] = -self.bc_loss_weight * m / total
+        dv = np.zeros((n, pitch), np.float32)
+        keep: list = []
+        gs = self._grad_struct(keep)
+        self.torch.cuda.synchronize(self.device)
+        check(e.lib.lmrl_policy_grad_host(e.handle, toks.ctypes.data, lens.ctypes.data, pitch, n, dlp.ctypes.data, dv.ctypes.data, C.c_float(1.0), C.byref(gs)))
+        return bc
+
     # ---- weight hand-over to the rollout engine (device to device; policy.set_params of ppo/train.py:244, 438) -------
     def push_to_engine(self, tower: int = 0, head_set: int = 0) -> None:
         torch = self.torch
@@ -385,11 +437,31 @@ class B200PPOTrain:
 TorchPPOTrain = B200PPOTrain          # earlier name, kept for callers that select backward="torch"
 
 
+def bc_batch_from_str_segments(items, tokenizer, max_length: int, pad_token_id: int) -> Dict[str, np.ndarray]:
+    """One BC minibatch from ``[(text, mask_value), ...]`` segment lists — the data format of the PPO drivers' ``bc_data_path``
+    (``MaskIterableDataset.blocked_from_str_segments_iterable``, train_ppo_gpt2.py:136-144): every segment is encoded on its own and
+    the ids concatenated, each token carrying its segment's mask value; rows are LEFT-truncated and RIGHT-padded to ``max_length``."""
+    ids = np.full((len(items), max_length), pad_token_id, np.int32)
+    mask = np.zeros((len(items), max_length), np.float32)
+    for i, segments in enumerate(items):
+        t, m = [], []
+        for text, w in segments:
+            enc = tokenizer.encode(text)
+            t += list(enc)
+            m += [float(w)] * len(enc)
+        t, m = t[-max_length:], m[-max_length:]
+        ids[i, :len(t)], mask[i, :len(m)] = t, m
+    return dict(input_ids=ids, input_training_mask=mask)
+
+
 def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
                    epochs: int = 1, train_bsize: int = 32, max_length: int = 128, gamma: float = 1.0, lam: float = 0.95,
                    use_advantage_whitening: bool = True, seed_generator=None, rng: Optional[np.random.Generator] = None,
-                   max_steps_per_round: Optional[int] = None, use_device_chains: bool = True, on_round: Optional[Callable[[int, Dict], None]] = None) -> List[Dict]:
-    """ppo/train.py:138-477 reduced to its data flow (no checkpointing / wandb): returns one log dict per round."""
+                   max_steps_per_round: Optional[int] = None, use_device_chains: bool = True, on_round: Optional[Callable[[int, Dict], None]] = None,
+                   bc_batches=None) -> List[Dict]:
+    """ppo/train.py:138-477 reduced to its data flow (no checkpointing / wandb): returns one log dict per round.  ``bc_batches``: an
+    iterator of BC minibatches (``bc_batch_from_str_segments``), one drawn per optimizer step like the reference's cycled ``bc_d``
+    (ppo/train.py:346-371); used when the trainer's ``bc_loss_weight`` is non-zero."""
     import time
     import torch
     rng = rng or np.random.default_rng(0)
@@ -433,7 +505,7 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTra
                 if max_steps_per_round is not None and len(losses) >= max_steps_per_round:
                     break
                 batch = block_ppo_data([datas[i] for i in order[lo:lo + train_bsize]], inference.pad_token_id, max_length)
-                losses.append(trainer.step(batch)[0])
+                losses.append(trainer.step(batch, next(bc_batches) if bc_batches is not None else None)[0])
         trainer.push_to_engine()
         torch.cuda.synchronize()
         t3 = time.perf_counter()

@@ -241,3 +241,58 @@ def test_policy_grad_edge_cases():
         check(eng.lib.lmrl_policy_grad_host(eng.handle, big.ctypes.data, np.full(8, 40, np.int32).ctypes.data, 40, 8, np.zeros((8, 40), np.float32).ctypes.data,
                                             np.zeros((8, 40), np.float32).ctypes.data, C.c_float(1.0), C.byref(gs)))
     eng.close()
+
+
+def test_bc_term_on_the_engine_matches_autograd():
+    """PPO step with the BC term (loss + w * bc_loss, ppo/gpt2/interface.py:183-205): the engine path (lmrl_ppo_grad_host, then
+    lmrl_policy_grad_host accumulating the masked cross-entropy gradient) against fp32 autograd of ``loss + w * bc_loss``."""
+    import torch
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    from lmrl_gym_b200 import ppo_train as T
+    from lmrl_gym_b200.value_inference import forward_tokens
+    from oracle.gpt2 import bf16_round
+    tok = ByteTokenizer.synthetic()
+    cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+    rng = np.random.default_rng(4)
+    params = init_gpt2_params(cfg, seed=6)
+    for k in ("wte", "wpe"):
+        params[k] = bf16_round(params[k])
+    for L in params["layers"]:
+        for k in ("attn_w", "proj_w", "fc_w", "fc2_w"):
+            L[k] = bf16_round(L[k])
+    lin = dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, 1)) / 16).astype(np.float32), bias=np.asarray([0.1], np.float32)))
+    eng = Engine(max_envs=32, max_input_length=64, max_new_tokens=4, tokenizer=tok)
+    B200GPT2Policy(eng, params, cfg)
+    W = 2.5
+    ref = T.B200PPOTrain(eng, params, lin, cfg, lr=0.0, pad_token_id=tok.pad_token_id, activation_dtype="f32", backward="torch", bc_loss_weight=W)
+    b2 = T.B200PPOTrain(eng, params, lin, cfg, lr=0.0, pad_token_id=tok.pad_token_id, backward="b200", max_rows=2048, max_scored_rows=1024, bc_loss_weight=W)
+    batch = make_batch(rng, cfg, tok.pad_token_id, None)
+    ids = batch["input_ids"]
+    lens = (ids != tok.pad_token_id).sum(1)
+    cur = forward_tokens(eng, 0, 0, [ids[i, :lens[i]] for i in range(ids.shape[0])], logprobs=True, pitch=ids.shape[1])["logprobs"][:, :ids.shape[1] - 1]
+    batch["old_logprobs"] = (cur + 0.25 * rng.standard_normal(cur.shape)).astype(np.float32)
+    items = [[("Wordle:\n", 0.0), ("c r a n e\n", 1.0), ("b y b b g\n", 0.0), ("s l a t e\n", 1.0)], [("Wordle:\n", 0.0), ("a d i e u\n", 1.0)],
+             [("Wordle:\n", 0.0), ("s t o r k\n", 1.0), ("g b b y b\n", 0.0)]]
+    bc = T.bc_batch_from_str_segments(items, tok, 40, tok.pad_token_id)
+    loss_ref, logs_ref = ref.step(batch, bc)
+    g_ref = [f.grad.clone() for f in ref.flat]
+    loss_b, logs_b = b2.step(batch, bc)
+    torch.cuda.synchronize()
+    assert abs(logs_b["bc_loss"] - logs_ref["bc_loss"]) <= 2e-2 * max(1.0, abs(logs_ref["bc_loss"])), (logs_b["bc_loss"], logs_ref["bc_loss"])
+    assert abs(loss_b - loss_ref) <= 2e-2 * max(1.0, abs(loss_ref)) and abs(loss_b - (logs_b["ppo_loss"] + W * logs_b["bc_loss"])) <= 1e-6 * abs(loss_b)
+    assert logs_b["bc_loss"] > 5.0                                        # random-init model: about log(vocab)
+    for name in [n for grp in ref._names for n in grp]:
+        grp, o, shape = ref._views[name]
+        n = int(np.prod(shape))
+        a = g_ref[grp][o:o + n].double().cpu().numpy()
+        c = b2.gflat[grp][o:o + n].double().cpu().numpy()
+        rel = np.linalg.norm(c - a) / max(np.linalg.norm(a), 1e-12)
+        cos = float(c @ a / max(np.linalg.norm(c) * np.linalg.norm(a), 1e-20))
+        assert rel <= 2e-2 and cos >= 0.9995, (name, rel, cos)
+    # the BC term really contributes: without the BC batch the gradients differ
+    b2.step(batch, None)
+    torch.cuda.synchronize()
+    assert float((b2.gflat[0] - g_ref[0]).norm() / g_ref[0].norm()) > 0.05
+    eng.close()

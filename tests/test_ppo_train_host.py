@@ -146,3 +146,65 @@ def test_ppo_loss_grads_match_autograd():
     (pg + 0.7 * vf).backward()
     assert np.abs(LP.grad.numpy() - dlp).max() < 1e-7 and np.abs(V.grad.numpy() - dv).max() < 1e-7
     assert np.abs(dlp).max() > 0 and np.abs(dv).max() > 0
+
+
+def make_bc_batch(rng, b=4, t=10):
+    ids = np.full((b, t), PAD, np.int32)
+    m = np.zeros((b, t), np.float32)
+    for i in range(b):
+        n = int(rng.integers(3, t + 1))
+        ids[i, :n] = rng.integers(0, CFG.n_vocab, n)
+        m[i, :n] = rng.random(n) < 0.5
+    m[0, 1] = 1.0
+    return dict(input_ids=ids, input_training_mask=m)
+
+
+def test_bc_term_of_the_ppo_step():
+    """loss + w * bc_loss with policy gradients + w * bc gradients (ppo/gpt2/interface.py:183-205); bc_loss = masked next-token
+    cross-entropy (JaxSeq loss_fn_mask), checked here against the oracle's token log-probs."""
+    rng = np.random.default_rng(5)
+    batch, bc = make_batch(rng), make_bc_batch(rng)
+    tr, params, lin = make_trainer()
+    want, total = 0.0, 0.0
+    for i, row in enumerate(bc["input_ids"]):
+        n = int((row != PAD).sum())
+        lp = og.token_logprobs_all(params, row[:n].tolist(), CFG.n_head, CFG.n_vocab, weights_bf16=False)
+        want -= float((lp * bc["input_training_mask"][i, 1:n]).sum())
+        total += float(bc["input_training_mask"][i, 1:n].sum())
+    assert abs(float(tr.bc_loss(bc)) - want / total) <= 2e-4 * max(1.0, abs(want / total))
+
+    def grads(weight, with_bc):
+        tr, _, _ = make_trainer(lr=0.0)
+        tr.bc_loss_weight = weight
+        loss, logs = tr.step(batch, bc if with_bc else None)
+        return loss, logs, [f.grad.clone() for f in tr.flat]
+    l0, _, g0 = grads(0.0, False)
+    l1, logs1, g1 = grads(1.0, True)
+    l3, logs3, g3 = grads(3.0, True)
+    assert "bc_loss" not in grads(0.0, True)[1]                         # weight 0: the BC batch is ignored
+    assert abs(logs1["bc_loss"] - want / total) <= 2e-4 * max(1.0, abs(want / total))
+    assert abs(l1 - (l0 + logs1["bc_loss"])) <= 1e-5 * max(1.0, abs(l1)) and abs(l3 - (l0 + 3.0 * logs3["bc_loss"])) <= 1e-5 * max(1.0, abs(l3))
+    assert abs(logs1["ppo_loss"] - l0) <= 1e-6 * max(1.0, abs(l0)) and abs(logs3["total_loss"] - l3) <= 1e-6 * max(1.0, abs(l3))
+    for a, b, c in zip(g0, g1, g3):                                     # gradients are affine in the weight: g3 - g0 = 3 (g1 - g0)
+        assert float((b - a).abs().max()) > 0
+        np.testing.assert_allclose((c - a).numpy(), 3.0 * (b - a).numpy(), rtol=2e-3, atol=1e-6)
+    # the value head receives nothing from the BC term
+    grp, o, shape = tr._views["vh_w"]
+    n = int(np.prod(shape))
+    np.testing.assert_allclose(g1[grp][o:o + n].numpy(), g0[grp][o:o + n].numpy(), rtol=0, atol=0)
+
+
+def test_bc_batch_from_str_segments():
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    tok = ByteTokenizer.synthetic()
+    items = [[("Wordle:\n", 0.0), ("c r a n e\n", 1.0), ("b y b b g\n", 0.0), ("s l a t e\n", 1.0)], [("Wordle:\n", 0.0), ("a b\n", 1.0)]]
+    out = T.bc_batch_from_str_segments(items, tok, 24, tok.pad_token_id)
+    for i, segs in enumerate(items):
+        ids = sum((list(tok.encode(s)) for s, _ in segs), [])
+        ms = sum(([w] * len(tok.encode(s)) for s, w in segs), [])
+        ids, ms = ids[-24:], ms[-24:]                                    # LEFT truncation, RIGHT padding
+        assert out["input_ids"][i, :len(ids)].tolist() == ids and (out["input_ids"][i, len(ids):] == tok.pad_token_id).all()
+        assert out["input_training_mask"][i, :len(ms)].tolist() == ms and (out["input_training_mask"][i, len(ms):] == 0).all()
+    short = T.bc_batch_from_str_segments(items[:1], tok, 8, tok.pad_token_id)
+    full = sum((list(tok.encode(s)) for s, _ in items[0]), [])
+    assert short["input_ids"][0].tolist() == full[-8:]
