@@ -62,3 +62,30 @@ def test_maze_driver(tmp_path):
     res2 = drv.main("config", cfg, policy_n_rollouts=1, policy_bsize=1, policy_max_input_length=128, policy_max_output_length=3, seed=1,
                     use_reranker_for_reward_eval=True, policy_do_sample=False, do_accuracy_eval=False)
     assert res2["reward_eval"]["avg_reward"]["reward"]["min"] >= -101.0
+
+
+def test_ppo_training_driver(tmp_path):
+    drv = _load("train_ppo_wordle")
+    cfg = _tiny_config(tmp_path)
+    bc_path = str(tmp_path / "bc.jsonl")
+    with open(bc_path, "w") as f:
+        for w in ("crane", "slate", "adieu", "stork", "pious", "mange", "blimp", "fudgy"):
+            f.write(json.dumps({"sequence": [["Wordle:\n", 0.0], [" ".join(w) + "\n", 1.0]]}) + "\n")
+    out = str(tmp_path / "out")
+    hist = drv.main("config", cfg, bc_path, "wordle_official.txt", outputs_path=out, n_rounds=2, n_rollouts=16, rollout_bsize=16, train_bsize=4,
+                    max_input_length=128, max_output_length=6, max_steps=2, lr=1e-4, seed=0, save_at_end=True)
+    assert len(hist) == 2 and all(h["updates"] == 2 and np.isfinite(h["loss"]) for h in hist)
+    assert all(h["env_steps"] == 16 * 6 for h in hist)                     # a random-init policy never says a word: six invalid tries each
+    assert all(h["reward_mean"] == pytest.approx(-60.0) for h in hist)      # bad_word_reward = -10 in the PPO driver
+    assert hist[0]["loss"] > 5.0                                            # the BC term (about log vocab) is part of the loss
+    rounds = json.load(open(os.path.join(out, "rounds.json")))
+    assert len(rounds) == 2 and rounds[1]["kl_coef"] == pytest.approx(0.001)
+    from lmrl_gym_b200.load import load_params
+    p2, c2 = load_params("params", os.path.join(out, "policy_params.npz"))
+    assert c2.n_layer == 2 and p2["wte"].shape[1] == 256
+    vh = np.load(os.path.join(out, "value_head.npz"))
+    assert vh["kernel"].shape == (256, 1) and abs(float(vh["bias"][0]) + 4.1) < 0.1
+    # without BC data the loss is the PPO loss alone
+    hist2 = drv.main("config", cfg, "none", "wordle_official.txt", n_rounds=1, n_rollouts=8, rollout_bsize=8, train_bsize=4, max_input_length=128,
+                     max_output_length=6, max_steps=1, seed=0)
+    assert hist2[0]["updates"] == 1 and abs(hist2[0]["loss"]) < hist[0]["loss"]
