@@ -114,3 +114,11 @@ def init_from_env() -> Tuple[int, int, int]:
     if not dist.is_initialized():
         dist.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
     return dist.get_rank(), dist.get_world_size(), local
+
+
+def finalize() -> None:
+    """Leave the process group ``init_from_env`` joined (no-op in a single process)."""
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()

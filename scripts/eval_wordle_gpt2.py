@@ -74,6 +74,7 @@ def main(
         print(summary)
         dump_outputs(outputs_path, [list(ep) for ep in raw], summary)
     engine.close()
+    D.finalize()
     return {"generation_metrics": summary}
 
 

@@ -141,6 +141,7 @@ def main(
             save_params(os.path.join(outputs_path, "policy_params.npz"), trainer.params_numpy(), cfg)
             np.savez(os.path.join(outputs_path, "value_head.npz"), kernel=trainer.vh_w.detach().cpu().numpy(), bias=trainer.vh_b.detach().cpu().numpy())
     engine.close()
+    D.finalize()
     return history
 
 
