@@ -127,7 +127,10 @@ typedef struct lmrl_mlp_head {
     int32_t hidden;
     int32_t n_out;
 } lmrl_mlp_head;
-/* q2 may be NULL (MC returns: one head, wordle/mc/eval_mc_gpt2.py:103-116).  Switches the engine to the value-perturbed policy. */
+/* q2 may be NULL (MC returns: one head, wordle/mc/eval_mc_gpt2.py:103-116).  Switches the engine to the value-perturbed policy.
+ * A head with w1 == NULL is a LinearHead (heads/linear_head.py:112-119, the Q head of the MC-returns drivers,
+ * wordle/mc/train_mc_returns_gpt2.py:198-206): q(h) = h . w2 + b2 with w2 [d_model, n_out], hidden = d_model, b1 ignored, b2 may be
+ * NULL (use_bias = False).  q1 and q2 must be of the same kind. */
 int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_head* q2, float beta);
 /* 0 = plain LM policy (logits of tower 0), 1 = value-perturbed policy (pi_beta + beta * min q),
  * 2 = the pi_beta = None variant (logits = beta * min q, generation.py:118-119: only the value tower runs) */

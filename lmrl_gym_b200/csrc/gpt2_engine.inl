@@ -33,6 +33,8 @@ struct TowerDev {
 // Q heads of the value-perturbed policy: MLPHead = dense2(relu(dense1(h))) (heads/mlp_head.py:139-148), one or two of them
 struct QHeadsDev {
     int n_q = 0, hidden = 0;
+    int linear = 0;                   // 1: LinearHead Q heads (heads/linear_head.py:112-119, the MC-returns drivers): q = dense(h), no first layer;
+                                      //    w2 then holds beta * kernel and the value tower's final LN writes h straight into xl[:, d:2d]
     float beta = 0.f;
     __nv_bfloat16* w1cat = nullptr;   // [n_q * hidden][d]   dense1 kernels, transposed, stacked along N
     float* b1cat = nullptr;           // [n_q * hidden]
@@ -493,9 +495,11 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
         const TowerDev& T = G.tw[t];
         if (t > t_first) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, Ln.rows, Ln.x));
         if (tower_layers(e, T, mode, n_env)) return -1;
-        // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1
+        // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1 (MLP Q heads: operand of their first
+        // layer) or straight into xl[:, d:2d] (LinearHead Q heads: operand of the head GEMM's second K segment)
+        const bool to_xl = t == 0 || G.qh.linear;
         LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, head_n, head_gather,
-                                                                  t == 0 ? xl : xl1, t == 0 ? G.xl_cols : D.d_model));
+                                                                  t == 0 ? xl : (G.qh.linear ? xl + D.d_model : xl1), to_xl ? G.xl_cols : D.d_model));
     }
     // top-k / top-p: the LM head dumps fp32 logits and a per-row filter kernel samples from the survivors (slow path)
     const bool filtered = !score && (s.top_k > 0 || (s.top_p > 0.f && s.top_p < 1.f));
@@ -521,20 +525,24 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     if (G.policy_kind >= 1) {
         // Q heads, first layer: xl[:, d + k*hidden ...] = beta * relu(xl1 · W1_k^T + b1_k)   (mlp_head.py:146-147; beta folded in here)
         const QHeadsDev& Q = G.qh;
-        GemmArgs r{};
-        r.A = xl1; r.W = Q.w1cat; r.bias = Q.b1cat; r.N = Q.n_q * Q.hidden; r.K = D.d_model; r.M_dev = head_n; r.out = xl;
-        r.out_col0 = D.d_model; r.out_scale = Q.beta;
-        GemmExtra rx;
-        rx.out_cols = (size_t)G.xl_cols;
-        if (launch_gemm<EPI_RELU>(e, r, r.N, 1, xl_rows, (size_t)r.N, 4, rx)) return -1;
-        // logits = min_k(h_pi · wte^T + beta * (relu_k · W2_k^T + b2_k))   (generation.py:112-119)
+        if (!Q.linear) {
+            GemmArgs r{};
+            r.A = xl1; r.W = Q.w1cat; r.bias = Q.b1cat; r.N = Q.n_q * Q.hidden; r.K = D.d_model; r.M_dev = head_n; r.out = xl;
+            r.out_col0 = D.d_model; r.out_scale = Q.beta;
+            GemmExtra rx;
+            rx.out_cols = (size_t)G.xl_cols;
+            if (launch_gemm<EPI_RELU>(e, r, r.N, 1, xl_rows, (size_t)r.N, 4, rx)) return -1;
+        }
+        // logits = min_k(h_pi · wte^T + beta * (relu_k · W2_k^T + b2_k))   (generation.py:112-119); LinearHead Q heads: both heads read
+        // the value tower's hidden h in xl[:, d:2d] and their kernels carry beta
         const int kb_h = Q.hidden / TC_BK;
+        const int a2 = Q.linear ? kb_d : kb_d + kb_h;          // A-operand column block of the second head
         h.n_acc = Q.n_q; h.n_seg = 2 * Q.n_q;
         h.seg[0] = {0, 0, 0, kb_d}; h.seg[1] = {0, kb_d, 1, kb_h};
-        h.seg[2] = {1, 0, 0, kb_d}; h.seg[3] = {1, kb_d + kb_h, 2, kb_h};
+        h.seg[2] = {1, 0, 0, kb_d}; h.seg[3] = {1, a2, 2, kb_h};
         if (G.policy_kind == 2) {                     // pi_beta is None: logits = beta * min_k q_k (generation.py:118-119) — no LM-head segment
             h.n_seg = Q.n_q;
-            h.seg[0] = {0, kb_d, 1, kb_h}; h.seg[1] = {1, kb_d + kb_h, 2, kb_h};
+            h.seg[0] = {0, kb_d, 1, kb_h}; h.seg[1] = {1, a2, 2, kb_h};
         }
         h.bias = Q.b2s[0]; h.bias2 = Q.b2s[1];
         hx.W1 = Q.w2[0]; hx.w1_cols = (size_t)Q.hidden;
@@ -743,18 +751,21 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
 
 int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_head* q2, float beta) {
     LMRL_CHECK(e && e->gpt2 && e->gpt2->tw[0].loaded && e->gpt2->tw[1].loaded, "lmrl_load_q_heads: load pi_beta (tower 0) and the value base (tower 1) first");
-    LMRL_CHECK(q1 && q1->w1 && q1->b1 && q1->w2 && q1->b2, "lmrl_load_q_heads: q1 is required");
+    LMRL_CHECK(q1 && q1->w2, "lmrl_load_q_heads: q1 is required");
+    const bool linear = q1->w1 == nullptr;          // LinearHead: only the one kernel (w2) and its optional bias (b2)
+    LMRL_CHECK(linear || (q1->b1 && q1->b2), "lmrl_load_q_heads: an MLPHead needs w1, b1, w2, b2");
+    LMRL_CHECK(!q2 || (q2->w2 && (q2->w1 == nullptr) == linear && (linear || (q2->b1 && q2->b2))), "lmrl_load_q_heads: q1 and q2 must be heads of the same kind");
     LMRL_CUDA(cudaSetDevice(e->device));
     Gpt2Dev& G = *e->gpt2;
     QHeadsDev& Q = G.qh;
     const int d = G.dims.d_model, hid = q1->hidden, n_q = q2 ? 2 : 1;
-    LMRL_CHECK(hid == d, "lmrl_load_q_heads: hidden_dim %d must equal d_model %d (MLPHeadConfig of train_ilql_gpt2.py:224-231)", hid, d);
+    LMRL_CHECK(hid == d, "lmrl_load_q_heads: hidden_dim %d must equal d_model %d (MLPHeadConfig of train_ilql_gpt2.py:224-231; a LinearHead passes d_model)", hid, d);
     LMRL_CHECK(!q2 || q2->hidden == hid, "lmrl_load_q_heads: q1 and q2 differ in hidden_dim");
     LMRL_CHECK(q1->n_out >= G.dims.n_vocab && (!q2 || q2->n_out >= G.dims.n_vocab), "lmrl_load_q_heads: head output_dim is smaller than n_vocab");
-    LMRL_CHECK(Q.n_q == 0 || Q.n_q == n_q, "lmrl_load_q_heads: set_params with a different number of Q heads");
+    LMRL_CHECK(Q.n_q == 0 || (Q.n_q == n_q && Q.linear == (linear ? 1 : 0)), "lmrl_load_q_heads: set_params with a different number or kind of Q heads");
     const bool fresh = Q.n_q == 0;
     if (fresh) {
-        if (e->alloc(&Q.w1cat, (size_t)n_q * hid * d) || e->alloc(&Q.b1cat, (size_t)n_q * hid)) return -1;
+        if (!linear && (e->alloc(&Q.w1cat, (size_t)n_q * hid * d) || e->alloc(&Q.b1cat, (size_t)n_q * hid))) return -1;
         for (int k = 0; k < n_q; ++k)
             if (e->alloc(&Q.w2[k], (size_t)G.v_pad * hid) || e->alloc(&Q.b2s[k], (size_t)G.v_pad)) return -1;
     }
@@ -763,24 +774,35 @@ int lmrl_load_q_heads(lmrl_engine* e, const lmrl_mlp_head* q1, const lmrl_mlp_he
     const lmrl_mlp_head* qs[2] = {q1, q2};
     for (int k = 0; k < n_q; ++k) {
         const lmrl_mlp_head* q = qs[k];
-        // dense1 kernel [d][hid] -> rows [k*hid, (k+1)*hid) of w1cat [.][d]
-        LMRL_CUDA(cudaMemcpyAsync(stage, q->w1, (size_t)d * hid * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        transpose_to_bf16_kernel<<<dim3((hid + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, hid, Q.w1cat + (size_t)k * hid * d);
-        LMRL_CUDA(cudaStreamSynchronize(e->stream));
-        LMRL_CUDA(cudaMemcpyAsync(Q.b1cat + (size_t)k * hid, q->b1, (size_t)hid * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        // dense2 kernel [hid][n_out] -> w2 [v_pad][hid] (rows beyond n_out stay zero; ids beyond n_vocab are masked by the sampler)
+        if (!linear) {
+            // dense1 kernel [d][hid] -> rows [k*hid, (k+1)*hid) of w1cat [.][d]
+            LMRL_CUDA(cudaMemcpyAsync(stage, q->w1, (size_t)d * hid * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            transpose_to_bf16_kernel<<<dim3((hid + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, hid, Q.w1cat + (size_t)k * hid * d);
+            LMRL_CUDA(cudaStreamSynchronize(e->stream));
+            LMRL_CUDA(cudaMemcpyAsync(Q.b1cat + (size_t)k * hid, q->b1, (size_t)hid * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        }
+        // dense2 (or LinearHead) kernel [hid][n_out] -> w2 [v_pad][hid] (rows beyond n_out stay zero; ids beyond n_vocab are masked by the
+        // sampler).  MLPHead: beta is folded into the first layer's output; LinearHead: into this kernel (one bf16 rounding of beta * w).
         const int n_rows = std::min(q->n_out, G.v_pad);
-        LMRL_CUDA(cudaMemcpyAsync(stage, q->w2, (size_t)hid * q->n_out * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (linear) {
+            std::vector<float> scaled((size_t)hid * q->n_out);
+            for (size_t i = 0; i < scaled.size(); ++i) scaled[i] = beta * q->w2[i];
+            LMRL_CUDA(cudaMemcpyAsync(stage, scaled.data(), scaled.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            LMRL_CUDA(cudaStreamSynchronize(e->stream));
+        } else {
+            LMRL_CUDA(cudaMemcpyAsync(stage, q->w2, (size_t)hid * q->n_out * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        }
         transpose_to_bf16_kernel<<<dim3((n_rows + 31) / 32, (hid + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, hid, q->n_out, Q.w2[k], n_rows);
         LMRL_CUDA(cudaStreamSynchronize(e->stream));
         std::vector<float> b2((size_t)G.v_pad, 0.f);
-        for (int i = 0; i < n_rows; ++i) b2[i] = beta * q->b2[i];
+        if (q->b2)
+            for (int i = 0; i < n_rows; ++i) b2[i] = beta * q->b2[i];
         LMRL_CUDA(cudaMemcpyAsync(Q.b2s[k], b2.data(), b2.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         LMRL_CUDA(cudaStreamSynchronize(e->stream));
     }
     cudaFree(stage);
     LMRL_CUDA(cudaGetLastError());
-    Q.n_q = n_q; Q.hidden = hid; Q.beta = beta;
+    Q.n_q = n_q; Q.hidden = hid; Q.beta = beta; Q.linear = linear ? 1 : 0;
     G.policy_kind = 1;
     return 0;
 }

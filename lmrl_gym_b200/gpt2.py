@@ -153,12 +153,16 @@ def _upload_q_heads(engine: Engine, q1: Dict, q2: Optional[Dict], beta: float):
         if q is None:
             return None
         h = _lib.lmrl_mlp_head()
-        for name, a in (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"])):
+        if "dense" in q:            # LinearHead (heads/linear_head.py:112-119; the MC-returns drivers' Q head): w1 / b1 stay NULL
+            fields = (("w2", q["dense"]["kernel"]),) + ((("b2", q["dense"]["bias"]),) if q["dense"].get("bias") is not None else ())
+            h.hidden, h.n_out = int(q["dense"]["kernel"].shape[0]), int(q["dense"]["kernel"].shape[1])
+        else:
+            fields = (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"]))
+            h.hidden, h.n_out = int(q["dense1"]["kernel"].shape[1]), int(q["dense2"]["kernel"].shape[1])
+        for name, a in fields:
             a = np.ascontiguousarray(a, dtype=np.float32)
             keep.append(a)
             setattr(h, name, a.ctypes.data_as(_lib._PF))
-        h.hidden = int(q["dense1"]["kernel"].shape[1])
-        h.n_out = int(q["dense2"]["kernel"].shape[1])
         keep.append(h)
         return h
 
@@ -256,8 +260,10 @@ class B200GPT2ValuePolicy(B200GPT2Policy):
     uses ``logits = pi_beta(x) + beta * min(Q1(h), Q2(h))`` with ``h`` the last hidden state of the value base
     (value_rl_base/gpt2/generation.py:36-121).  ``params`` is the reference's tuple
     ``(pi_beta_params, base_params, q1_head_params, q2_head_params-or-None)`` (interface.py:101); GPT-2 parameter sets use
-    the dict layout of ``init_gpt2_params``, heads the flax layout ``{'dense1': {'kernel','bias'}, 'dense2': {...}}``.
-    ILQL passes two Q heads (beta 16 in wordle/ilql/eval_ilql_gpt2.py:47), MC returns one (wordle/mc/eval_mc_gpt2.py:103-116)."""
+    the dict layout of ``init_gpt2_params``, heads the flax layout ``{'dense1': {'kernel','bias'}, 'dense2': {...}}`` (MLPHead) or
+    ``{'dense': {'kernel','bias'}}`` (LinearHead, ``q = dense(h)``).
+    ILQL passes two MLP Q heads (beta 16 in wordle/ilql/eval_ilql_gpt2.py:47), MC returns one LinearHead (wordle/mc/eval_mc_gpt2.py:93-107,
+    train_mc_returns_gpt2.py:198-206)."""
 
     def __init__(self, engine: Engine, params: Tuple, config: Optional[GPT2Config] = None, beta: float = 16.0, **kw):
         pi_beta, base, q1, q2 = params

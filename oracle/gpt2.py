@@ -105,7 +105,12 @@ def sequence_logprob(params: Dict, tokens: Sequence[int], prefix_len: int, n_hea
 # ---- ILQL / MC value-perturbed logits -------------------------------------------------------------------------------
 
 def mlp_head(h: "torch.Tensor", q: Dict, weights_bf16: bool = True) -> "torch.Tensor":
-    """MLPHead.__call__ (LLM_RL/heads/mlp_head.py:139-148): dense2(relu(dense1(x)))."""
+    """MLPHead.__call__ (LLM_RL/heads/mlp_head.py:139-148): dense2(relu(dense1(x))); a ``{"dense": ...}`` dict is a LinearHead
+    (heads/linear_head.py:112-119): dense(x)."""
+    if "dense" in q:
+        b = q["dense"].get("bias")
+        out = h @ _t(q["dense"]["kernel"], weights_bf16)
+        return out if b is None else out + torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32))
     w1, w2 = _t(q["dense1"]["kernel"], weights_bf16), _t(q["dense2"]["kernel"], weights_bf16)
     b1 = torch.from_numpy(np.ascontiguousarray(q["dense1"]["bias"], dtype=np.float32))
     b2 = torch.from_numpy(np.ascontiguousarray(q["dense2"]["bias"], dtype=np.float32))
@@ -132,6 +137,11 @@ def value_policy_last_logits(params, tokens: Sequence[int], n_head: int, n_vocab
     outs = []
     for q in (q1, q2):
         if q is None:
+            continue
+        if "dense" in q:                     # LinearHead: the engine folds beta into the bf16 kernel, h_v is already bf16-rounded
+            b = q["dense"].get("bias")
+            bias = torch.zeros(n_vocab) if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32))[:n_vocab]
+            outs.append(pi_logits + h_v @ _r(beta * _t(q["dense"]["kernel"], False), True)[:, :n_vocab] + beta * bias)
             continue
         b1 = torch.from_numpy(np.ascontiguousarray(q["dense1"]["bias"], dtype=np.float32))
         b2 = torch.from_numpy(np.ascontiguousarray(q["dense2"]["bias"], dtype=np.float32))

@@ -136,3 +136,51 @@ def test_value_policy_fused_rollout_replays_through_oracle_env(tok):
                 s = og.sample_scores(logits, og.row_key(3, seed_list[i], t, k), 1.0, True)
                 assert s[tk] >= s.max() - 2 * TOL_EMU, (i, t, k)
     eng.close()
+
+
+def _linear_head(cfg, seed, bias=True):
+    rng = np.random.default_rng(seed)
+    k = (rng.standard_normal((cfg.d_model, cfg.n_vocab_rows)) / np.sqrt(cfg.d_model)).astype(np.float32)
+    return dict(dense=dict(kernel=k, bias=(0.3 * rng.standard_normal(cfg.n_vocab_rows)).astype(np.float32) if bias else None))
+
+
+@pytest.mark.parametrize("n_heads,with_pi_beta,bias", [(1, True, True), (2, True, True), (1, False, False)],
+                         ids=["mc-one-linear-head", "two-linear-heads", "no-pi-beta-no-bias"])
+def test_value_policy_with_linear_q_heads(tok, n_heads, with_pi_beta, bias):
+    """The MC-returns policy: the Q head is a LinearHead over the value base's last hidden state (wordle/mc/eval_mc_gpt2.py:93-107,
+    heads/linear_head.py:112-119): logits = pi_beta + beta * (h W + b)."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2ValuePolicy
+    from oracle import gpt2 as og
+    cfg = _cfg()
+    q1 = _linear_head(cfg, 21, bias)
+    q2 = _linear_head(cfg, 22, bias) if n_heads == 2 else None
+    params = (init_gpt2_params(cfg, seed=30) if with_pi_beta else None, init_gpt2_params(cfg, seed=31), q1, q2)
+    eng = Engine(max_envs=64, max_input_length=48, max_new_tokens=4, tokenizer=tok)
+    pol = B200GPT2ValuePolicy(eng, params, cfg, beta=BETA, seed=3)
+    rng = np.random.default_rng(1)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, 48, size=40)]
+    got = pol.logits(prompts)
+    worst_emu = worst_f32 = 0.0
+    for i in range(0, 40, 4):
+        emu = og.value_policy_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, BETA, emulate_bf16=True)
+        f32 = og.value_policy_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, BETA)
+        worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+        worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+    print(f"linear Q heads ({n_heads}): max|logit diff| vs bf16-emulating oracle {worst_emu:.4g}, vs fp32 oracle {worst_f32:.4g}")
+    assert worst_emu <= TOL_EMU and worst_f32 <= TOL_F32
+    if n_heads == 2:                                    # min over the heads, not one of them
+        one = og.value_policy_last_logits(params[:3] + (None,), prompts[0], cfg.n_head, cfg.n_vocab, BETA, emulate_bf16=True)
+        assert np.abs(got[0] - one).max() > 0.5
+    # decode path (KV caches of both towers) + sampler: every sampled id is the oracle's arg-max up to tolerance
+    keys = [int(k) for k in rng.integers(0, 2**63, size=40)]
+    gens = pol.generate_tokens(prompts, episode_keys=keys, turn=2)
+    for i in range(0, 40, 8):
+        for k, t in enumerate(gens[i]):
+            logits = og.value_policy_last_logits(params, prompts[i] + gens[i][:k], cfg.n_head, cfg.n_vocab, BETA, emulate_bf16=True)
+            sc = og.sample_scores(logits, og.row_key(3, keys[i], 2, k))
+            assert sc[t] >= sc.max() - 2 * TOL_EMU, (i, k)
+    # set_params with heads of the other kind is refused (buffers are laid out per kind)
+    with pytest.raises(Exception):
+        pol.set_params(_params(cfg, n_heads == 2))
+    eng.close()
