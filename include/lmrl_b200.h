@@ -182,7 +182,7 @@ int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok,
  * Head sets: 0 = online heads (q1, q2, v), 1 = target heads (q1_target, q2_target).  A head set is independent of the
  * beta-scaled Q heads lmrl_load_q_heads installs for sampling. */
 typedef struct lmrl_value_heads {
-    const lmrl_mlp_head* q1;      /* MLPHead d -> hidden -> n_out (>= n_vocab), or NULL */
+    const lmrl_mlp_head* q1;      /* MLPHead d -> hidden -> n_out (>= n_vocab), or a LinearHead (w1 == NULL: kernel in w2, bias in b2 or NULL), or NULL */
     const lmrl_mlp_head* q2;      /* or NULL */
     const lmrl_mlp_head* v;       /* MLPHead d -> hidden -> 1 (ILQL V head), or NULL */
     const float* v_linear_w;      /* LinearHead kernel [d_model] (output_dim 1; the PPO value head), or NULL */

@@ -56,6 +56,7 @@ struct ValueHeadsDev {
     float* lin_w = nullptr;           // [d] LinearHead kernel
     float b2v = 0.f, lin_b = 0.f;
     bool has_lin = false, allocated = false;
+    bool q_lin[2] = {false, false};   // Q head k is a LinearHead: w2q[k] = its kernel (transposed), applied to the final-LN hidden itself
 };
 
 struct TrainDev;                          // train_kernels.inl: buffers of the hand-written backward pass
@@ -974,7 +975,8 @@ int lmrl_load_value_heads(lmrl_engine* e, int32_t head_set, const lmrl_value_hea
     const lmrl_mlp_head* mlp[3] = {h->q1, h->q2, h->v};
     for (int k = 0; k < 3; ++k) {
         if (!mlp[k]) continue;
-        LMRL_CHECK(mlp[k]->w1 && mlp[k]->b1 && mlp[k]->w2 && mlp[k]->b2, "lmrl_load_value_heads: head %d has a null array", k);
+        const bool lin_q = k < 2 && mlp[k]->w1 == nullptr;          // LinearHead Q head (MC returns): kernel in w2, optional bias in b2
+        LMRL_CHECK(mlp[k]->w2 && (lin_q || (mlp[k]->w1 && mlp[k]->b1 && mlp[k]->b2)), "lmrl_load_value_heads: head %d has a null array", k);
         LMRL_CHECK(mlp[k]->hidden == d, "lmrl_load_value_heads: hidden_dim %d must equal d_model %d", mlp[k]->hidden, d);
         LMRL_CHECK(k == 2 ? mlp[k]->n_out == 1 : mlp[k]->n_out >= G.dims.n_vocab, "lmrl_load_value_heads: head %d has output_dim %d", k, mlp[k]->n_out);
     }
@@ -989,23 +991,27 @@ int lmrl_load_value_heads(lmrl_engine* e, int32_t head_set, const lmrl_value_hea
     for (int k = 0; k < 2; ++k) if (mlp[k]) n_out_max = std::max(n_out_max, mlp[k]->n_out);
     float* stage = nullptr;
     LMRL_CUDA(cudaMalloc(&stage, (size_t)d * std::max(n_out_max, d) * sizeof(float)));
-    H.n_mlp = 0; H.hidden = d; H.slot_q1 = H.slot_q2 = H.slot_v = -1; H.has_lin = false;
+    H.n_mlp = 0; H.hidden = d; H.slot_q1 = H.slot_q2 = H.slot_v = -1; H.has_lin = false; H.q_lin[0] = H.q_lin[1] = false;
     for (int k = 0; k < 3; ++k) {
         const lmrl_mlp_head* q = mlp[k];
         if (!q) continue;
-        const int slot = H.n_mlp++;
-        (k == 0 ? H.slot_q1 : k == 1 ? H.slot_q2 : H.slot_v) = slot;
-        LMRL_CUDA(cudaMemcpyAsync(stage, q->w1, (size_t)d * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-        transpose_to_bf16_kernel<<<dim3((d + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, d, H.w1cat + (size_t)slot * d * d);
-        LMRL_CUDA(cudaStreamSynchronize(e->stream));
-        LMRL_CUDA(cudaMemcpyAsync(H.b1cat + (size_t)slot * d, q->b1, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        if (k < 2 && q->w1 == nullptr) {
+            H.q_lin[k] = true;                                      // no first layer, no slot in the ReLU buffer
+        } else {
+            const int slot = H.n_mlp++;
+            (k == 0 ? H.slot_q1 : k == 1 ? H.slot_q2 : H.slot_v) = slot;
+            LMRL_CUDA(cudaMemcpyAsync(stage, q->w1, (size_t)d * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            transpose_to_bf16_kernel<<<dim3((d + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, d, H.w1cat + (size_t)slot * d * d);
+            LMRL_CUDA(cudaStreamSynchronize(e->stream));
+            LMRL_CUDA(cudaMemcpyAsync(H.b1cat + (size_t)slot * d, q->b1, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        }
         if (k < 2) {
             const int n_rows = std::min(q->n_out, G.v_pad);
             LMRL_CUDA(cudaMemcpyAsync(stage, q->w2, (size_t)d * q->n_out * sizeof(float), cudaMemcpyHostToDevice, e->stream));
             transpose_to_bf16_kernel<<<dim3((n_rows + 31) / 32, (d + 31) / 32), dim3(32, 8), 0, e->stream>>>(stage, d, q->n_out, H.w2q[k], n_rows);
             LMRL_CUDA(cudaStreamSynchronize(e->stream));
             LMRL_CUDA(cudaMemsetAsync(H.b2q[k], 0, (size_t)G.v_pad * sizeof(float), e->stream));
-            LMRL_CUDA(cudaMemcpyAsync(H.b2q[k], q->b2, (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+            if (q->b2) LMRL_CUDA(cudaMemcpyAsync(H.b2q[k], q->b2, (size_t)n_rows * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         } else {
             LMRL_CUDA(cudaMemcpyAsync(H.w2v, q->w2, (size_t)d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
             H.b2v = q->b2[0];
@@ -1035,8 +1041,8 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
     const lmrl_gpt2_dims& D = G.dims;
     const ValueHeadsDev& H = G.vh[head_set];
     const bool want_lp = out->token_logprobs != nullptr, want_v = out->v != nullptr, want_q1 = out->q1 != nullptr, want_q2 = out->q2 != nullptr;
-    LMRL_CHECK(!want_q1 || H.slot_q1 >= 0, "lmrl_forward: q1 requested but head set %d has no Q1 head", head_set);
-    LMRL_CHECK(!want_q2 || H.slot_q2 >= 0, "lmrl_forward: q2 requested but head set %d has no Q2 head", head_set);
+    LMRL_CHECK(!want_q1 || H.slot_q1 >= 0 || H.q_lin[0], "lmrl_forward: q1 requested but head set %d has no Q1 head", head_set);
+    LMRL_CHECK(!want_q2 || H.slot_q2 >= 0 || H.q_lin[1], "lmrl_forward: q2 requested but head set %d has no Q2 head", head_set);
     LMRL_CHECK(!want_v || H.slot_v >= 0 || H.has_lin, "lmrl_forward: v requested but head set %d has no V head", head_set);
     if (forward_alloc(e)) return -1;
     const int max_in = e->cfg.max_input_length;
@@ -1050,7 +1056,8 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
     const TowerDev& T = G.tw[tower];
     cudaStream_t st = e->stream;
     const int ew_blocks = G.sm_count * 8;
-    const bool need_mlp = (want_q1 || want_q2 || (want_v && H.slot_v >= 0)) && H.n_mlp > 0;
+    const bool need_mlp = ((want_q1 && H.slot_q1 >= 0) || (want_q2 && H.slot_q2 >= 0) || (want_v && H.slot_v >= 0)) && H.n_mlp > 0;
+    const bool need_lin_q = (want_q1 && H.q_lin[0]) || (want_q2 && H.q_lin[1]);
     std::vector<int32_t> targets;
     std::vector<float> host[4];
     for (int i0 = 0; i0 < n;) {
@@ -1072,7 +1079,7 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
             LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
             LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
             if (tower_layers(e, T, 0, nc)) return -1;
-            if (want_lp || need_mlp)
+            if (want_lp || need_mlp || need_lin_q)
                 LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, T.lnf_g, T.lnf_b, D.d_model, D.ln_eps, G.rows.M, (const int*)nullptr, G.fx, D.d_model));
             if (want_lp) {
                 GemmArgs h{};
@@ -1095,6 +1102,7 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
                 ValueHeadArgs a{};
                 a.fr = G.fr; a.fr_pitch = 3 * D.d_model; a.hidden = H.hidden;
                 a.slot_q1 = want_q1 ? H.slot_q1 : -1; a.slot_q2 = want_q2 ? H.slot_q2 : -1; a.slot_v = want_v ? H.slot_v : -1;
+                a.fx = G.fx; a.q1_lin = (want_q1 && H.q_lin[0]) ? 1 : 0; a.q2_lin = (want_q2 && H.q_lin[1]) ? 1 : 0;
                 a.w2q1 = H.w2q[0]; a.b2q1 = H.b2q[0]; a.w2q2 = H.w2q[1]; a.b2q2 = H.b2q[1]; a.w2v = H.w2v; a.b2v = H.b2v;
                 a.targets = G.f_targets;
                 a.x = G.x; a.lnf_g = T.lnf_g; a.lnf_b = T.lnf_b; a.lin_w = H.lin_w; a.lin_b = H.lin_b; a.d = D.d_model; a.eps = D.ln_eps;

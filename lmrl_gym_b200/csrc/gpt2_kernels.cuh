@@ -198,6 +198,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 // HBM-bound: per row (n_heads + 1) * hidden * 2 B of operands -> 4..12 B of results.
 struct ValueHeadArgs {
     const __nv_bfloat16* fr; int fr_pitch; int hidden;
+    const __nv_bfloat16* fx; int q1_lin, q2_lin;      // LinearHead Q heads: q_k = fx_row . w2q_k[target] + b (fx = final-LN hidden, [M][d])
     int slot_q1, slot_q2, slot_v;
     const __nv_bfloat16* w2q1; const float* b2q1;
     const __nv_bfloat16* w2q2; const float* b2q2;
@@ -236,12 +237,12 @@ __global__ void value_heads_kernel(const int* __restrict__ n_dev, ValueHeadArgs 
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
         const int tgt = a.targets[r];
         const __nv_bfloat16* rr = a.fr + (size_t)r * a.fr_pitch;
-        if (a.slot_q1 >= 0) {
-            const float q = dot_bf16_bf16(rr + a.slot_q1 * a.hidden, a.w2q1 + (size_t)tgt * a.hidden, a.hidden, lane);
+        if (a.slot_q1 >= 0 || a.q1_lin) {
+            const float q = dot_bf16_bf16(a.q1_lin ? a.fx + (size_t)r * a.d : rr + a.slot_q1 * a.hidden, a.w2q1 + (size_t)tgt * a.hidden, a.hidden, lane);
             if (lane == 0) a.q1_out[r] = q + a.b2q1[tgt];
         }
-        if (a.slot_q2 >= 0) {
-            const float q = dot_bf16_bf16(rr + a.slot_q2 * a.hidden, a.w2q2 + (size_t)tgt * a.hidden, a.hidden, lane);
+        if (a.slot_q2 >= 0 || a.q2_lin) {
+            const float q = dot_bf16_bf16(a.q2_lin ? a.fx + (size_t)r * a.d : rr + a.slot_q2 * a.hidden, a.w2q2 + (size_t)tgt * a.hidden, a.hidden, lane);
             if (lane == 0) a.q2_out[r] = q + a.b2q2[tgt];
         }
         if (a.slot_v >= 0) {

@@ -28,19 +28,24 @@ def _mlp_struct(q: Optional[Dict], keep: list):
     if q is None:
         return None
     h = _lib.lmrl_mlp_head()
-    for name, a in (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"])):
+    if "dense" in q:                # LinearHead Q head (heads/linear_head.py:112-119; MC returns): w1 / b1 stay NULL
+        fields = (("w2", q["dense"]["kernel"]),) + ((("b2", q["dense"]["bias"]),) if q["dense"].get("bias") is not None else ())
+        h.hidden, h.n_out = int(q["dense"]["kernel"].shape[0]), int(q["dense"]["kernel"].shape[1])
+    else:
+        fields = (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"]))
+        h.hidden, h.n_out = int(q["dense1"]["kernel"].shape[1]), int(q["dense2"]["kernel"].shape[1])
+    for name, a in fields:
         a = np.ascontiguousarray(a, dtype=np.float32)
         keep.append(a)
         setattr(h, name, a.ctypes.data_as(_lib._PF))
-    h.hidden = int(q["dense1"]["kernel"].shape[1])
-    h.n_out = int(q["dense2"]["kernel"].shape[1])
     keep.append(h)
     return h
 
 
 def upload_value_heads(engine: Engine, head_set: int, q1: Optional[Dict] = None, q2: Optional[Dict] = None, v: Optional[Dict] = None,
                        v_linear: Optional[Dict] = None) -> None:
-    """q1 / q2 / v: flax ``MLPHead`` params ``{'dense1': {'kernel','bias'}, 'dense2': {...}}`` (heads/mlp_head.py:99-148);
+    """q1 / q2 / v: flax ``MLPHead`` params ``{'dense1': {'kernel','bias'}, 'dense2': {...}}`` (heads/mlp_head.py:99-148); q1 / q2 may
+    instead be ``LinearHead`` params ``{'dense': {'kernel' [d, n_out], 'bias'}}`` (the MC-returns Q head);
     v_linear: flax ``LinearHead`` params ``{'dense': {'kernel' [d, 1], 'bias' [1] (optional)}}`` (heads/linear_head.py:91-119)."""
     keep: list = []
     hs = _lib.lmrl_value_heads()

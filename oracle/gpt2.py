@@ -163,6 +163,11 @@ def value_forward_gathered(base: Dict, q1: Optional[Dict], q2: Optional[Dict], v
     for name, q in (("q1", q1), ("q2", q2)):
         if q is None:
             continue
+        if "dense" in q:                     # LinearHead Q head (heads/linear_head.py:112-119): q = dense(h)
+            w = _t(q["dense"]["kernel"], weights_bf16)[:, nxt]
+            b = q["dense"].get("bias")
+            out[name] = ((h[:-1] * w.T).sum(-1) + (0.0 if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32))[nxt])).numpy()
+            continue
         b1 = torch.from_numpy(np.ascontiguousarray(q["dense1"]["bias"], dtype=np.float32))
         b2 = torch.from_numpy(np.ascontiguousarray(q["dense2"]["bias"], dtype=np.float32))
         r = _r(torch.relu(h[:-1] @ _t(q["dense1"]["kernel"], weights_bf16) + b1), emulate_bf16)

@@ -176,3 +176,39 @@ def test_advantage_score_fns_and_reranker(tok, kind):
             n_ok += choice[-1].text == RR.MAZE_ACTIONS[int(np.argmax(want))]
     assert n_ok == n_clear
     eng.close()
+
+
+def test_forward_linear_q_head_matches_oracle(tok):
+    """MC returns: the Q head is a LinearHead over the base model's last hidden state (train_mc_returns_gpt2.py:198-206,
+    mc_returns/score_fn.py): q(h_t)[tok_{t+1}] = h_t . W[:, tok_{t+1}] + b — one kernel column gathered per position; an MLP V head next
+    to it keeps working (mixed head kinds in one head set)."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from lmrl_gym_b200 import value_inference as VI
+    from oracle import gpt2 as og
+    cfg = _cfg()
+    pi, base = init_gpt2_params(cfg, seed=0), init_gpt2_params(cfg, seed=1)
+    rng = np.random.default_rng(8)
+    lin = lambda bias: dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, cfg.n_vocab_rows)) / np.sqrt(cfg.d_model)).astype(np.float32),  # noqa: E731
+                                       bias=(0.3 * rng.standard_normal(cfg.n_vocab_rows)).astype(np.float32) if bias else None))
+    q1, q2 = lin(True), lin(False)
+    _, _, v = _heads(cfg, 10)
+    eng = Engine(max_envs=48, max_input_length=64, max_new_tokens=4, tokenizer=tok)
+    B200GPT2Policy(eng, pi, cfg)
+    inf = VI.B200ValueRLInference(eng, base, q1, q2, v, cfg, tower=1, head_set=0)
+    seqs = _seqs(cfg, 40, 1, 65, 4)
+    res = inf.forward_ragged(seqs)
+    worst = dict(emu=0.0, f32=0.0, v=0.0)
+    for i in range(0, 40, 3):
+        s, n = seqs[i], len(seqs[i])
+        for emu in (True, False):
+            o = og.value_forward_gathered(base, q1, q2, v, s, cfg.n_head, emulate_bf16=emu)
+            for name in ("q1", "q2"):
+                if n > 1:
+                    worst["emu" if emu else "f32"] = max(worst["emu" if emu else "f32"], float(np.abs(res[name][i, :n - 1] - o[name]).max()))
+            if emu:
+                worst["v"] = max(worst["v"], float(np.abs(res["v"][i, :n] - o["v"]).max()))
+    print("linear Q heads, per-position forward, max |diff| vs oracle:", {k: round(x, 5) for k, x in worst.items()})
+    assert worst["emu"] <= 3e-2 and worst["f32"] <= 8e-2 and worst["v"] <= 6e-2
+    assert np.abs(res["q1"] - res["q2"]).mean() > 1e-2
+    eng.close()
