@@ -68,3 +68,34 @@ def load_params(model_load_mode: ModelLoadMode, model_load_path: str, seed: int 
         params["wte"] = np.concatenate([params["wte"], pad_row], axis=0)
         cfg.n_vocab_rows = params["wte"].shape[0]
     return params, cfg
+
+
+def save_head_params(path: str, head: Dict) -> None:
+    """An MLPHead (``{'dense1': ..., 'dense2': ...}``) or LinearHead (``{'dense': ...}``) parameter dict -> ``.npz``."""
+    flat = {}
+    for layer, p in head.items():
+        flat[layer + ".kernel"] = np.asarray(p["kernel"], np.float32)
+        if p.get("bias") is not None:
+            flat[layer + ".bias"] = np.asarray(p["bias"], np.float32)
+    np.savez(path, **flat)
+
+
+def load_head_params(model_load_mode, model_load_path: str, cfg: GPT2Config, kind: str = "mlp", seed: int = 0, n_out: int = None) -> Dict:
+    """What the value-RL drivers call where the reference calls ``LLM_RL.heads.{mlp,linear}_head.load_params`` (eval_ilql_gpt2.py:92-110,
+    eval_mc_gpt2.py:93-101).  CONFIG: seeded init with the training scripts' head configs — MLPHead(d, d, vocab, layer2_bias_init=-4.4)
+    (train_ilql_gpt2.py:224-231) or LinearHead(d, vocab, initializer_range=0.0, bias_init=-4.4)-style (train_mc_returns_gpt2.py:198-206);
+    PARAMS: an ``.npz`` written by ``save_head_params``."""
+    from .gpt2 import init_mlp_head_params
+    mode = ModelLoadMode(model_load_mode) if not isinstance(model_load_mode, ModelLoadMode) else model_load_mode
+    n_out = n_out or cfg.n_vocab_rows
+    if mode is ModelLoadMode.PARAMS:
+        z = np.load(model_load_path)
+        layers = sorted({k.split(".")[0] for k in z.files})
+        return {l: dict(kernel=z[l + ".kernel"], bias=z[l + ".bias"] if l + ".bias" in z.files else None) for l in layers}
+    if mode is not ModelLoadMode.CONFIG:
+        raise ValueError("heads load from 'config' (seeded init) or 'params' (.npz)")
+    if kind == "mlp":
+        return init_mlp_head_params(cfg, seed=seed, n_out=n_out)
+    rng = np.random.default_rng(seed)
+    return dict(dense=dict(kernel=(rng.standard_normal((cfg.d_model, n_out)) / np.sqrt(cfg.d_model)).astype(np.float32),
+                           bias=np.full(n_out, -4.4, np.float32)))

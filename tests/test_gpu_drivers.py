@@ -89,3 +89,27 @@ def test_ppo_training_driver(tmp_path):
     hist2 = drv.main("config", cfg, "none", "wordle_official.txt", n_rounds=1, n_rollouts=8, rollout_bsize=8, train_bsize=4, max_input_length=128,
                      max_output_length=6, max_steps=1, seed=0)
     assert hist2[0]["updates"] == 1 and abs(hist2[0]["loss"]) < hist[0]["loss"]
+
+
+@pytest.mark.parametrize("algorithm", ["ilql", "mc"])
+def test_value_rl_driver(tmp_path, algorithm):
+    """ILQL (two MLP Q heads) and MC returns (one LinearHead Q head) evaluation drivers: reproducible under --seed, weights from files
+    (``params`` mode) give the same rollouts as the in-memory ones they were saved from."""
+    drv = _load("eval_value_rl_wordle")
+    cfg_path = _tiny_config(tmp_path)
+    kw = dict(algorithm=algorithm, policy_n_rollouts=8, policy_bsize=8, policy_max_input_length=128, policy_max_output_length=6, seed=0,
+              policy_beta=4.0, print_episodes=0)
+    a = drv.main("config", cfg_path, "config", cfg_path, "wordle_official.txt", **kw)["generation_metrics"]
+    assert set(a) == {"reward", "done", "length"} and a["done"]["mean"] == 1.0
+    from lmrl_gym_b200.load import load_head_params, load_params, save_head_params, save_params
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    base, cfg = load_params("config", cfg_path, seed=1)
+    save_params(str(d / "base.npz"), base, cfg)
+    if algorithm == "ilql":
+        save_head_params(str(d / "q1_head.npz"), load_head_params("config", "", cfg, kind="mlp", seed=2))
+        save_head_params(str(d / "q2_head.npz"), load_head_params("config", "", cfg, kind="mlp", seed=3))
+    else:
+        save_head_params(str(d / "q_head.npz"), load_head_params("config", "", cfg, kind="linear", seed=2))
+    b = drv.main("params", str(d), "config", cfg_path, "wordle_official.txt", **kw)["generation_metrics"]
+    assert a == b
