@@ -27,7 +27,7 @@ def __getattr__(name):
     if name in ("B200GPT2Policy", "B200GPT2ValuePolicy", "GPT2Config", "init_gpt2_params", "init_mlp_head_params"):
         from . import gpt2
         return getattr(gpt2, name)
-    lazy = {"B200TextNavEnv": "textnav", "B200PPOInference": "ppo", "AdaptiveKLController": "ppo", "FixedKLController": "ppo", "PPOData": "ppo",
+    lazy = {"B200TextNavEnv": "textnav", "B200PPOInference": "ppo", "AdaptiveKLController": "ppo", "FixedKLController": "ppo", "PPOData": "ppo", "PPODataset": "ppo", "PPOIterableDataset": "ppo", "BlockingStrategy": "ppo", "Padding": "ppo", "Truncation": "ppo",
             "B200PPOTrain": "ppo_train", "ppo_train_loop": "ppo_train", "B200ValueRLInference": "value_inference", "B200ILQLInference": "value_inference",
             "ReRankerPolicy": "reranker", "ReRankerSamplePolicy": "reranker", "build_bc_score_fn": "reranker", "build_ilql_score_fn": "reranker",
             "build_mc_score_fn": "reranker", "FenChessHistoryEnv": "chess_env", "BatchedFenChessHistoryEnv": "chess_env", "ChessEnv": "chess_env",

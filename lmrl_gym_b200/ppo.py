@@ -18,6 +18,7 @@ Not built: the gradient step (PPOTrain.step: backward pass, AdamW, NCCL gradient
 """
 from __future__ import annotations
 
+import enum
 from dataclasses import dataclass
 from typing import Callable, Dict, List, NamedTuple, Optional, Sequence, Tuple, Union
 
@@ -108,6 +109,39 @@ except Exception:
             return chain
 
 
+class Padding(enum.Enum):
+    LEFT = "left"
+    RIGHT = "right"
+
+
+class Truncation(enum.Enum):
+    LEFT = "left"
+    RIGHT = "right"
+
+
+class BlockingStrategy(NamedTuple):
+    """JaxSeq.utils.BlockingStrategy as the reference uses it (e.g. train_ppo_gpt2.py:356: ``BlockingStrategy(Padding.RIGHT,
+    Truncation.RIGHT, max_length)``); JaxSeq is not vendored, the three fields and the two enums are its published surface."""
+    padding: Padding
+    truncation: Truncation
+    max_length: Optional[int]
+
+
+def block_sequences(sequences: Sequence[Sequence], pad_value, dtype, blocking_strategy: BlockingStrategy) -> np.ndarray:
+    """``[n, max_length]`` (the longest sequence when max_length is None): each sequence truncated, then padded, on the given sides."""
+    T = blocking_strategy.max_length if blocking_strategy.max_length is not None else max((len(s) for s in sequences), default=0)
+    out = np.full((len(sequences), T), pad_value, dtype=dtype)
+    for i, s in enumerate(sequences):
+        s = np.asarray(s)
+        if len(s) > T:
+            s = s[len(s) - T:] if blocking_strategy.truncation == Truncation.LEFT else s[:T]
+        if blocking_strategy.padding == Padding.LEFT:
+            out[i, T - len(s):] = s
+        else:
+            out[i, :len(s)] = s
+    return out
+
+
 class PPOData(NamedTuple):
     input_ids: np.ndarray            # [t]
     should_take_action: np.ndarray   # [t-1]
@@ -115,6 +149,61 @@ class PPOData(NamedTuple):
     old_values: np.ndarray           # [t-1]
     old_advantages: np.ndarray       # [t-1]
     old_returns: np.ndarray          # [t-1]
+
+    @staticmethod
+    def block(data: List["PPOData"], blocking_strategy: BlockingStrategy, tokenizer) -> Dict[str, np.ndarray]:
+        """ppo/data.py:17-60: ids blocked to max_length with the pad id, the five per-output arrays to max_length - 1 with False / 0."""
+        shorter = blocking_strategy._replace(max_length=None if blocking_strategy.max_length is None else blocking_strategy.max_length - 1)
+        out = dict(input_ids=block_sequences([d.input_ids for d in data], tokenizer.pad_token_id, np.int32, blocking_strategy),
+                   should_take_action=block_sequences([d.should_take_action for d in data], False, np.bool_, shorter))
+        for k in ("old_logprobs", "old_values", "old_advantages", "old_returns"):
+            out[k] = block_sequences([getattr(d, k) for d in data], 0.0, np.float32, shorter)
+        return out
+
+
+_PPO_FIELDS = (("input_ids", np.int32), ("should_take_action", np.bool_), ("old_logprobs", np.float32), ("old_values", np.float32),
+               ("old_advantages", np.float32), ("old_returns", np.float32))
+
+
+class PPODataset:
+    """ppo/data.py:62-113: the blocked arrays of one collection round, indexable by minibatch (``dataset[idxs]`` -> dict of arrays — host
+    numpy here, where the reference converts to jnp; ``B200PPOTrain.step`` takes that dict)."""
+
+    def __init__(self, input_ids, should_take_action, old_logprobs, old_values, old_advantages, old_returns):
+        arrays = dict(input_ids=input_ids, should_take_action=should_take_action, old_logprobs=old_logprobs, old_values=old_values,
+                      old_advantages=old_advantages, old_returns=old_returns)
+        for k, a in arrays.items():
+            assert a.shape[0] == input_ids.shape[0] and a.shape[1] == input_ids.shape[1] - (k != "input_ids"), k
+        self.__dict__.update(arrays)
+
+    def __getitem__(self, index) -> Dict[str, np.ndarray]:
+        return {k: np.asarray(getattr(self, k)[index], dtype=dt) for k, dt in _PPO_FIELDS}
+
+    def __len__(self) -> int:
+        return self.input_ids.shape[0]
+
+    @classmethod
+    def from_ppo_data_list(cls, ppo_data_list: List[PPOData], tokenizer, blocking_strategy: BlockingStrategy) -> "PPODataset":
+        return cls(**PPOData.block(ppo_data_list, blocking_strategy, tokenizer))
+
+
+class PPOIterableDataset:
+    """ppo/data.py:130-158: a stream of single blocked items."""
+
+    def __init__(self, ppo_data):
+        self.ppo_data = ppo_data
+
+    def __iter__(self):
+        for item in self.ppo_data:
+            yield {k: np.asarray(item[k], dtype=dt) for k, dt in _PPO_FIELDS}
+
+    @classmethod
+    def from_ppo_data_iterable(cls, ppo_data, tokenizer, blocking_strategy: BlockingStrategy) -> "PPOIterableDataset":
+        class _Blocked:
+            def __iter__(self):
+                for item in ppo_data:
+                    yield {k: v[0] for k, v in PPOData.block([item], blocking_strategy, tokenizer).items()}
+        return cls(_Blocked())
 
 
 class CombinedTokenTrajectoryChain(NamedTuple):

@@ -205,10 +205,46 @@ def gen_ppo():
                 note="logits[b,t,:] = tab[tok[b,t]] * (1 + 0.01 t); values[b,t] = vtab[tok[b,t]] + 0.02 t")
 
 
+def gen_blocking():
+    """``PPOData.block`` / ``PPODataset`` / ``PPOIterableDataset`` of the reference (ppo/data.py:9-158) on ragged seeded items under the
+    four padding x truncation strategies.  JaxSeq's ``block_sequences`` underneath is the restatement in ref_shims (JaxSeq is not vendored);
+    what this pins is the reference's composition: pad values, the max_length - 1 rule, dtypes, dataset indexing."""
+    from LLM_RL.algorithms.ppo.data import PPOData, PPODataset, PPOIterableDataset
+    from JaxSeq.utils import BlockingStrategy, Padding, Truncation
+    rng = np.random.default_rng(11)
+    items = []
+    for n in (5, 9, 2, 12, 7, 8):
+        f = lambda: rng.standard_normal(n - 1).astype(np.float32)  # noqa: E731
+        items.append(PPOData(rng.integers(0, PAD, n).astype(np.int32), rng.random(n - 1) < 0.5, f(), f(), f(), f()))
+    tok = ToyTokenizer()
+    cases = []
+    for pad in (Padding.RIGHT, Padding.LEFT):
+        for trunc in (Truncation.RIGHT, Truncation.LEFT):
+            for max_length in (8, 16):
+                bs = BlockingStrategy(pad, trunc, max_length)
+                blocked = PPOData.block(items, bs, tok)
+                ds = PPODataset.from_ppo_data_list(items, tok, bs)
+                it, src = [], iter(PPOIterableDataset.from_ppo_data_iterable(items, tok, bs))     # the reference's iterator has __next__ only
+                while True:
+                    try:
+                        it.append(next(src))
+                    except StopIteration:
+                        break
+                cases.append(dict(padding=pad.name, truncation=trunc.name, max_length=max_length,
+                                  blocked={k: fl(np.asarray(v)) for k, v in blocked.items()}, dtypes={k: str(np.asarray(v).dtype) for k, v in blocked.items()},
+                                  dataset_len=len(ds), dataset_rows_1_3={k: fl(np.asarray(v)) for k, v in ds[np.asarray([1, 3])].items()},
+                                  iterable_item_4={k: fl(np.asarray(v)) for k, v in it[4].items()}, iterable_len=len(it)))
+    return dict(pad=PAD, items=[{k: fl(getattr(d, k)) for k in d._fields} for d in items], cases=cases)
+
+
 def main():
+    import sys
     ref_shims.install()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("score_fns", gen_score_fns), ("ppo_data", gen_ppo)):
+    only = set(sys.argv[1:])
+    for name, fn in (("score_fns", gen_score_fns), ("ppo_data", gen_ppo), ("ppo_blocking", gen_blocking)):
+        if only and name not in only:
+            continue
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(fn(), f, separators=(",", ":"))
         print("wrote", name, os.path.getsize(os.path.join(OUT, name + ".json")), "bytes")

@@ -174,7 +174,14 @@ def install() -> None:
     jax.nn = _module("jax.nn", log_softmax=log_softmax)
     jax.lax = _module("jax.lax", stop_gradient=lambda x: x)
     jax.random = _module("jax.random", split=lambda k, n=2: (None,) * n, PRNGKeyArray=Any, PRNGKey=lambda s: None)
-    jax.tree_util = _module("jax.tree_util", tree_map=lambda f, *t: None)
+    def tree_map(f, tree, *rest):        # dicts / lists / tuples of leaves: all the reference's data code maps over
+        if isinstance(tree, dict):
+            return {k: tree_map(f, v, *[r[k] for r in rest]) for k, v in tree.items()}
+        if isinstance(tree, (list, tuple)) and not hasattr(tree, "_fields"):
+            return type(tree)(tree_map(f, v, *[r[i] for r in rest]) for i, v in enumerate(tree))
+        return f(tree, *rest)
+
+    jax.tree_util = _module("jax.tree_util", tree_map=tree_map)
     jax.experimental = _module("jax.experimental")
     jax.experimental.pjit = _module("jax.experimental.pjit", pjit=_identity_decorator)
     jax.sharding = _module("jax.sharding", NamedSharding=object, PartitionSpec=object, Mesh=object)

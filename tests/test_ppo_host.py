@@ -129,3 +129,46 @@ def test_ppo_data_host_logic_equals_oracle_on_random_chains(seed):
         assert d.input_ids.tolist() == o.input_ids.tolist() and np.asarray(d.should_take_action).tolist() == o.should_take_action.tolist()
         for k in ("old_logprobs", "old_values", "old_advantages", "old_returns"):
             np.testing.assert_allclose(getattr(d, k), getattr(o, k), rtol=2e-6, atol=2e-6, err_msg=k)
+
+
+def test_ppo_data_blocking_and_datasets_match_reference(golden_dir):
+    """``PPOData.block`` / ``PPODataset`` / ``PPOIterableDataset`` (ppo/data.py:9-158) against the reference's own code run on the same
+    items (tests/golden/ppo_blocking.json, oracle/gen_golden_algos.py::gen_blocking): values, shapes and dtypes for the four
+    padding x truncation strategies."""
+    import json
+    import os
+    from lmrl_gym_b200 import ppo as P
+    g = json.load(open(os.path.join(golden_dir, "ppo_blocking.json")))
+
+    class Tok:
+        pad_token_id = g["pad"]
+    dt = dict(input_ids=np.int32, should_take_action=np.bool_, old_logprobs=np.float32, old_values=np.float32, old_advantages=np.float32,
+              old_returns=np.float32)
+    items = [P.PPOData(**{k: np.asarray(v, dtype=dt[k]) for k, v in it.items()}) for it in g["items"]]
+    assert len(g["cases"]) == 8
+    for case in g["cases"]:
+        bs = P.BlockingStrategy(P.Padding[case["padding"]], P.Truncation[case["truncation"]], case["max_length"])
+        blocked = P.PPOData.block(items, bs, Tok())
+        for k, want in case["blocked"].items():
+            want = np.asarray(want)
+            assert blocked[k].shape == want.shape and str(blocked[k].dtype) == case["dtypes"][k], (k, blocked[k].dtype)
+            np.testing.assert_allclose(blocked[k].astype(np.float64), want.astype(np.float64), rtol=0, atol=1e-9)
+        ds = P.PPODataset.from_ppo_data_list(items, Tok(), bs)
+        assert len(ds) == case["dataset_len"]
+        rows = ds[np.asarray([1, 3])]
+        for k, want in case["dataset_rows_1_3"].items():
+            np.testing.assert_allclose(rows[k].astype(np.float64), np.asarray(want, dtype=np.float64), rtol=0, atol=1e-9)
+            assert rows[k].dtype == dt[k]
+        stream = list(P.PPOIterableDataset.from_ppo_data_iterable(items, Tok(), bs))
+        assert len(stream) == case["iterable_len"]
+        for k, want in case["iterable_item_4"].items():
+            np.testing.assert_allclose(stream[4][k].astype(np.float64), np.asarray(want, dtype=np.float64), rtol=0, atol=1e-9)
+    # the trainer's own blocking (RIGHT / RIGHT) is the same function
+    from lmrl_gym_b200.ppo_train import block_ppo_data
+    mine = block_ppo_data(items, g["pad"], 8)
+    ref = P.PPOData.block(items, P.BlockingStrategy(P.Padding.RIGHT, P.Truncation.RIGHT, 8), Tok())
+    for k in ref:
+        np.testing.assert_array_equal(mine[k], ref[k])
+    # max_length None: the longest sequence
+    free = P.PPOData.block(items, P.BlockingStrategy(P.Padding.LEFT, P.Truncation.LEFT, None), Tok())
+    assert free["input_ids"].shape == (6, 12) and free["old_values"].shape == (6, 11)
