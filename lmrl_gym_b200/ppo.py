@@ -343,6 +343,22 @@ class B200PPOInference:
         ini = forward_tokens(self._lmrl_engine, 1, 0, seqs, logprobs=True, pitch=pitch)["logprobs"][:, :t - 1] if self.has_initial_policy else None
         return PPOForwardOutput(ini, pol["logprobs"][:, :t - 1], pol["v"][:, :t])
 
+    @staticmethod
+    def token_logprobs_from_logits(logits: np.ndarray, input_ids: np.ndarray) -> np.ndarray:
+        """ppo/base_interface.py:397-403 for callers that hold logits ``[b, t, V]`` (the engine itself never materialises them)."""
+        x = np.asarray(logits, dtype=np.float32)[:, :-1]
+        m = x.max(axis=-1, keepdims=True)
+        lse = np.log(np.exp(x - m).sum(axis=-1)) + m[..., 0]
+        return (np.take_along_axis(x, np.asarray(input_ids)[:, 1:, None], axis=-1)[..., 0] - lse).astype(np.float32)
+
+    def forward_from_str(self, input_strs: List[str], blocking_strategy: BlockingStrategy = BlockingStrategy(Padding.RIGHT, Truncation.RIGHT, None),
+                         token_process: Optional[Callable[[List[int]], List[int]]] = None) -> PPOForwardOutput:
+        """ppo/base_interface.py:437-462: encode every string on its own, block, forward.  The device forward takes RIGHT-padded rows."""
+        assert blocking_strategy.padding == Padding.RIGHT, "the device forward takes RIGHT-padded rows (sequences start at position 0)"
+        token_process = token_process or (lambda x: x)
+        tokens = [token_process(list(self.tokenizer.encode(item))) for item in input_strs]
+        return self.forward(block_sequences(tokens, self.pad_token_id, np.int32, blocking_strategy))
+
     def get_ppo_data_from_token_trajectory_chain(self, token_trajectory_chains: List[TokenTrajectoryChain], bsize: int, max_length: Optional[int] = None,
                                                  train: bool = False, prng_key=None, verbose: bool = True, *, gamma: float, lam: float, kl_weight: float,
                                                  use_advantage_whitening: bool = True, use_new_advantage_whitening: bool = False,
@@ -402,12 +418,28 @@ class B200PPOInference:
         chains = [TokenTrajectoryChain.from_text_trajectory_chain(c, self.tokenizer, token_process=token_process) for c in text_trajectory_chains]
         return self.get_ppo_data_from_token_trajectory_chain(chains, bsize=bsize, max_length=max_length, train=train, prng_key=prng_key, verbose=verbose, **kw)
 
+    get_ppo_data_from_text_trajectory_chain_iterble = get_ppo_data_from_text_trajectory_chain      # the reference's second name for it (:710-745)
+
     def eval_loss(self, input_ids, should_take_action, old_logprobs, old_values, old_advantages, old_returns, *, cliprange_value: float = 0.2,
-                  cliprange: float = 0.2, value_loss_coef: float = 1.0) -> Tuple[float, Dict[str, float]]:
-        """``PPOInference.eval_loss`` (:718-760) without the optional BC term: forward the current policy, then ``ppo_loss_fn`` with
-        ``values = forward.values[:, :-1]`` and ``attention_mask = (input_ids != pad)[:, 1:]`` (ppo/gpt2/interface.py loss_fn wiring)."""
+                  cliprange: float = 0.2, value_loss_coef: float = 1.0, bc_data_input_ids=None, bc_data_input_training_mask=None,
+                  bc_loss_weight: float = 0.0) -> Tuple[float, Dict[str, float]]:
+        """``PPOInference.eval_loss`` (:747-820; ppo/gpt2/interface.py:381-470): forward the current policy, then ``ppo_loss_fn`` with
+        ``values = forward.values[:, :-1]`` and ``attention_mask = (input_ids != pad)[:, 1:]``.  With a BC batch the masked next-token
+        cross-entropy is added as ``loss + bc_loss * bc_loss_weight`` and the logs become ``{'ppo': ..., 'bc': {'loss': ...}, 'total_loss': ...}``
+        (:451-464)."""
         input_ids = np.asarray(input_ids)
         o = self.forward(input_ids)
         mask = (input_ids != self.pad_token_id)[:, 1:].astype(np.float32)
-        return ppo_loss(self._lmrl_engine, mask, o.policy_logprobs, o.values[:, :-1], should_take_action, old_logprobs, old_values, old_advantages,
-                        old_returns, cliprange_value=cliprange_value, cliprange=cliprange, value_loss_coef=value_loss_coef)
+        loss, logs = ppo_loss(self._lmrl_engine, mask, o.policy_logprobs, o.values[:, :-1], should_take_action, old_logprobs, old_values, old_advantages,
+                              old_returns, cliprange_value=cliprange_value, cliprange=cliprange, value_loss_coef=value_loss_coef)
+        if bc_data_input_ids is None:
+            return loss, logs
+        bc_ids = np.asarray(bc_data_input_ids)
+        real = bc_ids != self.pad_token_id
+        lens = real.sum(axis=1)
+        lp = forward_tokens(self._lmrl_engine, 0, 0, [bc_ids[i, :lens[i]] for i in range(bc_ids.shape[0])], logprobs=True,
+                            pitch=max(8, bc_ids.shape[1]))["logprobs"][:, :bc_ids.shape[1] - 1]
+        m = np.asarray(bc_data_input_training_mask, dtype=np.float64)[:, 1:] * real[:, 1:]
+        bc = float(-(lp.astype(np.float64) * m).sum() / m.sum())
+        total = float(loss) + bc * float(bc_loss_weight)
+        return total, dict(ppo=logs, bc=dict(loss=bc), total_loss=total)

@@ -164,6 +164,49 @@ def test_ppo_inference_end_to_end_against_oracle(eng):
     assert abs(logs["policy_loss"] + adv_mean) < 1e-5
 
 
+def test_ppo_inference_forward_from_str_and_bc_eval_loss(eng):
+    """forward_from_str (ppo/base_interface.py:437-462) == forward of the separately encoded, RIGHT-blocked strings, checked against the
+    oracle's log-probs; eval_loss with a BC batch adds bc_loss * bc_loss_weight and nests the logs (:451-464)."""
+    from lmrl_gym_b200.ppo_train import bc_batch_from_str_segments
+    from oracle import gpt2 as og
+    cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024)
+    tok = eng.tokenizer
+    pol = init_gpt2_params(cfg, seed=60)
+    lin = dict(dense=dict(kernel=(np.random.default_rng(4).standard_normal((cfg.d_model, 1)) / 16).astype(np.float32), bias=np.asarray([0.2], np.float32)))
+    inf = P.B200PPOInference(eng, pol, lin, initial_policy_params=pol, config=cfg, pad_token_id=tok.pad_token_id)
+    strs = ["Wordle:\nc r a n e\nb y b b g\n", "Wordle:\n", "Wordle:\ns l a t e\n"]
+    out = inf.forward_from_str(strs)
+    T = max(len(tok.encode(x)) for x in strs)
+    assert out.policy_logprobs.shape == (3, T - 1) and out.values.shape == (3, T)
+    for i, x in enumerate(strs):
+        ids = list(tok.encode(x))
+        lp = og.token_logprobs_all(pol, ids, cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+        assert np.abs(out.policy_logprobs[i, :len(ids) - 1] - lp).max() <= 3e-2
+        assert (out.policy_logprobs[i, len(ids) - 1:] == 0).all() and (out.values[i, len(ids):] == 0).all()
+    np.testing.assert_array_equal(out.initial_policy_logprobs, out.policy_logprobs)         # same weights in both towers
+    cut = inf.forward_from_str(strs, P.BlockingStrategy(P.Padding.RIGHT, P.Truncation.LEFT, 6), token_process=lambda t: t[:-1])
+    assert cut.values.shape == (3, 6)
+    with pytest.raises(AssertionError):
+        inf.forward_from_str(strs, P.BlockingStrategy(P.Padding.LEFT, P.Truncation.LEFT, 8))
+    # eval_loss with the BC term
+    ids = P.block_sequences([tok.encode(x) for x in strs], tok.pad_token_id, np.int32, P.BlockingStrategy(P.Padding.RIGHT, P.Truncation.RIGHT, T))
+    sta = np.zeros((3, T - 1), bool)
+    sta[0, 3:9] = sta[2, 3:] = True
+    zeros = np.zeros((3, T - 1), np.float32)
+    args = (ids, sta, out.policy_logprobs, out.values[:, :-1], zeros + 0.5, zeros)
+    base_loss, base_logs = inf.eval_loss(*args)
+    bc = bc_batch_from_str_segments([[("Wordle:\n", 0.0), ("c r a n e\n", 1.0)], [("Wordle:\n", 0.0), ("a b\n", 1.0)]], tok, 16, tok.pad_token_id)
+    total, logs = inf.eval_loss(*args, bc_data_input_ids=bc["input_ids"], bc_data_input_training_mask=bc["input_training_mask"], bc_loss_weight=2.0)
+    want = 0.0
+    for row, m in zip(bc["input_ids"], bc["input_training_mask"]):
+        n = int((row != tok.pad_token_id).sum())
+        want -= float((og.token_logprobs_all(pol, row[:n].tolist(), cfg.n_head, cfg.n_vocab, emulate_bf16=True) * m[1:n]).sum())
+    want /= float(bc["input_training_mask"][:, 1:].sum())
+    assert abs(logs["bc"]["loss"] - want) <= 3e-2 and abs(total - (base_loss + 2.0 * logs["bc"]["loss"])) <= 1e-5
+    assert logs["total_loss"] == total and abs(logs["ppo"]["policy_loss"] - base_logs["policy_loss"]) <= 1e-6
+    assert inf.get_ppo_data_from_text_trajectory_chain_iterble.__func__ is inf.get_ppo_data_from_text_trajectory_chain.__func__
+
+
 def test_ppo_data_throughput_vs_cpu_port():
     """Measurement, not parity: the same PPO collection pass (GPT-2-small, Wordle-shaped chains) through B200PPOInference and through
     the CPU port (torch-CPU GPT-2 oracle + oracle/ppo.py on all host threads, bounded sample).  Printed for DESIGN.md; the only
