@@ -146,27 +146,30 @@ def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict, tower: int = 0
     check(engine.lib.lmrl_load_gpt2_tower(engine.handle, int(tower), C.byref(dims), C.byref(w)))
 
 
+def head_struct(q: Optional[Dict], keep: list):
+    """flax head params -> ``lmrl_mlp_head`` (None stays None): an MLPHead ``{'dense1': {'kernel','bias'}, 'dense2': {...}}``
+    (heads/mlp_head.py:99-148) or a LinearHead ``{'dense': {'kernel','bias'-or-None}}`` (heads/linear_head.py:91-119: w1 / b1 stay NULL, the
+    kernel travels in w2).  ``keep`` receives every object whose memory the struct points into."""
+    if q is None:
+        return None
+    h = _lib.lmrl_mlp_head()
+    if "dense" in q:
+        fields = (("w2", q["dense"]["kernel"]),) + ((("b2", q["dense"]["bias"]),) if q["dense"].get("bias") is not None else ())
+        h.hidden, h.n_out = int(np.shape(q["dense"]["kernel"])[0]), int(np.shape(q["dense"]["kernel"])[1])
+    else:
+        fields = (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"]))
+        h.hidden, h.n_out = int(np.shape(q["dense1"]["kernel"])[1]), int(np.shape(q["dense2"]["kernel"])[1])
+    for name, a in fields:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a)
+        setattr(h, name, a.ctypes.data_as(_lib._PF))
+    keep.append(h)
+    return h
+
+
 def _upload_q_heads(engine: Engine, q1: Dict, q2: Optional[Dict], beta: float):
-    keep = []
-
-    def head(q):
-        if q is None:
-            return None
-        h = _lib.lmrl_mlp_head()
-        if "dense" in q:            # LinearHead (heads/linear_head.py:112-119; the MC-returns drivers' Q head): w1 / b1 stay NULL
-            fields = (("w2", q["dense"]["kernel"]),) + ((("b2", q["dense"]["bias"]),) if q["dense"].get("bias") is not None else ())
-            h.hidden, h.n_out = int(q["dense"]["kernel"].shape[0]), int(q["dense"]["kernel"].shape[1])
-        else:
-            fields = (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"]))
-            h.hidden, h.n_out = int(q["dense1"]["kernel"].shape[1]), int(q["dense2"]["kernel"].shape[1])
-        for name, a in fields:
-            a = np.ascontiguousarray(a, dtype=np.float32)
-            keep.append(a)
-            setattr(h, name, a.ctypes.data_as(_lib._PF))
-        keep.append(h)
-        return h
-
-    h1, h2 = head(q1), head(q2)
+    keep: list = []
+    h1, h2 = head_struct(q1, keep), head_struct(q2, keep)
     check(engine.lib.lmrl_load_q_heads(engine.handle, C.byref(h1), None if h2 is None else C.byref(h2), float(beta)))
 
 

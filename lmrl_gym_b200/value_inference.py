@@ -21,25 +21,7 @@ import numpy as np
 from . import _lib
 from ._lib import check, ptr
 from .engine import Engine
-from .gpt2 import GPT2Config, _upload_params
-
-
-def _mlp_struct(q: Optional[Dict], keep: list):
-    if q is None:
-        return None
-    h = _lib.lmrl_mlp_head()
-    if "dense" in q:                # LinearHead Q head (heads/linear_head.py:112-119; MC returns): w1 / b1 stay NULL
-        fields = (("w2", q["dense"]["kernel"]),) + ((("b2", q["dense"]["bias"]),) if q["dense"].get("bias") is not None else ())
-        h.hidden, h.n_out = int(q["dense"]["kernel"].shape[0]), int(q["dense"]["kernel"].shape[1])
-    else:
-        fields = (("w1", q["dense1"]["kernel"]), ("b1", q["dense1"]["bias"]), ("w2", q["dense2"]["kernel"]), ("b2", q["dense2"]["bias"]))
-        h.hidden, h.n_out = int(q["dense1"]["kernel"].shape[1]), int(q["dense2"]["kernel"].shape[1])
-    for name, a in fields:
-        a = np.ascontiguousarray(a, dtype=np.float32)
-        keep.append(a)
-        setattr(h, name, a.ctypes.data_as(_lib._PF))
-    keep.append(h)
-    return h
+from .gpt2 import GPT2Config, _upload_params, head_struct
 
 
 def upload_value_heads(engine: Engine, head_set: int, q1: Optional[Dict] = None, q2: Optional[Dict] = None, v: Optional[Dict] = None,
@@ -50,7 +32,7 @@ def upload_value_heads(engine: Engine, head_set: int, q1: Optional[Dict] = None,
     keep: list = []
     hs = _lib.lmrl_value_heads()
     for name, q in (("q1", q1), ("q2", q2), ("v", v)):
-        s = _mlp_struct(q, keep)
+        s = head_struct(q, keep)
         if s is not None:
             setattr(hs, name, C.pointer(s))
     if v_linear is not None:

@@ -147,3 +147,25 @@ def test_product_never_imports_the_oracle():
         uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
         if uses:
             assert fn.name in ("run_reference", "cpu_reference_numbers"), fn.name
+
+
+def test_head_struct_for_mlp_and_linear_heads():
+    """The one place flax head params become the ABI's lmrl_mlp_head: MLPHead fills w1/b1/w2/b2, LinearHead only w2 (+ b2)."""
+    import ctypes as C
+    import numpy as np
+    from lmrl_gym_b200.gpt2 import GPT2Config, head_struct, init_mlp_head_params
+    cfg = GPT2Config(n_layer=1, n_head=2, d_model=32, d_ff=64, n_vocab=100, n_vocab_rows=101, n_pos=16)
+    keep = []
+    assert head_struct(None, keep) is None and keep == []
+    mlp = init_mlp_head_params(cfg, seed=1)
+    h = head_struct(mlp, keep)
+    assert (h.hidden, h.n_out) == (32, 101) and all(bool(getattr(h, f)) for f in ("w1", "b1", "w2", "b2"))
+    assert np.ctypeslib.as_array(h.w2, shape=(32, 101))[3, 7] == mlp["dense2"]["kernel"][3, 7] and h.b2[5] == np.float32(-4.4)
+    v = init_mlp_head_params(cfg, seed=2, n_out=1)
+    assert head_struct(v, keep).n_out == 1
+    k = np.arange(32 * 101, dtype=np.float64).reshape(32, 101)                 # a non-float32 source is converted, and kept alive
+    lin = head_struct(dict(dense=dict(kernel=k, bias=np.ones(101))), keep)
+    assert (lin.hidden, lin.n_out) == (32, 101) and not lin.w1 and not lin.b1 and lin.w2[101 + 2] == 103.0 and lin.b2[0] == 1.0
+    nob = head_struct(dict(dense=dict(kernel=k, bias=None)), keep)
+    assert not nob.b2 and bool(nob.w2)
+    assert sum(isinstance(x, np.ndarray) for x in keep) == 4 + 4 + 2 + 1
