@@ -122,3 +122,30 @@ def test_value_forward_gathered_equals_full_heads():
     np.testing.assert_allclose(lv, (h @ torch.from_numpy(lin["dense"]["kernel"]))[:, 0].numpy() + 0.25, rtol=1e-4, atol=1e-5)
     lp = og.token_logprobs_all(base, toks, cfg.n_head, cfg.n_vocab)
     assert lp.shape == (12,) and (lp < 0).all()
+
+
+def test_linear_q_head_restatement():
+    """MC returns: the Q head is a LinearHead (heads/linear_head.py:112-119: q = dense(h)); logits = pi_beta + beta * (h W + b)
+    (generation.py:112-119 with q2 None), and the gathered per-position form equals the gather of the full head output."""
+    cfg = GPT2Config(n_layer=1, n_head=2, d_model=64, d_ff=128, n_vocab=97, n_vocab_rows=98, n_pos=16)
+    pi, base = init_gpt2_params(cfg, seed=1), init_gpt2_params(cfg, seed=2)
+    rng = np.random.default_rng(3)
+    W, b = (rng.standard_normal((64, 98)) / 8).astype(np.float32), rng.standard_normal(98).astype(np.float32)
+    q, q_nobias = dict(dense=dict(kernel=W, bias=b)), dict(dense=dict(kernel=W, bias=None))
+    toks = [5, 9, 2, 77, 30]
+    pi_logits = og.forward_last_logits(pi, toks, cfg.n_head, cfg.n_vocab, weights_bf16=False)
+    h = og.forward_hidden(base, toks, cfg.n_head, weights_bf16=False).numpy()
+    want_q = h[-1] @ W + b
+    got = og.value_policy_last_logits((pi, base, q, None), toks, cfg.n_head, cfg.n_vocab, 16.0, weights_bf16=False)
+    assert np.allclose(got, pi_logits + 16.0 * want_q[:cfg.n_vocab], atol=2e-4)
+    no_pi = og.value_policy_last_logits((None, base, q_nobias, None), toks, cfg.n_head, cfg.n_vocab, 2.0, weights_bf16=False)
+    assert np.allclose(no_pi, 2.0 * (h[-1] @ W)[:cfg.n_vocab], atol=2e-4)
+    two = og.value_policy_last_logits((pi, base, q, q_nobias), toks, cfg.n_head, cfg.n_vocab, 4.0, weights_bf16=False)
+    assert np.allclose(two, pi_logits + 4.0 * np.minimum(want_q, h[-1] @ W)[:cfg.n_vocab], atol=2e-4)
+    # the engine-emulating variant (beta folded into the bf16 kernel) is the same function up to rounding
+    emu = og.value_policy_last_logits((pi, base, q, None), toks, cfg.n_head, cfg.n_vocab, 4.0, emulate_bf16=True)
+    assert np.abs(emu - og.value_policy_last_logits((pi, base, q, None), toks, cfg.n_head, cfg.n_vocab, 4.0)).max() < 0.2
+    g = og.value_forward_gathered(base, q, q_nobias, None, toks, cfg.n_head, weights_bf16=False)
+    full = h @ W
+    np.testing.assert_allclose(g["q1"], (full + b)[np.arange(4), toks[1:]], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(g["q2"], full[np.arange(4), toks[1:]], rtol=1e-5, atol=1e-5)
