@@ -6,7 +6,8 @@ vendored, so the file formats here are this repository's own).
                           reference's CONFIG mode: architecture from a config, fresh weights)
 ``ModelLoadMode.HF``      path = a LOCAL directory ``transformers.GPT2LMHeadModel.from_pretrained`` can read (torch weights; there is
                           no network here, so hub names only work from a warm cache)
-``ModelLoadMode.PARAMS``  path = an ``.npz`` written by ``save_params`` (fp32 arrays, flattened keys)
+``ModelLoadMode.PARAMS``  path = an ``.npz`` written by ``save_params`` (fp32 arrays, flattened keys), or a DIRECTORY holding the reference's own
+                          ``params.msgpack`` / ``train_state.msgpack`` + ``config.json`` (``flax_checkpoint.py``: format restated, unpinned)
 """
 from __future__ import annotations
 
@@ -49,7 +50,10 @@ def load_params(model_load_mode: ModelLoadMode, model_load_path: str, seed: int 
             with open(model_load_path) as f:
                 cfg = GPT2Config(**json.load(f))
         return init_gpt2_params(cfg, seed=seed), cfg
-    if mode is ModelLoadMode.PARAMS:
+    if mode is ModelLoadMode.PARAMS and os.path.isdir(model_load_path):
+        from .flax_checkpoint import load_reference_checkpoint
+        params, cfg = load_reference_checkpoint(model_load_path)
+    elif mode is ModelLoadMode.PARAMS:
         z = np.load(model_load_path)
         cfg = GPT2Config(**json.loads(bytes(z["config_json"]).decode()))
         layers = [{k: z[f"h{l}.{k}"] for k in _LAYER_KEYS} for l in range(cfg.n_layer)]
@@ -88,6 +92,10 @@ def load_head_params(model_load_mode, model_load_path: str, cfg: GPT2Config, kin
     from .gpt2 import init_mlp_head_params
     mode = ModelLoadMode(model_load_mode) if not isinstance(model_load_mode, ModelLoadMode) else model_load_mode
     n_out = n_out or cfg.n_vocab_rows
+    if mode is ModelLoadMode.PARAMS and (os.path.isdir(model_load_path) or model_load_path.endswith(".msgpack")):
+        from .flax_checkpoint import head_params_from_flax_tree, read_msgpack_tree
+        path = model_load_path if model_load_path.endswith(".msgpack") else os.path.join(model_load_path, "params.msgpack")
+        return head_params_from_flax_tree(read_msgpack_tree(path))
     if mode is ModelLoadMode.PARAMS:
         z = np.load(model_load_path)
         layers = sorted({k.split(".")[0] for k in z.files})
