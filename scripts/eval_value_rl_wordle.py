@@ -7,8 +7,9 @@ Same positional arguments and flags; ``--algorithm ilql|mc`` selects the head la
     python scripts/eval_value_rl_wordle.py config gpt2 config gpt2 wordle_official.txt --algorithm mc --policy-n-rollouts 4096 \
         --policy-bsize 4096 --policy-max-output-length 6
 
-In ``config`` mode the paths name architectures (random init), in ``params`` mode ``<model_load_path>/base.npz``, ``q1_head.npz``, ...
-(written by ``lmrl_gym_b200.load.save_params`` / ``save_head_params``).
+In ``config`` mode the paths name architectures (random init); in ``params`` mode ``<model_load_path>/base``, ``q1_head``, ... are either
+the reference's checkpoint directories (``params.msgpack`` [+ ``config.json``]) or ``.npz`` files written by ``lmrl_gym_b200.load.save_params``
+/ ``save_head_params``.
 """
 import os
 from typing import Optional
@@ -61,7 +62,11 @@ def main(
     rank, world, device = D.init_from_env()
     tokenizer = load_tokenizer(tokenizer_path)
     from_files = ModelLoadMode(model_load_mode) is ModelLoadMode.PARAMS
-    sub = (lambda name: os.path.join(model_load_path, name + ".npz")) if from_files else (lambda name: model_load_path)
+    def sub(name):               # the reference's layout <path>/<name>/params.msgpack (eval_ilql_gpt2.py:78-110), or this repo's <path>/<name>.npz
+        if not from_files:
+            return model_load_path
+        d = os.path.join(model_load_path, name)
+        return d if os.path.isdir(d) else d + ".npz"
     pi_beta, cfg = load_params(pi_beta_load_mode, pi_beta_load_path, seed=0, force_pad_embeddings=force_pad_embeddings)
     base, base_cfg = load_params(model_load_mode, sub("base"), seed=1, force_pad_embeddings=force_pad_embeddings)
     assert (base_cfg.n_layer, base_cfg.d_model, base_cfg.n_head) == (cfg.n_layer, cfg.d_model, cfg.n_head), "pi_beta and the value base share one architecture"
