@@ -129,3 +129,41 @@ def load_reference_checkpoint(model_dir: str) -> Tuple[Dict, GPT2Config]:
     if not os.path.exists(path):
         path = os.path.join(model_dir, "train_state.msgpack")
     return gpt2_params_from_flax_tree(read_msgpack_tree(path), cfg), cfg
+
+
+def _ext(a) -> Any:
+    import msgpack
+    a = np.ascontiguousarray(a)
+    return msgpack.ExtType(1, msgpack.packb((a.shape, a.dtype.name, a.tobytes()), use_bin_type=True))
+
+
+def flax_tree_from_gpt2_params(params: Dict) -> Dict:
+    """The inverse of ``gpt2_params_from_flax_tree``: numpy leaves, Conv1D kernels back in FlaxConv1D's ``[features, in]`` layout."""
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+    kT = lambda a: f32(np.asarray(a).T)  # noqa: E731
+    h = {}
+    for i, L in enumerate(params["layers"]):
+        h[str(i)] = dict(ln_1=dict(scale=f32(L["ln1_g"]), bias=f32(L["ln1_b"])), ln_2=dict(scale=f32(L["ln2_g"]), bias=f32(L["ln2_b"])),
+                         attn=dict(c_attn=dict(kernel=kT(L["attn_w"]), bias=f32(L["attn_b"])), c_proj=dict(kernel=kT(L["proj_w"]), bias=f32(L["proj_b"]))),
+                         mlp=dict(c_fc=dict(kernel=kT(L["fc_w"]), bias=f32(L["fc_b"])), c_proj=dict(kernel=kT(L["fc2_w"]), bias=f32(L["fc2_b"]))))
+    return dict(transformer=dict(wte=dict(embedding=f32(params["wte"])), wpe=dict(embedding=f32(params["wpe"])), h=h,
+                                 ln_f=dict(scale=f32(params["lnf_g"]), bias=f32(params["lnf_b"]))))
+
+
+def write_msgpack_tree(path: str, tree: Dict) -> None:
+    """One msgpack document of the nested state dict, leaves as ext type 1 (the ``flax.serialization.msgpack_serialize`` shape)."""
+    import msgpack
+
+    def enc(x):
+        return {k: enc(v) for k, v in x.items()} if isinstance(x, dict) else _ext(x)
+    with open(path, "wb") as f:
+        f.write(msgpack.packb(enc(tree), use_bin_type=True))
+
+
+def save_reference_checkpoint(model_dir: str, params: Dict, cfg: GPT2Config) -> None:
+    """``<model_dir>/params.msgpack`` + ``<model_dir>/config.json`` in the layout ``dump_state`` writes (ppo/train.py:28-85)."""
+    os.makedirs(model_dir, exist_ok=True)
+    write_msgpack_tree(os.path.join(model_dir, "params.msgpack"), flax_tree_from_gpt2_params(params))
+    with open(os.path.join(model_dir, "config.json"), "w") as f:
+        json.dump(dict(model_type="gpt2", n_layer=cfg.n_layer, n_head=cfg.n_head, n_embd=cfg.d_model, n_inner=cfg.d_ff, vocab_size=cfg.n_vocab_rows,
+                       n_positions=cfg.n_pos, layer_norm_epsilon=cfg.ln_eps, activation_function="gelu_new"), f)

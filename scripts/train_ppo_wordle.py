@@ -92,6 +92,7 @@ def main(
     from lmrl_gym_b200 import distributed as D, ppo as P, ppo_train as T
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from lmrl_gym_b200.flax_checkpoint import save_reference_checkpoint
     from lmrl_gym_b200.load import load_params, save_params
     from lmrl_gym_b200.randomness import seed_generator
     from lmrl_gym_b200.wordle import B200WordleEnv
@@ -139,6 +140,7 @@ def main(
             json.dump([to_floats({k: v for k, v in h.items() if v is not None}) for h in history], f)
         if save_at_end:
             save_params(os.path.join(outputs_path, "policy_params.npz"), trainer.params_numpy(), cfg)
+            save_reference_checkpoint(os.path.join(outputs_path, "policy"), trainer.params_numpy(), cfg)      # the reference's layout too (policy/params.msgpack + config.json)
             np.savez(os.path.join(outputs_path, "value_head.npz"), kernel=trainer.vh_w.detach().cpu().numpy(), bias=trainer.vh_b.detach().cpu().numpy())
     engine.close()
     D.finalize()
