@@ -7,7 +7,7 @@ env or policy loads ``csrc/liblmrl_b200.so`` and raises ``LmrlError`` if it is m
 from .environment import (  # noqa: F401
     Text, TextHistory, TextTrajectory, TextTrajectoryChain, TextEnv, BatchedTextEnv, TextPolicy, BatchedTextPolicy,
     TextEnvToBatchedTextEnv, BatchedTextEnvToTextEnv, TextPolicyToBatchedTextPolicy, BatchedTextPolicyToTextPolicy,
-    InteractionTransition, interact_environment, text_env_eval, text_history_to_str, summarize_episodes,
+    InteractionTransition, interact_environment, text_env_eval, text_history_to_str, summarize_episodes, UserPolicy,
 )
 from .tokenizer import ByteTokenizer  # noqa: F401
 from .randomness import seed_generator  # noqa: F401

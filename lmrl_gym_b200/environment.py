@@ -185,6 +185,24 @@ class BatchedTextPolicyToTextPolicy(TextPolicy):
         return self.policy.act([text_history])[0]
 
 
+class UserPolicy(TextPolicy):
+    """A human at the keyboard as the policy (LLM_RL/environment.py:271-288): prints the history, reads one line, returns the history plus
+    ``initial_str + line`` as the action.  The reference appends with ``text_history+[Text(...)]`` — a TypeError on the tuple histories the
+    loop passes; here the action is appended as a tuple."""
+
+    def __init__(self, initial_str: str, postproc_print_f: Optional[Callable[[str], str]] = None, postproc_action_f: Optional[Callable[[str], str]] = None):
+        self.initial_str = initial_str
+        self.postproc_print_f = postproc_print_f if postproc_print_f is not None else (lambda x: x)
+        self.postproc_action_f = postproc_action_f if postproc_action_f is not None else (lambda x: x)
+
+    def act(self, text_history):
+        print("=" * 25)
+        print(self.postproc_print_f(text_history_to_str(text_history)))
+        print("=" * 25)
+        response = self.initial_str + input(self.initial_str)
+        return tuple(text_history) + (Text(self.postproc_action_f(response), True),)
+
+
 # --- the rollout loop -------------------------------------------------------------------------------------
 
 def _fused_pair(env, policy):

@@ -169,3 +169,13 @@ def test_head_struct_for_mlp_and_linear_heads():
     nob = head_struct(dict(dense=dict(kernel=k, bias=None)), keep)
     assert not nob.b2 and bool(nob.w2)
     assert sum(isinstance(x, np.ndarray) for x in keep) == 4 + 4 + 2 + 1
+
+
+def test_user_policy_reads_one_line(monkeypatch, capsys):
+    from lmrl_gym_b200 import Text, UserPolicy
+    pol = UserPolicy("move ", postproc_print_f=lambda s: s.upper(), postproc_action_f=lambda s: s + "\n")
+    monkeypatch.setattr("builtins.input", lambda prompt: "left")
+    hist = (Text("There is a wall above you.\n", False),)
+    out = pol.act(hist)
+    assert out == hist + (Text("move left\n", True),)
+    assert "THERE IS A WALL ABOVE YOU." in capsys.readouterr().out
