@@ -131,3 +131,53 @@ def test_maze_core_matches_reference_goldens(hc, golden_dir):
         for k, st in enumerate(case["steps"]):
             assert float(reward[k]) == st["reward"] and bool(done[k]) == st["done"]
             assert pos[k].tolist() == st["position"]
+
+
+@pytest.mark.parametrize("vocab,episodes", [("10k_words", 40), ("large_words", 5), ("wordle_official_guess", 5), ("wordle_official_400", 40)])
+def test_wordle_core_randomised_against_oracle(hc, vocab, episodes):
+    """csrc/env_core.h (the code the device kernels run) against the reference-pinned Python oracle on the vocabularies the goldens do
+    not cover, with a mixture of smart guesses (drawn from the oracle's filtered list), random vocabulary words and malformed actions
+    (upper case, wrong length, inner whitespace, non-ASCII, Unicode whitespace padding)."""
+    from lmrl_gym_b200.vocab import load_vocab_words
+    from oracle import wordle as ow
+    words = load_vocab_words(vocab)
+    packed = load_packed(vocab)
+    rng = random.Random(sum(vocab.encode()) + 7)
+    sym = {"g": 0, "y": 1, "b": 2}
+    hc.hc_wordle_episode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64] + [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 6
+    bad = ["CRANE", "cran", "cranes", "cr\tne", "", "c r a n e s", "crané", "12345", "\n", "zzzzz"]
+    for ep in range(episodes):
+        require, bwr, seed = rng.random() < 0.8, rng.choice([-1.0, -10.0, 0.0]), rng.randrange(2 ** 62)
+        o = ow.WordleOracle(words, require, bwr)
+        o.reset(seed)
+        actions, want = [], []
+        while True:
+            u = rng.random()
+            if u < 0.55:
+                w = rng.choice(o.filtered)
+            elif u < 0.8:
+                w = rng.choice(words)
+            else:
+                w = rng.choice(bad)
+            text = " ".join(w) + "\n" if rng.random() < 0.7 else rng.choice(["", " ", " ", "\t"]) + w + rng.choice(["", "\n", " \n"])
+            fb, r, done = o.step(ow.normalise_action(text))
+            actions.append(text.encode("utf-8"))
+            want.append((fb, float(r), done, len(o.filtered), o.target if fb != "" else None))
+            if done:
+                break
+        blob = b"".join(actions)
+        buf = np.frombuffer(blob, np.uint8).copy() if blob else np.zeros(1, np.uint8)
+        lens = np.asarray([len(a) for a in actions], np.int32)
+        n = len(actions)
+        reward = np.zeros(n, np.float32); done_a = np.zeros(n, np.uint8); valid = np.zeros(n, np.uint8)
+        fb_a = np.zeros((n, 5), np.uint8); nf = np.zeros(n, np.int32); tg = np.zeros(n, np.uint32)
+        steps = hc.hc_wordle_episode(_p(packed), len(packed), int(require), bwr, seed, _p(buf), _p(lens), n, _p(reward), _p(done_a), _p(valid),
+                                     _p(fb_a), _p(nf), _p(tg))
+        assert steps == n, (vocab, ep, actions)
+        for k, (fb, r, done, n_f, target) in enumerate(want):
+            ctx = (vocab, ep, k, actions[k])
+            assert float(reward[k]) == r and bool(done_a[k]) == done and int(nf[k]) == n_f, ctx
+            assert [int(c) for c in fb_a[k] if c < 3] == [sym[c] for c in fb.replace("<", "").replace(">", "")], ctx
+            assert bool(valid[k]) == (fb != ""), ctx
+            if target is not None:                       # the word sampled from the filtered list BEFORE the feedback (game.py:219)
+                assert unpack_word(int(tg[k])) == target, ctx
