@@ -181,3 +181,50 @@ def test_wordle_core_randomised_against_oracle(hc, vocab, episodes):
             assert bool(valid[k]) == (fb != ""), ctx
             if target is not None:                       # the word sampled from the filtered list BEFORE the feedback (game.py:219)
                 assert unpack_word(int(tg[k])) == target, ctx
+
+
+@pytest.mark.parametrize("maze_name", ["double_t_maze", "umaze"])
+def test_maze_core_randomised_against_oracle(hc, maze_name):
+    """csrc/env_core.h Maze reset / step against the reference-pinned oracle: every reward function, random seeds (goal draw + start draw
+    of env.py:193-202) or an init_position option, random legal / blocked / unknown actions, step limits down to 3."""
+    from oracle import maze as om
+    hc.hc_maze_episode.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                                 C.c_int] + [C.c_void_p] * 5
+    grid = maze_grid(maze_name)
+    H, W = grid.shape
+    gy, gx = GOALS[maze_name]
+    rng = random.Random(len(maze_name))
+    moves = ["move left\n", "move right\n", "move up\n", "move down\n"]
+    junk = ["jump\n", "move left", "", "Move up\n", "move  down\n", "move up\n\n", "move north\n"]
+    for ep in range(200):
+        reward_function = rng.choice(list(REWARDS))
+        max_steps = rng.choice([3, 7, 25, 100])
+        o = om.MazeOracle(maze_name, "describe_observation_give_position", reward_function, last_k=1, max_steps=max_steps)
+        seed = rng.randrange(2 ** 62)
+        options = None
+        if rng.random() < 0.4:
+            free = [c for c in o.free_cells() if c != [gy, gx]]
+            options = {"init_position": tuple(rng.choice(free))}
+        hist = o.reset(seed, options)
+        start0 = list(o.position)
+        actions, want = [], []
+        while True:
+            a = rng.choice(moves) if rng.random() < 0.85 else rng.choice(junk)
+            hist, r, done = o.step(tuple(hist) + ((a, True),))
+            actions.append(a.encode())
+            want.append((float(r), done, list(o.position)))
+            if done:
+                break
+        blob = b"".join(actions)
+        buf = np.frombuffer(blob, np.uint8).copy() if blob else np.zeros(1, np.uint8)
+        lens = np.asarray([len(a) for a in actions], np.int32)
+        n = len(actions)
+        start = np.zeros(2, np.int32); reward = np.zeros(n, np.float32); done_a = np.zeros(n, np.uint8)
+        outcome = np.zeros(n, np.int32); pos = np.zeros((n, 2), np.int32)
+        oy, ox = options["init_position"] if options else (-1, -1)
+        rw = np.asarray(REWARDS[reward_function], np.float32)
+        steps = hc.hc_maze_episode(_p(np.ascontiguousarray(grid)), H, W, gy, gx, max_steps, _p(rw), seed, oy, ox, _p(buf), _p(lens), n,
+                                   _p(start), _p(reward), _p(done_a), _p(outcome), _p(pos))
+        assert steps == n and start.tolist() == start0, (maze_name, ep)
+        for k, (r, done, p) in enumerate(want):
+            assert float(reward[k]) == r and bool(done_a[k]) == done and pos[k].tolist() == p, (maze_name, ep, k, actions[k])
