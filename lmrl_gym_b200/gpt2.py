@@ -10,6 +10,7 @@ env on the same ``Engine`` the whole loop is fused on the GPU instead (lmrl_gym_
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Tuple, Callable, Dict, List, Optional
 
@@ -197,6 +198,8 @@ class B200GPT2Policy(BatchedTextPolicy):
         self.out_str_process = out_str_process
         self._calls = 0
         _upload_params(engine, self.config, params)
+        if os.environ.get("LMRL_NO_GRAPHS") == "1":        # debugging aid (compute-sanitizer racecheck, ncu): eager launches instead of graph replay
+            engine.set_use_graphs(False)
 
     @property
     def fusable(self) -> bool:
