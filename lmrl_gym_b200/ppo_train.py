@@ -319,6 +319,52 @@ class B200PPOTrain:
             self.push_to_engine()           # the next forward / backward (and the next rollout) run on the updated weights
         return float(loss), {k: float(v) for k, v in logs.items()}
 
+    def bc_step(self, bc_batch: Dict[str, np.ndarray]) -> float:
+        """One optimizer step on the BC loss alone (masked next-token cross-entropy; what the reference's BC drivers minimise,
+        wordle/bc/train_bc_gpt2.py with JaxSeq's ``loss_fn_mask``): same gradient paths, all-reduce and AdamW as ``step``; the value head
+        gets a zero gradient.  Returns the loss."""
+        torch = self.torch
+        if self.backward == "b200":
+            for g in self.gflat:
+                g.zero_()
+            w, self.bc_loss_weight = self.bc_loss_weight, 1.0          # _b200_bc_grads scales dL/dlogprob by the weight
+            try:
+                loss = self._b200_bc_grads(bc_batch)
+            finally:
+                self.bc_loss_weight = w
+            for f, g in zip(self.flat, self.gflat):
+                f.grad = g
+        else:
+            for f in self.flat:
+                f.grad = None
+            out = self.bc_loss(bc_batch)
+            out.backward()
+            loss = float(out.detach())
+            for f in self.flat:                                        # parameters the loss does not reach (the value head)
+                if f.grad is None:
+                    f.grad = torch.zeros_like(f.data)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            world = torch.distributed.get_world_size()
+            for f in self.flat:
+                torch.distributed.all_reduce(f.grad)
+        self.steps += 1
+        if self.use_device_adamw:
+            e = self._lmrl_engine
+            torch.cuda.synchronize(self.device)
+            for grp, f in enumerate(self.flat):
+                check(e.lib.lmrl_adamw_dev(e.handle, f.data.data_ptr(), f.grad.data_ptr(), self.m[grp].data_ptr(), self.v[grp].data_ptr(), f.numel(),
+                                           self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay if grp == 0 else 0.0, self.steps, 1.0 / world))
+            e.sync()
+        else:
+            if world > 1:
+                for f in self.flat:
+                    f.grad /= world
+            self.opt.step()
+        if self.backward == "b200":
+            self.push_to_engine()
+        return float(loss)
+
     def _grad_view(self, name):
         grp, o, shape = self._views[name]
         return self.gflat[grp][o:o + int(np.prod(shape))]

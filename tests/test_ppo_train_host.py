@@ -208,3 +208,16 @@ def test_bc_batch_from_str_segments():
     short = T.bc_batch_from_str_segments(items[:1], tok, 8, tok.pad_token_id)
     full = sum((list(tok.encode(s)) for s, _ in items[0]), [])
     assert short["input_ids"][0].tolist() == full[-8:]
+
+
+def test_bc_step_lowers_the_bc_loss():
+    """``bc_step``: AdamW on the masked cross-entropy alone — the loss of a fixed batch falls, the value head does not move."""
+    rng = np.random.default_rng(9)
+    bc = make_bc_batch(rng, b=6)
+    tr, _, _ = make_trainer(lr=3e-3)
+    vh0 = tr.vh_w.detach().clone()
+    losses = [tr.bc_step(bc) for _ in range(8)]
+    assert losses[-1] < losses[0] - 0.05 and all(np.isfinite(losses))
+    assert abs(losses[0] - float(tr.__class__.bc_loss(make_trainer()[0], bc))) < 1e-5        # the first loss is the untouched model's
+    assert torch.equal(tr.vh_w.detach(), vh0)
+    assert tr.steps == 8
