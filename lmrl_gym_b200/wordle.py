@@ -157,3 +157,22 @@ class B200WordleEnv(BatchedTextEnv):
 
     def copy(self):
         return self  # device state is per-slot already; TextEnvToBatchedTextEnv-style deep copies are not needed
+
+
+def scripted_rollout_records(act_words: np.ndarray, feedback: np.ndarray, step_reward: np.ndarray, ep_len: np.ndarray, ep_done: np.ndarray) -> List[Dict]:
+    """Logs of a scripted (``RandomMixturePolicy``-equivalent) device rollout — ``lmrl_wordle_scripted_rollout_dev``: packed action words
+    ``[n, T]``, feedback codes ``[n, T, 5]`` (0 g, 1 y, 2 b), per-step rewards ``[n, T]``, episode lengths and done flags — as the records
+    the reference's data generator writes (wordle/misc/data_gen.py:52-61 over ``PolicyDataGenerator``, wordle/env/data.py:23-34):
+    ``sequence`` = ``[(text, float(is_action)), ...]`` of the reformatted final history (env.py:7-17), ``reward`` = ``[r_0, 0.0, r_1, 0.0, ...]``,
+    ``done``.  These are the ``bc_data_path`` items of the PPO / BC drivers (``bc_batch_from_str_segments``)."""
+    from .vocab import unpack_word
+    out = []
+    for i in range(len(ep_len)):
+        seq, rew = [(HEADER, 0.0)], []
+        for t in range(int(ep_len[i])):
+            word = unpack_word(int(act_words[i, t]) & 0xFFFFFFFF)
+            seq.append((" ".join(word) + "\n", 1.0))
+            seq.append((" ".join("gyb"[int(c)] for c in feedback[i, t]) + "\n", 0.0))
+            rew += [float(step_reward[i, t]), 0.0]
+        out.append(dict(sequence=seq, reward=rew, done=bool(ep_done[i])))
+    return out

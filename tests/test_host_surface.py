@@ -179,3 +179,32 @@ def test_user_policy_reads_one_line(monkeypatch, capsys):
     out = pol.act(hist)
     assert out == hist + (Text("move left\n", True),)
     assert "THERE IS A WALL ABOVE YOU." in capsys.readouterr().out
+
+
+def test_scripted_rollout_records_have_the_data_generator_format(golden_dir):
+    """Device scripted-rollout logs -> the reference data generator's records (wordle/misc/data_gen.py:52-61), checked on golden episodes
+    whose actions are all legal words: ``sequence`` must be the reformatted final history with is_action as the mask."""
+    import json
+    import os
+    import numpy as np
+    from lmrl_gym_b200.vocab import pack_word
+    from lmrl_gym_b200.wordle import normalise_action, scripted_rollout_records
+    cases = json.load(open(os.path.join(golden_dir, "wordle_cases.json")))
+    sym = {"g": 0, "y": 1, "b": 2}
+    picked = [c for c in cases if all(s["obs"][-1][0] != "\n" for s in c["steps"])][:12]
+    assert len(picked) >= 6
+    T = 6
+    n = len(picked)
+    act, fb, rew = np.zeros((n, T), np.int64), np.zeros((n, T, 5), np.uint8), np.zeros((n, T), np.float32)
+    ep_len, ep_done = np.zeros(n, np.int32), np.zeros(n, np.uint8)
+    for i, c in enumerate(picked):
+        ep_len[i], ep_done[i] = len(c["steps"]), c["steps"][-1]["done"]
+        for t, s in enumerate(c["steps"]):
+            act[i, t] = pack_word(normalise_action(c["actions"][t]))
+            fb[i, t] = [sym[x] for x in s["obs"][-1][0].strip().split(" ")]
+            rew[i, t] = s["reward"]
+    recs = scripted_rollout_records(act, fb, rew, ep_len, ep_done)
+    for c, r in zip(picked, recs):
+        assert [[t, bool(m)] for t, m in r["sequence"]] == c["steps"][-1]["obs"]
+        assert r["reward"] == sum(([float(s["reward"]), 0.0] for s in c["steps"]), []) and r["done"] == c["steps"][-1]["done"]
+        assert len(r["reward"]) == len(r["sequence"]) - 1
