@@ -99,6 +99,9 @@ def traffic(path, out_path):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) < 3 or sys.argv[1] in ("-h", "--help"):
+        print(__doc__)
+        sys.exit(0 if len(sys.argv) > 1 and sys.argv[1] in ("-h", "--help") else 2)
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
     elif sys.argv[1] == "traffic":
