@@ -336,6 +336,17 @@ int lmrl_set_two_lanes(lmrl_engine* e, int32_t enable);
  * CTAs are scheduled and run their prologue behind the tail of the previous kernel, then wait for its completion before touching
  * global memory */
 int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
+/* named integer switches of the policy engine (A/B measurement and cross-checks; every value gives identical results up to the
+ * documented float tolerance):
+ *   "fuse_ln"        1 (default) LayerNorm fused into the residual GEMMs (the CTA completing an m-tile normalises its rows),
+ *                    0 separate layernorm_kernel launches
+ *   "attn_wide"      1 (default) prefill attention takes 32 query rows per warp pass (K / V streamed once for slots of <= 32 new rows),
+ *                    0 16-row passes
+ *   "gemv_max_rows"  decode passes of batches with at most this many envs run the weight-streaming GEMV kernels instead of
+ *                    128-row tensor-core tiles (default 8; 0 disables)
+ * Unknown names fail.  Changing a switch drops the captured rollout graph. */
+int lmrl_set_option(lmrl_engine* e, const char* name, int32_t value);
+int lmrl_get_option(lmrl_engine* e, const char* name, int32_t* value);
 
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);

@@ -133,6 +133,8 @@ SYMBOLS = {
     "lmrl_set_use_graphs": (C.c_int, [_V, _I]),
     "lmrl_set_two_lanes": (C.c_int, [_V, _I]),
     "lmrl_set_use_pdl": (C.c_int, [_V, _I]),
+    "lmrl_set_option": (C.c_int, [_V, C.c_char_p, _I]),
+    "lmrl_get_option": (C.c_int, [_V, C.c_char_p, _V]),
     "lmrl_launch_count": (C.c_int64, [_V, _I]),
     "lmrl_set_gemm_impl": (C.c_int, [_V, _I]),
     "lmrl_test_gemm_host": (C.c_int, [_V, _I, _I, _I, _I, _V, _V, _V, _V]),

@@ -62,6 +62,14 @@ struct GemmArgs {
     float* lp_tlogit;            // [rows] logit/T of the target
     int out_col0;                // EPI_RELU / EPI_GELU: column offset of the output box inside the tmOut tensor
     float out_scale;             // EPI_RELU: out = out_scale * relu(acc + bias)
+    // EPI_RESID + fused LayerNorm (tcgen05 one-CTA kernel): the CTA whose tile completes an m-tile of the residual stream (every
+    // N tile of those 128 rows has been reduce-added: per-m-tile arrival counter) normalises the 128 finished rows and writes the
+    // bf16 operand of the next GEMM, so the decoder stack launches no LayerNorm kernels.  ln_out == nullptr: plain EPI_RESID.
+    const float* ln_gamma;       // [N]
+    const float* ln_beta;        // [N]
+    __nv_bfloat16* ln_out;       // [M, N] bf16
+    int* ln_cnt;                 // [ceil(Mcap / 128)] arrival counters, zero between launches
+    float ln_eps;
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 3, GEMM_THREADS = 256;

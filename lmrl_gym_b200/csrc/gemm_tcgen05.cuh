@@ -39,7 +39,8 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;          // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int TC_EPI_BUF = 32 * 128;                   // one staged box: 32 rows x 128 bytes (128B-swizzled, TMA store source)
 constexpr int TC_EPI_BYTES = 8 * TC_EPI_BUF;           // one staging box per epilogue warp
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/;
+constexpr int TC_BIAS_BYTES = 256 * 4;                 // the tile's bias values, staged once per tile by the epilogue warps
+constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + TC_EPI_BYTES + TC_BIAS_BYTES + 256 /*barriers*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
 // per tile width BN (256 by default; 192 for the N = 768 GEMMs of a decode pass: 4 x 32 = 128 tiles fill 148 SMs in one wave of
 // 3/4-size tiles where 256-wide tiles give 96 full-size ones)
@@ -47,7 +48,8 @@ template <int BN> struct TcTile {
     static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "tile width: a multiple of 64 up to 256 (2 x BN TMEM columns)");
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * STAGE_BYTES + TC_EPI_BYTES + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * STAGE_BYTES + TC_EPI_BYTES + TC_BIAS_BYTES + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "shared memory of one CTA (227 KB)");
     // kind::f16 instruction descriptor: fp32 accumulate, bf16 A and B, both K-major, N = BN, M = 128
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 };
@@ -103,7 +105,8 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t r[32]) {
+// issue only: the destination registers are valid after the next tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld_32x32b_x32_issue(uint32_t taddr, uint32_t r[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -112,7 +115,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t r[32
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t r[32]) {
+    tmem_ld_32x32b_x32_issue(taddr, r);
+    tmem_ld_wait();
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -135,13 +142,29 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 // ---- storing epilogues of one 128 x BN accumulator (shared by the 1-CTA and the 2-CTA kernel) ------------------------
-// t_addr: TMEM address of this warp's lane quadrant; m0 / n0: origin of the CTA's tile; [c_beg, c_end): this warp's columns of
-// the tile; stg: this warp's staging box (32 rows x 128 bytes, 128B-swizzled).  The box is single buffered: TMEM load, bias and
-// activation happen in registers first, then the warp waits for the TMA engine to have read the previous box and refills it.
+// t_addr: TMEM address of this warp's lane quadrant; m0 / n0: origin of the CTA's tile; c_beg: first of this warp's BN / 2 columns
+// of the tile; stg: this warp's staging box (32 rows x 128 bytes, 128B-swizzled).  The TMEM loads are software pipelined: the
+// tcgen05.ld of 32-column chunk c + 1 is in flight while chunk c gets its bias / activation / packing (round 1 issued the wait
+// right behind every load: 30 % of the kernel's stall samples).  The staging box is single buffered: the warp waits for the TMA
+// engine to have read the previous box only when it is about to refill it.  sbias != 0: shared-memory address of the tile's BN
+// bias values (staged once per tile by the kernel); sbias == 0: bias read from global memory (the 2-CTA kernel).
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 tc_bias4(const GemmArgs& g, uint32_t sbias, int n0, int c) {      // bias of tile columns c .. c + 3
+    if (sbias) return ld_shared_f4(sbias + 4u * (uint32_t)c);
+    return __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c));
+}
+
 template <int EPI, int BN = TC_BN>
 __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorMap& tmOut, uint32_t t_addr, int M, int m0, int n0, int quad,
-                                              int lane, uint32_t stg, int c_beg, int c_end) {
+                                              int lane, uint32_t stg, int c_beg, uint32_t sbias) {
+    constexpr int NCH = BN / 64;                                                   // 32-column chunks per warp (half a tile)
     const int row = m0 + quad * 32 + lane;                                         // this thread's output row
+    uint32_t rr[2][32];
+    tmem_ld_32x32b_x32_issue(t_addr + c_beg, rr[0]);
     if (EPI == EPI_QKV && n0 >= g.d_model) {
         // K / V tile: scatter this thread's row segment into the KV slab at (env, pos)
         const bool live = row < M;
@@ -149,16 +172,18 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
         __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
         size_t base_off = 0;
         if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
-        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_addr + c0, r);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c0 = c_beg + 32 * ci;
+            tmem_ld_wait();
+            if (ci + 1 < NCH) tmem_ld_32x32b_x32_issue(t_addr + c0 + 32, rr[(ci + 1) & 1]);
+            const uint32_t* r = rr[ci & 1];
             if (live) {
                 const int c = n0 + c0 - part * g.d_model;                  // column inside K (or V): head = c / 64
                 __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * g.t_cap * 64 + (c & 63);
-                const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
+                    const float4 b0 = tc_bias4(g, sbias, n0, c0 + 8 * j), b1 = tc_bias4(g, sbias, n0, c0 + 8 * j + 4);
                     uint4 pk;
                     pk.x = pack_bf16x2_tc(__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
                     pk.y = pack_bf16x2_tc(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
@@ -170,14 +195,16 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
         }
     } else if constexpr (EPI == EPI_RESID) {
         // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
-        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_addr + c0, r);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c0 = c_beg + 32 * ci;
+            tmem_ld_wait();
+            if (ci + 1 < NCH) tmem_ld_32x32b_x32_issue(t_addr + c0 + 32, rr[(ci + 1) & 1]);
+            uint32_t* r = rr[ci & 1];
             if (g.bias) {
-                const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(bias4 + j);
+                    const float4 b = tc_bias4(g, sbias, n0, c0 + 4 * j);
                     r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + b.x); r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + b.y);
                     r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + b.z); r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + b.w);
                 }
@@ -193,39 +220,92 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
     } else {
         // bf16 outputs (GeLU, ReLU, Q): 64-column boxes by TMA store
         static_assert(EPI == EPI_RESID || (BN / 2) % 64 == 0, "bf16 epilogues store 64-column boxes: BN / 2 must be a multiple of 64");
-        for (int c0 = c_beg; c0 < c_end; c0 += 64) {
-            uint32_t pk[32];                                               // 64 columns of this row, packed bf16
+        uint32_t pk[32];                                                   // 64 columns of this row, packed bf16
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_addr + c0 + 32 * half, r);
-                const float4* bias4 = reinterpret_cast<const float4*>(g.bias + n0 + c0 + 32 * half);
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c0 = c_beg + 32 * ci;
+            tmem_ld_wait();
+            if (ci + 1 < NCH) tmem_ld_32x32b_x32_issue(t_addr + c0 + 32, rr[(ci + 1) & 1]);
+            const uint32_t* r = rr[ci & 1];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {                              // 8 columns -> one 16-byte chunk
-                    const float4 b0 = __ldg(bias4 + 2 * j), b1 = __ldg(bias4 + 2 * j + 1);
-                    float v[8] = {__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y, __uint_as_float(r[8 * j + 2]) + b0.z,
-                                  __uint_as_float(r[8 * j + 3]) + b0.w, __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
-                                  __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
-                    if constexpr (EPI == EPI_GELU) {
+            for (int j = 0; j < 4; ++j) {                                  // 8 columns -> one 16-byte chunk
+                const float4 b0 = tc_bias4(g, sbias, n0, c0 + 8 * j), b1 = tc_bias4(g, sbias, n0, c0 + 8 * j + 4);
+                float v[8] = {__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y, __uint_as_float(r[8 * j + 2]) + b0.z,
+                              __uint_as_float(r[8 * j + 3]) + b0.w, __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
+                              __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+                if constexpr (EPI == EPI_GELU) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
-                    }
-                    if constexpr (EPI == EPI_RELU) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) v[q] = g.out_scale * fmaxf(v[q], 0.f);
-                    }
-                    const int ch = half * 4 + j;
-                    pk[4 * ch] = pack_bf16x2_tc(v[0], v[1]); pk[4 * ch + 1] = pack_bf16x2_tc(v[2], v[3]);
-                    pk[4 * ch + 2] = pack_bf16x2_tc(v[4], v[5]); pk[4 * ch + 3] = pack_bf16x2_tc(v[6], v[7]);
+                    for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
                 }
-            }
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
+                if constexpr (EPI == EPI_RELU) {
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) st_shared_v4(stg + lane * 128 + ((ch ^ (lane & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { tma_store_2d(&tmOut, stg, g.out_col0 + n0 + c0, m0 + quad * 32); bulk_commit(); }
+                    for (int q = 0; q < 8; ++q) v[q] = g.out_scale * fmaxf(v[q], 0.f);
+                }
+                const int ch = (ci & 1) * 4 + j;
+                pk[4 * ch] = pack_bf16x2_tc(v[0], v[1]); pk[4 * ch + 1] = pack_bf16x2_tc(v[2], v[3]);
+                pk[4 * ch + 2] = pack_bf16x2_tc(v[4], v[5]); pk[4 * ch + 3] = pack_bf16x2_tc(v[6], v[7]);
+            }
+            if (ci & 1) {                                                  // two chunks = one 64-column box
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) st_shared_v4(stg + lane * 128 + ((ch ^ (lane & 7)) << 4), pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { tma_store_2d(&tmOut, stg, g.out_col0 + n0 + c0 - 32, m0 + quad * 32); bulk_commit(); }
+            }
+        }
+    }
+}
+
+// LayerNorm of the 128 rows of a finished m-tile of the fp32 residual stream (EPI_RESID with GemmArgs::ln_out): the eight epilogue
+// warps take 16 rows each, two rows in flight per warp (the rows were just reduce-added by TMA: they come from L2).  Same two-pass
+// arithmetic as layernorm_kernel.
+__device__ __forceinline__ void tc_ln_rows(const GemmArgs& g, int m0, int M, int w, int lane) {
+    const int d = g.N, nv = d >> 7;                                        // float4 per lane (d % 128 == 0, d <= 1024)
+#pragma unroll 1
+    for (int i = 0; i < 16; i += 2) {
+        const int r0 = m0 + w * 16 + i;
+        if (r0 >= M) break;
+        const bool two = r0 + 1 < M;
+        float4 v[2][8];
+        float s[2] = {0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float4* src = reinterpret_cast<const float4*>(g.resid + (size_t)(r0 + (two ? k : 0)) * d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nv) { v[k][j] = __ldcg(src + lane + 32 * j); s[k] += v[k][j].x + v[k][j].y + v[k][j].z + v[k][j].w; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { s[0] += __shfl_xor_sync(0xFFFFFFFFu, s[0], o); s[1] += __shfl_xor_sync(0xFFFFFFFFu, s[1], o); }
+        const float mean[2] = {s[0] / d, s[1] / d};
+        float q[2] = {0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nv) {
+                    const float a = v[k][j].x - mean[k], b = v[k][j].y - mean[k], c = v[k][j].z - mean[k], e = v[k][j].w - mean[k];
+                    q[k] += a * a + b * b + c * c + e * e;
+                }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { q[0] += __shfl_xor_sync(0xFFFFFFFFu, q[0], o); q[1] += __shfl_xor_sync(0xFFFFFFFFu, q[1], o); }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !two) break;
+            const float rstd = rsqrtf(q[k] / d + g.ln_eps);
+            __nv_bfloat16* dst = g.ln_out + (size_t)(r0 + k) * d;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < nv) {
+                    const int c = (lane + 32 * j) * 4;
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(g.ln_beta + c));
+                    uint2 pk;
+                    pk.x = pack_bf16x2_tc((v[k][j].x - mean[k]) * rstd * g4.x + b4.x, (v[k][j].y - mean[k]) * rstd * g4.y + b4.y);
+                    pk.y = pack_bf16x2_tc((v[k][j].z - mean[k]) * rstd * g4.z + b4.z, (v[k][j].w - mean[k]) * rstd * g4.w + b4.w);
+                    *reinterpret_cast<uint2*>(dst + c) = pk;
+                }
         }
     }
 }
@@ -247,8 +327,8 @@ __device__ __forceinline__ void sample_chunk(const uint32_t r[32], int col0, flo
 }
 
 template <int EPI, int BN = TC_BN>
-// 128 registers per thread hold every epilogue without spills and leave room for an attention CTA beside the GEMM CTA on the same SM
-__global__ void __maxnreg__(128) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+// 168 registers per thread: the pipelined epilogues (two TMEM chunks in flight) and the fused LayerNorm (two rows in flight) without spills
+__global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                                    const __grid_constant__ CUtensorMap tmW,
                                                                                    const __grid_constant__ CUtensorMap tmW1,
                                                                                    const __grid_constant__ CUtensorMap tmW2,
@@ -260,13 +340,16 @@ __global__ void __maxnreg__(128) gemm_bf16_tcgen05_kernel(const __grid_constant_
     const uint32_t base = (raw + 1023u) & ~1023u;                        // 128B swizzle atoms need 1024-byte alignment
     unsigned char* base_ptr = tc_smem_raw + (base - raw);
     const uint32_t epi_base = base + TC_STAGES * TcTile<BN>::STAGE_BYTES;
-    const uint32_t bar_base = epi_base + TC_EPI_BYTES;
-    // barrier layout (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base address word
+    const uint32_t bias_base = epi_base + TC_EPI_BYTES;                  // BN floats: the current tile's bias
+    const uint32_t bar_base = bias_base + TC_BIAS_BYTES;
+    // barrier layout (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then the TMEM base address word and the
+    // "this CTA finishes the m-tile's LayerNorm" flag
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC_STAGES * TcTile<BN>::STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC_STAGES + 4));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC_STAGES * TcTile<BN>::STAGE_BYTES + TC_EPI_BYTES + TC_BIAS_BYTES + 8 * (2 * TC_STAGES + 4));
+    volatile uint32_t* ln_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_acc = g.n_acc, n_stage = n_acc == 2 ? 1 : 2;          // TMEM: 512 columns = n_stage x n_acc accumulators of 256
@@ -350,9 +433,20 @@ __global__ void __maxnreg__(128) gemm_bf16_tcgen05_kernel(const __grid_constant_
         const int quad = warp & 3;
         const uint32_t stg = epi_base + (uint32_t)(warp - 2) * TC_EPI_BUF;         // this warp's 4 KB staging box, 1024-byte aligned
         const int half = (warp - 2) >> 2;                                          // which half of the tile's columns this warp drains
+        const int et = (int)threadIdx.x - 64;                                      // thread index inside the epilogue group (256 threads)
+        constexpr bool STORING = EPI != EPI_SAMPLE && EPI != EPI_LOGPROB;
+        const uint32_t sbias = (STORING && g.bias) ? bias_base : 0u;
+        auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };      // named barrier of the eight epilogue warps
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
+            if (sbias) {
+                // the tile's bias goes to shared memory once (while the MMAs of this tile are still running) instead of
+                // every thread re-loading all BN values from global memory for its own row
+                epi_bar();                                                         // nobody still reads the previous tile's values
+                if (et < BN) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * (uint32_t)et), "f"(__ldg(g.bias + n0 + et)) : "memory");
+                epi_bar();
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * n_acc * BN);
@@ -418,12 +512,30 @@ __global__ void __maxnreg__(128) gemm_bf16_tcgen05_kernel(const __grid_constant_
                     if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
                 if (EPI == EPI_SAMPLE && live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
             } else {
-                tc_store_tile<EPI, BN>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (BN / 2), (half + 1) * (BN / 2));
+                tc_store_tile<EPI, BN>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (BN / 2), sbias);
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == n_stage) { acc = 0; acc_phase ^= 1u; }
+            if constexpr (EPI == EPI_RESID) {
+                if (g.ln_out) {
+                    // fused LayerNorm: once every N tile of these 128 rows has been reduce-added into the residual stream (arrival
+                    // counter per m-tile, device scope), the CTA that arrives last normalises the rows for the next GEMM
+                    if (lane == 0) { bulk_wait_all(); asm volatile("fence.proxy.async;" ::: "memory"); __threadfence(); }
+                    epi_bar();                                                     // all eight warps' reductions of this tile have landed
+                    if (et == 0) {
+                        int* cnt = g.ln_cnt + m0 / TC_BM;
+                        const int old = atomicAdd(cnt, 1);
+                        const uint32_t last = old + 1 == n_tiles ? 1u : 0u;
+                        if (last) *cnt = 0;                                        // ready for the next launch (same stream: ordered)
+                        __threadfence();
+                        *ln_flag = last;
+                    }
+                    epi_bar();
+                    if (*ln_flag) tc_ln_rows(g, m0, M, warp - 2, lane);
+                }
+            }
         }
         if (lane == 0) bulk_wait_all();                                            // all TMA stores / reductions have landed
     }

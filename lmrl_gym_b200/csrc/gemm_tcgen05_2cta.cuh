@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
-            tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (TC_BN / 2), (half + 1) * (TC_BN / 2));
+            tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (TC_BN / 2), 0u);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));

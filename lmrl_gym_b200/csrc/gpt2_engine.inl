@@ -77,6 +77,7 @@ struct Lane {
     uint64_t* row_key = nullptr;
     unsigned long long *best = nullptr, *best_scratch = nullptr;
     cudaStream_t st = nullptr;
+    int* ln_cnt = nullptr;    // per-m-tile arrival counters of the LayerNorm fused into the residual GEMMs
     int e0 = 0;               // first env of the lane
     size_t m_cap = 0;         // row capacity of the lane's activation buffers
     size_t xl_rows = 0;       // rows behind xl / xl1
@@ -152,6 +153,11 @@ struct Gpt2Dev {
     int64_t graph_launches = 0;
     int use_graphs = 1;
     int narrow_decode_tiles = 1;      // 128 x 192 tiles for the N = 768 residual GEMMs of decode passes
+    // LayerNorm fused into the residual GEMMs (GemmArgs::ln_out): the decoder stack launches one LayerNorm per tower pass (layer 0's
+    // ln_1) instead of two per layer.  0 = separate layernorm_kernel launches (round-1 path; also taken by the mma.sync / CTA-pair GEMMs)
+    int fuse_ln = 1;
+    int attn_wide = 1;                // prefill attention: 32 query rows per warp pass (two m16 tiles share every staged K / V block)
+    int gemv_max_rows = 8;            // batches of at most this many envs decode through the weight-streaming GEMV kernels
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
     // for this path (4096-episode Wordle rollout: 208.2 ms with graphs and no PDL, 223.8 ms with PDL; letters variant 81.0 vs 84.2)
     int use_pdl = 0;
@@ -342,6 +348,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
         else to = ta;
         if (!ta || !tw || !tw1 || !tw2 || !to) return -1;
     }
+    LMRL_CHECK(!g.ln_out || (tc && !use2), "fused LayerNorm needs the tcgen05 one-CTA GEMM (N=%d K=%d impl=%d)", g.N, g.K, G.gemm_impl);
     double k_total = 0.0;
     for (int i = 0; i < g.n_seg; ++i) k_total += (double)g.seg[i].kb_count * TC_BK;
     if (e->prof_begin(0, 2.0 * (double)n_true * k_total, count_kind, 2 * kind + e->cur_mode)) return -1;
@@ -437,9 +444,13 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     cudaStream_t st = Ln.st;
     const int ew_blocks = G.sm_count * 8;
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
+    // ln_2 of this layer rides on the attention-projection GEMM, ln_1 of the next layer on the MLP-projection GEMM (tcgen05
+    // one-CTA kernel only); layer 0's ln_1 is the one LayerNorm launch of the pass
+    const bool fuse = G.fuse_ln && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
     for (int l = 0; l < D.n_layer; ++l) {
         const LayerDev& L = T.layers[l];
-        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
+        if (!fuse || l == 0)
+            LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
         GemmArgs a{};
         a.A = Ln.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = Ln.rows.M;
         a.out = Ln.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
@@ -448,20 +459,26 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
         // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
         if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
         if (mode == 0)
-            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, std::min((n_env * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                          0.125f * 1.4426950408889634f, Ln.att));
+            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, attp_grid(n_env, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                          0.125f * 1.4426950408889634f, G.attn_wide, Ln.att));
         else
             LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
                                                                                              0.125f, Ln.att));
         GemmArgs p{};
         p.A = Ln.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = Ln.rows.M; p.resid = Ln.x;
+        if (fuse) { p.ln_gamma = L.ln2_g; p.ln_beta = L.ln2_b; p.ln_out = Ln.xn; p.ln_cnt = Ln.ln_cnt; p.ln_eps = D.ln_eps; }
         if (launch_gemm<EPI_RESID>(e, p, p.N, 0, Ln.m_cap, p.N, 1)) return -1;
-        LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
+        if (!fuse)
+            LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln2_g, L.ln2_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
         GemmArgs f{};
         f.A = Ln.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = Ln.rows.M; f.out = Ln.h;
         if (launch_gemm<EPI_GELU>(e, f, f.N, 0, Ln.m_cap, f.N, 2)) return -1;
         GemmArgs f2{};
         f2.A = Ln.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = Ln.rows.M; f2.resid = Ln.x;
+        if (fuse && l + 1 < D.n_layer) {
+            const LayerDev& Nx = T.layers[l + 1];
+            f2.ln_gamma = Nx.ln1_g; f2.ln_beta = Nx.ln1_b; f2.ln_out = Ln.xn; f2.ln_cnt = Ln.ln_cnt; f2.ln_eps = D.ln_eps;
+        }
         if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, Ln.m_cap, f2.N, 3)) return -1;
     }
     return 0;
@@ -611,6 +628,8 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     L0.x = G.x; L0.xn = G.xn; L0.q = G.q; L0.att = G.att; L0.h = G.h; L0.xl = G.xl; L0.xl1 = G.xl1; L0.rows = G.rows; L0.row_key = G.row_key;
     L0.best = G.best; L0.best_scratch = G.best_scratch; L0.st = e->stream; L0.e0 = 0; L0.m_cap = (size_t)G.m_cap; L0.xl_rows = (size_t)(B + 127) / 128 * 128;
     G.cur = &G.lane[0];
+    const size_t m_tiles = ((size_t)G.m_cap + TC_BM - 1) / TC_BM + 1;
+    if (e->alloc(&L0.ln_cnt, m_tiles) || e->alloc(&G.lane[1].ln_cnt, m_tiles) || e->alloc(&G.lane[2].ln_cnt, m_tiles)) return -1;
     if (e->alloc(&G.lane_counts, 6)) return -1;
     LMRL_CUDA(cudaStreamCreateWithFlags(&G.stream_b, cudaStreamNonBlocking));
     LMRL_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
@@ -1270,6 +1289,31 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable) {
     return 0;
 }
 
+static int* option_slot(lmrl::Gpt2Dev& G, const char* name) {
+    if (!strcmp(name, "fuse_ln")) return &G.fuse_ln;
+    if (!strcmp(name, "attn_wide")) return &G.attn_wide;
+    if (!strcmp(name, "gemv_max_rows")) return &G.gemv_max_rows;
+    return nullptr;
+}
+
+int lmrl_set_option(lmrl_engine* e, const char* name, int32_t value) {
+    LMRL_CHECK(e && e->gpt2 && name, "lmrl_set_option: no GPT-2 parameters loaded");
+    int* slot = option_slot(*e->gpt2, name);
+    LMRL_CHECK(slot, "lmrl_set_option: unknown option '%s'", name);
+    *slot = value;
+    if (e->gpt2->graph_exec) { cudaGraphExecDestroy(e->gpt2->graph_exec); e->gpt2->graph_exec = nullptr; }
+    e->gpt2->warm_valid = false;
+    return 0;
+}
+
+int lmrl_get_option(lmrl_engine* e, const char* name, int32_t* value) {
+    LMRL_CHECK(e && e->gpt2 && name && value, "lmrl_get_option: no GPT-2 parameters loaded");
+    int* slot = option_slot(*e->gpt2, name);
+    LMRL_CHECK(slot, "lmrl_get_option: unknown option '%s'", name);
+    *value = *slot;
+    return 0;
+}
+
 int lmrl_set_two_lanes(lmrl_engine* e, int32_t enable) {
     LMRL_CHECK(e && e->gpt2, "lmrl_set_two_lanes: no GPT-2 parameters loaded");
     e->gpt2->two_lanes = enable ? 1 : 0;
@@ -1465,8 +1509,8 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                 case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx); break;
                 case 5:
                     if (rpe > 1)
-                        LMRL_K(attention_prefill_kernel, std::min((n_slots * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
-                                                                                      0.125f * 1.4426950408889634f, G.att);
+                        LMRL_K(attention_prefill_kernel, attp_grid(n_slots, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                                                                                      0.125f * 1.4426950408889634f, G.attn_wide, G.att);
                     else
                         LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
                     break;

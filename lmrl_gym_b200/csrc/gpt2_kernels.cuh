@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include "gemm_mma.cuh"
 
 namespace lmrl {
@@ -372,19 +373,20 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv
 }
 
 // ---- K3 (prefill): tensor-core attention for slots that bring many rows ------------------------------------------
-// One warp per (slot, head).  16 query rows of the slot (one m16 tile) are held as mma A fragments; the (env, head)
+// One warp per (slot, head).  MT m16 tiles of query rows (16 or 32 rows of the slot) are held as mma A fragments; the (env, head)
 // K / V slabs are staged 32 keys at a time into per-warp shared memory (cp.async, 128-byte rows, XOR-swizzled 16-byte
 // chunks), double buffered so the next key block is in flight while the current one is consumed with ldmatrix (K) /
 // ldmatrix.trans (V) by mma.sync m16n8k16 with a flash-style online soft-max (fp32 running max / sum, P re-packed from
-// the S accumulators as the next A operand).  Every K / V byte is read from HBM once per slot (slots with more than 16
-// rows re-read it from L1/L2).  One m-tile instead of two keeps the kernel under 128 registers: two CTAs per SM.
-constexpr int ATTP_WARPS = 7;                                   // 7 x 16 KB of staging: two CTAs (14 warps) per SM
+// the S accumulators as the next A operand).  With 32-row passes (MT = 2, the default) every staged K / V block and every
+// ldmatrix fragment feeds both m-tiles, so a Wordle turn's ~20 new rows per episode stream the episode's K / V exactly once
+// (round 1: 16-row passes, the second one re-reading K / V through L2 — DRAM traffic 1.25x the algorithmic bytes, 0.55 of HBM).
+// Slots with more than 32 new rows take further passes; the passes that will be followed by another one ask L2 to keep the lines.
+constexpr int ATTP_WARPS = 10;                                  // 10 x 16 KB of staging, one CTA per SM (<= 204 registers per thread)
 constexpr int ATTP_KEYS = 32;                                   // keys per staged block
 constexpr int ATTP_WARP_SMEM = 2 * 2 * ATTP_KEYS * 128;        // 2 buffers x (K block + V block)
+constexpr int ATTP_CTAS_PER_SM = 1;
 
-// cp.async with an L2 eviction-priority hint: a slot with more than 16 new rows streams its K / V once per 16-row block; the blocks
-// that will be followed by another one ask L2 to keep the lines (evict_last); the final (or only) block uses the default policy
-// (measured: 24 new rows at context 72, 0.325 -> 0.293 ms; single-block slots unchanged)
+// cp.async with an L2 eviction-priority hint (see above)
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -402,14 +404,171 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(ATTP_WARPS * 32, 2) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+// one pass over the keys for query rows [rb, rb + 16 * MT) of a slot (rows beyond n are computed on zero queries and not stored)
+template <int MT>
+__device__ __forceinline__ void attp_rows(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ gK, const __nv_bfloat16* __restrict__ gV,
+                                          int r0, int n, int rb, int p0, int head, int d_model, int t_cap, float scale_log2e, bool keep,
+                                          uint64_t pol_last, uint32_t sbase, int lane, __nv_bfloat16* __restrict__ out) {
+    const int g = lane >> 2, t = lane & 3;
+    const int nr = min(16 * MT, n - rb);                   // live query rows in this pass
+    const int n_keys = p0 + rb + nr;                       // keys visible to the last live row
+    auto stage = [&](int buf, int k0) {                    // 32 keys of K and V: 2 x 256 chunks of 16 B, 16 per lane
+        const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
+            const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
+            const int kk = min(k0 + key, t_cap - 1);
+            if (keep) {
+                cp_async16_hint(sK + off, gK + (size_t)kk * 64 + ch * 8, pol_last);
+                cp_async16_hint(sV + off, gV + (size_t)kk * 64 + ch * 8, pol_last);
+            } else {
+                cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
+                cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
+            }
+        }
+        cp_async_commit();
+    };
+    __syncwarp();
+    stage(0, 0);
+    // Q fragments: qa[mt][kk][0..3]
+    uint32_t qa[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int i = rb + mt * 16 + g + hh * 8;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(q + (size_t)(r0 + i) * d_model + head * 64);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                qa[mt][kk][hh] = i < n ? __ldg(src + kk * 8 + t) : 0u;            // dims 16kk + 2t, +1
+                qa[mt][kk][hh + 2] = i < n ? __ldg(src + kk * 8 + 4 + t) : 0u;    // dims 16kk + 8 + 2t, +1
+            }
+        }
+    float o[MT][8][4];
+    float mrow[MT][2], lrow[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        mrow[mt][0] = mrow[mt][1] = -INFINITY; lrow[mt][0] = lrow[mt][1] = 0.f;
+#pragma unroll
+        for (int d8 = 0; d8 < 8; ++d8)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[mt][d8][c] = 0.f;
+    }
+    int buf = 0;
+    for (int k0 = 0; k0 < n_keys; k0 += ATTP_KEYS, buf ^= 1) {
+        if (k0 + ATTP_KEYS < n_keys) { stage(buf ^ 1, k0 + ATTP_KEYS); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();
+        const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
+        // S = Q K^T  (4 key n8-blocks); every K fragment feeds all m-tiles
+        float sacc[MT][4][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) sacc[mt][j][c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {               // two k16 steps per ldmatrix.x4
+                const int key = j * 8 + (lane & 7), ch = kp * 4 + (lane >> 3);
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(sK + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_bf16(sacc[mt][j], qa[mt][2 * kp], b0, b1);
+                    mma_bf16(sacc[mt][j], qa[mt][2 * kp + 1], b2, b3);
+                }
+            }
+        }
+        // scale, causal mask, online soft-max
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int pos = p0 + rb + mt * 16 + g + hh * 8;
+                float bm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int key = k0 + j * 8 + 2 * t + c;
+                        float v = sacc[mt][j][hh * 2 + c] * scale_log2e;
+                        v = key <= pos ? v : -INFINITY;
+                        sacc[mt][j][hh * 2 + c] = v;
+                        bm = fmaxf(bm, v);
+                    }
+                bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 1));
+                bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 2));
+                const float m_new = fmaxf(mrow[mt][hh], bm);          // finite: key 0 is visible to every row
+                const float alpha = exp2f(mrow[mt][hh] - m_new);
+                mrow[mt][hh] = m_new;
+                float ls = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float pz = exp2f(sacc[mt][j][hh * 2 + c] - m_new);
+                        sacc[mt][j][hh * 2 + c] = pz;
+                        ls += pz;
+                    }
+                lrow[mt][hh] = lrow[mt][hh] * alpha + ls;
+#pragma unroll
+                for (int d8 = 0; d8 < 8; ++d8) { o[mt][d8][hh * 2] *= alpha; o[mt][d8][hh * 2 + 1] *= alpha; }
+            }
+        // O += P V   (two k16 key steps x 8 dim n8-blocks); every V fragment feeds all m-tiles
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t pa[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                pa[mt][0] = pack_bf16x2(sacc[mt][2 * ks][0], sacc[mt][2 * ks][1]);
+                pa[mt][1] = pack_bf16x2(sacc[mt][2 * ks][2], sacc[mt][2 * ks][3]);
+                pa[mt][2] = pack_bf16x2(sacc[mt][2 * ks + 1][0], sacc[mt][2 * ks + 1][1]);
+                pa[mt][3] = pack_bf16x2(sacc[mt][2 * ks + 1][2], sacc[mt][2 * ks + 1][3]);
+            }
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {               // two dim n8-blocks per ldmatrix.x4.trans
+                const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ch = dp * 2 + (lane >> 4);
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4_trans(sV + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    mma_bf16(o[mt][2 * dp], pa[mt], b0, b1);
+                    mma_bf16(o[mt][2 * dp + 1], pa[mt], b2, b3);
+                }
+            }
+        }
+        __syncwarp();                                      // everyone is done with this buffer before it is refilled
+    }
+    // normalise and store
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float l = lrow[mt][hh];
+            l += __shfl_xor_sync(0xFFFFFFFFu, l, 1);
+            l += __shfl_xor_sync(0xFFFFFFFFu, l, 2);
+            const int i = rb + mt * 16 + g + hh * 8;
+            if (i < n) {
+                const float inv = 1.0f / l;
+                __nv_bfloat16* dst = out + (size_t)(r0 + i) * d_model + head * 64;
+#pragma unroll
+                for (int d8 = 0; d8 < 8; ++d8)
+                    *reinterpret_cast<uint32_t*>(dst + d8 * 8 + 2 * t) = pack_bf16x2(o[mt][d8][hh * 2] * inv, o[mt][d8][hh * 2 + 1] * inv);
+            }
+        }
+}
+
+__global__ void __maxnreg__(200) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                                const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
-                                                                               int d_model, int t_cap, float scale_log2e,
+                                                                               int d_model, int t_cap, float scale_log2e, int wide,
                                                                                __nv_bfloat16* __restrict__ out) {
     pdl_enter();
     extern __shared__ __align__(128) unsigned char attp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
     const uint32_t sbase = smem_u32(attp_smem) + warp * ATTP_WARP_SMEM;
     const int total = *rows.n_slots * n_head;
     const uint64_t pol_last = l2_policy_evict_last();
@@ -419,140 +578,19 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32, 2) attention_prefill_kernel(c
         const int p0 = rows.row_pos[r0];
         const __nv_bfloat16* gK = kcache + ((size_t)e * n_head + head) * t_cap * 64;
         const __nv_bfloat16* gV = vcache + ((size_t)e * n_head + head) * t_cap * 64;
-        bool keep = false;                                     // set per row block below
-        auto stage = [&](int buf, int k0) {                    // 32 keys of K and V: 2 x 256 chunks of 16 B, 16 per lane
-            const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
-                const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
-                const int kk = min(k0 + key, t_cap - 1);
-                if (keep) {
-                    cp_async16_hint(sK + off, gK + (size_t)kk * 64 + ch * 8, pol_last);
-                    cp_async16_hint(sV + off, gV + (size_t)kk * 64 + ch * 8, pol_last);
-                } else {
-                    cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
-                    cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
-                }
-            }
-            cp_async_commit();
-        };
-        for (int rb = 0; rb < n; rb += 16) {
-            const int nr = min(16, n - rb);                    // live query rows in this block
-            const int n_keys = p0 + rb + nr;                   // keys visible to the last live row
-            keep = rb + 16 < n;                                // another block will stream the same K / V again: ask L2 to keep the lines
-            __syncwarp();
-            stage(0, 0);
-            // Q fragments: qa[kk][0..3]
-            uint32_t qa[4][4];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int i = rb + g + hh * 8;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(q + (size_t)(r0 + i) * d_model + head * 64);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    qa[kk][hh] = i < n ? __ldg(src + kk * 8 + t) : 0u;            // dims 16kk + 2t, +1
-                    qa[kk][hh + 2] = i < n ? __ldg(src + kk * 8 + 4 + t) : 0u;    // dims 16kk + 8 + 2t, +1
-                }
-            }
-            float o[8][4];
-            float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-#pragma unroll
-            for (int d8 = 0; d8 < 8; ++d8)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) o[d8][c] = 0.f;
-            int buf = 0;
-            for (int k0 = 0; k0 < n_keys; k0 += ATTP_KEYS, buf ^= 1) {
-                if (k0 + ATTP_KEYS < n_keys) { stage(buf ^ 1, k0 + ATTP_KEYS); cp_async_wait<1>(); }
-                else cp_async_wait<0>();
-                __syncwarp();
-                const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
-                // S = Q K^T  (4 key n8-blocks)
-                float sacc[4][4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) sacc[j][c] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                    for (int kp = 0; kp < 2; ++kp) {           // two k16 steps per ldmatrix.x4
-                        const int key = j * 8 + (lane & 7), ch = kp * 4 + (lane >> 3);
-                        uint32_t b0, b1, b2, b3;
-                        ldmatrix_x4(sK + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
-                        mma_bf16(sacc[j], qa[2 * kp], b0, b1);
-                        mma_bf16(sacc[j], qa[2 * kp + 1], b2, b3);
-                    }
-                }
-                // scale, causal mask, online soft-max
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int pos = p0 + rb + g + hh * 8;
-                    float bm = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int key = k0 + j * 8 + 2 * t + c;
-                            float v = sacc[j][hh * 2 + c] * scale_log2e;
-                            v = key <= pos ? v : -INFINITY;
-                            sacc[j][hh * 2 + c] = v;
-                            bm = fmaxf(bm, v);
-                        }
-                    bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 1));
-                    bm = fmaxf(bm, __shfl_xor_sync(0xFFFFFFFFu, bm, 2));
-                    const float m_new = fmaxf(mrow[hh], bm);              // finite: key 0 is visible to every row
-                    const float alpha = exp2f(mrow[hh] - m_new);
-                    mrow[hh] = m_new;
-                    float ls = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float pz = exp2f(sacc[j][hh * 2 + c] - m_new);
-                            sacc[j][hh * 2 + c] = pz;
-                            ls += pz;
-                        }
-                    lrow[hh] = lrow[hh] * alpha + ls;
-#pragma unroll
-                    for (int d8 = 0; d8 < 8; ++d8) { o[d8][hh * 2] *= alpha; o[d8][hh * 2 + 1] *= alpha; }
-                }
-                // O += P V   (two k16 key steps x 8 dim n8-blocks)
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    uint32_t pa[4];
-                    pa[0] = pack_bf16x2(sacc[2 * ks][0], sacc[2 * ks][1]);
-                    pa[1] = pack_bf16x2(sacc[2 * ks][2], sacc[2 * ks][3]);
-                    pa[2] = pack_bf16x2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
-                    pa[3] = pack_bf16x2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
-#pragma unroll
-                    for (int dp = 0; dp < 4; ++dp) {           // two dim n8-blocks per ldmatrix.x4.trans
-                        const int key = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ch = dp * 2 + (lane >> 4);
-                        uint32_t b0, b1, b2, b3;
-                        ldmatrix_x4_trans(sV + key * 128 + ((ch ^ (key & 7)) << 4), b0, b1, b2, b3);
-                        mma_bf16(o[2 * dp], pa, b0, b1);
-                        mma_bf16(o[2 * dp + 1], pa, b2, b3);
-                    }
-                }
-                __syncwarp();                                  // everyone is done with this buffer before it is refilled
-            }
-            // normalise and store
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                float l = lrow[hh];
-                l += __shfl_xor_sync(0xFFFFFFFFu, l, 1);
-                l += __shfl_xor_sync(0xFFFFFFFFu, l, 2);
-                const int i = rb + g + hh * 8;
-                if (i < n) {
-                    const float inv = 1.0f / l;
-                    __nv_bfloat16* dst = out + (size_t)(r0 + i) * d_model + head * 64;
-#pragma unroll
-                    for (int d8 = 0; d8 < 8; ++d8)
-                        *reinterpret_cast<uint32_t*>(dst + d8 * 8 + 2 * t) = pack_bf16x2(o[d8][hh * 2] * inv, o[d8][hh * 2 + 1] * inv);
-                }
+        for (int rb = 0; rb < n;) {
+            if (wide && n - rb > 16) {
+                attp_rows<2>(q, gK, gV, r0, n, rb, p0, head, d_model, t_cap, scale_log2e, rb + 32 < n, pol_last, sbase, lane, out);
+                rb += 32;
+            } else {
+                attp_rows<1>(q, gK, gV, r0, n, rb, p0, head, d_model, t_cap, scale_log2e, rb + 16 < n, pol_last, sbase, lane, out);
+                rb += 16;
             }
         }
     }
+}
+static inline int attp_grid(int n_env, int n_head, int sm_count) {
+    return std::max(1, std::min((n_env * n_head + ATTP_WARPS - 1) / ATTP_WARPS, sm_count * ATTP_CTAS_PER_SM));
 }
 
 // ---- sampler bookkeeping ------------------------------------------------------------------------------------------------

@@ -761,8 +761,8 @@ static int train_layer_forward(lmrl_engine* e, int l, int n_seq, bool with_fc2) 
     a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
     a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
     if (launch_gemm<EPI_QKV>(e, a, a.N, 0, (size_t)Tr.m_cap, a.N, 0)) return -1;
-    LMRL_K(attention_prefill_kernel, std::min((n_seq * D.n_head + ATTP_WARPS - 1) / ATTP_WARPS, G.sm_count * 2), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q,
-           a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f * 1.4426950408889634f, G.att);
+    LMRL_K(attention_prefill_kernel, attp_grid(n_seq, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q,
+           a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f * 1.4426950408889634f, G.attn_wide, G.att);
     GemmArgs p{};
     p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
     if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;

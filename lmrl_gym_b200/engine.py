@@ -96,6 +96,15 @@ class Engine:
         """Programmatic dependent launch between the kernels of a pass (default off: measured slower on B200)."""
         check(self.lib.lmrl_set_use_pdl(self.handle, 1 if enable else 0))
 
+    def set_option(self, name: str, value: int):
+        """Named integer switch of the policy engine (include/lmrl_b200.h::lmrl_set_option): fuse_ln, attn_wide, gemv_max_rows."""
+        check(self.lib.lmrl_set_option(self.handle, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int32(0)
+        check(self.lib.lmrl_get_option(self.handle, name.encode(), C.addressof(v)))
+        return int(v.value)
+
     def set_gemm_impl(self, impl: int):
         """1 = tcgen05/TMEM/TMA (default), 0 = the mma.sync kernel (independent cross-check used by the tests)."""
         check(self.lib.lmrl_set_gemm_impl(self.handle, int(impl)))

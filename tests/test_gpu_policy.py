@@ -292,3 +292,47 @@ def test_sampler_distribution_matches_softmax(tok):
     again = pol.generate_tokens([prompt] * 64, episode_keys=list(range(1000, 1064)), turn=0)
     assert [g[0] for g in again] == first[:64].tolist()
     eng.close()
+
+
+def test_fused_layernorm_and_wide_prefill_attention_are_bit_identical(tok):
+    """Round-2 kernels vs the round-1 launch sequence on the same inputs: LayerNorm fused into the residual GEMMs (the CTA that
+    completes an m-tile normalises its rows; same two-pass arithmetic as layernorm_kernel) and 32-row prefill-attention passes
+    (the extra keys a 32-row pass shows the first 16 rows are masked: exp2(-inf) = 0) must reproduce the separate-launch /
+    16-row-pass logits bit for bit, at a toy shape (192-wide decode tiles not involved) and at GPT-2-small shape, ragged
+    prompts of 1..max rows (several m-tiles, partial last tile), and the sampled tokens of a decode loop."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    for cfg, n_prompts, max_in in ((_small_cfg(), 150, 64), (GPT2Config.small(), 40, 80)):
+        params = init_gpt2_params(cfg, seed=11)
+        rng = np.random.default_rng(4)
+        for l in params["layers"]:
+            for k in ("ln1_b", "ln2_b", "proj_b", "fc2_b"):
+                l[k] = (0.1 * rng.standard_normal(l[k].shape)).astype(np.float32)
+            l["ln2_g"] = (1 + 0.1 * rng.standard_normal(l["ln2_g"].shape)).astype(np.float32)
+        eng = Engine(max_envs=160, max_input_length=max_in, max_new_tokens=4, tokenizer=tok)
+        pol = B200GPT2Policy(eng, params, cfg, seed=5)
+        prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, max_in, size=n_prompts)]
+        prompts[1] = rng.integers(0, cfg.n_vocab, size=max_in).tolist()
+        prompts[2] = prompts[2][:17]
+        prompts[3] = (prompts[3] * 3)[:33]
+        keys = [int(k) for k in rng.integers(0, 2**63, size=n_prompts)]
+        outs = {}
+        for fuse, wide in ((1, 1), (0, 1), (1, 0), (0, 0)):
+            eng.set_option("fuse_ln", fuse)
+            eng.set_option("attn_wide", wide)
+            assert eng.get_option("fuse_ln") == fuse and eng.get_option("attn_wide") == wide
+            outs[(fuse, wide)] = (pol.logits(prompts), pol.generate_tokens(prompts, episode_keys=keys, turn=1))
+        ref_logits, ref_gen = outs[(0, 0)]
+        assert np.isfinite(ref_logits).all()
+        for fuse in (0, 1):                       # attention pass width: exactly the same arithmetic per row
+            assert np.array_equal(outs[(fuse, 1)][0], outs[(fuse, 0)][0]), f"logits differ between 32- and 16-row attention passes (fuse_ln={fuse})"
+            assert outs[(fuse, 1)][1] == outs[(fuse, 0)][1]
+        # fused vs separate LayerNorm: same formula at two code sites (the compiler may contract the FMAs differently): identical
+        # or within a few bf16 ulps of the normalised activations
+        d = np.abs(outs[(1, 1)][0] - ref_logits).max()
+        same_tok = np.mean([a == b for a, b in zip(outs[(1, 1)][1], ref_gen)])
+        print(f"{cfg.d_model}: fused-LN vs separate-LN max |logit diff| {d:.3g} (bit-identical: {bool(d == 0)}), identical sampled rows {same_tok:.3f}")
+        assert d <= 2e-3 and same_tok >= 0.97
+        with pytest.raises(Exception):
+            eng.set_option("no_such_option", 1)
+        eng.close()
