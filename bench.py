@@ -108,44 +108,65 @@ def build_policy_params(medium: bool = False):
     return cfg, init_gpt2_params(cfg, seed=0)
 
 
-def cpu_reference_numbers(params, cfg, tok, bs, seed=0):
-    """The CPU restatement of the reference path on all host threads, two ways: *charitable* = prompts padded to the
-    longest in the batch, *faithful* = LEFT-padded to max_input_length=256 as wordle/bc/eval_bc_gpt2.py:100-104 does."""
+def _ref_runner():
+    """The CPU arm's rollout function: the unmodified reference loop + env staged under oracle/_ref when present (kind "reference"),
+    else the oracle port (kind "port").  Only `--impl reference` processes call this (the product arm spawns one for cpu_baseline)."""
+    from oracle import build_ref
+    if build_ref.available():
+        build_ref.activate()
+        from oracle.ref_runner import run_ref_wordle
+        return run_ref_wordle, "reference", ("LLM_RL.environment.text_env_eval + ReformatWordleEnvironment(WordleEnvironment) imported unmodified from oracle/_ref "
+                                             "(oracle/build_ref.py); policy = HF torch-CPU GPT2LMHeadModel.generate (the JaxSeq policy is not installable)")
     from oracle.cpu_rollout import run_cpu_wordle
-    char = run_cpu_wordle(params, cfg, tok, n_rollouts=bs, bsize=bs, seed=seed)
-    faith = run_cpu_wordle(params, cfg, tok, n_rollouts=max(bs // 4, 4), bsize=max(bs // 4, 4), seed=seed, pad_to_max_input=True)
-    return char, faith
+    return run_cpu_wordle, "port", "oracle port of the loop + env (oracle/_ref absent); policy = HF torch-CPU GPT2LMHeadModel.generate"
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the reference path on all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU rollout path on all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must use the host's cores whatever launched it
+    n_threads = os.cpu_count() or 1
+    torch.set_num_threads(n_threads)
+    run, kind, how = _ref_runner()
     from lmrl_gym_b200.tokenizer import ByteTokenizer
-    from oracle.cpu_rollout import run_cpu_wordle
     cfg, params = build_policy_params()
     tok = ByteTokenizer.synthetic()
     bs = args.ref_batch
     for _ in range(min(args.warmup, 1)):
-        run_cpu_wordle(params, cfg, tok, n_rollouts=4, bsize=4)
+        run(params, cfg, tok, n_rollouts=4, bsize=4, threads=n_threads)
     steps_total, secs = 0, 0.0
     for k in range(args.steps):
-        r = run_cpu_wordle(params, cfg, tok, n_rollouts=bs, bsize=bs, seed=k)
+        r = run(params, cfg, tok, n_rollouts=bs, bsize=bs, seed=k, threads=n_threads)
         steps_total += r["env_steps"]; secs += r["seconds"]
     value = steps_total / secs
-    faith = run_cpu_wordle(params, cfg, tok, n_rollouts=max(bs // 4, 4), bsize=max(bs // 4, 4), seed=0, pad_to_max_input=True)
-    sample = (f"{args.steps} x text_env_eval(n_rollouts={bs}, bsize={bs}) episodes of the same workload, prompts padded to the longest in the batch "
-              f"(charitable); faithful variant (LEFT-padded to 256 tokens, eval_bc_gpt2.py:100-104) on {max(bs // 4, 4)} episodes: "
-              f"{faith['env_steps_per_s']:.2f} env-steps/s")
+    faith = run(params, cfg, tok, n_rollouts=max(bs // 4, 4), bsize=max(bs // 4, 4), seed=0, pad_to_max_input=True, threads=n_threads)
+    sample = (f"{args.steps} x text_env_eval(n_rollouts={bs}, bsize={bs}) episodes of the same workload ({steps_total} env-steps in {secs:.1f} s), prompts padded to the "
+              f"longest in the batch (charitable); faithful variant (LEFT-padded to 256 tokens, eval_bc_gpt2.py:100-104) on {max(bs // 4, 4)} episodes: "
+              f"{faith['env_steps_per_s']:.2f} env-steps/s; {how}")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 * secs / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(workload=WORKLOAD, batch_per_step=bs, policy="transformers GPT2LMHeadModel.generate torch-CPU fp32"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample, host_cpus=os.cpu_count(),
-                                  faithful_value=faith["env_steps_per_s"]),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind=kind, sample=sample, host_cpus=os.cpu_count(),
+                                  faithful_value=faith["env_steps_per_s"], faithful_env_steps=faith["env_steps"], faithful_seconds=faith["seconds"],
+                                  env_steps=steps_total, seconds=secs),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(ref_batch):
+    """cpu_baseline leg of the product arm: the reference arm in its own process (it imports oracle/_ref, which the product process
+    never does), all host threads, one bounded step."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-batch", str(ref_batch)],
+                         capture_output=True, text=True, env=env, timeout=900)
+    for ln in reversed(res.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu_baseline subprocess printed no JSON line: " + res.stderr[-2000:])
 
 
 def main():
@@ -382,12 +403,7 @@ def main():
         if letters_variant is not None:
             line["letters_variant"] = letters_variant
         if world == 1 and not args.no_cpu_baseline and not maze:
-            r, rf = cpu_reference_numbers(params, cfg, tok, args.ref_batch)
-            line["cpu_baseline"] = dict(value=r["env_steps_per_s"], unit=UNIT, cores=r["cores"], kind="port", host_cpus=r["host_cpus"],
-                                        sample=f"text_env_eval(n_rollouts={args.ref_batch}, bsize={args.ref_batch}) of the same workload "
-                                               f"({r['env_steps']} env-steps in {r['seconds']:.1f} s), prompts padded to the longest in the batch (charitable)",
-                                        faithful_value=rf["env_steps_per_s"],
-                                        faithful_sample=f"prompts LEFT-padded to 256 tokens as eval_bc_gpt2.py:100-104 ({rf['env_steps']} env-steps in {rf['seconds']:.1f} s)")
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.ref_batch)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -338,8 +338,8 @@ int lmrl_set_two_lanes(lmrl_engine* e, int32_t enable);
 int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
 /* named integer switches of the policy engine (A/B measurement and cross-checks; every value gives identical results up to the
  * documented float tolerance):
- *   "fuse_ln"        1 (default) LayerNorm fused into the residual GEMMs (the CTA completing an m-tile normalises its rows),
- *                    0 separate layernorm_kernel launches
+ *   "fuse_ln"        1 LayerNorm fused into the residual GEMMs (the CTA completing an m-tile normalises its rows; bit-identical,
+ *                    measured slower on B200), 0 (default) separate layernorm_kernel launches
  *   "attn_wide"      1 (default) prefill attention takes 32 query rows per warp pass (K / V streamed once for slots of <= 32 new rows),
  *                    0 16-row passes
  *   "gemv_max_rows"  decode passes of batches with at most this many envs run the weight-streaming GEMV kernels instead of

@@ -537,7 +537,9 @@ __global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant_
                 }
             }
         }
-        if (lane == 0) bulk_wait_all();                                            // all TMA stores / reductions have landed
+        // the staging boxes must have been read before the CTA's shared memory goes away; the global writes themselves complete with
+        // the grid (the fused LayerNorm above is the one consumer inside the kernel, and it waits for full completion itself)
+        if (lane == 0) bulk_wait_read<0>();
     }
     tcgen05_fence_before();
     __syncthreads();

@@ -154,8 +154,12 @@ struct Gpt2Dev {
     int use_graphs = 1;
     int narrow_decode_tiles = 1;      // 128 x 192 tiles for the N = 768 residual GEMMs of decode passes
     // LayerNorm fused into the residual GEMMs (GemmArgs::ln_out): the decoder stack launches one LayerNorm per tower pass (layer 0's
-    // ln_1) instead of two per layer.  0 = separate layernorm_kernel launches (round-1 path; also taken by the mma.sync / CTA-pair GEMMs)
-    int fuse_ln = 1;
+    // ln_1) instead of two per layer.  Bit-identical to the separate launches, but measured SLOWER on B200 (4096-episode Wordle
+    // rollout: 247.7 vs 211.3 ms): the CTA that completes an m-tile has to wait for the TMA reductions of all its peers to land
+    // and then normalises 128 rows at one SM's L2 latency (~20 us per m-tile), which lands on the critical path of every residual
+    // GEMM (proj prefill 8.5 -> 35.8 ms per step), while the stand-alone layernorm_kernel runs at 6.1 TB/s (74 us per 98 k rows,
+    // 6.6 us at 4096 rows).  Default 0 = separate layernorm_kernel launches; 1 is kept selectable (lmrl_set_option "fuse_ln").
+    int fuse_ln = 0;
     int attn_wide = 1;                // prefill attention: 32 query rows per warp pass (two m16 tiles share every staged K / V block)
     int gemv_max_rows = 8;            // batches of at most this many envs decode through the weight-streaming GEMV kernels
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
@@ -384,6 +388,10 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     do {                                               \
         if ((cat) >= 0 && e->prof_begin(cat)) return -1; \
         __VA_ARGS__;                                   \
+        {                                              \
+            const cudaError_t lerr__ = cudaPeekAtLastError(); \
+            if (lerr__ != cudaSuccess) return ::lmrl::fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(lerr__), __FILE__, __LINE__); \
+        }                                              \
         e->prof_end();                                 \
         e->launches++;                                 \
     } while (0)

@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv
 // ldmatrix fragment feeds both m-tiles, so a Wordle turn's ~20 new rows per episode stream the episode's K / V exactly once
 // (round 1: 16-row passes, the second one re-reading K / V through L2 — DRAM traffic 1.25x the algorithmic bytes, 0.55 of HBM).
 // Slots with more than 32 new rows take further passes; the passes that will be followed by another one ask L2 to keep the lines.
-constexpr int ATTP_WARPS = 10;                                  // 10 x 16 KB of staging, one CTA per SM (<= 204 registers per thread)
+constexpr int ATTP_WARPS = 12;                                  // 12 x 16 KB of staging, one CTA per SM: 3 warps per SM sub-partition (16 K registers each) -> 168 registers per thread
 constexpr int ATTP_KEYS = 32;                                   // keys per staged block
 constexpr int ATTP_WARP_SMEM = 2 * 2 * ATTP_KEYS * 128;        // 2 buffers x (K block + V block)
 constexpr int ATTP_CTAS_PER_SM = 1;
@@ -562,7 +562,7 @@ __device__ __forceinline__ void attp_rows(const __nv_bfloat16* __restrict__ q, c
         }
 }
 
-__global__ void __maxnreg__(200) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+__global__ void __launch_bounds__(ATTP_WARPS * 32, ATTP_CTAS_PER_SM) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                                const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
                                                                                int d_model, int t_cap, float scale_log2e, int wide,
                                                                                __nv_bfloat16* __restrict__ out) {

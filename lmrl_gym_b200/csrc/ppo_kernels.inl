@@ -22,6 +22,11 @@ struct PpoArgs {
     int* part_n;                     // [n_chains] action tokens of the chain
 };
 
+// the library is compiled with --use_fast_math (expf -> ex2.approx): the KL estimate exp(lr) - 1 - lr cancels catastrophically and feeds
+// the adaptive KL controller, so exp goes through double precision here (unaffected by the flag; the result rounds to the correctly
+// rounded float32 exp in all but ~1e-9 of cases) — per-token work, not a hot loop
+__device__ __forceinline__ float exp_precise(float x) { return (float)exp((double)x); }
+
 __global__ void ppo_gae_kernel(PpoArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_chains) return;
@@ -35,7 +40,7 @@ __global__ void ppo_gae_kernel(PpoArgs a) {
     for (int64_t t = t1 - 1; t >= t0; --t) {
         if (!a.sta[t]) { a.adv[t] = 0.f; a.ret[t] = 0.f; a.kls[t] = 0.f; continue; }
         const float lr = __fsub_rn(a.policy_lp[t], a.initial_lp[t]);                     // log_ratio (:572-575)
-        a.kls[t] = __fsub_rn(__fsub_rn(expf(lr), 1.f), lr);                              // exp(lr) - 1 - lr (:579)
+        a.kls[t] = __fsub_rn(__fsub_rn(exp_precise(lr), 1.f), lr);                              // exp(lr) - 1 - lr (:579)
         const float r = __fsub_rn(a.rewards[t], __fmul_rn(a.kl_weight, lr));             // :581-584
         const float sv = v[t - t0];
         const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(a.gamma, next_v)), sv);     // :284
@@ -97,7 +102,7 @@ __global__ void ppo_loss_partial_kernel(PpoLossArgs a) {
         const float d1 = __fsub_rn(v, ret), d2 = __fsub_rn(vc, ret);
         const float vf1 = __fmul_rn(d1, d1), vf2 = __fmul_rn(d2, d2);
         const float lr = __fmul_rn(__fsub_rn(a.logprobs[i], a.old_logprobs[i]), m);
-        const float ratio = expf(lr);
+        const float ratio = exp_precise(lr);
         const float pg1 = __fmul_rn(-adv, ratio), pg2 = __fmul_rn(-adv, fminf(fmaxf(ratio, lo_r), hi_r));
         const float dm = __fmul_rn(d1, m);
         acc[0] += (double)m;
@@ -256,7 +261,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi; v[i] = vi;
-        const float upd = (mi / bc1) / (sqrtf(vi / bc2) + eps) + wd * p[i];
+        const float upd = __fdiv_rn(__fdiv_rn(mi, bc1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, bc2)), eps)) + wd * p[i];      // IEEE division / sqrt whatever --use_fast_math says
         p[i] -= lr * upd;
     }
 }

@@ -53,7 +53,10 @@ def _unchunk(x: Any) -> Any:
         if x.get("__msgpack_chunked_array__"):
             chunks = x["chunks"]
             flat = np.concatenate([np.asarray(chunks[str(i)]).reshape(-1) for i in range(len(chunks))])
-            return flat.reshape(tuple(x["shape"]))
+            shape = x["shape"]
+            if isinstance(shape, dict):               # flax.serialization._chunk stores the shape as _tuple_to_dict: {'0': d0, '1': d1, ...}
+                shape = [shape[str(i)] for i in range(len(shape))]
+            return flat.reshape(tuple(int(d) for d in shape))
         return {k: _unchunk(v) for k, v in x.items()}
     return x
 

@@ -480,9 +480,6 @@ class B200PPOTrain:
         return dict(wte=g(P["wte"]), wpe=g(P["wpe"]), lnf_g=g(P["lnf_g"]), lnf_b=g(P["lnf_b"]), layers=[{k: g(L[k]) for k in _LAYER_KEYS} for L in P["layers"]])
 
 
-TorchPPOTrain = B200PPOTrain          # earlier name, kept for callers that select backward="torch"
-
-
 def bc_batch_from_str_segments(items, tokenizer, max_length: int, pad_token_id: int) -> Dict[str, np.ndarray]:
     """One BC minibatch from ``[(text, mask_value), ...]`` segment lists — the data format of the PPO drivers' ``bc_data_path``
     (``MaskIterableDataset.blocked_from_str_segments_iterable``, train_ppo_gpt2.py:136-144): every segment is encoded on its own and
@@ -498,6 +495,64 @@ def bc_batch_from_str_segments(items, tokenizer, max_length: int, pad_token_id: 
         t, m = t[-max_length:], m[-max_length:]
         ids[i, :len(t)], mask[i, :len(m)] = t, m
     return dict(input_ids=ids, input_training_mask=mask)
+
+
+# ---- agreement across data-parallel ranks ---------------------------------------------------------------------------------
+# The reference is one pjit controller: the PPO batch statistics (advantage whitening, mean KL for the adaptive controller) and the
+# number of optimizer steps are functions of the GLOBAL batch (ppo/train.py:267-438).  With one process per GPU each rank collects its own
+# episodes and may drop some (truncated chains), so these three quantities are agreed on explicitly: every rank must call all_reduce
+# the same number of times, or NCCL hangs.
+
+def _dist_group():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+
+
+def _all_reduce_f64(values, op: str = "sum") -> np.ndarray:
+    """All-reduce a small float64 vector over the ranks (identity without a process group); NCCL needs device tensors."""
+    dist = _dist_group()
+    v = np.asarray(values, dtype=np.float64)
+    if dist is None:
+        return v
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(v.copy()).to(dev)
+    dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op])
+    return t.cpu().numpy()
+
+
+def global_mean_kl(kls: np.ndarray) -> float:
+    """Mean per-action-token KL over every rank's PPO data (what ``kl_controller.update`` sees in the reference)."""
+    s = _all_reduce_f64([float(np.sum(kls, dtype=np.float64)), float(len(kls))])
+    return float(s[0] / s[1]) if s[1] > 0 else 0.0
+
+
+def whiten_advantages_global(datas: List[PPOData]) -> List[PPOData]:
+    """``whiten`` (ppo/base_interface.py:245-251: (x - mean) / sqrt(var + 1e-8)) of the action-token advantages with mean / variance taken
+    over ALL ranks' data (three summed scalars); used instead of the per-rank device whitening when a process group is active."""
+    acc = np.zeros(3, np.float64)
+    for d in datas:
+        a = np.asarray(d.old_advantages, np.float64)[np.asarray(d.should_take_action, bool)]
+        acc += (a.sum(), (a * a).sum(), a.size)
+    acc = _all_reduce_f64(acc)
+    if acc[2] == 0:
+        return datas
+    mean = acc[0] / acc[2]
+    var = max(acc[1] / acc[2] - mean * mean, 0.0)
+    scale = 1.0 / np.sqrt(var + 1e-8)
+    out = []
+    for d in datas:
+        sta = np.asarray(d.should_take_action, bool)
+        adv = np.asarray(d.old_advantages, np.float32).copy()
+        adv[sta] = ((adv[sta].astype(np.float64) - mean) * scale).astype(np.float32)
+        out.append(d._replace(old_advantages=adv))
+    return out
+
+
+def agreed_steps_per_epoch(n_datas: int, train_bsize: int) -> int:
+    """Optimizer steps every rank takes per epoch: the minimum over ranks of len(datas) // train_bsize (a rank with more data drops its
+    surplus for the round rather than entering an all_reduce its peers never join)."""
+    return int(_all_reduce_f64([float(n_datas // train_bsize)], "min")[0])
 
 
 def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTrain, kl_controller, *, n_rounds: int, n_rollouts: int, rollout_bsize: int,
@@ -539,17 +594,23 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTra
         t1 = t0 + rollout_s
         if not fused_wordle:
             token_chains = [TokenTrajectoryChain.from_text_trajectory_chain(c, tok) for c in episodes_to_chains(raw, tok, max_length, gamma)]
+        multi = _dist_group() is not None
         datas, kls = inference.get_ppo_data_from_token_trajectory_chain(token_chains, bsize=1 << 20, max_length=max_length, gamma=gamma, lam=lam,
-                                                                        kl_weight=kl_controller.value, use_advantage_whitening=use_advantage_whitening, verbose=False)
-        mean_kl = float(np.mean(kls)) if len(kls) else 0.0
+                                                                        kl_weight=kl_controller.value,
+                                                                        use_advantage_whitening=use_advantage_whitening and not multi, verbose=False)
+        if use_advantage_whitening and multi:
+            datas = whiten_advantages_global(datas)          # statistics of the global batch, as the single-controller reference has them
+        mean_kl = global_mean_kl(kls)                         # identical on every rank: kl_coef cannot diverge between replicas
         kl_controller.update(mean_kl, train_bsize)
         t2 = time.perf_counter()
         losses = []
+        steps_per_epoch = agreed_steps_per_epoch(len(datas), train_bsize)     # same all_reduce count on every rank
         for _ in range(epochs):
             order = rng.permutation(len(datas))
-            for lo in range(0, len(order) - train_bsize + 1, train_bsize):
+            for k in range(steps_per_epoch):
                 if max_steps_per_round is not None and len(losses) >= max_steps_per_round:
                     break
+                lo = k * train_bsize
                 batch = block_ppo_data([datas[i] for i in order[lo:lo + train_bsize]], inference.pad_token_id, max_length)
                 losses.append(trainer.step(batch, next(bc_batches) if bc_batches is not None else None)[0])
         trainer.push_to_engine()

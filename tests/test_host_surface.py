@@ -146,7 +146,7 @@ def test_product_never_imports_the_oracle():
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
         uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle")]
         if uses:
-            assert fn.name in ("run_reference", "cpu_reference_numbers"), fn.name
+            assert fn.name in ("run_reference", "_ref_runner"), fn.name          # the product arm reaches the CPU arm only through a subprocess
 
 
 def test_head_struct_for_mlp_and_linear_heads():
@@ -208,3 +208,24 @@ def test_scripted_rollout_records_have_the_data_generator_format(golden_dir):
         assert [[t, bool(m)] for t, m in r["sequence"]] == c["steps"][-1]["obs"]
         assert r["reward"] == sum(([float(s["reward"]), 0.0] for s in c["steps"]), []) and r["done"] == c["steps"][-1]["done"]
         assert len(r["reward"]) == len(r["sequence"]) - 1
+
+
+def test_reference_arm_uses_host_threads_under_torchrun_env(tmp_path):
+    """`bench.py --impl reference` must not inherit torchrun's OMP_NUM_THREADS=1 (round-1 defect: the N >= 2 reference lines ran on
+    one thread); rank != 0 exits without work; with oracle/_ref staged the arm is the unmodified reference loop + env."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-batch", "2"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    from oracle import build_ref
+    assert line["cpu_baseline"]["kind"] == ("reference" if build_ref.available() else "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    env["RANK"] = "1"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-batch", "2"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and not [l for l in res.stdout.splitlines() if l.startswith("{")]

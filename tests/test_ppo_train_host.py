@@ -221,3 +221,44 @@ def test_bc_step_lowers_the_bc_loss():
     assert abs(losses[0] - float(tr.__class__.bc_loss(make_trainer()[0], bc))) < 1e-5        # the first loss is the untouched model's
     assert torch.equal(tr.vh_w.detach(), vh0)
     assert tr.steps == 8
+
+
+def _agree_main(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from lmrl_gym_b200.ppo import PPOData
+    from lmrl_gym_b200.ppo_train import agreed_steps_per_epoch, global_mean_kl, whiten_advantages_global
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7 + rank)
+    n = 11 if rank == 0 else 5                        # rank 1 dropped episodes (truncated chains): fewer PPO data than rank 0
+    datas = []
+    for _ in range(n):
+        t = int(rng.integers(4, 9))
+        sta = rng.random(t) < 0.6
+        sta[0] = True
+        adv = np.where(sta, rng.standard_normal(t) * (2.0 + rank) + rank, 0.0).astype(np.float32)
+        datas.append(PPOData(np.arange(t + 1, dtype=np.int32), sta, np.zeros(t, np.float32), np.zeros(t, np.float32), adv, np.zeros(t, np.float32)))
+    steps = agreed_steps_per_epoch(len(datas), 2)
+    kl = global_mean_kl(np.full(3 + rank, float(rank + 1)))
+    white = whiten_advantages_global(datas)
+    acts = np.concatenate([np.asarray(d.old_advantages)[np.asarray(d.should_take_action, bool)] for d in white])
+    rest = np.concatenate([np.asarray(d.old_advantages)[~np.asarray(d.should_take_action, bool)] for d in white])
+    np.save(os.path.join(out_dir, f"agree{rank}.npy"), np.array([steps, kl, acts.sum(), (acts.astype(np.float64) ** 2).sum(), acts.size, np.abs(rest).max() if rest.size else 0.0]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_ppo_round_agrees_on_steps_kl_and_whitening(tmp_path):
+    """ranks with different numbers of PPO data must take the same number of optimizer steps (one all_reduce
+    per step: otherwise NCCL hangs), see the same mean KL (so kl_coef stays equal) and whiten with the statistics of the global batch."""
+    import torch.multiprocessing as mp
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_agree_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "agree0.npy"), np.load(tmp_path / "agree1.npy")
+    assert a[0] == b[0] == 2                                    # min(11 // 2, 5 // 2)
+    assert a[1] == b[1] == (3 * 1.0 + 4 * 2.0) / 7              # token-weighted global mean
+    n = a[4] + b[4]
+    mean, var = (a[2] + b[2]) / n, (a[3] + b[3]) / n - ((a[2] + b[2]) / n) ** 2
+    assert abs(mean) < 1e-6 and abs(var - 1.0) < 1e-4           # the UNION of both ranks' action advantages is white, neither half alone is
+    assert abs(a[2] / a[4]) > 1e-3 and a[5] == 0.0 and b[5] == 0.0
+    from lmrl_gym_b200.ppo_train import agreed_steps_per_epoch, global_mean_kl
+    assert agreed_steps_per_epoch(11, 2) == 5 and global_mean_kl(np.array([1.0, 3.0])) == 2.0        # no process group: local values
