@@ -38,7 +38,10 @@ typedef struct lmrl_config {
     int32_t max_input_length;  /* BlockingStrategy max_length (LEFT pad / LEFT truncate), eval_bc_gpt2.py:100-104 */
     int32_t max_new_tokens;    /* GenerationConfig.max_new_tokens, eval_bc_gpt2.py:90-95 */
     int32_t max_turns;         /* upper bound on env steps per episode (6 Wordle, max_steps+1 Maze) */
-    int32_t reserved[3];
+    int32_t kv_pages;          /* pages (32 positions each, per layer and tower) of the paged KV cache; 0 = max_envs * ceil((max_input_length +
+                                  max_new_tokens) / 32): every env at full length.  A smaller pool fits more envs per GPU when episodes stay
+                                  short; a batch that runs out of pages fails with an error (lmrl_kv_stats reports the use) */
+    int32_t reserved[2];
 } lmrl_config;
 
 typedef struct lmrl_gpt2_dims {
@@ -347,6 +350,9 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
  * Unknown names fail.  Changing a switch drops the captured rollout graph. */
 int lmrl_set_option(lmrl_engine* e, const char* name, int32_t value);
 int lmrl_get_option(lmrl_engine* e, const char* name, int32_t* value);
+
+/* paged KV cache: pages handed out since the current batch started, pool capacity, positions per page; fails if the pool overflowed */
+int lmrl_kv_stats(lmrl_engine* e, int32_t* pages_in_use, int32_t* pages_total, int32_t* page_positions);
 
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);

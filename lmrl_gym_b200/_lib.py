@@ -18,7 +18,7 @@ class LmrlError(RuntimeError):
 
 class lmrl_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_envs", C.c_int32), ("max_input_length", C.c_int32),
-                ("max_new_tokens", C.c_int32), ("max_turns", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("max_new_tokens", C.c_int32), ("max_turns", C.c_int32), ("kv_pages", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class lmrl_gpt2_dims(C.Structure):
@@ -135,6 +135,7 @@ SYMBOLS = {
     "lmrl_set_use_pdl": (C.c_int, [_V, _I]),
     "lmrl_set_option": (C.c_int, [_V, C.c_char_p, _I]),
     "lmrl_get_option": (C.c_int, [_V, C.c_char_p, _V]),
+    "lmrl_kv_stats": (C.c_int, [_V, _V, _V, _V]),
     "lmrl_launch_count": (C.c_int64, [_V, _I]),
     "lmrl_set_gemm_impl": (C.c_int, [_V, _I]),
     "lmrl_test_gemm_host": (C.c_int, [_V, _I, _I, _I, _I, _V, _V, _V, _V]),

@@ -34,11 +34,12 @@ struct GemmArgs {
     // EPI_GELU / EPI_QKV(q)
     __nv_bfloat16* out;          // [M, N] (GELU) or [M, d] (QKV)
     // EPI_QKV
-    __nv_bfloat16* kcache;       // this layer: [B, H, Tcap, 64]
+    __nv_bfloat16* kcache;       // this layer's page pool: [n_pages, H, 32, 64] (see KvPages in gpt2_kernels.cuh)
     __nv_bfloat16* vcache;
     const int* row_env;
     const int* row_pos;
-    int d_model, n_head, t_cap;
+    const int* kv_table;         // [B][kv_ppe] page of (env, position / 32)
+    int d_model, n_head, kv_ppe;
     // EPI_SAMPLE
     unsigned long long* best;    // [rows] packed (ordered score << 32 | ~col)
     const uint64_t* row_key;     // [rows] per-row sampling key
@@ -150,7 +151,8 @@ __device__ __forceinline__ void epi_store(const GemmArgs& g, int row, int col, f
             const int e = g.row_env[row], p = g.row_pos[row];
             const int head = c >> 6, dd = c & 63;
             __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
-            *reinterpret_cast<__nv_bfloat162*>(cache + (((size_t)e * g.n_head + head) * g.t_cap + p) * 64 + dd) = v;
+            const int page = g.kv_table[(size_t)e * g.kv_ppe + (p >> 5)];
+            *reinterpret_cast<__nv_bfloat162*>(cache + (((size_t)page * g.n_head + head) * 32 + (p & 31)) * 64 + dd) = v;
         }
     }
 }

@@ -166,12 +166,15 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
     uint32_t rr[2][32];
     tmem_ld_32x32b_x32_issue(t_addr + c_beg, rr[0]);
     if (EPI == EPI_QKV && n0 >= g.d_model) {
-        // K / V tile: scatter this thread's row segment into the KV slab at (env, pos)
+        // K / V tile: scatter this thread's row segment into the KV page of (env, pos)
         const bool live = row < M;
         const int part = n0 / g.d_model;                                   // 1 = K, 2 = V (tiles never straddle: d % BN == 0)
         __nv_bfloat16* cache = part == 1 ? g.kcache : g.vcache;
-        size_t base_off = 0;
-        if (live) base_off = ((size_t)g.row_env[row] * g.n_head * g.t_cap + (size_t)g.row_pos[row]) * 64;
+        size_t base_off = 0;                                               // (page, head 0, position inside the page)
+        if (live) {
+            const int pos = g.row_pos[row];
+            base_off = ((size_t)g.kv_table[(size_t)g.row_env[row] * g.kv_ppe + (pos >> 5)] * g.n_head * 32 + (size_t)(pos & 31)) * 64;
+        }
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
             const int c0 = c_beg + 32 * ci;
@@ -180,7 +183,7 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
             const uint32_t* r = rr[ci & 1];
             if (live) {
                 const int c = n0 + c0 - part * g.d_model;                  // column inside K (or V): head = c / 64
-                __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * g.t_cap * 64 + (c & 63);
+                __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * (32 * 64) + (c & 63);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 b0 = tc_bias4(g, sbias, n0, c0 + 8 * j), b1 = tc_bias4(g, sbias, n0, c0 + 8 * j + 4);

@@ -27,7 +27,7 @@ struct TowerDev {
     __nv_bfloat16 *wte = nullptr, *wpe = nullptr;
     float *lnf_g = nullptr, *lnf_b = nullptr;
     std::vector<LayerDev> layers;
-    __nv_bfloat16* kv = nullptr;      // [L][2][B][H][t_cap][64]
+    __nv_bfloat16* kv = nullptr;      // [L][2][n_pages][H][KV_PAGE][64] page pools (one page table for all layers and towers: Gpt2Dev::kvp)
 };
 
 // Q heads of the value-perturbed policy: MLPHead = dense2(relu(dense1(h))) (heads/mlp_head.py:139-148), one or two of them
@@ -94,6 +94,7 @@ struct Gpt2Dev {
     ValueHeadsDev vh[2];              // head sets of lmrl_forward_host: 0 online, 1 target
     int policy_kind = 0;              // 0 = LM policy (logits of tower 0); 1 = value-perturbed (pi_beta + beta * min q); 2 = beta * min q alone (pi_beta None)
     size_t kv_layer_stride = 0;       // elements between layers (covers K and V)
+    KvPages kvp{};                    // page table + allocator of the paged KV cache (gpt2_kernels.cuh)
     // activations
     float* x = nullptr;
     // xl: [B_pad][3 d] = [final-LN hidden of tower 0 | beta*relu(dense1) of Q head 1 | of Q head 2] (A operand of the sampler);
@@ -230,9 +231,10 @@ __global__ void log_turn_kernel(int n, int max_turns, GenDev gen, StepOut step,
 }
 
 // ---- kernel microbenchmark helpers (lmrl_bench_kernels): synthetic row map + random activations ----------------------
-__global__ void bench_rows_kernel(int M, int rpe, int ctx, int n_slots, RowsDev rows) {
+__global__ void bench_rows_kernel(int M, int rpe, int ctx, int n_slots, RowsDev rows, KvPages kv) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r == 0) { *rows.M = M; *rows.n_slots = n_slots; }
+    if (r < n_slots * kv.ppe) kv.table[r] = r % kv.n_pages;          // env e owns pages [e * ppe, (e + 1) * ppe)
     if (r >= M) return;
     const int e = r / rpe, i = r - e * rpe;
     rows.row_env[r] = e; rows.row_pos[r] = ctx - rpe + i; rows.row_tok[r] = (r * 7919) % 50000;
@@ -462,15 +464,15 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
         GemmArgs a{};
         a.A = Ln.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = Ln.rows.M;
         a.out = Ln.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
-        a.row_env = Ln.rows.row_env; a.row_pos = Ln.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+        a.row_env = Ln.rows.row_env; a.row_pos = Ln.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.kv_table = G.kvp.table; a.kv_ppe = G.kvp.ppe;
         if (launch_gemm<EPI_QKV>(e, a, a.N, 0, Ln.m_cap, a.N, 0)) return -1;
         // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
         if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
         if (mode == 0)
-            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, attp_grid(n_env, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
+            LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, attp_grid(n_env, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
                                                                                           0.125f * 1.4426950408889634f, G.attn_wide, Ln.att));
         else
-            LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.t_cap,
+            LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
                                                                                              0.125f, Ln.att));
         GemmArgs p{};
         p.A = Ln.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = Ln.rows.M; p.resid = Ln.x;
@@ -504,10 +506,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     const int ew_blocks = G.sm_count * 8;
     e->cur_pass_slot = -1;
     e->cur_mode = mode;
-    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, Ln.e0, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows));
+    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, Ln.e0, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows, G.kvp));
     note_pass_counts(e);
     if (mode == 0)
-        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows));
+        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows, G.kvp));
     // towers of this policy: 0 = LM policy; 0 and 1 = pi_beta + value base (kind 1); 1 alone = value base without pi_beta (kind 2)
     const int t_first = G.policy_kind == 2 ? 1 : 0, t_last = G.policy_kind >= 1 ? 1 : 0;
     LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[t_first].wte, G.tw[t_first].wpe, D.d_model, Ln.rows, Ln.x));
@@ -607,7 +609,15 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     G.t_cap = (max_in + max_new + 7) / 8 * 8;
     G.stream_cap = max_in + MAX_LINE_TOKENS;
     G.m_cap = ((size_t)B * max_in + 127) / 128 * 128;
-    G.kv_layer_stride = (size_t)2 * B * D.d_model * G.t_cap;
+    // paged KV: pages of KV_PAGE positions; the pool defaults to every env at full length (it can never run out), lmrl_config.kv_pages
+    // sizes it for the lengths a workload really reaches (the row builder raises an error flag when the pool is exhausted)
+    G.kvp.ppe = (G.t_cap + KV_PAGE - 1) / KV_PAGE;
+    LMRL_CHECK(G.kvp.ppe <= 32, "max_input_length + max_new_tokens = %d exceeds %d KV positions per env", G.t_cap, 32 * KV_PAGE);
+    G.kvp.n_pages = e->cfg.kv_pages > 0 ? e->cfg.kv_pages : B * G.kvp.ppe;
+    LMRL_CHECK(G.kvp.n_pages >= G.kvp.ppe, "lmrl_config.kv_pages = %d is smaller than one env's %d pages", G.kvp.n_pages, G.kvp.ppe);
+    if (e->alloc(&G.kvp.table, (size_t)B * G.kvp.ppe) || e->alloc(&G.kvp.n_alloc, 1) || e->alloc(&G.kvp.overflow, 1)) return -1;
+    LMRL_CUDA(cudaMemsetAsync(G.kvp.table, 0xFF, sizeof(int) * (size_t)B * G.kvp.ppe, e->stream));
+    G.kv_layer_stride = (size_t)2 * G.kvp.n_pages * D.d_model * KV_PAGE;
     if (e->alloc(&G.x, (size_t)G.m_cap * D.d_model) || e->alloc(&G.xn, (size_t)G.m_cap * D.d_model) ||
         e->alloc(&G.q, (size_t)G.m_cap * D.d_model) || e->alloc(&G.att, (size_t)G.m_cap * D.d_model) ||
         e->alloc(&G.h, (size_t)G.m_cap * D.d_ff) || e->alloc(&G.xl, (size_t)((B + 127) / 128 * 128) * 3 * D.d_model) ||
@@ -843,6 +853,17 @@ int lmrl_set_policy_kind(lmrl_engine* e, int32_t kind) {
     return 0;
 }
 
+// after a stream synchronisation: turn the allocator's overflow flag into an error
+static int kv_check_overflow(lmrl_engine* e) {
+    Gpt2Dev& G = *e->gpt2;
+    int h[2] = {0, 0};
+    LMRL_CUDA(cudaMemcpy(&h[0], G.kvp.overflow, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!h[0]) return 0;
+    LMRL_CUDA(cudaMemcpy(&h[1], G.kvp.n_alloc, sizeof(int), cudaMemcpyDeviceToHost));
+    return lmrl::fail("paged KV cache exhausted: the batch asked for %d pages of %d positions, the pool has %d (lmrl_config.kv_pages); results of this call are invalid",
+                      h[1], KV_PAGE, G.kvp.n_pages);
+}
+
 static int load_prompts(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n) {
     Gpt2Dev& G = *e->gpt2;
     LMRL_CHECK(n > 0 && n <= e->cfg.max_envs, "batch of %d rows exceeds engine capacity %d", n, e->cfg.max_envs);
@@ -859,6 +880,7 @@ static int load_prompts(lmrl_engine* e, const int32_t* tokens, const int32_t* n_
                                 sizeof(int32_t) * max_in, n, cudaMemcpyHostToDevice, e->stream));
     LMRL_CUDA(cudaMemcpyAsync(G.stream.len, lens.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     LMRL_CUDA(cudaMemsetAsync(G.stream.kv_len, 0, sizeof(int32_t) * n, e->stream));
+    kv_reset_kernel<<<(e->cfg.max_envs * G.kvp.ppe + 255) / 256, 256, 0, e->stream>>>(G.kvp, e->cfg.max_envs);      // a new batch: every KV page is free again
     LMRL_CUDA(cudaStreamSynchronize(e->stream));   // host staging vectors die at return
     return 0;
 }
@@ -883,7 +905,7 @@ int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_t
     LMRL_CUDA(cudaMemcpyAsync(out_tokens, G.gen.tok, sizeof(int32_t) * (size_t)n * e->cfg.max_new_tokens, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaMemcpyAsync(out_len, G.gen.len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return kv_check_overflow(e);
 }
 
 int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok, int32_t pitch, int32_t n, float* logits) {
@@ -968,6 +990,7 @@ int lmrl_score_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok,
     std::vector<float> lp(n_score);
     LMRL_CUDA(cudaMemcpyAsync(lp.data(), G.lp_out, sizeof(float) * n_score, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    if (kv_check_overflow(e)) return -1;
     for (int j = 0; j < n_score; ++j) logprob_sum[owner[j]] += lp[j];          // fp32 sum in token order, as .sum(axis=0) of the reference
     if (token_logprobs) memcpy(token_logprobs, lp.data(), sizeof(float) * n_score);
     return 0;
@@ -1101,9 +1124,9 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
             e->cur_pass_slot = -1;
             e->cur_mode = 0;
             LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (nc + 255) / 256, 256, 0, st, nc, G.gen));
-            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp));
             note_pass_counts(e);
-            LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows));
+            LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp));
             LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
             if (tower_layers(e, T, 0, nc)) return -1;
             if (want_lp || need_mlp || need_lin_q)
@@ -1142,6 +1165,7 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
                 if (outs[k]) { host[k].resize(rows); LMRL_CUDA(cudaMemcpyAsync(host[k].data(), dev[k], sizeof(float) * rows, cudaMemcpyDeviceToHost, st)); }
             LMRL_CUDA(cudaStreamSynchronize(st));
             LMRL_CUDA(cudaGetLastError());
+            if (kv_check_overflow(e)) return -1;
             for (int i = i0, r = 0; i < i1; ++i)
                 for (int t = 0; t < n_tok[i]; ++t, ++r) {
                     const bool has_next = t + 1 < n_tok[i];
@@ -1184,6 +1208,7 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
                                                                            G.episode_key, G.ep_return, G.ep_length, G.ep_done));
         LMRL_LAUNCH(3, LMRL_K(maze_init_stream_kernel, (n + 127) / 128, 128, 0, st, e->maze, G.stream, n));
     }
+    LMRL_LAUNCH(2, LMRL_K(kv_reset_kernel, (e->cfg.max_envs * G.kvp.ppe + 255) / 256, 256, 0, st, G.kvp, e->cfg.max_envs));     // a new batch: every KV page is free again
     ActionSrc src{};
     src.tokens = G.gen.tok; src.ntokens = G.gen.len; src.tpitch = G.gen.max_new;
     // two half-batch lanes on two streams (see struct Lane); not under the per-launch profiler (its events live on one stream) and not
@@ -1297,6 +1322,18 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable) {
     return 0;
 }
 
+int lmrl_kv_stats(lmrl_engine* e, int32_t* pages_in_use, int32_t* pages_total, int32_t* page_positions) {
+    LMRL_CHECK(e && e->gpt2, "lmrl_kv_stats: no GPT-2 parameters loaded");
+    LMRL_CUDA(cudaSetDevice(e->device));
+    LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    int used = 0;
+    LMRL_CUDA(cudaMemcpy(&used, e->gpt2->kvp.n_alloc, sizeof(int), cudaMemcpyDeviceToHost));
+    if (pages_in_use) *pages_in_use = std::min(used, e->gpt2->kvp.n_pages);
+    if (pages_total) *pages_total = e->gpt2->kvp.n_pages;
+    if (page_positions) *page_positions = KV_PAGE;
+    return kv_check_overflow(e);
+}
+
 static int* option_slot(lmrl::Gpt2Dev& G, const char* name) {
     if (!strcmp(name, "fuse_ln")) return &G.fuse_ln;
     if (!strcmp(name, "attn_wide")) return &G.attn_wide;
@@ -1345,7 +1382,7 @@ int lmrl_rollout_host(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds, c
     if (rollout_run(e, env_kind, opt_pos != nullptr, n, *s)) return -1;
     if (rollout_export(e, n, out, cudaMemcpyDeviceToHost)) return -1;
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return kv_check_overflow(e);
 }
 
 int lmrl_rollout_dev(lmrl_engine* e, int32_t env_kind, const uint64_t* seeds_dev, const int32_t* opt_pos_dev, int32_t n,
@@ -1473,7 +1510,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     const int rpe = M <= B ? 1 : M / B, n_slots = M <= B ? M : B;
     LMRL_CHECK(ctx >= rpe && ctx <= G.t_cap && iters > 0, "lmrl_bench_kernels: ctx=%d must be in [%d, %d]", ctx, rpe, G.t_cap);
     cudaStream_t st = e->stream;
-    bench_rows_kernel<<<(M + 255) / 256, 256, 0, st>>>(M, rpe, ctx, n_slots, G.rows);
+    bench_rows_kernel<<<(std::max(M, n_slots * G.kvp.ppe) + 255) / 256, 256, 0, st>>>(M, rpe, ctx, n_slots, G.rows, G.kvp);
     bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.xn, (size_t)M * D.d_model, 0x1234u, 1.0f);
     bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.att, (size_t)M * D.d_model, 0x2345u, 1.0f);
     bench_fill_bf16_kernel<<<1024, 256, 0, st>>>(G.q, (size_t)M * D.d_model, 0x3456u, 1.0f);
@@ -1485,7 +1522,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     GemmArgs a{};
     a.A = G.xn; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
     a.out = G.q; a.kcache = G.tw[0].kv; a.vcache = a.kcache + G.kv_layer_stride / 2;
-    a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+    a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.kv_table = G.kvp.table; a.kv_ppe = G.kvp.ppe;
     GemmArgs p{};
     p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
     GemmArgs f{};
@@ -1517,10 +1554,10 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                 case 4: rc = launch_gemm<EPI_SAMPLE>(e, h, D.n_vocab, 1, xl_rows, G.v_pad, 4, hx); break;
                 case 5:
                     if (rpe > 1)
-                        LMRL_K(attention_prefill_kernel, attp_grid(n_slots, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap,
+                        LMRL_K(attention_prefill_kernel, attp_grid(n_slots, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp,
                                                                                       0.125f * 1.4426950408889634f, G.attn_wide, G.att);
                     else
-                        LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f, G.att);
+                        LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp, 0.125f, G.att);
                     break;
                 case 6: LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, G.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, G.rows.M, nullptr, G.xn, D.d_model); break;
                 case 7: LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[0].wte, G.tw[0].wpe, D.d_model, G.rows, G.x); break;

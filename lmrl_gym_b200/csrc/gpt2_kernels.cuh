@@ -38,13 +38,46 @@ struct GenDev {
     int eos_id;
 };
 
+// ---- paged KV cache ---------------------------------------------------------------------------------------------------
+// The K / V of one layer live in a pool of pages of KV_PAGE positions, [n_pages][n_head][KV_PAGE][64] bf16 each for K and for V
+// (4 KB contiguous per (page, head)): position p of env e is row (p % KV_PAGE) of page table[e][p / KV_PAGE].  ONE table and one
+// allocator serve every layer and every tower (they all cache the same (env, position) pairs).  Pages are handed out on the
+// device when the row builder assigns a position whose page is still unset (bump counter); an env keeps its pages when its
+// stream rolls back (kv_len rollback after an action, LEFT truncation) and the whole table is cleared when a new batch starts, so
+// memory follows the positions actually reached instead of max_input_length + max_new_tokens per env (reference cache shape:
+// value_rl_base/gpt2/generation.py:123-150, a dense [B, max_length] slab per layer).
+constexpr int KV_PAGE = 32, KV_PAGE_SHIFT = 5;
+struct KvPages {
+    int* table;        // [B][ppe]  page id or -1
+    int* n_alloc;      // [1] pages handed out since the last reset
+    int* overflow;     // [1] set when the pool ran out (the host turns it into an error)
+    int ppe;           // pages per env = ceil(t_cap / KV_PAGE)  (<= 32: a warp holds one env's table, one entry per lane)
+    int n_pages;       // pool capacity
+};
+__device__ __forceinline__ size_t kv_row_off(int page, int n_head, int head, int pos) {
+    return (((size_t)page * n_head + head) * KV_PAGE + (pos & (KV_PAGE - 1))) * 64;
+}
+__device__ __forceinline__ void kv_ensure_page(const KvPages& kv, int e, int pg) {
+    int* slot = kv.table + (size_t)e * kv.ppe + pg;
+    if (*slot < 0) {
+        int id = atomicAdd(kv.n_alloc, 1);
+        if (id >= kv.n_pages) { *kv.overflow = 1; id = 0; }
+        *slot = id;
+    }
+}
+__global__ void kv_reset_kernel(KvPages kv, int n_env) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_env * kv.ppe) kv.table[i] = -1;
+    if (i == 0) { *kv.n_alloc = 0; *kv.overflow = 0; }
+}
+
 // ---- row builder: exclusive scan over envs (single CTA; B <= 16384) ---------------------------------------------
 // mode 0 (prefill): env e contributes stream tokens [kv_len[e], len[e]) if it is not done
 // mode 1 (decode) : env e contributes its last sampled token at position cur[e] if it is still generating
 // e0 / B: the env range of the calling lane (the whole batch: 0 / n)
 __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __restrict__ done, const int32_t* __restrict__ stream_tok,
                                   const int32_t* __restrict__ stream_len, const int32_t* __restrict__ kv_len, int stream_cap,
-                                  GenDev gen, RowsDev rows) {
+                                  GenDev gen, RowsDev rows, KvPages kv) {
     pdl_enter();
     __shared__ int warp_sums[2][32];
     __shared__ int carry[2];
@@ -86,6 +119,7 @@ __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __rest
                 const int p = gen.cur[e];
                 rows.row_env[row0] = e; rows.row_pos[row0] = p; rows.row_tok[row0] = gen.tok[e * gen.max_new + gen.len[e] - 1];
                 gen.cur[e] = p + 1;
+                kv_ensure_page(kv, e, p >> KV_PAGE_SHIFT);                  // the page this row's K / V go to
             }
         }
         __syncthreads();
@@ -100,12 +134,16 @@ __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __rest
 
 // prefill: expand each slot into its rows (one warp per slot); also resets the per-turn generation state
 __global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok, const int32_t* __restrict__ stream_len,
-                                         int32_t* __restrict__ kv_len, int stream_cap, GenDev gen, RowsDev rows) {
+                                         int32_t* __restrict__ kv_len, int stream_cap, GenDev gen, RowsDev rows, KvPages kv) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= *rows.n_slots) return;
     const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot], p0 = kv_len[e];
+    {   // pages of positions [p0, p0 + n): one lane per page (ppe <= 32)
+        const int pg = (p0 >> KV_PAGE_SHIFT) + lane;
+        if (pg <= ((p0 + n - 1) >> KV_PAGE_SHIFT)) kv_ensure_page(kv, e, pg);
+    }
     for (int i = lane; i < n; i += 32) {
         rows.row_env[r0 + i] = e; rows.row_pos[r0 + i] = p0 + i; rows.row_tok[r0 + i] = stream_tok[(size_t)e * stream_cap + p0 + i];
     }
@@ -287,7 +325,7 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& u, float f[8]) {
 
 __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                       const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
-                                                                      int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ out) {
+                                                                      int d_model, KvPages kv, float scale, __nv_bfloat16* __restrict__ out) {
     pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, s = lane & 7;
@@ -295,8 +333,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv
     for (int w = blockIdx.x * ATT_WARPS + warp; w < total; w += gridDim.x * ATT_WARPS) {
         const int slot = w / n_head, head = w - slot * n_head;
         const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
-        const uint4* gK = reinterpret_cast<const uint4*>(kcache + ((size_t)e * n_head + head) * t_cap * 64) + s;   // + j*8 per key
-        const uint4* gV = reinterpret_cast<const uint4*>(vcache + ((size_t)e * n_head + head) * t_cap * 64) + s;
+        // this env's page table, one entry per lane; a step of 16 keys lies inside one page (KV_PAGE = 32)
+        const int my_page = lane < kv.ppe ? kv.table[(size_t)e * kv.ppe + lane] : 0;
+        const uint4* gK = reinterpret_cast<const uint4*>(kcache) + s;       // + kv_row_off(page, head, j) / 8 per key
+        const uint4* gV = reinterpret_cast<const uint4*>(vcache) + s;
         for (int i = 0; i < n; ++i) {
             const int r = r0 + i, nkeys = rows.row_pos[r] + 1;
             float qf[8];
@@ -310,12 +350,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int j0 = 0; j0 < nkeys; j0 += 16) {
                 uint4 kk[4], vv[4];
+                const int page = __shfl_sync(0xFFFFFFFFu, my_page, j0 >> KV_PAGE_SHIFT);
+                const size_t pbase = (((size_t)page * n_head + head) * KV_PAGE + (j0 & (KV_PAGE - 1))) * 8;      // in uint4 units (8 per key)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int j = j0 + 4 * u + g;
                     const bool ok = j < nkeys;
-                    kk[u] = ok ? __ldg(gK + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
-                    vv[u] = ok ? __ldg(gV + (size_t)j * 8) : make_uint4(0, 0, 0, 0);
+                    kk[u] = ok ? __ldg(gK + pbase + (size_t)(4 * u + g) * 8) : make_uint4(0, 0, 0, 0);
+                    vv[u] = ok ? __ldg(gV + pbase + (size_t)(4 * u + g) * 8) : make_uint4(0, 0, 0, 0);
                 }
                 float sc[4];
                 float cm = -INFINITY;
@@ -407,24 +449,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // one pass over the keys for query rows [rb, rb + 16 * MT) of a slot (rows beyond n are computed on zero queries and not stored)
 template <int MT>
 __device__ __forceinline__ void attp_rows(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ gK, const __nv_bfloat16* __restrict__ gV,
-                                          int r0, int n, int rb, int p0, int head, int d_model, int t_cap, float scale_log2e, bool keep,
+                                          int r0, int n, int rb, int p0, int head, int d_model, int n_head, int my_page, float scale_log2e, bool keep,
                                           uint64_t pol_last, uint32_t sbase, int lane, __nv_bfloat16* __restrict__ out) {
     const int g = lane >> 2, t = lane & 3;
     const int nr = min(16 * MT, n - rb);                   // live query rows in this pass
     const int n_keys = p0 + rb + nr;                       // keys visible to the last live row
-    auto stage = [&](int buf, int k0) {                    // 32 keys of K and V: 2 x 256 chunks of 16 B, 16 per lane
+    auto stage = [&](int buf, int k0) {                    // 32 keys of K and V = one KV page: 2 x 256 chunks of 16 B, 16 per lane
         const uint32_t sK = sbase + buf * (2 * ATTP_KEYS * 128), sV = sK + ATTP_KEYS * 128;
+        const int page = __shfl_sync(0xFFFFFFFFu, my_page, k0 >> KV_PAGE_SHIFT);     // keys past the last live one stay inside the page (masked)
+        const size_t pbase = ((size_t)page * n_head + head) * KV_PAGE * 64;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
             const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
-            const int kk = min(k0 + key, t_cap - 1);
             if (keep) {
-                cp_async16_hint(sK + off, gK + (size_t)kk * 64 + ch * 8, pol_last);
-                cp_async16_hint(sV + off, gV + (size_t)kk * 64 + ch * 8, pol_last);
+                cp_async16_hint(sK + off, gK + pbase + (size_t)key * 64 + ch * 8, pol_last);
+                cp_async16_hint(sV + off, gV + pbase + (size_t)key * 64 + ch * 8, pol_last);
             } else {
-                cp_async16(sK + off, gK + (size_t)kk * 64 + ch * 8);
-                cp_async16(sV + off, gV + (size_t)kk * 64 + ch * 8);
+                cp_async16(sK + off, gK + pbase + (size_t)key * 64 + ch * 8);
+                cp_async16(sV + off, gV + pbase + (size_t)key * 64 + ch * 8);
             }
         }
         cp_async_commit();
@@ -564,7 +607,7 @@ __device__ __forceinline__ void attp_rows(const __nv_bfloat16* __restrict__ q, c
 
 __global__ void __launch_bounds__(ATTP_WARPS * 32, ATTP_CTAS_PER_SM) attention_prefill_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                                const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
-                                                                               int d_model, int t_cap, float scale_log2e, int wide,
+                                                                               int d_model, KvPages kv, float scale_log2e, int wide,
                                                                                __nv_bfloat16* __restrict__ out) {
     pdl_enter();
     extern __shared__ __align__(128) unsigned char attp_smem[];
@@ -576,14 +619,13 @@ __global__ void __launch_bounds__(ATTP_WARPS * 32, ATTP_CTAS_PER_SM) attention_p
         const int slot = w / n_head, head = w - slot * n_head;
         const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
         const int p0 = rows.row_pos[r0];
-        const __nv_bfloat16* gK = kcache + ((size_t)e * n_head + head) * t_cap * 64;
-        const __nv_bfloat16* gV = vcache + ((size_t)e * n_head + head) * t_cap * 64;
+        const int my_page = lane < kv.ppe ? kv.table[(size_t)e * kv.ppe + lane] : 0;     // this env's page table, one entry per lane
         for (int rb = 0; rb < n;) {
             if (wide && n - rb > 16) {
-                attp_rows<2>(q, gK, gV, r0, n, rb, p0, head, d_model, t_cap, scale_log2e, rb + 32 < n, pol_last, sbase, lane, out);
+                attp_rows<2>(q, kcache, vcache, r0, n, rb, p0, head, d_model, n_head, my_page, scale_log2e, rb + 32 < n, pol_last, sbase, lane, out);
                 rb += 32;
             } else {
-                attp_rows<1>(q, gK, gV, r0, n, rb, p0, head, d_model, t_cap, scale_log2e, rb + 16 < n, pol_last, sbase, lane, out);
+                attp_rows<1>(q, kcache, vcache, r0, n, rb, p0, head, d_model, n_head, my_page, scale_log2e, rb + 16 < n, pol_last, sbase, lane, out);
                 rb += 16;
             }
         }

@@ -198,7 +198,7 @@ __device__ __forceinline__ float attb_dot_rs(const uint4 (&a)[8], const __nv_bfl
 }
 __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                    const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout, RowsDev rows,
-                                                                   int n_head, int d_model, int t_cap, float scale, __nv_bfloat16* __restrict__ dqkv) {
+                                                                   int n_head, int d_model, KvPages kv, float scale, __nv_bfloat16* __restrict__ dqkv) {
     extern __shared__ __align__(16) unsigned char ab_raw[];
     const int slot = blockIdx.x / n_head, head = blockIdx.x % n_head;
     if (slot >= *rows.n_slots) return;
@@ -211,15 +211,15 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_kernel(const __nv_bf
     float* st_l = st_m + T;
     float* st_D = st_l + T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATTB_THREADS >> 5;
-    const __nv_bfloat16* Kb = kcache + ((size_t)env * n_head + head) * t_cap * 64;
-    const __nv_bfloat16* Vb = vcache + ((size_t)env * n_head + head) * t_cap * 64;
+    const int* ptab = kv.table + (size_t)env * kv.ppe;                       // position r of the sequence: row r % 32 of page ptab[r / 32]
+    auto kv_off = [&](int r) { return kv_row_off(ptab[r >> KV_PAGE_SHIFT], n_head, head, r); };
     for (int i = tid; i < T * 8; i += ATTB_THREADS) {                        // one 16-byte chunk per thread per step
         const int r = i >> 3, w = i & 7;
         const size_t grow = (size_t)(r0 + r) * d_model + head * 64 + 8 * w;
         reinterpret_cast<uint4*>(Qs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(q + grow);
         reinterpret_cast<uint4*>(Os + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(dout + grow);
-        reinterpret_cast<uint4*>(Ks + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(Kb + (size_t)r * 64 + 8 * w);
-        reinterpret_cast<uint4*>(Vs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(Vb + (size_t)r * 64 + 8 * w);
+        reinterpret_cast<uint4*>(Ks + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(kcache + kv_off(r) + 8 * w);
+        reinterpret_cast<uint4*>(Vs + (size_t)r * ATTB_PITCH)[w] = *reinterpret_cast<const uint4*>(vcache + kv_off(r) + 8 * w);
     }
     __syncthreads();
     // ---- phase 1: dQ and the row statistics (warp per query row, lanes over keys)
@@ -361,7 +361,7 @@ __device__ __forceinline__ void attb_mma_rows(const uint32_t (&a)[4], uint32_t t
 }
 __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                                                                        const __nv_bfloat16* __restrict__ vcache, const __nv_bfloat16* __restrict__ dout,
-                                                                       const __nv_bfloat16* __restrict__ att, RowsDev rows, int n_head, int d_model, int t_cap,
+                                                                       const __nv_bfloat16* __restrict__ att, RowsDev rows, int n_head, int d_model, KvPages kv,
                                                                        float scale, __nv_bfloat16* __restrict__ dqkv) {
     extern __shared__ __align__(16) unsigned char ab_raw[];
     const int slot = blockIdx.x / n_head, head = blockIdx.x % n_head;
@@ -377,8 +377,8 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_mma_kernel(const __n
     float* st_D = st_l + Tp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = ATTB_THREADS >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const __nv_bfloat16* Kb = kcache + ((size_t)env * n_head + head) * t_cap * 64;
-    const __nv_bfloat16* Vb = vcache + ((size_t)env * n_head + head) * t_cap * 64;
+    const int* ptab = kv.table + (size_t)env * kv.ppe;                       // position r of the sequence: row r % 32 of page ptab[r / 32]
+    auto kv_off = [&](int r) { return kv_row_off(ptab[r >> KV_PAGE_SHIFT], n_head, head, r); };
     for (int i = tid; i < Tp * 8; i += ATTB_THREADS) {
         const int r = i >> 3, w = i & 7;
         uint4 vq = make_uint4(0, 0, 0, 0), vo = vq, vk = vq, vv = vq;
@@ -386,8 +386,8 @@ __global__ void __launch_bounds__(ATTB_THREADS, 1) attn_bwd_mma_kernel(const __n
             const size_t grow = (size_t)(r0 + r) * d_model + head * 64 + 8 * w;
             vq = *reinterpret_cast<const uint4*>(q + grow);
             vo = *reinterpret_cast<const uint4*>(dout + grow);
-            vk = *reinterpret_cast<const uint4*>(Kb + (size_t)r * 64 + 8 * w);
-            vv = *reinterpret_cast<const uint4*>(Vb + (size_t)r * 64 + 8 * w);
+            vk = *reinterpret_cast<const uint4*>(kcache + kv_off(r) + 8 * w);
+            vv = *reinterpret_cast<const uint4*>(vcache + kv_off(r) + 8 * w);
         }
         reinterpret_cast<uint4*>(Qs + (size_t)r * ATTB_PITCH)[w] = vq;
         reinterpret_cast<uint4*>(Os + (size_t)r * ATTB_PITCH)[w] = vo;
@@ -759,10 +759,10 @@ static int train_layer_forward(lmrl_engine* e, int l, int n_seq, bool with_fc2) 
     GemmArgs a{};
     a.A = Tr.xn1; a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = G.rows.M;
     a.out = G.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
-    a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.t_cap = G.t_cap;
+    a.row_env = G.rows.row_env; a.row_pos = G.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.kv_table = G.kvp.table; a.kv_ppe = G.kvp.ppe;
     if (launch_gemm<EPI_QKV>(e, a, a.N, 0, (size_t)Tr.m_cap, a.N, 0)) return -1;
     LMRL_K(attention_prefill_kernel, attp_grid(n_seq, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q,
-           a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.t_cap, 0.125f * 1.4426950408889634f, G.attn_wide, G.att);
+           a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp, 0.125f * 1.4426950408889634f, G.attn_wide, G.att);
     GemmArgs p{};
     p.A = G.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = G.rows.M; p.resid = G.x;
     if (launch_gemm<EPI_RESID>(e, p, p.N, 0, G.m_cap, p.N, 1)) return -1;
@@ -842,9 +842,9 @@ static int train_layer_backward(lmrl_engine* e, int l, int n_seq, int Mp, const 
         }
         const char* sel = getenv("LMRL_ATTN_BWD");                        // "cuda" selects the CUDA-core kernel (cross-check in the tests)
         if (sel && sel[0] == 'c')
-            attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.t_cap, 0.125f, Tr.dqkv);
+            attn_bwd_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.rows, D.n_head, d, G.kvp, 0.125f, Tr.dqkv);
         else
-            attn_bwd_mma_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.att, G.rows, D.n_head, d, G.t_cap, 0.125f,
+            attn_bwd_mma_kernel<<<n_seq * D.n_head, ATTB_THREADS, smem, st>>>(G.q, kc, kc + G.kv_layer_stride / 2, Tr.datt, G.att, G.rows, D.n_head, d, G.kvp, 0.125f,
                                                                               Tr.dqkv);
     }
     // ---- attn.c_attn: qkv = xn1 . Wqkv + b
@@ -940,8 +940,8 @@ static int policy_grad_impl(lmrl_engine* e, const int32_t* tokens, const int32_t
     mark("start");
     // ---- forward, saving the residual stream before every layer
     LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen);
-    LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, n, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
-    LMRL_K(fill_prefill_rows_kernel, (n * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows);
+    LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, n, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp);
+    LMRL_K(fill_prefill_rows_kernel, (n * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp);
     LMRL_K(embed_kernel, ew, 256, 0, st, T.wte, T.wpe, d, G.rows, G.x);
     const size_t xbytes = sizeof(float) * (size_t)M * d, xstride = (size_t)Tr.m_cap * d;
     for (int l = 0; l < L; ++l) {

@@ -18,10 +18,11 @@ class Engine:
     ``text_env_eval`` / ``interact_environment`` (lmrl_gym_b200/environment.py)."""
 
     def __init__(self, max_envs: int, device: int = 0, max_input_length: int = 256, max_new_tokens: int = 6,
-                 max_turns: int = 6, tokenizer: Optional[ByteTokenizer] = None):
+                 max_turns: int = 6, tokenizer: Optional[ByteTokenizer] = None, kv_pages: int = 0):
+        """``kv_pages``: size of the paged KV cache in pages of 32 positions (0 = every env at full length, the default)."""
         self.lib = _lib.load()
         self.cfg = _lib.lmrl_config(device=device, max_envs=max_envs, max_input_length=max_input_length,
-                                    max_new_tokens=max_new_tokens, max_turns=max_turns)
+                                    max_new_tokens=max_new_tokens, max_turns=max_turns, kv_pages=kv_pages)
         self.handle = C.c_void_p()
         check(self.lib.lmrl_create(C.byref(self.cfg), C.byref(self.handle)))
         self.max_envs = max_envs
@@ -125,6 +126,12 @@ class Engine:
         out = np.zeros(8, dtype=np.float32)
         check(self.lib.lmrl_bench_kernels(self.handle, int(M), int(ctx), int(iters), ptr(out)))
         return dict(zip(("qkv", "proj", "fc", "fc2", "head", "attention", "layernorm", "embed"), out.tolist()))
+
+    def kv_stats(self):
+        """Paged KV cache: (pages in use since the current batch started, pool capacity, positions per page); raises if the pool overflowed."""
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(self.lib.lmrl_kv_stats(self.handle, C.addressof(a), C.addressof(b), C.addressof(c)))
+        return int(a.value), int(b.value), int(c.value)
 
     def sync(self):
         check(self.lib.lmrl_sync(self.handle))
