@@ -9,6 +9,7 @@
 #include "gpt2_kernels.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_tcgen05_2cta.cuh"
+#include "gemv.cuh"
 #include <map>
 #include <tuple>
 
@@ -382,6 +383,42 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
     return rc;
 }
 
+// weight-streaming GEMV (gemv.cuh) of a small-batch decode pass: R = rows staged per CTA (1, 2, 4 or 8 >= the batch's envs)
+template <int EPI, bool LN, int R>
+static int launch_gemv_r(lmrl_engine* e, const GemvArgs& a) {
+    Gpt2Dev& G = *e->gpt2;
+    const size_t smem = (size_t)R * a.K * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        LMRL_CUDA(cudaFuncSetAttribute(gemv_kernel<EPI, R, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GV_MAX_ROWS * 4096 * (int)sizeof(float)));
+        configured = true;
+    }
+    const int n_groups = a.N / GV_COLS;
+    const int grid = std::max(1, std::min((n_groups + GV_WARPS - 1) / GV_WARPS, G.sm_count * 4));
+    LMRL_CUDA(launch_k(G.use_pdl, 1, gemv_kernel<EPI, R, LN>, dim3(grid), dim3(GV_WARPS * 32), smem, G.cur->st, a));
+    return 0;
+}
+template <int EPI, bool LN>
+static int launch_gemv(lmrl_engine* e, const GemvArgs& a, int R, int n_true, int count_kind, int kind) {
+    LMRL_CHECK(a.N % GV_COLS == 0 && a.K % 128 == 0 && a.K <= 4096, "GEMV path: unsupported shape N=%d K=%d", a.N, a.K);
+    if (e->prof_begin(0, 2.0 * (double)n_true * a.K, count_kind, 2 * kind + e->cur_mode)) return -1;
+    int rc;
+    switch (R) {
+        case 1: rc = launch_gemv_r<EPI, LN, 1>(e, a); break;
+        case 2: rc = launch_gemv_r<EPI, LN, 2>(e, a); break;
+        case 4: rc = launch_gemv_r<EPI, LN, 4>(e, a); break;
+        default: rc = launch_gemv_r<EPI, LN, 8>(e, a); break;
+    }
+    e->prof_end();
+    e->launches++;
+    return rc;
+}
+// rows staged by the GEMV path for a decode pass over n_env envs; 0 = the pass takes the tensor-core tiles
+static int gemv_rows(const Gpt2Dev& G, int mode, int n_env) {
+    if (mode != 1 || G.gemv_max_rows <= 0 || n_env > std::min(G.gemv_max_rows, GV_MAX_ROWS) || G.gemm_impl == 0) return 0;
+    return n_env <= 1 ? 1 : n_env <= 2 ? 2 : n_env <= 4 ? 4 : 8;
+}
+
 // every kernel of the rollout path is launched through launch_k so that programmatic dependent launch can be switched on
 #define LMRL_K(kernel, grid, block, smem, st, ...) \
     ::lmrl::launch_k((e && e->gpt2) ? e->gpt2->use_pdl : 0, 1, kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
@@ -457,8 +494,32 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     // ln_2 of this layer rides on the attention-projection GEMM, ln_1 of the next layer on the MLP-projection GEMM (tcgen05
     // one-CTA kernel only); layer 0's ln_1 is the one LayerNorm launch of the pass
     const bool fuse = G.fuse_ln && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
+    const int gv = gemv_rows(G, mode, n_env);
     for (int l = 0; l < D.n_layer; ++l) {
         const LayerDev& L = T.layers[l];
+        if (gv) {
+            // small-batch decode pass: five launches per layer, the two LayerNorms folded into the QKV / FC GEMVs' operand staging
+            __nv_bfloat16* kc = T.kv + (size_t)l * G.kv_layer_stride;
+            GemvArgs a{};
+            a.x_f32 = Ln.x; a.ln_gamma = L.ln1_g; a.ln_beta = L.ln1_b; a.ln_eps = D.ln_eps;
+            a.W = L.w_qkv; a.bias = L.b_qkv; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = Ln.rows.M; a.out = Ln.q;
+            a.kcache = kc; a.vcache = kc + G.kv_layer_stride / 2; a.row_env = Ln.rows.row_env; a.row_pos = Ln.rows.row_pos;
+            a.kv_table = G.kvp.table; a.kv_ppe = G.kvp.ppe; a.d_model = D.d_model; a.n_head = D.n_head;
+            if (launch_gemv<EPI_QKV, true>(e, a, gv, a.N, 0, 0)) return -1;
+            if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
+            LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
+            GemvArgs p{};
+            p.A = Ln.att; p.a_pitch = D.d_model; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = Ln.rows.M; p.resid = Ln.x;
+            if (launch_gemv<EPI_RESID, false>(e, p, gv, p.N, 0, 1)) return -1;
+            GemvArgs f{};
+            f.x_f32 = Ln.x; f.ln_gamma = L.ln2_g; f.ln_beta = L.ln2_b; f.ln_eps = D.ln_eps;
+            f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = Ln.rows.M; f.out = Ln.h;
+            if (launch_gemv<EPI_GELU, true>(e, f, gv, f.N, 0, 2)) return -1;
+            GemvArgs f2{};
+            f2.A = Ln.h; f2.a_pitch = D.d_ff; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = Ln.rows.M; f2.resid = Ln.x;
+            if (launch_gemv<EPI_RESID, false>(e, f2, gv, f2.N, 0, 3)) return -1;
+            continue;
+        }
         if (!fuse || l == 0)
             LMRL_LAUNCH(2, LMRL_K(layernorm_kernel, ew_blocks, 256, 0, st, Ln.x, L.ln1_g, L.ln1_b, D.d_model, D.ln_eps, Ln.rows.M, nullptr, Ln.xn, D.d_model));
         GemmArgs a{};
@@ -519,10 +580,13 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     const size_t xl_rows = score ? (size_t)G.s_cap : Ln.xl_rows;
     const int* head_n = score ? score->n_dev : Ln.rows.n_slots;
     const int* head_gather = score ? score->rows : Ln.rows.slot_last;
+    // small-batch decode pass of the plain LM policy: the final LayerNorm and the LM head + sampler are one GEMV launch
+    const int gv_head = (!score && G.policy_kind == 0) ? gemv_rows(G, mode, n_env) : 0;
     for (int t = t_first; t <= t_last; ++t) {
         const TowerDev& T = G.tw[t];
         if (t > t_first) LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, Ln.rows, Ln.x));
         if (tower_layers(e, T, mode, n_env)) return -1;
+        if (gv_head) break;
         // final LayerNorm of the sampled rows only: tower 0 -> xl[:, 0:d], value tower -> xl1 (MLP Q heads: operand of their first
         // layer) or straight into xl[:, d:2d] (LinearHead Q heads: operand of the head GEMM's second K segment)
         const bool to_xl = t == 0 || G.qh.linear;
@@ -542,6 +606,29 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     }
     if (!score)
         LMRL_LAUNCH(2, LMRL_K(prepare_sample_kernel, (n_env + 255) / 256, 256, 0, st, Ln.rows, G.gen, G.episode_key, turn_of_env, turn_const, s.seed, Ln.row_key, Ln.best));
+    if (gv_head) {
+        GemvArgs hv{};
+        hv.x_f32 = Ln.x; hv.ln_gamma = G.tw[0].lnf_g; hv.ln_beta = G.tw[0].lnf_b; hv.ln_eps = D.ln_eps; hv.gather = head_gather;
+        hv.W = G.tw[0].wte; hv.N = G.v_pad; hv.K = D.d_model; hv.M_dev = head_n;
+        hv.best = filtered ? Ln.best_scratch : Ln.best; hv.row_key = Ln.row_key; hv.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f);
+        hv.do_sample = s.do_sample; hv.n_vocab = D.n_vocab; hv.logits_out = logits_out;
+        if (launch_gemv<EPI_SAMPLE, true>(e, hv, gv_head, D.n_vocab, 1, 4)) return -1;
+        if (filtered) {
+            static bool configured_gv = false;
+            const size_t fs_smem = (size_t)D.n_vocab * sizeof(float);
+            LMRL_CHECK(fs_smem <= 220 * 1024, "top-k / top-p sampling keeps one row of logits in shared memory: n_vocab %d is too large", D.n_vocab);
+            if (!configured_gv) {
+                LMRL_CUDA(cudaFuncSetAttribute(filtered_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fs_smem));
+                configured_gv = true;
+            }
+            LMRL_LAUNCH(2, LMRL_K(filtered_sample_kernel, n_env, FS_THREADS, fs_smem, st, logits_out, D.n_vocab, Ln.rows, Ln.row_key, hv.inv_temp, s.do_sample,
+                                                                                    s.top_k, s.top_p, Ln.best));
+        }
+        LMRL_LAUNCH(2, LMRL_K(finalize_sample_kernel, (n_env + 255) / 256, 256, 0, st, Ln.rows, G.gen, Ln.best));
+        e->cur_pass_slot = -1;
+        LMRL_CUDA(cudaGetLastError());
+        return 0;
+    }
     GemmArgs h{};
     h.A = xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = head_n;
     h.best = filtered ? Ln.best_scratch : Ln.best; h.row_key = Ln.row_key; h.inv_temp = 1.0f / (s.temperature > 0.f ? s.temperature : 1.0f);
@@ -932,7 +1019,7 @@ int lmrl_logits_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_tok
         LMRL_CUDA(cudaMemcpyAsync(logits + (size_t)slot_env[j] * G.dims.n_vocab, G.logits + (size_t)j * G.dims.n_vocab,
                                   sizeof(float) * G.dims.n_vocab, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
-    return 0;
+    return kv_check_overflow(e);
 }
 
 }  // extern "C" (reopened below)
