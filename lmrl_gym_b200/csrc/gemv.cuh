@@ -70,7 +70,17 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
     extern __shared__ __align__(16) float gv_x[];
     pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int M = min(*a.M_dev, R), K = a.K;
+    const int K = a.K;
+    // the weights do not depend on the previous kernel's output: pull this warp's first group of W rows towards L2 while the
+    // activation rows are being staged (the kernel is a chain of dependent latencies at this size, not a bandwidth problem)
+    {
+        const int grp0 = blockIdx.x * GV_WARPS + warp;
+        if (grp0 < a.N / GV_COLS) {
+            const char* w0 = reinterpret_cast<const char*>(a.W + (size_t)grp0 * GV_COLS * K);
+            for (int off = lane * 128; off < GV_COLS * K * 2; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + off));
+        }
+    }
+    const int M = min(*a.M_dev, R);
     if (M <= 0) return;
     // ---- stage the activation rows (zero rows beyond M) ----
     if constexpr (LN) {
@@ -161,9 +171,10 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
                     for (int t = 0; t < 8; ++t) acc[c * R + r] = fmaf(wf[t], xf[r][t], acc[c * R + r]);
             }
         }
-        warp_reduce_many<NV>(acc, lane);
         const int n = n0 + my_c;
-        float val = acc[0] + (a.bias ? __ldg(a.bias + n) : 0.f);
+        const float bias_n = a.bias ? __ldg(a.bias + n) : 0.f;     // issued before the shuffle tree, consumed after it
+        warp_reduce_many<NV>(acc, lane);
+        float val = acc[0] + bias_n;
         if constexpr (EPI == EPI_SAMPLE) {
             if (my_r < M && n < a.n_vocab) {
                 if (a.logits_out && writer) a.logits_out[(size_t)my_r * a.n_vocab + n] = val;

@@ -149,6 +149,13 @@ struct Gpt2Dev {
                    has_opt == o.has_opt && two_lanes == o.two_lanes && temperature == o.temperature && seed == o.seed;
         }
     };
+    // the text path's generate call replays ONE captured decode pass max_new_tokens - 1 times (the turn index is read from device memory,
+    // so the same graph serves every turn of an episode)
+    cudaGraphExec_t decode_graph = nullptr;
+    RolloutKey decode_key{}, decode_warm{};
+    bool decode_warm_valid = false;
+    int64_t decode_graph_launches = 0;
+    int32_t* gen_turn = nullptr;      // [B] turn index of the current generate call
     cudaGraphExec_t graph_exec = nullptr;
     RolloutKey graph_key{}, warm_key{};
     bool warm_valid = false;
@@ -722,7 +729,9 @@ static int gpt2_alloc_state(lmrl_engine* e) {
         e->alloc(&G.stream.is_action, (size_t)B * G.stream_cap) || e->alloc(&G.stream.tok_reward, (size_t)B * G.stream_cap) || e->alloc(&G.stream.truncated, B))
         return -1;
     G.stream.cap = G.stream_cap; G.stream.max_input = max_in;
-    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.best_scratch, B) || e->alloc(&G.episode_key, B) || e->alloc(&G.live, 1)) return -1;
+    if (e->alloc(&G.row_key, B) || e->alloc(&G.best, B) || e->alloc(&G.best_scratch, B) || e->alloc(&G.episode_key, B) || e->alloc(&G.live, 1) ||
+        e->alloc(&G.gen_turn, B))
+        return -1;
     if (e->alloc(&G.ep_return, B) || e->alloc(&G.ep_length, B) || e->alloc(&G.ep_done, B) || e->alloc(&G.step_reward, (size_t)B * T) ||
         e->alloc(&G.step_valid, (size_t)B * T) || e->alloc(&G.step_fb, (size_t)B * T * 5) || e->alloc(&G.step_aux, (size_t)B * T) ||
         e->alloc(&G.act_tokens, (size_t)B * T * max_new) || e->alloc(&G.act_len, (size_t)B * T))
@@ -769,6 +778,7 @@ using namespace lmrl;
 void lmrl_gpt2_free(lmrl_engine* e) {
     if (!e || !e->gpt2) return;
     if (e->gpt2->graph_exec) cudaGraphExecDestroy(e->gpt2->graph_exec);
+    if (e->gpt2->decode_graph) cudaGraphExecDestroy(e->gpt2->decode_graph);
     if (e->gpt2->train) lmrl_train_free(e->gpt2);
     if (e->gpt2->stream_b) cudaStreamDestroy(e->gpt2->stream_b);
     if (e->gpt2->ev_fork) cudaEventDestroy(e->gpt2->ev_fork);
@@ -987,8 +997,41 @@ int lmrl_generate_host(lmrl_engine* e, const int32_t* tokens, const int32_t* n_t
         LMRL_CUDA(cudaStreamSynchronize(e->stream));
     }
     LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, e->stream, n, G.gen));
-    for (int k = 0; k < e->cfg.max_new_tokens; ++k)
-        if (forward_and_sample(e, k == 0 ? 0 : 1, n, nullptr, nullptr, turn, *s, nullptr)) return -1;
+    {
+        std::vector<int32_t> turns(n, turn);
+        LMRL_CUDA(cudaMemcpyAsync(G.gen_turn, turns.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+        LMRL_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    if (forward_and_sample(e, 0, n, nullptr, G.gen_turn, 0, *s, nullptr)) return -1;                 // prefill pass + first token
+    const int n_decode = e->cfg.max_new_tokens - 1;
+    const bool graphable = G.use_graphs && !e->profile && n_decode >= 2;
+    const Gpt2Dev::RolloutKey key{-1, n, s->do_sample, G.policy_kind, G.gemm_impl, G.gemv_max_rows, G.fuse_ln, s->temperature, s->seed, s->top_k, s->top_p};
+    if (graphable && G.decode_graph && G.decode_key == key) {
+        for (int k = 0; k < n_decode; ++k) LMRL_CUDA(cudaGraphLaunch(G.decode_graph, e->stream));
+        e->launches += G.decode_graph_launches * n_decode;
+    } else if (graphable && G.decode_warm_valid && G.decode_warm == key) {
+        // second use of this configuration: capture one decode pass, then replay it for every remaining token
+        if (G.decode_graph) { cudaGraphExecDestroy(G.decode_graph); G.decode_graph = nullptr; }
+        const int64_t before = e->launches;
+        LMRL_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = forward_and_sample(e, 1, n, nullptr, G.gen_turn, 0, *s, nullptr);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t err = cudaStreamEndCapture(e->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return -1; }
+        LMRL_CHECK(err == cudaSuccess && graph, "lmrl_generate: CUDA graph capture of the decode pass failed: %s", cudaGetErrorString(err));
+        G.decode_graph_launches = e->launches - before;
+        e->launches = before;
+        const cudaError_t ierr = cudaGraphInstantiate(&G.decode_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        LMRL_CHECK(ierr == cudaSuccess, "lmrl_generate: cudaGraphInstantiate failed: %s", cudaGetErrorString(ierr));
+        G.decode_key = key;
+        for (int k = 0; k < n_decode; ++k) LMRL_CUDA(cudaGraphLaunch(G.decode_graph, e->stream));
+        e->launches += G.decode_graph_launches * n_decode;
+    } else {
+        if (graphable) { G.decode_warm = key; G.decode_warm_valid = true; }
+        for (int k = 0; k < n_decode; ++k)
+            if (forward_and_sample(e, 1, n, nullptr, G.gen_turn, 0, *s, nullptr)) return -1;
+    }
     LMRL_CUDA(cudaMemcpyAsync(out_tokens, G.gen.tok, sizeof(int32_t) * (size_t)n * e->cfg.max_new_tokens, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaMemcpyAsync(out_len, G.gen.len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, e->stream));
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
@@ -1405,7 +1448,8 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable) {
     LMRL_CHECK(e && e->gpt2, "lmrl_set_use_pdl: no GPT-2 parameters loaded");
     e->gpt2->use_pdl = enable ? 1 : 0;
     if (e->gpt2->graph_exec) { cudaGraphExecDestroy(e->gpt2->graph_exec); e->gpt2->graph_exec = nullptr; }
-    e->gpt2->warm_valid = false;
+    if (e->gpt2->decode_graph) { cudaGraphExecDestroy(e->gpt2->decode_graph); e->gpt2->decode_graph = nullptr; }
+    e->gpt2->warm_valid = false; e->gpt2->decode_warm_valid = false;
     return 0;
 }
 
@@ -1434,7 +1478,8 @@ int lmrl_set_option(lmrl_engine* e, const char* name, int32_t value) {
     LMRL_CHECK(slot, "lmrl_set_option: unknown option '%s'", name);
     *slot = value;
     if (e->gpt2->graph_exec) { cudaGraphExecDestroy(e->gpt2->graph_exec); e->gpt2->graph_exec = nullptr; }
-    e->gpt2->warm_valid = false;
+    if (e->gpt2->decode_graph) { cudaGraphExecDestroy(e->gpt2->decode_graph); e->gpt2->decode_graph = nullptr; }
+    e->gpt2->warm_valid = false; e->gpt2->decode_warm_valid = false;
     return 0;
 }
 

@@ -297,11 +297,7 @@ class B200PPOTrain:
                 loss = loss + self.bc_loss_weight * bc
             loss.backward()
             loss = float(loss.detach())
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            world = torch.distributed.get_world_size()
-            for f in self.flat:
-                torch.distributed.all_reduce(f.grad)
+        world = self._allreduce_grads()
         self.steps += 1
         if self.use_device_adamw:
             e = self._lmrl_engine
@@ -318,6 +314,36 @@ class B200PPOTrain:
         if self.backward == "b200":
             self.push_to_engine()           # the next forward / backward (and the next rollout) run on the updated weights
         return float(loss), {k: float(v) for k, v in logs.items()}
+
+    def _allreduce_grads(self) -> int:
+        """Summing all-reduce of the two flat gradient buffers over the data-parallel ranks (the one collective of the system:
+        ppo/gpt2/interface.py:165-181 leaves it to pjit).  Returns the world size (AdamW divides by it).  Every call is bracketed by
+        CUDA events so that ``allreduce_stats`` can report its device time and bytes (bench.py's ``ppo_round`` block)."""
+        torch = self.torch
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1):
+            return 1
+        timed = self.flat[0].is_cuda
+        if timed:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        for f in self.flat:
+            torch.distributed.all_reduce(f.grad)
+        if timed:
+            ev1.record()
+            self._ar_events = getattr(self, "_ar_events", [])[-255:] + [(ev0, ev1)]
+        self._ar_bytes = getattr(self, "_ar_bytes", 0) + sum(int(f.grad.numel()) * f.grad.element_size() for f in self.flat)
+        self._ar_calls = getattr(self, "_ar_calls", 0) + 1
+        return torch.distributed.get_world_size()
+
+    def allreduce_stats(self) -> Dict[str, float]:
+        """Mean device milliseconds and bytes of the gradient all-reduce per optimizer step since construction (zeros on one rank)."""
+        calls = getattr(self, "_ar_calls", 0)
+        if not calls:
+            return dict(calls=0, ms_per_step=0.0, bytes_per_step=0)
+        self.torch.cuda.synchronize(self.device)
+        ev = getattr(self, "_ar_events", [])
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev])) if ev else 0.0
+        return dict(calls=calls, ms_per_step=ms, bytes_per_step=self._ar_bytes // calls)
 
     def bc_step(self, bc_batch: Dict[str, np.ndarray]) -> float:
         """One optimizer step on the BC loss alone (masked next-token cross-entropy; what the reference's BC drivers minimise,
@@ -343,11 +369,7 @@ class B200PPOTrain:
             for f in self.flat:                                        # parameters the loss does not reach (the value head)
                 if f.grad is None:
                     f.grad = torch.zeros_like(f.data)
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            world = torch.distributed.get_world_size()
-            for f in self.flat:
-                torch.distributed.all_reduce(f.grad)
+        world = self._allreduce_grads()
         self.steps += 1
         if self.use_device_adamw:
             e = self._lmrl_engine

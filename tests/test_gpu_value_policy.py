@@ -184,3 +184,54 @@ def test_value_policy_with_linear_q_heads(tok, n_heads, with_pi_beta, bias):
     with pytest.raises(Exception):
         pol.set_params(_params(cfg, n_heads == 2))
     eng.close()
+
+
+@pytest.mark.parametrize("beta", [16.0, 32.0])
+@pytest.mark.parametrize("heads", ["ilql-two-mlp-heads", "mc-linear-head"])
+def test_value_policy_at_reference_operating_point(tok, beta, heads):
+    """GPT-2-small shape at the reference's own beta (wordle/ilql/eval_ilql_gpt2.py:47 policy_beta = 16; the sweeps go to 32), two MLP Q
+    heads (ILQL) and one LinearHead (MC returns).  beta is a power of two, so folding it into the bf16 operand is exact; the error of
+    beta * q is 2^-9 relative to |beta * q| ~ beta * 4.4, hence bounds that scale with beta / 4 from the beta = 4 ones above.  What the
+    sampler sees is the ORDER of the logits: the arg-max of the engine's logits must be the oracle's arg-max up to that bound on every
+    row, and the greedy-token agreement rate with the plain fp32 oracle is reported and bounded below."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2ValuePolicy
+    from oracle import gpt2 as og
+    cfg = GPT2Config.small()
+    rng = np.random.default_rng(5)
+    if heads == "ilql-two-mlp-heads":
+        q1, q2 = init_mlp_head_params(cfg, seed=12), init_mlp_head_params(cfg, seed=13)
+        q1["dense1"]["bias"] = (0.1 * rng.standard_normal(cfg.d_model)).astype(np.float32)
+    else:
+        q1, q2 = _linear_head(cfg, 21), None
+    params = (init_gpt2_params(cfg, seed=40), init_gpt2_params(cfg, seed=41), q1, q2)
+    eng = Engine(max_envs=32, max_input_length=48, max_new_tokens=3, tokenizer=tok)
+    pol = B200GPT2ValuePolicy(eng, params, cfg, beta=beta, seed=3)
+    prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(3, 48, size=24)]
+    prompts[0] = tok.encode("Wordle:\nc r a n e\nb y b b g\n")
+    got = pol.logits(prompts)
+    tol_emu, tol_f32 = TOL_EMU * beta / 4.0, TOL_F32 * beta / 4.0
+    worst_emu = worst_f32 = 0.0
+    agree = []
+    for i in range(0, 24, 2):
+        emu = og.value_policy_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, beta, emulate_bf16=True)
+        f32 = og.value_policy_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, beta)
+        worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+        worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+        agree.append(int(np.argmax(got[i]) == np.argmax(f32)))
+        assert f32[np.argmax(got[i])] >= f32.max() - 2 * tol_f32, i          # the engine's greedy token is within tolerance of the oracle's best
+        assert emu[np.argmax(got[i])] >= emu.max() - 2 * tol_emu, i
+    scale = float(np.abs(f32).mean())
+    print(f"{heads} beta={beta:g} GPT-2-small: max|logit diff| vs bf16-emulating oracle {worst_emu:.4g} (bound {tol_emu:.3g}), vs fp32 oracle "
+          f"{worst_f32:.4g} (bound {tol_f32:.3g}); mean |logit| {scale:.1f}; greedy-token agreement with the fp32 oracle {np.mean(agree):.2f}")
+    assert worst_emu <= tol_emu and worst_f32 <= tol_f32
+    assert np.mean(agree) >= 0.5
+    # decode path with both KV caches at this shape: sampled ids are the oracle's arg-max within the bound
+    keys = [int(k) for k in rng.integers(0, 2**63, size=24)]
+    gens = pol.generate_tokens(prompts, episode_keys=keys, turn=1)
+    for i in (0, 7, 19):
+        for k, t in enumerate(gens[i]):
+            logits = og.value_policy_last_logits(params, prompts[i] + gens[i][:k], cfg.n_head, cfg.n_vocab, beta, emulate_bf16=True)
+            sc = og.sample_scores(logits, og.row_key(3, keys[i], 1, k))
+            assert sc[t] >= sc.max() - 2 * tol_emu, (i, k)
+    eng.close()
