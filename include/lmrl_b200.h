@@ -347,6 +347,10 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
  *                    0 16-row passes
  *   "gemv_max_rows"  decode passes of batches with at most this many envs run the weight-streaming GEMV kernels instead of
  *                    128-row tensor-core tiles (default 8; 0 disables)
+ *   "tok_nlnl_id"    id of the tokenizer's '\n\n' token, -1 (default) = none.  The reference encodes the JOINED history every turn
+ *                    (ppo/gpt2/interface.py:519-522), so with GPT-2's merges a prompt ending in an action line + an empty feedback
+ *                    line ends in that single token; the fused rollout reproduces this in its prompt view (the stream itself stays
+ *                    tokenised per Text item).  The Python policy classes set it from the tokenizer.
  * Unknown names fail.  Changing a switch drops the captured rollout graph. */
 int lmrl_set_option(lmrl_engine* e, const char* name, int32_t value);
 int lmrl_get_option(lmrl_engine* e, const char* name, int32_t* value);

@@ -23,7 +23,7 @@ from typing import Callable, Dict, Iterator, List, Optional, Tuple, Union
 import numpy as np
 
 from . import _lib
-from .environment import BatchedTextEnv, BatchedTextPolicy, Text, TextEnv, TextHistory, TextPolicy, interact_environment
+from .environment import BatchedTextEnv, BatchedTextPolicy, InteractionTransition, Text, TextEnv, TextHistory, TextPolicy, interact_environment
 
 START_FEN = "rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1"
 
@@ -137,9 +137,12 @@ class UciOpponent:
     """A UCI engine process (``Stockfish(path, parameters={"Threads": 1, "UCI_Elo": elo})``, env.py:58-60; reply =
     ``get_best_move_time(100)``, :163).  ``nodes`` replaces the wall-clock budget by a node budget (deterministic; a deviation)."""
 
-    def __init__(self, path: str, movetime_ms: int = 100, nodes: Optional[int] = None, options: Optional[Dict[str, object]] = None):
+    def __init__(self, path: str, movetime_ms: int = 100, nodes: Optional[int] = None, options: Optional[Dict[str, object]] = None,
+                 clear_hash: bool = False):
+        """``clear_hash``: send ``ucinewgame`` before every search, so that with a node budget and one thread the reply is a function of
+        the position alone (whichever process of a pool answers, whatever it searched before) — reproducible games for tests."""
         self.p = subprocess.Popen([path] if isinstance(path, str) else list(path), stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1)
-        self.movetime_ms, self.nodes = movetime_ms, nodes
+        self.movetime_ms, self.nodes, self.clear_hash = movetime_ms, nodes, clear_hash
         self._send("uci")
         self._wait("uciok")
         for k, v in (options or {}).items():
@@ -160,6 +163,10 @@ class UciOpponent:
                 return line.strip()
 
     def best_move(self, board: ChessBoard, start_fen: str, moves: List[str]) -> str:
+        if self.clear_hash:
+            self._send("ucinewgame")
+            self._send("isready")
+            self._wait("readyok")
         self._send(f"position fen {start_fen}" + (" moves " + " ".join(moves) if moves else ""))
         self._send(f"go nodes {self.nodes}" if self.nodes else f"go movetime {self.movetime_ms}")
         return self._wait("bestmove").split()[1]
@@ -441,3 +448,48 @@ class BatchedFenChessHistoryEnv(BatchedTextEnv):
                 dn = 1
             out.append(((Text(preprocess_state_og(st), False),), reward, dn))
         return out
+
+
+def interact_environment_overlapped(env_factory, policy: BatchedTextPolicy, n: int, env_seed: Optional[List[Optional[int]]] = None,
+                                    env_options: Optional[List[Optional[Dict]]] = None) -> List[List[InteractionTransition]]:
+    """``interact_environment`` (LLM_RL/environment.py:154-207) for a host-bound env, as a two-stage pipeline over two half-batches: while
+    the env step of one half runs on a worker thread (for chess: the Stockfish pool searching the opponent replies, chess/env/env.py:157-170),
+    the policy acts on the other half — the GPU decode and the engine search overlap instead of alternating.  ``env_factory()`` builds one
+    ``BatchedTextEnv`` per half (both may share one engine pool).  Per-episode results are those of the plain loop: every half follows
+    the reference's loop (``None`` skip rule of :192-197 included); only the interleaving changes."""
+    from concurrent.futures import ThreadPoolExecutor
+    assert n >= 1
+    n_a = (n + 1) // 2
+    spans = [(0, n_a), (n_a, n)] if n > n_a else [(0, n_a)]
+    halves = []
+    for lo, hi in spans:
+        env = env_factory()
+        seeds = [None] * (hi - lo) if env_seed is None else list(env_seed[lo:hi])
+        opts = [None] * (hi - lo) if env_options is None else list(env_options[lo:hi])
+        halves.append(dict(env=env, hist=env.reset(seeds, opts), done=[False] * (hi - lo), tr=[[] for _ in range(hi - lo)], fut=None, pre=None, acted=None))
+
+    def collect(h):
+        results = [(None, None, True) if r is None else r for r in h["fut"].result()]
+        h["fut"] = None
+        pre, acted = h["pre"], h["acted"]
+        h["hist"] = [r[0] for r in results]
+        reward = [r[1] for r in results]
+        h["done"] = [bool(r[2]) for r in results]
+        for i in range(len(results)):
+            if h["done"][i] and (pre[i] is None or acted[i] is None or h["hist"][i] is None or reward[i] is None):
+                continue
+            h["tr"][i].append(InteractionTransition(pre[i], acted[i], h["hist"][i], reward[i], results[i][2]))
+
+    with ThreadPoolExecutor(max_workers=1) as worker:
+        k = 0
+        while any(not all(h["done"]) or h["fut"] is not None for h in halves):
+            h = halves[k % len(halves)]
+            k += 1
+            if h["fut"] is not None:
+                collect(h)                                   # the step submitted one round ago (it ran while the other half was in policy.act)
+            if all(h["done"]):
+                continue
+            h["pre"] = h["hist"]
+            h["acted"] = policy.act(list(h["hist"]), done=list(h["done"]))
+            h["fut"] = worker.submit(h["env"].step, h["acted"], list(h["done"]))
+    return [ep for h in halves for ep in h["tr"]]

@@ -290,7 +290,7 @@ __global__ void wordle_step_kernel(WordleDev w, TokenizerDev tk, ActionSrc src, 
                 for (int i = keep; i < len; ++i) { ia[i] = i < act_end ? 1 : 0; tr[i] = 0.f; }
                 if (act_end > keep) tr[act_end - 1] = reward;
             }
-            int kv = keep;
+            int kv = min(keep, st.kv_len[e]);           // (a folded '\n\n' prompt tail leaves kv_len one short of the stream: gpt2_kernels.cuh)
             if (len > st.max_input) {                   // LEFT truncation (BlockingStrategy, eval_bc_gpt2.py:100-104)
                 const int drop = len - st.max_input;
                 for (int i = 0; i < st.max_input; ++i) row[i] = row[i + drop];

@@ -171,6 +171,8 @@ struct Gpt2Dev {
     int fuse_ln = 0;
     int attn_wide = 1;                // prefill attention: 32 query rows per warp pass (two m16 tiles share every staged K / V block)
     int gemv_max_rows = 8;            // batches of at most this many envs decode through the weight-streaming GEMV kernels
+    int nlnl_id = -1;                 // id of the tokenizer's '\n\n' token (joined-history prompts fold a trailing newline pair into it); -1 = none
+    int fold_nlnl = -1;               // nlnl_id while a fused Wordle rollout is being enqueued, -1 on the text paths (their callers tokenise themselves)
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
     // for this path (4096-episode Wordle rollout: 208.2 ms with graphs and no PDL, 223.8 ms with PDL; letters variant 81.0 vs 84.2)
     int use_pdl = 0;
@@ -574,10 +576,10 @@ static int forward_and_sample(lmrl_engine* e, int mode, int n_env, const uint8_t
     const int ew_blocks = G.sm_count * 8;
     e->cur_pass_slot = -1;
     e->cur_mode = mode;
-    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, Ln.e0, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows, G.kvp));
+    LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, mode, Ln.e0, n_env, done, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows, G.kvp, G.fold_nlnl));
     note_pass_counts(e);
     if (mode == 0)
-        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows, G.kvp));
+        LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (n_env * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, Ln.rows, G.kvp, G.fold_nlnl));
     // towers of this policy: 0 = LM policy; 0 and 1 = pi_beta + value base (kind 1); 1 alone = value base without pi_beta (kind 2)
     const int t_first = G.policy_kind == 2 ? 1 : 0, t_last = G.policy_kind >= 1 ? 1 : 0;
     LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, G.tw[t_first].wte, G.tw[t_first].wpe, D.d_model, Ln.rows, Ln.x));
@@ -1254,9 +1256,9 @@ int lmrl_forward_host(lmrl_engine* e, int32_t tower, int32_t head_set, const int
             e->cur_pass_slot = -1;
             e->cur_mode = 0;
             LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (nc + 255) / 256, 256, 0, st, nc, G.gen));
-            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp));
+            LMRL_LAUNCH(2, LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, nc, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp, -1));
             note_pass_counts(e);
-            LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp));
+            LMRL_LAUNCH(2, LMRL_K(fill_prefill_rows_kernel, (nc * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp, -1));
             LMRL_LAUNCH(2, LMRL_K(embed_kernel, ew_blocks, 256, 0, st, T.wte, T.wpe, D.d_model, G.rows, G.x));
             if (tower_layers(e, T, 0, nc)) return -1;
             if (want_lp || need_mlp || need_lin_q)
@@ -1347,7 +1349,8 @@ static int rollout_enqueue(lmrl_engine* e, int32_t env_kind, const uint64_t* see
     const bool split = G.two_lanes && lanes_usable(e) && !e->profile && !filtered && n >= 256;
     const int n1 = std::min(e->cfg.max_envs / 2, (n + 1) / 2);
     G.lane[1].e0 = 0; G.lane[2].e0 = n1;
-    struct RestoreLane { Gpt2Dev& g; ~RestoreLane() { g.cur = &g.lane[0]; } } restore_lane{G};
+    struct RestoreLane { Gpt2Dev& g; ~RestoreLane() { g.cur = &g.lane[0]; g.fold_nlnl = -1; } } restore_lane{G};
+    G.fold_nlnl = wordle ? G.nlnl_id : -1;
     for (int turn = 0; turn < T; ++turn) {
         LMRL_LAUNCH(2, LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen));
         if (!split) {
@@ -1469,6 +1472,7 @@ static int* option_slot(lmrl::Gpt2Dev& G, const char* name) {
     if (!strcmp(name, "fuse_ln")) return &G.fuse_ln;
     if (!strcmp(name, "attn_wide")) return &G.attn_wide;
     if (!strcmp(name, "gemv_max_rows")) return &G.gemv_max_rows;
+    if (!strcmp(name, "tok_nlnl_id")) return &G.nlnl_id;
     return nullptr;
 }
 

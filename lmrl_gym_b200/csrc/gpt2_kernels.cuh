@@ -71,13 +71,24 @@ __global__ void kv_reset_kernel(KvPages kv, int n_env) {
     if (i == 0) { *kv.n_alloc = 0; *kv.overflow = 0; }
 }
 
+// Joined-history tokenisation (ppo/gpt2/interface.py:519-522 -> value_rl_base/base_interface.py:111-112: the reference encodes the
+// JOINED history string every turn).  The token stream is kept per Text item (append-only, the reference's train-time convention,
+// environment.py:313-322); with GPT-2's pre-tokeniser and merges the two differ in exactly one place for env text: a prompt that ENDS in
+// two newlines (an action line followed by the empty feedback line of an invalid guess) encodes its tail as the single '\n\n' token
+// (id 628 in GPT-2), while the same two newlines in the middle of a prompt stay two tokens.  So the fold is a property of the prompt
+// VIEW: when the stream ends (NL, NL) and the tokenizer has a '\n\n' token, the prefill feeds ONE row with that token at the
+// position of the first newline; its K / V are valid for this turn's decode passes only (the next turn re-prefills from there).
+__device__ __forceinline__ int prompt_tail_folds(const int32_t* __restrict__ tok, int len, int kv_len, int nl_id, int nlnl_id) {
+    return (nlnl_id >= 0 && len - kv_len >= 2 && tok[len - 1] == nl_id && tok[len - 2] == nl_id) ? 1 : 0;
+}
+
 // ---- row builder: exclusive scan over envs (single CTA; B <= 16384) ---------------------------------------------
 // mode 0 (prefill): env e contributes stream tokens [kv_len[e], len[e]) if it is not done
 // mode 1 (decode) : env e contributes its last sampled token at position cur[e] if it is still generating
 // e0 / B: the env range of the calling lane (the whole batch: 0 / n)
 __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __restrict__ done, const int32_t* __restrict__ stream_tok,
                                   const int32_t* __restrict__ stream_len, const int32_t* __restrict__ kv_len, int stream_cap,
-                                  GenDev gen, RowsDev rows, KvPages kv) {
+                                  GenDev gen, RowsDev rows, KvPages kv, int nlnl_id) {
     pdl_enter();
     __shared__ int warp_sums[2][32];
     __shared__ int carry[2];
@@ -89,7 +100,11 @@ __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __rest
         const int e = e0 + base + tid;
         int n = 0;
         if (base + tid < B) {
-            if (mode == 0) { n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0); if (n > 0) ctx += stream_len[e]; }
+            if (mode == 0) {
+                n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0);
+                n -= prompt_tail_folds(stream_tok + (size_t)e * stream_cap, stream_len[e], kv_len[e], gen.eos_id, nlnl_id);
+                if (n > 0) ctx += kv_len[e] + n;
+            }
             else { n = gen.active[e] ? 1 : 0; if (n > 0) ctx += gen.cur[e] + 1; }
         }
         const int has = n > 0;
@@ -134,7 +149,7 @@ __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __rest
 
 // prefill: expand each slot into its rows (one warp per slot); also resets the per-turn generation state
 __global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok, const int32_t* __restrict__ stream_len,
-                                         int32_t* __restrict__ kv_len, int stream_cap, GenDev gen, RowsDev rows, KvPages kv) {
+                                         int32_t* __restrict__ kv_len, int stream_cap, GenDev gen, RowsDev rows, KvPages kv, int nlnl_id) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -144,10 +159,14 @@ __global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok,
         const int pg = (p0 >> KV_PAGE_SHIFT) + lane;
         if (pg <= ((p0 + n - 1) >> KV_PAGE_SHIFT)) kv_ensure_page(kv, e, pg);
     }
+    // n already excludes the folded newline (build_rows_kernel): the last row then carries the '\n\n' token
+    const int fold = prompt_tail_folds(stream_tok + (size_t)e * stream_cap, stream_len[e], p0, gen.eos_id, nlnl_id);
     for (int i = lane; i < n; i += 32) {
-        rows.row_env[r0 + i] = e; rows.row_pos[r0 + i] = p0 + i; rows.row_tok[r0 + i] = stream_tok[(size_t)e * stream_cap + p0 + i];
+        rows.row_env[r0 + i] = e; rows.row_pos[r0 + i] = p0 + i;
+        rows.row_tok[r0 + i] = (fold && i == n - 1) ? nlnl_id : stream_tok[(size_t)e * stream_cap + p0 + i];
     }
-    if (lane == 0) { gen.cur[e] = p0 + n; gen.len[e] = 0; gen.active[e] = 1; kv_len[e] = p0 + n; }
+    // a folded position's K / V belong to this turn's prompt view only: the next prefill starts there again
+    if (lane == 0) { gen.cur[e] = p0 + n; gen.len[e] = 0; gen.active[e] = 1; kv_len[e] = p0 + n - fold; }
 }
 
 __global__ void clear_gen_kernel(int B, GenDev gen) {

@@ -940,8 +940,8 @@ static int policy_grad_impl(lmrl_engine* e, const int32_t* tokens, const int32_t
     mark("start");
     // ---- forward, saving the residual stream before every layer
     LMRL_K(clear_gen_kernel, (n + 255) / 256, 256, 0, st, n, G.gen);
-    LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, n, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp);
-    LMRL_K(fill_prefill_rows_kernel, (n * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp);
+    LMRL_K(build_rows_kernel, 1, 1024, 0, st, 0, 0, n, (const uint8_t*)nullptr, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp, -1);
+    LMRL_K(fill_prefill_rows_kernel, (n * 32 + 255) / 256, 256, 0, st, G.stream.tokens, G.stream.len, G.stream.kv_len, G.stream.cap, G.gen, G.rows, G.kvp, -1);
     LMRL_K(embed_kernel, ew, 256, 0, st, T.wte, T.wpe, d, G.rows, G.x);
     const size_t xbytes = sizeof(float) * (size_t)M * d, xstride = (size_t)Tr.m_cap * d;
     for (int l = 0; l < L; ++l) {

@@ -179,6 +179,12 @@ def default_out_str_process(s: str) -> str:
     return s.removesuffix("\n") + "\n"
 
 
+def nlnl_token_id(tok) -> int:
+    """Id of the single token a prompt ending in two newlines ends with under this tokenizer, or -1 when it ends with two newline tokens."""
+    e = tok.encode("e\n\n")
+    return int(e[-1]) if len(e) >= 1 and tok.token_bytes[e[-1]] == b"\n\n" else -1
+
+
 class B200GPT2Policy(BatchedTextPolicy):
     def __init__(self, engine: Engine, params: Dict, config: Optional[GPT2Config] = None, do_sample: bool = True,
                  temperature: Optional[float] = None, seed: int = 0, in_str_process: Optional[Callable[[str], str]] = None,
@@ -198,6 +204,9 @@ class B200GPT2Policy(BatchedTextPolicy):
         self.out_str_process = out_str_process
         self._calls = 0
         _upload_params(engine, self.config, params)
+        # joined-history tokenisation (ppo/gpt2/interface.py:519-522): a tokenizer that encodes a trailing "\n\n" as ONE token (GPT-2's
+        # merges do: id 628) makes the fused rollout fold the newline pair at the end of a prompt into that token
+        engine.set_option("tok_nlnl_id", nlnl_token_id(engine.tokenizer))
         if os.environ.get("LMRL_NO_GRAPHS") == "1":        # debugging aid (compute-sanitizer racecheck, ncu): eager launches instead of graph replay
             engine.set_use_graphs(False)
 

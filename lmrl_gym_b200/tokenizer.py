@@ -139,10 +139,15 @@ class ByteTokenizer:
                 continue
             a, b = line.split()
             merges.append((bytes(u2b[ch] for ch in a), bytes(u2b[ch] for ch in b)))
+        eot = vocab.get("<|endoftext|>")
         if add_pad:
             toks.append(b"")
             specials.add(len(toks) - 1)
-        return cls(toks, merges, specials, name="gpt2-bpe")
+        tok = cls(toks, merges, specials, name="gpt2-bpe")
+        if eot is not None:                                   # vocabularies of any size: ids come from the file, not from GPT-2's constants
+            tok.eos_token_id = int(eot)
+        tok.pad_token_id = len(toks) - 1 if add_pad else None
+        return tok
 
     def __len__(self):
         return len(self.token_bytes)

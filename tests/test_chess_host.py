@@ -214,3 +214,130 @@ def test_batched_env_with_engine_pool_equals_the_per_game_env():
         for ta, tb in zip(ea, eb):
             assert ta.post_transition_history == tb.post_transition_history and ta.reward == tb.reward and bool(ta.done) == bool(tb.done)
     assert a[1][0].reward == 1 and a[2][0].reward == -1 and a[4][0].reward == -1          # mate in one; null move; illegal first move
+
+
+STOCKFISH = os.environ.get("LMRL_STOCKFISH", "/root/reference/stockfish/stockfish-ubuntu-20.04-x86-64-avx2")
+needs_stockfish = pytest.mark.skipif(not os.path.exists(STOCKFISH), reason="the reference's vendored Stockfish binary is only present in the build container")
+
+
+def _san(board, uci):
+    """SAN of a legal move given in UCI notation (push, read ``board.san``, pop)."""
+    san = board.push_uci(uci)
+    board.pop()
+    return san
+
+
+class _StockfishProbe(CE.UciOpponent):
+    """The real engine as an independent chess-rules oracle: `d` prints its FEN of the current position, `go perft n` its leaf count."""
+
+    def fen_after(self, start_fen, moves):
+        self._send(f"position fen {start_fen}" + (" moves " + " ".join(moves) if moves else ""))
+        self._send("d")
+        return self._wait("Fen:").split("Fen:")[1].strip()
+
+    def perft(self, fen, depth):
+        self._send(f"position fen {fen}")
+        self._send(f"go perft {depth}")
+        return int(self._wait("Nodes searched:").split(":")[1])
+
+
+@needs_stockfish
+def test_real_stockfish_opponent_and_rules_cross_check():
+    """chess/env/env.py:157-170 with the engine the reference vendors (stockfish/stockfish-ubuntu-20.04-x86-64-avx2; round 1 only ever
+    drove a fake engine).  Random-endgame games against it: every engine reply is legal under this repo's C++ rules, the FEN this repo
+    emits after every ply equals Stockfish's own FEN of the same move list (piece placement, side, castling, en passant as python-chess /
+    Stockfish print it, clocks), perft counts agree, and a K+Q vs K game is won by the engine's side when it plays both colours."""
+    rng = np.random.default_rng(3)
+    sf = _StockfishProbe(STOCKFISH, nodes=400, options={"Threads": 1})
+    try:
+        n_plies = 0
+        for g in range(6):
+            fen = CE.large_piece_random_endgame(["kQK", "kRK", "kRRK", "kQRK", "kBNK", "kQBK"][g], rng)
+            assert sf.perft(fen, 3) == CE.ChessBoard(fen).perft(3), fen
+            env = CE.ChessEnv(from_position=fen, opponent=sf)
+            done = False
+            for ply in range(12):
+                legal = env.board.legal_moves()
+                move = _san(env.board, legal[int(rng.integers(len(legal)))])
+                st, r, done, info = env.step(move)
+                n_plies += 1
+                assert sf.fen_after(fen, env.uci_moves) == env.board.fen(), (fen, env.uci_moves)
+                if done:
+                    break
+                assert info["opponent move"] is not None and st.split()[1] == "w"
+        assert n_plies >= 20
+        # the engine against itself from a won position: white (K+Q) mates within the move budget, this repo's rules see the mate
+        b = CE.ChessBoard("8/8/8/4k3/8/8/3QK3/8 w - - 0 1")
+        moves = []
+        strong = CE.UciOpponent(STOCKFISH, nodes=20000, options={"Threads": 1})
+        try:
+            for _ in range(80):
+                mv = strong.best_move(b, "8/8/8/4k3/8/8/3QK3/8 w - - 0 1", moves)
+                b.push_uci(mv)
+                moves.append(mv)
+                if b.is_game_over():
+                    break
+        finally:
+            strong.close()
+        assert b.is_checkmate() and not b.turn_white, (len(moves), b.fen())
+    finally:
+        sf.close()
+
+
+@needs_stockfish
+def test_engine_pool_with_real_stockfish_overlaps_replies_with_the_policy():
+    """BASELINE.json configs[3] on the host side: a pool of real Stockfish processes behind `BatchedFenChessHistoryEnv`, driven by the
+    two-half-batch pipelined loop (`interact_environment_overlapped`): while the engines search the replies of one half, the policy acts
+    on the other.  Node-limited search makes the games deterministic, so the pipelined loop must reproduce the plain loop's episodes; the
+    overlap is observed directly (a policy call starts while an env step of the other half is still running)."""
+    import threading
+    import time
+    from lmrl_gym_b200.environment import BatchedTextPolicy
+    fen = "8/8/8/4k3/8/8/3QK3/8 w - - 0 1"
+    events = []
+
+    class FirstLegal(BatchedTextPolicy):
+        """Stand-in for the GPU policy: the lexicographically first legal SAN move, 30 ms per call (a decode call's order of magnitude)."""
+
+        def act(self, text_history, done=None):
+            events.append(("act_start", time.perf_counter(), threading.get_ident()))
+            time.sleep(0.03)
+            out = []
+            for h, d in zip(text_history, done):
+                if d or h is None:
+                    out.append(None)
+                    continue
+                b = CE.ChessBoard(CE.postprocess_state(h[-1].text))
+                out.append(tuple(h) + (Text(CE.preprocess_move(_san(b, sorted(b.legal_moves())[0])), True),))
+            events.append(("act_end", time.perf_counter(), threading.get_ident()))
+            return out
+
+    class Timed(CE.BatchedFenChessHistoryEnv):
+        def step(self, text_history, done=None):
+            events.append(("step_start", time.perf_counter(), threading.get_ident()))
+            r = super().step(text_history, done)
+            events.append(("step_end", time.perf_counter(), threading.get_ident()))
+            return r
+
+    pool = CE.UciOpponentPool(STOCKFISH, n_workers=4, nodes=3000, options={"Threads": 1}, clear_hash=True)
+    try:
+        plain = interact_environment(CE.BatchedFenChessHistoryEnv(max_moves=5, from_position=fen, opponent=pool), FirstLegal(), env_seed=[None] * 8, env_options=[None] * 8, bsize=8)
+        events.clear()
+        over = CE.interact_environment_overlapped(lambda: Timed(max_moves=5, from_position=fen, opponent=pool), FirstLegal(), n=8)
+    finally:
+        pool.close()
+    assert len(over) == len(plain) == 8
+    for ea, eb in zip(over, plain):
+        assert len(ea) == len(eb)
+        for ta, tb in zip(ea, eb):
+            assert ta.post_transition_history == tb.post_transition_history and ta.reward == tb.reward and bool(ta.done) == bool(tb.done)
+    # some policy call began while an env step (other half, other thread) was in flight
+    open_steps, overlapped = 0, False
+    for kind, t, _ in sorted(events, key=lambda e: e[1]):
+        if kind == "step_start":
+            open_steps += 1
+        elif kind == "step_end":
+            open_steps -= 1
+        elif kind == "act_start" and open_steps > 0:
+            overlapped = True
+    assert overlapped

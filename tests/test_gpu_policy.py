@@ -336,3 +336,74 @@ def test_fused_layernorm_and_wide_prefill_attention_are_bit_identical(tok):
         with pytest.raises(Exception):
             eng.set_option("no_such_option", 1)
         eng.close()
+
+
+@pytest.mark.parametrize("kind", ["synthetic+nlnl", "gpt2-format-bpe-fixture"])
+def test_fused_rollout_feeds_the_joined_history_encoding(kind):
+    """The reference encodes the JOINED history every turn (ppo/gpt2/interface.py:519-522 -> value_rl_base/base_interface.py:111-112).
+    With a tokenizer that merges a trailing newline pair (GPT-2's does: 'ĊĊ', id 628) the prompt after an invalid guess ends in that ONE
+    token.  The fused rollout must feed exactly `tokenizer.encode(joined history)`: every sampled id is checked against the oracle sampler
+    on that prompt (a per-item prompt — two newline tokens — gives different logits), for a tokenizer with the extra token bolted onto the
+    synthetic table and for the committed GPT-2-format BPE fixture (true merges, 304-token vocabulary); env transitions replay exactly."""
+    import os
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.environment import text_env_eval
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy, nlnl_token_id
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from oracle import gpt2 as og
+    from oracle.mt19937 import seed_stream
+    from oracle.wordle import ReformatWordleOracle
+    if kind == "synthetic+nlnl":
+        toks = list(ByteTokenizer.synthetic().token_bytes)
+        toks[45000] = b"\n\n"
+        tok = ByteTokenizer(toks, name="synthetic-gpt2-shape-v1+nlnl")
+        cfg = _small_cfg()
+        params = _steer_to_letters(init_gpt2_params(cfg, seed=7), tok)
+    else:
+        d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt2_format_tokenizer")
+        tok = ByteTokenizer.from_gpt2_files(os.path.join(d, "vocab.json"), os.path.join(d, "merges.txt"))
+        cfg = GPT2Config(n_layer=2, n_head=4, d_model=256, d_ff=1024, n_vocab=303, n_vocab_rows=304, n_pos=256)
+        params = init_gpt2_params(cfg, seed=7)          # 303 ids, ~1/5 of them letters or spaced letters: a mix of well-formed and malformed guesses
+    nlnl = nlnl_token_id(tok)
+    assert nlnl >= 0
+    B = 96
+    eng = Engine(max_envs=B, max_input_length=128, max_new_tokens=6, max_turns=6, tokenizer=tok)
+    env = B200WordleEnv(eng, "wordle_official.txt", require_words_in_vocab=False)
+    pol = B200GPT2Policy(eng, params, cfg, seed=11)
+    assert eng.get_option("tok_nlnl_id") == nlnl
+    words = load_vocab_words("wordle_official.txt")
+    for rep in range(2):                                  # eager, then graph capture
+        inter, summary = text_env_eval(env, pol, n_rollouts=B, seed_generator=seed_stream(2), bsize=B, verbose=False)
+    seeds = seed_stream(2)
+    seed_list = [next(seeds) for _ in range(B)]
+    n_folded = n_checked = 0
+    for i, ep in enumerate(inter):
+        o = ReformatWordleOracle(words, require_words_in_vocab=False)
+        h = o.reset(seed_list[i])
+        for tr in ep:
+            h, r, d = o.step(h + ((tr.post_action_history[-1].text, True),))
+            assert [[x.text, x.is_action] for x in tr.post_transition_history] == [[a, b] for a, b in h]
+            assert tr.reward == r and tr.done == d
+    for i in (0, 5, 33, 70, B - 1):
+        ep = inter[i]
+        logs, j = ep._logs, ep._i
+        for t, tr in enumerate(ep):
+            text = "".join(x.text for x in tr.pre_action_history)
+            prompt = tok.encode(text)
+            folded = text.endswith("\n\n")
+            assert (prompt[-1] == nlnl) == folded
+            n_folded += folded
+            gen = logs.act_tokens[j, t, :logs.act_len[j, t]].tolist()
+            for k, tk in enumerate(gen):
+                logits = og.forward_last_logits(params, prompt + gen[:k], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+                s = og.sample_scores(logits, og.row_key(11, seed_list[i], t, k), 1.0, True)
+                assert s[tk] >= s.max() - 2 * TOL_EMU, (kind, i, t, k, folded)
+                n_checked += 1
+    assert n_folded >= 3 and n_checked >= 30, (n_folded, n_checked)
+    # the same rollout with the fold switched off feeds per-item tokens: it must differ from the joined-history run on folded prompts
+    eng.set_option("tok_nlnl_id", -1)
+    inter_off, _ = text_env_eval(env, pol, n_rollouts=B, seed_generator=seed_stream(2), bsize=B, verbose=False)
+    diff = sum(int(a._logs.act_tokens[a._i].tolist() != b._logs.act_tokens[b._i].tolist()) for a, b in zip(inter, inter_off))
+    print(f"{kind}: {n_folded} folded prompts checked, {n_checked} sampled ids within tolerance; episodes that change without the fold: {diff} of {B}")
+    assert diff > 0
+    eng.close()

@@ -229,3 +229,28 @@ def test_reference_arm_uses_host_threads_under_torchrun_env(tmp_path):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-batch", "2"],
                          capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0 and not [l for l in res.stdout.splitlines() if l.startswith("{")]
+
+
+def test_gpt2_format_tokenizer_fixture_and_the_trailing_newline_pair():
+    """`ByteTokenizer.from_gpt2_files` on the committed GPT-2-format fixture (true BPE merges; oracle/gen_tokenizer_fixture.py): a spaced
+    Wordle line is one token per letter, and a prompt ENDING in two newlines ends in the single merged token while the same pair in the
+    middle of a prompt stays two tokens — the one place where the reference's joined-history encoding (ppo/gpt2/interface.py:519-522)
+    differs from per-item encoding (environment.py:313-322) on env text."""
+    from lmrl_gym_b200.gpt2 import nlnl_token_id
+    from lmrl_gym_b200.tokenizer import ByteTokenizer
+    d = os.path.join(ROOT, "tests", "golden", "gpt2_format_tokenizer")
+    tok = ByteTokenizer.from_gpt2_files(os.path.join(d, "vocab.json"), os.path.join(d, "merges.txt"))
+    assert len(tok) == 304 and tok.pad_token_id == 303 and tok.eos_token_id == 302 and tok.newline_id() == 198
+    nlnl = nlnl_token_id(tok)
+    assert nlnl >= 256 and tok.token_bytes[nlnl] == b"\n\n"
+    assert nlnl_token_id(ByteTokenizer.synthetic()) == -1
+    items = ["Wordle:\n", "c r a n e\n", "\n", "s l a t e\n", "b y b b g\n"]
+    per_item = [t for it in items for t in tok.encode(it)]
+    assert tok.encode("".join(items)) == per_item                          # a newline pair INSIDE the prompt: identical
+    assert [tok.token_bytes[t] for t in tok.encode(items[1])] == [b"c", b" r", b" a", b" n", b" e", b"\n"]
+    joined3 = tok.encode("".join(items[:3]))                               # the prompt right after the invalid guess ends in '\n\n'
+    per3 = [t for it in items[:3] for t in tok.encode(it)]
+    assert joined3 == per3[:-2] + [nlnl] and per3[-2:] == [198, 198]
+    assert tok.decode(joined3) == "".join(items[:3]) and tok.token_bytes[tok.encode("Wordle")[0]] == b"Wordle"
+    t = tok.device_tables()
+    assert t["tok_first"][ord("c")] == tok.encode("c")[0] and t["tok_space"][ord("r")] == tok.encode(" r")[0]
