@@ -71,8 +71,11 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// wall-clock bound of one mbarrier wait; LMRL_MBAR_TIMEOUT_S (read at lmrl_create) raises it for tools that slow kernels down by orders of
+// magnitude (compute-sanitizer racecheck: a tile's MMAs can take seconds)
+__device__ unsigned long long g_mbar_timeout_ns = 2000000000ull;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // bounded wait (2 s of wall clock): a protocol bug traps with a context error instead of hanging the GPU
+    // bounded wait (2 s of wall clock by default): a protocol bug traps with a context error instead of hanging the GPU
     uint32_t done = 0;
     uint64_t t0 = 0;
     for (uint32_t spin = 0; !done; ++spin) {
@@ -81,7 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && (spin & 1023u) == 1023u) {
             const uint64_t now = global_timer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) {
+            else if (now - t0 > g_mbar_timeout_ns) {
                 printf("lmrl gemm_tcgen05: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
                 __trap();
             }

@@ -74,12 +74,26 @@ __global__ void kv_reset_kernel(KvPages kv, int n_env) {
 // Joined-history tokenisation (ppo/gpt2/interface.py:519-522 -> value_rl_base/base_interface.py:111-112: the reference encodes the
 // JOINED history string every turn).  The token stream is kept per Text item (append-only, the reference's train-time convention,
 // environment.py:313-322); with GPT-2's pre-tokeniser and merges the two differ in exactly one place for env text: a prompt that ENDS in
-// two newlines (an action line followed by the empty feedback line of an invalid guess) encodes its tail as the single '\n\n' token
-// (id 628 in GPT-2), while the same two newlines in the middle of a prompt stay two tokens.  So the fold is a property of the prompt
-// VIEW: when the stream ends (NL, NL) and the tokenizer has a '\n\n' token, the prefill feeds ONE row with that token at the
-// position of the first newline; its K / V are valid for this turn's decode passes only (the next turn re-prefills from there).
-__device__ __forceinline__ int prompt_tail_folds(const int32_t* __restrict__ tok, int len, int kv_len, int nl_id, int nlnl_id) {
-    return (nlnl_id >= 0 && len - kv_len >= 2 && tok[len - 1] == nl_id && tok[len - 2] == nl_id) ? 1 : 0;
+// a run of k >= 2 newlines (an action line followed by the empty feedback line of an invalid guess; k = 3 when the action itself was
+// empty) is ONE pre-token there, which the merge 'Ċ'+'Ċ' -> 'ĊĊ' (id 628 in GPT-2) turns into floor(k / 2) '\n\n' tokens followed by
+// k % 2 plain newlines, while the same newlines in the middle of a prompt stay single tokens (`\s+(?!\S)` backs off by one before
+// a non-space).  So the fold is a property of the prompt VIEW: positions before the trailing run are the stream's, the run is fed
+// folded, and because the run's K / V (and its first newline's, possibly cached as a plain token by an earlier turn) belong to this
+// turn's view only, the cache is valid up to the run's start afterwards.
+struct PromptView { int kv; int len; int run_start; int n_pairs; };   // rows cover positions [kv, len); tokens at >= run_start are folded
+__device__ __forceinline__ PromptView prompt_view(const int32_t* __restrict__ tok, int len, int kv_len, int nl_id, int nlnl_id) {
+    PromptView v{kv_len, len, len, 0};
+    if (nlnl_id < 0 || len < 2 || tok[len - 1] != nl_id || tok[len - 2] != nl_id) return v;
+    int rs = len - 2;
+    while (rs > 0 && tok[rs - 1] == nl_id) --rs;
+    const int k = len - rs;
+    v.run_start = rs; v.n_pairs = k >> 1;
+    v.len = rs + (k >> 1) + (k & 1);
+    v.kv = min(kv_len, rs);
+    return v;
+}
+__device__ __forceinline__ int prompt_view_token(const PromptView& v, const int32_t* __restrict__ tok, int pos, int nl_id, int nlnl_id) {
+    return pos < v.run_start ? tok[pos] : (pos - v.run_start < v.n_pairs ? nlnl_id : nl_id);
 }
 
 // ---- row builder: exclusive scan over envs (single CTA; B <= 16384) ---------------------------------------------
@@ -101,9 +115,9 @@ __global__ void build_rows_kernel(int mode, int e0, int B, const uint8_t* __rest
         int n = 0;
         if (base + tid < B) {
             if (mode == 0) {
-                n = (done && done[e]) ? 0 : max(stream_len[e] - kv_len[e], 0);
-                n -= prompt_tail_folds(stream_tok + (size_t)e * stream_cap, stream_len[e], kv_len[e], gen.eos_id, nlnl_id);
-                if (n > 0) ctx += kv_len[e] + n;
+                const PromptView v = prompt_view(stream_tok + (size_t)e * stream_cap, stream_len[e], kv_len[e], gen.eos_id, nlnl_id);
+                n = (done && done[e]) ? 0 : max(v.len - v.kv, 0);
+                if (n > 0) ctx += v.len;
             }
             else { n = gen.active[e] ? 1 : 0; if (n > 0) ctx += gen.cur[e] + 1; }
         }
@@ -154,19 +168,21 @@ __global__ void fill_prefill_rows_kernel(const int32_t* __restrict__ stream_tok,
     const int lane = threadIdx.x & 31;
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= *rows.n_slots) return;
-    const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot], p0 = kv_len[e];
+    const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
+    const int32_t* stok = stream_tok + (size_t)e * stream_cap;
+    const PromptView v = prompt_view(stok, stream_len[e], kv_len[e], gen.eos_id, nlnl_id);      // the same view build_rows_kernel sized n from
+    const int p0 = v.kv;
     {   // pages of positions [p0, p0 + n): one lane per page (ppe <= 32)
         const int pg = (p0 >> KV_PAGE_SHIFT) + lane;
         if (pg <= ((p0 + n - 1) >> KV_PAGE_SHIFT)) kv_ensure_page(kv, e, pg);
     }
-    // n already excludes the folded newline (build_rows_kernel): the last row then carries the '\n\n' token
-    const int fold = prompt_tail_folds(stream_tok + (size_t)e * stream_cap, stream_len[e], p0, gen.eos_id, nlnl_id);
     for (int i = lane; i < n; i += 32) {
         rows.row_env[r0 + i] = e; rows.row_pos[r0 + i] = p0 + i;
-        rows.row_tok[r0 + i] = (fold && i == n - 1) ? nlnl_id : stream_tok[(size_t)e * stream_cap + p0 + i];
+        rows.row_tok[r0 + i] = prompt_view_token(v, stok, p0 + i, gen.eos_id, nlnl_id);
     }
-    // a folded position's K / V belong to this turn's prompt view only: the next prefill starts there again
-    if (lane == 0) { gen.cur[e] = p0 + n; gen.len[e] = 0; gen.active[e] = 1; kv_len[e] = p0 + n - fold; }
+    // a folded run's K / V belong to this turn's prompt view only: the next prefill starts at the run again
+    __syncwarp();                                              // every lane has read kv_len[e] (prompt_view) before it changes
+    if (lane == 0) { gen.cur[e] = p0 + n; gen.len[e] = 0; gen.active[e] = 1; kv_len[e] = min(p0 + n, v.run_start); }
 }
 
 __global__ void clear_gen_kernel(int B, GenDev gen) {

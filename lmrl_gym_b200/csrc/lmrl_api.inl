@@ -27,6 +27,10 @@ int lmrl_create(const lmrl_config* cfg, lmrl_engine** out) {
     e->cfg = *cfg;
     e->device = cfg->device;
     LMRL_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    if (const char* t = getenv("LMRL_MBAR_TIMEOUT_S")) {            // debugging aid: mbarrier wait bound of the tcgen05 kernels (default 2 s)
+        const unsigned long long ns = (unsigned long long)(atof(t) * 1e9);
+        if (ns > 0) LMRL_CUDA(cudaMemcpyToSymbol(lmrl::g_mbar_timeout_ns, &ns, sizeof ns));
+    }
     const int B = cfg->max_envs;
     e->act_pitch = MAX_ACTION_CP;
     if (e->alloc(&e->d_act_bytes, (size_t)B * e->act_pitch) || e->alloc(&e->d_act_len, B) || e->alloc(&e->d_skip, B) ||

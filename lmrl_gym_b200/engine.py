@@ -32,6 +32,7 @@ class Engine:
         self.max_turns = max_turns
         self.tokenizer: Optional[ByteTokenizer] = None
         self.env_kind = 0
+        self._slots = {}          # (kind, index) -> role of what was loaded there (claim_slot)
         if tokenizer is not None:
             self.load_tokenizer(tokenizer)
 
@@ -96,6 +97,20 @@ class Engine:
     def set_use_pdl(self, enable: bool):
         """Programmatic dependent launch between the kernels of a pass (default off: measured slower on B200)."""
         check(self.lib.lmrl_set_use_pdl(self.handle, 1 if enable else 0))
+
+    def claim_slot(self, kind: str, index: int, role: str):
+        """The engine has three parameter towers and two value-head sets, and several host classes load into the same indices (tower 1:
+        the frozen initial policy of PPO *or* the value base of ILQL / MC; head set 0: the PPO value head *or* the Q / V heads).  Loading a
+        second role into an occupied slot would silently overwrite the first object's weights; refuse it instead."""
+        cur = self._slots.get((kind, index))
+        if cur is not None and cur != role:
+            raise LmrlError(f"engine {kind} {index} already holds the {cur}: loading the {role} there would overwrite it "
+                            f"(bind the two objects to separate engines)")
+        self._slots[(kind, index)] = role
+
+    def release_slots(self):
+        """Forget what the towers / head sets hold (a caller that is done with the objects bound so far and reuses the engine)."""
+        self._slots.clear()
 
     def set_option(self, name: str, value: int):
         """Named integer switch of the policy engine (include/lmrl_b200.h::lmrl_set_option): fuse_ln, attn_wide, gemv_max_rows."""

@@ -122,7 +122,8 @@ def init_mlp_head_params(cfg: GPT2Config, seed: int = 0, hidden: Optional[int] =
                             bias=np.full(n_out, layer2_bias_init, np.float32)))
 
 
-def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict, tower: int = 0):
+def _upload_params(engine: Engine, cfg: GPT2Config, params: Dict, tower: int = 0, role: Optional[str] = None):
+    engine.claim_slot("tower", int(tower), role or ("policy" if tower == 0 else "value base"))
     L = cfg.n_layer
     assert len(params["layers"]) == L
     keep = []  # keep contiguous fp32 copies alive during the call
@@ -169,6 +170,7 @@ def head_struct(q: Optional[Dict], keep: list):
 
 
 def _upload_q_heads(engine: Engine, q1: Dict, q2: Optional[Dict], beta: float):
+    engine.claim_slot("sampler heads", 0, "Q heads of the value-perturbed policy")
     keep: list = []
     h1, h2 = head_struct(q1, keep), head_struct(q2, keep)
     check(engine.lib.lmrl_load_q_heads(engine.handle, C.byref(h1), None if h2 is None else C.byref(h2), float(beta)))
@@ -180,9 +182,17 @@ def default_out_str_process(s: str) -> str:
 
 
 def nlnl_token_id(tok) -> int:
-    """Id of the single token a prompt ending in two newlines ends with under this tokenizer, or -1 when it ends with two newline tokens."""
-    e = tok.encode("e\n\n")
-    return int(e[-1]) if len(e) >= 1 and tok.token_bytes[e[-1]] == b"\n\n" else -1
+    """Id of the tokenizer's "\\n\\n" token when prompts ending in a run of k newlines encode that run as floor(k / 2) of it followed by
+    k % 2 plain newlines (GPT-2's pre-tokeniser + the 'ĊĊ' merge; what the device's prompt view reproduces), else -1 (no fold: the run
+    stays k newline tokens, which is exact for tokenizers without such a token)."""
+    nl = tok.encode("\n")
+    e2 = tok.encode("e\n\n")
+    if len(nl) != 1 or len(e2) < 1 or tok.token_bytes[e2[-1]] != b"\n\n":
+        return -1
+    nlnl, head = int(e2[-1]), tok.encode("e")
+    ok = (tok.encode("e\n\n\n") == head + [nlnl, nl[0]] and tok.encode("e\n\n\n\n") == head + [nlnl, nlnl] and
+          tok.encode("e\n\nx") == head + [nl[0], nl[0]] + tok.encode("x"))
+    return nlnl if ok else -1
 
 
 class B200GPT2Policy(BatchedTextPolicy):
@@ -209,6 +219,8 @@ class B200GPT2Policy(BatchedTextPolicy):
         engine.set_option("tok_nlnl_id", nlnl_token_id(engine.tokenizer))
         if os.environ.get("LMRL_NO_GRAPHS") == "1":        # debugging aid (compute-sanitizer racecheck, ncu): eager launches instead of graph replay
             engine.set_use_graphs(False)
+        if os.environ.get("LMRL_GEMM_IMPL"):                # debugging aid: 0 = mma.sync GEMMs (tools that cannot instrument tcgen05 / TMA kernels)
+            engine.set_gemm_impl(int(os.environ["LMRL_GEMM_IMPL"]))
 
     @property
     def fusable(self) -> bool:

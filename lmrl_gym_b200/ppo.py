@@ -322,13 +322,13 @@ class B200PPOInference:
             _upload_params(engine, self.config, policy_params, tower=0)
         self.has_initial_policy = initial_policy_params is not None
         if self.has_initial_policy:
-            _upload_params(engine, self.config, initial_policy_params, tower=1)
-        upload_value_heads(engine, 0, v_linear=value_head_params)
+            _upload_params(engine, self.config, initial_policy_params, tower=1, role="frozen initial policy (PPO KL term)")
+        upload_value_heads(engine, 0, v_linear=value_head_params, role="PPO value head")
 
     def set_params(self, policy_params: Dict, value_head_params: Optional[Dict] = None) -> None:
         _upload_params(self._lmrl_engine, self.config, policy_params, tower=0)
         if value_head_params is not None:
-            upload_value_heads(self._lmrl_engine, 0, v_linear=value_head_params)
+            upload_value_heads(self._lmrl_engine, 0, v_linear=value_head_params, role="PPO value head")
 
     def forward(self, input_ids: np.ndarray) -> PPOForwardOutput:
         """RIGHT-padded ``[b, t]`` ids -> per-token log-probs of both policies and the values of every position (0 on padding)."""

@@ -494,7 +494,7 @@ class B200PPOTrain:
         dims = _lib.lmrl_gpt2_dims(n_layer=cfg.n_layer, n_head=cfg.n_head, d_model=cfg.d_model, d_ff=cfg.d_ff, n_vocab=cfg.n_vocab, n_pos=cfg.n_pos, ln_eps=cfg.ln_eps)
         e = self._lmrl_engine
         check(e.lib.lmrl_load_gpt2_tower(e.handle, int(tower), C.byref(dims), C.byref(w)))
-        upload_value_heads(e, head_set, v_linear=dict(dense=dict(kernel=self.vh_w.detach().cpu().numpy(), bias=self.vh_b.detach().cpu().numpy())))
+        upload_value_heads(e, head_set, v_linear=dict(dense=dict(kernel=self.vh_w.detach().cpu().numpy(), bias=self.vh_b.detach().cpu().numpy())), role="PPO value head")
 
     def params_numpy(self) -> Dict:
         g = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731

@@ -70,23 +70,35 @@ def score_token_sequences(policy, seqs: Sequence[Sequence[int]], prefix_lens: Se
 
 def build_bc_score_fn(policy, max_length: Optional[int] = None, bsize: Optional[int] = None) -> Callable[[List[TextHistory]], List[float]]:
     """``build_bc_score_fn`` / ``build_ppo_score_fn`` (ppo/score_fn.py:69-126, 10-67) bound to a device policy: the score of a
-    history whose last item is an action is the summed log-probability of that action's tokens.  ``max_length`` LEFT-truncates the
-    token history like the reference's ``tokens[-max_length:]`` (the prefix length shrinks with it); ``bsize`` is accepted for
-    signature compatibility (the engine batches by its own capacity)."""
+    history whose last item is an action is the summed log-probability of that action's tokens.
+
+    Truncation follows the reference to the letter (as ``_advantage_score_fn`` below already did): the token history is LEFT-truncated
+    to ``max_length`` (``tokens[-max_length:]``, :86) but the slice that selects the action's log-probs uses the UNtruncated prefix
+    length, ``masked_action_logits[x][(prefix_len[x]-1):]`` (:118) — so under truncation fewer (possibly no) action tokens are summed,
+    and an empty prefix (``prefix_len = 0`` -> ``[-1:]``) selects the last column of the padded row (0.0 unless the row is full).
+    ``max_length=None`` scores untruncated rows; ``bsize`` is accepted for signature compatibility (the engine batches by its own
+    capacity)."""
     tok = policy._lmrl_engine.tokenizer
 
     def score_fn(text_histories: List[TextHistory]) -> List[float]:
         assert all(h[-1].is_action for h in text_histories)
-        seqs, prefix = [], []
-        for h in text_histories:
+        seqs, prefix, where = [], [], []
+        out = [0.0] * len(text_histories)
+        for i, h in enumerate(text_histories):
             full = token_history(h, tok)
             pre = len(token_history(h[:-1], tok))
-            if max_length is not None and len(full) > max_length:
-                cut = len(full) - max_length
-                full, pre = full[cut:], max(pre - cut, 1)
-            seqs.append(full)
-            prefix.append(max(pre, 1))
-        return [float(x) for x in score_token_sequences(policy, seqs, prefix)]
+            width = len(full) if max_length is None else max_length          # columns of the reference's padded row
+            row = full[-width:]
+            start = pre - 1 if pre >= 1 else width - 2                       # first scored column of action_logits (python slice semantics)
+            if start > len(row) - 2 or len(row) < 2:
+                continue                                                     # the slice is empty or covers only padding: the reference sums to 0.0
+            seqs.append(row)
+            prefix.append(start + 1)
+            where.append(i)
+        if seqs:
+            for i, x in zip(where, score_token_sequences(policy, seqs, prefix)):
+                out[i] = float(x)
+        return out
 
     return score_fn
 

@@ -25,10 +25,11 @@ from .gpt2 import GPT2Config, _upload_params, head_struct
 
 
 def upload_value_heads(engine: Engine, head_set: int, q1: Optional[Dict] = None, q2: Optional[Dict] = None, v: Optional[Dict] = None,
-                       v_linear: Optional[Dict] = None) -> None:
+                       v_linear: Optional[Dict] = None, role: str = "ILQL / MC value heads") -> None:
     """q1 / q2 / v: flax ``MLPHead`` params ``{'dense1': {'kernel','bias'}, 'dense2': {...}}`` (heads/mlp_head.py:99-148); q1 / q2 may
     instead be ``LinearHead`` params ``{'dense': {'kernel' [d, n_out], 'bias'}}`` (the MC-returns Q head);
     v_linear: flax ``LinearHead`` params ``{'dense': {'kernel' [d, 1], 'bias' [1] (optional)}}`` (heads/linear_head.py:91-119)."""
+    engine.claim_slot("value-head set", int(head_set), role)
     keep: list = []
     hs = _lib.lmrl_value_heads()
     for name, q in (("q1", q1), ("q2", q2), ("v", v)):

@@ -91,6 +91,7 @@ def main():
     # ILQL advantage re-ranking
     q1, q2 = init_mlp_head_params(cfg, seed=2), init_mlp_head_params(cfg, seed=3)
     v = init_mlp_head_params(cfg, seed=4, n_out=1, layer2_bias_init=0.0)
+    eng.release_slots()                # the PPO objects above are finished: tower 1 / head set 0 are reused for the value networks
     ilql = VI.B200ILQLInference(VI.B200ValueRLInference(eng, ini, q1, q2, v, cfg, tower=1, head_set=0),
                                 VI.B200ValueRLInference(eng, pol, q1, q2, None, cfg, tower=2, head_set=1))
     fn = RR.build_ilql_score_fn(ilql, None, tok, max_length=128, value_weight=1.0, logit_weight=None, bsize=4096)

@@ -358,7 +358,7 @@ def test_fused_rollout_feeds_the_joined_history_encoding(kind):
         toks[45000] = b"\n\n"
         tok = ByteTokenizer(toks, name="synthetic-gpt2-shape-v1+nlnl")
         cfg = _small_cfg()
-        params = _steer_to_letters(init_gpt2_params(cfg, seed=7), tok)
+        params = init_gpt2_params(cfg, seed=7)          # NOT steered: a context-dependent head, every guess malformed -> every later prompt folded
     else:
         d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt2_format_tokenizer")
         tok = ByteTokenizer.from_gpt2_files(os.path.join(d, "vocab.json"), os.path.join(d, "merges.txt"))
@@ -391,7 +391,7 @@ def test_fused_rollout_feeds_the_joined_history_encoding(kind):
             text = "".join(x.text for x in tr.pre_action_history)
             prompt = tok.encode(text)
             folded = text.endswith("\n\n")
-            assert (prompt[-1] == nlnl) == folded
+            assert (nlnl in prompt[-2:]) == folded          # a run of k trailing newlines: floor(k / 2) merged tokens, then k % 2 plain ones
             n_folded += folded
             gen = logs.act_tokens[j, t, :logs.act_len[j, t]].tolist()
             for k, tk in enumerate(gen):
@@ -406,4 +406,42 @@ def test_fused_rollout_feeds_the_joined_history_encoding(kind):
     diff = sum(int(a._logs.act_tokens[a._i].tolist() != b._logs.act_tokens[b._i].tolist()) for a, b in zip(inter, inter_off))
     print(f"{kind}: {n_folded} folded prompts checked, {n_checked} sampled ids within tolerance; episodes that change without the fold: {diff} of {B}")
     assert diff > 0
+    eng.close()
+
+
+def test_sampler_tail_matches_the_float64_oracle_on_every_token(tok):
+    """Round-2 fix of the Gumbel noise: u = (k + 0.5) / 2^24 formed in float32 rounds to exactly 1.0 for the top bucket (noise = +inf) and
+    the fast log is inaccurate next to 1, so the upper tail of the noise — the draws that let an unlikely token win — was wrong: ~0.5 % of
+    sampled tokens of the letters-steered policy disagreed with the float64 oracle.  With a context-free LM head (steer_to_letters) the
+    oracle's logits are one vector, so EVERY sampled token of 256 episodes is checked (not a sample of three episodes as elsewhere)."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.environment import text_env_eval
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from lmrl_gym_b200.wordle import B200WordleEnv
+    from oracle import gpt2 as og
+    from oracle.mt19937 import seed_stream
+    cfg = _small_cfg()
+    params = _steer_to_letters(init_gpt2_params(cfg, seed=7), tok)
+    B = 256
+    eng = Engine(max_envs=B, max_input_length=128, max_new_tokens=6, max_turns=6, tokenizer=tok)
+    env = B200WordleEnv(eng, "wordle_official.txt", require_words_in_vocab=False)
+    pol = B200GPT2Policy(eng, params, cfg, seed=11)
+    inter, _ = text_env_eval(env, pol, n_rollouts=B, seed_generator=seed_stream(2), bsize=B, verbose=False)
+    seeds = seed_stream(2)
+    seed_list = [next(seeds) for _ in range(B)]
+    logits = og.forward_last_logits(params, tok.encode("Wordle:\n"), cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+    other = og.forward_last_logits(params, tok.encode("Wordle:\na b c\n\n"), cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+    assert np.abs(logits - other).max() < 1e-6                     # the head really is context-free
+    n = bad = rare = 0
+    letters = set(int(t) for t in np.argsort(-logits)[:53])
+    for i, ep in enumerate(inter):
+        logs, j = ep._logs, ep._i
+        for t in range(len(ep)):
+            for k, tk in enumerate(logs.act_tokens[j, t, :logs.act_len[j, t]].tolist()):
+                s = og.sample_scores(logits, og.row_key(11, seed_list[i], t, k), 1.0, True)
+                n += 1
+                bad += int(s[tk] < s.max() - 2 * TOL_EMU)
+                rare += int(tk not in letters)
+    print(f"{n} sampled tokens, {bad} outside the oracle bound, {rare} low-probability winners (expected ~{n * 4.8e-4:.1f})")
+    assert n > 5000 and bad == 0
     eng.close()

@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from lmrl_gym_b200 import _lib, build
 from lmrl_gym_b200.environment import (BatchedTextEnv, BatchedTextPolicy, Text, TextEnv, TextPolicy, interact_environment,
@@ -252,5 +253,26 @@ def test_gpt2_format_tokenizer_fixture_and_the_trailing_newline_pair():
     per3 = [t for it in items[:3] for t in tok.encode(it)]
     assert joined3 == per3[:-2] + [nlnl] and per3[-2:] == [198, 198]
     assert tok.decode(joined3) == "".join(items[:3]) and tok.token_bytes[tok.encode("Wordle")[0]] == b"Wordle"
+    # runs of k trailing newlines (k = 3: an EMPTY action line between the header / feedback newlines): floor(k / 2) merged + k % 2 plain
+    assert tok.encode("Wordle:\n\n\n")[-2:] == [nlnl, 198] and tok.encode("Wordle:\n\n\n\n")[-2:] == [nlnl, nlnl]
     t = tok.device_tables()
     assert t["tok_first"][ord("c")] == tok.encode("c")[0] and t["tok_space"][ord("r")] == tok.encode(" r")[0]
+
+
+def test_engine_slots_refuse_a_second_role():
+    """ADVICE round 1: tower 1 serves the PPO initial policy OR the ILQL / MC value base, head set 0 the PPO value head OR the Q / V heads;
+    a second role in an occupied slot must raise instead of silently overwriting the first object's weights (host bookkeeping: no GPU)."""
+    from lmrl_gym_b200._lib import LmrlError
+    from lmrl_gym_b200.engine import Engine
+    e = Engine.__new__(Engine)
+    e._slots = {}
+    e.handle = None
+    e.claim_slot("tower", 0, "policy")
+    e.claim_slot("tower", 0, "policy")                                   # same role again: set_params
+    e.claim_slot("tower", 1, "frozen initial policy (PPO KL term)")
+    with pytest.raises(LmrlError, match="already holds the frozen initial policy"):
+        e.claim_slot("tower", 1, "value base")
+    e.claim_slot("value-head set", 0, "PPO value head")
+    with pytest.raises(LmrlError, match="separate engines"):
+        e.claim_slot("value-head set", 0, "ILQL / MC value heads")
+    e.claim_slot("value-head set", 1, "ILQL / MC value heads")

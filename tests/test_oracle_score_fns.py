@@ -136,3 +136,52 @@ def test_product_host_logic_equals_oracle_on_random_histories(seed, monkeypatch)
     want = O.score_histories(kind, full, pre, PAD, max_length, vw, lw, bsize, q_fn=lambda b: (table_q(TAB["q1"], b), table_q(TAB["q2"], b)), v_fn=table_v,
                              pi_fn=lambda b: table_q(TAB["pi"], b))
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+
+
+def test_bc_score_fn_follows_the_reference_truncation_indexing(monkeypatch):
+    """ppo/score_fn.py:86,118: rows are LEFT-truncated to max_length but sliced with the UNtruncated prefix length, and an empty prefix
+    selects `[-1:]` of the padded row.  A numpy restatement of those two lines over a table of per-token log-probs is the oracle; the
+    device call is stubbed with the same table (the BC / PPO score fn used to shift the prefix by the cut)."""
+    import numpy as np
+    from lmrl_gym_b200 import reranker as RR
+    from lmrl_gym_b200.environment import Text
+
+    class Tok:
+        pad_token_id = 0
+
+        def encode(self, s):
+            return [ord(c) for c in s]
+
+    class Pol:
+        class _lmrl_engine:
+            tokenizer = Tok()
+
+    def lp(prev, nxt):                                   # a fixed "model": log p(next | prev) depends on the pair only
+        return -0.01 * ((prev * 7 + nxt * 13) % 97) - 0.5
+
+    def stub(policy, seqs, prefix_lens, **kw):
+        return np.asarray([sum(lp(s[t - 1], s[t]) for t in range(p, len(s))) for s, p in zip(seqs, prefix_lens)], np.float32)
+
+    monkeypatch.setattr(RR, "score_token_sequences", stub)
+
+    def reference(h, max_length):
+        full = [t for it in h for t in Tok().encode(it.text)]
+        pre = len([t for it in h[:-1] for t in Tok().encode(it.text)])
+        row = full[-max_length:] + [0] * (max_length - min(len(full), max_length))
+        mask = [float(t != 0) for t in row]
+        action_logits = [lp(row[j], row[j + 1]) * mask[j + 1] for j in range(max_length - 1)]
+        return float(np.sum(action_logits[(pre - 1):], dtype=np.float64))
+
+    cases = [
+        (Text("abcdefgh", False), Text("xyz", True)),                     # fits: the three action tokens
+        (Text("abcdefghijklmnop", False), Text("xyz", True)),             # truncated: prefix_len - 1 lands past the row's end -> 0.0
+        (Text("abcdefghijk", False), Text("xy", True)),                   # truncated by 1: the slice starts one token late
+        (Text("", False), Text("hello", True)),                           # empty prefix, short row: [-1:] is padding -> 0.0
+        (Text("", False), Text("abcdefghijklmnopq", True)),               # empty prefix, full row: the last column only
+        (Text("ab", False), Text("c", True), Text("de", False), Text("fgh", True)),
+    ]
+    fn = RR.build_bc_score_fn(Pol(), max_length=12)
+    got = fn(cases)
+    want = [reference(h, 12) for h in cases]
+    assert np.allclose(got, want, atol=1e-6), (got, want)
+    assert got[1] == 0.0 and got[3] == 0.0 and got[2] != 0.0 and got[4] != 0.0
