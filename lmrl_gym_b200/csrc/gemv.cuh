@@ -6,8 +6,10 @@
 //   * the R <= 8 activation rows are staged ONCE per CTA in shared memory as fp32 — and when the operand is a LayerNorm of the
 //     fp32 residual stream (ln_1 -> QKV, ln_2 -> FC, ln_f -> LM head) the CTA normalises the rows itself while staging them
 //     (values rounded to bf16 exactly like the tensor-core path's operand), so the small-batch decoder launches no LayerNorm;
-//   * every warp streams groups of 4 consecutive W rows (output features) with 16-byte coalesced loads straight from HBM,
-//     4 x R fp32 accumulators per lane, each shared-memory read of X feeding 4 columns;
+//   * a CTA (4 warps) takes one group of 4 consecutive W rows (output features) at a time and splits K across its warps, so that ALL of
+//     the group's 16-byte coalesced loads are in flight at once (one memory round trip per group instead of K / 2048 dependent ones:
+//     at this size the kernel is a latency chain, not a bandwidth problem); 4 x R fp32 accumulators per lane, each shared-memory
+//     read of X feeding 4 columns; the four warps' partial sums meet in shared memory;
 //   * the 4R partial sums are reduced across the warp with a halving butterfly (4R - 1 + log2(32 / 4R) shuffles instead of
 //     5 * 4R) that leaves ONE finished (column, row) element in each lane, which then runs the epilogue for its element:
 //     bias + KV-page append / q (QKV), fp32 residual add, GeLU -> bf16, or the fused temperature + Gumbel arg-max of the LM head.
@@ -71,14 +73,11 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
     pdl_enter();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = a.K;
-    // the weights do not depend on the previous kernel's output: pull this warp's first group of W rows towards L2 while the
-    // activation rows are being staged (the kernel is a chain of dependent latencies at this size, not a bandwidth problem)
-    {
-        const int grp0 = blockIdx.x * GV_WARPS + warp;
-        if (grp0 < a.N / GV_COLS) {
-            const char* w0 = reinterpret_cast<const char*>(a.W + (size_t)grp0 * GV_COLS * K);
-            for (int off = lane * 128; off < GV_COLS * K * 2; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + off));
-        }
+    // the weights do not depend on the previous kernel's output: pull this CTA's first group of W rows towards L2 while the
+    // activation rows are being staged
+    if ((int)blockIdx.x < a.N / GV_COLS) {
+        const char* w0 = reinterpret_cast<const char*>(a.W + (size_t)blockIdx.x * GV_COLS * K);
+        for (int off = (int)threadIdx.x * 128; off < GV_COLS * K * 2; off += GV_WARPS * 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + off));
     }
     const int M = min(*a.M_dev, R);
     if (M <= 0) return;
@@ -136,45 +135,60 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
         }
     }
     __syncthreads();
-    // ---- stream W: one group of GV_COLS consecutive output features per warp pass ----
+    // ---- stream W: one group of GV_COLS consecutive output features per CTA pass, K split over the warps ----
     constexpr int NV = GV_COLS * R;
+    constexpr int KSTEPS = 4;                                      // K <= 4096: at most 512 chunks = 4 per lane of the CTA
+    __shared__ float gv_red[2][GV_WARPS][32];
     const int my_idx = warp_reduce_many_index<NV>(lane);           // the (column, row) element this lane finishes
     const int my_c = my_idx / R, my_r = my_idx - my_c * R;
-    const bool writer = (lane & ((32 / NV) - 1)) == 0 && my_r < M; // one lane per element (NV < 32: low lane bits replicate)
+    const bool writer = warp == 0 && (lane & ((32 / NV) - 1)) == 0 && my_r < M;   // one lane per element (NV < 32: low lane bits replicate)
     const int n_groups = a.N / GV_COLS, kchunks = K >> 3;
-    float best_s = -INFINITY; int best_c = 0x7FFFFFFF;             // EPI_SAMPLE: running arg-max of this lane's row over its columns
-    for (int grp = blockIdx.x * GV_WARPS + warp; grp < n_groups; grp += gridDim.x * GV_WARPS) {
+    float best_s = -INFINITY; int best_c = 0x7FFFFFFF;             // EPI_SAMPLE: running arg-max of this lane's row over its columns (warp 0)
+    int it = 0;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
         const int n0 = grp * GV_COLS;
         const uint4* w4 = reinterpret_cast<const uint4*>(a.W + (size_t)n0 * K);
+        uint4 wv[KSTEPS][GV_COLS];
+#pragma unroll
+        for (int st = 0; st < KSTEPS; ++st) {                       // every load of the group first
+            const int ch = (st * GV_WARPS + warp) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < GV_COLS; ++c) wv[st][c] = ch < kchunks ? __ldg(w4 + (size_t)c * kchunks + ch) : make_uint4(0, 0, 0, 0);
+        }
         float acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-#pragma unroll 2
-        for (int ch = lane; ch < kchunks; ch += 32) {
-            uint4 wv[GV_COLS];
 #pragma unroll
-            for (int c = 0; c < GV_COLS; ++c) wv[c] = __ldg(w4 + (size_t)c * kchunks + ch);
-            float xf[R][8];
+        for (int st = 0; st < KSTEPS; ++st) {
+            const int ch = (st * GV_WARPS + warp) * 32 + lane;
+            if (ch < kchunks) {
+                float xf[R][8];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4* xs = reinterpret_cast<const float4*>(gv_x + (size_t)r * K);
-                const float4 x0 = xs[ch], x1 = xs[kchunks + ch];
-                xf[r][0] = x0.x; xf[r][1] = x0.y; xf[r][2] = x0.z; xf[r][3] = x0.w; xf[r][4] = x1.x; xf[r][5] = x1.y; xf[r][6] = x1.z; xf[r][7] = x1.w;
-            }
+                for (int r = 0; r < R; ++r) {
+                    const float4* xs = reinterpret_cast<const float4*>(gv_x + (size_t)r * K);
+                    const float4 x0 = xs[ch], x1 = xs[kchunks + ch];
+                    xf[r][0] = x0.x; xf[r][1] = x0.y; xf[r][2] = x0.z; xf[r][3] = x0.w; xf[r][4] = x1.x; xf[r][5] = x1.y; xf[r][6] = x1.z; xf[r][7] = x1.w;
+                }
 #pragma unroll
-            for (int c = 0; c < GV_COLS; ++c) {
-                float wf[8];
-                bf16x8_to_float(wv[c], wf);
+                for (int c = 0; c < GV_COLS; ++c) {
+                    float wf[8];
+                    bf16x8_to_float(wv[st][c], wf);
 #pragma unroll
-                for (int r = 0; r < R; ++r)
+                    for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) acc[c * R + r] = fmaf(wf[t], xf[r][t], acc[c * R + r]);
+                        for (int t = 0; t < 8; ++t) acc[c * R + r] = fmaf(wf[t], xf[r][t], acc[c * R + r]);
+                }
             }
         }
         const int n = n0 + my_c;
-        const float bias_n = a.bias ? __ldg(a.bias + n) : 0.f;     // issued before the shuffle tree, consumed after it
+        const float bias_n = (warp == 0 && a.bias) ? __ldg(a.bias + n) : 0.f;     // issued before the shuffle tree, consumed after it
         warp_reduce_many<NV>(acc, lane);
-        float val = acc[0] + bias_n;
+        gv_red[it & 1][warp][lane] = acc[0];                         // the warps' K-partials of element (my_c, my_r) meet here
+        __syncthreads();                                            // (double buffered: one barrier per group)
+        if (warp != 0) continue;
+        float val = bias_n;
+#pragma unroll
+        for (int w = 0; w < GV_WARPS; ++w) val += gv_red[it & 1][w][lane];
         if constexpr (EPI == EPI_SAMPLE) {
             if (my_r < M && n < a.n_vocab) {
                 if (a.logits_out && writer) a.logits_out[(size_t)my_r * a.n_vocab + n] = val;
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
             const int oc = __shfl_xor_sync(0xFFFFFFFFu, best_c, o), orow = __shfl_xor_sync(0xFFFFFFFFu, my_r, o);
             if (orow == my_r && (os > best_s || (os == best_s && oc < best_c))) { best_s = os; best_c = oc; }
         }
-        if (my_r < M && best_c != 0x7FFFFFFF) atomicMax(a.best + my_r, pack_best(best_s, best_c));
+        if (warp == 0 && my_r < M && best_c != 0x7FFFFFFF) atomicMax(a.best + my_r, pack_best(best_s, best_c));
     }
 }
 

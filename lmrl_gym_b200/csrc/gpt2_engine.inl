@@ -403,7 +403,7 @@ static int launch_gemv_r(lmrl_engine* e, const GemvArgs& a) {
         configured = true;
     }
     const int n_groups = a.N / GV_COLS;
-    const int grid = std::max(1, std::min((n_groups + GV_WARPS - 1) / GV_WARPS, G.sm_count * 4));
+    const int grid = std::max(1, std::min(n_groups, G.sm_count * 8));          // one group of 4 output features per CTA pass
     LMRL_CUDA(launch_k(G.use_pdl, 1, gemv_kernel<EPI, R, LN>, dim3(grid), dim3(GV_WARPS * 32), smem, G.cur->st, a));
     return 0;
 }

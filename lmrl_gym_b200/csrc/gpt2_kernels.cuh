@@ -472,6 +472,14 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 __device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, uint64_t policy) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "l"(policy));
 }
+// src_bytes = 16: plain copy; 0: nothing is read from global memory and the 16 shared-memory bytes are zero-filled (keys past the
+// last visible one: masked anyway, but stale shared memory could hold NaN patterns and 0 * NaN would poison P.V)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async16_zfill_hint(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(policy));
+}
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
@@ -497,12 +505,14 @@ __device__ __forceinline__ void attp_rows(const __nv_bfloat16* __restrict__ q, c
         for (int c = 0; c < 8; ++c) {
             const int idx = c * 32 + lane, key = idx >> 3, ch = idx & 7;
             const uint32_t off = key * 128 + ((ch ^ (key & 7)) << 4);
+            const uint32_t nb = k0 + key < n_keys ? 16u : 0u;         // the last block of a context: only the visible keys are read (round 1
+                                                                      // fetched the whole 32-key block: +16 keys per (env, head) on average)
             if (keep) {
-                cp_async16_hint(sK + off, gK + pbase + (size_t)key * 64 + ch * 8, pol_last);
-                cp_async16_hint(sV + off, gV + pbase + (size_t)key * 64 + ch * 8, pol_last);
+                cp_async16_zfill_hint(sK + off, gK + pbase + (size_t)key * 64 + ch * 8, nb, pol_last);
+                cp_async16_zfill_hint(sV + off, gV + pbase + (size_t)key * 64 + ch * 8, nb, pol_last);
             } else {
-                cp_async16(sK + off, gK + pbase + (size_t)key * 64 + ch * 8);
-                cp_async16(sV + off, gV + pbase + (size_t)key * 64 + ch * 8);
+                cp_async16_zfill(sK + off, gK + pbase + (size_t)key * 64 + ch * 8, nb);
+                cp_async16_zfill(sV + off, gV + pbase + (size_t)key * 64 + ch * 8, nb);
             }
         }
         cp_async_commit();
