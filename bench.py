@@ -539,9 +539,10 @@ def run_workload(args, workload, rank, world, local, barrier, log, skip, headlin
         eng.profile_enable(False)
         one_steps = int(ep_len_dev[0].sum().item())
         ms, steps_v = reduce_max_sum(ms, steps_v, world)
+        att_b = sum(vprof["tags"].get(k, dict(work=0.0))["work"] for k in ("attention_decode", "attention_prefill"))
         return dict(value=steps_v / (ms / 1000.0), unit=UNIT, ms_per_step=ms / K, mean_return=ret_v, mean_episode_length=steps_v / (K * B * world),
                     decoder_rows_per_step=vprof["rows"], sampled_tokens_per_step=vprof["sampled"],
-                    decoder_rows_per_env_step=vprof["rows"] / max(one_steps, 1)), vprof, one_steps
+                    decoder_rows_per_env_step=vprof["rows"] / max(one_steps, 1), _att_bytes=att_b), vprof, one_steps
 
     # ---- same engine, policy steered to the token shape of a trained Wordle policy (~5 letter tokens + newline per action):
     #      prompts grow by ~7 tokens per turn instead of ~20 (SURVEY.md §8d's token counts); secondary number, not the headline
@@ -550,6 +551,7 @@ def run_workload(args, workload, rank, world, local, barrier, log, skip, headlin
         from lmrl_gym_b200.gpt2 import steer_to_letters
         pol.set_params(steer_to_letters(params, tok))
         letters_variant, _, _ = variant_run("letters")
+        letters_variant.pop("_att_bytes", None)
         letters_variant["variant"] = ("2d: random-init GPT-2-small with the LM head steered to letter tokens + newline (well-formed 5-letter-ish "
                                       "guesses, almost never vocabulary words): the token shape of a trained policy")
         pol.set_params(params)
@@ -641,10 +643,9 @@ def run_workload(args, workload, rank, world, local, barrier, log, skip, headlin
             line["letters_variant"] = letters_variant
         if variant_2c is not None:
             if variant_2c.get("decoder_rows_per_env_step"):
+                steps_1 = max(variant_2c["decoder_rows_per_step"] / variant_2c["decoder_rows_per_env_step"], 1)      # env-steps of the profiled batch
                 variant_2c["section_8d"] = section_8d(variant_2c["value"] / world, variant_2c["decoder_rows_per_env_step"],
-                                                      variant_2c["sampled_tokens_per_step"] / max(variant_2c["decoder_rows_per_step"] / variant_2c["decoder_rows_per_env_step"], 1),
-                                                      0.0, peaks, B)
-                variant_2c["section_8d"]["note"] = "attention bytes not included in this variant's byte count (no per-kernel pass was run for it)"
+                                                      variant_2c["sampled_tokens_per_step"] / steps_1, variant_2c.pop("_att_bytes", 0.0) / steps_1, peaks, B)
             line["variant_2c"] = variant_2c
         if small_batch is not None:
             line["small_batch"] = small_batch
