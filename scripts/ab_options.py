@@ -43,7 +43,12 @@ def main():
     for combo in args.combos.split(";"):
         opts = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in combo.split(",") if kv)
         for k, v in opts.items():
-            eng.set_option(k, v)
+            if k == "pdl":
+                eng.set_use_pdl(bool(v))
+            elif k == "graphs":
+                eng.set_use_graphs(bool(v))
+            else:
+                eng.set_option(k, v)
         for _ in range(3):
             eng.rollout_dev(ENV_WORDLE, seeds.data_ptr(), B, s, out)
         eng.sync()
