@@ -342,6 +342,11 @@ __global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant_
                                                                                    const GemmArgs g) {
     extern __shared__ unsigned char tc_smem_raw[];
     pdl_trigger();                                                       // the next kernel may start its prologue behind my tail
+    // the live row count: issued FIRST so that its global-memory round trip (~0.7 us, on the critical path of every launch: no TMA can be
+    // issued before the tile count is known) overlaps barrier initialisation and the TMEM allocation.  With programmatic dependent
+    // launch the predecessor must be complete before the load (griddepcontrol.wait); PDL is off by default (measured slower).
+    pdl_wait();
+    const int M = __ldg(g.M_dev);
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                        // 128B swizzle atoms need 1024-byte alignment
     unsigned char* base_ptr = tc_smem_raw + (base - raw);
@@ -380,9 +385,6 @@ __global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // everything above touched only shared memory / TMEM / kernel parameters; global memory of the predecessor from here on
-    pdl_wait();
-    const int M = *g.M_dev;
     const int n_tiles = g.N / BN, m_tiles = (M + TC_BM - 1) / TC_BM, total = M > 0 ? n_tiles * m_tiles : 0;
 
     if (warp == 0) {

@@ -171,6 +171,7 @@ struct Gpt2Dev {
     int fuse_ln = 0;
     int attn_wide = 1;                // prefill attention: 32 query rows per warp pass (two m16 tiles share every staged K / V block)
     int gemv_max_rows = 8;            // batches of at most this many envs decode through the weight-streaming GEMV kernels
+    int att_grid_mult = 8;            // decode attention: grid cap in CTAs per SM (grid-stride beyond it)
     int nlnl_id = -1;                 // id of the tokenizer's '\n\n' token (joined-history prompts fold a trailing newline pair into it); -1 = none
     int fold_nlnl = -1;               // nlnl_id while a fused Wordle rollout is being enqueued, -1 on the text paths (their callers tokenise themselves)
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
@@ -499,7 +500,7 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     const lmrl_gpt2_dims& D = G.dims;
     cudaStream_t st = Ln.st;
     const int ew_blocks = G.sm_count * 8;
-    const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * 8);
+    const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * G.att_grid_mult);
     // ln_2 of this layer rides on the attention-projection GEMM, ln_1 of the next layer on the MLP-projection GEMM (tcgen05
     // one-CTA kernel only); layer 0's ln_1 is the one LayerNorm launch of the pass
     const bool fuse = G.fuse_ln && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
@@ -1473,6 +1474,7 @@ static int* option_slot(lmrl::Gpt2Dev& G, const char* name) {
     if (!strcmp(name, "attn_wide")) return &G.attn_wide;
     if (!strcmp(name, "gemv_max_rows")) return &G.gemv_max_rows;
     if (!strcmp(name, "tok_nlnl_id")) return &G.nlnl_id;
+    if (!strcmp(name, "att_grid_mult")) return &G.att_grid_mult;
     return nullptr;
 }
 
