@@ -347,6 +347,9 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
  *                    0 16-row passes
  *   "gemv_max_rows"  decode passes of batches with at most this many envs run the weight-streaming GEMV kernels instead of
  *                    128-row tensor-core tiles (default 8; 0 disables)
+ *   "att_decode_impl" decode-pass attention: 0 (default) the streaming SIMT kernel, 1 the cp.async-staged tensor-core prefill kernel with one
+ *                    row per slot, 2 the SIMT kernel with software-pipelined K / V loads (bit-identical to 0).  Both alternatives measured
+ *                    1-2 % slower per rollout on B200; "att_grid_mult" caps the SIMT kernel's grid at that many CTAs per SM (default 8)
  *   "tok_nlnl_id"    id of the tokenizer's '\n\n' token, -1 (default) = none.  The reference encodes the JOINED history every turn
  *                    (ppo/gpt2/interface.py:519-522), so with GPT-2's merges a prompt ending in an action line + an empty feedback
  *                    line ends in that single token; the fused rollout reproduces this in its prompt view (the stream itself stays

@@ -172,6 +172,7 @@ struct Gpt2Dev {
     int attn_wide = 1;                // prefill attention: 32 query rows per warp pass (two m16 tiles share every staged K / V block)
     int gemv_max_rows = 8;            // batches of at most this many envs decode through the weight-streaming GEMV kernels
     int att_grid_mult = 8;            // decode attention: grid cap in CTAs per SM (grid-stride beyond it)
+    int att_decode_impl = 0;          // 0 = SIMT streaming kernel for decode passes, 1 = the tensor-core (cp.async staged) prefill kernel with one row per slot
     int nlnl_id = -1;                 // id of the tokenizer's '\n\n' token (joined-history prompts fold a trailing newline pair into it); -1 = none
     int fold_nlnl = -1;               // nlnl_id while a fused Wordle rollout is being enqueued, -1 on the text paths (their callers tokenise themselves)
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
@@ -539,9 +540,12 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
         if (launch_gemm<EPI_QKV>(e, a, a.N, 0, Ln.m_cap, a.N, 0)) return -1;
         // algorithmic bytes: every cached K and V position of the contributing envs once (bf16) + q in / out rows
         if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
-        if (mode == 0)
+        if (mode == 0 || G.att_decode_impl == 1)
             LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, attp_grid(n_env, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
                                                                                           0.125f * 1.4426950408889634f, G.attn_wide, Ln.att));
+        else if (G.att_decode_impl == 2)
+            LMRL_LAUNCH(-1, LMRL_K(attention_pipe_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
+                                                                                                  0.125f, Ln.att));
         else
             LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
                                                                                              0.125f, Ln.att));
@@ -1475,6 +1479,7 @@ static int* option_slot(lmrl::Gpt2Dev& G, const char* name) {
     if (!strcmp(name, "gemv_max_rows")) return &G.gemv_max_rows;
     if (!strcmp(name, "tok_nlnl_id")) return &G.nlnl_id;
     if (!strcmp(name, "att_grid_mult")) return &G.att_grid_mult;
+    if (!strcmp(name, "att_decode_impl")) return &G.att_decode_impl;
     return nullptr;
 }
 

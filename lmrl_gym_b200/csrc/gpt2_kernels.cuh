@@ -449,6 +449,113 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_kernel(const __nv
     }
 }
 
+// ---- K3, software-pipelined variant ---------------------------------------------------------------------------------------
+// Same arithmetic as attention_kernel (bit-identical results), but the K / V loads of the NEXT 16-key step are issued before the current
+// step is consumed (two register buffers), so an item's dependent memory round trips drop from ceil(ctx / 16) to about half: at the
+// contexts of a Wordle rollout (30-110 keys) the streaming kernel is bound by those round trips per (slot, head), not by bandwidth.
+__device__ __forceinline__ void att_load_step(const uint4* __restrict__ gK, const uint4* __restrict__ gV, int my_page, int n_head, int head, int j0,
+                                              int g, int nkeys, uint4 (&kk)[4], uint4 (&vv)[4]) {
+    const int page = __shfl_sync(0xFFFFFFFFu, my_page, j0 >> KV_PAGE_SHIFT);
+    const size_t pbase = (((size_t)page * n_head + head) * KV_PAGE + (j0 & (KV_PAGE - 1))) * 8;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const bool ok = j0 + 4 * u + g < nkeys;
+        kk[u] = ok ? __ldg(gK + pbase + (size_t)(4 * u + g) * 8) : make_uint4(0, 0, 0, 0);
+        vv[u] = ok ? __ldg(gV + pbase + (size_t)(4 * u + g) * 8) : make_uint4(0, 0, 0, 0);
+    }
+}
+__device__ __forceinline__ void att_consume_step(const uint4 (&kk)[4], const uint4 (&vv)[4], const float (&qf)[8], int j0, int g, int nkeys,
+                                                 float& m, float& l, float (&acc)[8]) {
+    float sc[4];
+    float cm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        float kf[8];
+        bf16x8_to_float(kk[u], kf);
+        float dot = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) dot = fmaf(qf[t], kf[t], dot);
+        dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 1);
+        dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 2);
+        dot += __shfl_xor_sync(0xFFFFFFFFu, dot, 4);
+        sc[u] = (j0 + 4 * u + g < nkeys) ? dot : -INFINITY;
+        cm = fmaxf(cm, sc[u]);
+    }
+    if (cm > -INFINITY) {
+        const float m_new = fmaxf(m, cm);
+        const float corr = __expf(m - m_new);
+        l *= corr;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] *= corr;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float p = __expf(sc[u] - m_new);
+            float vf[8];
+            bf16x8_to_float(vv[u], vf);
+            l += p;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) acc[t] = fmaf(p, vf[t], acc[t]);
+        }
+        m = m_new;
+    }
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32, 2) attention_pipe_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                           const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
+                                                                           int d_model, KvPages kv, float scale, __nv_bfloat16* __restrict__ out) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, s = lane & 7;
+    const int total = *rows.n_slots * n_head;
+    const uint4* gK = reinterpret_cast<const uint4*>(kcache) + s;
+    const uint4* gV = reinterpret_cast<const uint4*>(vcache) + s;
+    for (int w = blockIdx.x * ATT_WARPS + warp; w < total; w += gridDim.x * ATT_WARPS) {
+        const int slot = w / n_head, head = w - slot * n_head;
+        const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
+        const int my_page = lane < kv.ppe ? kv.table[(size_t)e * kv.ppe + lane] : 0;
+        for (int i = 0; i < n; ++i) {
+            const int r = r0 + i, nkeys = rows.row_pos[r] + 1;
+            uint4 ka[4], va[4], kb[4], vb[4];
+            att_load_step(gK, gV, my_page, n_head, head, 0, g, nkeys, ka, va);            // in flight while q arrives
+            float qf[8];
+            {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(q + (size_t)r * d_model + head * 64) + s);
+                bf16x8_to_float(u, qf);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) qf[t] *= scale;
+            }
+            float m = -INFINITY, l = 0.f;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int j0 = 0; j0 < nkeys; j0 += 32) {
+                const bool has_b = j0 + 16 < nkeys;
+                if (has_b) att_load_step(gK, gV, my_page, n_head, head, j0 + 16, g, nkeys, kb, vb);
+                att_consume_step(ka, va, qf, j0, g, nkeys, m, l, acc);
+                if (has_b) {
+                    if (j0 + 32 < nkeys) att_load_step(gK, gV, my_page, n_head, head, j0 + 32, g, nkeys, ka, va);
+                    att_consume_step(kb, vb, qf, j0 + 16, g, nkeys, m, l, acc);
+                }
+            }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                const float m_o = __shfl_xor_sync(0xFFFFFFFFu, m, o), l_o = __shfl_xor_sync(0xFFFFFFFFu, l, o);
+                const float m_n = fmaxf(m, m_o);
+                const float c1 = m > -INFINITY ? __expf(m - m_n) : 0.f, c2 = m_o > -INFINITY ? __expf(m_o - m_n) : 0.f;
+                l = l * c1 + l_o * c2;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) acc[t] = acc[t] * c1 + __shfl_xor_sync(0xFFFFFFFFu, acc[t], o) * c2;
+                m = m_n;
+            }
+            if (g == 0) {
+                const float inv = 1.0f / l;
+                __nv_bfloat162 o2[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+                *reinterpret_cast<uint4*>(out + (size_t)r * d_model + head * 64 + s * 8) = *reinterpret_cast<const uint4*>(o2);
+            }
+        }
+    }
+}
+
 // ---- K3 (prefill): tensor-core attention for slots that bring many rows ------------------------------------------
 // One warp per (slot, head).  MT m16 tiles of query rows (16 or 32 rows of the slot) are held as mma A fragments; the (env, head)
 // K / V slabs are staged 32 keys at a time into per-warp shared memory (cp.async, 128-byte rows, XOR-swizzled 16-byte

@@ -341,6 +341,17 @@ def test_fused_layernorm_and_wide_prefill_attention_are_bit_identical(tok):
         same_tok = np.mean([a == b for a, b in zip(outs[(1, 1)][1], ref_gen)])
         print(f"{cfg.d_model}: fused-LN vs separate-LN max |logit diff| {d:.3g} (bit-identical: {bool(d == 0)}), identical sampled rows {same_tok:.3f}")
         assert d <= 2e-3 and same_tok >= 0.97
+        # decode-attention variants: the software-pipelined SIMT kernel is the same arithmetic (identical tokens); the staged tensor-core
+        # kernel rounds P to bf16 before P.V like the prefill passes do (tokens agree except at near-ties)
+        eng.set_option("fuse_ln", 0)
+        eng.set_option("attn_wide", 1)
+        base = pol.generate_tokens(prompts, episode_keys=keys, turn=1)
+        eng.set_option("att_decode_impl", 2)
+        assert pol.generate_tokens(prompts, episode_keys=keys, turn=1) == base
+        eng.set_option("att_decode_impl", 1)
+        staged = pol.generate_tokens(prompts, episode_keys=keys, turn=1)
+        assert np.mean([a == b for a, b in zip(staged, base)]) >= 0.9
+        eng.set_option("att_decode_impl", 0)
         with pytest.raises(Exception):
             eng.set_option("no_such_option", 1)
         eng.close()
