@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
     // [R][2][K / 8] float4: fp32 copies of the bf16-valued activations; plane h holds elements 8c + 4h .. 8c + 4h + 3 of every 8-element
     // chunk c, so that the 32 lanes of a warp (consecutive chunks) read consecutive float4 from either plane: no bank conflicts
     extern __shared__ __align__(16) float gv_x[];
-    pdl_enter();
+    pdl_trigger();                                                // (programmatic dependent launch: the next kernel may begin its own prologue)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = a.K;
     // the weights do not depend on the previous kernel's output: pull this CTA's first group of W rows towards L2 while the
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvArgs a) {
         const char* w0 = reinterpret_cast<const char*>(a.W + (size_t)blockIdx.x * GV_COLS * K);
         for (int off = (int)threadIdx.x * 128; off < GV_COLS * K * 2; off += GV_WARPS * 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(w0 + off));
     }
+    pdl_wait();                                                   // everything below reads what the previous kernel wrote
     const int M = min(*a.M_dev, R);
     if (M <= 0) return;
     // ---- stage the activation rows (zero rows beyond M) ----

@@ -66,6 +66,7 @@ __device__ __forceinline__ void kv_ensure_page(const KvPages& kv, int e, int pg)
     }
 }
 __global__ void kv_reset_kernel(KvPages kv, int n_env) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_env * kv.ppe) kv.table[i] = -1;
     if (i == 0) { *kv.n_alloc = 0; *kv.overflow = 0; }
