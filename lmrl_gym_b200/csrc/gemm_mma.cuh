@@ -71,6 +71,16 @@ struct GemmArgs {
     __nv_bfloat16* ln_out;       // [M, N] bf16
     int* ln_cnt;                 // [ceil(Mcap / 128)] arrival counters, zero between launches
     float ln_eps;
+    // LayerNorm folded into the CONSUMER GEMM (tcgen05 one-CTA kernel; Gpt2Dev::ln_fold).  LN(x)·W^T + b = rstd * (x · W''^T) + b' with
+    // W''[n][k] = gamma[k] W[n][k] - mean_k(gamma[k] W[n][k]) (row-centred, so the mean of x drops out of the product) and
+    // b'[n] = b[n] + sum_k beta[k] W[n][k]: the consumer reads the RAW residual stream as a bf16 copy and only needs 1/sigma per row.
+    //   producer (EPI_RESID with xb_out): reads x, writes x + acc + bias (fp32) and its bf16 copy, and the per-row partial
+    //            (sum, sum of squares) of its columns into stat_out[row][stat_slot0 + 2 * n_tile + half] — fixed slots, no atomics: deterministic
+    //   consumer (EPI_QKV / EPI_GELU with stat_in): rstd from the stat_n partial pairs of the row, epilogue value = rstd * acc + bias'
+    __nv_bfloat16* xb_out;       // [M, N] bf16 copy of the updated residual stream
+    float2* stat_out;            // [M][8] partial (sum, sumsq)
+    const float2* stat_in;       // [M][8]
+    int stat_n;                  // partial pairs per row to add up (consumer)
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 3, GEMM_THREADS = 256;

@@ -140,6 +140,10 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 32 contiguous bytes per thread (sm_100: 256-bit global store): one full sector per lane
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -161,9 +165,22 @@ __device__ __forceinline__ float4 tc_bias4(const GemmArgs& g, uint32_t sbias, in
     return __ldg(reinterpret_cast<const float4*>(g.bias + n0 + c));
 }
 
-template <int EPI, int BN = TC_BN>
+// XB residual epilogue: coalesced read of a warp's 32-row x 32-column fp32 box of x (lane -> row 4i + lane / 8, 16-byte chunk lane % 8)
+__device__ __forceinline__ void tc_xb_load_box(const GemmArgs& g, int M, int brow0, int col, int lane, float4 xin[8]) {
+    const int lr = lane >> 3, lc = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = brow0 + 4 * i + lr;
+        xin[i] = r < M ? __ldcg(reinterpret_cast<const float4*>(g.resid + (size_t)r * g.N + col) + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int EPI, int BN = TC_BN, bool XB = false>
 __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorMap& tmOut, uint32_t t_addr, int M, int m0, int n0, int quad,
-                                              int lane, uint32_t stg, int c_beg, uint32_t sbias) {
+                                              int lane, uint32_t stg, int c_beg, uint32_t sbias, float rs = 1.0f, float4* xin = nullptr, int nm0 = -1, int nn0 = 0) {
+    // xin (XB only): the first two chunks' boxes of x, loaded BEFORE the accumulator wait (by the caller, or by the previous tile's call when
+    // nm0 / nn0 = origin of this CTA's next tile was passed: with an even chunk count the two-deep x prefetch runs on across tiles)
+    // rs: per-row scale of the accumulator (1 / sigma of the row when the LayerNorm is folded into this GEMM's weights, else 1)
     constexpr int NCH = BN / 64;                                                   // 32-column chunks per warp (half a tile)
     const int row = m0 + quad * 32 + lane;                                         // this thread's output row
     uint32_t rr[2][32];
@@ -187,18 +204,72 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
             if (live) {
                 const int c = n0 + c0 - part * g.d_model;                  // column inside K (or V): head = c / 64
                 __nv_bfloat16* dst = cache + base_off + (size_t)(c >> 6) * (32 * 64) + (c & 63);
+                uint32_t pk[16];                                           // 32 columns = 64 bytes: two 32-byte stores (one full sector per lane each)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 b0 = tc_bias4(g, sbias, n0, c0 + 8 * j), b1 = tc_bias4(g, sbias, n0, c0 + 8 * j + 4);
-                    uint4 pk;
-                    pk.x = pack_bf16x2_tc(__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
-                    pk.y = pack_bf16x2_tc(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
-                    pk.z = pack_bf16x2_tc(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
-                    pk.w = pack_bf16x2_tc(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
-                    *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = tc_bias4(g, sbias, n0, c0 + 4 * j);
+                    pk[2 * j] = pack_bf16x2_tc(fmaf(rs, __uint_as_float(r[4 * j]), b.x), fmaf(rs, __uint_as_float(r[4 * j + 1]), b.y));
+                    pk[2 * j + 1] = pack_bf16x2_tc(fmaf(rs, __uint_as_float(r[4 * j + 2]), b.z), fmaf(rs, __uint_as_float(r[4 * j + 3]), b.w));
                 }
+                st_global_v8(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                st_global_v8(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
             }
         }
+    } else if constexpr (EPI == EPI_RESID && XB) {
+        // residual GEMM that also feeds a LayerNorm-folded consumer.  Per 32-column chunk the warp
+        //   1. reads its 32-row x 128-byte box of x with COALESCED 16-byte loads (lane -> row 4i + lane / 8, chunk lane % 8: four full lines
+        //      per instruction; a first version had every thread read its own row, 32 lines per instruction, and was L1-wavefront bound:
+        //      +17 ms per rollout), one chunk ahead of its use, and parks it in the swizzled staging box,
+        //   2. every thread updates ITS row in place (x + acc + bias) and the box leaves through a plain TMA store,
+        //   3. the bf16 copy of the row goes out as two 32-byte stores per thread (full sectors), and the row's partial (sum, sum of squares)
+        //      over this warp's columns lands in a fixed slot: no atomics, deterministic.
+        const bool live = row < M;
+        const int lr = lane >> 3, lc = lane & 7;
+        const int brow0 = m0 + quad * 32;                                  // first row of the warp's box
+        __nv_bfloat16* brow = g.xb_out + (size_t)row * g.N + n0;
+        float s1 = 0.f, s2 = 0.f;
+        // x boxes are loaded TWO chunks ahead (xin[8 * (ci & 1)]).  The TMEM chunk is single buffered here (registers): the next chunk's load is
+        // issued as soon as this chunk's accumulator values are consumed, and is in flight during the stores and the next box's staging
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c0 = c_beg + 32 * ci;
+            float4* xc = xin + 8 * (ci & 1);
+            if (lane == 0) bulk_wait_read<0>();                            // the TMA engine has read the previous box
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int br = 4 * i + lr;
+                st_shared_v4(stg + br * 128 + ((lc ^ (br & 7)) << 4), __float_as_uint(xc[i].x), __float_as_uint(xc[i].y), __float_as_uint(xc[i].z), __float_as_uint(xc[i].w));
+            }
+            __syncwarp();
+            if (ci + 2 < NCH) tc_xb_load_box(g, M, brow0, n0 + c0 + 64, lane, xc);
+            else if (NCH % 2 == 0 && nm0 >= 0) tc_xb_load_box(g, M, nm0 + quad * 32, nn0 + c_beg + 32 * (ci + 2 - NCH), lane, xc);
+            tmem_ld_wait();
+            const uint32_t* r = rr[0];
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                                  // 4 columns of this thread's row per step
+                const uint32_t addr = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+                const float4 x4 = ld_shared_f4(addr);
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.bias) b = tc_bias4(g, sbias, n0, c0 + 4 * j);
+                const float4 v = make_float4(x4.x + (__uint_as_float(r[4 * j]) + b.x), x4.y + (__uint_as_float(r[4 * j + 1]) + b.y),
+                                             x4.z + (__uint_as_float(r[4 * j + 2]) + b.z), x4.w + (__uint_as_float(r[4 * j + 3]) + b.w));
+                st_shared_v4(addr, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                s1 += (v.x + v.y) + (v.z + v.w);
+                s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+                pk[2 * j] = pack_bf16x2_tc(v.x, v.y); pk[2 * j + 1] = pack_bf16x2_tc(v.z, v.w);
+            }
+            if (ci + 1 < NCH) tmem_ld_32x32b_x32_issue(t_addr + c0 + 32, rr[0]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&tmOut, stg, n0 + c0, brow0); bulk_commit(); }
+            if (live) {
+                st_global_v8(brow + c0, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                st_global_v8(brow + c0 + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            }
+        }
+        if (live) g.stat_out[(size_t)row * 8 + 2 * (n0 / BN) + (c_beg != 0 ? 1 : 0)] = make_float2(s1, s2);
     } else if constexpr (EPI == EPI_RESID) {
         // fp32 residual: 32-column boxes, x += acc + bias by TMA reduce-add
 #pragma unroll
@@ -236,9 +307,9 @@ __device__ __forceinline__ void tc_store_tile(const GemmArgs& g, const CUtensorM
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                                  // 8 columns -> one 16-byte chunk
                 const float4 b0 = tc_bias4(g, sbias, n0, c0 + 8 * j), b1 = tc_bias4(g, sbias, n0, c0 + 8 * j + 4);
-                float v[8] = {__uint_as_float(r[8 * j]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y, __uint_as_float(r[8 * j + 2]) + b0.z,
-                              __uint_as_float(r[8 * j + 3]) + b0.w, __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
-                              __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+                float v[8] = {fmaf(rs, __uint_as_float(r[8 * j]), b0.x), fmaf(rs, __uint_as_float(r[8 * j + 1]), b0.y), fmaf(rs, __uint_as_float(r[8 * j + 2]), b0.z),
+                              fmaf(rs, __uint_as_float(r[8 * j + 3]), b0.w), fmaf(rs, __uint_as_float(r[8 * j + 4]), b1.x), fmaf(rs, __uint_as_float(r[8 * j + 5]), b1.y),
+                              fmaf(rs, __uint_as_float(r[8 * j + 6]), b1.z), fmaf(rs, __uint_as_float(r[8 * j + 7]), b1.w)};
                 if constexpr (EPI == EPI_GELU) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] = gelu_new(v[q]);
@@ -332,7 +403,9 @@ __device__ __forceinline__ void sample_chunk(const uint32_t r[32], int col0, flo
     for (int j = 0; j < 32; ++j) sample_update<NOISE, MASK>(__uint_as_float(r[j]), col0 + j, inv_temp, key, n_vocab, best[j & 3], best_col[j & 3]);
 }
 
-template <int EPI, int BN = TC_BN>
+// XB (EPI_RESID only): the residual epilogue that also writes the bf16 copy + row statistics for a LayerNorm-folded consumer
+// (GemmArgs::xb_out / stat_out); its own instantiation so that its register allocation does not touch the plain kernels
+template <int EPI, int BN = TC_BN, bool XB = false>
 // 168 registers per thread: the pipelined epilogues (two TMEM chunks in flight) and the fused LayerNorm (two rows in flight) without spills
 __global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                                    const __grid_constant__ CUtensorMap tmW,
@@ -446,14 +519,51 @@ __global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant_
         const uint32_t sbias = (STORING && g.bias) ? bias_base : 0u;
         auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };      // named barrier of the eight epilogue warps
         int acc = 0; uint32_t acc_phase = 0;
+        float4 xin[16];                                                            // XB residual epilogue: two boxes of x in flight
+        bool x_ready = false;
+        float bias_next = 0.f;                                                     // this thread's bias value of the CTA's next tile
+        if (sbias && et < BN && (int)blockIdx.x < total) bias_next = __ldg(g.bias + ((int)blockIdx.x % n_tiles) * BN + et);
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
             if (sbias) {
                 // the tile's bias goes to shared memory once (while the MMAs of this tile are still running) instead of
-                // every thread re-loading all BN values from global memory for its own row
+                // every thread re-loading all BN values from global memory for its own row.  The value was fetched into a register
+                // during the PREVIOUS tile's epilogue: no global-memory round trip between the two barriers
                 epi_bar();                                                         // nobody still reads the previous tile's values
-                if (et < BN) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * (uint32_t)et), "f"(__ldg(g.bias + n0 + et)) : "memory");
+                if (et < BN) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * (uint32_t)et), "f"(bias_next) : "memory");
                 epi_bar();
+                const int nt_b = tile + gridDim.x;
+                if (nt_b < total && et < BN) bias_next = __ldg(g.bias + (nt_b % n_tiles) * BN + et);
+            }
+            int nm0 = -1, nn0 = 0;
+            if constexpr (EPI == EPI_RESID && XB) {
+                // the NEXT tile's part of x on its way into L2 (the plain epilogue's reduce-add never waits for x; this one reads it)
+                const int nt = tile + gridDim.x;
+                if (nt < total) {
+                    nm0 = (nt / n_tiles) * TC_BM; nn0 = (nt % n_tiles) * BN;
+                    const int prow = nm0 + quad * 32 + lane;
+                    if (prow < M) {
+                        const float* px = g.resid + (size_t)prow * g.N + nn0 + half * (BN / 2);
+#pragma unroll
+                        for (int k = 0; k < BN / 2; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + k));
+                    }
+                }
+                if (!x_ready) {                                                    // the first two x boxes of this warp: under the tile's MMAs
+                    tc_xb_load_box(g, M, m0 + quad * 32, n0 + half * (BN / 2), lane, xin);
+                    tc_xb_load_box(g, M, m0 + quad * 32, n0 + half * (BN / 2) + 32, lane, xin + 8);
+                }
+                x_ready = (BN / 64) % 2 == 0 && nm0 >= 0;                          // even chunk count: this tile's epilogue loads the next tile's first boxes
+            }
+            // LayerNorm-folded consumer: the row's partial (sum, sum of squares) pairs, also fetched under the MMAs
+            float4 st4[4];
+            bool has_stat = false;
+            if constexpr (EPI == EPI_QKV || EPI == EPI_GELU) {
+                has_stat = g.stat_in != nullptr && m0 + quad * 32 + lane < M;
+                if (has_stat) {
+                    const float4* sp = reinterpret_cast<const float4*>(g.stat_in + (size_t)(m0 + quad * 32 + lane) * 8);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) st4[i] = __ldcg(sp + i);
+                }
             }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
@@ -520,13 +630,26 @@ __global__ void __maxnreg__(168) gemm_bf16_tcgen05_kernel(const __grid_constant_
                     if (best[q] > best[0] || (best[q] == best[0] && best_col[q] < best_col[0])) { best[0] = best[q]; best_col[0] = best_col[q]; }
                 if (EPI == EPI_SAMPLE && live && best_col[0] != 0x7FFFFFFF) atomicMax(g.best + row, pack_best(best[0], best_col[0]));
             } else {
-                tc_store_tile<EPI, BN>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (BN / 2), sbias);
+                float rs = 1.0f;
+                if constexpr (EPI == EPI_QKV || EPI == EPI_GELU) {
+                    if (has_stat) {                                                // 1 / sigma of this thread's row from the producer's partial sums
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (2 * i < g.stat_n) { s1 += st4[i].x; s2 += st4[i].y; }
+                            if (2 * i + 1 < g.stat_n) { s1 += st4[i].z; s2 += st4[i].w; }
+                        }
+                        const float mean = s1 / g.K;
+                        rs = rsqrtf(fmaxf(s2 / g.K - mean * mean, 0.f) + g.ln_eps);
+                    }
+                }
+                tc_store_tile<EPI, BN, XB>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (BN / 2), sbias, rs, xin, nm0, nn0);
             }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == n_stage) { acc = 0; acc_phase ^= 1u; }
-            if constexpr (EPI == EPI_RESID) {
+            if constexpr (EPI == EPI_RESID && !XB) {
                 if (g.ln_out) {
                     // fused LayerNorm: once every N tile of these 128 rows has been reduce-added into the residual stream (arrival
                     // counter per m-tile, device scope), the CTA that arrives last normalises the rows for the next GEMM

@@ -19,6 +19,9 @@ struct LayerDev {
     float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
     __nv_bfloat16 *w_qkv, *w_proj, *w_fc, *w_fc2;      // [N][K] bf16
     float *b_qkv, *b_proj, *b_fc, *b_fc2;
+    // LayerNorm-folded copies for the consumer-side fold (GemmArgs::stat_in): W''[n][k] = gamma[k] W[n][k] - mean_k(.), b' = b + beta . W
+    __nv_bfloat16 *w_qkv_f = nullptr, *w_fc_f = nullptr;
+    float *b_qkv_f = nullptr, *b_fc_f = nullptr;
 };
 
 // one GPT-2 parameter set + its KV slab.  Tower 0 = the sampled policy (PPO / BC policy, or pi_beta of ILQL / MC);
@@ -79,6 +82,7 @@ struct Lane {
     unsigned long long *best = nullptr, *best_scratch = nullptr;
     cudaStream_t st = nullptr;
     int* ln_cnt = nullptr;    // per-m-tile arrival counters of the LayerNorm fused into the residual GEMMs
+    float2* stat[2] = {nullptr, nullptr};   // [m_cap][8] per-row partial (sum, sumsq) of the residual stream: [0] feeds ln_1 consumers, [1] ln_2 consumers
     int e0 = 0;               // first env of the lane
     size_t m_cap = 0;         // row capacity of the lane's activation buffers
     size_t xl_rows = 0;       // rows behind xl / xl1
@@ -171,6 +175,10 @@ struct Gpt2Dev {
     int fuse_ln = 0;
     int attn_wide = 1;                // prefill attention: 32 query rows per warp pass (two m16 tiles share every staged K / V block)
     int gemv_max_rows = 8;            // batches of at most this many envs decode through the weight-streaming GEMV kernels
+    // LayerNorm folded into the CONSUMER GEMMs (see GemmArgs::stat_in): the residual GEMMs write x, its bf16 copy and per-row partial
+    // statistics; QKV / FC run on the raw bf16 copy with gamma-folded, row-centred weights and scale their accumulators by 1 / sigma.
+    // No LayerNorm launches in the decoder stack (one statistics pass per tower pass for layer 0).
+    int ln_fold = 0;
     int att_grid_mult = 8;            // decode attention: grid cap in CTAs per SM (grid-stride beyond it)
     int att_decode_impl = 0;          // 0 = SIMT streaming kernel for decode passes, 1 = the tensor-core (cp.async staged) prefill kernel with one row per slot
     int nlnl_id = -1;                 // id of the tokenizer's '\n\n' token (joined-history prompts fold a trailing newline pair into it); -1 = none
@@ -196,6 +204,47 @@ __global__ void transpose_to_bf16_kernel(const float* __restrict__ src, int K, i
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y)
         if (n0 + i < n_lim && k0 + threadIdx.x < K) dst[(size_t)(n0 + i) * K + k0 + threadIdx.x] = __float2bfloat16(tile[threadIdx.x][i]);
+}
+
+// LayerNorm fold of one [K][N] fp32 matrix (HF Conv1D layout) into dst [N][K] bf16: W''[n][k] = gamma[k] W[k][n] - mean_k(gamma[k] W[k][n]);
+// bfold[n] = bias[n] + sum_k beta[k] W[k][n].  One block per output feature n (load-time work: the strided reads do not matter).
+__global__ void fold_ln_weights_kernel(const float* __restrict__ src, int K, int N, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst, float* __restrict__ bfold) {
+    __shared__ float red[2][32];
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float sg = 0.f, sb = 0.f;
+    for (int k = tid; k < K; k += blockDim.x) { const float w = src[(size_t)k * N + n]; sg = fmaf(gamma[k], w, sg); sb = fmaf(beta[k], w, sb); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { sg += __shfl_xor_sync(0xFFFFFFFFu, sg, o); sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o); }
+    if (lane == 0) { red[0][warp] = sg; red[1][warp] = sb; }
+    __syncthreads();
+    float tg = 0.f, tb = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { tg += red[0][i]; tb += red[1][i]; }
+    const float mean = tg / K;
+    for (int k = tid; k < K; k += blockDim.x) dst[(size_t)n * K + k] = __float2bfloat16(gamma[k] * src[(size_t)k * N + n] - mean);
+    if (tid == 0) bfold[n] = bias[n] + tb;
+}
+
+// first statistics of a tower pass (the embedded rows): bf16 copy of x and the full-row (sum, sumsq) into partial slot 0; one warp per row
+__global__ void xb_stats_kernel(const float* __restrict__ x, int d, const int* __restrict__ n_dev, __nv_bfloat16* __restrict__ xb, float2* __restrict__ stat) {
+    pdl_enter();
+    const int n = *n_dev;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * d + c);
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+            uint2 pk;
+            pk.x = pack_bf16x2_tc(v.x, v.y); pk.y = pack_bf16x2_tc(v.z, v.w);
+            *reinterpret_cast<uint2*>(xb + (size_t)r * d + c) = pk;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o); }
+        if (lane == 0) stat[(size_t)r * 8] = make_float2(s1, s2);
+    }
 }
 
 __global__ void convert_to_bf16_kernel(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
@@ -287,15 +336,15 @@ static int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uin
     return make_tmap(out, base, rows, K, box_rows, false);
 }
 
-template <int EPI, int BN = TC_BN>
+template <int EPI, int BN = TC_BN, bool XB = false>
 static int launch_gemm_tc(cudaStream_t st, int pdl, int sm_count, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmW1,
                           const CUtensorMap& tmW2, const CUtensorMap& tmOut, const GemmArgs& g) {
     static bool configured = false;
     if (!configured) {
-        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTile<BN>::SMEM_BYTES));
+        LMRL_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI, BN, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTile<BN>::SMEM_BYTES));
         configured = true;
     }
-    LMRL_CUDA(launch_k(pdl, 1, gemm_bf16_tcgen05_kernel<EPI, BN>, dim3(sm_count), dim3(TcCfg<EPI>::THREADS), (size_t)TcTile<BN>::SMEM_BYTES, st, tmA, tmW,
+    LMRL_CUDA(launch_k(pdl, 1, gemm_bf16_tcgen05_kernel<EPI, BN, XB>, dim3(sm_count), dim3(TcCfg<EPI>::THREADS), (size_t)TcTile<BN>::SMEM_BYTES, st, tmA, tmW,
                        tmW1, tmW2, tmOut, g));
     return 0;
 }
@@ -366,7 +415,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
         else to = ta;
         if (!ta || !tw || !tw1 || !tw2 || !to) return -1;
     }
-    LMRL_CHECK(!g.ln_out || (tc && !use2), "fused LayerNorm needs the tcgen05 one-CTA GEMM (N=%d K=%d impl=%d)", g.N, g.K, G.gemm_impl);
+    LMRL_CHECK(!(g.ln_out || g.xb_out || g.stat_in) || (tc && !use2), "fused / folded LayerNorm needs the tcgen05 one-CTA GEMM (N=%d K=%d impl=%d)", g.N, g.K, G.gemm_impl);
     double k_total = 0.0;
     for (int i = 0; i < g.n_seg; ++i) k_total += (double)g.seg[i].kb_count * TC_BK;
     if (e->prof_begin(0, 2.0 * (double)n_true * k_total, count_kind, 2 * kind + e->cur_mode)) return -1;
@@ -380,8 +429,10 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
         }
     }
     if constexpr (EPI == EPI_RESID) {
-        if (narrow) {
-            rc = launch_gemm_tc<EPI_RESID, 192>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g);
+        if (narrow || g.xb_out) {
+            if (g.xb_out) rc = narrow ? launch_gemm_tc<EPI_RESID, 192, true>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g)
+                                      : launch_gemm_tc<EPI_RESID, TC_BN, true>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g);
+            else rc = launch_gemm_tc<EPI_RESID, 192>(G.cur->st, G.use_pdl, G.sm_count, *ta, *tw, *tw, *tw, *to, g);
             e->prof_end();
             e->launches++;
             return rc;
@@ -506,8 +557,43 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     // one-CTA kernel only); layer 0's ln_1 is the one LayerNorm launch of the pass
     const bool fuse = G.fuse_ln && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
     const int gv = gemv_rows(G, mode, n_env);
+    // consumer-side LayerNorm fold: no LayerNorm launches; stat_n = partial pairs a residual GEMM writes per row (2 per N tile of its config)
+    const bool fold = !gv && !fuse && G.ln_fold && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.stat[0] != nullptr && T.layers[0].w_qkv_f != nullptr;
+    const int resid_parts = 2 * (D.d_model / ((G.narrow_decode_tiles && mode == 1 && D.d_model == 768) ? 192 : TC_BN));
+    int n_a = 1;                                                            // partial pairs behind ln_1's input (layer 0: one full-row pair)
+    if (fold) LMRL_LAUNCH(2, LMRL_K(xb_stats_kernel, ew_blocks, 256, 0, st, Ln.x, D.d_model, Ln.rows.M, Ln.xn, Ln.stat[0]));
     for (int l = 0; l < D.n_layer; ++l) {
         const LayerDev& L = T.layers[l];
+        if (fold) {
+            GemmArgs a{};
+            a.A = Ln.xn; a.W = L.w_qkv_f; a.bias = L.b_qkv_f; a.N = 3 * D.d_model; a.K = D.d_model; a.M_dev = Ln.rows.M;
+            a.out = Ln.q; a.kcache = T.kv + (size_t)l * G.kv_layer_stride; a.vcache = a.kcache + G.kv_layer_stride / 2;
+            a.row_env = Ln.rows.row_env; a.row_pos = Ln.rows.row_pos; a.d_model = D.d_model; a.n_head = D.n_head; a.kv_table = G.kvp.table; a.kv_ppe = G.kvp.ppe;
+            a.stat_in = Ln.stat[0]; a.stat_n = n_a; a.ln_eps = D.ln_eps;
+            if (launch_gemm<EPI_QKV>(e, a, a.N, 0, Ln.m_cap, a.N, 0)) return -1;
+            if (e->prof_begin(1, 4.0 * D.d_model, 2, 10 + mode, 4.0 * D.d_model, 0)) return -1;
+            if (mode == 0 || G.att_decode_impl == 1)
+                LMRL_LAUNCH(-1, LMRL_K(attention_prefill_kernel, attp_grid(n_env, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, Ln.q, a.kcache, a.vcache, Ln.rows,
+                                       D.n_head, D.d_model, G.kvp, 0.125f * 1.4426950408889634f, G.attn_wide, Ln.att));
+            else if (G.att_decode_impl == 2)
+                LMRL_LAUNCH(-1, LMRL_K(attention_pipe_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
+            else
+                LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
+            GemmArgs p{};
+            p.A = Ln.att; p.W = L.w_proj; p.bias = L.b_proj; p.N = D.d_model; p.K = D.d_model; p.M_dev = Ln.rows.M; p.resid = Ln.x;
+            p.xb_out = Ln.xn; p.stat_out = Ln.stat[1];
+            if (launch_gemm<EPI_RESID>(e, p, p.N, 0, Ln.m_cap, p.N, 1)) return -1;
+            GemmArgs f{};
+            f.A = Ln.xn; f.W = L.w_fc_f; f.bias = L.b_fc_f; f.N = D.d_ff; f.K = D.d_model; f.M_dev = Ln.rows.M; f.out = Ln.h;
+            f.stat_in = Ln.stat[1]; f.stat_n = resid_parts; f.ln_eps = D.ln_eps;
+            if (launch_gemm<EPI_GELU>(e, f, f.N, 0, Ln.m_cap, f.N, 2)) return -1;
+            GemmArgs f2{};
+            f2.A = Ln.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = Ln.rows.M; f2.resid = Ln.x;
+            if (l + 1 < D.n_layer) { f2.xb_out = Ln.xn; f2.stat_out = Ln.stat[0]; }
+            if (launch_gemm<EPI_RESID>(e, f2, f2.N, 0, Ln.m_cap, f2.N, 3)) return -1;
+            n_a = resid_parts;
+            continue;
+        }
         if (gv) {
             // small-batch decode pass: five launches per layer, the two LayerNorms folded into the QKV / FC GEMVs' operand staging
             __nv_bfloat16* kc = T.kv + (size_t)l * G.kv_layer_stride;
@@ -751,6 +837,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
     G.cur = &G.lane[0];
     const size_t m_tiles = ((size_t)G.m_cap + TC_BM - 1) / TC_BM + 1;
     if (e->alloc(&L0.ln_cnt, m_tiles) || e->alloc(&G.lane[1].ln_cnt, m_tiles) || e->alloc(&G.lane[2].ln_cnt, m_tiles)) return -1;
+    if (e->alloc(&L0.stat[0], (size_t)G.m_cap * 8) || e->alloc(&L0.stat[1], (size_t)G.m_cap * 8)) return -1;
     if (e->alloc(&G.lane_counts, 6)) return -1;
     LMRL_CUDA(cudaStreamCreateWithFlags(&G.stream_b, cudaStreamNonBlocking));
     LMRL_CUDA(cudaEventCreateWithFlags(&G.ev_fork, cudaEventDisableTiming));
@@ -767,6 +854,7 @@ static int gpt2_alloc_state(lmrl_engine* e) {
         L.rows.slot_env += so; L.rows.slot_row0 += so; L.rows.slot_nrow += so; L.rows.slot_last += so;
         L.row_key = G.row_key + so; L.best = G.best + so; L.best_scratch = G.best_scratch + so;
         L.st = k == 2 ? G.stream_b : e->stream;
+        L.stat[0] = G.lane[0].stat[0] + ro * 8; L.stat[1] = G.lane[0].stat[1] + ro * 8;
         L.m_cap = half_rows; L.xl_rows = hb;
     }
     return 0;
@@ -799,6 +887,8 @@ extern "C" {
 
 int lmrl_load_gpt2(lmrl_engine* e, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) { return lmrl_load_gpt2_tower(e, 0, dims, w); }
 
+static int* option_slot(lmrl::Gpt2Dev& G, const char* name);
+
 int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* dims, const lmrl_gpt2_weights* w) {
     LMRL_CHECK(e && dims && w, "lmrl_load_gpt2: null argument");
     LMRL_CHECK(tower >= 0 && tower <= 2, "lmrl_load_gpt2_tower: tower must be 0 (policy / pi_beta), 1 (value base / initial policy) or 2 (target value base)");
@@ -817,6 +907,22 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         cudaDeviceProp prop;
         LMRL_CUDA(cudaGetDeviceProperties(&prop, e->device));
         e->gpt2->sm_count = prop.multiProcessorCount;
+        // A/B aid: LMRL_OPTIONS="name=value,name=value" presets lmrl_set_option switches for every engine of the process
+        if (const char* env = getenv("LMRL_OPTIONS")) {
+            std::string all(env);
+            for (size_t p0 = 0; p0 < all.size();) {
+                size_t p1 = all.find(',', p0);
+                if (p1 == std::string::npos) p1 = all.size();
+                const std::string kv = all.substr(p0, p1 - p0);
+                const size_t eq = kv.find('=');
+                if (eq != std::string::npos) {
+                    int* slot = option_slot(*e->gpt2, kv.substr(0, eq).c_str());
+                    LMRL_CHECK(slot, "LMRL_OPTIONS: unknown option '%s'", kv.substr(0, eq).c_str());
+                    *slot = atoi(kv.c_str() + eq + 1);
+                }
+                p0 = p1 + 1;
+            }
+        }
     } else {
         LMRL_CHECK(memcmp(&e->gpt2->dims, dims, sizeof *dims) == 0, "lmrl_load_gpt2: set_params with a different architecture");
     }
@@ -855,6 +961,16 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         if (!dev_src) LMRL_CUDA(cudaStreamSynchronize(e->stream));      // the staging buffer is reused by the next matrix
         return 0;
     };
+    // [K][N] fp32 -> the plain [N][K] bf16 copy AND the LayerNorm-folded copy + folded bias (gamma / beta / bias already on the device)
+    auto mat_t_fold = [&](__nv_bfloat16** dst, __nv_bfloat16** dst_f, float** bias_f, const float* host, int K, int N, const float* gamma,
+                          const float* beta, const float* bias) -> int {
+        if (fresh && (e->alloc(dst, (size_t)K * N) || e->alloc(dst_f, (size_t)K * N) || e->alloc(bias_f, (size_t)N))) return -1;
+        if (up(host, (size_t)K * N)) return -1;
+        transpose_to_bf16_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, e->stream>>>(cur_src, K, N, *dst);
+        fold_ln_weights_kernel<<<N, 256, 0, e->stream>>>(cur_src, K, N, gamma, beta, bias, *dst_f, *bias_f);
+        if (!dev_src) LMRL_CUDA(cudaStreamSynchronize(e->stream));      // the staging buffer is reused by the next matrix
+        return 0;
+    };
     int rc = 0;
     if (fresh) { rc |= e->alloc(&G.wte, (size_t)GG.v_pad * d); rc |= e->alloc(&G.wpe, (size_t)dims->n_pos * d); G.layers.resize(L); }
     if (!rc) {
@@ -871,9 +987,11 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         LayerDev& Ld = G.layers[l];
         rc |= vec(&Ld.ln1_g, w->ln1_g[l], d); rc |= vec(&Ld.ln1_b, w->ln1_b[l], d);
         rc |= vec(&Ld.ln2_g, w->ln2_g[l], d); rc |= vec(&Ld.ln2_b, w->ln2_b[l], d);
-        rc |= mat_t(&Ld.w_qkv, w->attn_w[l], d, 3 * d); rc |= vec(&Ld.b_qkv, w->attn_b[l], 3 * d);
+        rc |= vec(&Ld.b_qkv, w->attn_b[l], 3 * d);
+        if (!rc) rc |= mat_t_fold(&Ld.w_qkv, &Ld.w_qkv_f, &Ld.b_qkv_f, w->attn_w[l], d, 3 * d, Ld.ln1_g, Ld.ln1_b, Ld.b_qkv);
         rc |= mat_t(&Ld.w_proj, w->proj_w[l], d, d); rc |= vec(&Ld.b_proj, w->proj_b[l], d);
-        rc |= mat_t(&Ld.w_fc, w->fc_w[l], d, ff); rc |= vec(&Ld.b_fc, w->fc_b[l], ff);
+        rc |= vec(&Ld.b_fc, w->fc_b[l], ff);
+        if (!rc) rc |= mat_t_fold(&Ld.w_fc, &Ld.w_fc_f, &Ld.b_fc_f, w->fc_w[l], d, ff, Ld.ln2_g, Ld.ln2_b, Ld.b_fc);
         rc |= mat_t(&Ld.w_fc2, w->fc2_w[l], ff, d); rc |= vec(&Ld.b_fc2, w->fc2_b[l], d);
     }
     cudaStreamSynchronize(e->stream);
@@ -1479,6 +1597,7 @@ static int* option_slot(lmrl::Gpt2Dev& G, const char* name) {
     if (!strcmp(name, "gemv_max_rows")) return &G.gemv_max_rows;
     if (!strcmp(name, "tok_nlnl_id")) return &G.nlnl_id;
     if (!strcmp(name, "att_grid_mult")) return &G.att_grid_mult;
+    if (!strcmp(name, "ln_fold")) return &G.ln_fold;
     if (!strcmp(name, "att_decode_impl")) return &G.att_decode_impl;
     return nullptr;
 }
@@ -1672,6 +1791,16 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
     GemmArgs f2{};
     f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
+    if (G.ln_fold && G.gemm_impl == 1 && L.w_qkv_f && G.lane[0].stat[0] && D.d_model % TC_BN == 0) {
+        // the LayerNorm-folded launch sequence: residual GEMMs with the bf16 copy + statistics epilogue, consumers scaling by 1 / sigma
+        const int parts = 2 * (D.d_model / ((G.narrow_decode_tiles && rpe == 1 && D.d_model == 768) ? 192 : TC_BN));
+        a.W = L.w_qkv_f; a.bias = L.b_qkv_f; a.stat_in = G.lane[0].stat[0]; a.stat_n = parts; a.ln_eps = D.ln_eps;
+        f.W = L.w_fc_f; f.bias = L.b_fc_f; f.stat_in = G.lane[0].stat[1]; f.stat_n = parts; f.ln_eps = D.ln_eps;
+        p.xb_out = G.xn; p.stat_out = G.lane[0].stat[1];
+        f2.xb_out = G.xn; f2.stat_out = G.lane[0].stat[0];
+        LMRL_CUDA(cudaMemsetAsync(G.lane[0].stat[0], 0, (size_t)M * 8 * sizeof(float2), st));
+        LMRL_CUDA(cudaMemsetAsync(G.lane[0].stat[1], 0, (size_t)M * 8 * sizeof(float2), st));
+    }
     GemmArgs h{};
     h.A = G.xl; h.W = G.tw[0].wte; h.bias = nullptr; h.N = G.v_pad; h.K = D.d_model; h.M_dev = G.rows.n_slots;
     h.best = G.best; h.row_key = G.row_key; h.inv_temp = 1.0f; h.do_sample = 1; h.n_vocab = D.n_vocab; h.logits_out = nullptr;

@@ -13,7 +13,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def measure(batches=(1, 2, 4, 8, 16, 32, 128), n_new=65, medium=False, reps=3, peaks_gbs=None):
+def measure(batches=(1, 2, 4, 8, 16, 32, 128), n_new=65, medium=False, reps=3, peaks_gbs=None, pdl=False):
     import numpy as np
     from lmrl_gym_b200.engine import Engine
     from lmrl_gym_b200.gpt2 import B200GPT2Policy, GPT2Config, init_gpt2_params
@@ -29,6 +29,8 @@ def measure(batches=(1, 2, 4, 8, 16, 32, 128), n_new=65, medium=False, reps=3, p
     for B in batches:
         eng = Engine(max_envs=B, max_input_length=32, max_new_tokens=n_new, tokenizer=tok)
         pol = B200GPT2Policy(eng, params, cfg, seed=0)
+        if pdl:
+            eng.set_use_pdl(True)
         rng = np.random.default_rng(B)
         prompts = [rng.integers(0, V, size=8).tolist() for _ in range(B)]
         row = dict(batch=B)
@@ -61,12 +63,13 @@ def main():
     ap.add_argument("--batches", default="1,2,4,8,16,32,128")
     ap.add_argument("--new", type=int, default=65)
     ap.add_argument("--medium", action="store_true")
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch on")
     args = ap.parse_args()
     peaks = None
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     if os.path.exists(p):
         peaks = json.load(open(p))["hbm_gbs"]
-    for row in measure(tuple(int(x) for x in args.batches.split(",")), args.new, args.medium, peaks_gbs=peaks):
+    for row in measure(tuple(int(x) for x in args.batches.split(",")), args.new, args.medium, peaks_gbs=peaks, pdl=args.pdl):
         print(json.dumps(row), flush=True)
 
 

@@ -357,6 +357,53 @@ def test_fused_layernorm_and_wide_prefill_attention_are_bit_identical(tok):
         eng.close()
 
 
+def test_layernorm_folded_into_the_consumer_gemms_matches_the_oracle(tok):
+    """``ln_fold``: no LayerNorm launches in the decoder stack.  The residual GEMMs write x, its bf16 copy and per-row partial (sum, sum of
+    squares); the QKV / FC GEMMs run on the raw bf16 copy against gamma-folded, row-centred weights (W'' = gamma W - mean_k(gamma W), so the
+    row mean drops out of the product) and scale their accumulators by 1 / sigma.  Algebraically LN(x) W^T + b; the rounding points move
+    (x is rounded to bf16 before instead of after the normalisation), so the comparison is against the fp32 oracle with the same bounds as
+    the default path, and against the default path itself."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    from oracle import gpt2 as og
+    for cfg, n_prompts, max_in in ((_small_cfg(), 150, 64), (GPT2Config.small(), 40, 80)):
+        params = init_gpt2_params(cfg, seed=13)
+        rng = np.random.default_rng(6)
+        for l in params["layers"]:       # non-trivial LayerNorm parameters and biases: the fold must carry all of them
+            for k in ("attn_b", "proj_b", "fc_b", "fc2_b", "ln1_b", "ln2_b"):
+                l[k] = (0.1 * rng.standard_normal(l[k].shape)).astype(np.float32)
+            for k in ("ln1_g", "ln2_g"):
+                l[k] = (1 + 0.2 * rng.standard_normal(l[k].shape)).astype(np.float32)
+        eng = Engine(max_envs=160, max_input_length=max_in, max_new_tokens=4, tokenizer=tok)
+        pol = B200GPT2Policy(eng, params, cfg, seed=5)
+        prompts = [rng.integers(0, cfg.n_vocab, size=int(n)).tolist() for n in rng.integers(1, max_in, size=n_prompts)]
+        prompts[1] = rng.integers(0, cfg.n_vocab, size=max_in).tolist()
+        prompts[2] = prompts[2][:1]
+        keys = [int(k) for k in rng.integers(0, 2**63, size=n_prompts)]
+        eng.set_option("ln_fold", 0)
+        base_logits, base_gen = pol.logits(prompts), pol.generate_tokens(prompts, episode_keys=keys, turn=1)
+        eng.set_option("ln_fold", 1)
+        assert eng.get_option("ln_fold") == 1
+        got, gen = pol.logits(prompts), pol.generate_tokens(prompts, episode_keys=keys, turn=1)
+        again = pol.logits(prompts)
+        assert np.array_equal(got, again), "fixed statistic slots, no atomics: the folded path must be deterministic"
+        assert np.isfinite(got).all()
+        worst_f32 = worst_emu = 0.0
+        for i in range(0, n_prompts, 5):
+            f32 = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab)
+            emu = og.forward_last_logits(params, prompts[i], cfg.n_head, cfg.n_vocab, emulate_bf16=True)
+            worst_f32 = max(worst_f32, np.abs(got[i] - f32).max())
+            worst_emu = max(worst_emu, np.abs(got[i] - emu).max())
+            assert np.abs(got[i] - f32).mean() <= TOL_F32_MEAN
+        d = np.abs(got - base_logits).max()
+        same_tok = np.mean([a == b for a, b in zip(gen, base_gen)])
+        print(f"{cfg.d_model}: ln_fold max |logit diff| vs fp32 oracle {worst_f32:.4g}, vs bf16-emulating oracle {worst_emu:.4g}, vs the default path {d:.4g}; "
+              f"identical sampled rows {same_tok:.3f}")
+        assert worst_f32 <= TOL_F32 and d <= TOL_F32
+        assert same_tok >= 0.8
+        eng.close()
+
+
 @pytest.mark.parametrize("kind", ["synthetic+nlnl", "gpt2-format-bpe-fixture"])
 def test_fused_rollout_feeds_the_joined_history_encoding(kind):
     """The reference encodes the JOINED history every turn (ppo/gpt2/interface.py:519-522 -> value_rl_base/base_interface.py:111-112).
