@@ -347,9 +347,16 @@ int lmrl_set_use_pdl(lmrl_engine* e, int32_t enable);
  *                    0 16-row passes
  *   "gemv_max_rows"  decode passes of batches with at most this many envs run the weight-streaming GEMV kernels instead of
  *                    128-row tensor-core tiles (default 8; 0 disables)
- *   "att_decode_impl" decode-pass attention: 0 (default) the streaming SIMT kernel, 1 the cp.async-staged tensor-core prefill kernel with one
- *                    row per slot, 2 the SIMT kernel with software-pipelined K / V loads (bit-identical to 0).  Both alternatives measured
- *                    1-2 % slower per rollout on B200; "att_grid_mult" caps the SIMT kernel's grid at that many CTAs per SM (default 8)
+ *   "att_decode_impl" decode-pass attention: 4 (default) the streaming SIMT kernel with 4 consecutive heads of a slot per warp (the slot's
+ *                    metadata chain slot -> env -> page table is paid once per 4 heads: +14 % at context 24, +4 % at 40, -5 % at 80 against
+ *                    one head per warp in isolation, -1 % per Wordle rollout), 3 two heads per warp, 0 one head per warp, 2 one head per warp
+ *                    with software-pipelined K / V loads (0, 2, 3, 4 are bit-identical), 1 the cp.async-staged tensor-core prefill kernel
+ *                    with one row per slot (1 and 2 measured 1-2 % slower per rollout); "att_grid_mult" caps the SIMT kernels' grid at
+ *                    that many CTAs per SM (default 8)
+ *   "ln_fold"        1 LayerNorm folded into the CONSUMER GEMMs: the residual GEMMs write x, its bf16 copy and per-row partial (sum, sum of
+ *                    squares); QKV / FC run on the raw copy against gamma-folded row-centred weights and scale their accumulators by
+ *                    1 / sigma.  No LayerNorm launches in the decoder stack; results within the float tolerance of the default path
+ *                    (different rounding points); measured 0-1 % faster per rollout, 0 (default)
  *   "tok_nlnl_id"    id of the tokenizer's '\n\n' token, -1 (default) = none.  The reference encodes the JOINED history every turn
  *                    (ppo/gpt2/interface.py:519-522), so with GPT-2's merges a prompt ending in an action line + an empty feedback
  *                    line ends in that single token; the fused rollout reproduces this in its prompt view (the stream itself stays

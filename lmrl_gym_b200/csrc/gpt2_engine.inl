@@ -180,7 +180,10 @@ struct Gpt2Dev {
     // No LayerNorm launches in the decoder stack (one statistics pass per tower pass for layer 0).
     int ln_fold = 0;
     int att_grid_mult = 8;            // decode attention: grid cap in CTAs per SM (grid-stride beyond it)
-    int att_decode_impl = 0;          // 0 = SIMT streaming kernel for decode passes, 1 = the tensor-core (cp.async staged) prefill kernel with one row per slot
+    // decode-pass attention: 4 (default) = SIMT streaming kernel, a warp takes 4 consecutive heads of a slot (the slot's metadata chain is paid once
+    // per 4 heads; falls back to one head per warp when n_head % 4 != 0), 3 = 2 heads per warp, 0 = one head per warp, 1 = the tensor-core
+    // (cp.async staged) prefill kernel with one row per slot, 2 = one head per warp with software-pipelined K / V loads
+    int att_decode_impl = 4;
     int nlnl_id = -1;                 // id of the tokenizer's '\n\n' token (joined-history prompts fold a trailing newline pair into it); -1 = none
     int fold_nlnl = -1;               // nlnl_id while a fused Wordle rollout is being enqueued, -1 on the text paths (their callers tokenise themselves)
     // programmatic dependent launch between the kernels of a pass (pdl.cuh).  Off by default: measured on B200 it is SLOWER
@@ -577,6 +580,10 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
                                        D.n_head, D.d_model, G.kvp, 0.125f * 1.4426950408889634f, G.attn_wide, Ln.att));
             else if (G.att_decode_impl == 2)
                 LMRL_LAUNCH(-1, LMRL_K(attention_pipe_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
+            else if (G.att_decode_impl == 3 && D.n_head % 2 == 0)
+                LMRL_LAUNCH(-1, LMRL_K(attention_hpw_kernel<2>, std::min(att_blocks, (n_env * D.n_head / 2 + ATT_WARPS - 1) / ATT_WARPS), ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
+            else if (G.att_decode_impl == 4 && D.n_head % 4 == 0)
+                LMRL_LAUNCH(-1, LMRL_K(attention_hpw_kernel<4>, std::min(att_blocks, (n_env * D.n_head / 4 + ATT_WARPS - 1) / ATT_WARPS), ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
             else
                 LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
             GemmArgs p{};
@@ -632,6 +639,10 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
         else if (G.att_decode_impl == 2)
             LMRL_LAUNCH(-1, LMRL_K(attention_pipe_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
                                                                                                   0.125f, Ln.att));
+        else if (G.att_decode_impl == 3 && D.n_head % 2 == 0)
+            LMRL_LAUNCH(-1, LMRL_K(attention_hpw_kernel<2>, std::min(att_blocks, (n_env * D.n_head / 2 + ATT_WARPS - 1) / ATT_WARPS), ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
+        else if (G.att_decode_impl == 4 && D.n_head % 4 == 0)
+            LMRL_LAUNCH(-1, LMRL_K(attention_hpw_kernel<4>, std::min(att_blocks, (n_env * D.n_head / 4 + ATT_WARPS - 1) / ATT_WARPS), ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp, 0.125f, Ln.att));
         else
             LMRL_LAUNCH(-1, LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, Ln.q, a.kcache, a.vcache, Ln.rows, D.n_head, D.d_model, G.kvp,
                                                                                              0.125f, Ln.att));
@@ -1828,6 +1839,12 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
                     if (rpe > 1)
                         LMRL_K(attention_prefill_kernel, attp_grid(n_slots, D.n_head, G.sm_count), ATTP_WARPS * 32, ATTP_WARPS * ATTP_WARP_SMEM, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp,
                                                                                       0.125f * 1.4426950408889634f, G.attn_wide, G.att);
+                    else if (G.att_decode_impl == 2)
+                        LMRL_K(attention_pipe_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp, 0.125f, G.att);
+                    else if (G.att_decode_impl == 3 && D.n_head % 2 == 0)
+                        LMRL_K(attention_hpw_kernel<2>, std::min(att_blocks, (n_slots * D.n_head / 2 + ATT_WARPS - 1) / ATT_WARPS), ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp, 0.125f, G.att);
+                    else if (G.att_decode_impl == 4 && D.n_head % 4 == 0)
+                        LMRL_K(attention_hpw_kernel<4>, std::min(att_blocks, (n_slots * D.n_head / 4 + ATT_WARPS - 1) / ATT_WARPS), ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp, 0.125f, G.att);
                     else
                         LMRL_K(attention_kernel, att_blocks, ATT_WARPS * 32, 0, st, G.q, a.kcache, a.vcache, G.rows, D.n_head, D.d_model, G.kvp, 0.125f, G.att);
                     break;

@@ -557,6 +557,67 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 2) attention_pipe_kernel(const
     }
 }
 
+// ---- K3, several heads per warp ---------------------------------------------------------------------------------------------
+// Same arithmetic as attention_kernel (bit-identical results).  A warp takes HPW consecutive heads of ONE slot: the slot's metadata chain
+// (slot -> env / first row -> page table / position: two dependent round trips before the first K / V byte can be asked for) is paid once
+// per HPW heads instead of once per head, and the first K / V loads of a head are issued before its q is converted.
+template <int HPW>
+__global__ void __launch_bounds__(ATT_WARPS * 32, 3) attention_hpw_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                                                                          const __nv_bfloat16* __restrict__ vcache, RowsDev rows, int n_head,
+                                                                          int d_model, KvPages kv, float scale, __nv_bfloat16* __restrict__ out) {
+    pdl_enter();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, s = lane & 7;
+    const int groups = n_head / HPW;                                       // head groups per slot (n_head % HPW == 0: checked by the host)
+    const int total = *rows.n_slots * groups;
+    const uint4* gK = reinterpret_cast<const uint4*>(kcache) + s;
+    const uint4* gV = reinterpret_cast<const uint4*>(vcache) + s;
+    for (int w = blockIdx.x * ATT_WARPS + warp; w < total; w += gridDim.x * ATT_WARPS) {
+        const int slot = w / groups, head0 = (w - slot * groups) * HPW;
+        const int e = rows.slot_env[slot], r0 = rows.slot_row0[slot], n = rows.slot_nrow[slot];
+        const int my_page = lane < kv.ppe ? kv.table[(size_t)e * kv.ppe + lane] : 0;
+        for (int i = 0; i < n; ++i) {
+            const int r = r0 + i, nkeys = rows.row_pos[r] + 1;
+#pragma unroll 1
+            for (int hh = 0; hh < HPW; ++hh) {
+                const int head = head0 + hh;
+                uint4 kk[4], vv[4];
+                att_load_step(gK, gV, my_page, n_head, head, 0, g, nkeys, kk, vv);        // in flight while q arrives
+                float qf[8];
+                {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(q + (size_t)r * d_model + head * 64) + s);
+                    bf16x8_to_float(u, qf);
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) qf[t] *= scale;
+                }
+                float m = -INFINITY, l = 0.f;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int j0 = 0; j0 < nkeys; j0 += 16) {
+                    if (j0 > 0) att_load_step(gK, gV, my_page, n_head, head, j0, g, nkeys, kk, vv);
+                    att_consume_step(kk, vv, qf, j0, g, nkeys, m, l, acc);
+                }
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                    const float m_o = __shfl_xor_sync(0xFFFFFFFFu, m, o), l_o = __shfl_xor_sync(0xFFFFFFFFu, l, o);
+                    const float m_n = fmaxf(m, m_o);
+                    const float c1 = m > -INFINITY ? __expf(m - m_n) : 0.f, c2 = m_o > -INFINITY ? __expf(m_o - m_n) : 0.f;
+                    l = l * c1 + l_o * c2;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) acc[t] = acc[t] * c1 + __shfl_xor_sync(0xFFFFFFFFu, acc[t], o) * c2;
+                    m = m_n;
+                }
+                if (g == 0) {
+                    const float inv = 1.0f / l;
+                    __nv_bfloat162 o2[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(acc[2 * t] * inv, acc[2 * t + 1] * inv);
+                    *reinterpret_cast<uint4*>(out + (size_t)r * d_model + head * 64 + s * 8) = *reinterpret_cast<const uint4*>(o2);
+                }
+            }
+        }
+    }
+}
+
 // ---- K3 (prefill): tensor-core attention for slots that bring many rows ------------------------------------------
 // One warp per (slot, head).  MT m16 tiles of query rows (16 or 32 rows of the slot) are held as mma A fragments; the (env, head)
 // K / V slabs are staged 32 keys at a time into per-warp shared memory (cp.async, 128-byte rows, XOR-swizzled 16-byte

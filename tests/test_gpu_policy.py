@@ -345,13 +345,15 @@ def test_fused_layernorm_and_wide_prefill_attention_are_bit_identical(tok):
         # kernel rounds P to bf16 before P.V like the prefill passes do (tokens agree except at near-ties)
         eng.set_option("fuse_ln", 0)
         eng.set_option("attn_wide", 1)
+        eng.set_option("att_decode_impl", 0)
         base = pol.generate_tokens(prompts, episode_keys=keys, turn=1)
-        eng.set_option("att_decode_impl", 2)
-        assert pol.generate_tokens(prompts, episode_keys=keys, turn=1) == base
+        for impl in (2, 3, 4):                    # software-pipelined loads; 2 / 4 heads of a slot per warp: the same arithmetic per (slot, head)
+            eng.set_option("att_decode_impl", impl)
+            assert pol.generate_tokens(prompts, episode_keys=keys, turn=1) == base, impl
         eng.set_option("att_decode_impl", 1)
         staged = pol.generate_tokens(prompts, episode_keys=keys, turn=1)
         assert np.mean([a == b for a, b in zip(staged, base)]) >= 0.9
-        eng.set_option("att_decode_impl", 0)
+        eng.set_option("att_decode_impl", 4)
         with pytest.raises(Exception):
             eng.set_option("no_such_option", 1)
         eng.close()
