@@ -9,7 +9,8 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "liblmrl_b200.so")
+# LMRL_LIB_PATH: A/B aid — another build of the SAME C ABI (e.g. the previous commit's kernels) instead of the in-tree library
+LIB_PATH = os.environ.get("LMRL_LIB_PATH") or os.path.join(HERE, "csrc", "liblmrl_b200.so")
 
 
 class LmrlError(RuntimeError):
