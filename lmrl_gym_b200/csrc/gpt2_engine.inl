@@ -561,7 +561,7 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     const bool fuse = G.fuse_ln && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
     const int gv = gemv_rows(G, mode, n_env);
     // consumer-side LayerNorm fold: no LayerNorm launches; stat_n = partial pairs a residual GEMM writes per row (2 per N tile of its config)
-    const bool fold = !gv && !fuse && G.ln_fold && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.stat[0] != nullptr && T.layers[0].w_qkv_f != nullptr;
+    const bool fold = !gv && !fuse && (G.ln_fold == 1 || (G.ln_fold == 2 && mode == 1)) && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.stat[0] != nullptr && T.layers[0].w_qkv_f != nullptr;
     const int resid_parts = 2 * (D.d_model / ((G.narrow_decode_tiles && mode == 1 && D.d_model == 768) ? 192 : TC_BN));
     int n_a = 1;                                                            // partial pairs behind ln_1's input (layer 0: one full-row pair)
     if (fold) LMRL_LAUNCH(2, LMRL_K(xb_stats_kernel, ew_blocks, 256, 0, st, Ln.x, D.d_model, Ln.rows.M, Ln.xn, Ln.stat[0]));
