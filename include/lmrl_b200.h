@@ -371,8 +371,9 @@ int lmrl_kv_stats(lmrl_engine* e, int32_t* pages_in_use, int32_t* pages_total, i
 /* counters for bench.py: kernels launched by this engine since the last reset */
 int64_t lmrl_launch_count(lmrl_engine* e, int32_t reset);
 
-/* GEMM implementation switch (default 1 = tcgen05/TMEM/TMA, one CTA per 128x256 tile; 2 = CTA pairs (cta_group::2, 256x256) on
- * prefill passes; 0 = the mma.sync kernel kept as an independent cross-check) and a unit-test hook:
+/* GEMM implementation switch (default 2 = tcgen05/TMEM/TMA with CTA pairs (cta_group::2, 256x256 tiles) on the plain GEMMs of prefill
+ * passes and one CTA per 128x256 tile elsewhere; 1 = one CTA per tile everywhere; 0 = the mma.sync kernel kept as an independent
+ * cross-check) and a unit-test hook:
  * resid[M,N] += A[M,K] · W[N,K]^T + bias through the chosen implementation (bf16 bit patterns in); the hook also accepts
  * impl 3 = the 128x192-tile tcgen05 kernel the engine uses for the N = 768 GEMMs of decode passes */
 int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl);

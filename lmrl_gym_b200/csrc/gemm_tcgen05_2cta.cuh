@@ -18,7 +18,8 @@ namespace lmrl {
 constexpr int TC2_STAGES = 6;
 constexpr int TC2_B_ROWS = TC_BN / 2;                                  // W rows staged per CTA
 constexpr int TC2_STAGE_BYTES = TC_A_BYTES + TC2_B_ROWS * TC_BK * 2;   // 16 KB + 16 KB
-constexpr int TC2_SMEM_BYTES = 1024 + TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_BYTES + 256;
+constexpr int TC2_SMEM_BYTES = 1024 + TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_BYTES + TC_BIAS_BYTES + 256;
+static_assert(TC2_SMEM_BYTES <= 232448, "shared memory of one CTA (227 KB)");
 constexpr int TC2_THREADS = 64 + 32 * 8;                                // producer, MMA issuer, 8 epilogue warps
 // instruction descriptor of the pair: M = 256, N = 256
 constexpr uint32_t TC2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -66,13 +67,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* base_ptr = tc2_smem_raw + (base - raw);
     const uint32_t epi_base = base + TC2_STAGES * TC2_STAGE_BYTES;
-    const uint32_t bar_base = epi_base + TC_EPI_BYTES;
+    const uint32_t bias_base = epi_base + TC_EPI_BYTES;                  // the current tile's 256 bias values (staged once per tile, as in the one-CTA kernel)
+    const uint32_t bar_base = bias_base + TC_BIAS_BYTES;
     // barriers (8 bytes each): full[6], empty[6], tmem_full[2], tmem_empty[2], then the TMEM base address word
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC2_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC2_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC2_STAGES + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_BYTES + 8 * (2 * TC2_STAGES + 4));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_BYTES + TC_BIAS_BYTES + 8 * (2 * TC2_STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kt = g.K / TC_BK;
@@ -144,13 +146,25 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) gemm_bf16_tcgen05_2cta_kernel(
         const int quad = warp & 3;
         const uint32_t stg = epi_base + (uint32_t)(warp - 2) * TC_EPI_BUF;
         const int half = (warp - 2) >> 2;
+        const int et = (int)threadIdx.x - 64;                                     // thread index inside the epilogue group (256 threads)
+        const uint32_t sbias = g.bias ? bias_base : 0u;
+        auto epi_bar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };      // named barrier of the eight epilogue warps
+        float bias_next = 0.f;                                                     // this thread's bias value of the cluster's next tile
+        if (sbias && cluster_id < total) bias_next = __ldg(g.bias + (cluster_id % n_tiles) * TC_BN + et);
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < total; tile += n_clusters) {
             const int m0 = (tile / n_tiles) * 2 * TC_BM + (int)rank * TC_BM, n0 = (tile % n_tiles) * TC_BN;
+            if (sbias) {
+                epi_bar();                                                         // nobody still reads the previous tile's values
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * (uint32_t)et), "f"(bias_next) : "memory");
+                epi_bar();
+                const int nt_b = tile + n_clusters;
+                if (nt_b < total) bias_next = __ldg(g.bias + (nt_b % n_tiles) * TC_BN + et);
+            }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * TC_BN);
-            tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (TC_BN / 2), 0u);
+            tc_store_tile<EPI>(g, tmOut, t_addr, M, m0, n0, quad, lane, stg, half * (TC_BN / 2), sbias);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));

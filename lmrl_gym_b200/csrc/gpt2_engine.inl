@@ -190,9 +190,10 @@ struct Gpt2Dev {
     // for this path (4096-episode Wordle rollout: 208.2 ms with graphs and no PDL, 223.8 ms with PDL; letters variant 81.0 vs 84.2)
     int use_pdl = 0;
     int sm_count = 148;
-    // 1 = tcgen05, one CTA per tile (default); 2 = CTA pairs on prefill passes (3-12 % faster per GEMM at M ~ 100 k rows in
-    // isolation, no gain over a whole rollout: 211.4 vs 207.6 ms); 0 = mma.sync cross-check
-    int gemm_impl = 1;
+    // 2 (default) = tcgen05 with CTA pairs (cta_group::2, 256 x 256 tiles) on the plain GEMMs of prefill passes and one CTA per 128 x 256
+    // tile everywhere else; 1 = one CTA per tile everywhere; 0 = mma.sync cross-check.  The pair kernel became the default once it
+    // got the shared-memory bias staging of the one-CTA epilogue: 2-5 % per prefill GEMM, -1.2 ms per 4096-episode rollout (same box)
+    int gemm_impl = 2;
     std::map<std::tuple<const void*, size_t, size_t, int>, CUtensorMap> tmaps;   // (base pointer, row bound, columns, box rows | f32 flag) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
@@ -404,7 +405,7 @@ static int launch_gemm(lmrl_engine* e, GemmArgs g, int n_true, int count_kind, s
             return &it->second;
         };
         // CTA-pair kernel: plain GEMMs of the prefill passes (many rows); each CTA stages 128 of the 256 W rows
-        use2 = G.gemm_impl == 2 && e->cur_mode == 0 && g.n_seg == 1 && EPI != EPI_SAMPLE && EPI != EPI_LOGPROB && !x.W1;
+        use2 = G.gemm_impl == 2 && e->cur_mode == 0 && g.n_seg == 1 && EPI != EPI_SAMPLE && EPI != EPI_LOGPROB && !x.W1 && !g.ln_out && !g.xb_out && !g.stat_in;
         // decode pass (one row per env), N = 768 residual GEMMs: 192-wide tiles fill the SMs better than 256-wide ones
         narrow = EPI == EPI_RESID && G.narrow_decode_tiles && e->cur_mode == 1 && g.N == 768 && g.n_seg == 1 && !use2;
         ta = get(g.A, a_rows, x.a_cols ? x.a_cols : (size_t)g.K, TC_BM, false);
@@ -558,10 +559,10 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     const int att_blocks = std::min((n_env * D.n_head + ATT_WARPS - 1) / ATT_WARPS, G.sm_count * G.att_grid_mult);
     // ln_2 of this layer rides on the attention-projection GEMM, ln_1 of the next layer on the MLP-projection GEMM (tcgen05
     // one-CTA kernel only); layer 0's ln_1 is the one LayerNorm launch of the pass
-    const bool fuse = G.fuse_ln && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
+    const bool fuse = G.fuse_ln && G.gemm_impl >= 1 && D.d_model % TC_BN == 0 && Ln.ln_cnt != nullptr;
     const int gv = gemv_rows(G, mode, n_env);
     // consumer-side LayerNorm fold: no LayerNorm launches; stat_n = partial pairs a residual GEMM writes per row (2 per N tile of its config)
-    const bool fold = !gv && !fuse && (G.ln_fold == 1 || (G.ln_fold == 2 && mode == 1)) && G.gemm_impl == 1 && D.d_model % TC_BN == 0 && Ln.stat[0] != nullptr && T.layers[0].w_qkv_f != nullptr;
+    const bool fold = !gv && !fuse && (G.ln_fold == 1 || (G.ln_fold == 2 && mode == 1)) && G.gemm_impl >= 1 && D.d_model % TC_BN == 0 && Ln.stat[0] != nullptr && T.layers[0].w_qkv_f != nullptr;
     const int resid_parts = 2 * (D.d_model / ((G.narrow_decode_tiles && mode == 1 && D.d_model == 768) ? 192 : TC_BN));
     int n_a = 1;                                                            // partial pairs behind ln_1's input (layer 0: one full-row pair)
     if (fold) LMRL_LAUNCH(2, LMRL_K(xb_stats_kernel, ew_blocks, 256, 0, st, Ln.x, D.d_model, Ln.rows.M, Ln.xn, Ln.stat[0]));
@@ -1720,6 +1721,10 @@ int lmrl_set_gemm_impl(lmrl_engine* e, int32_t impl) {
     LMRL_CHECK(e && e->gpt2, "lmrl_set_gemm_impl: no GPT-2 parameters loaded");
     LMRL_CHECK(impl >= 0 && impl <= 2, "lmrl_set_gemm_impl: impl must be 0 (mma.sync), 1 (tcgen05, one CTA per tile) or 2 (tcgen05, CTA pairs on prefill passes)");
     e->gpt2->gemm_impl = impl;
+    // a captured rollout / decode graph holds the old kernels
+    if (e->gpt2->graph_exec) { cudaGraphExecDestroy(e->gpt2->graph_exec); e->gpt2->graph_exec = nullptr; }
+    if (e->gpt2->decode_graph) { cudaGraphExecDestroy(e->gpt2->decode_graph); e->gpt2->decode_graph = nullptr; }
+    e->gpt2->warm_valid = false; e->gpt2->decode_warm_valid = false;
     return 0;
 }
 
@@ -1802,7 +1807,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
     GemmArgs f2{};
     f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-    if (G.ln_fold && G.gemm_impl == 1 && L.w_qkv_f && G.lane[0].stat[0] && D.d_model % TC_BN == 0) {
+    if (G.ln_fold && G.gemm_impl >= 1 && L.w_qkv_f && G.lane[0].stat[0] && D.d_model % TC_BN == 0) {
         // the LayerNorm-folded launch sequence: residual GEMMs with the bf16 copy + statistics epilogue, consumers scaling by 1 / sigma
         const int parts = 2 * (D.d_model / ((G.narrow_decode_tiles && rpe == 1 && D.d_model == 768) ? 192 : TC_BN));
         a.W = L.w_qkv_f; a.bias = L.b_qkv_f; a.stat_in = G.lane[0].stat[0]; a.stat_n = parts; a.ln_eps = D.ln_eps;

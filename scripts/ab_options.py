@@ -47,6 +47,8 @@ def main():
                 eng.set_use_pdl(bool(v))
             elif k == "graphs":
                 eng.set_use_graphs(bool(v))
+            elif k == "gemm_impl":
+                eng.set_gemm_impl(v)
             else:
                 eng.set_option(k, v)
         for _ in range(3):
