@@ -595,7 +595,7 @@ def run_workload(args, workload, rank, world, local, barrier, log, skip, headlin
         total_kernel_ms = sum(prof["ms"].values())
         fam = load_traffic() or {}
         gemm_traffic = fam.get("gemm_bf16_tcgen05_kernel", {}).get("dram_bytes_per_launch")
-        att_traffic = fam.get("attention_kernel", {}).get("dram_bytes_per_launch")
+        att_traffic = (fam.get("attention_hpw_kernel") or fam.get("attention_kernel") or {}).get("dram_bytes_per_launch")
         local_steps = max(env_steps, 1)
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=elapsed_ms / K, higher_is_better=True,
@@ -612,13 +612,13 @@ def run_workload(args, workload, rank, world, local, barrier, log, skip, headlin
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, api="lmrl_gym_b200.text_env_eval"),
             gpu_launches=total_launches,
             clocks=clock_info,
-            roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel (tcgen05.mma UMMA 128x256x16 + TMA + TMEM, all epilogues)", achieved=achieved, peak=peak,
+            roofline=dict(bound="tensor", kernel="gemm_bf16_tcgen05_kernel + gemm_bf16_tcgen05_2cta_kernel (tcgen05.mma UMMA 128x256x16 / cta_group::2 256x256x16 on the plain prefill GEMMs, TMA + TMEM, all epilogues)", achieved=achieved, peak=peak,
                           unit="TFLOP/s", frac=achieved / peak if peak else None, peak_source=f"{peaks['source']} bf16_tflops_sustained", traffic=gemm_traffic,
                           traffic_source="profiles/r02_traffic.json (r01 when absent): mean dram__bytes_read.sum + dram__bytes_write.sum per launch over every GEMM launch of one ncu-profiled step" if gemm_traffic else None,
                           flops_per_step=gemm_flops / K, launches_per_step=prof["launches"]["gemm"] / K,
                           share_of_kernel_time=gemm_ms / total_kernel_ms if total_kernel_ms else None,
                           # the HBM-bound batched GEMV of the path (north_star's "decode GEMV"): KV-cache attention of the decode passes
-                          decode_attention_hbm=dict(kernel="attention_kernel (decode passes, paged KV)", achieved=att_gbs, peak=peaks["hbm_gbs"], unit="GB/s",
+                          decode_attention_hbm=dict(kernel="attention_hpw_kernel<4> (decode passes, paged KV, 4 heads of a slot per warp)", achieved=att_gbs, peak=peaks["hbm_gbs"], unit="GB/s",
                                                     frac=att_gbs / peaks["hbm_gbs"], bytes_per_step=att["work"] / K, traffic=att_traffic,
                                                     peak_source=f"{peaks['source']} hbm_gbs",
                                                     algorithmic_bytes="every cached K and V position of the live envs once (bf16) + q / out rows")),

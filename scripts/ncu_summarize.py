@@ -89,7 +89,7 @@ def traffic(path, out_path):
                       dram_write_per_launch=d["write"] / n, us_per_launch=1000.0 * d["ms"] / n)
     fam = defaultdict(lambda: dict(launches=0, bytes=0.0))
     for k, d in out.items():
-        f = "gemm_bf16_tcgen05_kernel" if "gemm_bf16_tcgen05" in k else k
+        f = "gemm_bf16_tcgen05_kernel" if "gemm_bf16_tcgen05" in k else ("attention_hpw_kernel" if "attention_hpw_kernel" in k else k)
         fam[f]["launches"] += d["launches"]
         fam[f]["bytes"] += d["dram_bytes_per_launch"] * d["launches"]
     summary = {f: dict(launches=d["launches"], dram_bytes_per_launch=d["bytes"] / max(d["launches"], 1)) for f, d in fam.items()}
