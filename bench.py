@@ -260,6 +260,9 @@ def bc_train_on_device(eng, tok, cfg, params, n_data, steps, bsize, lr, seed=0, 
     rows = bsize * max_length
     trainer = T.B200PPOTrain(eng, params, lin, cfg, lr=lr, weight_decay=0.0, pad_token_id=tok.pad_token_id, backward="b200", max_rows=rows, max_scored_rows=rows)
     rng = np.random.default_rng(seed)
+    import gc
+    gc.collect()
+    gc.freeze()          # 32 768 episode records (+ whatever earlier blocks left alive) stay out of the collector's passes during the 2 000 steps
     t0 = time.perf_counter()
     first = last = None
     warm = max(1, steps // 20)
@@ -273,6 +276,7 @@ def bc_train_on_device(eng, tok, cfg, params, n_data, steps, bsize, lr, seed=0, 
         if log and (step % 200 == 0 or step == steps - 1):
             log(f"bc step {step}: loss {loss:.4f}")
     train_s = time.perf_counter() - t0
+    gc.unfreeze()
     return trainer, dict(episodes=len(records), data="device RandomMixturePolicy(prob_smart=0.5) episodes (wordle/misc/data_gen.py:16-27 equivalent)",
                          data_gen_s=gen_s, steps=steps, bsize=bsize, lr=lr, max_length=max_length, loss_first=first, loss_last=last, train_s=train_s,
                          s_per_step=train_s / max(steps, 1))

@@ -278,6 +278,10 @@ class B200PPOTrain:
         (library path), a summing all-reduce of the two flat gradient buffers over the ranks, then AdamW — the hand-written streaming
         kernel ``lmrl_adamw_dev`` when an engine is attached, ``torch.optim.AdamW`` otherwise (CPU tests)."""
         torch = self.torch
+        import os as _os
+        import time as _time
+        _timing = _os.environ.get("LMRL_STEP_TIMING") == "1"       # diagnostics: host wall clock of the step's phases on stderr
+        _t = [_time.perf_counter()]
         # optional BC term (ppo/gpt2/interface.py:183-205): loss + w * bc_loss, policy gradients + w * bc gradients
         use_bc = bc_batch is not None and self.bc_loss_weight != 0.0
         if self.backward == "b200":
@@ -297,6 +301,7 @@ class B200PPOTrain:
                 loss = loss + self.bc_loss_weight * bc
             loss.backward()
             loss = float(loss.detach())
+        _t.append(_time.perf_counter())
         world = self._allreduce_grads()
         self.steps += 1
         if self.use_device_adamw:
@@ -311,8 +316,13 @@ class B200PPOTrain:
                 for f in self.flat:
                     f.grad /= world
             self.opt.step()
+        _t.append(_time.perf_counter())
         if self.backward == "b200":
             self.push_to_engine()           # the next forward / backward (and the next rollout) run on the updated weights
+        if _timing:
+            import sys as _sys
+            _t.append(_time.perf_counter())
+            print("[B200PPOTrain.step] grads %.1f ms  allreduce+adamw %.1f ms  push_to_engine %.1f ms" % tuple(1e3 * (b - a) for a, b in zip(_t[:-1], _t[1:])), file=_sys.stderr, flush=True)
         return float(loss), {k: float(v) for k, v in logs.items()}
 
     def _allreduce_grads(self) -> int:
@@ -627,6 +637,11 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTra
         t2 = time.perf_counter()
         losses = []
         steps_per_epoch = agreed_steps_per_epoch(len(datas), train_bsize)     # same all_reduce count on every rank
+        # the round's PPO data (thousands of small numpy-holding objects) is parked in the collector's permanent generation while the
+        # optimizer steps run: a full collection traversing it in the middle of a 13 ms step showed up as 10-45 ms stalls
+        import gc
+        gc.collect()
+        gc.freeze()
         for _ in range(epochs):
             order = rng.permutation(len(datas))
             for k in range(steps_per_epoch):
@@ -635,6 +650,7 @@ def ppo_train_loop(env, policy, inference: B200PPOInference, trainer: B200PPOTra
                 lo = k * train_bsize
                 batch = block_ppo_data([datas[i] for i in order[lo:lo + train_bsize]], inference.pad_token_id, max_length)
                 losses.append(trainer.step(batch, next(bc_batches) if bc_batches is not None else None)[0])
+        gc.unfreeze()
         trainer.push_to_engine()
         torch.cuda.synchronize()
         t3 = time.perf_counter()
