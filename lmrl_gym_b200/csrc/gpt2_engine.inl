@@ -28,6 +28,7 @@ struct LayerDev {
 // tower 1 = the value base of ILQL / MC (value_rl_base/gpt2/generation.py:77-88), same architecture, own KV cache.
 struct TowerDev {
     bool loaded = false;
+    bool fold_valid = false;          // the LayerNorm-folded weight copies (LayerDev::w_qkv_f ...) match the current weights
     __nv_bfloat16 *wte = nullptr, *wpe = nullptr;
     float *lnf_g = nullptr, *lnf_b = nullptr;
     std::vector<LayerDev> layers;
@@ -563,6 +564,8 @@ static int tower_layers(lmrl_engine* e, const TowerDev& T, int mode, int n_env) 
     const int gv = gemv_rows(G, mode, n_env);
     // consumer-side LayerNorm fold: no LayerNorm launches; stat_n = partial pairs a residual GEMM writes per row (2 per N tile of its config)
     const bool fold = !gv && !fuse && (G.ln_fold == 1 || (G.ln_fold == 2 && mode == 1)) && G.gemm_impl >= 1 && D.d_model % TC_BN == 0 && Ln.stat[0] != nullptr && T.layers[0].w_qkv_f != nullptr;
+    LMRL_CHECK(!fold || T.fold_valid, "ln_fold is on but this tower's LayerNorm-folded weight copies are stale (the weights were re-loaded while ln_fold was off; "
+               "the copies are refreshed on every load while it is on): load the weights again (set_params / the trainer's hand-over) with ln_fold set");
     const int resid_parts = 2 * (D.d_model / ((G.narrow_decode_tiles && mode == 1 && D.d_model == 768) ? 192 : TC_BN));
     int n_a = 1;                                                            // partial pairs behind ln_1's input (layer 0: one full-row pair)
     if (fold) LMRL_LAUNCH(2, LMRL_K(xb_stats_kernel, ew_blocks, 256, 0, st, Ln.x, D.d_model, Ln.rows.M, Ln.xn, Ln.stat[0]));
@@ -973,13 +976,16 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         if (!dev_src) LMRL_CUDA(cudaStreamSynchronize(e->stream));      // the staging buffer is reused by the next matrix
         return 0;
     };
-    // [K][N] fp32 -> the plain [N][K] bf16 copy AND the LayerNorm-folded copy + folded bias (gamma / beta / bias already on the device)
+    // [K][N] fp32 -> the plain [N][K] bf16 copy AND the LayerNorm-folded copy + folded bias (gamma / beta / bias already on the device).
+    // A weight hand-over from a trainer (every optimizer step) refreshes the folded copies only while ln_fold is on; otherwise they are
+    // marked stale and the fold stays off for this tower until a load with ln_fold set
+    const bool do_fold = fresh || GG.ln_fold != 0;
     auto mat_t_fold = [&](__nv_bfloat16** dst, __nv_bfloat16** dst_f, float** bias_f, const float* host, int K, int N, const float* gamma,
                           const float* beta, const float* bias) -> int {
         if (fresh && (e->alloc(dst, (size_t)K * N) || e->alloc(dst_f, (size_t)K * N) || e->alloc(bias_f, (size_t)N))) return -1;
         if (up(host, (size_t)K * N)) return -1;
         transpose_to_bf16_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, e->stream>>>(cur_src, K, N, *dst);
-        fold_ln_weights_kernel<<<N, 256, 0, e->stream>>>(cur_src, K, N, gamma, beta, bias, *dst_f, *bias_f);
+        if (do_fold) fold_ln_weights_kernel<<<N, 256, 0, e->stream>>>(cur_src, K, N, gamma, beta, bias, *dst_f, *bias_f);
         if (!dev_src) LMRL_CUDA(cudaStreamSynchronize(e->stream));      // the staging buffer is reused by the next matrix
         return 0;
     };
@@ -1016,6 +1022,7 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     LMRL_CUDA(cudaStreamSynchronize(e->stream));
     LMRL_CUDA(cudaGetLastError());
     G.loaded = true;
+    G.fold_valid = do_fold;
     e->has_gpt2 = true;
     if (tower == 0 && GG.train) return train_refresh_weight_copies(e);      // the backward pass keeps HF-layout copies of tower 0
     return 0;
@@ -1807,7 +1814,7 @@ int lmrl_bench_kernels(lmrl_engine* e, int32_t M, int32_t ctx, int32_t iters, fl
     f.A = G.xn; f.W = L.w_fc; f.bias = L.b_fc; f.N = D.d_ff; f.K = D.d_model; f.M_dev = G.rows.M; f.out = G.h;
     GemmArgs f2{};
     f2.A = G.h; f2.W = L.w_fc2; f2.bias = L.b_fc2; f2.N = D.d_model; f2.K = D.d_ff; f2.M_dev = G.rows.M; f2.resid = G.x;
-    if (G.ln_fold && G.gemm_impl >= 1 && L.w_qkv_f && G.lane[0].stat[0] && D.d_model % TC_BN == 0) {
+    if (G.ln_fold && G.gemm_impl >= 1 && L.w_qkv_f && G.tw[0].fold_valid && G.lane[0].stat[0] && D.d_model % TC_BN == 0) {
         // the LayerNorm-folded launch sequence: residual GEMMs with the bf16 copy + statistics epilogue, consumers scaling by 1 / sigma
         const int parts = 2 * (D.d_model / ((G.narrow_decode_tiles && rpe == 1 && D.d_model == 768) ? 192 : TC_BN));
         a.W = L.w_qkv_f; a.bias = L.b_qkv_f; a.stat_in = G.lane[0].stat[0]; a.stat_n = parts; a.ln_eps = D.ln_eps;

@@ -403,6 +403,15 @@ def test_layernorm_folded_into_the_consumer_gemms_matches_the_oracle(tok):
               f"identical sampled rows {same_tok:.3f}")
         assert worst_f32 <= TOL_F32 and d <= TOL_F32
         assert same_tok >= 0.8
+        # a re-load with the fold off leaves the folded copies stale (a trainer hands weights over every optimizer step and does not pay for
+        # the fold then): using the fold afterwards fails loudly until the weights are loaded again with ln_fold on
+        eng.set_option("ln_fold", 0)
+        pol.set_params(params)
+        eng.set_option("ln_fold", 1)
+        with pytest.raises(Exception, match="stale"):
+            pol.logits(prompts[:4])
+        pol.set_params(params)
+        assert np.array_equal(pol.logits(prompts), got)
         eng.close()
 
 
