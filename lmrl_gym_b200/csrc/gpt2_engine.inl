@@ -66,6 +66,7 @@ struct ValueHeadsDev {
 
 struct TrainDev;                          // train_kernels.inl: buffers of the hand-written backward pass
 struct Gpt2Dev;
+struct VecCopy;
 }  // namespace lmrl
 void lmrl_train_free(lmrl::Gpt2Dev* g);
 static int train_refresh_weight_copies(lmrl_engine* e);
@@ -195,6 +196,7 @@ struct Gpt2Dev {
     // tile everywhere else; 1 = one CTA per tile everywhere; 0 = mma.sync cross-check.  The pair kernel became the default once it
     // got the shared-memory bias staging of the one-CTA epilogue: 2-5 % per prefill GEMM, -1.2 ms per 4096-episode rollout (same box)
     int gemm_impl = 2;
+    VecCopy* vec_tab_dev = nullptr;   // copy table of lmrl_load_gpt2_tower's device-to-device path
     std::map<std::tuple<const void*, size_t, size_t, int>, CUtensorMap> tmaps;   // (base pointer, row bound, columns, box rows | f32 flag) -> descriptor
     std::vector<void*> owned;         // allocations made outside engine::alloc (freed in lmrl_gpt2_free)
 };
@@ -250,6 +252,14 @@ __global__ void xb_stats_kernel(const float* __restrict__ x, int d, const int* _
         for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o); s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o); }
         if (lane == 0) stat[(size_t)r * 8] = make_float2(s1, s2);
     }
+}
+
+// the ~100 small fp32 vectors of a parameter set (LayerNorm scales / offsets, biases) when the source is already on the device (a trainer's
+// weight hand-over after every optimizer step): ONE launch over a table instead of one cudaMemcpyAsync per vector
+struct VecCopy { const float* src; float* dst; int n; int pad; };
+__global__ void batched_vec_copy_kernel(const VecCopy* __restrict__ tab) {
+    const VecCopy c = tab[blockIdx.x];
+    for (int i = threadIdx.x; i < c.n; i += blockDim.x) c.dst[i] = c.src[i];
 }
 
 __global__ void convert_to_bf16_kernel(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
@@ -964,8 +974,11 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         cur_src = stage;
         return 0;
     };
+    const bool do_fold = fresh || GG.ln_fold != 0;
+    std::vector<VecCopy> vec_tab;                                       // device-resident sources: gathered, copied by one kernel at the end
     auto vec = [&](float** dst, const float* host, size_t n) -> int {
         if (fresh && e->alloc(dst, n)) return -1;
+        if (dev_src && !fresh && !do_fold) { vec_tab.push_back(VecCopy{host, *dst, (int)n, 0}); return 0; }   // (the fold kernels read these vectors: no deferral then)
         LMRL_CUDA(cudaMemcpyAsync(*dst, host, n * sizeof(float), cudaMemcpyDefault, e->stream));
         return 0;
     };
@@ -979,7 +992,6 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
     // [K][N] fp32 -> the plain [N][K] bf16 copy AND the LayerNorm-folded copy + folded bias (gamma / beta / bias already on the device).
     // A weight hand-over from a trainer (every optimizer step) refreshes the folded copies only while ln_fold is on; otherwise they are
     // marked stale and the fold stays off for this tower until a load with ln_fold set
-    const bool do_fold = fresh || GG.ln_fold != 0;
     auto mat_t_fold = [&](__nv_bfloat16** dst, __nv_bfloat16** dst_f, float** bias_f, const float* host, int K, int N, const float* gamma,
                           const float* beta, const float* bias) -> int {
         if (fresh && (e->alloc(dst, (size_t)K * N) || e->alloc(dst_f, (size_t)K * N) || e->alloc(bias_f, (size_t)N))) return -1;
@@ -1011,6 +1023,12 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         rc |= vec(&Ld.b_fc, w->fc_b[l], ff);
         if (!rc) rc |= mat_t_fold(&Ld.w_fc, &Ld.w_fc_f, &Ld.b_fc_f, w->fc_w[l], d, ff, Ld.ln2_g, Ld.ln2_b, Ld.b_fc);
         rc |= mat_t(&Ld.w_fc2, w->fc2_w[l], ff, d); rc |= vec(&Ld.b_fc2, w->fc2_b[l], d);
+    }
+    if (!rc && !vec_tab.empty()) {
+        LMRL_CHECK(vec_tab.size() <= 512, "lmrl_load_gpt2: %zu small vectors exceed the copy table", vec_tab.size());
+        if (!GG.vec_tab_dev && e->alloc(&GG.vec_tab_dev, 512)) return -1;
+        LMRL_CUDA(cudaMemcpyAsync(GG.vec_tab_dev, vec_tab.data(), vec_tab.size() * sizeof(VecCopy), cudaMemcpyHostToDevice, e->stream));
+        batched_vec_copy_kernel<<<(unsigned)vec_tab.size(), 256, 0, e->stream>>>(GG.vec_tab_dev);
     }
     cudaStreamSynchronize(e->stream);
     cudaFree(stage);
