@@ -942,7 +942,11 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
                 const size_t eq = kv.find('=');
                 if (eq != std::string::npos) {
                     int* slot = option_slot(*e->gpt2, kv.substr(0, eq).c_str());
-                    LMRL_CHECK(slot, "LMRL_OPTIONS: unknown option '%s'", kv.substr(0, eq).c_str());
+                    if (!slot) {                                          // nothing is loaded yet: leave the engine as it was
+                        delete e->gpt2;
+                        e->gpt2 = nullptr;
+                        return lmrl::fail("LMRL_OPTIONS: unknown option '%s'", kv.substr(0, eq).c_str());
+                    }
                     *slot = atoi(kv.c_str() + eq + 1);
                 }
                 p0 = p1 + 1;

@@ -415,6 +415,26 @@ def test_layernorm_folded_into_the_consumer_gemms_matches_the_oracle(tok):
         eng.close()
 
 
+def test_option_presets_from_the_environment(tok, monkeypatch):
+    """``LMRL_OPTIONS="name=value,..."`` presets the ``lmrl_set_option`` switches of every engine created afterwards (A/B runs of whole
+    scripts); an unknown name fails the load instead of being ignored."""
+    from lmrl_gym_b200.engine import Engine
+    from lmrl_gym_b200.gpt2 import B200GPT2Policy
+    cfg = _small_cfg()
+    params = init_gpt2_params(cfg, seed=2)
+    monkeypatch.setenv("LMRL_OPTIONS", "ln_fold=1,att_decode_impl=0,attn_wide=0")
+    eng = Engine(max_envs=8, max_input_length=32, max_new_tokens=2, tokenizer=tok)
+    pol = B200GPT2Policy(eng, params, cfg)
+    assert (eng.get_option("ln_fold"), eng.get_option("att_decode_impl"), eng.get_option("attn_wide")) == (1, 0, 0)
+    assert np.isfinite(pol.logits([[1, 2, 3], [4, 5]])).all()
+    eng.close()
+    monkeypatch.setenv("LMRL_OPTIONS", "no_such_switch=1")
+    eng = Engine(max_envs=8, max_input_length=32, max_new_tokens=2, tokenizer=tok)
+    with pytest.raises(Exception, match="no_such_switch"):
+        B200GPT2Policy(eng, params, cfg)
+    eng.close()
+
+
 @pytest.mark.parametrize("kind", ["synthetic+nlnl", "gpt2-format-bpe-fixture"])
 def test_fused_rollout_feeds_the_joined_history_encoding(kind):
     """The reference encodes the JOINED history every turn (ppo/gpt2/interface.py:519-522 -> value_rl_base/base_interface.py:111-112).
