@@ -149,3 +149,25 @@ def test_linear_q_head_restatement():
     full = h @ W
     np.testing.assert_allclose(g["q1"], (full + b)[np.arange(4), toks[1:]], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(g["q2"], full[np.arange(4), toks[1:]], rtol=1e-5, atol=1e-5)
+
+
+def test_layernorm_fold_identity_of_the_consumer_gemms():
+    """The algebra behind ``ln_fold`` (csrc/gemm_tcgen05.cuh, fold_ln_weights_kernel): with W''[n][k] = gamma[k] W[k][n] - mean_k(gamma[k] W[k][n])
+    and b'[n] = b[n] + sum_k beta[k] W[k][n], LayerNorm(x) @ W + b == rstd * (x @ W''^T) + b' for the RAW row x — the row mean drops out
+    because every row of W'' sums to zero — and rstd follows from the row's (sum, sum of squares) alone."""
+    rng = np.random.default_rng(0)
+    K, N, M = 96, 40, 7
+    x = (3.0 + 2.0 * rng.standard_normal((M, K))).astype(np.float64)            # non-zero mean on purpose
+    gamma, beta = 1 + 0.2 * rng.standard_normal(K), 0.1 * rng.standard_normal(K)
+    W, b = rng.standard_normal((K, N)) / 8, 0.1 * rng.standard_normal(N)         # HF Conv1D layout [K][N]
+    eps = 1e-5
+    mean, var = x.mean(axis=1, keepdims=True), x.var(axis=1, keepdims=True)
+    ref = ((x - mean) / np.sqrt(var + eps) * gamma + beta) @ W + b
+    gw = gamma[:, None] * W                                                        # [K][N]
+    w_fold = (gw - gw.mean(axis=0, keepdims=True)).T                               # [N][K], rows sum to zero
+    b_fold = b + beta @ W
+    s1, s2 = x.sum(axis=1), (x * x).sum(axis=1)                                    # what the residual epilogue accumulates per row
+    rstd = 1.0 / np.sqrt(np.maximum(s2 / K - (s1 / K) ** 2, 0.0) + eps)
+    got = rstd[:, None] * (x @ w_fold.T) + b_fold
+    assert np.abs(w_fold.sum(axis=1)).max() < 1e-12
+    assert np.abs(got - ref).max() < 1e-10
