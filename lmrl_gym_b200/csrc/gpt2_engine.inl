@@ -1035,7 +1035,7 @@ int lmrl_load_gpt2_tower(lmrl_engine* e, int32_t tower, const lmrl_gpt2_dims* di
         batched_vec_copy_kernel<<<(unsigned)vec_tab.size(), 256, 0, e->stream>>>(GG.vec_tab_dev);
     }
     cudaStreamSynchronize(e->stream);
-    cudaFree(stage);
+    if (stage) cudaFree(stage);
     if (rc) return -1;
     if (first && gpt2_alloc_state(e)) return -1;
     // tower 2 is only ever run by the self-contained per-position forward (kv_len = 0 on entry): it borrows tower 1's slab
@@ -1335,8 +1335,10 @@ int lmrl_load_value_heads(lmrl_engine* e, int32_t head_set, const lmrl_value_hea
     }
     int n_out_max = 1;
     for (int k = 0; k < 2; ++k) if (mlp[k]) n_out_max = std::max(n_out_max, mlp[k]->n_out);
+    // staging buffer of the fp32 kernels — only when there is an MLP / Q head to transpose: a PPO LinearHead hand-over (every optimizer
+    // step) must not pay a cudaMalloc + cudaFree, which synchronise the device and, with peer access enabled by NCCL, cost 1-13 ms
     float* stage = nullptr;
-    LMRL_CUDA(cudaMalloc(&stage, (size_t)d * std::max(n_out_max, d) * sizeof(float)));
+    if (mlp[0] || mlp[1] || mlp[2]) LMRL_CUDA(cudaMalloc(&stage, (size_t)d * std::max(n_out_max, d) * sizeof(float)));
     H.n_mlp = 0; H.hidden = d; H.slot_q1 = H.slot_q2 = H.slot_v = -1; H.has_lin = false; H.q_lin[0] = H.q_lin[1] = false;
     for (int k = 0; k < 3; ++k) {
         const lmrl_mlp_head* q = mlp[k];
@@ -1371,7 +1373,7 @@ int lmrl_load_value_heads(lmrl_engine* e, int32_t head_set, const lmrl_value_hea
         H.has_lin = true;
         LMRL_CUDA(cudaStreamSynchronize(e->stream));
     }
-    cudaFree(stage);
+    if (stage) cudaFree(stage);
     LMRL_CUDA(cudaGetLastError());
     return 0;
 }
